@@ -1,0 +1,217 @@
+/* soupgpu.h — C ABI of libsoupgpu, the B200-native (sm_100a) replacement for the
+ * genotype-clustering hot path of wheaton5/souporcell.
+ *
+ * The reference has no FFI: its boundary is the `souporcell` process
+ * (/root/reference/souporcell/src/main.rs, "S:" below; argv contract in
+ * souporcell/src/params.yml).  Each entry point here names the reference function
+ * it replaces so a Rust `-sys` crate can bind it 1:1.
+ *
+ * Conventions: every function returns int32_t status (SOUP_OK = 0, < 0 = error);
+ * soup_last_error() gives the message.  No C++ exceptions cross the boundary.
+ * The caller owns every host buffer; the library owns device memory behind the
+ * opaque soup_ctx.  A ctx is single-threaded; distinct ctxs may be used from
+ * distinct threads.  There is NO CPU fallback: device entry points fail with
+ * SOUP_ERR_CUDA when no sm_100 GPU is usable.
+ */
+#ifndef SOUPGPU_H
+#define SOUPGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOUP_OK 0
+#define SOUP_ERR_INVALID (-1)     /* bad argument / malformed input (reference: panic!/assert!) */
+#define SOUP_ERR_CUDA (-2)        /* CUDA runtime failure or no usable GPU */
+#define SOUP_ERR_IO (-3)          /* cannot open / read a file */
+#define SOUP_ERR_UNSUPPORTED (-4) /* valid in the reference but outside this build's limits */
+#define SOUP_ERR_NOMEM (-5)
+
+#define SOUP_METHOD_EM 0  /* S:189-278 */
+#define SOUP_METHOD_KHM 1 /* S:280-358 */
+
+typedef struct soup_ctx soup_ctx;
+
+int32_t soup_version(void); /* 3000 = "souporcell 3.0" contract */
+/* message of the last failure on `ctx` (or, with ctx == NULL, of the last failing
+ * call on this thread that had no ctx).  Valid until the next call. */
+const char* soup_last_error(const soup_ctx* ctx);
+
+/* ------------------------------------------------------------------ host side (no GPU needed) */
+
+/* Loader: replaces load_cell_data S:601-681 (parse both .mtx, per-locus tallies, the
+ * min_ref/min_alt/min_*_umis filter S:659, dense re-index S:648-675, per-cell ascending-
+ * locus vectors).  Output is a CSR over cells (columns = used-locus index, ascending),
+ * entries with ref+alt == 0 dropped (S:664), duplicates resolved last-wins (S:633-634). */
+typedef struct soup_mtx {
+    uint64_t n_cells;          /* header column count (S:638) */
+    uint64_t n_loci_total;     /* header row count (S:637) */
+    uint64_t n_loci;           /* loci passing the filter = "total loci used" (S:678) */
+    uint64_t nnz;              /* stored entries after filter */
+    uint64_t* row_ptr;         /* [n_cells + 1] */
+    uint32_t* locus;           /* [nnz] used-locus index */
+    uint32_t* alt;             /* [nnz] */
+    uint32_t* ref;             /* [nnz] */
+    uint64_t* index_to_locus;  /* [n_loci] original 0-based locus id (S:649,661) */
+    int32_t pinned;            /* buffers are cudaHostAlloc'ed */
+} soup_mtx;
+#define SOUP_MTX_PINNED 1 /* allocate the CSR in page-locked memory (needs a CUDA driver) */
+int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uint32_t min_alt, uint32_t min_ref,
+                      uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags, soup_mtx** out);
+void soup_mtx_free(soup_mtx* m);
+
+/* load_barcodes S:707-718 (+ reader S:500-511: ".gz" via zlib).  Returns one malloc'ed
+ * buffer of NUL-separated barcodes; free with soup_free(). */
+int32_t soup_barcodes_load(const char* path, char** blob, uint64_t* n_barcodes);
+void soup_free(void* p);
+
+/* rand 0.9.3 StdRng (= rand_chacha 0.9.0 ChaCha12, key = seed, 64-bit counter from 0):
+ * `n` consecutive u32 words starting at absolute word `word_offset` (S:52,62,559,858). */
+int32_t soup_chacha_words(const uint8_t seed[32], int32_t rounds, uint64_t word_offset, uint32_t* out, uint64_t n);
+/* new_seed S:855-861 applied as souporcell_main does (S:61-62, 77-80): the 32-byte seeds of
+ * the `threads` ThreadData of run `run` (0..2) for CLI seed `seed`.  out[threads][32]. */
+int32_t soup_thread_seeds(uint8_t seed, uint32_t threads, uint32_t run, uint8_t* out);
+/* Rust `{}` (width8 = 0) / `{:8}` (width8 = 1) formatting of an f32 (S:144, S:264). */
+int32_t soup_format_f32(float v, int32_t width8, char* buf, int32_t buflen);
+/* statrs 0.11.0 ln_binomial as used at S:669-670, already cast to f32. */
+float soup_ln_binomial_f32(uint32_t n, uint32_t k);
+/* bad_cluster_detection S:150-187.  best_log_probs [n_cells][k]; out_idx holds up to k
+ * indices; returns the count (>= 0) or an error (< 0).  Writes the "Cluster Analysis" table
+ * to `log_fd`'s FILE if log != NULL (a `FILE*`). */
+int32_t soup_bad_cluster_detection(int32_t run, int32_t k, const float* best_log_probs, uint64_t n_cells,
+                                   int32_t* out_idx, void* log_file);
+
+/* ------------------------------------------------------------------ device side */
+
+/* `cuda_stream` may be NULL (the ctx creates its own) or a cudaStream_t to enqueue on. */
+int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx** out);
+void soup_ctx_destroy(soup_ctx* ctx);
+
+/* Upload the filtered CSR (host pointers; what load_cell_data returns as Vec<CellData>,
+ * S:663-674) and build on the GPU: packed 8-byte entries, the CSC transpose (cells
+ * ascending inside a locus = the order update_centers_average S:476-483 accumulates in),
+ * per-cell total_alleles (S:671, f32, ascending locus) and the ln_binomial table (S:669). */
+int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loci, uint64_t nnz, const uint64_t* row_ptr,
+                      const uint32_t* locus, const uint32_t* alt, const uint32_t* ref);
+int32_t soup_get_dims(soup_ctx* ctx, uint64_t* n_cells, uint64_t* n_loci, uint64_t* nnz /* after dropping ref+alt == 0 */);
+/* Test/inspection hooks: copy the device-built structures back (any pointer may be NULL). */
+int32_t soup_get_csc(soup_ctx* ctx, uint64_t* col_ptr /*[L+1]*/, uint32_t* cell /*[nnz]*/, uint32_t* alt,
+                     uint32_t* ref);
+int32_t soup_get_cell_totals(soup_ctx* ctx, float* total_alleles /*[N]*/);
+int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc /*[nnz]: log_binomial_coefficient per stored entry, S:669*/);
+
+typedef struct soup_solve_params {
+    int32_t k;                 /* num_clusters (S:726) */
+    int32_t method;            /* SOUP_METHOD_EM | SOUP_METHOD_KHM (S:101-108) */
+    int32_t n_streams;         /* `threads`: number of seed streams / ThreadData (S:77-80) */
+    int32_t solves_per_stream; /* solves_per_thread (S:63); total solves = n_streams * this */
+    const uint8_t* stream_seeds; /* [n_streams][32]: ThreadData rng seeds; used when theta0 == NULL */
+    const float* theta0;       /* optional host [n_solves][k][L] initial centers, solve = stream*sps + iter */
+    const float* base_theta;   /* optional host [k][L]: best_cluster_centers of the previous run (S:93) */
+    const int32_t* reinit_clusters; /* bad clusters re-drawn this run (S:92-96); the rest are locked (S:97) */
+    int32_t n_reinit;          /* 0 = run 0: draw all k, lock nothing */
+    int32_t iteration_cap;     /* 0 -> 1000 (S:222) */
+    int32_t max_slots;         /* solves resident on the GPU at once; 0 = auto */
+    int32_t lanes;             /* columns per lane (1, 2, 4); 0 = auto */
+    int32_t record_counts;     /* also record clusters-with->200-cells per iteration (S:252-263) */
+    int32_t keep_trace;        /* copy the per-iteration trace back (soup_get_trace) */
+    int32_t poll_chunk;        /* iterations enqueued between host polls of the done counter; 0 = 4 */
+    /* multi-GPU restart sharding: this process runs solves with (solve % world) == rank */
+    int32_t shard_rank, shard_world; /* world 0 or 1 = no sharding */
+} soup_solve_params;
+
+typedef struct soup_solve_result {
+    int32_t has_best;      /* 0 if no solve beat -inf (reference prints an empty TSV) */
+    int32_t best_solve;    /* index stream*sps + iteration of the winner (ties: lowest, S:110,120) */
+    float best_loss;       /* best_log_probability (S:65,121) */
+    float* best_log_probs; /* optional host [n_cells][k]  (S:122) */
+    float* best_theta;     /* optional host [k][n_loci]   (S:123), after the winner's last M-step */
+    float* solve_loss;     /* optional host [n_solves]; NaN for solves of other shards */
+    int32_t* solve_iters;  /* optional host [n_solves] */
+    uint64_t nnz_updates;  /* nnz * sum(iterations) over the solves this call ran */
+} soup_solve_result;
+
+/* Runs every solve of one `run` of souporcell_main (S:77-125): init (S:485-498, 554-563),
+ * em()/khm() to convergence with all control flow on the device, best-of selection. */
+int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_solve_result* r);
+
+/* per-iteration stderr trace of one solve (S:264 / S:354) from the last soup_solve */
+typedef struct soup_iter_record {
+    int32_t temp_step;
+    float loss;    /* log_binom_loss */
+    float change;  /* log_loss_change */
+    int32_t clusters_above_threshold; /* -1 unless record_counts */
+} soup_iter_record;
+int32_t soup_get_trace(soup_ctx* ctx, int32_t solve, soup_iter_record* out, int32_t cap, int32_t* n);
+
+typedef struct soup_stats {
+    uint64_t kernel_launches;   /* kernels launched by the last soup_solve / hook call */
+    uint64_t estep_launches, mstep_launches;
+    double solve_ms;            /* CUDA-event duration of the whole solve loop */
+    uint64_t slot_iterations;   /* sum over launches of active solves (= sum of iterations) */
+    int32_t slots, lanes, groups, padded_cols;
+    uint64_t h2d_bytes, d2h_bytes; /* copies made by the last load / solve call */
+} soup_stats;
+int32_t soup_get_stats(soup_ctx* ctx, soup_stats* out);
+
+/* Fine-grained parity hooks: one E pass (binomial_loss_with_min_index S:409-426, log_sum_exp
+ * S:428-432, normalize_in_log_with_temp S:443-454, KHM q S:360-384) and one M pass
+ * (update_centers_average S:476-483 + update_final_with_lock S:386-396) for `n_slots`
+ * independent center sets at once.  All pointers are host memory. */
+int32_t soup_estep(soup_ctx* ctx, int32_t k, int32_t method, int32_t n_slots, int32_t lanes,
+                   const float* theta /*[n_slots][k][L]*/, const int32_t* temp_step /*[n_slots]*/,
+                   float* log_probs /*[n_slots][N][k]*/, float* weights /*[n_slots][N][k]*/,
+                   float* lse /*[n_slots][N]*/, float* loss /*[n_slots]*/, int32_t* cells_per_cluster /*[n_slots][k]*/);
+int32_t soup_mstep(soup_ctx* ctx, int32_t k, int32_t n_slots, int32_t lanes, const float* weights /*[n_slots][N][k]*/,
+                   const float* theta_in /*[n_slots][k][L]: kept for locked clusters*/,
+                   const int32_t* locked, int32_t n_locked, float* theta_out /*[n_slots][k][L]*/);
+
+/* Device math self-test hook: applies the on-device ln / exp used by the kernels to n
+ * host floats (parity check against the host libm the oracle uses). op 0 = ln, 1 = exp. */
+int32_t soup_device_math(soup_ctx* ctx, int32_t op, const float* in, float* out, uint64_t n);
+
+/* ------------------------------------------------------------------ driver */
+
+/* souporcell_main S:60-131 on top of soup_solve: seeds (S:61-63,77-80), up to 3 souporcell3
+ * runs (S:70-76,127-129), bad-cluster detection and locking (S:72,92-97), global best-of
+ * (S:119-125).  Restarts are independent (S:81-118), so they shard with no data-path
+ * collective: solve s runs on shard (s mod world).  Inside one process the shards are the
+ * `n_ctx` contexts (one per GPU, each holding the same matrix); across processes (one rank per
+ * GPU, e.g. torchrun / MPI) the caller supplies two host-memory exchange callbacks that are
+ * used once per run to agree on the winner (a few bytes all-gathered) and to fetch its
+ * log-probabilities and centers from the owning rank.  `log_file` is a FILE* or NULL. */
+typedef int32_t (*soup_allgather_fn)(void* user, const void* send, void* recv, uint64_t bytes_per_rank);
+typedef int32_t (*soup_bcast_fn)(void* user, void* buf, uint64_t bytes, int32_t root);
+typedef struct soup_main_params {
+    int32_t k, method;
+    uint32_t restarts, threads;
+    uint8_t seed;
+    int32_t souporcell3;
+    int32_t iteration_cap; /* 0 -> 1000 */
+    int32_t max_slots, lanes, record_counts, verbose_trace;
+    int32_t proc_rank, proc_world;   /* process-level shard; world 0/1 = single process */
+    soup_allgather_fn allgather;     /* required when proc_world > 1 */
+    soup_bcast_fn bcast;
+    void* comm_user;
+} soup_main_params;
+typedef struct soup_main_result {
+    int32_t has_best, runs;
+    float best_loss;
+    float* best_log_probs; /* host [n_cells][k], caller-allocated */
+    float* best_theta;     /* host [k][n_loci], caller-allocated, may be NULL */
+    uint64_t nnz_updates;  /* over the solves this process ran */
+    uint64_t kernel_launches;
+    double solve_ms;       /* sum over runs of the slowest context's device time */
+} soup_main_result;
+int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_main_params* p, soup_main_result* r, void* log_file);
+
+/* TSV writer S:133-147 into `out_file` (a FILE*): barcode, FIRST-max cluster, k log-probs. */
+int32_t soup_write_clusters(void* out_file, const char* barcode_blob, uint64_t n_barcodes,
+                            const float* best_log_probs, uint64_t n_cells, int32_t k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOUPGPU_H */

@@ -1,0 +1,9 @@
+"""souporcell_b200 — B200-native (sm_100a) replacement for the genotype-clustering hot path of
+wheaton5/souporcell (the EM / k-harmonic-means loop of the `souporcell` Rust binary).
+
+The product is `lib/libsoupgpu.so` (C ABI, include/soupgpu.h) and `bin/souporcell` (drop-in CLI);
+this package is the thin ctypes host mirror used by the tests and the benchmark."""
+from .api import (  # noqa: F401
+    METHOD_EM, METHOD_KHM, CellCSR, Context, MainResult, SolveResult, SoupError, bad_cluster_detection, chacha_words,
+    format_f32, lib, ln_binomial_f32, load_barcodes, load_mtx, main, thread_seeds, write_clusters,
+)

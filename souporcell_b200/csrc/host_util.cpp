@@ -1,0 +1,226 @@
+// Host-side pieces of libsoupgpu that need no GPU: RNG streams, Rust-compatible number
+// formatting, the ln_binomial table, barcodes, the TSV writer, souporcell3 outlier logic.
+// Reference: /root/reference/souporcell/src/main.rs ("S:").
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <mutex>
+#include <zlib.h>
+
+#include "soup_common.hpp"
+
+namespace soup {
+
+static thread_local std::string g_thread_error;
+
+std::string vformat(const char* fmt, va_list ap) {
+    char buf[1024];
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    return std::string(buf);
+}
+void set_thread_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    g_thread_error = vformat(fmt, ap);
+    va_end(ap);
+}
+const char* thread_error() { return g_thread_error.c_str(); }
+
+// statrs 0.11.0 function::factorial — FCACHE[i] = FCACHE[i-1] * i for i <= 170, ln_factorial =
+// ln(FCACHE[x]) (x <= 170) else ln_gamma(x + 1); ln_binomial(n, k) = lf(n) - lf(k) - lf(n - k).
+// For n > 170 statrs uses its own Lanczos ln_gamma; libm lgamma stands in (differences are
+// below f32 resolution except at rounding ties — documented in DESIGN.md).
+static double ln_factorial(uint64_t x) {
+    static double cache[171];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cache[0] = 1.0;
+        for (int i = 1; i <= 170; ++i) cache[i] = cache[i - 1] * (double)i;
+    });
+    return x <= 170 ? std::log(cache[x]) : std::lgamma((double)x + 1.0);
+}
+float ln_binomial_f32(uint32_t n, uint32_t k) {
+    if (k > n) return -INFINITY;
+    return (float)(ln_factorial(n) - ln_factorial(k) - ln_factorial((uint64_t)n - k));
+}
+
+// Rust's Display for f32: shortest digits that round-trip, positional notation, no exponent.
+std::string format_f32(float v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    if (v == 0.0f) return std::signbit(v) ? "-0" : "0";
+    char buf[48];
+    auto res = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
+    const char* p = buf;
+    std::string out;
+    if (*p == '-') { out.push_back('-'); ++p; }
+    std::string digits;
+    const char* e = p;
+    while (e < res.ptr && *e != 'e') { if (*e != '.') digits.push_back(*e); ++e; }
+    int exp10 = atoi(e + 1);
+    int nd = (int)digits.size();
+    if (exp10 >= 0) {
+        if (nd <= exp10 + 1) { out += digits; out.append((size_t)(exp10 + 1 - nd), '0'); }
+        else { out.append(digits, 0, (size_t)exp10 + 1); out.push_back('.'); out.append(digits, (size_t)exp10 + 1, std::string::npos); }
+    } else {
+        out += "0.";
+        out.append((size_t)(-exp10 - 1), '0');
+        out += digits;
+    }
+    return out;
+}
+std::string format_f32_w8(float v) {
+    std::string s = format_f32(v);
+    if (s.size() < 8) s.insert(0, 8 - s.size(), ' ');
+    return s;
+}
+
+}  // namespace soup
+
+using namespace soup;
+
+extern "C" {
+
+int32_t soup_version(void) { return 3000; }
+void soup_free(void* p) { free(p); }
+
+int32_t soup_chacha_words(const uint8_t seed[32], int32_t rounds, uint64_t word_offset, uint32_t* out, uint64_t n) {
+    if (!seed || !out || (rounds != 8 && rounds != 12 && rounds != 20)) { set_thread_error("soup_chacha_words: bad argument"); return SOUP_ERR_INVALID; }
+    uint32_t key[8], buf[16];
+    seed_to_key(seed, key);
+    uint64_t blk = word_offset / 16;
+    int idx = (int)(word_offset % 16);
+    chacha_block(key, blk++, rounds, buf);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (idx == 16) { chacha_block(key, blk++, rounds, buf); idx = 0; }
+        out[i] = buf[idx++];
+    }
+    return SOUP_OK;
+}
+
+int32_t soup_thread_seeds(uint8_t seed, uint32_t threads, uint32_t run, uint8_t* out) {
+    if (!out || run > 2) { set_thread_error("soup_thread_seeds: bad argument"); return SOUP_ERR_INVALID; }
+    uint8_t s[32];
+    memset(s, seed, 32);                                   // S:61
+    StdRng rng = StdRng::from_seed(s);                     // S:62
+    for (uint32_t r = 0; r <= run; ++r)                    // each run draws a fresh set (S:77-80)
+        for (uint32_t t = 0; t < threads; ++t)
+            for (int i = 0; i < 32; ++i) {                 // new_seed S:855-861
+                uint8_t b = rng.gen_u8();
+                if (r == run) out[(size_t)t * 32 + i] = b;
+            }
+    return SOUP_OK;
+}
+
+int32_t soup_format_f32(float v, int32_t width8, char* buf, int32_t buflen) {
+    std::string s = width8 ? format_f32_w8(v) : format_f32(v);
+    if (!buf || (int32_t)s.size() + 1 > buflen) { set_thread_error("soup_format_f32: buffer too small"); return SOUP_ERR_INVALID; }
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return (int32_t)s.size();
+}
+
+float soup_ln_binomial_f32(uint32_t n, uint32_t k) { return ln_binomial_f32(n, k); }
+
+// load_barcodes S:707-718 / reader S:500-511
+int32_t soup_barcodes_load(const char* path, char** blob, uint64_t* n_barcodes) {
+    if (!path || !blob || !n_barcodes) { set_thread_error("soup_barcodes_load: bad argument"); return SOUP_ERR_INVALID; }
+    std::string content;
+    size_t plen = strlen(path);
+    if (plen >= 3 && !strcmp(path + plen - 3, ".gz")) {
+        gzFile f = gzopen(path, "rb");
+        if (!f) { set_thread_error("couldn't open file %s", path); return SOUP_ERR_IO; }
+        char buf[1 << 16];
+        int n;
+        while ((n = gzread(f, buf, sizeof(buf))) > 0) content.append(buf, (size_t)n);
+        gzclose(f);
+    } else {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) { set_thread_error("couldn't open file %s", path); return SOUP_ERR_IO; }
+        content.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    }
+    std::string packed;
+    uint64_t n = 0;
+    size_t i = 0;
+    while (i < content.size()) {   // BufRead::lines(): split on '\n', strip one trailing '\r'
+        size_t j = content.find('\n', i);
+        if (j == std::string::npos) j = content.size();
+        size_t e = j;
+        if (e > i && content[e - 1] == '\r') --e;
+        packed.append(content, i, e - i);
+        packed.push_back('\0');
+        ++n;
+        i = j + 1;
+    }
+    char* out = (char*)malloc(packed.size() + 1);
+    if (!out) { set_thread_error("out of memory"); return SOUP_ERR_NOMEM; }
+    memcpy(out, packed.data(), packed.size());
+    out[packed.size()] = 0;
+    *blob = out;
+    *n_barcodes = n;
+    return SOUP_OK;
+}
+
+// S:133-147: zip(barcodes, best_log_probabilities), FIRST max (strict >), Rust {} floats.
+int32_t soup_write_clusters(void* out_file, const char* barcode_blob, uint64_t n_barcodes, const float* lp,
+                            uint64_t n_cells, int32_t k) {
+    FILE* out = (FILE*)out_file;
+    if (!out || (!barcode_blob && n_barcodes) || (!lp && n_cells) || k <= 0) { set_thread_error("soup_write_clusters: bad argument"); return SOUP_ERR_INVALID; }
+    uint64_t n = std::min(n_barcodes, n_cells);
+    const char* bc = barcode_blob;
+    std::string line;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* row = lp + i * (uint64_t)k;
+        int best = 0;
+        float best_lp = -INFINITY;
+        for (int c = 0; c < k; ++c)
+            if (row[c] > best_lp) { best = c; best_lp = row[c]; }
+        line.assign(bc);
+        bc += strlen(bc) + 1;
+        line.push_back('\t');
+        line += std::to_string(best);
+        line.push_back('\t');
+        for (int c = 0; c < k; ++c) {
+            line += format_f32(row[c]);
+            if (c < k - 1) line.push_back('\t');
+        }
+        line.push_back('\n');
+        if (fwrite(line.data(), 1, line.size(), out) != line.size()) { set_thread_error("write failed"); return SOUP_ERR_IO; }
+    }
+    return SOUP_OK;
+}
+
+// S:150-187
+int32_t soup_bad_cluster_detection(int32_t run, int32_t k, const float* best_lp, uint64_t n_cells, int32_t* out_idx,
+                                   void* log_file) {
+    FILE* log = (FILE*)log_file;
+    if (k <= 0 || run < 0 || !out_idx) { set_thread_error("soup_bad_cluster_detection: bad argument"); return SOUP_ERR_INVALID; }
+    if (k < 16 || run == 0) return 0;
+    std::vector<std::pair<int32_t, uint64_t>> assigned((size_t)k);
+    for (int32_t c = 0; c < k; ++c) assigned[(size_t)c] = {c, 0};
+    for (uint64_t i = 0; i < n_cells; ++i) {             // max_by(total_cmp) = LAST maximum (S:159)
+        const float* row = best_lp + i * (uint64_t)k;
+        int32_t best = 0;
+        for (int32_t c = 1; c < k; ++c)
+            if (total_key(row[c]) >= total_key(row[best])) best = c;
+        assigned[(size_t)best].second += 1;
+    }
+    std::stable_sort(assigned.begin(), assigned.end(),
+                     [](const std::pair<int32_t, uint64_t>& a, const std::pair<int32_t, uint64_t>& b) { return a.second < b.second; });
+    size_t run_value = (size_t)(3 - run);
+    size_t low = run_value * ((size_t)k / 16), high = (16 - run_value) * ((size_t)k / 16);
+    int32_t n_out = 0;
+    if (log) fprintf(log, "Cluster Analysis\n");
+    for (size_t index = 0; index < assigned.size(); ++index) {
+        int32_t cluster = assigned[index].first;
+        bool outlier = index < low || index > high;
+        if (log) fprintf(log, "%zu:\tcluster\t%d\tloss\t%llu%s\n", index, cluster, (unsigned long long)assigned[index].second, outlier ? " outlier" : "");
+        if (outlier && std::find(out_idx, out_idx + n_out, cluster) == out_idx + n_out) out_idx[n_out++] = cluster;
+    }
+    return n_out;
+}
+
+}  // extern "C"

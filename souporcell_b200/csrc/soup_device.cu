@@ -1,0 +1,827 @@
+// libsoupgpu device side: context, CSR upload + on-GPU CSC transpose, the resident-slot EM/KHM
+// engine (soup_solve) and the fine-grained parity hooks.  sm_100a only; there is no CPU fallback.
+// Reference: /root/reference/souporcell/src/main.rs ("S:").
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "soup_kernels.cuh"
+
+using namespace soup;
+
+namespace soup {
+void* pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pinned_free(void* p) { if (p) cudaFreeHost(p); }
+}  // namespace soup
+
+// ------------------------------------------------------------------ workspace of one (K, slots, V) shape
+struct Workspace {
+    int K = 0, slots = 0, V = 0, GW = 0, n_groups = 0, iter_cap = 0, queue_cap = 0;
+    uint32_t Cpad = 0;
+    float *LA = nullptr, *LB = nullptr, *TH = nullptr, *ELL = nullptr, *W = nullptr, *LSE = nullptr;
+    SlotState* st = nullptr;
+    Ctl* ctl = nullptr;
+    uint8_t *col_write = nullptr, *k_locked = nullptr;
+    int *group_active = nullptr, *counts = nullptr, *queue = nullptr, *draw_of_k = nullptr, *solve_iters = nullptr;
+    float *solve_loss = nullptr, *best_lp = nullptr, *best_theta = nullptr;
+    IterRec* trace = nullptr;
+    uint32_t* stream_keys = nullptr;
+    int n_streams_cap = 0;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+};
+
+struct soup_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int sm_count = 0;
+    // matrix
+    uint64_t N = 0, L = 0, nnz = 0;
+    uint64_t *d_row_ptr = nullptr, *d_col_ptr = nullptr;
+    uint4 *d_csr = nullptr, *d_csc = nullptr;
+    uint32_t *d_cell_order = nullptr, *d_locus_order = nullptr;
+    float* d_total_alleles = nullptr;
+    bool loaded = false;
+    Workspace ws;
+    // pinned staging for the polling loop
+    Ctl* h_ctl = nullptr;
+    // last-call bookkeeping
+    soup_stats stats{};
+    std::vector<IterRec> h_trace;
+    std::vector<int> h_trace_solve, h_trace_iters;
+    int h_trace_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
+
+    int32_t fail(int32_t code, const char* fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        err = vformat(fmt, ap);
+        va_end(ap);
+        return code;
+    }
+};
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return ctx->fail(SOUP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static void ws_free(Workspace& w) {
+    for (void* p : w.allocs) cudaFree(p);
+    w = Workspace();
+}
+template <typename T>
+static cudaError_t ws_alloc(Workspace& w, T** p, size_t count, bool zero) {
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e != cudaSuccess) return e;
+    w.allocs.push_back(*p);
+    w.bytes += bytes;
+    if (zero) e = cudaMemset(*p, 0, bytes);
+    return e;
+}
+
+static void free_matrix(soup_ctx* ctx) {
+    cudaFree(ctx->d_row_ptr); cudaFree(ctx->d_col_ptr); cudaFree(ctx->d_csr); cudaFree(ctx->d_csc);
+    cudaFree(ctx->d_cell_order); cudaFree(ctx->d_locus_order); cudaFree(ctx->d_total_alleles);
+    ctx->d_row_ptr = ctx->d_col_ptr = nullptr;
+    ctx->d_csr = ctx->d_csc = nullptr;
+    ctx->d_cell_order = ctx->d_locus_order = nullptr;
+    ctx->d_total_alleles = nullptr;
+    ctx->loaded = false;
+}
+
+extern "C" const char* soup_last_error(const soup_ctx* ctx) { return ctx ? ctx->err.c_str() : thread_error(); }
+
+extern "C" int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx** out) {
+    if (!out) { set_thread_error("soup_ctx_create: bad argument"); return SOUP_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_thread_error("no CUDA device available (%s); libsoupgpu has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return SOUP_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_thread_error("soup_ctx_create: device %d out of range (%d visible)", device, n); return SOUP_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { set_thread_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return SOUP_ERR_CUDA; }
+    if (prop.major != 10) {
+        set_thread_error("device %d is sm_%d%d; libsoupgpu is built for sm_100a (B200) only and has no fallback", device, prop.major, prop.minor);
+        return SOUP_ERR_CUDA;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { set_thread_error("cudaSetDevice: %s", cudaGetErrorString(e)); return SOUP_ERR_CUDA; }
+    soup_ctx* ctx = new soup_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
+    else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            set_thread_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+            delete ctx;
+            return SOUP_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    cudaEventCreateWithFlags(&ctx->ev_poll[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_poll[1], cudaEventDisableTiming);
+    if (cudaHostAlloc((void**)&ctx->h_ctl, sizeof(Ctl) * 4, cudaHostAllocDefault) != cudaSuccess) {
+        set_thread_error("cudaHostAlloc failed");
+        delete ctx;
+        return SOUP_ERR_CUDA;
+    }
+    // statrs FCACHE -> ln(n!) table (S:669-670)
+    double lf[171], f = 1.0;
+    lf[0] = std::log(1.0);
+    for (int i = 1; i <= 170; ++i) { f *= (double)i; lf[i] = std::log(f); }
+    if ((e = cudaMemcpyToSymbol(c_ln_factorial, lf, sizeof(lf))) != cudaSuccess) {
+        set_thread_error("cudaMemcpyToSymbol: %s", cudaGetErrorString(e));
+        delete ctx;
+        return SOUP_ERR_CUDA;
+    }
+    *out = ctx;
+    return SOUP_OK;
+}
+
+extern "C" void soup_ctx_destroy(soup_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ws_free(ctx->ws);
+    free_matrix(ctx);
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->ev_poll) if (e) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ------------------------------------------------------------------ soup_load_csr
+extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loci, uint64_t nnz_in, const uint64_t* row_ptr,
+                                 const uint32_t* locus, const uint32_t* alt, const uint32_t* ref) {
+    if (!ctx) return SOUP_ERR_INVALID;
+    if (!row_ptr || (nnz_in && (!locus || !alt || !ref))) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: null pointer");
+    if (n_cells >= INT32_MAX || n_loci >= INT32_MAX || nnz_in >= INT32_MAX)
+        return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_load_csr: dimensions above 2^31-1 are not supported");
+    if (row_ptr[0] != 0 || row_ptr[n_cells] != nnz_in) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: row_ptr does not span [0, nnz]");
+    CK(cudaSetDevice(ctx->device));
+    ctx->stats = soup_stats{};
+    // validate (loci strictly ascending inside a cell: the order S:663-674 appends in); drop ref+alt == 0 (S:664)
+    bool has_zero = false;
+    std::vector<uint32_t> big_idx;
+    for (uint64_t c = 0; c < n_cells; ++c) {
+        if (row_ptr[c + 1] < row_ptr[c]) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: row_ptr not monotone at cell %llu", (unsigned long long)c);
+        for (uint64_t j = row_ptr[c]; j < row_ptr[c + 1]; ++j) {
+            if (locus[j] >= n_loci) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: locus index out of range at entry %llu", (unsigned long long)j);
+            if (j > row_ptr[c] && locus[j] <= locus[j - 1]) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: loci must be strictly ascending inside a cell (cell %llu)", (unsigned long long)c);
+            if ((uint32_t)(alt[j] + ref[j]) == 0) has_zero = true;
+        }
+    }
+    std::vector<uint64_t> rp2;
+    std::vector<uint32_t> l2, a2, r2;
+    uint64_t nnz = nnz_in;
+    if (has_zero) {
+        rp2.resize(n_cells + 1);
+        l2.reserve(nnz_in); a2.reserve(nnz_in); r2.reserve(nnz_in);
+        for (uint64_t c = 0; c < n_cells; ++c) {
+            rp2[c] = l2.size();
+            for (uint64_t j = row_ptr[c]; j < row_ptr[c + 1]; ++j)
+                if ((uint32_t)(alt[j] + ref[j]) != 0) { l2.push_back(locus[j]); a2.push_back(alt[j]); r2.push_back(ref[j]); }
+        }
+        rp2[n_cells] = l2.size();
+        nnz = l2.size();
+        row_ptr = rp2.data(); locus = l2.data(); alt = a2.data(); ref = r2.data();
+    }
+    std::vector<float> big_val;
+    for (uint64_t j = 0; j < nnz; ++j)
+        if ((uint32_t)(alt[j] + ref[j]) > 170u) { big_idx.push_back((uint32_t)j); big_val.push_back(ln_binomial_f32(alt[j] + ref[j], alt[j])); }
+
+    free_matrix(ctx);
+    ws_free(ctx->ws);
+    ctx->N = n_cells; ctx->L = n_loci; ctx->nnz = nnz;
+    cudaStream_t st = ctx->stream;
+    const size_t nz = std::max<uint64_t>(nnz, 1);
+    uint32_t *d_locus = nullptr, *d_alt = nullptr, *d_ref = nullptr, *d_vals = nullptr, *d_vals2 = nullptr, *d_len = nullptr, *d_len2 = nullptr, *d_idx = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    void* d_tmp = nullptr;
+    auto cleanup = [&] {
+        cudaFree(d_locus); cudaFree(d_alt); cudaFree(d_ref); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_keys); cudaFree(d_keys2);
+        cudaFree(d_len); cudaFree(d_len2); cudaFree(d_idx); cudaFree(d_tmp);
+    };
+#define CKL(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) { cleanup(); free_matrix(ctx); return ctx->fail(e_ == cudaErrorMemoryAllocation ? SOUP_ERR_NOMEM : SOUP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    CKL(cudaMalloc(&ctx->d_row_ptr, (n_cells + 1) * sizeof(uint64_t)));
+    CKL(cudaMalloc(&ctx->d_col_ptr, (n_loci + 1) * sizeof(uint64_t)));
+    CKL(cudaMalloc(&ctx->d_csr, nz * sizeof(uint4)));
+    CKL(cudaMalloc(&ctx->d_csc, nz * sizeof(uint4)));
+    CKL(cudaMalloc(&ctx->d_cell_order, std::max<uint64_t>(n_cells, 1) * sizeof(uint32_t)));
+    CKL(cudaMalloc(&ctx->d_locus_order, std::max<uint64_t>(n_loci, 1) * sizeof(uint32_t)));
+    CKL(cudaMalloc(&ctx->d_total_alleles, std::max<uint64_t>(n_cells, 1) * sizeof(float)));
+    CKL(cudaMalloc(&d_locus, nz * 4)); CKL(cudaMalloc(&d_alt, nz * 4)); CKL(cudaMalloc(&d_ref, nz * 4));
+    CKL(cudaMalloc(&d_vals, nz * 4)); CKL(cudaMalloc(&d_vals2, nz * 4));
+    CKL(cudaMalloc(&d_keys, nz * 8)); CKL(cudaMalloc(&d_keys2, nz * 8));
+    const size_t nmax = std::max<uint64_t>(std::max(n_cells, n_loci), 1);
+    CKL(cudaMalloc(&d_len, nmax * 4)); CKL(cudaMalloc(&d_len2, nmax * 4)); CKL(cudaMalloc(&d_idx, nmax * 4));
+    CKL(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, (n_cells + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CKL(cudaMemcpyAsync(d_locus, locus, nnz * 4, cudaMemcpyHostToDevice, st));
+        CKL(cudaMemcpyAsync(d_alt, alt, nnz * 4, cudaMemcpyHostToDevice, st));
+        CKL(cudaMemcpyAsync(d_ref, ref, nnz * 4, cudaMemcpyHostToDevice, st));
+    }
+    ctx->stats.h2d_bytes = (n_cells + 1) * 8 + nnz * 12;
+    if (n_cells) {
+        build_csr_kernel<<<(unsigned)((n_cells + 7) / 8), 256, 0, st>>>(ctx->d_row_ptr, d_locus, d_alt, d_ref, ctx->d_csr, d_keys, d_vals,
+                                                                        ctx->d_total_alleles, d_len, (uint32_t)n_cells);
+        CKL(cudaGetLastError());
+    }
+    if (!big_idx.empty()) {   // ln_binomial for n > 170 comes from the host (statrs ln_gamma branch)
+        uint32_t* d_bi = nullptr; float* d_bv = nullptr;
+        CKL(cudaMalloc(&d_bi, big_idx.size() * 4));
+        cudaError_t e2 = cudaMalloc(&d_bv, big_val.size() * 4);
+        if (e2 != cudaSuccess) { cudaFree(d_bi); CKL(e2); }
+        cudaMemcpyAsync(d_bi, big_idx.data(), big_idx.size() * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_bv, big_val.data(), big_val.size() * 4, cudaMemcpyHostToDevice, st);
+        patch_lbc_kernel<<<(unsigned)((big_idx.size() + 255) / 256), 256, 0, st>>>(ctx->d_csr, d_bi, d_bv, (uint32_t)big_idx.size());
+        cudaStreamSynchronize(st);
+        cudaFree(d_bi); cudaFree(d_bv);
+        CKL(cudaGetLastError());
+        ctx->stats.h2d_bytes += big_idx.size() * 8;
+    }
+    // CSC transpose: stable radix sort of (locus, cell) keys -> cells ascending inside a locus (S:227 order)
+    int bits_l = 1, bits_total;
+    while ((1ull << bits_l) < std::max<uint64_t>(n_loci, 2)) ++bits_l;
+    bits_total = 32 + bits_l;
+    size_t tmp_bytes = 0, tmp2 = 0;
+    cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys2);
+    cub::DoubleBuffer<uint32_t> vb(d_vals, d_vals2);
+    cub::DoubleBuffer<uint32_t> lb(d_len, d_len2), ib(d_idx, d_vals2);
+    CKL(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)nnz, 0, bits_total, st));
+    CKL(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, lb, ib, (int)nmax, 0, 32, st));
+    tmp_bytes = std::max(tmp_bytes, tmp2);
+    CKL(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    if (nnz) {
+        CKL(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, kb, vb, (int)nnz, 0, bits_total, st));
+        build_csc_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(kb.Current(), vb.Current(), d_alt, d_ref, ctx->d_csc, nnz);
+        CKL(cudaGetLastError());
+    }
+    col_ptr_kernel<<<(unsigned)((n_loci + 1 + 255) / 256), 256, 0, st>>>(kb.Current(), nnz, ctx->d_col_ptr, (uint32_t)n_loci);
+    CKL(cudaGetLastError());
+    // longest-first (LPT) visiting orders for the E and M kernels (ties -> ascending index; stable sort)
+    auto lpt = [&](const uint64_t* ptr, uint32_t n, uint32_t* order) -> cudaError_t {
+        if (n == 0) return cudaSuccess;
+        uint32_t* idx2 = nullptr;
+        cudaError_t e = cudaMalloc(&idx2, (size_t)n * 4);
+        if (e != cudaSuccess) return e;
+        seg_len_kernel<<<(n + 255) / 256, 256, 0, st>>>(ptr, d_len, d_idx, n);
+        cub::DoubleBuffer<uint32_t> k(d_len, d_len2), v(d_idx, idx2);
+        size_t tb = tmp_bytes;
+        e = cub::DeviceRadixSort::SortPairsDescending(d_tmp, tb, k, v, (int)n, 0, 32, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(order, v.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+        cudaStreamSynchronize(st);
+        cudaFree(idx2);
+        return e;
+    };
+    CKL(lpt(ctx->d_row_ptr, (uint32_t)n_cells, ctx->d_cell_order));
+    CKL(lpt(ctx->d_col_ptr, (uint32_t)n_loci, ctx->d_locus_order));
+    CKL(cudaStreamSynchronize(st));
+    CKL(cudaGetLastError());
+    cleanup();
+#undef CKL
+    ctx->stats.kernel_launches = 6;
+    ctx->loaded = true;
+    return SOUP_OK;
+}
+
+extern "C" int32_t soup_get_dims(soup_ctx* ctx, uint64_t* n_cells, uint64_t* n_loci, uint64_t* nnz) {
+    if (!ctx) return SOUP_ERR_INVALID;
+    if (!ctx->loaded) return ctx->fail(SOUP_ERR_INVALID, "no matrix loaded (call soup_load_csr first)");
+    if (n_cells) *n_cells = ctx->N;
+    if (n_loci) *n_loci = ctx->L;
+    if (nnz) *nnz = ctx->nnz;
+    return SOUP_OK;
+}
+extern "C" int32_t soup_get_csc(soup_ctx* ctx, uint64_t* col_ptr, uint32_t* cell, uint32_t* alt, uint32_t* ref) {
+    if (!ctx || !ctx->loaded) return ctx ? ctx->fail(SOUP_ERR_INVALID, "no matrix loaded") : SOUP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (col_ptr) CK(cudaMemcpy(col_ptr, ctx->d_col_ptr, (ctx->L + 1) * 8, cudaMemcpyDeviceToHost));
+    if (cell || alt || ref) {
+        std::vector<uint4> h(ctx->nnz);
+        if (ctx->nnz) CK(cudaMemcpy(h.data(), ctx->d_csc, ctx->nnz * sizeof(uint4), cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < ctx->nnz; ++i) {
+            float a, t;
+            memcpy(&a, &h[i].y, 4); memcpy(&t, &h[i].z, 4);
+            if (cell) cell[i] = h[i].x;
+            if (alt) alt[i] = (uint32_t)a;
+            if (ref) ref[i] = (uint32_t)t - (uint32_t)a;
+        }
+    }
+    return SOUP_OK;
+}
+extern "C" int32_t soup_get_cell_totals(soup_ctx* ctx, float* total_alleles) {
+    if (!ctx || !ctx->loaded || !total_alleles) return ctx ? ctx->fail(SOUP_ERR_INVALID, "no matrix loaded") : SOUP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->N) CK(cudaMemcpy(total_alleles, ctx->d_total_alleles, ctx->N * 4, cudaMemcpyDeviceToHost));
+    return SOUP_OK;
+}
+extern "C" int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc) {
+    if (!ctx || !ctx->loaded || !lbc) return ctx ? ctx->fail(SOUP_ERR_INVALID, "no matrix loaded") : SOUP_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint4> h(ctx->nnz);
+    if (ctx->nnz) CK(cudaMemcpy(h.data(), ctx->d_csr, ctx->nnz * sizeof(uint4), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < ctx->nnz; ++i) memcpy(&lbc[i], &h[i].w, 4);
+    return SOUP_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+static int pick_lanes(int cols) {
+    // widest vector (columns per lane) whose padding wastes <= 12.5 % of the lanes
+    for (int V : {4, 2}) {
+        int gw = 32 * V, padded = (cols + gw - 1) / gw * gw;
+        if (padded * 8 <= cols * 9) return V;
+    }
+    return 1;
+}
+
+static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int V, int iter_cap, int queue_cap, int n_streams) {
+    Workspace& w = ctx->ws;
+    if (w.K == K && w.slots == slots && w.V == V && w.iter_cap == iter_cap && w.queue_cap >= queue_cap && w.n_streams_cap >= n_streams) return SOUP_OK;
+    ws_free(w);
+    w.K = K; w.slots = slots; w.V = V; w.GW = 32 * V; w.iter_cap = iter_cap; w.queue_cap = queue_cap; w.n_streams_cap = n_streams;
+    const size_t cols = (size_t)slots * K;
+    w.Cpad = (uint32_t)((cols + w.GW - 1) / w.GW * w.GW);
+    w.n_groups = (int)(w.Cpad / w.GW);
+    const size_t L = std::max<uint64_t>(ctx->L, 1), N = std::max<uint64_t>(ctx->N, 1);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](auto** p, size_t n, bool zero) { if (e == cudaSuccess) e = ws_alloc(w, p, n, zero); };
+    A(&w.LA, L * w.Cpad, true); A(&w.LB, L * w.Cpad, true); A(&w.TH, L * w.Cpad, true);
+    A(&w.ELL, N * w.Cpad, true); A(&w.W, N * w.Cpad, true); A(&w.LSE, N * slots, true);
+    A(&w.st, (size_t)slots, true); A(&w.ctl, 1, true);
+    A(&w.col_write, w.Cpad, true); A(&w.k_locked, (size_t)K, true);
+    A(&w.group_active, (size_t)w.n_groups, true); A(&w.counts, cols, true);
+    A(&w.queue, (size_t)queue_cap, true); A(&w.draw_of_k, (size_t)K, true);
+    A(&w.solve_iters, (size_t)queue_cap, true); A(&w.solve_loss, (size_t)queue_cap, true);
+    A(&w.best_lp, N * K, true); A(&w.best_theta, L * K, true);
+    A(&w.trace, (size_t)queue_cap * iter_cap, true);
+    A(&w.stream_keys, (size_t)std::max(n_streams, 1) * 8, true);
+    if (e != cudaSuccess) {
+        ws_free(w);
+        cudaGetLastError();
+        return ctx->fail(e == cudaErrorMemoryAllocation ? SOUP_ERR_NOMEM : SOUP_ERR_CUDA, "workspace allocation failed: %s", cudaGetErrorString(e));
+    }
+    return SOUP_OK;
+}
+
+static size_t bytes_per_slot(const soup_ctx* ctx, int K) {
+    return (size_t)K * (3 * ctx->L + 2 * ctx->N) * 4 + ctx->N * 4 + 64;
+}
+
+// ------------------------------------------------------------------ one EM/KHM iteration for every resident slot
+struct IterLaunch {
+    soup_ctx* ctx;
+    int method;
+    float log_prior, limit;
+    bool record_counts;
+    RefillArgs refill;
+    FinalizeArgs fin;
+};
+
+template <int V>
+static void launch_e(soup_ctx* ctx, float log_prior) {
+    Workspace& w = ctx->ws;
+    const uint32_t bpg = (uint32_t)((ctx->N + EM_WARPS - 1) / EM_WARPS);
+    if (bpg == 0) return;
+    estep_kernel<V><<<bpg * w.n_groups, EM_THREADS, 0, ctx->stream>>>(ctx->d_csr, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB, w.ELL,
+                                                                      w.group_active, w.ctl, (uint32_t)ctx->N, w.Cpad, bpg, log_prior);
+}
+template <int V>
+static void launch_m(soup_ctx* ctx) {
+    Workspace& w = ctx->ws;
+    const uint32_t bpg = (uint32_t)((ctx->L + EM_WARPS - 1) / EM_WARPS);
+    if (bpg == 0) return;
+    mstep_kernel<V><<<bpg * w.n_groups, EM_THREADS, 0, ctx->stream>>>(ctx->d_csc, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB,
+                                                                      w.col_write, w.group_active, w.ctl, (uint32_t)ctx->L, w.Cpad, bpg);
+}
+static void launch_e(soup_ctx* ctx, float log_prior) {
+    switch (ctx->ws.V) { case 4: launch_e<4>(ctx, log_prior); break; case 2: launch_e<2>(ctx, log_prior); break; default: launch_e<1>(ctx, log_prior); }
+}
+static void launch_m(soup_ctx* ctx) {
+    switch (ctx->ws.V) { case 4: launch_m<4>(ctx); break; case 2: launch_m<2>(ctx); break; default: launch_m<1>(ctx); }
+}
+static void launch_post(soup_ctx* ctx, int method, bool counts) {
+    Workspace& w = ctx->ws;
+    PostArgs a{w.ELL, w.W, w.LSE, ctx->d_total_alleles, w.st, counts ? w.counts : nullptr, (uint32_t)ctx->N, w.Cpad, w.K, w.slots, method};
+    const size_t n = (size_t)ctx->N * w.slots;
+    if (n) post_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
+}
+static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
+    Workspace& w = ctx->ws;
+    const size_t n = (size_t)ctx->L * w.K;
+    if (n) refill_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)w.slots), 256, 0, ctx->stream>>>(a);
+}
+
+static uint64_t launches_per_iteration(const soup_ctx* ctx) { (void)ctx; return 7; }
+
+static void enqueue_iteration(const IterLaunch& it) {
+    soup_ctx* ctx = it.ctx;
+    Workspace& w = ctx->ws;
+    launch_e(ctx, it.log_prior);
+    launch_post(ctx, it.method, it.record_counts);
+    ControlArgs c{w.LSE, w.st, w.ctl, it.record_counts ? w.counts : nullptr, w.trace, w.solve_loss, w.solve_iters,
+                  (uint32_t)ctx->N, w.K, w.slots, w.iter_cap, it.limit};
+    control_kernel<<<1, std::min(1024, (w.slots + 31) / 32 * 32), 0, ctx->stream>>>(c);
+    launch_m(ctx);
+    harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K);
+    launch_refill(ctx, it.refill);
+    finalize_kernel<<<1, 1024, 0, ctx->stream>>>(it.fin);
+}
+
+// ------------------------------------------------------------------ soup_solve
+extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_solve_result* r) {
+    if (!ctx) return SOUP_ERR_INVALID;
+    if (!p || !r) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: null argument");
+    if (!ctx->loaded) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: no matrix loaded (call soup_load_csr first)");
+    if (p->k <= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: k must be >= 1");
+    if (p->method != SOUP_METHOD_EM && p->method != SOUP_METHOD_KHM) return ctx->fail(SOUP_ERR_INVALID, "Clustering method must be one of em, khm");
+    if (p->n_streams <= 0 || p->solves_per_stream <= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: n_streams and solves_per_stream must be >= 1");
+    if (!p->theta0 && !p->stream_seeds) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: need stream_seeds or theta0");
+    if (p->n_reinit < 0 || p->n_reinit > p->k || (p->n_reinit > 0 && (!p->reinit_clusters || !p->base_theta)))
+        return ctx->fail(SOUP_ERR_INVALID, "soup_solve: bad reinit_clusters / base_theta");
+    if ((uint64_t)p->n_streams * (uint64_t)p->solves_per_stream > (1u << 30)) return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: too many solves");
+    CK(cudaSetDevice(ctx->device));
+    const int K = p->k;
+    const int n_solves = p->n_streams * p->solves_per_stream;
+    const int world = p->shard_world > 1 ? p->shard_world : 1, rank = world > 1 ? p->shard_rank : 0;
+    if (rank < 0 || rank >= world) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: shard_rank out of range");
+    const int iter_cap = p->iteration_cap > 0 ? p->iteration_cap : 1000;
+    std::vector<int> queue;
+    for (int s = rank; s < n_solves; s += world) queue.push_back(s);
+    const int n_local = (int)queue.size();
+
+    ctx->stats = soup_stats{};
+    r->has_best = 0; r->best_solve = -1; r->best_loss = -INFINITY; r->nnz_updates = 0;
+    if (r->solve_loss) for (int i = 0; i < n_solves; ++i) r->solve_loss[i] = NAN;
+    if (r->solve_iters) for (int i = 0; i < n_solves; ++i) r->solve_iters[i] = 0;
+    ctx->h_trace.clear(); ctx->h_trace_solve.clear(); ctx->h_trace_iters.clear(); ctx->h_trace_cap = iter_cap;
+
+    const float limit = 0.01f * (float)ctx->N;                 // S:214
+    const float log_prior = logf(1.0f / (float)K);             // S:202 (host libm = the reference's f32::ln)
+    const bool any_iteration = (10000.0f > limit) && iter_cap > 0;
+    if (n_local == 0 || !any_iteration) {
+        // em()/khm() with no iteration returns (-inf, empty): nothing can beat -inf (S:65, S:110)
+        if (r->solve_loss) for (int s : queue) r->solve_loss[s] = -INFINITY;
+        return SOUP_OK;
+    }
+
+    // ---- shape: resident slots and vector width
+    int slots = p->max_slots > 0 ? p->max_slots : std::max(1, 2048 / K);
+    slots = std::min(slots, n_local);
+    {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        free_b += ctx->ws.bytes;
+        size_t fixed = (size_t)K * (ctx->L + ctx->N) * 4 + (size_t)n_local * iter_cap * sizeof(IterRec) + (64u << 20);
+        if (p->theta0) fixed += (size_t)n_solves * K * ctx->L * 4;
+        size_t per = bytes_per_slot(ctx, K);
+        if (free_b < fixed + per) return ctx->fail(SOUP_ERR_NOMEM, "soup_solve: not enough device memory for one resident solve");
+        size_t cap = (size_t)((double)(free_b - fixed) * 0.85 / (double)per);
+        slots = (int)std::min<size_t>((size_t)slots, std::max<size_t>(cap, 1));
+    }
+    slots = std::min(slots, 1024);
+    int V = p->lanes;
+    if (V != 1 && V != 2 && V != 4) V = pick_lanes(slots * K);
+    int32_t rc = ensure_workspace(ctx, K, slots, V, iter_cap, n_local, p->n_streams);
+    if (rc != SOUP_OK) return rc;
+    Workspace& w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+
+    // ---- per-call device inputs
+    float *d_theta0 = nullptr, *d_base = nullptr;
+    auto cleanup = [&] { cudaFree(d_theta0); cudaFree(d_base); };
+#define CKS(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) { cleanup(); return ctx->fail(e_ == cudaErrorMemoryAllocation ? SOUP_ERR_NOMEM : SOUP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    std::vector<int> draw_of_k(K);
+    std::vector<uint8_t> k_locked(K, 0);
+    int n_draw = K;
+    if (p->n_reinit > 0) {   // S:92-97: re-draw the flagged clusters in list order, lock the rest
+        std::fill(draw_of_k.begin(), draw_of_k.end(), -1);
+        std::fill(k_locked.begin(), k_locked.end(), 1);
+        for (int i = 0; i < p->n_reinit; ++i) {
+            int c = p->reinit_clusters[i];
+            if (c < 0 || c >= K || draw_of_k[c] >= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: bad reinit_clusters entry");
+            draw_of_k[c] = i;
+            k_locked[c] = 0;
+        }
+        n_draw = p->n_reinit;
+    } else {
+        for (int k = 0; k < K; ++k) draw_of_k[k] = k;
+    }
+    uint64_t h2d = 0;
+    if (p->theta0) {
+        size_t n = (size_t)n_solves * K * ctx->L;
+        CKS(cudaMalloc(&d_theta0, std::max<size_t>(n, 1) * 4));
+        CKS(cudaMemcpyAsync(d_theta0, p->theta0, n * 4, cudaMemcpyHostToDevice, st));
+        h2d += n * 4;
+    }
+    if (p->base_theta && p->n_reinit > 0) {
+        size_t n = (size_t)K * ctx->L;
+        CKS(cudaMalloc(&d_base, std::max<size_t>(n, 1) * 4));
+        CKS(cudaMemcpyAsync(d_base, p->base_theta, n * 4, cudaMemcpyHostToDevice, st));
+        h2d += n * 4;
+    }
+    std::vector<uint32_t> keys((size_t)p->n_streams * 8, 0);
+    if (p->stream_seeds)
+        for (int t = 0; t < p->n_streams; ++t) seed_to_key(p->stream_seeds + (size_t)t * 32, keys.data() + (size_t)t * 8);
+    CKS(cudaMemcpyAsync(w.stream_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, st));
+    CKS(cudaMemcpyAsync(w.queue, queue.data(), (size_t)n_local * 4, cudaMemcpyHostToDevice, st));
+    CKS(cudaMemcpyAsync(w.draw_of_k, draw_of_k.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    CKS(cudaMemcpyAsync(w.k_locked, k_locked.data(), (size_t)K, cudaMemcpyHostToDevice, st));
+    h2d += keys.size() * 4 + (size_t)n_local * 4 + (size_t)K * 5;
+    // initial slot table: every slot "finished" with its first queue entry pending -> refill + finalize install them
+    std::vector<SlotState> hst(slots);
+    for (int s = 0; s < slots; ++s) {
+        hst[s] = SlotState{};
+        hst[s].solve = -1; hst[s].fin = 1; hst[s].pending = s < n_local ? s : -1;
+        hst[s].last_loss = -INFINITY; hst[s].loss = -INFINITY;
+    }
+    Ctl hc{};
+    hc.queue_head = std::min(slots, n_local); hc.queue_len = n_local; hc.copy_slot = -1; hc.best_solve = -1; hc.best_loss = -INFINITY;
+    CKS(cudaMemcpyAsync(w.st, hst.data(), sizeof(SlotState) * slots, cudaMemcpyHostToDevice, st));
+    CKS(cudaMemcpyAsync(w.ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, st));
+    CKS(cudaMemsetAsync(w.counts, 0, (size_t)slots * K * 4, st));
+
+    IterLaunch it;
+    it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0;
+    it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, w.draw_of_k, w.TH, w.LA, w.LB,
+                           (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream};
+    it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write, w.group_active, K, slots, w.GW, w.n_groups, iter_cap, w.Cpad, limit};
+
+    CKS(cudaEventRecord(ctx->ev0, st));
+    launch_refill(ctx, it.refill);
+    finalize_kernel<<<1, 1024, 0, st>>>(it.fin);
+    CKS(cudaGetLastError());
+    uint64_t launches = 2;
+
+    // ---- iterate: chunk i+1 is enqueued before the host waits for chunk i's done counter, so the
+    // GPU never idles on the poll; kernels of chunks past the end find no active slot and exit.
+    const int chunk = p->poll_chunk > 0 ? p->poll_chunk : 4;
+    uint64_t iters_enqueued = 0;
+    int polls = 0;
+    auto enqueue_chunk = [&](int which) -> cudaError_t {
+        for (int i = 0; i < chunk; ++i) enqueue_iteration(it);
+        iters_enqueued += chunk;
+        launches += (uint64_t)chunk * launches_per_iteration(ctx);
+        cudaError_t e = cudaMemcpyAsync(ctx->h_ctl + which, w.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_poll[which], st);
+        return e;
+    };
+    CKS(enqueue_chunk(0));
+    for (;;) {
+        const int cur = polls & 1;
+        CKS(enqueue_chunk(cur ^ 1));
+        CKS(cudaEventSynchronize(ctx->ev_poll[cur]));
+        ++polls;
+        if (ctx->h_ctl[cur].done_count >= n_local) break;
+        if (iters_enqueued > (uint64_t)n_local * (uint64_t)(iter_cap + TEMP_STEPS) + 64) { cleanup(); return ctx->fail(SOUP_ERR_CUDA, "soup_solve: device control loop did not converge"); }
+    }
+    CKS(cudaEventRecord(ctx->ev1, st));
+    CKS(cudaStreamSynchronize(st));
+    CKS(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+
+    // ---- results
+    Ctl fc;
+    CKS(cudaMemcpy(&fc, w.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    std::vector<float> h_loss(n_local);
+    std::vector<int> h_iters(n_local);
+    CKS(cudaMemcpy(h_loss.data(), w.solve_loss, (size_t)n_local * 4, cudaMemcpyDeviceToHost));
+    CKS(cudaMemcpy(h_iters.data(), w.solve_iters, (size_t)n_local * 4, cudaMemcpyDeviceToHost));
+    uint64_t d2h = sizeof(Ctl) * (polls + 1) + (size_t)n_local * 8;
+    uint64_t total_iters = 0;
+    for (int i = 0; i < n_local; ++i) {
+        total_iters += (uint64_t)h_iters[i];
+        if (r->solve_loss) r->solve_loss[queue[i]] = h_loss[i];
+        if (r->solve_iters) r->solve_iters[queue[i]] = h_iters[i];
+    }
+    r->has_best = fc.has_best;
+    r->best_solve = fc.best_solve;
+    r->best_loss = fc.best_loss;
+    r->nnz_updates = ctx->nnz * total_iters;
+    if (fc.has_best) {
+        if (r->best_log_probs) { CKS(cudaMemcpy(r->best_log_probs, w.best_lp, (size_t)ctx->N * K * 4, cudaMemcpyDeviceToHost)); d2h += (size_t)ctx->N * K * 4; }
+        if (r->best_theta) { CKS(cudaMemcpy(r->best_theta, w.best_theta, (size_t)ctx->L * K * 4, cudaMemcpyDeviceToHost)); d2h += (size_t)ctx->L * K * 4; }
+    }
+    // per-iteration trace (S:264 / S:354)
+    if (p->keep_trace) {
+        ctx->h_trace.resize((size_t)n_local * iter_cap);
+        CKS(cudaMemcpy(ctx->h_trace.data(), w.trace, ctx->h_trace.size() * sizeof(IterRec), cudaMemcpyDeviceToHost));
+        d2h += ctx->h_trace.size() * sizeof(IterRec);
+        ctx->h_trace_solve = queue;
+        ctx->h_trace_iters = h_iters;
+    }
+    cleanup();
+#undef CKS
+    ctx->stats.kernel_launches = launches;
+    ctx->stats.estep_launches = iters_enqueued;
+    ctx->stats.mstep_launches = iters_enqueued;
+    ctx->stats.solve_ms = ms;
+    ctx->stats.slot_iterations = fc.slot_iterations;
+    ctx->stats.slots = slots; ctx->stats.lanes = V; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    ctx->stats.h2d_bytes = h2d; ctx->stats.d2h_bytes = d2h;
+    return SOUP_OK;
+}
+
+extern "C" int32_t soup_get_trace(soup_ctx* ctx, int32_t solve, soup_iter_record* out, int32_t cap, int32_t* n) {
+    if (!ctx || !n) return SOUP_ERR_INVALID;
+    for (size_t i = 0; i < ctx->h_trace_solve.size(); ++i)
+        if (ctx->h_trace_solve[i] == solve) {
+            int m = ctx->h_trace_iters[i];
+            *n = m;
+            for (int j = 0; j < m && j < cap && out; ++j) {
+                const IterRec& t = ctx->h_trace[i * (size_t)ctx->h_trace_cap + j];
+                out[j] = soup_iter_record{t.temp_step, t.loss, t.change, t.above};
+            }
+            return SOUP_OK;
+        }
+    return ctx->fail(SOUP_ERR_INVALID, "soup_get_trace: solve %d was not run by the last soup_solve (or keep_trace was 0)", solve);
+}
+
+extern "C" int32_t soup_get_stats(soup_ctx* ctx, soup_stats* out) {
+    if (!ctx || !out) return SOUP_ERR_INVALID;
+    *out = ctx->stats;
+    return SOUP_OK;
+}
+
+// ------------------------------------------------------------------ parity hooks
+static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
+    if (!ctx->loaded) return ctx->fail(SOUP_ERR_INVALID, "no matrix loaded (call soup_load_csr first)");
+    if (k <= 0 || n_slots <= 0 || n_slots > 1024) return ctx->fail(SOUP_ERR_INVALID, "bad k / n_slots");
+    int V = (lanes == 1 || lanes == 2 || lanes == 4) ? lanes : pick_lanes(n_slots * k);
+    int32_t rc = ensure_workspace(ctx, k, n_slots, V, 1, n_slots, 1);
+    if (rc != SOUP_OK) return rc;
+    Workspace& w = ctx->ws;
+    std::vector<int> ga(w.n_groups, 1);
+    cudaMemcpyAsync(w.group_active, ga.data(), ga.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    Ctl hc{};
+    hc.copy_slot = -1; hc.best_solve = -1; hc.best_loss = -INFINITY;
+    cudaMemcpyAsync(w.ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return SOUP_OK;
+}
+
+extern "C" int32_t soup_estep(soup_ctx* ctx, int32_t k, int32_t method, int32_t n_slots, int32_t lanes, const float* theta,
+                              const int32_t* temp_step, float* log_probs, float* weights, float* lse, float* loss,
+                              int32_t* cells_per_cluster) {
+    if (!ctx) return SOUP_ERR_INVALID;
+    if (!theta || !temp_step) return ctx->fail(SOUP_ERR_INVALID, "soup_estep: null argument");
+    CK(cudaSetDevice(ctx->device));
+    int32_t rc = hook_setup(ctx, k, n_slots, lanes);
+    if (rc != SOUP_OK) return rc;
+    Workspace& w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    const size_t nth = (size_t)n_slots * k * ctx->L, nlp = (size_t)n_slots * ctx->N * k;
+    float *d_theta = nullptr, *d_out = nullptr;
+    auto cleanup = [&] { cudaFree(d_theta); cudaFree(d_out); };
+#define CKH(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) { cleanup(); return ctx->fail(SOUP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    CKH(cudaMalloc(&d_theta, std::max<size_t>(nth, 1) * 4));
+    CKH(cudaMalloc(&d_out, std::max<size_t>(nlp, 1) * 4));
+    CKH(cudaMemcpyAsync(d_theta, theta, nth * 4, cudaMemcpyHostToDevice, st));
+    std::vector<SlotState> hst(n_slots);
+    for (int s = 0; s < n_slots; ++s) {
+        hst[s] = SlotState{};
+        hst[s].solve = s; hst[s].local = s; hst[s].active = 1; hst[s].temp_step = temp_step[s];
+        hst[s].last_loss = -INFINITY; hst[s].loss = -INFINITY; hst[s].pending = -1;
+        if (temp_step[s] < 0 || temp_step[s] >= TEMP_STEPS) { cleanup(); return ctx->fail(SOUP_ERR_INVALID, "soup_estep: temp_step must be in [0, 9)"); }
+    }
+    CKH(cudaMemcpyAsync(w.st, hst.data(), sizeof(SlotState) * n_slots, cudaMemcpyHostToDevice, st));
+    CKH(cudaMemsetAsync(w.counts, 0, (size_t)n_slots * k * 4, st));
+    if (nth) tables_from_theta_kernel<<<(unsigned)((nth + 255) / 256), 256, 0, st>>>(d_theta, w.TH, w.LA, w.LB, w.ctl, (uint32_t)ctx->L, w.Cpad, k, n_slots);
+    const float log_prior = logf(1.0f / (float)k);
+    launch_e(ctx, log_prior);
+    launch_post(ctx, method, true);
+    std::vector<int> h_counts((size_t)n_slots * k);
+    CKH(cudaMemcpyAsync(h_counts.data(), w.counts, h_counts.size() * 4, cudaMemcpyDeviceToHost, st));
+    ControlArgs c{w.LSE, w.st, w.ctl, nullptr, w.trace, w.solve_loss, w.solve_iters, (uint32_t)ctx->N, k, n_slots, 1, 0.01f * (float)ctx->N};
+    control_kernel<<<1, std::min(1024, (n_slots + 31) / 32 * 32), 0, st>>>(c);
+    CKH(cudaGetLastError());
+    if (log_probs && nlp) {
+        plane_to_host_kernel<<<(unsigned)((nlp + 255) / 256), 256, 0, st>>>(w.ELL, d_out, (uint32_t)ctx->N, w.Cpad, k, n_slots, 1);
+        CKH(cudaMemcpyAsync(log_probs, d_out, nlp * 4, cudaMemcpyDeviceToHost, st));
+        CKH(cudaStreamSynchronize(st));
+    }
+    if (weights && nlp) {
+        plane_to_host_kernel<<<(unsigned)((nlp + 255) / 256), 256, 0, st>>>(w.W, d_out, (uint32_t)ctx->N, w.Cpad, k, n_slots, 1);
+        CKH(cudaMemcpyAsync(weights, d_out, nlp * 4, cudaMemcpyDeviceToHost, st));
+        CKH(cudaStreamSynchronize(st));
+    }
+    if (lse && ctx->N) {
+        std::vector<float> h((size_t)ctx->N * n_slots);
+        CKH(cudaMemcpyAsync(h.data(), w.LSE, h.size() * 4, cudaMemcpyDeviceToHost, st));
+        CKH(cudaStreamSynchronize(st));
+        for (int s = 0; s < n_slots; ++s)
+            for (uint64_t cidx = 0; cidx < ctx->N; ++cidx) lse[(size_t)s * ctx->N + cidx] = h[cidx * n_slots + s];
+    }
+    CKH(cudaMemcpyAsync(hst.data(), w.st, sizeof(SlotState) * n_slots, cudaMemcpyDeviceToHost, st));
+    CKH(cudaStreamSynchronize(st));
+    CKH(cudaGetLastError());
+    if (loss) for (int s = 0; s < n_slots; ++s) loss[s] = hst[s].loss;
+    if (cells_per_cluster) for (size_t i = 0; i < h_counts.size(); ++i) cells_per_cluster[i] = h_counts[i];
+    cleanup();
+    ctx->stats = soup_stats{};
+    ctx->stats.kernel_launches = 4 + (log_probs ? 1 : 0) + (weights ? 1 : 0);
+    ctx->stats.estep_launches = 1;
+    ctx->stats.slots = n_slots; ctx->stats.lanes = w.V; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    return SOUP_OK;
+}
+
+extern "C" int32_t soup_mstep(soup_ctx* ctx, int32_t k, int32_t n_slots, int32_t lanes, const float* weights, const float* theta_in,
+                              const int32_t* locked, int32_t n_locked, float* theta_out) {
+    if (!ctx) return SOUP_ERR_INVALID;
+    if (!weights || !theta_in || !theta_out || n_locked < 0 || (n_locked && !locked)) return ctx->fail(SOUP_ERR_INVALID, "soup_mstep: null argument");
+    CK(cudaSetDevice(ctx->device));
+    int32_t rc = hook_setup(ctx, k, n_slots, lanes);
+    if (rc != SOUP_OK) return rc;
+    Workspace& w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    const size_t nth = (size_t)n_slots * k * ctx->L, nw = (size_t)n_slots * ctx->N * k;
+    float *d_theta = nullptr, *d_w = nullptr;
+    auto cleanup = [&] { cudaFree(d_theta); cudaFree(d_w); };
+    CKH(cudaMalloc(&d_theta, std::max<size_t>(nth, 1) * 4));
+    CKH(cudaMalloc(&d_w, std::max<size_t>(nw, 1) * 4));
+    CKH(cudaMemcpyAsync(d_theta, theta_in, nth * 4, cudaMemcpyHostToDevice, st));
+    CKH(cudaMemcpyAsync(d_w, weights, nw * 4, cudaMemcpyHostToDevice, st));
+    std::vector<uint8_t> cw(w.Cpad, 0);
+    for (int s = 0; s < n_slots; ++s)
+        for (int c = 0; c < k; ++c) cw[(size_t)s * k + c] = 1;
+    for (int i = 0; i < n_locked; ++i) {
+        if (locked[i] < 0 || locked[i] >= k) { cleanup(); return ctx->fail(SOUP_ERR_INVALID, "soup_mstep: locked cluster out of range"); }
+        for (int s = 0; s < n_slots; ++s) cw[(size_t)s * k + locked[i]] = 0;
+    }
+    CKH(cudaMemcpyAsync(w.col_write, cw.data(), cw.size(), cudaMemcpyHostToDevice, st));
+    if (nth) tables_from_theta_kernel<<<(unsigned)((nth + 255) / 256), 256, 0, st>>>(d_theta, w.TH, w.LA, w.LB, w.ctl, (uint32_t)ctx->L, w.Cpad, k, n_slots);
+    if (nw) host_to_plane_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(d_w, w.W, (uint32_t)ctx->N, w.Cpad, k, n_slots);
+    // arbitrary caller weights may be non-finite: use the literal (no-shortcut) path
+    Ctl hc{};
+    hc.copy_slot = -1; hc.nonfinite = 1; hc.best_loss = -INFINITY;
+    CKH(cudaMemcpyAsync(w.ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, st));
+    launch_m(ctx);
+    CKH(cudaGetLastError());
+    if (nth) {
+        plane_to_host_kernel<<<(unsigned)((nth + 255) / 256), 256, 0, st>>>(w.TH, d_theta, (uint32_t)ctx->L, w.Cpad, k, n_slots, 0);
+        CKH(cudaMemcpyAsync(theta_out, d_theta, nth * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CKH(cudaStreamSynchronize(st));
+    CKH(cudaGetLastError());
+    cleanup();
+#undef CKH
+    ctx->stats = soup_stats{};
+    ctx->stats.kernel_launches = 4;
+    ctx->stats.mstep_launches = 1;
+    ctx->stats.slots = n_slots; ctx->stats.lanes = w.V; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    return SOUP_OK;
+}
+
+extern "C" int32_t soup_device_math(soup_ctx* ctx, int32_t op, const float* in, float* out, uint64_t n) {
+    if (!ctx) return SOUP_ERR_INVALID;
+    if (!in || !out || (op != 0 && op != 1)) return ctx->fail(SOUP_ERR_INVALID, "soup_device_math: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return SOUP_OK;
+    float *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_in, n * 4));
+    if (cudaMalloc(&d_out, n * 4) != cudaSuccess) { cudaFree(d_in); return ctx->fail(SOUP_ERR_NOMEM, "soup_device_math: out of device memory"); }
+    cudaMemcpyAsync(d_in, in, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op, d_in, d_out, n);
+    cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return ctx->fail(SOUP_ERR_CUDA, "soup_device_math: %s", cudaGetErrorString(e));
+    return SOUP_OK;
+}

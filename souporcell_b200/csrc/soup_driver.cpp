@@ -1,0 +1,197 @@
+// soup_main: souporcell_main (/root/reference/souporcell/src/main.rs:60-131, "S:") on top of
+// soup_solve.  Host-only logic: seed fan-out, the souporcell3 three-run loop, bad-cluster
+// detection, best-of bookkeeping, restart sharding over contexts (GPUs) and processes.
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+#include "soup_common.hpp"
+
+using namespace soup;
+
+namespace {
+
+struct Candidate {   // what ranks all-gather once per run
+    float loss;
+    int32_t solve;
+    int32_t has_best;
+    int32_t pad;
+    uint64_t nnz_updates;
+};
+
+// reference best-of order inside a run: higher loss wins, ties keep the lowest solve index (S:110, S:120)
+bool better(float loss, int solve, bool has, float cur_loss, int cur_solve, bool cur_has) {
+    if (!has) return false;
+    if (!cur_has) return true;
+    return loss > cur_loss || (loss == cur_loss && solve < cur_solve);
+}
+
+void log_solves(FILE* log, const soup_main_params* p, int spt, const std::vector<float>& loss, const std::vector<uint8_t>& mine) {
+    // "thread {} iteration {} done with {}, best so far {}" (S:115-116) for the solves this process ran;
+    // "best so far" is the thread's running best over those solves.
+    if (!log) return;
+    for (uint32_t t = 0; t < p->threads; ++t) {
+        float best = -INFINITY;
+        for (int i = 0; i < spt; ++i) {
+            int s = (int)t * spt + i;
+            if (!mine[s]) continue;
+            float l = loss[s];
+            if (l > best) best = l;
+            fprintf(log, "thread %u iteration %d done with %s, best so far %s\n", t, i, format_f32(l).c_str(), format_f32(best).c_str());
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_main_params* p, soup_main_result* r, void* log_file) {
+    if (!ctxs || n_ctx <= 0 || !ctxs[0]) { set_thread_error("soup_main: need at least one context"); return SOUP_ERR_INVALID; }
+    soup_ctx* ctx0 = ctxs[0];
+    if (!p || !r || !r->best_log_probs) { set_thread_error("soup_main: null argument"); return SOUP_ERR_INVALID; }
+    if (p->threads == 0 || p->k <= 0) { set_thread_error("soup_main: threads and k must be >= 1"); return SOUP_ERR_INVALID; }
+    const int pworld = p->proc_world > 1 ? p->proc_world : 1, prank = pworld > 1 ? p->proc_rank : 0;
+    if (pworld > 1 && (!p->allgather || !p->bcast)) { set_thread_error("soup_main: proc_world > 1 needs the allgather and bcast callbacks"); return SOUP_ERR_INVALID; }
+    FILE* log = (FILE*)log_file;
+    const int K = p->k;
+    uint64_t n_cells = 0, n_loci = 0, nnz = 0;
+    int32_t rc = soup_get_dims(ctx0, &n_cells, &n_loci, &nnz);
+    if (rc != SOUP_OK) { set_thread_error("%s", soup_last_error(ctx0)); return rc; }
+    const int spt = (int)std::ceil((float)p->restarts / (float)p->threads);   // S:63 (f32 arithmetic)
+    const int n_solves = (int)p->threads * spt;
+    const int world = pworld * n_ctx;
+
+    uint8_t seed[32];
+    memset(seed, p->seed, 32);                   // S:61
+    StdRng master = StdRng::from_seed(seed);     // S:62
+
+    r->has_best = 0; r->runs = 0; r->best_loss = -INFINITY; r->nnz_updates = 0; r->kernel_launches = 0; r->solve_ms = 0;
+    std::vector<float> best_theta((size_t)K * n_loci);
+    bool have_best = false;
+    float best_loss = -INFINITY;
+    std::vector<int32_t> bad(K);
+
+    for (int run = 0; run < 3; ++run) {          // S:70
+        int n_bad = 0;
+        if (have_best || run == 0) {
+            n_bad = soup_bad_cluster_detection(run, K, r->best_log_probs, have_best ? n_cells : 0, bad.data(), log);
+        } else {
+            // S:93 would index an empty best_cluster_centers and panic
+            set_thread_error("souporcell3 run %d: no finite solve in the previous run (the reference panics here)", run + 1);
+            return SOUP_ERR_INVALID;
+        }
+        if (n_bad < 0) return n_bad;
+        if (run != 0 && n_bad == 0) {            // S:73-76
+            if (log) fprintf(log, "No outliers detected on run %d!, Exiting.\n", run + 1);
+            break;
+        }
+        std::vector<uint8_t> seeds((size_t)p->threads * 32);
+        for (uint32_t t = 0; t < p->threads; ++t)            // S:77-80, new_seed S:855-861
+            for (int i = 0; i < 32; ++i) seeds[(size_t)t * 32 + i] = master.gen_u8();
+
+        // ---- one soup_solve per context, concurrently
+        struct PerCtx {
+            soup_solve_result res{};
+            std::vector<float> lp, th, loss;
+            std::vector<int32_t> iters;
+            int32_t rc = SOUP_OK;
+            soup_stats stats{};
+        };
+        std::vector<PerCtx> pc(n_ctx);
+        auto work = [&](int i) {
+            PerCtx& c = pc[i];
+            c.lp.resize((size_t)n_cells * K);
+            c.th.resize((size_t)K * n_loci);
+            c.loss.assign(n_solves, NAN);
+            c.iters.assign(n_solves, 0);
+            soup_solve_params sp{};
+            sp.k = K; sp.method = p->method; sp.n_streams = (int)p->threads; sp.solves_per_stream = spt;
+            sp.stream_seeds = seeds.data();
+            sp.base_theta = run > 0 ? best_theta.data() : nullptr;
+            sp.reinit_clusters = run > 0 ? bad.data() : nullptr;
+            sp.n_reinit = run > 0 ? n_bad : 0;
+            sp.iteration_cap = p->iteration_cap; sp.max_slots = p->max_slots; sp.lanes = p->lanes;
+            sp.record_counts = p->record_counts; sp.keep_trace = p->verbose_trace;
+            sp.shard_rank = prank * n_ctx + i; sp.shard_world = world;
+            c.res.best_log_probs = c.lp.data(); c.res.best_theta = c.th.data();
+            c.res.solve_loss = c.loss.data(); c.res.solve_iters = c.iters.data();
+            c.rc = soup_solve(ctxs[i], &sp, &c.res);
+            if (c.rc == SOUP_OK) soup_get_stats(ctxs[i], &c.stats);
+        };
+        if (n_ctx == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (int i = 0; i < n_ctx; ++i) pool.emplace_back(work, i);
+            for (auto& t : pool) t.join();
+        }
+        double run_ms = 0;
+        std::vector<float> loss(n_solves, NAN);
+        std::vector<int32_t> iters(n_solves, 0);
+        std::vector<uint8_t> mine(n_solves, 0);
+        int win_ctx = -1;
+        for (int i = 0; i < n_ctx; ++i) {
+            if (pc[i].rc != SOUP_OK) { set_thread_error("%s", soup_last_error(ctxs[i])); return pc[i].rc; }
+            run_ms = std::max(run_ms, pc[i].stats.solve_ms);
+            r->nnz_updates += pc[i].res.nnz_updates;
+            r->kernel_launches += pc[i].stats.kernel_launches;
+            for (int s = prank * n_ctx + i; s < n_solves; s += world) { loss[s] = pc[i].loss[s]; iters[s] = pc[i].iters[s]; mine[s] = 1; }
+            if (better(pc[i].res.best_loss, pc[i].res.best_solve, pc[i].res.has_best != 0,
+                       win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY, win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, win_ctx >= 0))
+                win_ctx = i;
+        }
+        r->solve_ms += run_ms;
+        if (log) {
+            if (p->verbose_trace) {   // per-iteration lines S:264 / S:354, grouped per solve
+                std::vector<soup_iter_record> rec(p->iteration_cap > 0 ? p->iteration_cap : 1000);
+                for (int s = 0; s < n_solves; ++s) {
+                    int owner = s % world - prank * n_ctx;
+                    if (owner < 0 || owner >= n_ctx) continue;
+                    int32_t n = 0;
+                    if (soup_get_trace(ctxs[owner], s, rec.data(), (int32_t)rec.size(), &n) != SOUP_OK) continue;
+                    for (int j = 0; j < n; ++j) {
+                        std::string a = p->method == SOUP_METHOD_EM ? format_f32_w8(rec[j].loss) : format_f32(rec[j].loss);
+                        std::string b = p->method == SOUP_METHOD_EM ? format_f32_w8(rec[j].change) : format_f32(rec[j].change);
+                        fprintf(log, "binomial\t%d\t%d\t%d\t%d\t%s\t%s\t%d\n", s / spt, s % spt, j + 1, rec[j].temp_step, a.c_str(), b.c_str(),
+                                rec[j].clusters_above_threshold);
+                    }
+                }
+            }
+            log_solves(log, p, spt, loss, mine);
+        }
+
+        // ---- winner of this run: local first, then across processes
+        Candidate cand{win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY, win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, win_ctx >= 0 ? 1 : 0, 0, 0};
+        int win_rank = prank;
+        Candidate win = cand;
+        if (pworld > 1) {
+            std::vector<Candidate> all(pworld);
+            int32_t e = p->allgather(p->comm_user, &cand, all.data(), sizeof(Candidate));
+            if (e != SOUP_OK) { set_thread_error("soup_main: allgather callback failed (%d)", e); return e; }
+            win = Candidate{-INFINITY, -1, 0, 0, 0};
+            win_rank = 0;
+            for (int q = 0; q < pworld; ++q)
+                if (better(all[q].loss, all[q].solve, all[q].has_best != 0, win.loss, win.solve, win.has_best != 0)) { win = all[q]; win_rank = q; }
+        }
+        // adopt only if strictly better than the best carried over from earlier runs (S:120)
+        const bool adopt = win.has_best && win.loss > best_loss;
+        if (adopt) {
+            if (win_rank == prank) {
+                memcpy(r->best_log_probs, pc[win_ctx].lp.data(), pc[win_ctx].lp.size() * sizeof(float));
+                best_theta = pc[win_ctx].th;
+            }
+            if (pworld > 1) {
+                int32_t e = p->bcast(p->comm_user, r->best_log_probs, (uint64_t)n_cells * K * sizeof(float), win_rank);
+                if (e == SOUP_OK) e = p->bcast(p->comm_user, best_theta.data(), (uint64_t)K * n_loci * sizeof(float), win_rank);
+                if (e != SOUP_OK) { set_thread_error("soup_main: bcast callback failed (%d)", e); return e; }
+            }
+            best_loss = win.loss;
+            have_best = true;
+        }
+        r->runs = run + 1;
+        if (!p->souporcell3) break;              // S:127-129
+    }
+    if (log) fprintf(log, "best total log probability = %s\n", format_f32(best_loss).c_str());   // S:131
+    r->has_best = have_best ? 1 : 0;
+    r->best_loss = best_loss;
+    if (r->best_theta && have_best) memcpy(r->best_theta, best_theta.data(), best_theta.size() * sizeof(float));
+    return SOUP_OK;
+}

@@ -1,0 +1,576 @@
+// Device kernels of libsoupgpu (sm_100a).  Reference: /root/reference/souporcell/src/main.rs ("S:").
+//
+// Layout in HBM.  A *column* is one (slot, cluster) pair, col = slot*K + k; a
+// *slot* is one resident solve (one em()/khm() call, S:189/S:280).  Columns are padded to a
+// multiple of the group width GW = 32*V (V = columns per lane, 1/2/4).
+//   LA, LB, TH : [L][Cpad] f32   ln(theta), ln(1-theta), theta          (row = used locus)
+//   ELL, W     : [N][Cpad] f32   per-cell log-likelihoods, M-step weights (row = cell)
+//   LSE        : [N][slots] f32  per-cell log_sum_exp (S:230)
+//   csr        : [nnz] uint4 {locus, f32 alt, f32 ref, f32 ln_binomial}  rows = cells, loci ascending
+//   csc        : [nnz] uint4 {cell,  f32 alt, f32 alt+ref, 0}            cols = loci, cells ascending
+// One warp owns one (row, column-group) pair and walks the row's entries strictly in order,
+// so every (cell,k) / (locus,k) sum is accumulated in the reference's own order (S:415-418,
+// S:476-483) and the results are bit-identical to the scalar code; lanes never exchange data.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "glibc_flt32.h"
+#include "soup_common.hpp"
+
+namespace soup {
+
+constexpr int EM_THREADS = 256;            // 8 warps per CTA in the E / M kernels
+constexpr int EM_WARPS = EM_THREADS / 32;
+constexpr int TEMP_STEPS = 9;              // S:215
+
+struct SlotState {
+    int solve;        // global solve index (stream * solves_per_stream + iteration), -1 = empty
+    int local;        // index into this call's solve queue (trace / result rows)
+    int active;       // takes part in this iteration's E / post / M
+    int temp_step;    // S:217
+    int iterations;   // S:204
+    float last_loss;  // S:216
+    float loss;       // total_log_loss S:245
+    int fin;          // finished in this iteration (theta is final after this iteration's M pass)
+    int pending;      // next queue position to load into the slot, -1 = none
+    int pad[3];
+};
+
+struct Ctl {
+    int queue_head, queue_len;
+    int done_count;
+    int copy_slot;      // slot whose log-probs / theta the harvest kernel copies this iteration
+    int best_solve;
+    int has_best;
+    float best_loss;
+    int nonfinite;      // a ln-table holds a non-finite value: exact zero-count shortcuts are off
+    int n_active;
+    int pad0;
+    unsigned long long slot_iterations;
+};
+
+struct IterRec { int temp_step; float loss; float change; int above; };
+
+// ------------------------------------------------------------------ small helpers
+template <int V> struct FVec { float v[V]; };
+template <int V> __device__ __forceinline__ FVec<V> ld_row(const float* p);
+template <> __device__ __forceinline__ FVec<1> ld_row<1>(const float* p) { FVec<1> r; r.v[0] = __ldg(p); return r; }
+template <> __device__ __forceinline__ FVec<2> ld_row<2>(const float* p) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p)); FVec<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
+}
+template <> __device__ __forceinline__ FVec<4> ld_row<4>(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p)); FVec<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+template <int V> __device__ __forceinline__ void st_row(float* p, const FVec<V>& x);
+template <> __device__ __forceinline__ void st_row<1>(float* p, const FVec<1>& x) { *p = x.v[0]; }
+template <> __device__ __forceinline__ void st_row<2>(float* p, const FVec<2>& x) { *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]); }
+template <> __device__ __forceinline__ void st_row<4>(float* p, const FVec<4>& x) { *reinterpret_cast<float4*>(p) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]); }
+
+// ------------------------------------------------------------------ E pass  (S:409-426)
+// acc_k = ln(1/K); for each entry j (ascending locus): acc_k += (lbc_j + alt_j*ln th) + ref_j*ln(1-th).
+// Exact shortcuts (only while every table value is finite): ref_j == 0 drops the "+ ref*ln(1-th)"
+// term (it adds -0.0) and alt_j == 0 drops "alt*ln th" (lbc + -0.0 == lbc), so one-sided
+// entries gather one table plane instead of two.
+template <int V, bool EXACT_SKIP>
+__device__ __forceinline__ void e_accumulate(FVec<V>& acc, const uint4& e, const float* __restrict__ LA,
+                                             const float* __restrict__ LB, size_t Cpad) {
+    const float alt = __uint_as_float(e.y), ref = __uint_as_float(e.z), lbc = __uint_as_float(e.w);
+    const size_t off = (size_t)e.x * Cpad;
+    const bool ha = !EXACT_SKIP || alt != 0.0f, hr = !EXACT_SKIP || ref != 0.0f;
+    FVec<V> a, b;
+    if (ha) a = ld_row<V>(LA + off);
+    if (hr) b = ld_row<V>(LB + off);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        float t = lbc;
+        if (ha) t = __fadd_rn(lbc, __fmul_rn(alt, a.v[v]));
+        if (hr) t = __fadd_rn(t, __fmul_rn(ref, b.v[v]));
+        acc.v[v] = __fadd_rn(acc.v[v], t);
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(EM_THREADS)
+estep_kernel(const uint4* __restrict__ csr, const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ cell_order,
+             const float* __restrict__ LA, const float* __restrict__ LB, float* __restrict__ ELL,
+             const int* __restrict__ group_active, const Ctl* __restrict__ ctl, uint32_t N, uint32_t Cpad,
+             uint32_t blocks_per_group, float log_prior) {
+    const uint32_t group = blockIdx.x / blocks_per_group;
+    if (!group_active[group]) return;
+    const uint32_t chunk = blockIdx.x - group * blocks_per_group;
+    const uint32_t ci = chunk * EM_WARPS + (threadIdx.x >> 5);
+    if (ci >= N) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t cell = cell_order[ci];
+    const size_t col = (size_t)group * (32 * V) + lane * V;
+    const float* la = LA + col;
+    const float* lb = LB + col;
+    uint64_t j = row_ptr[cell];
+    const uint64_t j1 = row_ptr[cell + 1];
+    FVec<V> acc;
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc.v[v] = log_prior;
+    constexpr int U = 4;
+    if (!ctl->nonfinite) {
+        for (; j + U <= j1; j += U) {
+            uint4 e[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) e[u] = __ldg(csr + j + u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) e_accumulate<V, true>(acc, e[u], la, lb, Cpad);
+        }
+        for (; j < j1; ++j) e_accumulate<V, true>(acc, __ldg(csr + j), la, lb, Cpad);
+    } else {
+        for (; j < j1; ++j) e_accumulate<V, false>(acc, __ldg(csr + j), la, lb, Cpad);
+    }
+    st_row<V>(ELL + (size_t)cell * Cpad + col, acc);
+}
+
+// ------------------------------------------------------------------ per-cell pass (S:230-236 / S:318-330)
+struct PostArgs {
+    const float* ELL;
+    float* W;
+    float* LSE;
+    const float* total_alleles;
+    const SlotState* st;
+    int* counts;          // [slots][K] cells per cluster (LAST max, S:254), or nullptr
+    uint32_t N, Cpad;
+    int K, slots, method;
+};
+
+__device__ __forceinline__ float rust_lse(const float* x, int K) {   // log_sum_exp S:428-432
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) m = fmaxf(m, x[k]);
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s = s + soupmath::glibc_expf(x[k] - m);
+    return m + soupmath::glibc_logf(s);
+}
+
+__global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)a.N * a.slots) return;
+    const uint32_t cell = (uint32_t)(idx / a.slots);
+    const int slot = (int)(idx - (size_t)cell * a.slots);
+    const SlotState s = a.st[slot];
+    if (!s.active) return;
+    const int K = a.K;
+    const float* x = a.ELL + (size_t)cell * a.Cpad + (size_t)slot * K;
+    float* w = a.W + (size_t)cell * a.Cpad + (size_t)slot * K;
+    a.LSE[(size_t)cell * a.slots + slot] = rust_lse(x, K);
+    const float total = a.total_alleles[cell];
+    float temp;
+    if (a.method == SOUP_METHOD_EM) temp = fmaxf(total / ldexpf(20.0f, s.temp_step), 1.0f);   // S:233
+    else temp = fmaxf(total / ldexpf(0.5f, s.temp_step), 1.0f);                               // S:327
+    if (s.temp_step == TEMP_STEPS - 1) temp = 1.0f;                                            // S:234 / S:328
+    if (a.method == SOUP_METHOD_EM) {
+        // normalize_in_log_with_temp S:443-454 on the log-likelihoods themselves
+        float m = -INFINITY;
+        for (int k = 0; k < K; ++k) m = fmaxf(m, x[k] / temp);
+        float sum = 0.0f;
+        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf(x[k] / temp - m);
+        const float lse = m + soupmath::glibc_logf(sum);
+        for (int k = 0; k < K; ++k) w[k] = soupmath::glibc_expf(x[k] / temp - lse);
+    } else {
+        // calculate_q_for_current_cell S:360-384 in the reference's literal operation order
+        int win = 0;
+        float best = -3.40282347e+38f;   // f32::MIN S:411
+        for (int k = 0; k < K; ++k) if (x[k] > best) { best = x[k]; win = k; }
+        const float wl = -x[win];
+        float m = -INFINITY;
+        for (int k = 0; k < K; ++k) m = fmaxf(m, k != win ? 25.0f * (wl + x[k]) : 0.0f);
+        float sum = 0.0f;
+        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf((k != win ? 25.0f * (wl + x[k]) : 0.0f) - m);
+        const float q_denom = m + soupmath::glibc_logf(sum);
+        const float c0 = 50.0f * wl, c2 = 2.0f * q_denom;
+#define SOUP_Q(k) ((c0 - (27.0f * -x[k])) - c2)
+        m = -INFINITY;
+        for (int k = 0; k < K; ++k) m = fmaxf(m, SOUP_Q(k));
+        sum = 0.0f;
+        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf(SOUP_Q(k) - m);
+        const float q_sum = m + soupmath::glibc_logf(sum);
+        // khm_prob = q - q_sum (S:322-325), then normalize_in_log_with_temp (S:330)
+        m = -INFINITY;
+        for (int k = 0; k < K; ++k) m = fmaxf(m, (SOUP_Q(k) - q_sum) / temp);
+        sum = 0.0f;
+        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf((SOUP_Q(k) - q_sum) / temp - m);
+        const float lse = m + soupmath::glibc_logf(sum);
+        for (int k = 0; k < K; ++k) w[k] = soupmath::glibc_expf((SOUP_Q(k) - q_sum) / temp - lse);
+#undef SOUP_Q
+    }
+    if (a.counts) {   // max_by(total_cmp) keeps the LAST maximum (S:254)
+        int bi = 0;
+        int32_t bk = total_key(x[0]);
+        for (int k = 1; k < K; ++k) {
+            int32_t kk = total_key(x[k]);
+            if (kk >= bk) { bk = kk; bi = k; }
+        }
+        atomicAdd(a.counts + (size_t)slot * K + bi, 1);
+    }
+}
+
+// ------------------------------------------------------------------ loss + control (S:217-222, 245-250)
+struct ControlArgs {
+    const float* LSE;
+    SlotState* st;
+    Ctl* ctl;
+    int* counts;              // [slots][K] or nullptr
+    IterRec* trace;           // [queue_len][iter_cap]
+    float* solve_loss;        // [queue_len]
+    int* solve_iters;         // [queue_len]
+    uint32_t N;
+    int K, slots, iter_cap;
+    float limit;              // log_loss_change_limit S:214
+};
+
+// advance to the first temp step whose while-condition holds with log_loss_change = 10000 (S:219-222)
+__device__ __forceinline__ int next_temp_step(int t, int iterations, int cap, float limit) {
+    while (t < TEMP_STEPS && !(10000.0f > limit && iterations < cap)) ++t;
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) control_kernel(ControlArgs a) {
+    for (int slot = threadIdx.x; slot < a.slots; slot += blockDim.x) {
+        SlotState s = a.st[slot];
+        if (!s.active) continue;
+        // log_binom_loss: strictly sequential f32 sum over cells in index order (S:225-230)
+        float loss = 0.0f;
+        const float* p = a.LSE + slot;
+        uint32_t c = 0;
+        for (; c + 8 <= a.N; c += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(c + u) * a.slots];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) loss = loss + v[u];
+        }
+        for (; c < a.N; ++c) loss = loss + p[(size_t)c * a.slots];
+        const float change = loss - s.last_loss;     // S:246
+        s.loss = loss;
+        s.last_loss = loss;
+        s.iterations += 1;                           // S:250
+        int above = -1;
+        if (a.counts) {
+            above = 0;
+            for (int k = 0; k < a.K; ++k) {
+                if (a.counts[(size_t)slot * a.K + k] > 200) ++above;   // S:260
+                a.counts[(size_t)slot * a.K + k] = 0;
+            }
+        }
+        if (s.iterations <= a.iter_cap) a.trace[(size_t)s.local * a.iter_cap + (s.iterations - 1)] = IterRec{s.temp_step, loss, change, above};
+        if (!(change > a.limit && s.iterations < a.iter_cap))   // leave this temp step's while loop (S:222)
+            s.temp_step = next_temp_step(s.temp_step + 1, s.iterations, a.iter_cap, a.limit);
+        if (s.temp_step >= TEMP_STEPS) s.fin = 1;
+        a.st[slot] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Ctl c = *a.ctl;
+        c.copy_slot = -1;
+        for (int slot = 0; slot < a.slots; ++slot) {
+            SlotState s = a.st[slot];
+            if (!s.active) continue;
+            c.slot_iterations += 1;
+            if (!s.fin) continue;
+            a.solve_loss[s.local] = s.loss;
+            a.solve_iters[s.local] = s.iterations;
+            // best-of (S:110, S:120: strict >, threads in index order) == max loss, ties -> lowest solve index
+            if (s.loss > c.best_loss || (c.has_best && s.loss == c.best_loss && s.solve < c.best_solve)) {
+                c.best_loss = s.loss;
+                c.best_solve = s.solve;
+                c.has_best = 1;
+                c.copy_slot = slot;
+            }
+            c.done_count += 1;
+            s.pending = c.queue_head < c.queue_len ? c.queue_head++ : -1;
+            a.st[slot] = s;
+        }
+        *a.ctl = c;
+    }
+}
+
+// ------------------------------------------------------------------ M pass (S:476-483, S:386-396)
+// s = 1 + sum_cells p*alt ; d = 2 + sum_cells p*(alt+ref), cells ascending; theta = clamp(s/d).
+template <int V, bool EXACT_SKIP>
+__device__ __forceinline__ void m_accumulate(FVec<V>& s, FVec<V>& d, const uint4& e, const float* __restrict__ W, size_t Cpad) {
+    const float alt = __uint_as_float(e.y), tot = __uint_as_float(e.z);
+    const FVec<V> p = ld_row<V>(W + (size_t)e.x * Cpad);
+    if (!EXACT_SKIP || alt != 0.0f) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) s.v[v] = __fadd_rn(s.v[v], __fmul_rn(p.v[v], alt));
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], __fmul_rn(p.v[v], tot));
+}
+
+template <int V>
+__global__ void __launch_bounds__(EM_THREADS)
+mstep_kernel(const uint4* __restrict__ csc, const uint64_t* __restrict__ col_ptr, const uint32_t* __restrict__ locus_order,
+             const float* __restrict__ W, float* __restrict__ TH, float* __restrict__ LA, float* __restrict__ LB,
+             const uint8_t* __restrict__ col_write, const int* __restrict__ group_active, const Ctl* __restrict__ ctl,
+             uint32_t L, uint32_t Cpad, uint32_t blocks_per_group) {
+    const uint32_t group = blockIdx.x / blocks_per_group;
+    if (!group_active[group]) return;
+    const uint32_t chunk = blockIdx.x - group * blocks_per_group;
+    const uint32_t li = chunk * EM_WARPS + (threadIdx.x >> 5);
+    if (li >= L) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t locus = locus_order[li];
+    const size_t col = (size_t)group * (32 * V) + lane * V;
+    const float* w = W + col;
+    uint64_t j = col_ptr[locus];
+    const uint64_t j1 = col_ptr[locus + 1];
+    FVec<V> s, d;
+#pragma unroll
+    for (int v = 0; v < V; ++v) { s.v[v] = 1.0f; d.v[v] = 2.0f; }   // pseudocounts S:197-198, S:456-464
+    constexpr int U = 4;
+    if (!ctl->nonfinite) {
+        for (; j + U <= j1; j += U) {
+            uint4 e[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) e[u] = __ldg(csc + j + u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) m_accumulate<V, true>(s, d, e[u], w, Cpad);
+        }
+        for (; j < j1; ++j) m_accumulate<V, true>(s, d, __ldg(csc + j), w, Cpad);
+    } else {
+        for (; j < j1; ++j) m_accumulate<V, false>(s, d, __ldg(csc + j), w, Cpad);
+    }
+    const size_t o = (size_t)locus * Cpad + col;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (!col_write[col + v]) continue;          // locked cluster (S:389) or idle column
+        const float th = fmaxf(fminf(__fdiv_rn(s.v[v], d.v[v]), 0.99f), 0.01f);   // S:392-393
+        TH[o + v] = th;
+        LA[o + v] = soupmath::glibc_logf(th);
+        LB[o + v] = soupmath::glibc_logf(1.0f - th);
+    }
+}
+
+// ------------------------------------------------------------------ harvest: keep the best solve (S:110-114)
+__global__ void harvest_kernel(const Ctl* __restrict__ ctl, const float* __restrict__ ELL, const float* __restrict__ TH,
+                               float* __restrict__ best_lp, float* __restrict__ best_theta, uint32_t N, uint32_t L,
+                               uint32_t Cpad, int K) {
+    const int slot = ctl->copy_slot;
+    if (slot < 0) return;
+    const size_t nlp = (size_t)N * K, nth = (size_t)L * K;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nlp + nth; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < nlp) {
+            const size_t cell = i / K, k = i - cell * K;
+            best_lp[i] = ELL[cell * Cpad + (size_t)slot * K + k];
+        } else {
+            const size_t e = i - nlp, l = e / K, k = e - l * K;
+            best_theta[k * L + l] = TH[l * Cpad + (size_t)slot * K + k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ refill: theta0 of the next solve (S:485-498, 554-563)
+struct RefillArgs {
+    SlotState* st;
+    Ctl* ctl;
+    const int* queue;             // [queue_len] global solve indices
+    const uint32_t* stream_keys;  // [n_streams][8] ChaCha keys of the ThreadData rngs (S:52)
+    const float* theta0;          // [n_solves][K][L] or nullptr
+    const float* base_theta;      // [K][L] or nullptr (S:93)
+    const int* draw_of_k;         // [K]: position of cluster k in this run's draw order, -1 = locked (S:92-97)
+    float *TH, *LA, *LB;
+    uint32_t L, Cpad;
+    int K, n_draw, solves_per_stream;
+};
+
+__global__ void __launch_bounds__(256) refill_kernel(RefillArgs a) {
+    const int slot = blockIdx.y;
+    const SlotState s = a.st[slot];
+    if (!s.fin || s.pending < 0) return;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // e = l*K + k (k fastest: coalesced table writes)
+    if (e >= (size_t)a.L * a.K) return;
+    const uint32_t l = (uint32_t)(e / a.K);
+    const int k = (int)(e - (size_t)l * a.K);
+    const int solve = a.queue[s.pending];
+    float th;
+    const int d = a.draw_of_k[k];
+    if (a.theta0) {
+        th = a.theta0[((size_t)solve * a.K + k) * a.L + l];
+    } else if (d < 0) {
+        th = a.base_theta[(size_t)k * a.L + l];
+    } else {
+        // init_cluster_centers_uniform S:554-563: cluster-major then locus draw order, one u32 word per f32
+        const int stream = solve / a.solves_per_stream, it = solve - stream * a.solves_per_stream;
+        const uint64_t word = ((uint64_t)it * a.n_draw + d) * a.L + l;
+        uint32_t blk[16];
+        chacha_block(a.stream_keys + (size_t)stream * 8, word >> 4, 12, blk);
+        uint32_t wv = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if ((int)(word & 15) == i) wv = blk[i];
+        th = fmaxf(fminf((float)(wv >> 8) * (1.0f / 16777216.0f), 0.9999f), 0.0001f);
+    }
+    const size_t o = (size_t)l * a.Cpad + (size_t)slot * a.K + k;
+    const float la = soupmath::glibc_logf(th), lb = soupmath::glibc_logf(1.0f - th);
+    a.TH[o] = th;
+    a.LA[o] = la;
+    a.LB[o] = lb;
+    if (!isfinite(la) || !isfinite(lb)) a.ctl->nonfinite = 1;
+}
+
+// after refill: install pending solves, retire finished slots, rebuild the column / group masks
+struct FinalizeArgs {
+    SlotState* st;
+    Ctl* ctl;
+    const int* queue;
+    const uint8_t* k_locked;   // [K]
+    uint8_t* col_write;        // [Cpad]
+    int* group_active;         // [n_groups]
+    int K, slots, GW, n_groups, iter_cap;
+    uint32_t Cpad;
+    float limit;
+};
+
+__global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
+    __shared__ int n_active;
+    if (threadIdx.x == 0) n_active = 0;
+    __syncthreads();
+    for (int slot = threadIdx.x; slot < a.slots; slot += blockDim.x) {
+        SlotState s = a.st[slot];
+        if (s.fin) {
+            s.fin = 0;
+            if (s.pending >= 0) {
+                s.local = s.pending;
+                s.solve = a.queue[s.pending];
+                s.active = 1;
+                s.temp_step = next_temp_step(0, 0, a.iter_cap, a.limit);
+                s.iterations = 0;
+                s.last_loss = -INFINITY;
+                s.loss = -INFINITY;
+            } else {
+                s.active = 0;
+                s.solve = -1;
+            }
+            s.pending = -1;
+            a.st[slot] = s;
+        }
+        if (s.active) atomicAdd(&n_active, 1);
+    }
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < a.Cpad; c += blockDim.x) {
+        const int slot = (int)(c / a.K), k = (int)(c - (uint32_t)slot * a.K);
+        a.col_write[c] = (slot < a.slots && a.st[slot].active && !a.k_locked[k]) ? 1 : 0;
+    }
+    for (int g = threadIdx.x; g < a.n_groups; g += blockDim.x) {
+        const int first = (g * a.GW) / a.K;
+        int last = (g * a.GW + a.GW - 1) / a.K;
+        if (last >= a.slots) last = a.slots - 1;
+        int any = 0;
+        for (int s = first; s <= last; ++s) any |= a.st[s].active;
+        a.group_active[g] = any;
+    }
+    if (threadIdx.x == 0) a.ctl->n_active = n_active;
+}
+
+// ------------------------------------------------------------------ load-time kernels
+__constant__ double c_ln_factorial[171];   // statrs FCACHE: ln(n!) for n <= 170 (S:669-670)
+
+__global__ void build_csr_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ locus,
+                                 const uint32_t* __restrict__ alt, const uint32_t* __restrict__ ref, uint4* __restrict__ csr,
+                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, float* __restrict__ total_alleles,
+                                 uint32_t* __restrict__ row_len, uint32_t N) {
+    const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (cell >= N) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t j0 = row_ptr[cell], j1 = row_ptr[cell + 1];
+    for (uint64_t j = j0 + lane; j < j1; j += 32) {
+        const uint32_t a = alt[j], r = ref[j], n = a + r;   // wrapping u32 add as in release-mode Rust (S:664, S:670)
+        float lbc = 0.0f;
+        if (n <= 170u) lbc = (float)(c_ln_factorial[n] - c_ln_factorial[a] - c_ln_factorial[n - a]);   // n > 170 patched from the host
+        csr[j] = make_uint4(locus[j], __float_as_uint((float)a), __float_as_uint((float)r), __float_as_uint(lbc));
+        keys[j] = ((unsigned long long)locus[j] << 32) | cell;
+        vals[j] = (uint32_t)j;
+    }
+    if (lane == 0) {
+        float t = 0.0f;                                      // total_alleles S:671: sequential f32, ascending locus
+        for (uint64_t j = j0; j < j1; ++j) t = t + (float)(alt[j] + ref[j]);
+        total_alleles[cell] = t;
+        row_len[cell] = (uint32_t)(j1 - j0);
+    }
+}
+
+__global__ void patch_lbc_kernel(uint4* csr, const uint32_t* __restrict__ idx, const float* __restrict__ val, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) csr[idx[i]].w = __float_as_uint(val[i]);
+}
+
+// csc entry = {cell, f32 alt, f32 (alt+ref: integer add, then cast, S:480), 0} in (locus, cell) order
+__global__ void build_csc_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                 const uint32_t* __restrict__ alt, const uint32_t* __restrict__ ref, uint4* __restrict__ csc,
+                                 uint64_t nnz) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const uint32_t j = vals[i];
+    const uint32_t a = alt[j], r = ref[j];
+    csc[i] = make_uint4((uint32_t)(keys[i] & 0xffffffffu), __float_as_uint((float)a), __float_as_uint((float)(a + r)), 0u);
+}
+
+__global__ void col_ptr_kernel(const unsigned long long* __restrict__ keys, uint64_t nnz, uint64_t* __restrict__ col_ptr, uint32_t L) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > L) return;
+    const unsigned long long target = (unsigned long long)l << 32;   // first key with locus >= l
+    uint64_t lo = 0, hi = nnz;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    col_ptr[l] = lo;
+}
+__global__ void seg_len_kernel(const uint64_t* __restrict__ ptr, uint32_t* __restrict__ len, uint32_t* __restrict__ idx, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    len[i] = (uint32_t)(ptr[i + 1] - ptr[i]);
+    idx[i] = i;
+}
+
+// ------------------------------------------------------------------ test hooks
+__global__ void math_kernel(int op, const float* __restrict__ in, float* __restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = op == 0 ? soupmath::glibc_logf(in[i]) : soupmath::glibc_expf(in[i]);
+}
+
+// theta [n_slots][K][L] (host layout) -> TH / LA / LB planes
+__global__ void tables_from_theta_kernel(const float* __restrict__ theta, float* TH, float* LA, float* LB, Ctl* ctl,
+                                         uint32_t L, uint32_t Cpad, int K, int slots) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // e = (l*slots + slot)*K + k
+    if (e >= (size_t)L * slots * K) return;
+    const int k = (int)(e % K);
+    const size_t t = e / K;
+    const int slot = (int)(t % slots);
+    const size_t l = t / slots;
+    const float th = theta[((size_t)slot * K + k) * L + l];
+    const size_t o = l * Cpad + (size_t)slot * K + k;
+    const float la = soupmath::glibc_logf(th), lb = soupmath::glibc_logf(1.0f - th);
+    TH[o] = th; LA[o] = la; LB[o] = lb;
+    if (!isfinite(la) || !isfinite(lb)) ctl->nonfinite = 1;
+}
+// [rows][Cpad] plane -> host layout [slots][rows][K] (row_major_k = 1) or [slots][K][rows] (0)
+__global__ void plane_to_host_kernel(const float* __restrict__ plane, float* __restrict__ out, uint32_t rows, uint32_t Cpad, int K,
+                                     int slots, int row_major_k) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)rows * slots * K) return;
+    const int k = (int)(e % K);
+    const size_t t = e / K;
+    const int slot = (int)(t % slots);
+    const size_t r = t / slots;
+    const float v = plane[r * Cpad + (size_t)slot * K + k];
+    if (row_major_k) out[((size_t)slot * rows + r) * K + k] = v;
+    else out[((size_t)slot * K + k) * rows + r] = v;
+}
+__global__ void host_to_plane_kernel(const float* __restrict__ in, float* __restrict__ plane, uint32_t rows, uint32_t Cpad, int K, int slots) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // in: [slots][rows][K]
+    if (e >= (size_t)rows * slots * K) return;
+    const int k = (int)(e % K);
+    const size_t t = e / K;
+    const int slot = (int)(t % slots);
+    const size_t r = t / slots;
+    plane[r * Cpad + (size_t)slot * K + k] = in[((size_t)slot * rows + r) * K + k];
+}
+
+}  // namespace soup

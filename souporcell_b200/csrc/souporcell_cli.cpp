@@ -1,0 +1,179 @@
+// `souporcell` — drop-in executable for the reference clustering binary
+// (/root/reference/souporcell/src/main.rs:31-36 main(), argv schema souporcell/src/params.yml:1-98).
+// Same flags, clusters_tmp.tsv on stdout, the reference's log lines on stderr, non-zero exit on
+// any failure with nothing written to stdout.  All numerics run on the GPU through libsoupgpu.
+//
+// Extra, optional flags (absent from the reference; the pipeline's argv works unchanged):
+//   --gpus N           use the first N visible GPUs (restart-sharded); default: all visible
+//   --max_slots N      resident solves per GPU (0 = auto)
+//   --quiet_iterations do not print the per-iteration "binomial" lines
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime_api.h>
+
+#include "soup_common.hpp"
+
+namespace {
+
+struct Opt { const char* name; char shrt; bool multiple; bool flag; const char* help; };
+const Opt kOpts[] = {
+    {"ref_matrix", 'r', false, false, "ref matrix from vartrix"},
+    {"alt_matrix", 'a', false, false, "alt matrix from vartrix"},
+    {"barcodes", 'b', false, false, "cell barcodes"},
+    {"num_clusters", 'k', false, false, "number of clusters"},
+    {"min_alt", 0, false, false, "minimum number of cells containing the alt allele for the variant to be used for clustering"},
+    {"min_ref", 0, false, false, "minimum number of cells containing the ref allele for the variant to be used for clustering"},
+    {"restarts", 0, false, false, "number of random seedings"},
+    {"known_genotypes", 'g', false, false, "population vcf/bcf of known genotypes if available."},
+    {"known_genotypes_sample_names", 0, true, false, "sample names, must be samples from the known_genotypes vcf"},
+    {"known_cell_assignments", 0, false, false, "tsv with barcodes and their known assignments"},
+    {"initialization_strategy", 0, false, false, "cluster initialization strategy, defaults to random_uniform, other methods not yet implemented"},
+    {"threads", 't', false, false, "number of threads to use"},
+    {"seed", 0, false, false, "optional random seed"},
+    {"min_alt_umis", 0, false, false, "min alt umis to use locus for clustering"},
+    {"min_ref_umis", 0, false, false, "min ref umis to use locus for clustering"},
+    {"souporcell3", 's', false, false, "activate bad cluster detection and multiple runs"},
+    {"clustering_method", 'm', false, false, "choose between expectation maximization (em) and k harmonic means (khm)"},
+    {"gpus", 0, false, false, "[soupgpu] number of GPUs to shard restarts over (default: all visible)"},
+    {"max_slots", 0, false, false, "[soupgpu] resident solves per GPU (default: auto)"},
+    {"quiet_iterations", 0, false, true, "[soupgpu] do not log per-iteration lines"},
+};
+
+void usage(FILE* f) {
+    fprintf(f, "souporcell 3.0\nHaynes Heaton <whheaton@gmail.com>\nclustering scRNAseq cells by genotype\n\nUSAGE:\n"
+               "    souporcell [OPTIONS] --alt_matrix <alt_matrix> --barcodes <barcodes> --num_clusters <num_clusters> --ref_matrix <ref_matrix>\n\n"
+               "FLAGS:\n    -h, --help       Prints help information\n    -V, --version    Prints version information\n\nOPTIONS:\n");
+    for (const Opt& o : kOpts) {
+        if (o.shrt) fprintf(f, "    -%c, --%s%s    %s\n", o.shrt, o.name, o.flag ? "" : " <value>", o.help);
+        else fprintf(f, "        --%s%s    %s\n", o.name, o.flag ? "" : (o.multiple ? " <value>..." : " <value>"), o.help);
+    }
+}
+
+[[noreturn]] void die(const std::string& msg, int code = 1) {
+    fprintf(stderr, "%s\n", msg.c_str());
+    exit(code);
+}
+// mirrors `value.parse::<T>().unwrap()` panics (exit code 101)
+uint64_t parse_num(const std::string& s, const char* what, uint64_t maxv) {
+    size_t i = (!s.empty() && s[0] == '+') ? 1 : 0;
+    if (i >= s.size()) die(std::string("thread 'main' panicked: invalid value for ") + what + ": '" + s + "'", 101);
+    uint64_t v = 0;
+    for (; i < s.size(); ++i) {
+        if (s[i] < '0' || s[i] > '9' || v > (maxv - (uint64_t)(s[i] - '0')) / 10) die(std::string("thread 'main' panicked: invalid value for ") + what + ": '" + s + "'", 101);
+        v = v * 10 + (uint64_t)(s[i] - '0');
+    }
+    return v;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    std::map<std::string, std::vector<std::string>> vals;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "-h" || a == "--help") { usage(stdout); return 0; }
+        if (a == "-V" || a == "--version") { printf("souporcell 3.0\n"); return 0; }
+        const Opt* o = nullptr;
+        std::string inl;
+        bool has_inl = false;
+        if (a.rfind("--", 0) == 0) {
+            std::string name = a.substr(2);
+            size_t eq = name.find('=');
+            if (eq != std::string::npos) { inl = name.substr(eq + 1); name = name.substr(0, eq); has_inl = true; }
+            for (const Opt& c : kOpts) if (name == c.name) o = &c;
+        } else if (a.size() >= 2 && a[0] == '-') {
+            for (const Opt& c : kOpts) if (c.shrt && c.shrt == a[1]) o = &c;
+            if (a.size() > 2) { inl = a.substr(a[2] == '=' ? 3 : 2); has_inl = true; }
+        }
+        if (!o) { fprintf(stderr, "error: Found argument '%s' which wasn't expected, or isn't valid in this context\n\n", a.c_str()); usage(stderr); return 1; }
+        if (o->flag) { vals[o->name].push_back("true"); continue; }
+        if (has_inl) { vals[o->name].push_back(inl); continue; }
+        if (i + 1 >= argc) { fprintf(stderr, "error: The argument '--%s <%s>' requires a value but none was supplied\n\n", o->name, o->name); usage(stderr); return 1; }
+        vals[o->name].push_back(argv[++i]);
+        if (o->multiple) while (i + 1 < argc && argv[i + 1][0] != '-') vals[o->name].push_back(argv[++i]);
+    }
+    for (const char* req : {"alt_matrix", "barcodes", "num_clusters", "ref_matrix"})
+        if (!vals.count(req)) { fprintf(stderr, "error: The following required arguments were not provided:\n    --%s <%s>\n\n", req, req); usage(stderr); return 1; }
+    auto get = [&](const char* n, const char* d) { return vals.count(n) ? vals[n].back() : std::string(d); };
+
+    // ---- load_params S:756-853
+    const std::string ref_mtx = get("ref_matrix", ""), alt_mtx = get("alt_matrix", ""), barcodes_path = get("barcodes", "");
+    const uint64_t k = parse_num(get("num_clusters", ""), "num_clusters", INT32_MAX);
+    const uint32_t min_alt = (uint32_t)parse_num(get("min_alt", "4"), "min_alt", UINT32_MAX);
+    const uint32_t min_ref = (uint32_t)parse_num(get("min_ref", "4"), "min_ref", UINT32_MAX);
+    const uint32_t restarts = (uint32_t)parse_num(get("restarts", "100"), "restarts", UINT32_MAX);
+    const bool known_cells = vals.count("known_cell_assignments") > 0, known_gt = vals.count("known_genotypes") > 0;
+    if (known_gt && known_cells) die("thread 'main' panicked: Cannot set both known_genotypes and known_cell_assignments", 101);
+    const std::string init = get("initialization_strategy", "random_uniform");
+    if (init != "kmeans++" && init != "random_uniform" && init != "random_cell_assignment" && init != "middle_variance")
+        die("thread 'main' panicked: initialization strategy must be one of kmeans++, random_uniform, random_cell_assignment, middle_variance", 101);
+    const uint64_t threads = parse_num(get("threads", "1"), "threads", 1u << 20);
+    const uint8_t seed = (uint8_t)parse_num(get("seed", "4"), "seed", 255);
+    const uint32_t min_ref_umis = (uint32_t)parse_num(get("min_ref_umis", "0"), "min_ref_umis", UINT32_MAX);
+    const uint32_t min_alt_umis = (uint32_t)parse_num(get("min_alt_umis", "0"), "min_alt_umis", UINT32_MAX);
+    const std::string method_s = get("clustering_method", "em");
+    if (method_s != "em" && method_s != "khm") die("thread 'main' panicked: Clustering method must be one of em, khm", 101);
+    const std::string s3_s = get("souporcell3", "false");
+    if (s3_s != "true" && s3_s != "false") die("thread 'main' panicked: provided string was not `true` or `false`", 101);
+    const bool s3 = s3_s == "true";
+    if (k > 16 && (method_s == "em" || !s3))   // S:831-833
+        fprintf(stderr, "For k > 16, using souporcell3 (with '-s true' flag) is recommended with khm clustering method (with '-m khm' flag)\n");
+    if (k == 0 || threads == 0) die("thread 'main' panicked: num_clusters and threads must be positive (the reference divides by them)", 101);
+    // initialisation paths: S:485-498
+    if (known_gt) die("thread 'main' panicked: --known_genotypes initialisation is not built in this release (SURVEY 8f-3)", 101);
+    if (known_cells) die("thread 'main' panicked: known cell assignments not yet implemented", 101);   // S:545
+    if (init == "kmeans++") die("thread 'main' panicked: kmeans++ not yet implemented", 101);           // S:550
+    if (init == "middle_variance") die("thread 'main' panicked: middle variance not yet implemented", 101);   // S:597
+    if (init == "random_cell_assignment") die("thread 'main' panicked: random_cell_assignment initialisation is not built in this release (SURVEY 8f-3)", 101);
+
+    // ---- load_barcodes S:707-718, load_cell_data S:601-681
+    char* bc_blob = nullptr;
+    uint64_t n_bc = 0;
+    if (soup_barcodes_load(barcodes_path.c_str(), &bc_blob, &n_bc) != SOUP_OK) die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    if (n_bc > 200000)
+        fprintf(stderr, "More than 200_000 barcodes in barcodes file? is this the filtered barcode file? (do not use raw barcode file)\n");
+    soup_mtx* m = nullptr;
+    if (soup_mtx_load(alt_mtx.c_str(), ref_mtx.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, &m) != SOUP_OK)
+        die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    fprintf(stderr, "total loci used %llu\n", (unsigned long long)m->n_loci);   // S:678
+
+    // ---- GPUs
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) die("souporcell (soupgpu): no CUDA device available; this build has no CPU fallback", 101);
+    int n_gpu = vals.count("gpus") ? (int)parse_num(get("gpus", "1"), "gpus", 1024) : visible;
+    if (n_gpu < 1 || n_gpu > visible) die("souporcell (soupgpu): --gpus out of range", 1);
+    const uint64_t spt = (restarts + threads - 1) / threads;
+    if ((uint64_t)n_gpu > threads * spt) n_gpu = (int)std::max<uint64_t>(1, threads * spt);
+    std::vector<soup_ctx*> ctxs(n_gpu, nullptr);
+    for (int g = 0; g < n_gpu; ++g) {
+        if (soup_ctx_create(g, nullptr, &ctxs[g]) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
+        if (soup_load_csr(ctxs[g], m->n_cells, m->n_loci, m->nnz, m->row_ptr, m->locus, m->alt, m->ref) != SOUP_OK)
+            die(std::string("souporcell (soupgpu): ") + soup_last_error(ctxs[g]), 101);
+    }
+
+    // ---- souporcell_main S:60-148
+    soup_main_params mp{};
+    mp.k = (int32_t)k; mp.method = method_s == "khm" ? SOUP_METHOD_KHM : SOUP_METHOD_EM;
+    mp.restarts = restarts; mp.threads = (uint32_t)threads; mp.seed = seed; mp.souporcell3 = s3 ? 1 : 0;
+    mp.max_slots = (int32_t)parse_num(get("max_slots", "0"), "max_slots", 1024);
+    const bool quiet = vals.count("quiet_iterations") > 0;
+    mp.record_counts = quiet ? 0 : 1; mp.verbose_trace = quiet ? 0 : 1;
+    std::vector<float> best_lp((size_t)m->n_cells * k);
+    soup_main_result res{};
+    res.best_log_probs = best_lp.data();
+    if (soup_main(ctxs.data(), n_gpu, &mp, &res, stderr) != SOUP_OK) die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    fprintf(stderr, "soupgpu\tgpus\t%d\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, res.solve_ms, (unsigned long long)res.nnz_updates);
+    // zip(barcodes, best_log_probabilities): an empty best (nothing beat -inf) prints nothing (S:133)
+    if (res.has_best && soup_write_clusters(stdout, bc_blob, n_bc, best_lp.data(), m->n_cells, (int32_t)k) != SOUP_OK)
+        die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    if (fflush(stdout) != 0) die("thread 'main' panicked: failed printing to stdout", 101);
+    for (soup_ctx* c : ctxs) soup_ctx_destroy(c);
+    soup_mtx_free(m);
+    soup_free(bc_blob);
+    return 0;
+}
