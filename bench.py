@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the souporcell clustering hot path (EM / KHM restarts) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2]
+
+One "step" is one complete clustering job of BASELINE.json's config (default configs[1]:
+EM, k=8, 10k cells x 50k loci, 50 restarts per GPU) on synthetic vartrix-shaped data:
+every restart runs its 9 annealing steps to convergence.  The metric is E+M nnz-updates/s
+(1 update = one stored (cell, locus) entry carried through one E+M iteration of one solve).
+
+  value   : whole-job nnz-updates/s with the CSR already resident in HBM (device time, CUDA events)
+  e2e     : same metric through the public API from HOST buffers: CSR upload (+ CSC transpose on the
+            GPU) + solve + best log-probs/centers read back, every step
+  roofline: the dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the CPU oracle (C++ restatement of the Rust reference, which cannot
+            be built here: no cargo/rustc) on the host cores, bounded sample of the same workload.
+
+N > 1 (torchrun, one rank per GPU): restarts shard across ranks with no data-path collective
+(weak scaling: 50 restarts per GPU); ranks only exchange the winner once per run.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from souporcell_b200 import synth  # noqa: E402
+
+METRIC = "E+M nnz-updates/s (clustering hot path)"
+UNIT = "nnz-updates/s"
+
+
+def workload(config: int):
+    c = dict(synth.CONFIGS[config])
+    v = synth.generate_config(config)
+    row_ptr, locus, alt, ref, i2l = synth.filter_to_csr(v)
+    return c, (v.n_cells, int(i2l.shape[0]), row_ptr, locus, alt, ref)
+
+
+def algorithmic_bytes(nnz, K, L, N):
+    """compulsory HBM bytes per solve-iteration, split by pass."""
+    e = 8 * nnz + 8 * K * L + 4 * K * N + 12 * N
+    m = 8 * nnz + 4 * K * N + 8 * K * L + 4 * L
+    return e, m
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if mx and x > 0.3 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- reference arm (CPU oracle)
+def run_oracle_sample(csr, cfg, cores, budget_s):
+    """Time the CPU oracle's souporcell_main on a bounded sample: `cores` restarts (one per thread),
+    iteration cap chosen so the sample costs about `budget_s` seconds.  Returns (updates/s, desc, secs)."""
+    from oracle import oracle_py as orc
+
+    od = orc.OracleData.from_csr(*csr)
+    method = 1 if cfg["method"] == "khm" else 0
+    t0 = time.perf_counter()
+    r = od.main(cfg["k"], method=method, restarts=cores, threads=cores, seed=4, iteration_cap=1)
+    t1 = time.perf_counter() - t0                       # one iteration per thread (all threads in parallel)
+    cap = int(max(1, min(1000, budget_s / max(t1, 1e-3))))
+    if cap > 1:
+        t0 = time.perf_counter()
+        r = od.main(cfg["k"], method=method, restarts=cores, threads=cores, seed=4, iteration_cap=cap)
+        t1 = time.perf_counter() - t0
+    rate = r["nnz_updates"] / t1
+    return rate, f"{cores} restarts (1 per thread) x iteration_cap {cap} of the same matrix, {r['nnz_updates']} nnz-updates in {t1:.1f}s", t1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, csr = workload(args.config)
+    cores = os.cpu_count() or 1
+    budget = max(2.0, min(25.0, 150.0 / (args.steps + args.warmup)))
+    vals, desc = [], ""
+    for i in range(args.warmup + args.steps):
+        rate, desc, secs = run_oracle_sample(csr, cfg, cores, budget)
+        if i >= args.warmup:
+            vals.append((rate, secs))
+    value = float(np.mean([v for v, _ in vals]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean([s for _, s in vals]) * 1e3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, cfg, csr, restarts_per_gpu=cfg["restarts"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = C++ restatement of souporcell/src/main.rs (oracle/); the Rust binary cannot be built in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, cfg, csr, restarts_per_gpu):
+    n, L, row_ptr, locus, _, _ = csr
+    return {"workload": f"BASELINE.json configs[{args.config - 1}]: {cfg['method'].upper()} k={cfg['k']}, {n} cells x {cfg['n_loci']} loci "
+                        f"({L} after the min_alt/min_ref=4 filter), nnz={int(locus.shape[0])}, {restarts_per_gpu} restarts per GPU, synthetic vartrix (seed {synth.BASE_SEED + args.config})",
+            "k": cfg["k"], "method": cfg["method"], "cells": n, "loci_used": L, "nnz": int(locus.shape[0]),
+            "restarts_per_gpu": restarts_per_gpu, "sharding": "restarts (solve mod world), no data-path collective",
+            "l2": "inputs larger than L2 (tables+weights of the resident restarts) and a 512 MB L2 flush between steps"}
+
+
+# ---------------------------------------------------------------------------------- our arm
+def ours(args):
+    import torch
+    import souporcell_b200 as sp
+    from souporcell_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg, csr = workload(args.config)
+    n, L, row_ptr, locus, alt, ref = csr
+    nnz, K = int(locus.shape[0]), cfg["k"]
+    method = sp.METHOD_KHM if cfg["method"] == "khm" else sp.METHOD_EM
+    restarts = cfg["restarts"] * world                       # weak scaling: fixed restarts per GPU
+    stream = torch.cuda.Stream()                            # a real (non-NULL) stream: the library launches on it,
+    torch.cuda.set_stream(stream)                           # so torch.cuda.Event brackets the library's kernels
+    ctx = sp.Context(local, stream=stream.cuda_stream)
+    ctx.load_csr(*csr)
+    cb = api.torch_exchange_callbacks(dist) if world > 1 else (None, None)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def job(time_kernels=False):
+        return sp.main(ctx, K, method=method, restarts=restarts, threads=restarts, seed=4, time_kernels=time_kernels,
+                       proc_rank=rank, proc_world=world, allgather=cb[0], bcast=cb[1])
+
+    def timed(fn):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        out = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_dev, ms_wall = e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3
+        t = torch.tensor([ms_dev, ms_wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t[0]), float(t[1])
+
+    def total(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t[0])
+
+    # ---- device-resident leg ("value")
+    for _ in range(args.warmup):
+        timed(job)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms = wall_ms = updates = launches = 0.0
+    em = [0.0, 0.0, 0, 0]
+    for _ in range(args.steps):
+        r, ms_d, ms_w = timed(lambda: job(time_kernels=True))
+        dev_ms += ms_d; wall_ms += ms_w
+        updates += total(r.nnz_updates); launches += total(r.kernel_launches)
+        em[0] += r.estep_ms; em[1] += r.mstep_ms; em[2] += r.timed_iterations; em[3] += r.slot_iterations
+    clocks = sampler.stop() if rank == 0 else None
+    value = updates / (dev_ms * 1e-3)
+
+    # ---- end-to-end leg: host CSR -> upload + transpose -> solve -> results on the host, every step
+    def e2e_job():
+        ctx.load_csr(*csr)
+        return job()
+    for _ in range(min(args.warmup, 1)):
+        timed(e2e_job)
+    e_ms = e_upd = 0.0
+    for _ in range(args.steps):
+        r, ms_d, ms_w = timed(e2e_job)
+        e_ms += ms_w; e_upd += total(r.nnz_updates)       # wall clock: includes host-side packing and copies
+    h2d = (n + 1) * 8 + nnz * 12 + restarts // world * 32
+    d2h = n * K * 4 + K * L * 4
+
+    if rank == 0:
+        be, bm = algorithmic_bytes(nnz, K, L, n)
+        peak, peak_src = measured_peak()
+        kern, k_ms, k_bytes = ("estep_kernel", em[0], be) if em[0] >= em[1] else ("mstep_kernel", em[1], bm)
+        per_launch_bytes = k_bytes * em[3] / max(em[2], 1)            # active solves per launch x bytes per solve-iteration
+        achieved = per_launch_bytes / (k_ms / max(em[2], 1) * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args, cfg, csr, cfg["restarts"]),
+            "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks,
+            "e2e": {"value": e_upd / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": per_launch_bytes,
+                         "avg_launch_ms": k_ms / max(em[2], 1), "estep_ms": em[0], "mstep_ms": em[1], "launches_timed": em[2],
+                         "whole_step": {"bytes_per_nnz_update": (be + bm) / nnz, "achieved": value * (be + bm) / nnz / 1e9,
+                                        "frac": value * (be + bm) / nnz / 1e9 / peak}},
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rate, desc, _ = run_oracle_sample(csr, cfg, cores, 15.0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config number (1-based)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from souporcell_b200 import build
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        build.build_all()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,7 @@ typedef struct soup_solve_params {
     int32_t record_counts;     /* also record clusters-with->200-cells per iteration (S:252-263) */
     int32_t keep_trace;        /* copy the per-iteration trace back (soup_get_trace) */
     int32_t poll_chunk;        /* iterations enqueued between host polls of the done counter; 0 = 4 */
+    int32_t time_kernels;      /* bracket each iteration's E and M launches with CUDA events (soup_get_stats) */
     /* multi-GPU restart sharding: this process runs solves with (solve % world) == rank */
     int32_t shard_rank, shard_world; /* world 0 or 1 = no sharding */
 } soup_solve_params;
@@ -150,6 +151,8 @@ typedef struct soup_stats {
     uint64_t kernel_launches;   /* kernels launched by the last soup_solve / hook call */
     uint64_t estep_launches, mstep_launches;
     double solve_ms;            /* CUDA-event duration of the whole solve loop */
+    double estep_ms, mstep_ms;  /* summed CUDA-event durations of the E / M launches (time_kernels = 1), else 0 */
+    uint64_t timed_iterations;  /* launches of each kind covered by estep_ms / mstep_ms */
     uint64_t slot_iterations;   /* sum over launches of active solves (= sum of iterations) */
     int32_t slots, lanes, groups, padded_cols;
     uint64_t h2d_bytes, d2h_bytes; /* copies made by the last load / solve call */
@@ -190,7 +193,7 @@ typedef struct soup_main_params {
     uint8_t seed;
     int32_t souporcell3;
     int32_t iteration_cap; /* 0 -> 1000 */
-    int32_t max_slots, lanes, record_counts, verbose_trace;
+    int32_t max_slots, lanes, record_counts, verbose_trace, time_kernels;
     int32_t proc_rank, proc_world;   /* process-level shard; world 0/1 = single process */
     soup_allgather_fn allgather;     /* required when proc_world > 1 */
     soup_bcast_fn bcast;
@@ -203,7 +206,10 @@ typedef struct soup_main_result {
     float* best_theta;     /* host [k][n_loci], caller-allocated, may be NULL */
     uint64_t nnz_updates;  /* over the solves this process ran */
     uint64_t kernel_launches;
+    uint64_t slot_iterations; /* solve-iterations executed (sum over E launches of the active slots) */
+    uint64_t timed_iterations;
     double solve_ms;       /* sum over runs of the slowest context's device time */
+    double estep_ms, mstep_ms; /* context 0, time_kernels = 1 */
 } soup_main_result;
 int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_main_params* p, soup_main_result* r, void* log_file);
 

@@ -20,7 +20,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsoupgpu.so")
+LIB_PATH = os.environ.get("SOUP_LIB") or os.path.join(_HERE, "lib", "libsoupgpu.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 METHOD_EM, METHOD_KHM = 0, 1
@@ -52,7 +52,7 @@ class _SolveParams(C.Structure):
                 ("stream_seeds", C.c_void_p), ("theta0", C.c_void_p), ("base_theta", C.c_void_p),
                 ("reinit_clusters", C.c_void_p), ("n_reinit", C.c_int32), ("iteration_cap", C.c_int32),
                 ("max_slots", C.c_int32), ("lanes", C.c_int32), ("record_counts", C.c_int32), ("keep_trace", C.c_int32),
-                ("poll_chunk", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
+                ("poll_chunk", C.c_int32), ("time_kernels", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
 
 
 class _SolveResult(C.Structure):
@@ -67,7 +67,8 @@ class _IterRecord(C.Structure):
 
 class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("estep_launches", C.c_uint64), ("mstep_launches", C.c_uint64),
-                ("solve_ms", C.c_double), ("slot_iterations", C.c_uint64), ("slots", C.c_int32), ("lanes", C.c_int32),
+                ("solve_ms", C.c_double), ("estep_ms", C.c_double), ("mstep_ms", C.c_double), ("timed_iterations", C.c_uint64),
+                ("slot_iterations", C.c_uint64), ("slots", C.c_int32), ("lanes", C.c_int32),
                 ("groups", C.c_int32), ("padded_cols", C.c_int32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
@@ -78,7 +79,7 @@ BCAST_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32)
 class _MainParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("method", C.c_int32), ("restarts", C.c_uint32), ("threads", C.c_uint32),
                 ("seed", C.c_uint8), ("souporcell3", C.c_int32), ("iteration_cap", C.c_int32), ("max_slots", C.c_int32),
-                ("lanes", C.c_int32), ("record_counts", C.c_int32), ("verbose_trace", C.c_int32),
+                ("lanes", C.c_int32), ("record_counts", C.c_int32), ("verbose_trace", C.c_int32), ("time_kernels", C.c_int32),
                 ("proc_rank", C.c_int32), ("proc_world", C.c_int32), ("allgather", ALLGATHER_FN), ("bcast", BCAST_FN),
                 ("comm_user", C.c_void_p)]
 
@@ -86,7 +87,8 @@ class _MainParams(C.Structure):
 class _MainResult(C.Structure):
     _fields_ = [("has_best", C.c_int32), ("runs", C.c_int32), ("best_loss", C.c_float), ("best_log_probs", C.c_void_p),
                 ("best_theta", C.c_void_p), ("nnz_updates", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("solve_ms", C.c_double)]
+                ("slot_iterations", C.c_uint64), ("timed_iterations", C.c_uint64), ("solve_ms", C.c_double),
+                ("estep_ms", C.c_double), ("mstep_ms", C.c_double)]
 
 
 _lib = None
@@ -323,7 +325,7 @@ class Context:
 
     def solve(self, k, method=METHOD_EM, n_streams=1, solves_per_stream=1, stream_seeds=None, theta0=None,
               base_theta=None, reinit_clusters=None, iteration_cap=0, max_slots=0, lanes=0, record_counts=False,
-              keep_trace=False, poll_chunk=0, shard_rank=0, shard_world=1) -> SolveResult:
+              keep_trace=False, poll_chunk=0, time_kernels=False, shard_rank=0, shard_world=1) -> SolveResult:
         n_solves = n_streams * solves_per_stream
         p = _SolveParams()
         p.k, p.method, p.n_streams, p.solves_per_stream = k, method, n_streams, solves_per_stream
@@ -347,7 +349,7 @@ class Context:
             p.n_reinit = rc_.shape[0]
         p.iteration_cap, p.max_slots, p.lanes = iteration_cap, max_slots, lanes
         p.record_counts, p.keep_trace, p.poll_chunk = int(record_counts), int(keep_trace), poll_chunk
-        p.shard_rank, p.shard_world = shard_rank, shard_world
+        p.shard_rank, p.shard_world, p.time_kernels = shard_rank, shard_world, int(time_kernels)
         r = _SolveResult()
         lp = np.zeros((self.n_cells, k), dtype=np.float32)
         th = np.zeros((k, self.n_loci), dtype=np.float32)
@@ -404,6 +406,10 @@ class MainResult:
     nnz_updates: int
     kernel_launches: int
     solve_ms: float
+    slot_iterations: int = 0
+    timed_iterations: int = 0
+    estep_ms: float = 0.0
+    mstep_ms: float = 0.0
 
     @property
     def assignments(self) -> np.ndarray:
@@ -412,7 +418,8 @@ class MainResult:
 
 
 def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3=False, iteration_cap=0, max_slots=0,
-         lanes=0, record_counts=False, verbose_trace=False, proc_rank=0, proc_world=1, allgather=None, bcast=None) -> MainResult:
+         lanes=0, record_counts=False, verbose_trace=False, time_kernels=False, proc_rank=0, proc_world=1, allgather=None,
+         bcast=None) -> MainResult:
     """souporcell_main S:60-131 over one context per GPU (restart-sharded)."""
     if isinstance(ctxs, Context):
         ctxs = [ctxs]
@@ -420,7 +427,7 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
     p = _MainParams()
     p.k, p.method, p.restarts, p.threads, p.seed = k, method, restarts, threads, seed
     p.souporcell3, p.iteration_cap, p.max_slots, p.lanes = int(souporcell3), iteration_cap, max_slots, lanes
-    p.record_counts, p.verbose_trace = int(record_counts), int(verbose_trace)
+    p.record_counts, p.verbose_trace, p.time_kernels = int(record_counts), int(verbose_trace), int(time_kernels)
     p.proc_rank, p.proc_world = proc_rank, proc_world
     if allgather is not None:
         p.allgather = allgather
@@ -432,7 +439,8 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
     r = _MainResult()
     r.best_log_probs, r.best_theta = _ptr(lp), _ptr(th)
     _check(lib().soup_main(arr, len(ctxs), C.byref(p), C.byref(r), None))
-    return MainResult(bool(r.has_best), r.runs, float(r.best_loss), lp, th, int(r.nnz_updates), int(r.kernel_launches), float(r.solve_ms))
+    return MainResult(bool(r.has_best), r.runs, float(r.best_loss), lp, th, int(r.nnz_updates), int(r.kernel_launches), float(r.solve_ms),
+                      int(r.slot_iterations), int(r.timed_iterations), float(r.estep_ms), float(r.mstep_ms))
 
 
 def torch_exchange_callbacks(dist):

@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -30,7 +32,7 @@ void pinned_free(void* p) { if (p) cudaFreeHost(p); }
 struct Workspace {
     int K = 0, slots = 0, V = 0, GW = 0, n_groups = 0, iter_cap = 0, queue_cap = 0;
     uint32_t Cpad = 0;
-    float *LA = nullptr, *LB = nullptr, *TH = nullptr, *ELL = nullptr, *W = nullptr, *LSE = nullptr;
+    float *LA = nullptr, *LB = nullptr, *TH = nullptr, *ELL = nullptr, *W = nullptr, *LSE = nullptr, *loss = nullptr;
     SlotState* st = nullptr;
     Ctl* ctl = nullptr;
     uint8_t *col_write = nullptr, *k_locked = nullptr;
@@ -45,14 +47,18 @@ struct Workspace {
 
 struct soup_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;   // side: loss + control, concurrent with the M pass
     bool own_stream = false;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int sm_count = 0;
     // matrix
     uint64_t N = 0, L = 0, nnz = 0;
     uint64_t *d_row_ptr = nullptr, *d_col_ptr = nullptr;
-    uint4 *d_csr = nullptr, *d_csc = nullptr;
+    uint32_t *d_csr_idx = nullptr, *d_csc_idx = nullptr;
+    float4* d_csr_aux = nullptr;
+    float2* d_csc_aux = nullptr;
+    Packing pk_csr{}, pk_csc{};
     uint32_t *d_cell_order = nullptr, *d_locus_order = nullptr;
     float* d_total_alleles = nullptr;
     bool loaded = false;
@@ -65,6 +71,7 @@ struct soup_ctx {
     std::vector<int> h_trace_solve, h_trace_iters;
     int h_trace_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_k;   // per-iteration E / M brackets (time_kernels)
 
     int32_t fail(int32_t code, const char* fmt, ...) {
         va_list ap;
@@ -97,10 +104,12 @@ static cudaError_t ws_alloc(Workspace& w, T** p, size_t count, bool zero) {
 }
 
 static void free_matrix(soup_ctx* ctx) {
-    cudaFree(ctx->d_row_ptr); cudaFree(ctx->d_col_ptr); cudaFree(ctx->d_csr); cudaFree(ctx->d_csc);
+    cudaFree(ctx->d_row_ptr); cudaFree(ctx->d_col_ptr); cudaFree(ctx->d_csr_idx); cudaFree(ctx->d_csc_idx);
+    cudaFree(ctx->d_csr_aux); cudaFree(ctx->d_csc_aux);
     cudaFree(ctx->d_cell_order); cudaFree(ctx->d_locus_order); cudaFree(ctx->d_total_alleles);
     ctx->d_row_ptr = ctx->d_col_ptr = nullptr;
-    ctx->d_csr = ctx->d_csc = nullptr;
+    ctx->d_csr_idx = ctx->d_csc_idx = nullptr;
+    ctx->d_csr_aux = nullptr; ctx->d_csc_aux = nullptr;
     ctx->d_cell_order = ctx->d_locus_order = nullptr;
     ctx->d_total_alleles = nullptr;
     ctx->loaded = false;
@@ -138,6 +147,9 @@ extern "C" int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx**
         }
         ctx->own_stream = true;
     }
+    cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaEventCreateWithFlags(&ctx->ev_poll[0], cudaEventDisableTiming);
@@ -170,6 +182,10 @@ extern "C" void soup_ctx_destroy(soup_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->ev_poll) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_k) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -179,8 +195,8 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
                                  const uint32_t* locus, const uint32_t* alt, const uint32_t* ref) {
     if (!ctx) return SOUP_ERR_INVALID;
     if (!row_ptr || (nnz_in && (!locus || !alt || !ref))) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: null pointer");
-    if (n_cells >= INT32_MAX || n_loci >= INT32_MAX || nnz_in >= INT32_MAX)
-        return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_load_csr: dimensions above 2^31-1 are not supported");
+    if (n_cells >= (1u << 30) || n_loci >= (1u << 30) || nnz_in >= INT32_MAX)
+        return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_load_csr: more than 2^30 cells / loci or 2^31 entries are not supported");
     if (row_ptr[0] != 0 || row_ptr[n_cells] != nnz_in) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: row_ptr does not span [0, nnz]");
     CK(cudaSetDevice(ctx->device));
     ctx->stats = soup_stats{};
@@ -217,6 +233,27 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     free_matrix(ctx);
     ws_free(ctx->ws);
     ctx->N = n_cells; ctx->L = n_loci; ctx->nnz = nnz;
+    // packed entry words: index bits as needed, the rest split between the two count fields (<= 6 bits each)
+    auto make_packing = [](uint64_t n_index) {
+        uint32_t ib = 1;
+        while ((1ull << ib) < std::max<uint64_t>(n_index, 2)) ++ib;
+        Packing pk;
+        pk.cbits = std::min<uint32_t>(6, (32 - ib) / 2);
+        pk.cmask = (1u << pk.cbits) - 1;
+        pk.sh_a = 32 - pk.cbits;
+        pk.sh_r = 32 - 2 * pk.cbits;
+        pk.imask = (1u << pk.sh_r) - 1;
+        return pk;
+    };
+    ctx->pk_csr = make_packing(n_loci);
+    ctx->pk_csc = make_packing(n_cells);
+    {   // ln_binomial table for in-field counts (statrs FCACHE arithmetic, S:669-670)
+        std::vector<float> tab(4096, 0.0f);
+        const uint32_t cb = ctx->pk_csr.cbits;
+        for (uint32_t a = 0; a < (1u << cb); ++a)
+            for (uint32_t r = 0; r < (1u << cb); ++r) tab[(a << cb) | r] = ln_binomial_f32(a + r, a);
+        CK(cudaMemcpyToSymbol(c_lbc, tab.data(), tab.size() * sizeof(float)));
+    }
     cudaStream_t st = ctx->stream;
     const size_t nz = std::max<uint64_t>(nnz, 1);
     uint32_t *d_locus = nullptr, *d_alt = nullptr, *d_ref = nullptr, *d_vals = nullptr, *d_vals2 = nullptr, *d_len = nullptr, *d_len2 = nullptr, *d_idx = nullptr;
@@ -233,8 +270,10 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     } while (0)
     CKL(cudaMalloc(&ctx->d_row_ptr, (n_cells + 1) * sizeof(uint64_t)));
     CKL(cudaMalloc(&ctx->d_col_ptr, (n_loci + 1) * sizeof(uint64_t)));
-    CKL(cudaMalloc(&ctx->d_csr, nz * sizeof(uint4)));
-    CKL(cudaMalloc(&ctx->d_csc, nz * sizeof(uint4)));
+    CKL(cudaMalloc(&ctx->d_csr_idx, nz * sizeof(uint32_t)));
+    CKL(cudaMalloc(&ctx->d_csc_idx, nz * sizeof(uint32_t)));
+    CKL(cudaMalloc(&ctx->d_csr_aux, nz * sizeof(float4)));
+    CKL(cudaMalloc(&ctx->d_csc_aux, nz * sizeof(float2)));
     CKL(cudaMalloc(&ctx->d_cell_order, std::max<uint64_t>(n_cells, 1) * sizeof(uint32_t)));
     CKL(cudaMalloc(&ctx->d_locus_order, std::max<uint64_t>(n_loci, 1) * sizeof(uint32_t)));
     CKL(cudaMalloc(&ctx->d_total_alleles, std::max<uint64_t>(n_cells, 1) * sizeof(float)));
@@ -251,8 +290,8 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     }
     ctx->stats.h2d_bytes = (n_cells + 1) * 8 + nnz * 12;
     if (n_cells) {
-        build_csr_kernel<<<(unsigned)((n_cells + 7) / 8), 256, 0, st>>>(ctx->d_row_ptr, d_locus, d_alt, d_ref, ctx->d_csr, d_keys, d_vals,
-                                                                        ctx->d_total_alleles, d_len, (uint32_t)n_cells);
+        build_csr_kernel<<<(unsigned)((n_cells + 7) / 8), 256, 0, st>>>(ctx->d_row_ptr, d_locus, d_alt, d_ref, ctx->d_csr_idx, ctx->d_csr_aux, d_keys,
+                                                                        d_vals, ctx->d_total_alleles, ctx->pk_csr, (uint32_t)n_cells);
         CKL(cudaGetLastError());
     }
     if (!big_idx.empty()) {   // ln_binomial for n > 170 comes from the host (statrs ln_gamma branch)
@@ -262,7 +301,7 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
         if (e2 != cudaSuccess) { cudaFree(d_bi); CKL(e2); }
         cudaMemcpyAsync(d_bi, big_idx.data(), big_idx.size() * 4, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_bv, big_val.data(), big_val.size() * 4, cudaMemcpyHostToDevice, st);
-        patch_lbc_kernel<<<(unsigned)((big_idx.size() + 255) / 256), 256, 0, st>>>(ctx->d_csr, d_bi, d_bv, (uint32_t)big_idx.size());
+        patch_lbc_kernel<<<(unsigned)((big_idx.size() + 255) / 256), 256, 0, st>>>(ctx->d_csr_aux, d_bi, d_bv, (uint32_t)big_idx.size());
         cudaStreamSynchronize(st);
         cudaFree(d_bi); cudaFree(d_bv);
         CKL(cudaGetLastError());
@@ -282,7 +321,7 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     CKL(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
     if (nnz) {
         CKL(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, kb, vb, (int)nnz, 0, bits_total, st));
-        build_csc_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(kb.Current(), vb.Current(), d_alt, d_ref, ctx->d_csc, nnz);
+        build_csc_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(kb.Current(), vb.Current(), d_alt, d_ref, ctx->d_csc_idx, ctx->d_csc_aux, ctx->pk_csc, nnz);
         CKL(cudaGetLastError());
     }
     col_ptr_kernel<<<(unsigned)((n_loci + 1 + 255) / 256), 256, 0, st>>>(kb.Current(), nnz, ctx->d_col_ptr, (uint32_t)n_loci);
@@ -326,14 +365,16 @@ extern "C" int32_t soup_get_csc(soup_ctx* ctx, uint64_t* col_ptr, uint32_t* cell
     CK(cudaSetDevice(ctx->device));
     if (col_ptr) CK(cudaMemcpy(col_ptr, ctx->d_col_ptr, (ctx->L + 1) * 8, cudaMemcpyDeviceToHost));
     if (cell || alt || ref) {
-        std::vector<uint4> h(ctx->nnz);
-        if (ctx->nnz) CK(cudaMemcpy(h.data(), ctx->d_csc, ctx->nnz * sizeof(uint4), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> hi(ctx->nnz);
+        std::vector<float2> hx(ctx->nnz);
+        if (ctx->nnz) {
+            CK(cudaMemcpy(hi.data(), ctx->d_csc_idx, ctx->nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(hx.data(), ctx->d_csc_aux, ctx->nnz * sizeof(float2), cudaMemcpyDeviceToHost));
+        }
         for (uint64_t i = 0; i < ctx->nnz; ++i) {
-            float a, t;
-            memcpy(&a, &h[i].y, 4); memcpy(&t, &h[i].z, 4);
-            if (cell) cell[i] = h[i].x;
-            if (alt) alt[i] = (uint32_t)a;
-            if (ref) ref[i] = (uint32_t)t - (uint32_t)a;
+            if (cell) cell[i] = hi[i] & ctx->pk_csc.imask;
+            if (alt) alt[i] = (uint32_t)hx[i].x;
+            if (ref) ref[i] = (uint32_t)hx[i].y - (uint32_t)hx[i].x;
         }
     }
     return SOUP_OK;
@@ -347,9 +388,9 @@ extern "C" int32_t soup_get_cell_totals(soup_ctx* ctx, float* total_alleles) {
 extern "C" int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc) {
     if (!ctx || !ctx->loaded || !lbc) return ctx ? ctx->fail(SOUP_ERR_INVALID, "no matrix loaded") : SOUP_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    std::vector<uint4> h(ctx->nnz);
-    if (ctx->nnz) CK(cudaMemcpy(h.data(), ctx->d_csr, ctx->nnz * sizeof(uint4), cudaMemcpyDeviceToHost));
-    for (uint64_t i = 0; i < ctx->nnz; ++i) memcpy(&lbc[i], &h[i].w, 4);
+    std::vector<float4> h(ctx->nnz);
+    if (ctx->nnz) CK(cudaMemcpy(h.data(), ctx->d_csr_aux, ctx->nnz * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < ctx->nnz; ++i) lbc[i] = h[i].z;
     return SOUP_OK;
 }
 
@@ -376,7 +417,7 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int V, int iter
     auto A = [&](auto** p, size_t n, bool zero) { if (e == cudaSuccess) e = ws_alloc(w, p, n, zero); };
     A(&w.LA, L * w.Cpad, true); A(&w.LB, L * w.Cpad, true); A(&w.TH, L * w.Cpad, true);
     A(&w.ELL, N * w.Cpad, true); A(&w.W, N * w.Cpad, true); A(&w.LSE, N * slots, true);
-    A(&w.st, (size_t)slots, true); A(&w.ctl, 1, true);
+    A(&w.st, (size_t)slots, true); A(&w.ctl, 1, true); A(&w.loss, (size_t)slots, true);
     A(&w.col_write, w.Cpad, true); A(&w.k_locked, (size_t)K, true);
     A(&w.group_active, (size_t)w.n_groups, true); A(&w.counts, cols, true);
     A(&w.queue, (size_t)queue_cap, true); A(&w.draw_of_k, (size_t)K, true);
@@ -402,6 +443,7 @@ struct IterLaunch {
     int method;
     float log_prior, limit;
     bool record_counts;
+    int timed_iter = -1;   // >= 0: bracket this iteration's E and M launches with events ev_k[4*i .. 4*i+3]
     RefillArgs refill;
     FinalizeArgs fin;
 };
@@ -411,16 +453,16 @@ static void launch_e(soup_ctx* ctx, float log_prior) {
     Workspace& w = ctx->ws;
     const uint32_t bpg = (uint32_t)((ctx->N + EM_WARPS - 1) / EM_WARPS);
     if (bpg == 0) return;
-    estep_kernel<V><<<bpg * w.n_groups, EM_THREADS, 0, ctx->stream>>>(ctx->d_csr, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB, w.ELL,
-                                                                      w.group_active, w.ctl, (uint32_t)ctx->N, w.Cpad, bpg, log_prior);
+    estep_kernel<V><<<bpg * w.n_groups, EM_THREADS, 0, ctx->stream>>>(ctx->d_csr_idx, ctx->d_csr_aux, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB,
+                                                                      w.ELL, w.group_active, w.ctl, ctx->pk_csr, (uint32_t)ctx->N, w.Cpad, bpg, log_prior);
 }
 template <int V>
 static void launch_m(soup_ctx* ctx) {
     Workspace& w = ctx->ws;
     const uint32_t bpg = (uint32_t)((ctx->L + EM_WARPS - 1) / EM_WARPS);
     if (bpg == 0) return;
-    mstep_kernel<V><<<bpg * w.n_groups, EM_THREADS, 0, ctx->stream>>>(ctx->d_csc, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB,
-                                                                      w.col_write, w.group_active, w.ctl, (uint32_t)ctx->L, w.Cpad, bpg);
+    mstep_kernel<V><<<bpg * w.n_groups, EM_THREADS, 0, ctx->stream>>>(ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH,
+                                                                      w.LA, w.LB, w.col_write, w.group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, bpg);
 }
 static void launch_e(soup_ctx* ctx, float log_prior) {
     switch (ctx->ws.V) { case 4: launch_e<4>(ctx, log_prior); break; case 2: launch_e<2>(ctx, log_prior); break; default: launch_e<1>(ctx, log_prior); }
@@ -431,8 +473,7 @@ static void launch_m(soup_ctx* ctx) {
 static void launch_post(soup_ctx* ctx, int method, bool counts) {
     Workspace& w = ctx->ws;
     PostArgs a{w.ELL, w.W, w.LSE, ctx->d_total_alleles, w.st, counts ? w.counts : nullptr, (uint32_t)ctx->N, w.Cpad, w.K, w.slots, method};
-    const size_t n = (size_t)ctx->N * w.slots;
-    if (n) post_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
+    if (ctx->N) post_kernel<<<dim3((unsigned)((ctx->N + 127) / 128), (unsigned)w.slots), 128, 0, ctx->stream>>>(a);
 }
 static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
     Workspace& w = ctx->ws;
@@ -440,17 +481,34 @@ static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
     if (n) refill_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)w.slots), 256, 0, ctx->stream>>>(a);
 }
 
-static uint64_t launches_per_iteration(const soup_ctx* ctx) { (void)ctx; return 7; }
+static uint64_t launches_per_iteration(const soup_ctx* ctx) { (void)ctx; return 8; }
 
+static void launch_loss_control(soup_ctx* ctx, cudaStream_t st, bool counts, float limit) {
+    Workspace& w = ctx->ws;
+    loss_kernel<<<w.slots, 256, 0, st>>>(w.LSE, w.st, w.loss, (uint32_t)ctx->N);
+    ControlArgs c{w.loss, w.st, w.ctl, counts ? w.counts : nullptr, w.trace, w.solve_loss, w.solve_iters,
+                  (uint32_t)ctx->N, w.K, w.slots, w.iter_cap, limit};
+    control_kernel<<<1, std::min(1024, (w.slots + 31) / 32 * 32), 0, st>>>(c);
+}
+
+// E -> post -> { loss + control on the side stream  ||  M on the main stream } -> harvest -> refill -> finalize.
+// The M pass does not depend on the loss, so the strictly sequential loss sum hides behind it.
 static void enqueue_iteration(const IterLaunch& it) {
     soup_ctx* ctx = it.ctx;
     Workspace& w = ctx->ws;
+    cudaEvent_t* ev = it.timed_iter >= 0 ? ctx->ev_k.data() + (size_t)it.timed_iter * 4 : nullptr;
+    if (ev) cudaEventRecord(ev[0], ctx->stream);
     launch_e(ctx, it.log_prior);
+    if (ev) cudaEventRecord(ev[1], ctx->stream);
     launch_post(ctx, it.method, it.record_counts);
-    ControlArgs c{w.LSE, w.st, w.ctl, it.record_counts ? w.counts : nullptr, w.trace, w.solve_loss, w.solve_iters,
-                  (uint32_t)ctx->N, w.K, w.slots, w.iter_cap, it.limit};
-    control_kernel<<<1, std::min(1024, (w.slots + 31) / 32 * 32), 0, ctx->stream>>>(c);
+    cudaEventRecord(ctx->ev_fork, ctx->stream);
+    cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
+    launch_loss_control(ctx, ctx->side, it.record_counts, it.limit);
+    cudaEventRecord(ctx->ev_join, ctx->side);
+    if (ev) cudaEventRecord(ev[2], ctx->stream);
     launch_m(ctx);
+    if (ev) cudaEventRecord(ev[3], ctx->stream);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K);
     launch_refill(ctx, it.refill);
     finalize_kernel<<<1, 1024, 0, ctx->stream>>>(it.fin);
@@ -508,6 +566,17 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         slots = (int)std::min<size_t>((size_t)slots, std::max<size_t>(cap, 1));
     }
     slots = std::min(slots, 1024);
+    // table / weight rows are addressed with 32-bit element offsets
+    while (slots > 1 && (uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32)) --slots;
+    if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32))
+        return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: max(cells, loci) * k exceeds the 32-bit row-offset range");
+    if (p->max_slots <= 0 && p->lanes <= 0) {
+        // prefer a column count that fills whole 128-wide groups (4 columns per lane, 128-bit gathers)
+        int g = 128, a = K;
+        while (a) { int t = g % a; g = a; a = t; }          // gcd(128, K)
+        const int m = 128 / g, rounded = slots / m * m;
+        if (rounded > 0 && rounded * 8 >= slots * 7) slots = rounded;
+    }
     int V = p->lanes;
     if (V != 1 && V != 2 && V != 4) V = pick_lanes(slots * K);
     int32_t rc = ensure_workspace(ctx, K, slots, V, iter_cap, n_local, p->n_streams);
@@ -590,8 +659,20 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     const int chunk = p->poll_chunk > 0 ? p->poll_chunk : 4;
     uint64_t iters_enqueued = 0;
     int polls = 0;
+    const size_t max_timed = 4096;
+    if (p->time_kernels) {
+        while (ctx->ev_k.size() < max_timed * 4) {
+            cudaEvent_t e = nullptr;
+            CKS(cudaEventCreate(&e));
+            ctx->ev_k.push_back(e);
+        }
+    }
+    size_t n_timed = 0;
     auto enqueue_chunk = [&](int which) -> cudaError_t {
-        for (int i = 0; i < chunk; ++i) enqueue_iteration(it);
+        for (int i = 0; i < chunk; ++i) {
+            it.timed_iter = (p->time_kernels && n_timed < max_timed) ? (int)n_timed++ : -1;
+            enqueue_iteration(it);
+        }
         iters_enqueued += chunk;
         launches += (uint64_t)chunk * launches_per_iteration(ctx);
         cudaError_t e = cudaMemcpyAsync(ctx->h_ctl + which, w.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st);
@@ -649,6 +730,23 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     ctx->stats.estep_launches = iters_enqueued;
     ctx->stats.mstep_launches = iters_enqueued;
     ctx->stats.solve_ms = ms;
+    for (size_t i = 0; i < n_timed; ++i) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->ev_k[i * 4], ctx->ev_k[i * 4 + 1]);
+        cudaEventElapsedTime(&b, ctx->ev_k[i * 4 + 2], ctx->ev_k[i * 4 + 3]);
+        ctx->stats.estep_ms += a;
+        ctx->stats.mstep_ms += b;
+    }
+    ctx->stats.timed_iterations = n_timed;
+    if (getenv("SOUP_DEBUG_ITERS")) {
+        for (size_t i = 0; i < n_timed; ++i) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, ctx->ev_k[i * 4], ctx->ev_k[i * 4 + 1]);
+            cudaEventElapsedTime(&b, ctx->ev_k[i * 4 + 2], ctx->ev_k[i * 4 + 3]);
+            if (i + 1 < n_timed) cudaEventElapsedTime(&c, ctx->ev_k[i * 4], ctx->ev_k[i * 4 + 4]);
+            fprintf(stderr, "soup_debug iter %zu E %.3f ms M %.3f ms total %.3f ms\n", i, a, b, c);
+        }
+    }
     ctx->stats.slot_iterations = fc.slot_iterations;
     ctx->stats.slots = slots; ctx->stats.lanes = V; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     ctx->stats.h2d_bytes = h2d; ctx->stats.d2h_bytes = d2h;
@@ -680,6 +778,8 @@ extern "C" int32_t soup_get_stats(soup_ctx* ctx, soup_stats* out) {
 static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
     if (!ctx->loaded) return ctx->fail(SOUP_ERR_INVALID, "no matrix loaded (call soup_load_csr first)");
     if (k <= 0 || n_slots <= 0 || n_slots > 1024) return ctx->fail(SOUP_ERR_INVALID, "bad k / n_slots");
+    if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)n_slots * k + 128) >= (1ull << 32))
+        return ctx->fail(SOUP_ERR_UNSUPPORTED, "max(cells, loci) * columns exceeds the 32-bit row-offset range");
     int V = (lanes == 1 || lanes == 2 || lanes == 4) ? lanes : pick_lanes(n_slots * k);
     int32_t rc = ensure_workspace(ctx, k, n_slots, V, 1, n_slots, 1);
     if (rc != SOUP_OK) return rc;
@@ -729,8 +829,7 @@ extern "C" int32_t soup_estep(soup_ctx* ctx, int32_t k, int32_t method, int32_t 
     launch_post(ctx, method, true);
     std::vector<int> h_counts((size_t)n_slots * k);
     CKH(cudaMemcpyAsync(h_counts.data(), w.counts, h_counts.size() * 4, cudaMemcpyDeviceToHost, st));
-    ControlArgs c{w.LSE, w.st, w.ctl, nullptr, w.trace, w.solve_loss, w.solve_iters, (uint32_t)ctx->N, k, n_slots, 1, 0.01f * (float)ctx->N};
-    control_kernel<<<1, std::min(1024, (n_slots + 31) / 32 * 32), 0, st>>>(c);
+    launch_loss_control(ctx, st, false, 0.01f * (float)ctx->N);
     CKH(cudaGetLastError());
     if (log_probs && nlp) {
         plane_to_host_kernel<<<(unsigned)((nlp + 255) / 256), 256, 0, st>>>(w.ELL, d_out, (uint32_t)ctx->N, w.Cpad, k, n_slots, 1);
@@ -746,8 +845,7 @@ extern "C" int32_t soup_estep(soup_ctx* ctx, int32_t k, int32_t method, int32_t 
         std::vector<float> h((size_t)ctx->N * n_slots);
         CKH(cudaMemcpyAsync(h.data(), w.LSE, h.size() * 4, cudaMemcpyDeviceToHost, st));
         CKH(cudaStreamSynchronize(st));
-        for (int s = 0; s < n_slots; ++s)
-            for (uint64_t cidx = 0; cidx < ctx->N; ++cidx) lse[(size_t)s * ctx->N + cidx] = h[cidx * n_slots + s];
+        memcpy(lse, h.data(), h.size() * 4);
     }
     CKH(cudaMemcpyAsync(hst.data(), w.st, sizeof(SlotState) * n_slots, cudaMemcpyDeviceToHost, st));
     CKH(cudaStreamSynchronize(st));

@@ -65,6 +65,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
     StdRng master = StdRng::from_seed(seed);     // S:62
 
     r->has_best = 0; r->runs = 0; r->best_loss = -INFINITY; r->nnz_updates = 0; r->kernel_launches = 0; r->solve_ms = 0;
+    r->slot_iterations = 0; r->timed_iterations = 0; r->estep_ms = 0; r->mstep_ms = 0;
     std::vector<float> best_theta((size_t)K * n_loci);
     bool have_best = false;
     float best_loss = -INFINITY;
@@ -110,7 +111,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             sp.reinit_clusters = run > 0 ? bad.data() : nullptr;
             sp.n_reinit = run > 0 ? n_bad : 0;
             sp.iteration_cap = p->iteration_cap; sp.max_slots = p->max_slots; sp.lanes = p->lanes;
-            sp.record_counts = p->record_counts; sp.keep_trace = p->verbose_trace;
+            sp.record_counts = p->record_counts; sp.keep_trace = p->verbose_trace; sp.time_kernels = p->time_kernels;
             sp.shard_rank = prank * n_ctx + i; sp.shard_world = world;
             c.res.best_log_probs = c.lp.data(); c.res.best_theta = c.th.data();
             c.res.solve_loss = c.loss.data(); c.res.solve_iters = c.iters.data();
@@ -133,6 +134,8 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             run_ms = std::max(run_ms, pc[i].stats.solve_ms);
             r->nnz_updates += pc[i].res.nnz_updates;
             r->kernel_launches += pc[i].stats.kernel_launches;
+            r->slot_iterations += pc[i].stats.slot_iterations;
+            if (i == 0) { r->estep_ms += pc[i].stats.estep_ms; r->mstep_ms += pc[i].stats.mstep_ms; r->timed_iterations += pc[i].stats.timed_iterations; }
             for (int s = prank * n_ctx + i; s < n_solves; s += world) { loss[s] = pc[i].loss[s]; iters[s] = pc[i].iters[s]; mine[s] = 1; }
             if (better(pc[i].res.best_loss, pc[i].res.best_solve, pc[i].res.has_best != 0,
                        win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY, win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, win_ctx >= 0))

@@ -5,9 +5,10 @@
 // multiple of the group width GW = 32*V (V = columns per lane, 1/2/4).
 //   LA, LB, TH : [L][Cpad] f32   ln(theta), ln(1-theta), theta          (row = used locus)
 //   ELL, W     : [N][Cpad] f32   per-cell log-likelihoods, M-step weights (row = cell)
-//   LSE        : [N][slots] f32  per-cell log_sum_exp (S:230)
-//   csr        : [nnz] uint4 {locus, f32 alt, f32 ref, f32 ln_binomial}  rows = cells, loci ascending
-//   csc        : [nnz] uint4 {cell,  f32 alt, f32 alt+ref, 0}            cols = loci, cells ascending
+//   LSE        : [slots][N] f32  per-cell log_sum_exp (S:230)
+//   csr_idx    : [nnz] u32 alt|ref|locus packed       rows = cells, loci ascending;  csr_aux [nnz] float4 {alt, ref, ln_binomial, 0}
+//   csc_idx    : [nnz] u32 alt|alt+ref|cell packed    cols = loci, cells ascending;  csc_aux [nnz] float2 {alt, alt+ref}
+//   (the side records are only read for counts that do not fit the packed fields)
 // One warp owns one (row, column-group) pair and walks the row's entries strictly in order,
 // so every (cell,k) / (locus,k) sum is accumulated in the reference's own order (S:415-418,
 // S:476-483) and the results are bit-identical to the scalar code; lanes never exchange data.
@@ -20,6 +21,18 @@
 
 namespace soup {
 
+#ifndef SOUP_E_U
+#define SOUP_E_U 4       // entries (row gathers) in flight per warp in the E walk
+#endif
+#ifndef SOUP_E_MINB
+#define SOUP_E_MINB 3    // min resident CTAs per SM the E kernel is compiled for
+#endif
+#ifndef SOUP_M_U
+#define SOUP_M_U 8
+#endif
+#ifndef SOUP_M_MINB
+#define SOUP_M_MINB 3
+#endif
 constexpr int EM_THREADS = 256;            // 8 warps per CTA in the E / M kernels
 constexpr int EM_WARPS = EM_THREADS / 32;
 constexpr int TEMP_STEPS = 9;              // S:215
@@ -67,35 +80,126 @@ template <> __device__ __forceinline__ void st_row<1>(float* p, const FVec<1>& x
 template <> __device__ __forceinline__ void st_row<2>(float* p, const FVec<2>& x) { *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]); }
 template <> __device__ __forceinline__ void st_row<4>(float* p, const FVec<4>& x) { *reinterpret_cast<float4*>(p) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]); }
 
+// base + row * row_bytes in ONE instruction (IMAD.WIDE.U32); the compiler otherwise widens the
+// index arithmetic to 64 bits and spends four instructions per gathered row.
+__device__ __forceinline__ const float* row_at(const float* base, uint32_t row, uint32_t row_bytes) {
+    const float* r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(row), "r"(row_bytes), "l"(base));
+    return r;
+}
+
 // ------------------------------------------------------------------ E pass  (S:409-426)
 // acc_k = ln(1/K); for each entry j (ascending locus): acc_k += (lbc_j + alt_j*ln th) + ref_j*ln(1-th).
-// Exact shortcuts (only while every table value is finite): ref_j == 0 drops the "+ ref*ln(1-th)"
-// term (it adds -0.0) and alt_j == 0 drops "alt*ln th" (lbc + -0.0 == lbc), so one-sided
-// entries gather one table plane instead of two.
+//
+// Entry stream: ONE 32-bit word per stored entry,  alt << sh_a | ref << sh_r | locus  (Packing below);
+// counts that do not fit their field set both fields to the all-ones marker and live in a float4 side
+// record {alt, ref, lbc, 0}.  ln_binomial of in-field counts comes from a constant-memory table.
+// 70 % of vartrix entries are single-UMI, so the common case is: one word, one row gather, V adds.
+// Exact shortcuts, all bit-identical to the literal expression:
+//   alt 1, ref 0 : acc += ln th          (1*x == x, lbc == +0, 0 + x == x, and "+ 0*ln(1-th)" adds -0.0)
+//   alt 0, ref 1 : acc += ln(1-th)
+//   ref 0        : acc += lbc + alt*ln th
+//   alt 0        : acc += lbc + ref*ln(1-th)
+// Dropping a zero-count product is valid only while every table value is finite (0*inf = NaN), so
+// Ctl::nonfinite switches every entry to the literal expression.
+struct Packing {
+    uint32_t sh_a, sh_r;   // shifts of the two count fields
+    uint32_t cmask;        // (1 << count_bits) - 1: field mask and overflow marker
+    uint32_t imask;        // row-index mask (locus in the CSR stream, cell in the CSC stream)
+    uint32_t cbits;
+};
+__constant__ float c_lbc[4096];   // ln_binomial(alt + ref, alt) as f32 for in-field counts, index alt << cbits | ref
+
+template <int V>
+struct ETile { FVec<V> a, b; };
+
 template <int V, bool EXACT_SKIP>
-__device__ __forceinline__ void e_accumulate(FVec<V>& acc, const uint4& e, const float* __restrict__ LA,
-                                             const float* __restrict__ LB, size_t Cpad) {
-    const float alt = __uint_as_float(e.y), ref = __uint_as_float(e.z), lbc = __uint_as_float(e.w);
-    const size_t off = (size_t)e.x * Cpad;
-    const bool ha = !EXACT_SKIP || alt != 0.0f, hr = !EXACT_SKIP || ref != 0.0f;
-    FVec<V> a, b;
-    if (ha) a = ld_row<V>(LA + off);
-    if (hr) b = ld_row<V>(LB + off);
+__device__ __forceinline__ void e_issue(ETile<V>& t, uint32_t w, const Packing& pk, const float* __restrict__ la,
+                                        const float* __restrict__ lb, uint32_t row_bytes) {
+    const uint32_t locus = w & pk.imask;
+    if (!EXACT_SKIP || (w >> pk.sh_a) != 0) t.a = ld_row<V>(row_at(la, locus, row_bytes));
+    if (!EXACT_SKIP || ((w >> pk.sh_r) & pk.cmask) != 0) t.b = ld_row<V>(row_at(lb, locus, row_bytes));
+}
+template <int V, bool EXACT_SKIP>
+__device__ __forceinline__ void e_consume(FVec<V>& acc, const ETile<V>& t, uint32_t w, const Packing& pk, const float4* __restrict__ aux) {
+    const uint32_t ai = w >> pk.sh_a, ri = (w >> pk.sh_r) & pk.cmask;
+    if (EXACT_SKIP && ri == 0 && ai == 1) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        float t = lbc;
-        if (ha) t = __fadd_rn(lbc, __fmul_rn(alt, a.v[v]));
-        if (hr) t = __fadd_rn(t, __fmul_rn(ref, b.v[v]));
-        acc.v[v] = __fadd_rn(acc.v[v], t);
+        for (int v = 0; v < V; ++v) acc.v[v] = __fadd_rn(acc.v[v], t.a.v[v]);
+    } else if (EXACT_SKIP && ai == 0 && ri == 1) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc.v[v] = __fadd_rn(acc.v[v], t.b.v[v]);
+    } else {
+        float alt, ref, lbc;
+        if (ai == pk.cmask && ri == pk.cmask) {          // counts outside the packed fields (rare)
+            const float4 x = __ldg(aux);
+            alt = x.x; ref = x.y; lbc = x.z;
+        } else {
+            alt = (float)ai; ref = (float)ri; lbc = c_lbc[(ai << pk.cbits) | ri];
+        }
+        if (EXACT_SKIP && ri == 0) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc.v[v] = __fadd_rn(acc.v[v], __fadd_rn(lbc, __fmul_rn(alt, t.a.v[v])));
+        } else if (EXACT_SKIP && ai == 0) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc.v[v] = __fadd_rn(acc.v[v], __fadd_rn(lbc, __fmul_rn(ref, t.b.v[v])));
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                acc.v[v] = __fadd_rn(acc.v[v], __fadd_rn(__fadd_rn(lbc, __fmul_rn(alt, t.a.v[v])), __fmul_rn(ref, t.b.v[v])));
+        }
+    }
+}
+
+template <int V, int U, bool EXACT_SKIP>
+__device__ __forceinline__ void e_batch(FVec<V>& acc, const uint32_t (&cur)[U], const Packing& pk, const float4* __restrict__ aux,
+                                        const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes) {
+    ETile<V> t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) e_issue<V, EXACT_SKIP>(t[u], cur[u], pk, la, lb, row_bytes);
+#pragma unroll
+    for (int u = 0; u < U; ++u) e_consume<V, EXACT_SKIP>(acc, t[u], cur[u], pk, aux + u);
+}
+
+// Software-pipelined walk: the next U entry words are fetched while the current U row gathers are in
+// flight; many resident warps (small register footprint, compact code) hide the rest.  The loop body is
+// kept to ONE copy of the batch code — an earlier ping-pong version tripled the kernel's SASS and lost
+// more to instruction-cache misses than it saved in register moves.
+template <int V, int U, bool EXACT_SKIP>
+__device__ __forceinline__ void e_walk(FVec<V>& acc, const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t n,
+                                       const Packing& pk, const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes) {
+    uint32_t x[U], y[U];
+    uint32_t done = 0;
+    if (n >= U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = __ldg(p + u);
+#pragma unroll 1
+        for (;;) {
+            const bool more = done + 2 * U <= n;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) y[u] = __ldg(p + done + U + u);
+            }
+            e_batch<V, U, EXACT_SKIP>(acc, x, pk, aux + done, la, lb, row_bytes);
+            done += U;
+            if (!more) break;
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = y[u];
+        }
+    }
+#pragma unroll 1
+    for (; done < n; ++done) {
+        const uint32_t w[1] = {__ldg(p + done)};
+        e_batch<V, 1, EXACT_SKIP>(acc, w, pk, aux + done, la, lb, row_bytes);
     }
 }
 
 template <int V>
-__global__ void __launch_bounds__(EM_THREADS)
-estep_kernel(const uint4* __restrict__ csr, const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ cell_order,
-             const float* __restrict__ LA, const float* __restrict__ LB, float* __restrict__ ELL,
-             const int* __restrict__ group_active, const Ctl* __restrict__ ctl, uint32_t N, uint32_t Cpad,
-             uint32_t blocks_per_group, float log_prior) {
+__global__ void __launch_bounds__(EM_THREADS, SOUP_E_MINB)
+estep_kernel(const uint32_t* __restrict__ csr_idx, const float4* __restrict__ csr_aux, const uint64_t* __restrict__ row_ptr,
+             const uint32_t* __restrict__ cell_order, const float* __restrict__ LA, const float* __restrict__ LB,
+             float* __restrict__ ELL, const int* __restrict__ group_active, const Ctl* __restrict__ ctl, Packing pk, uint32_t N,
+             uint32_t Cpad, uint32_t blocks_per_group, float log_prior) {
     const uint32_t group = blockIdx.x / blocks_per_group;
     if (!group_active[group]) return;
     const uint32_t chunk = blockIdx.x - group * blocks_per_group;
@@ -103,27 +207,14 @@ estep_kernel(const uint4* __restrict__ csr, const uint64_t* __restrict__ row_ptr
     if (ci >= N) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t cell = cell_order[ci];
-    const size_t col = (size_t)group * (32 * V) + lane * V;
-    const float* la = LA + col;
-    const float* lb = LB + col;
-    uint64_t j = row_ptr[cell];
-    const uint64_t j1 = row_ptr[cell + 1];
+    const uint32_t col = group * (32 * V) + lane * V;
+    const uint64_t j0 = row_ptr[cell];
+    const uint32_t n = (uint32_t)(row_ptr[cell + 1] - j0);
     FVec<V> acc;
 #pragma unroll
     for (int v = 0; v < V; ++v) acc.v[v] = log_prior;
-    constexpr int U = 4;
-    if (!ctl->nonfinite) {
-        for (; j + U <= j1; j += U) {
-            uint4 e[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) e[u] = __ldg(csr + j + u);
-#pragma unroll
-            for (int u = 0; u < U; ++u) e_accumulate<V, true>(acc, e[u], la, lb, Cpad);
-        }
-        for (; j < j1; ++j) e_accumulate<V, true>(acc, __ldg(csr + j), la, lb, Cpad);
-    } else {
-        for (; j < j1; ++j) e_accumulate<V, false>(acc, __ldg(csr + j), la, lb, Cpad);
-    }
+    if (!ctl->nonfinite) e_walk<V, SOUP_E_U, true>(acc, csr_idx + j0, csr_aux + j0, n, pk, LA + col, LB + col, Cpad * 4u);
+    else e_walk<V, 2, false>(acc, csr_idx + j0, csr_aux + j0, n, pk, LA + col, LB + col, Cpad * 4u);
     st_row<V>(ELL + (size_t)cell * Cpad + col, acc);
 }
 
@@ -148,16 +239,15 @@ __device__ __forceinline__ float rust_lse(const float* x, int K) {   // log_sum_
 }
 
 __global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)a.N * a.slots) return;
-    const uint32_t cell = (uint32_t)(idx / a.slots);
-    const int slot = (int)(idx - (size_t)cell * a.slots);
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;   // cell fastest: coalesced LSE / total_alleles
+    const int slot = blockIdx.y;
+    if (cell >= a.N) return;
     const SlotState s = a.st[slot];
     if (!s.active) return;
     const int K = a.K;
     const float* x = a.ELL + (size_t)cell * a.Cpad + (size_t)slot * K;
     float* w = a.W + (size_t)cell * a.Cpad + (size_t)slot * K;
-    a.LSE[(size_t)cell * a.slots + slot] = rust_lse(x, K);
+    a.LSE[(size_t)slot * a.N + cell] = rust_lse(x, K);
     const float total = a.total_alleles[cell];
     float temp;
     if (a.method == SOUP_METHOD_EM) temp = fmaxf(total / ldexpf(20.0f, s.temp_step), 1.0f);   // S:233
@@ -210,8 +300,41 @@ __global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
 }
 
 // ------------------------------------------------------------------ loss + control (S:217-222, 245-250)
+// log_binom_loss (S:225-230) is a strictly sequential f32 sum over cells in index order; it decides
+// convergence (S:222), so it is reproduced literally: one block per slot streams LSE[slot][:] through
+// shared memory (all warps fetch, double-buffered) and a single thread adds in order.
+constexpr int LOSS_TILE = 2048;
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ LSE, const SlotState* __restrict__ st,
+                                                   float* __restrict__ loss_out, uint32_t N) {
+    const int slot = blockIdx.x;
+    if (!st[slot].active) return;
+    __shared__ __align__(16) float buf[2][LOSS_TILE];
+    const float* p = LSE + (size_t)slot * N;
+    const uint32_t tiles = (N + LOSS_TILE - 1) / LOSS_TILE;
+    for (uint32_t i = threadIdx.x; i < LOSS_TILE; i += blockDim.x) buf[0][i] = i < N ? p[i] : 0.0f;
+    __syncthreads();
+    float acc = 0.0f;
+    for (uint32_t t = 0; t < tiles; ++t) {
+        const uint32_t base = (t + 1) * LOSS_TILE;
+        if (t + 1 < tiles)
+            for (uint32_t i = threadIdx.x; i < LOSS_TILE; i += blockDim.x) buf[(t + 1) & 1][i] = base + i < N ? p[base + i] : 0.0f;
+        if (threadIdx.x == 0) {
+            const uint32_t cnt = min((uint32_t)LOSS_TILE, N - t * LOSS_TILE);
+            const float4* b4 = reinterpret_cast<const float4*>(buf[t & 1]);
+            uint32_t i = 0;
+            for (; i + 4 <= cnt; i += 4) {
+                const float4 v = b4[i >> 2];
+                acc = acc + v.x; acc = acc + v.y; acc = acc + v.z; acc = acc + v.w;
+            }
+            for (; i < cnt; ++i) acc = acc + buf[t & 1][i];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss_out[slot] = acc;
+}
+
 struct ControlArgs {
-    const float* LSE;
+    const float* loss_in;     // [slots] from loss_kernel
     SlotState* st;
     Ctl* ctl;
     int* counts;              // [slots][K] or nullptr
@@ -233,18 +356,7 @@ __global__ void __launch_bounds__(1024) control_kernel(ControlArgs a) {
     for (int slot = threadIdx.x; slot < a.slots; slot += blockDim.x) {
         SlotState s = a.st[slot];
         if (!s.active) continue;
-        // log_binom_loss: strictly sequential f32 sum over cells in index order (S:225-230)
-        float loss = 0.0f;
-        const float* p = a.LSE + slot;
-        uint32_t c = 0;
-        for (; c + 8 <= a.N; c += 8) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(c + u) * a.slots];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) loss = loss + v[u];
-        }
-        for (; c < a.N; ++c) loss = loss + p[(size_t)c * a.slots];
+        const float loss = a.loss_in[slot];
         const float change = loss - s.last_loss;     // S:246
         s.loss = loss;
         s.last_loss = loss;
@@ -291,24 +403,82 @@ __global__ void __launch_bounds__(1024) control_kernel(ControlArgs a) {
 
 // ------------------------------------------------------------------ M pass (S:476-483, S:386-396)
 // s = 1 + sum_cells p*alt ; d = 2 + sum_cells p*(alt+ref), cells ascending; theta = clamp(s/d).
+// Entry stream: alt << sh_a | (alt+ref) << sh_r | cell; out-of-field counts -> float2 side record {alt, alt+ref}.
+//   alt 1, tot 1 : s += p, d += p        (p*1 == p)
+//   alt 0, tot 1 : d += p                (s + p*0 == s while the weights are finite)
+//   alt 0        : d += p*tot
+//   otherwise    : s += p*alt, d += p*tot (literal)
 template <int V, bool EXACT_SKIP>
-__device__ __forceinline__ void m_accumulate(FVec<V>& s, FVec<V>& d, const uint4& e, const float* __restrict__ W, size_t Cpad) {
-    const float alt = __uint_as_float(e.y), tot = __uint_as_float(e.z);
-    const FVec<V> p = ld_row<V>(W + (size_t)e.x * Cpad);
-    if (!EXACT_SKIP || alt != 0.0f) {
+__device__ __forceinline__ void m_consume(FVec<V>& s, FVec<V>& d, const FVec<V>& p, uint32_t w, const Packing& pk, const float2* __restrict__ aux) {
+    const uint32_t ai = w >> pk.sh_a, ti = (w >> pk.sh_r) & pk.cmask;
+    if (ti == 1 && ai == 1) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) s.v[v] = __fadd_rn(s.v[v], __fmul_rn(p.v[v], alt));
+        for (int v = 0; v < V; ++v) { s.v[v] = __fadd_rn(s.v[v], p.v[v]); d.v[v] = __fadd_rn(d.v[v], p.v[v]); }
+    } else if (EXACT_SKIP && ti == 1 && ai == 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], p.v[v]);
+    } else {
+        float alt, tot;
+        if (ai == pk.cmask && ti == pk.cmask) {
+            const float2 x = __ldg(aux);
+            alt = x.x; tot = x.y;
+        } else {
+            alt = (float)ai; tot = (float)ti;
+        }
+        if (!EXACT_SKIP || alt != 0.0f) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) s.v[v] = __fadd_rn(s.v[v], __fmul_rn(p.v[v], alt));
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], __fmul_rn(p.v[v], tot));
     }
+}
+
+template <int V, int U, bool EXACT_SKIP>
+__device__ __forceinline__ void m_batch(FVec<V>& s, FVec<V>& d, const uint32_t (&cur)[U], const Packing& pk, const float2* __restrict__ aux,
+                                        const float* __restrict__ w, uint32_t row_bytes) {
+    FVec<V> p[U];
 #pragma unroll
-    for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], __fmul_rn(p.v[v], tot));
+    for (int u = 0; u < U; ++u) p[u] = ld_row<V>(row_at(w, cur[u] & pk.imask, row_bytes));
+#pragma unroll
+    for (int u = 0; u < U; ++u) m_consume<V, EXACT_SKIP>(s, d, p[u], cur[u], pk, aux + u);
+}
+
+template <int V, int U, bool EXACT_SKIP>
+__device__ __forceinline__ void m_walk(FVec<V>& s, FVec<V>& d, const uint32_t* __restrict__ q, const float2* __restrict__ aux, uint32_t n,
+                                       const Packing& pk, const float* __restrict__ w, uint32_t row_bytes) {
+    uint32_t x[U], y[U];
+    uint32_t done = 0;
+    if (n >= U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = __ldg(q + u);
+#pragma unroll 1
+        for (;;) {
+            const bool more = done + 2 * U <= n;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) y[u] = __ldg(q + done + U + u);
+            }
+            m_batch<V, U, EXACT_SKIP>(s, d, x, pk, aux + done, w, row_bytes);
+            done += U;
+            if (!more) break;
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = y[u];
+        }
+    }
+#pragma unroll 1
+    for (; done < n; ++done) {
+        const uint32_t wd[1] = {__ldg(q + done)};
+        m_batch<V, 1, EXACT_SKIP>(s, d, wd, pk, aux + done, w, row_bytes);
+    }
 }
 
 template <int V>
-__global__ void __launch_bounds__(EM_THREADS)
-mstep_kernel(const uint4* __restrict__ csc, const uint64_t* __restrict__ col_ptr, const uint32_t* __restrict__ locus_order,
-             const float* __restrict__ W, float* __restrict__ TH, float* __restrict__ LA, float* __restrict__ LB,
-             const uint8_t* __restrict__ col_write, const int* __restrict__ group_active, const Ctl* __restrict__ ctl,
-             uint32_t L, uint32_t Cpad, uint32_t blocks_per_group) {
+__global__ void __launch_bounds__(EM_THREADS, SOUP_M_MINB)
+mstep_kernel(const uint32_t* __restrict__ csc_idx, const float2* __restrict__ csc_aux, const uint64_t* __restrict__ col_ptr,
+             const uint32_t* __restrict__ locus_order, const float* __restrict__ W, float* __restrict__ TH, float* __restrict__ LA,
+             float* __restrict__ LB, const uint8_t* __restrict__ col_write, const int* __restrict__ group_active,
+             const Ctl* __restrict__ ctl, Packing pk, uint32_t L, uint32_t Cpad, uint32_t blocks_per_group) {
     const uint32_t group = blockIdx.x / blocks_per_group;
     if (!group_active[group]) return;
     const uint32_t chunk = blockIdx.x - group * blocks_per_group;
@@ -316,26 +486,14 @@ mstep_kernel(const uint4* __restrict__ csc, const uint64_t* __restrict__ col_ptr
     if (li >= L) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t locus = locus_order[li];
-    const size_t col = (size_t)group * (32 * V) + lane * V;
-    const float* w = W + col;
-    uint64_t j = col_ptr[locus];
-    const uint64_t j1 = col_ptr[locus + 1];
+    const uint32_t col = group * (32 * V) + lane * V;
+    const uint64_t j0 = col_ptr[locus];
+    const uint32_t n = (uint32_t)(col_ptr[locus + 1] - j0);
     FVec<V> s, d;
 #pragma unroll
     for (int v = 0; v < V; ++v) { s.v[v] = 1.0f; d.v[v] = 2.0f; }   // pseudocounts S:197-198, S:456-464
-    constexpr int U = 4;
-    if (!ctl->nonfinite) {
-        for (; j + U <= j1; j += U) {
-            uint4 e[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) e[u] = __ldg(csc + j + u);
-#pragma unroll
-            for (int u = 0; u < U; ++u) m_accumulate<V, true>(s, d, e[u], w, Cpad);
-        }
-        for (; j < j1; ++j) m_accumulate<V, true>(s, d, __ldg(csc + j), w, Cpad);
-    } else {
-        for (; j < j1; ++j) m_accumulate<V, false>(s, d, __ldg(csc + j), w, Cpad);
-    }
+    if (!ctl->nonfinite) m_walk<V, SOUP_M_U, true>(s, d, csc_idx + j0, csc_aux + j0, n, pk, W + col, Cpad * 4u);
+    else m_walk<V, 2, false>(s, d, csc_idx + j0, csc_aux + j0, n, pk, W + col, Cpad * 4u);
     const size_t o = (size_t)locus * Cpad + col;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -470,10 +628,15 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
 // ------------------------------------------------------------------ load-time kernels
 __constant__ double c_ln_factorial[171];   // statrs FCACHE: ln(n!) for n <= 170 (S:669-670)
 
+__device__ __forceinline__ uint32_t pack_word(uint32_t idx, uint32_t c0, uint32_t c1, const Packing& pk) {
+    if (c0 >= pk.cmask || c1 >= pk.cmask) c0 = c1 = pk.cmask;   // out-of-field: marker, the side record holds the counts
+    return (c0 << pk.sh_a) | (c1 << pk.sh_r) | idx;
+}
+
 __global__ void build_csr_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ locus,
-                                 const uint32_t* __restrict__ alt, const uint32_t* __restrict__ ref, uint4* __restrict__ csr,
-                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, float* __restrict__ total_alleles,
-                                 uint32_t* __restrict__ row_len, uint32_t N) {
+                                 const uint32_t* __restrict__ alt, const uint32_t* __restrict__ ref, uint32_t* __restrict__ csr_idx,
+                                 float4* __restrict__ csr_aux, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                                 float* __restrict__ total_alleles, Packing pk, uint32_t N) {
     const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (cell >= N) return;
     const uint32_t lane = threadIdx.x & 31;
@@ -482,7 +645,8 @@ __global__ void build_csr_kernel(const uint64_t* __restrict__ row_ptr, const uin
         const uint32_t a = alt[j], r = ref[j], n = a + r;   // wrapping u32 add as in release-mode Rust (S:664, S:670)
         float lbc = 0.0f;
         if (n <= 170u) lbc = (float)(c_ln_factorial[n] - c_ln_factorial[a] - c_ln_factorial[n - a]);   // n > 170 patched from the host
-        csr[j] = make_uint4(locus[j], __float_as_uint((float)a), __float_as_uint((float)r), __float_as_uint(lbc));
+        csr_idx[j] = pack_word(locus[j], a, r, pk);
+        csr_aux[j] = make_float4((float)a, (float)r, lbc, 0.0f);
         keys[j] = ((unsigned long long)locus[j] << 32) | cell;
         vals[j] = (uint32_t)j;
     }
@@ -490,24 +654,24 @@ __global__ void build_csr_kernel(const uint64_t* __restrict__ row_ptr, const uin
         float t = 0.0f;                                      // total_alleles S:671: sequential f32, ascending locus
         for (uint64_t j = j0; j < j1; ++j) t = t + (float)(alt[j] + ref[j]);
         total_alleles[cell] = t;
-        row_len[cell] = (uint32_t)(j1 - j0);
     }
 }
 
-__global__ void patch_lbc_kernel(uint4* csr, const uint32_t* __restrict__ idx, const float* __restrict__ val, uint32_t n) {
+__global__ void patch_lbc_kernel(float4* csr_aux, const uint32_t* __restrict__ idx, const float* __restrict__ val, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) csr[idx[i]].w = __float_as_uint(val[i]);
+    if (i < n) csr_aux[idx[i]].z = val[i];
 }
 
-// csc entry = {cell, f32 alt, f32 (alt+ref: integer add, then cast, S:480), 0} in (locus, cell) order
+// csc stream in (locus, cell) order; alt+ref is the reference's integer add, then cast (S:480)
 __global__ void build_csc_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                 const uint32_t* __restrict__ alt, const uint32_t* __restrict__ ref, uint4* __restrict__ csc,
-                                 uint64_t nnz) {
+                                 const uint32_t* __restrict__ alt, const uint32_t* __restrict__ ref, uint32_t* __restrict__ csc_idx,
+                                 float2* __restrict__ csc_aux, Packing pk, uint64_t nnz) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
     const uint32_t j = vals[i];
-    const uint32_t a = alt[j], r = ref[j];
-    csc[i] = make_uint4((uint32_t)(keys[i] & 0xffffffffu), __float_as_uint((float)a), __float_as_uint((float)(a + r)), 0u);
+    const uint32_t a = alt[j], t = a + ref[j];
+    csc_idx[i] = pack_word((uint32_t)(keys[i] & 0xffffffffu), a, t, pk);
+    csc_aux[i] = make_float2((float)a, (float)t);
 }
 
 __global__ void col_ptr_kernel(const unsigned long long* __restrict__ keys, uint64_t nnz, uint64_t* __restrict__ col_ptr, uint32_t L) {
