@@ -30,7 +30,7 @@ void pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------ workspace of one (K, slots, V) shape
 struct Workspace {
-    int K = 0, slots = 0, V = 0, GW = 0, n_groups = 0, iter_cap = 0, queue_cap = 0;
+    int K = 0, slots = 0, VM = 0, VT = 0, n_main = 0, n_groups = 0, iter_cap = 0, queue_cap = 0, forced_lanes = 0;
     uint32_t Cpad = 0;
     float *LA = nullptr, *LB = nullptr, *TH = nullptr, *ELL = nullptr, *W = nullptr, *LSE = nullptr, *loss = nullptr;
     SlotState* st = nullptr;
@@ -395,23 +395,33 @@ extern "C" int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc) {
 }
 
 // ------------------------------------------------------------------ workspace
-static int pick_lanes(int cols) {
-    // widest vector (columns per lane) whose padding wastes <= 12.5 % of the lanes
-    for (int V : {4, 2}) {
-        int gw = 32 * V, padded = (cols + gw - 1) / gw * gw;
-        if (padded * 8 <= cols * 9) return V;
+// Column groups: `n_main` groups of 128 columns (4 per lane, 128-bit gathers) and, if the column count
+// is not a multiple of 128, one narrower last group (1, 2 or 4 columns per lane).  `forced_lanes`
+// (tests) makes every group that many columns per lane wide.
+static void plan_groups(int cols, int forced_lanes, int* VM, int* VT, int* n_main, int* n_groups, uint32_t* Cpad) {
+    if (forced_lanes == 1 || forced_lanes == 2 || forced_lanes == 4) {
+        const int gw = 32 * forced_lanes;
+        *VM = *VT = forced_lanes;
+        *n_main = *n_groups = (cols + gw - 1) / gw;
+        *Cpad = (uint32_t)(*n_groups * gw);
+        return;
     }
-    return 1;
+    *VM = 4;
+    *n_main = cols / 128;
+    const int rem = cols - *n_main * 128;
+    if (rem == 0) { *VT = 4; *n_groups = *n_main; *Cpad = (uint32_t)cols; return; }
+    *VT = rem <= 32 ? 1 : (rem <= 64 ? 2 : 4);
+    *n_groups = *n_main + 1;
+    *Cpad = (uint32_t)(*n_main * 128 + 32 * *VT);
 }
 
-static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int V, int iter_cap, int queue_cap, int n_streams) {
+static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lanes, int iter_cap, int queue_cap, int n_streams) {
     Workspace& w = ctx->ws;
-    if (w.K == K && w.slots == slots && w.V == V && w.iter_cap == iter_cap && w.queue_cap >= queue_cap && w.n_streams_cap >= n_streams) return SOUP_OK;
+    if (w.K == K && w.slots == slots && w.forced_lanes == forced_lanes && w.iter_cap == iter_cap && w.queue_cap >= queue_cap && w.n_streams_cap >= n_streams) return SOUP_OK;
     ws_free(w);
-    w.K = K; w.slots = slots; w.V = V; w.GW = 32 * V; w.iter_cap = iter_cap; w.queue_cap = queue_cap; w.n_streams_cap = n_streams;
+    w.K = K; w.slots = slots; w.forced_lanes = forced_lanes; w.iter_cap = iter_cap; w.queue_cap = queue_cap; w.n_streams_cap = n_streams;
     const size_t cols = (size_t)slots * K;
-    w.Cpad = (uint32_t)((cols + w.GW - 1) / w.GW * w.GW);
-    w.n_groups = (int)(w.Cpad / w.GW);
+    plan_groups((int)cols, forced_lanes, &w.VM, &w.VT, &w.n_main, &w.n_groups, &w.Cpad);
     const size_t L = std::max<uint64_t>(ctx->L, 1), N = std::max<uint64_t>(ctx->N, 1);
     cudaError_t e = cudaSuccess;
     auto A = [&](auto** p, size_t n, bool zero) { if (e == cudaSuccess) e = ws_alloc(w, p, n, zero); };
@@ -448,27 +458,31 @@ struct IterLaunch {
     FinalizeArgs fin;
 };
 
-template <int V>
 static void launch_e(soup_ctx* ctx, float log_prior) {
     Workspace& w = ctx->ws;
     const uint32_t bpg = (uint32_t)((ctx->N + EM_WARPS - 1) / EM_WARPS);
     if (bpg == 0) return;
-    estep_kernel<V><<<bpg * w.n_groups, EM_THREADS, 0, ctx->stream>>>(ctx->d_csr_idx, ctx->d_csr_aux, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB,
-                                                                      w.ELL, w.group_active, w.ctl, ctx->pk_csr, (uint32_t)ctx->N, w.Cpad, bpg, log_prior);
+    const EArgs a{ctx->d_csr_idx, ctx->d_csr_aux, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB, w.ELL, w.group_active, w.ctl,
+                  ctx->pk_csr, (uint32_t)ctx->N, w.Cpad, bpg, (uint32_t)w.n_main, log_prior};
+    const dim3 grid(bpg * w.n_groups);
+    if (w.VM == 4 && w.VT == 4) estep_kernel<4, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    else if (w.VM == 4 && w.VT == 2) estep_kernel<4, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    else if (w.VM == 4 && w.VT == 1) estep_kernel<4, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    else if (w.VM == 2) estep_kernel<2, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    else estep_kernel<1, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
 }
-template <int V>
 static void launch_m(soup_ctx* ctx) {
     Workspace& w = ctx->ws;
-    const uint32_t bpg = (uint32_t)((ctx->L + EM_WARPS - 1) / EM_WARPS);
-    if (bpg == 0) return;
-    mstep_kernel<V><<<bpg * w.n_groups, EM_THREADS, 0, ctx->stream>>>(ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH,
-                                                                      w.LA, w.LB, w.col_write, w.group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, bpg);
-}
-static void launch_e(soup_ctx* ctx, float log_prior) {
-    switch (ctx->ws.V) { case 4: launch_e<4>(ctx, log_prior); break; case 2: launch_e<2>(ctx, log_prior); break; default: launch_e<1>(ctx, log_prior); }
-}
-static void launch_m(soup_ctx* ctx) {
-    switch (ctx->ws.V) { case 4: launch_m<4>(ctx); break; case 2: launch_m<2>(ctx); break; default: launch_m<1>(ctx); }
+    const uint32_t chunks = (uint32_t)((ctx->L + EM_WARPS - 1) / EM_WARPS);
+    if (chunks == 0) return;
+    const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
+                  w.group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.n_groups, (uint32_t)w.n_main};
+    const dim3 grid(chunks * w.n_groups);
+    if (w.VM == 4 && w.VT == 4) mstep_kernel<4, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    else if (w.VM == 4 && w.VT == 2) mstep_kernel<4, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    else if (w.VM == 4 && w.VT == 1) mstep_kernel<4, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    else if (w.VM == 2) mstep_kernel<2, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    else mstep_kernel<1, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
 }
 static void launch_post(soup_ctx* ctx, int method, bool counts) {
     Workspace& w = ctx->ws;
@@ -570,16 +584,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     while (slots > 1 && (uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32)) --slots;
     if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32))
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: max(cells, loci) * k exceeds the 32-bit row-offset range");
-    if (p->max_slots <= 0 && p->lanes <= 0) {
-        // prefer a column count that fills whole 128-wide groups (4 columns per lane, 128-bit gathers)
-        int g = 128, a = K;
-        while (a) { int t = g % a; g = a; a = t; }          // gcd(128, K)
-        const int m = 128 / g, rounded = slots / m * m;
-        if (rounded > 0 && rounded * 8 >= slots * 7) slots = rounded;
-    }
-    int V = p->lanes;
-    if (V != 1 && V != 2 && V != 4) V = pick_lanes(slots * K);
-    int32_t rc = ensure_workspace(ctx, K, slots, V, iter_cap, n_local, p->n_streams);
+    const int forced_lanes = (p->lanes == 1 || p->lanes == 2 || p->lanes == 4) ? p->lanes : 0;
+    int32_t rc = ensure_workspace(ctx, K, slots, forced_lanes, iter_cap, n_local, p->n_streams);
     if (rc != SOUP_OK) return rc;
     Workspace& w = ctx->ws;
     cudaStream_t st = ctx->stream;
@@ -646,7 +652,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0;
     it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, w.draw_of_k, w.TH, w.LA, w.LB,
                            (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream};
-    it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write, w.group_active, K, slots, w.GW, w.n_groups, iter_cap, w.Cpad, limit};
+    it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write, w.group_active, K, slots, 32 * w.VM, w.n_main, w.n_groups, iter_cap, w.Cpad, limit};
 
     CKS(cudaEventRecord(ctx->ev0, st));
     launch_refill(ctx, it.refill);
@@ -748,7 +754,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         }
     }
     ctx->stats.slot_iterations = fc.slot_iterations;
-    ctx->stats.slots = slots; ctx->stats.lanes = V; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    ctx->stats.slots = slots; ctx->stats.lanes = w.VM; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     ctx->stats.h2d_bytes = h2d; ctx->stats.d2h_bytes = d2h;
     return SOUP_OK;
 }
@@ -780,8 +786,8 @@ static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
     if (k <= 0 || n_slots <= 0 || n_slots > 1024) return ctx->fail(SOUP_ERR_INVALID, "bad k / n_slots");
     if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)n_slots * k + 128) >= (1ull << 32))
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "max(cells, loci) * columns exceeds the 32-bit row-offset range");
-    int V = (lanes == 1 || lanes == 2 || lanes == 4) ? lanes : pick_lanes(n_slots * k);
-    int32_t rc = ensure_workspace(ctx, k, n_slots, V, 1, n_slots, 1);
+    const int forced = (lanes == 1 || lanes == 2 || lanes == 4) ? lanes : 0;
+    int32_t rc = ensure_workspace(ctx, k, n_slots, forced, 1, n_slots, 1);
     if (rc != SOUP_OK) return rc;
     Workspace& w = ctx->ws;
     std::vector<int> ga(w.n_groups, 1);
@@ -856,7 +862,7 @@ extern "C" int32_t soup_estep(soup_ctx* ctx, int32_t k, int32_t method, int32_t 
     ctx->stats = soup_stats{};
     ctx->stats.kernel_launches = 4 + (log_probs ? 1 : 0) + (weights ? 1 : 0);
     ctx->stats.estep_launches = 1;
-    ctx->stats.slots = n_slots; ctx->stats.lanes = w.V; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    ctx->stats.slots = n_slots; ctx->stats.lanes = w.VM; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     return SOUP_OK;
 }
 
@@ -903,7 +909,7 @@ extern "C" int32_t soup_mstep(soup_ctx* ctx, int32_t k, int32_t n_slots, int32_t
     ctx->stats = soup_stats{};
     ctx->stats.kernel_launches = 4;
     ctx->stats.mstep_launches = 1;
-    ctx->stats.slots = n_slots; ctx->stats.lanes = w.V; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    ctx->stats.slots = n_slots; ctx->stats.lanes = w.VM; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     return SOUP_OK;
 }
 

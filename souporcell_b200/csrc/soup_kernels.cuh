@@ -194,28 +194,40 @@ __device__ __forceinline__ void e_walk(FVec<V>& acc, const uint32_t* __restrict_
     }
 }
 
+struct EArgs {
+    const uint32_t* csr_idx; const float4* csr_aux; const uint64_t* row_ptr; const uint32_t* cell_order;
+    const float* LA; const float* LB; float* ELL; const int* group_active; const Ctl* ctl;
+    Packing pk;
+    uint32_t N, Cpad, blocks_per_group, n_main;   // groups [0, n_main) are VM columns per lane wide, group n_main (if any) VT
+    float log_prior;
+};
+
 template <int V>
-__global__ void __launch_bounds__(EM_THREADS, SOUP_E_MINB)
-estep_kernel(const uint32_t* __restrict__ csr_idx, const float4* __restrict__ csr_aux, const uint64_t* __restrict__ row_ptr,
-             const uint32_t* __restrict__ cell_order, const float* __restrict__ LA, const float* __restrict__ LB,
-             float* __restrict__ ELL, const int* __restrict__ group_active, const Ctl* __restrict__ ctl, Packing pk, uint32_t N,
-             uint32_t Cpad, uint32_t blocks_per_group, float log_prior) {
-    const uint32_t group = blockIdx.x / blocks_per_group;
-    if (!group_active[group]) return;
-    const uint32_t chunk = blockIdx.x - group * blocks_per_group;
-    const uint32_t ci = chunk * EM_WARPS + (threadIdx.x >> 5);
-    if (ci >= N) return;
+__device__ __forceinline__ void estep_body(const EArgs& a, uint32_t cell, uint32_t col0) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t cell = cell_order[ci];
-    const uint32_t col = group * (32 * V) + lane * V;
-    const uint64_t j0 = row_ptr[cell];
-    const uint32_t n = (uint32_t)(row_ptr[cell + 1] - j0);
+    const uint32_t col = col0 + lane * V;
+    const uint64_t j0 = a.row_ptr[cell];
+    const uint32_t n = (uint32_t)(a.row_ptr[cell + 1] - j0);
     FVec<V> acc;
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc.v[v] = log_prior;
-    if (!ctl->nonfinite) e_walk<V, SOUP_E_U, true>(acc, csr_idx + j0, csr_aux + j0, n, pk, LA + col, LB + col, Cpad * 4u);
-    else e_walk<V, 2, false>(acc, csr_idx + j0, csr_aux + j0, n, pk, LA + col, LB + col, Cpad * 4u);
-    st_row<V>(ELL + (size_t)cell * Cpad + col, acc);
+    for (int v = 0; v < V; ++v) acc.v[v] = a.log_prior;
+    if (!a.ctl->nonfinite) e_walk<V, SOUP_E_U, true>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + col, a.LB + col, a.Cpad * 4u);
+    else e_walk<V, 2, false>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + col, a.LB + col, a.Cpad * 4u);
+    st_row<V>(a.ELL + (size_t)cell * a.Cpad + col, acc);
+}
+
+// grid: group-major (all cells of group 0, then group 1, ...) so one group's table slice stays hot in L2;
+// inside a group the cells are visited longest-first.
+template <int VM, int VT>
+__global__ void __launch_bounds__(EM_THREADS, SOUP_E_MINB) estep_kernel(const EArgs a) {
+    const uint32_t group = blockIdx.x / a.blocks_per_group;
+    if (!a.group_active[group]) return;
+    const uint32_t chunk = blockIdx.x - group * a.blocks_per_group;
+    const uint32_t ci = chunk * EM_WARPS + (threadIdx.x >> 5);
+    if (ci >= a.N) return;
+    const uint32_t cell = a.cell_order[ci];
+    if (VM == VT || group < a.n_main) estep_body<VM>(a, cell, group * (32 * VM));
+    else estep_body<VT>(a, cell, a.n_main * (32 * VM));
 }
 
 // ------------------------------------------------------------------ per-cell pass (S:230-236 / S:318-330)
@@ -404,33 +416,24 @@ __global__ void __launch_bounds__(1024) control_kernel(ControlArgs a) {
 // ------------------------------------------------------------------ M pass (S:476-483, S:386-396)
 // s = 1 + sum_cells p*alt ; d = 2 + sum_cells p*(alt+ref), cells ascending; theta = clamp(s/d).
 // Entry stream: alt << sh_a | (alt+ref) << sh_r | cell; out-of-field counts -> float2 side record {alt, alt+ref}.
-//   alt 1, tot 1 : s += p, d += p        (p*1 == p)
-//   alt 0, tot 1 : d += p                (s + p*0 == s while the weights are finite)
-//   alt 0        : d += p*tot
-//   otherwise    : s += p*alt, d += p*tot (literal)
+// The inner loop is the reference's literal expression with NO data-dependent branch: a locus covered
+// by every cell is a 10^4..10^5-long strictly sequential chain owned by one warp, and on that critical
+// path a branch per entry (resolve latency, no ILP across it) costs more than the multiplies it saves.
+__device__ __forceinline__ float small_u2f(uint32_t i) {   // exact (float)i for i < 2^23 without the conversion pipe
+    return __fadd_rn(__uint_as_float(0x4B000000u | i), -8388608.0f);
+}
 template <int V, bool EXACT_SKIP>
 __device__ __forceinline__ void m_consume(FVec<V>& s, FVec<V>& d, const FVec<V>& p, uint32_t w, const Packing& pk, const float2* __restrict__ aux) {
     const uint32_t ai = w >> pk.sh_a, ti = (w >> pk.sh_r) & pk.cmask;
-    if (ti == 1 && ai == 1) {
+    float alt = small_u2f(ai), tot = small_u2f(ti);
+    if (ai == pk.cmask && ti == pk.cmask) {          // counts outside the packed fields (rare)
+        const float2 x = __ldg(aux);
+        alt = x.x; tot = x.y;
+    }
 #pragma unroll
-        for (int v = 0; v < V; ++v) { s.v[v] = __fadd_rn(s.v[v], p.v[v]); d.v[v] = __fadd_rn(d.v[v], p.v[v]); }
-    } else if (EXACT_SKIP && ti == 1 && ai == 0) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], p.v[v]);
-    } else {
-        float alt, tot;
-        if (ai == pk.cmask && ti == pk.cmask) {
-            const float2 x = __ldg(aux);
-            alt = x.x; tot = x.y;
-        } else {
-            alt = (float)ai; tot = (float)ti;
-        }
-        if (!EXACT_SKIP || alt != 0.0f) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) s.v[v] = __fadd_rn(s.v[v], __fmul_rn(p.v[v], alt));
-        }
-#pragma unroll
-        for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], __fmul_rn(p.v[v], tot));
+    for (int v = 0; v < V; ++v) {
+        s.v[v] = __fadd_rn(s.v[v], __fmul_rn(p.v[v], alt));
+        d.v[v] = __fadd_rn(d.v[v], __fmul_rn(p.v[v], tot));
     }
 }
 
@@ -473,36 +476,45 @@ __device__ __forceinline__ void m_walk(FVec<V>& s, FVec<V>& d, const uint32_t* _
     }
 }
 
+struct MArgs {
+    const uint32_t* csc_idx; const float2* csc_aux; const uint64_t* col_ptr; const uint32_t* locus_order;
+    const float* W; float* TH; float* LA; float* LB; const uint8_t* col_write; const int* group_active; const Ctl* ctl;
+    Packing pk;
+    uint32_t L, Cpad, n_groups, n_main;
+};
+
 template <int V>
-__global__ void __launch_bounds__(EM_THREADS, SOUP_M_MINB)
-mstep_kernel(const uint32_t* __restrict__ csc_idx, const float2* __restrict__ csc_aux, const uint64_t* __restrict__ col_ptr,
-             const uint32_t* __restrict__ locus_order, const float* __restrict__ W, float* __restrict__ TH, float* __restrict__ LA,
-             float* __restrict__ LB, const uint8_t* __restrict__ col_write, const int* __restrict__ group_active,
-             const Ctl* __restrict__ ctl, Packing pk, uint32_t L, uint32_t Cpad, uint32_t blocks_per_group) {
-    const uint32_t group = blockIdx.x / blocks_per_group;
-    if (!group_active[group]) return;
-    const uint32_t chunk = blockIdx.x - group * blocks_per_group;
-    const uint32_t li = chunk * EM_WARPS + (threadIdx.x >> 5);
-    if (li >= L) return;
+__device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint32_t col0) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t locus = locus_order[li];
-    const uint32_t col = group * (32 * V) + lane * V;
-    const uint64_t j0 = col_ptr[locus];
-    const uint32_t n = (uint32_t)(col_ptr[locus + 1] - j0);
+    const uint32_t col = col0 + lane * V;
+    const uint64_t j0 = a.col_ptr[locus];
+    const uint32_t n = (uint32_t)(a.col_ptr[locus + 1] - j0);
     FVec<V> s, d;
 #pragma unroll
     for (int v = 0; v < V; ++v) { s.v[v] = 1.0f; d.v[v] = 2.0f; }   // pseudocounts S:197-198, S:456-464
-    if (!ctl->nonfinite) m_walk<V, SOUP_M_U, true>(s, d, csc_idx + j0, csc_aux + j0, n, pk, W + col, Cpad * 4u);
-    else m_walk<V, 2, false>(s, d, csc_idx + j0, csc_aux + j0, n, pk, W + col, Cpad * 4u);
-    const size_t o = (size_t)locus * Cpad + col;
+    m_walk<V, SOUP_M_U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+    const size_t o = (size_t)locus * a.Cpad + col;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        if (!col_write[col + v]) continue;          // locked cluster (S:389) or idle column
+        if (!a.col_write[col + v]) continue;          // locked cluster (S:389) or idle column
         const float th = fmaxf(fminf(__fdiv_rn(s.v[v], d.v[v]), 0.99f), 0.01f);   // S:392-393
-        TH[o + v] = th;
-        LA[o + v] = soupmath::glibc_logf(th);
-        LB[o + v] = soupmath::glibc_logf(1.0f - th);
+        a.TH[o + v] = th;
+        a.LA[o + v] = soupmath::glibc_logf(th);
+        a.LB[o + v] = soupmath::glibc_logf(1.0f - th);
     }
+}
+
+// grid: locus-major (group fastest) so every group's longest loci start in the first wave (LPT order)
+template <int VM, int VT>
+__global__ void __launch_bounds__(EM_THREADS, SOUP_M_MINB) mstep_kernel(const MArgs a) {
+    const uint32_t chunk = blockIdx.x / a.n_groups;
+    const uint32_t group = blockIdx.x - chunk * a.n_groups;
+    if (!a.group_active[group]) return;
+    const uint32_t li = chunk * EM_WARPS + (threadIdx.x >> 5);
+    if (li >= a.L) return;
+    const uint32_t locus = a.locus_order[li];
+    if (VM == VT || group < a.n_main) mstep_body<VM>(a, locus, group * (32 * VM));
+    else mstep_body<VT>(a, locus, a.n_main * (32 * VM));
 }
 
 // ------------------------------------------------------------------ harvest: keep the best solve (S:110-114)
@@ -579,7 +591,7 @@ struct FinalizeArgs {
     const uint8_t* k_locked;   // [K]
     uint8_t* col_write;        // [Cpad]
     int* group_active;         // [n_groups]
-    int K, slots, GW, n_groups, iter_cap;
+    int K, slots, WM, n_main, n_groups, iter_cap;   // groups [0, n_main): WM columns each; an optional last group takes the rest
     uint32_t Cpad;
     float limit;
 };
@@ -615,8 +627,9 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
         a.col_write[c] = (slot < a.slots && a.st[slot].active && !a.k_locked[k]) ? 1 : 0;
     }
     for (int g = threadIdx.x; g < a.n_groups; g += blockDim.x) {
-        const int first = (g * a.GW) / a.K;
-        int last = (g * a.GW + a.GW - 1) / a.K;
+        const int c0 = g * a.WM, c1 = g < a.n_main ? c0 + a.WM : (int)a.Cpad;
+        const int first = c0 / a.K;
+        int last = (c1 - 1) / a.K;
         if (last >= a.slots) last = a.slots - 1;
         int any = 0;
         for (int s = first; s <= last; ++s) any |= a.st[s].active;
