@@ -30,13 +30,14 @@ void pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------ workspace of one (K, slots, V) shape
 struct Workspace {
-    int K = 0, slots = 0, VM = 0, VT = 0, n_main = 0, n_groups = 0, iter_cap = 0, queue_cap = 0, forced_lanes = 0;
+    int K = 0, slots = 0, iter_cap = 0, queue_cap = 0, forced_lanes = 0;
+    struct GroupPlan { int VM = 0, VT = 0, n_main = 0, n_groups = 0; uint32_t padded = 0; } ep, mp;   // E / M kernel column groups
     uint32_t Cpad = 0;
     float *LA = nullptr, *LB = nullptr, *TH = nullptr, *ELL = nullptr, *W = nullptr, *LSE = nullptr, *loss = nullptr;
     SlotState* st = nullptr;
     Ctl* ctl = nullptr;
     uint8_t *col_write = nullptr, *k_locked = nullptr;
-    int *group_active = nullptr, *counts = nullptr, *queue = nullptr, *draw_of_k = nullptr, *solve_iters = nullptr;
+    int *e_group_active = nullptr, *m_group_active = nullptr, *counts = nullptr, *queue = nullptr, *draw_of_k = nullptr, *solve_iters = nullptr;
     float *solve_loss = nullptr, *best_lp = nullptr, *best_theta = nullptr;
     IterRec* trace = nullptr;
     uint32_t* stream_keys = nullptr;
@@ -395,24 +396,37 @@ extern "C" int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc) {
 }
 
 // ------------------------------------------------------------------ workspace
-// Column groups: `n_main` groups of 128 columns (4 per lane, 128-bit gathers) and, if the column count
-// is not a multiple of 128, one narrower last group (1, 2 or 4 columns per lane).  `forced_lanes`
-// (tests) makes every group that many columns per lane wide.
-static void plan_groups(int cols, int forced_lanes, int* VM, int* VT, int* n_main, int* n_groups, uint32_t* Cpad) {
-    if (forced_lanes == 1 || forced_lanes == 2 || forced_lanes == 4) {
+// Column groups of one kernel: `n_main` groups of 32*VM columns and, if the column count is not a
+// multiple of that, one narrower last group (the smallest of 1/2/4/8 columns per lane that holds the
+// rest).  The E pass is per-entry-latency bound, so it takes wide groups (8 columns per lane: two
+// 512-byte row pieces per gather); the M pass owns a strictly sequential chain per (locus, column), so
+// it takes narrower groups (4 per lane) that put more warps on the long loci.  `forced_lanes` (tests)
+// makes every group of both kernels that many columns per lane wide.
+static Workspace::GroupPlan plan_groups(int cols, int vmax, int forced_lanes) {
+    Workspace::GroupPlan g;
+    if (forced_lanes) {
         const int gw = 32 * forced_lanes;
-        *VM = *VT = forced_lanes;
-        *n_main = *n_groups = (cols + gw - 1) / gw;
-        *Cpad = (uint32_t)(*n_groups * gw);
-        return;
+        g.VM = g.VT = forced_lanes;
+        g.n_main = g.n_groups = (cols + gw - 1) / gw;
+        g.padded = (uint32_t)(g.n_groups * gw);
+        return g;
     }
-    *VM = 4;
-    *n_main = cols / 128;
-    const int rem = cols - *n_main * 128;
-    if (rem == 0) { *VT = 4; *n_groups = *n_main; *Cpad = (uint32_t)cols; return; }
-    *VT = rem <= 32 ? 1 : (rem <= 64 ? 2 : 4);
-    *n_groups = *n_main + 1;
-    *Cpad = (uint32_t)(*n_main * 128 + 32 * *VT);
+    auto fit = [](int c) { return c <= 32 ? 1 : (c <= 64 ? 2 : (c <= 128 ? 4 : 8)); };
+    const int wm = 32 * vmax;
+    if (cols <= wm) {                       // one group, as narrow as fits
+        g.VM = g.VT = std::min(vmax, fit(cols));
+        g.n_main = g.n_groups = 1;
+        g.padded = (uint32_t)(32 * g.VM);
+        return g;
+    }
+    g.VM = vmax;
+    g.n_main = cols / wm;
+    const int rem = cols - g.n_main * wm;
+    if (rem == 0) { g.VT = vmax; g.n_groups = g.n_main; g.padded = (uint32_t)cols; return g; }
+    g.VT = std::min(vmax, fit(rem));
+    g.n_groups = g.n_main + 1;
+    g.padded = (uint32_t)(g.n_main * wm + 32 * g.VT);
+    return g;
 }
 
 static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lanes, int iter_cap, int queue_cap, int n_streams) {
@@ -421,7 +435,9 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     ws_free(w);
     w.K = K; w.slots = slots; w.forced_lanes = forced_lanes; w.iter_cap = iter_cap; w.queue_cap = queue_cap; w.n_streams_cap = n_streams;
     const size_t cols = (size_t)slots * K;
-    plan_groups((int)cols, forced_lanes, &w.VM, &w.VT, &w.n_main, &w.n_groups, &w.Cpad);
+    w.ep = plan_groups((int)cols, 8, forced_lanes);
+    w.mp = plan_groups((int)cols, 4, forced_lanes);
+    w.Cpad = std::max(w.ep.padded, w.mp.padded);
     const size_t L = std::max<uint64_t>(ctx->L, 1), N = std::max<uint64_t>(ctx->N, 1);
     cudaError_t e = cudaSuccess;
     auto A = [&](auto** p, size_t n, bool zero) { if (e == cudaSuccess) e = ws_alloc(w, p, n, zero); };
@@ -429,7 +445,7 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     A(&w.ELL, N * w.Cpad, true); A(&w.W, N * w.Cpad, true); A(&w.LSE, N * slots, true);
     A(&w.st, (size_t)slots, true); A(&w.ctl, 1, true); A(&w.loss, (size_t)slots, true);
     A(&w.col_write, w.Cpad, true); A(&w.k_locked, (size_t)K, true);
-    A(&w.group_active, (size_t)w.n_groups, true); A(&w.counts, cols, true);
+    A(&w.e_group_active, (size_t)w.ep.n_groups, true); A(&w.m_group_active, (size_t)w.mp.n_groups, true); A(&w.counts, cols, true);
     A(&w.queue, (size_t)queue_cap, true); A(&w.draw_of_k, (size_t)K, true);
     A(&w.solve_iters, (size_t)queue_cap, true); A(&w.solve_loss, (size_t)queue_cap, true);
     A(&w.best_lp, N * K, true); A(&w.best_theta, L * K, true);
@@ -458,31 +474,37 @@ struct IterLaunch {
     FinalizeArgs fin;
 };
 
+#define SOUP_DISPATCH(KERNEL, PLAN, ARGS)                                                                    \
+    do {                                                                                                     \
+        const int vm_ = (PLAN).VM, vt_ = (PLAN).VT;                                                          \
+        if (vm_ == 8 && vt_ == 8) KERNEL<8, 8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                  \
+        else if (vm_ == 8 && vt_ == 4) KERNEL<8, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
+        else if (vm_ == 8 && vt_ == 2) KERNEL<8, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
+        else if (vm_ == 8 && vt_ == 1) KERNEL<8, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
+        else if (vm_ == 4 && vt_ == 4) KERNEL<4, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
+        else if (vm_ == 4 && vt_ == 2) KERNEL<4, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
+        else if (vm_ == 4 && vt_ == 1) KERNEL<4, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
+        else if (vm_ == 2) KERNEL<2, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                         \
+        else KERNEL<1, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                                       \
+    } while (0)
+
 static void launch_e(soup_ctx* ctx, float log_prior) {
     Workspace& w = ctx->ws;
     const uint32_t bpg = (uint32_t)((ctx->N + EM_WARPS - 1) / EM_WARPS);
     if (bpg == 0) return;
-    const EArgs a{ctx->d_csr_idx, ctx->d_csr_aux, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB, w.ELL, w.group_active, w.ctl,
-                  ctx->pk_csr, (uint32_t)ctx->N, w.Cpad, bpg, (uint32_t)w.n_main, log_prior};
-    const dim3 grid(bpg * w.n_groups);
-    if (w.VM == 4 && w.VT == 4) estep_kernel<4, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
-    else if (w.VM == 4 && w.VT == 2) estep_kernel<4, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
-    else if (w.VM == 4 && w.VT == 1) estep_kernel<4, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
-    else if (w.VM == 2) estep_kernel<2, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
-    else estep_kernel<1, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+    const EArgs a{ctx->d_csr_idx, ctx->d_csr_aux, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB, w.ELL, w.e_group_active, w.ctl,
+                  ctx->pk_csr, (uint32_t)ctx->N, w.Cpad, bpg, (uint32_t)w.ep.n_main, log_prior};
+    const dim3 grid(bpg * w.ep.n_groups);
+    SOUP_DISPATCH(estep_kernel, w.ep, a);
 }
 static void launch_m(soup_ctx* ctx) {
     Workspace& w = ctx->ws;
     const uint32_t chunks = (uint32_t)((ctx->L + EM_WARPS - 1) / EM_WARPS);
     if (chunks == 0) return;
     const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
-                  w.group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.n_groups, (uint32_t)w.n_main};
-    const dim3 grid(chunks * w.n_groups);
-    if (w.VM == 4 && w.VT == 4) mstep_kernel<4, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
-    else if (w.VM == 4 && w.VT == 2) mstep_kernel<4, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
-    else if (w.VM == 4 && w.VT == 1) mstep_kernel<4, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
-    else if (w.VM == 2) mstep_kernel<2, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
-    else mstep_kernel<1, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(a);
+                  w.m_group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main};
+    const dim3 grid(chunks * w.mp.n_groups);
+    SOUP_DISPATCH(mstep_kernel, w.mp, a);
 }
 static void launch_post(soup_ctx* ctx, int method, bool counts) {
     Workspace& w = ctx->ws;
@@ -584,7 +606,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     while (slots > 1 && (uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32)) --slots;
     if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32))
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: max(cells, loci) * k exceeds the 32-bit row-offset range");
-    const int forced_lanes = (p->lanes == 1 || p->lanes == 2 || p->lanes == 4) ? p->lanes : 0;
+    const int forced_lanes = (p->lanes == 1 || p->lanes == 2 || p->lanes == 4 || p->lanes == 8) ? p->lanes : 0;
     int32_t rc = ensure_workspace(ctx, K, slots, forced_lanes, iter_cap, n_local, p->n_streams);
     if (rc != SOUP_OK) return rc;
     Workspace& w = ctx->ws;
@@ -652,7 +674,9 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0;
     it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, w.draw_of_k, w.TH, w.LA, w.LB,
                            (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream};
-    it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write, w.group_active, K, slots, 32 * w.VM, w.n_main, w.n_groups, iter_cap, w.Cpad, limit};
+    it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write, w.e_group_active, w.m_group_active,
+                          32 * w.ep.VM, 32 * w.ep.VT, w.ep.n_main, w.ep.n_groups, 32 * w.mp.VM, 32 * w.mp.VT, w.mp.n_main, w.mp.n_groups,
+                          K, slots, iter_cap, w.Cpad, limit};
 
     CKS(cudaEventRecord(ctx->ev0, st));
     launch_refill(ctx, it.refill);
@@ -754,7 +778,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         }
     }
     ctx->stats.slot_iterations = fc.slot_iterations;
-    ctx->stats.slots = slots; ctx->stats.lanes = w.VM; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    ctx->stats.slots = slots; ctx->stats.lanes = w.ep.VM; ctx->stats.groups = w.ep.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     ctx->stats.h2d_bytes = h2d; ctx->stats.d2h_bytes = d2h;
     return SOUP_OK;
 }
@@ -786,12 +810,13 @@ static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
     if (k <= 0 || n_slots <= 0 || n_slots > 1024) return ctx->fail(SOUP_ERR_INVALID, "bad k / n_slots");
     if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)n_slots * k + 128) >= (1ull << 32))
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "max(cells, loci) * columns exceeds the 32-bit row-offset range");
-    const int forced = (lanes == 1 || lanes == 2 || lanes == 4) ? lanes : 0;
+    const int forced = (lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8) ? lanes : 0;
     int32_t rc = ensure_workspace(ctx, k, n_slots, forced, 1, n_slots, 1);
     if (rc != SOUP_OK) return rc;
     Workspace& w = ctx->ws;
-    std::vector<int> ga(w.n_groups, 1);
-    cudaMemcpyAsync(w.group_active, ga.data(), ga.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    std::vector<int> ga(std::max(w.ep.n_groups, w.mp.n_groups), 1);
+    cudaMemcpyAsync(w.e_group_active, ga.data(), (size_t)w.ep.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(w.m_group_active, ga.data(), (size_t)w.mp.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);
     Ctl hc{};
     hc.copy_slot = -1; hc.best_solve = -1; hc.best_loss = -INFINITY;
     cudaMemcpyAsync(w.ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream);
@@ -862,7 +887,7 @@ extern "C" int32_t soup_estep(soup_ctx* ctx, int32_t k, int32_t method, int32_t 
     ctx->stats = soup_stats{};
     ctx->stats.kernel_launches = 4 + (log_probs ? 1 : 0) + (weights ? 1 : 0);
     ctx->stats.estep_launches = 1;
-    ctx->stats.slots = n_slots; ctx->stats.lanes = w.VM; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    ctx->stats.slots = n_slots; ctx->stats.lanes = w.ep.VM; ctx->stats.groups = w.ep.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     return SOUP_OK;
 }
 
@@ -909,7 +934,7 @@ extern "C" int32_t soup_mstep(soup_ctx* ctx, int32_t k, int32_t n_slots, int32_t
     ctx->stats = soup_stats{};
     ctx->stats.kernel_launches = 4;
     ctx->stats.mstep_launches = 1;
-    ctx->stats.slots = n_slots; ctx->stats.lanes = w.VM; ctx->stats.groups = w.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
+    ctx->stats.slots = n_slots; ctx->stats.lanes = w.ep.VM; ctx->stats.groups = w.ep.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     return SOUP_OK;
 }
 

@@ -24,6 +24,18 @@ namespace soup {
 #ifndef SOUP_E_U
 #define SOUP_E_U 4       // entries (row gathers) in flight per warp in the E walk
 #endif
+#ifndef SOUP_E_U8
+#define SOUP_E_U8 2      // ... at 8 columns per lane
+#endif
+#ifndef SOUP_E_U16
+#define SOUP_E_U16 2     // ... at 12 / 16 columns per lane
+#endif
+#ifndef SOUP_M_U8
+#define SOUP_M_U8 4
+#endif
+#ifndef SOUP_M_U16
+#define SOUP_M_U16 2
+#endif
 #ifndef SOUP_E_MINB
 #define SOUP_E_MINB 3    // min resident CTAs per SM the E kernel is compiled for
 #endif
@@ -66,19 +78,37 @@ struct Ctl {
 struct IterRec { int temp_step; float loss; float change; int above; };
 
 // ------------------------------------------------------------------ small helpers
+// V = columns per lane.  V <= 4: one vector load per row, lane l owns columns [l*V, l*V+V) of its group.
+// V = 4*H (8, 12, 16): the group is H adjacent 128-column sub-blocks and lane l owns columns
+// [h*128 + 4*l, +4) of every sub-block, so each of the H loads is one fully coalesced 512-byte row piece.
 template <int V> struct FVec { float v[V]; };
-template <int V> __device__ __forceinline__ FVec<V> ld_row(const float* p);
+template <int V> __device__ __forceinline__ constexpr uint32_t lane_cols() { return V < 4 ? V : 4; }
+template <int V> __device__ __forceinline__ FVec<V> ld_row(const float* p) {
+    static_assert(V % 4 == 0, "wide rows are multiples of 4 columns per lane");
+    FVec<V> r;
+#pragma unroll
+    for (int h = 0; h < V / 4; ++h) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p + h * 128));
+        r.v[4 * h] = t.x; r.v[4 * h + 1] = t.y; r.v[4 * h + 2] = t.z; r.v[4 * h + 3] = t.w;
+    }
+    return r;
+}
 template <> __device__ __forceinline__ FVec<1> ld_row<1>(const float* p) { FVec<1> r; r.v[0] = __ldg(p); return r; }
 template <> __device__ __forceinline__ FVec<2> ld_row<2>(const float* p) {
     float2 t = __ldg(reinterpret_cast<const float2*>(p)); FVec<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
 }
-template <> __device__ __forceinline__ FVec<4> ld_row<4>(const float* p) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(p)); FVec<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+template <int V> __device__ __forceinline__ void st_row(float* p, const FVec<V>& x) {
+    static_assert(V % 4 == 0, "wide rows are multiples of 4 columns per lane");
+#pragma unroll
+    for (int h = 0; h < V / 4; ++h)
+        *reinterpret_cast<float4*>(p + h * 128) = make_float4(x.v[4 * h], x.v[4 * h + 1], x.v[4 * h + 2], x.v[4 * h + 3]);
 }
-template <int V> __device__ __forceinline__ void st_row(float* p, const FVec<V>& x);
 template <> __device__ __forceinline__ void st_row<1>(float* p, const FVec<1>& x) { *p = x.v[0]; }
 template <> __device__ __forceinline__ void st_row<2>(float* p, const FVec<2>& x) { *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]); }
-template <> __device__ __forceinline__ void st_row<4>(float* p, const FVec<4>& x) { *reinterpret_cast<float4*>(p) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]); }
+// global column of slot v of lane `lane` in a group starting at col0
+template <int V> __device__ __forceinline__ uint32_t col_of(uint32_t col0, uint32_t lane, int v) {
+    return V < 4 ? col0 + lane * V + v : col0 + (v >> 2) * 128 + lane * 4 + (v & 3);
+}
 
 // base + row * row_bytes in ONE instruction (IMAD.WIDE.U32); the compiler otherwise widens the
 // index arithmetic to 64 bits and spends four instructions per gathered row.
@@ -205,13 +235,14 @@ struct EArgs {
 template <int V>
 __device__ __forceinline__ void estep_body(const EArgs& a, uint32_t cell, uint32_t col0) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t col = col0 + lane * V;
+    const uint32_t col = col0 + lane * lane_cols<V>();
     const uint64_t j0 = a.row_ptr[cell];
     const uint32_t n = (uint32_t)(a.row_ptr[cell + 1] - j0);
     FVec<V> acc;
 #pragma unroll
     for (int v = 0; v < V; ++v) acc.v[v] = a.log_prior;
-    if (!a.ctl->nonfinite) e_walk<V, SOUP_E_U, true>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + col, a.LB + col, a.Cpad * 4u);
+    constexpr int U = V <= 4 ? SOUP_E_U : (V == 8 ? SOUP_E_U8 : SOUP_E_U16);
+    if (!a.ctl->nonfinite) e_walk<V, U, true>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + col, a.LB + col, a.Cpad * 4u);
     else e_walk<V, 2, false>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + col, a.LB + col, a.Cpad * 4u);
     st_row<V>(a.ELL + (size_t)cell * a.Cpad + col, acc);
 }
@@ -219,7 +250,7 @@ __device__ __forceinline__ void estep_body(const EArgs& a, uint32_t cell, uint32
 // grid: group-major (all cells of group 0, then group 1, ...) so one group's table slice stays hot in L2;
 // inside a group the cells are visited longest-first.
 template <int VM, int VT>
-__global__ void __launch_bounds__(EM_THREADS, SOUP_E_MINB) estep_kernel(const EArgs a) {
+__global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_E_MINB : 2)) estep_kernel(const EArgs a) {
     const uint32_t group = blockIdx.x / a.blocks_per_group;
     if (!a.group_active[group]) return;
     const uint32_t chunk = blockIdx.x - group * a.blocks_per_group;
@@ -486,27 +517,29 @@ struct MArgs {
 template <int V>
 __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint32_t col0) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t col = col0 + lane * V;
+    const uint32_t col = col0 + lane * lane_cols<V>();
     const uint64_t j0 = a.col_ptr[locus];
     const uint32_t n = (uint32_t)(a.col_ptr[locus + 1] - j0);
     FVec<V> s, d;
 #pragma unroll
     for (int v = 0; v < V; ++v) { s.v[v] = 1.0f; d.v[v] = 2.0f; }   // pseudocounts S:197-198, S:456-464
-    m_walk<V, SOUP_M_U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
-    const size_t o = (size_t)locus * a.Cpad + col;
+    constexpr int U = V <= 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16);
+    m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        if (!a.col_write[col + v]) continue;          // locked cluster (S:389) or idle column
+        const uint32_t c = col_of<V>(col0, lane, v);
+        if (!a.col_write[c]) continue;                // locked cluster (S:389) or idle column
         const float th = fmaxf(fminf(__fdiv_rn(s.v[v], d.v[v]), 0.99f), 0.01f);   // S:392-393
-        a.TH[o + v] = th;
-        a.LA[o + v] = soupmath::glibc_logf(th);
-        a.LB[o + v] = soupmath::glibc_logf(1.0f - th);
+        const size_t o = (size_t)locus * a.Cpad + c;
+        a.TH[o] = th;
+        a.LA[o] = soupmath::glibc_logf(th);
+        a.LB[o] = soupmath::glibc_logf(1.0f - th);
     }
 }
 
 // grid: locus-major (group fastest) so every group's longest loci start in the first wave (LPT order)
 template <int VM, int VT>
-__global__ void __launch_bounds__(EM_THREADS, SOUP_M_MINB) mstep_kernel(const MArgs a) {
+__global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2)) mstep_kernel(const MArgs a) {
     const uint32_t chunk = blockIdx.x / a.n_groups;
     const uint32_t group = blockIdx.x - chunk * a.n_groups;
     if (!a.group_active[group]) return;
@@ -590,8 +623,11 @@ struct FinalizeArgs {
     const int* queue;
     const uint8_t* k_locked;   // [K]
     uint8_t* col_write;        // [Cpad]
-    int* group_active;         // [n_groups]
-    int K, slots, WM, n_main, n_groups, iter_cap;   // groups [0, n_main): WM columns each; an optional last group takes the rest
+    int* e_group_active;       // [e_groups] column groups of the E kernel
+    int* m_group_active;       // [m_groups] column groups of the M kernel
+    // groups [0, n_main) are WM columns wide; an optional last group starts at n_main*WM and is WT wide
+    int e_WM, e_WT, e_main, e_groups, m_WM, m_WT, m_main, m_groups;
+    int K, slots, iter_cap;
     uint32_t Cpad;
     float limit;
 };
@@ -626,14 +662,17 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
         const int slot = (int)(c / a.K), k = (int)(c - (uint32_t)slot * a.K);
         a.col_write[c] = (slot < a.slots && a.st[slot].active && !a.k_locked[k]) ? 1 : 0;
     }
-    for (int g = threadIdx.x; g < a.n_groups; g += blockDim.x) {
-        const int c0 = g * a.WM, c1 = g < a.n_main ? c0 + a.WM : (int)a.Cpad;
+    for (int g = threadIdx.x; g < a.e_groups + a.m_groups; g += blockDim.x) {
+        const bool is_e = g < a.e_groups;
+        const int gi = is_e ? g : g - a.e_groups;
+        const int WM = is_e ? a.e_WM : a.m_WM, WT = is_e ? a.e_WT : a.m_WT, nm = is_e ? a.e_main : a.m_main;
+        const int c0 = gi * WM, c1 = gi < nm ? c0 + WM : c0 + WT;
         const int first = c0 / a.K;
         int last = (c1 - 1) / a.K;
         if (last >= a.slots) last = a.slots - 1;
         int any = 0;
         for (int s = first; s <= last; ++s) any |= a.st[s].active;
-        a.group_active[g] = any;
+        (is_e ? a.e_group_active : a.m_group_active)[gi] = any;
     }
     if (threadIdx.x == 0) a.ctl->n_active = n_active;
 }

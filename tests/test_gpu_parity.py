@@ -51,7 +51,7 @@ def test_load_builds_csc_totals_lbc(small):
 
 
 @pytest.mark.parametrize("method", [sp.METHOD_EM, sp.METHOD_KHM])
-@pytest.mark.parametrize("lanes", [1, 2, 4])
+@pytest.mark.parametrize("lanes", [0, 1, 2, 4, 8])
 @pytest.mark.parametrize("k", [1, 3, 8])
 def test_estep_mstep_bit_exact(small, method, lanes, k):
     _, csr, ctx, od = small
