@@ -31,13 +31,13 @@ void pinned_free(void* p) { if (p) cudaFreeHost(p); }
 // ------------------------------------------------------------------ workspace of one (K, slots, V) shape
 struct Workspace {
     int K = 0, slots = 0, iter_cap = 0, queue_cap = 0, forced_lanes = 0;
-    struct GroupPlan { int VM = 0, VT = 0, n_main = 0, n_groups = 0; uint32_t padded = 0; } ep, mp;   // E / M kernel column groups
+    struct GroupPlan { int VM = 0, VT = 0, n_main = 0, n_groups = 0; uint32_t padded = 0; } ep, mp, lp;   // E / M wide / M long column groups
     uint32_t Cpad = 0;
     float *LA = nullptr, *LB = nullptr, *TH = nullptr, *ELL = nullptr, *W = nullptr, *LSE = nullptr, *loss = nullptr;
     SlotState* st = nullptr;
     Ctl* ctl = nullptr;
     uint8_t *col_write = nullptr, *k_locked = nullptr;
-    int *e_group_active = nullptr, *m_group_active = nullptr, *counts = nullptr, *queue = nullptr, *draw_of_k = nullptr, *solve_iters = nullptr;
+    int *e_group_active = nullptr, *m_group_active = nullptr, *l_group_active = nullptr, *counts = nullptr, *queue = nullptr, *draw_of_k = nullptr, *solve_iters = nullptr;
     float *solve_loss = nullptr, *best_lp = nullptr, *best_theta = nullptr;
     IterRec* trace = nullptr;
     uint32_t* stream_keys = nullptr;
@@ -63,6 +63,7 @@ struct soup_ctx {
     uint32_t *d_cell_order = nullptr, *d_locus_order = nullptr;
     float* d_total_alleles = nullptr;
     bool loaded = false;
+    uint32_t n_long = 0;   // loci (in LPT order) whose M-pass chain is long enough for the narrow deep-walk role
     Workspace ws;
     // pinned staging for the polling loop
     Ctl* h_ctl = nullptr;
@@ -344,6 +345,15 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     };
     CKL(lpt(ctx->d_row_ptr, (uint32_t)n_cells, ctx->d_cell_order));
     CKL(lpt(ctx->d_col_ptr, (uint32_t)n_loci, ctx->d_locus_order));
+    {   // long loci: covered by >= 40 % of the cells (and >= 512 entries)
+        std::vector<uint64_t> h_col(n_loci + 1);
+        CKL(cudaMemcpy(h_col.data(), ctx->d_col_ptr, (n_loci + 1) * 8, cudaMemcpyDeviceToHost));
+        uint64_t thr = std::max<uint64_t>(512, n_cells * 2 / 5);
+        if (const char* e = getenv("SOUP_LONG_THRESHOLD")) thr = std::max<uint64_t>(1, strtoull(e, nullptr, 10));   // tests / tuning
+        uint32_t cnt = 0;
+        for (uint64_t l = 0; l < n_loci; ++l) cnt += (h_col[l + 1] - h_col[l]) >= thr;
+        ctx->n_long = getenv("SOUP_NO_LONG") ? 0 : cnt;
+    }
     CKL(cudaStreamSynchronize(st));
     CKL(cudaGetLastError());
     cleanup();
@@ -436,8 +446,9 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     w.K = K; w.slots = slots; w.forced_lanes = forced_lanes; w.iter_cap = iter_cap; w.queue_cap = queue_cap; w.n_streams_cap = n_streams;
     const size_t cols = (size_t)slots * K;
     w.ep = plan_groups((int)cols, 8, forced_lanes);
-    w.mp = plan_groups((int)cols, 4, forced_lanes);
-    w.Cpad = std::max(w.ep.padded, w.mp.padded);
+    w.mp = plan_groups((int)cols, SOUP_M_VWIDE, forced_lanes);
+    w.lp = plan_groups((int)cols, SOUP_M_VLONG, SOUP_M_VLONG);
+    w.Cpad = std::max(std::max(w.ep.padded, w.mp.padded), w.lp.padded);
     const size_t L = std::max<uint64_t>(ctx->L, 1), N = std::max<uint64_t>(ctx->N, 1);
     cudaError_t e = cudaSuccess;
     auto A = [&](auto** p, size_t n, bool zero) { if (e == cudaSuccess) e = ws_alloc(w, p, n, zero); };
@@ -445,7 +456,8 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     A(&w.ELL, N * w.Cpad, true); A(&w.W, N * w.Cpad, true); A(&w.LSE, N * slots, true);
     A(&w.st, (size_t)slots, true); A(&w.ctl, 1, true); A(&w.loss, (size_t)slots, true);
     A(&w.col_write, w.Cpad, true); A(&w.k_locked, (size_t)K, true);
-    A(&w.e_group_active, (size_t)w.ep.n_groups, true); A(&w.m_group_active, (size_t)w.mp.n_groups, true); A(&w.counts, cols, true);
+    A(&w.e_group_active, (size_t)w.ep.n_groups, true); A(&w.m_group_active, (size_t)w.mp.n_groups, true);
+    A(&w.l_group_active, (size_t)w.lp.n_groups, true); A(&w.counts, cols, true);
     A(&w.queue, (size_t)queue_cap, true); A(&w.draw_of_k, (size_t)K, true);
     A(&w.solve_iters, (size_t)queue_cap, true); A(&w.solve_loss, (size_t)queue_cap, true);
     A(&w.best_lp, N * K, true); A(&w.best_theta, L * K, true);
@@ -477,7 +489,8 @@ struct IterLaunch {
 #define SOUP_DISPATCH(KERNEL, PLAN, ARGS)                                                                    \
     do {                                                                                                     \
         const int vm_ = (PLAN).VM, vt_ = (PLAN).VT;                                                          \
-        if (vm_ == 8 && vt_ == 8) KERNEL<8, 8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                  \
+        if (vm_ == 16) KERNEL<16, 16><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                           \
+        else if (vm_ == 8 && vt_ == 8) KERNEL<8, 8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                  \
         else if (vm_ == 8 && vt_ == 4) KERNEL<8, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
         else if (vm_ == 8 && vt_ == 2) KERNEL<8, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
         else if (vm_ == 8 && vt_ == 1) KERNEL<8, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
@@ -501,9 +514,14 @@ static void launch_m(soup_ctx* ctx) {
     Workspace& w = ctx->ws;
     const uint32_t chunks = (uint32_t)((ctx->L + EM_WARPS - 1) / EM_WARPS);
     if (chunks == 0) return;
+    const uint32_t n_long = ctx->n_long, long_items = n_long * (uint32_t)w.lp.n_groups;
+    const uint32_t long_blocks = (long_items + EM_WARPS - 1) / EM_WARPS;
+    const uint32_t wide_chunks = (uint32_t)((ctx->L - n_long + EM_WARPS - 1) / EM_WARPS);
     const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
-                  w.m_group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main};
-    const dim3 grid(chunks * w.mp.n_groups);
+                  w.m_group_active, w.l_group_active, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main,
+                  n_long, (uint32_t)w.lp.n_groups, long_blocks};
+    const dim3 grid(long_blocks + wide_chunks * w.mp.n_groups);
+    if (grid.x == 0) return;
     SOUP_DISPATCH(mstep_kernel, w.mp, a);
 }
 static void launch_post(soup_ctx* ctx, int method, bool counts) {
@@ -606,7 +624,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     while (slots > 1 && (uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32)) --slots;
     if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32))
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: max(cells, loci) * k exceeds the 32-bit row-offset range");
-    const int forced_lanes = (p->lanes == 1 || p->lanes == 2 || p->lanes == 4 || p->lanes == 8) ? p->lanes : 0;
+    const int forced_lanes = (p->lanes == 1 || p->lanes == 2 || p->lanes == 4 || p->lanes == 8 || p->lanes == 16) ? p->lanes : 0;
     int32_t rc = ensure_workspace(ctx, K, slots, forced_lanes, iter_cap, n_local, p->n_streams);
     if (rc != SOUP_OK) return rc;
     Workspace& w = ctx->ws;
@@ -674,8 +692,10 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0;
     it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, w.draw_of_k, w.TH, w.LA, w.LB,
                            (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream};
-    it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write, w.e_group_active, w.m_group_active,
-                          32 * w.ep.VM, 32 * w.ep.VT, w.ep.n_main, w.ep.n_groups, 32 * w.mp.VM, 32 * w.mp.VT, w.mp.n_main, w.mp.n_groups,
+    it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write,
+                          {{w.e_group_active, 32 * w.ep.VM, 32 * w.ep.VT, w.ep.n_main, w.ep.n_groups},
+                           {w.m_group_active, 32 * w.mp.VM, 32 * w.mp.VT, w.mp.n_main, w.mp.n_groups},
+                           {w.l_group_active, 32 * w.lp.VM, 32 * w.lp.VT, w.lp.n_main, w.lp.n_groups}},
                           K, slots, iter_cap, w.Cpad, limit};
 
     CKS(cudaEventRecord(ctx->ev0, st));
@@ -814,7 +834,8 @@ static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
     int32_t rc = ensure_workspace(ctx, k, n_slots, forced, 1, n_slots, 1);
     if (rc != SOUP_OK) return rc;
     Workspace& w = ctx->ws;
-    std::vector<int> ga(std::max(w.ep.n_groups, w.mp.n_groups), 1);
+    std::vector<int> ga(std::max(std::max(w.ep.n_groups, w.mp.n_groups), w.lp.n_groups), 1);
+    cudaMemcpyAsync(w.l_group_active, ga.data(), (size_t)w.lp.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(w.e_group_active, ga.data(), (size_t)w.ep.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(w.m_group_active, ga.data(), (size_t)w.mp.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);
     Ctl hc{};

@@ -36,6 +36,18 @@ namespace soup {
 #ifndef SOUP_M_U16
 #define SOUP_M_U16 2
 #endif
+#ifndef SOUP_M_VLONG
+#define SOUP_M_VLONG 1   // columns per lane for the long loci of the M pass
+#endif
+#ifndef SOUP_M_ULONG
+#define SOUP_M_ULONG 16  // row gathers in flight per warp in the long role
+#endif
+#ifndef SOUP_M_DEEP
+#define SOUP_M_DEEP 0    // 1: ping-pong register tiles in the long role (measured slower); 0: single tile of SOUP_M_ULONG rows
+#endif
+#ifndef SOUP_M_VWIDE
+#define SOUP_M_VWIDE 8   // columns per lane for all other loci
+#endif
 #ifndef SOUP_E_MINB
 #define SOUP_E_MINB 3    // min resident CTAs per SM the E kernel is compiled for
 #endif
@@ -507,14 +519,79 @@ __device__ __forceinline__ void m_walk(FVec<V>& s, FVec<V>& d, const uint32_t* _
     }
 }
 
+// Deep walk for the long loci (the M pass's critical path): two register tiles of U gathered rows are
+// kept in flight in ping-pong, so a lone warp always has U..2U row gathers outstanding while it adds.
+template <int V, int U>
+__device__ __forceinline__ void m_issue(FVec<V> (&p)[U], const uint32_t (&x)[U], const Packing& pk, const float* __restrict__ w, uint32_t row_bytes) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = ld_row<V>(row_at(w, x[u] & pk.imask, row_bytes));
+}
+template <int V, int U>
+__device__ __forceinline__ void m_eat(FVec<V>& s, FVec<V>& d, const FVec<V> (&p)[U], const uint32_t (&x)[U], const Packing& pk, const float2* __restrict__ aux) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) m_consume<V, true>(s, d, p[u], x[u], pk, aux + u);
+}
+template <int V, int U>
+__device__ __forceinline__ void m_walk_deep(FVec<V>& s, FVec<V>& d, const uint32_t* __restrict__ q, const float2* __restrict__ aux, uint32_t n,
+                                            const Packing& pk, const float* __restrict__ w, uint32_t row_bytes) {
+    const uint32_t nb = n / U;
+    uint32_t done = 0;
+    if (nb >= 2) {
+        uint32_t xa[U], xb[U], xn[U];
+        FVec<V> pa[U], pb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { xa[u] = __ldg(q + u); xb[u] = __ldg(q + U + u); }
+        m_issue<V, U>(pa, xa, pk, w, row_bytes);
+        m_issue<V, U>(pb, xb, pk, w, row_bytes);
+        uint32_t b = 0;
+#pragma unroll 1
+        for (;;) {
+            bool more = b + 2 < nb;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) xn[u] = __ldg(q + (b + 2) * U + u);
+            }
+            m_eat<V, U>(s, d, pa, xa, pk, aux + b * U);
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) xa[u] = xn[u];
+                m_issue<V, U>(pa, xa, pk, w, row_bytes);
+            }
+            if (b + 1 >= nb) { b += 1; break; }
+            more = b + 3 < nb;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) xn[u] = __ldg(q + (b + 3) * U + u);
+            }
+            m_eat<V, U>(s, d, pb, xb, pk, aux + (b + 1) * U);
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) xb[u] = xn[u];
+                m_issue<V, U>(pb, xb, pk, w, row_bytes);
+            }
+            b += 2;
+            if (b >= nb) break;
+        }
+        done = b * U;
+    }
+#pragma unroll 1
+    for (; done < n; ++done) {
+        const uint32_t wd[1] = {__ldg(q + done)};
+        m_batch<V, 1, true>(s, d, wd, pk, aux + done, w, row_bytes);
+    }
+}
+
 struct MArgs {
     const uint32_t* csc_idx; const float2* csc_aux; const uint64_t* col_ptr; const uint32_t* locus_order;
-    const float* W; float* TH; float* LA; float* LB; const uint8_t* col_write; const int* group_active; const Ctl* ctl;
+    const float* W; float* TH; float* LA; float* LB; const uint8_t* col_write;
+    const int* group_active;        // wide role: column groups of 32*VM (+ one narrower last group)
+    const int* long_group_active;   // long role: column groups of 32*SOUP_M_VLONG
     Packing pk;
     uint32_t L, Cpad, n_groups, n_main;
+    uint32_t n_long, long_groups, long_blocks;   // loci [0, n_long) of the LPT order take the long role
 };
 
-template <int V>
+template <int V, bool DEEP>
 __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint32_t col0) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t col = col0 + lane * lane_cols<V>();
@@ -523,8 +600,16 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
     FVec<V> s, d;
 #pragma unroll
     for (int v = 0; v < V; ++v) { s.v[v] = 1.0f; d.v[v] = 2.0f; }   // pseudocounts S:197-198, S:456-464
-    constexpr int U = V <= 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16);
-    m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+    if (DEEP) {
+#if SOUP_M_DEEP
+        m_walk_deep<V, SOUP_M_ULONG>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+#else
+        m_walk<V, SOUP_M_ULONG, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+#endif
+    } else {
+        constexpr int U = V <= 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16);
+        m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+    }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const uint32_t c = col_of<V>(col0, lane, v);
@@ -537,17 +622,30 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
     }
 }
 
-// grid: locus-major (group fastest) so every group's longest loci start in the first wave (LPT order)
+// Two roles in one grid.  Blocks [0, long_blocks): the n_long longest loci (LPT order), each split into
+// narrow column groups so that many warps share a long locus and each warp's sequential chain is
+// short per entry; they launch first.  Remaining blocks: all other loci with wide column groups
+// (locus-major, group fastest) where the per-entry cost is amortised over more columns.
 template <int VM, int VT>
 __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2)) mstep_kernel(const MArgs a) {
-    const uint32_t chunk = blockIdx.x / a.n_groups;
-    const uint32_t group = blockIdx.x - chunk * a.n_groups;
+    const uint32_t warp = threadIdx.x >> 5;
+    if (blockIdx.x < a.long_blocks) {
+        const uint32_t item = blockIdx.x * EM_WARPS + warp;
+        if (item >= a.n_long * a.long_groups) return;
+        const uint32_t li = item / a.long_groups, group = item - li * a.long_groups;
+        if (!a.long_group_active[group]) return;
+        mstep_body<SOUP_M_VLONG, true>(a, a.locus_order[li], group * (32 * SOUP_M_VLONG));
+        return;
+    }
+    const uint32_t bi = blockIdx.x - a.long_blocks;
+    const uint32_t chunk = bi / a.n_groups;
+    const uint32_t group = bi - chunk * a.n_groups;
     if (!a.group_active[group]) return;
-    const uint32_t li = chunk * EM_WARPS + (threadIdx.x >> 5);
+    const uint32_t li = a.n_long + chunk * EM_WARPS + warp;
     if (li >= a.L) return;
     const uint32_t locus = a.locus_order[li];
-    if (VM == VT || group < a.n_main) mstep_body<VM>(a, locus, group * (32 * VM));
-    else mstep_body<VT>(a, locus, a.n_main * (32 * VM));
+    if (VM == VT || group < a.n_main) mstep_body<VM, false>(a, locus, group * (32 * VM));
+    else mstep_body<VT, false>(a, locus, a.n_main * (32 * VM));
 }
 
 // ------------------------------------------------------------------ harvest: keep the best solve (S:110-114)
@@ -623,10 +721,9 @@ struct FinalizeArgs {
     const int* queue;
     const uint8_t* k_locked;   // [K]
     uint8_t* col_write;        // [Cpad]
-    int* e_group_active;       // [e_groups] column groups of the E kernel
-    int* m_group_active;       // [m_groups] column groups of the M kernel
-    // groups [0, n_main) are WM columns wide; an optional last group starts at n_main*WM and is WT wide
-    int e_WM, e_WT, e_main, e_groups, m_WM, m_WT, m_main, m_groups;
+    // column-group tables (E kernel, M wide role, M long role): groups [0, n_main) are WM columns wide;
+    // an optional last group starts at n_main*WM and is WT wide
+    struct Plan { int* active; int WM, WT, n_main, n_groups; } plan[3];
     int K, slots, iter_cap;
     uint32_t Cpad;
     float limit;
@@ -662,17 +759,17 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
         const int slot = (int)(c / a.K), k = (int)(c - (uint32_t)slot * a.K);
         a.col_write[c] = (slot < a.slots && a.st[slot].active && !a.k_locked[k]) ? 1 : 0;
     }
-    for (int g = threadIdx.x; g < a.e_groups + a.m_groups; g += blockDim.x) {
-        const bool is_e = g < a.e_groups;
-        const int gi = is_e ? g : g - a.e_groups;
-        const int WM = is_e ? a.e_WM : a.m_WM, WT = is_e ? a.e_WT : a.m_WT, nm = is_e ? a.e_main : a.m_main;
-        const int c0 = gi * WM, c1 = gi < nm ? c0 + WM : c0 + WT;
-        const int first = c0 / a.K;
-        int last = (c1 - 1) / a.K;
-        if (last >= a.slots) last = a.slots - 1;
-        int any = 0;
-        for (int s = first; s <= last; ++s) any |= a.st[s].active;
-        (is_e ? a.e_group_active : a.m_group_active)[gi] = any;
+    for (int t = 0; t < 3; ++t) {
+        const FinalizeArgs::Plan pl = a.plan[t];
+        for (int g = threadIdx.x; g < pl.n_groups; g += blockDim.x) {
+            const int c0 = g * pl.WM, c1 = g < pl.n_main ? c0 + pl.WM : c0 + pl.WT;
+            const int first = c0 / a.K;
+            int last = (c1 - 1) / a.K;
+            if (last >= a.slots) last = a.slots - 1;
+            int any = 0;
+            for (int s = first; s <= last; ++s) any |= a.st[s].active;
+            pl.active[g] = any;
+        }
     }
     if (threadIdx.x == 0) a.ctl->n_active = n_active;
 }

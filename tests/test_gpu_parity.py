@@ -14,10 +14,17 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-@pytest.fixture(scope="module")
-def small():
+@pytest.fixture(scope="module", params=["default", "long_role"])
+def small(request):
+    """`long_role` lowers the long-locus threshold so the M kernel's deep narrow-group role runs on this small matrix."""
+    import os
     v, csr = synth_csr()
-    ctx = sp.Context(0).load_csr(*csr)
+    if request.param == "long_role":
+        os.environ["SOUP_LONG_THRESHOLD"] = "12"
+    try:
+        ctx = sp.Context(0).load_csr(*csr)
+    finally:
+        os.environ.pop("SOUP_LONG_THRESHOLD", None)
     od = orc.OracleData.from_csr(*csr)
     yield v, csr, ctx, od
     ctx.close()
