@@ -46,8 +46,33 @@ struct Workspace {
     size_t bytes = 0;
 };
 
+struct DevBuf {   // grow-only device allocation
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~DevBuf() {}
+};
+struct LoadBufs {
+    DevBuf row_ptr, col_ptr, csr_idx, csc_idx, csr_aux, csc_aux, cell_order, locus_order, total_alleles;   // the matrix
+    DevBuf locus, alt, ref, vals, vals2, keys, keys2, len, len2, idx, idx2, tmp, flags;                        // load-time scratch
+    void release_all() {
+        for (DevBuf* b : {&row_ptr, &col_ptr, &csr_idx, &csc_idx, &csr_aux, &csc_aux, &cell_order, &locus_order, &total_alleles,
+                          &locus, &alt, &ref, &vals, &vals2, &keys, &keys2, &len, &len2, &idx, &idx2, &tmp, &flags}) b->release();
+    }
+};
+
 struct soup_ctx {
     int device = 0;
+    LoadBufs lb;
+    bool lbc_table_set = false;
     cudaStream_t stream = nullptr, side = nullptr;   // side: loss + control, concurrent with the M pass
     bool own_stream = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -106,9 +131,7 @@ static cudaError_t ws_alloc(Workspace& w, T** p, size_t count, bool zero) {
 }
 
 static void free_matrix(soup_ctx* ctx) {
-    cudaFree(ctx->d_row_ptr); cudaFree(ctx->d_col_ptr); cudaFree(ctx->d_csr_idx); cudaFree(ctx->d_csc_idx);
-    cudaFree(ctx->d_csr_aux); cudaFree(ctx->d_csc_aux);
-    cudaFree(ctx->d_cell_order); cudaFree(ctx->d_locus_order); cudaFree(ctx->d_total_alleles);
+    ctx->lb.release_all();
     ctx->d_row_ptr = ctx->d_col_ptr = nullptr;
     ctx->d_csr_idx = ctx->d_csc_idx = nullptr;
     ctx->d_csr_aux = nullptr; ctx->d_csc_aux = nullptr;
@@ -193,30 +216,68 @@ extern "C" void soup_ctx_destroy(soup_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------ soup_load_csr
+#include <chrono>
+struct PhaseTimer {
+    bool on = getenv("SOUP_DEBUG_ITERS") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "soup_debug phase %-28s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loci, uint64_t nnz_in, const uint64_t* row_ptr,
                                  const uint32_t* locus, const uint32_t* alt, const uint32_t* ref) {
     if (!ctx) return SOUP_ERR_INVALID;
+    PhaseTimer pt;
     if (!row_ptr || (nnz_in && (!locus || !alt || !ref))) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: null pointer");
     if (n_cells >= (1u << 30) || n_loci >= (1u << 30) || nnz_in >= INT32_MAX)
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_load_csr: more than 2^30 cells / loci or 2^31 entries are not supported");
     if (row_ptr[0] != 0 || row_ptr[n_cells] != nnz_in) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: row_ptr does not span [0, nnz]");
+    for (uint64_t c = 0; c < n_cells; ++c)
+        if (row_ptr[c + 1] < row_ptr[c]) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: row_ptr not monotone at cell %llu", (unsigned long long)c);
     CK(cudaSetDevice(ctx->device));
     ctx->stats = soup_stats{};
-    // validate (loci strictly ascending inside a cell: the order S:663-674 appends in); drop ref+alt == 0 (S:664)
-    bool has_zero = false;
-    std::vector<uint32_t> big_idx;
-    for (uint64_t c = 0; c < n_cells; ++c) {
-        if (row_ptr[c + 1] < row_ptr[c]) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: row_ptr not monotone at cell %llu", (unsigned long long)c);
-        for (uint64_t j = row_ptr[c]; j < row_ptr[c + 1]; ++j) {
-            if (locus[j] >= n_loci) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: locus index out of range at entry %llu", (unsigned long long)j);
-            if (j > row_ptr[c] && locus[j] <= locus[j - 1]) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: loci must be strictly ascending inside a cell (cell %llu)", (unsigned long long)c);
-            if ((uint32_t)(alt[j] + ref[j]) == 0) has_zero = true;
-        }
-    }
+    ctx->loaded = false;
+    cudaStream_t st = ctx->stream;
+    // Device buffers are grow-only and cached in the context: reloading a matrix of the same size allocates nothing.
+    LoadBufs& B = ctx->lb;
+    const bool same_shape = ctx->N == n_cells && ctx->L == n_loci;
+    if (!same_shape) ws_free(ctx->ws);
+#define CKL(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) { cudaGetLastError(); return ctx->fail(e_ == cudaErrorMemoryAllocation ? SOUP_ERR_NOMEM : SOUP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
     std::vector<uint64_t> rp2;
     std::vector<uint32_t> l2, a2, r2;
     uint64_t nnz = nnz_in;
-    if (has_zero) {
+    LoadFlags flags{};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const size_t nz = std::max<uint64_t>(nnz, 1);
+        CKL(B.row_ptr.ensure((n_cells + 1) * 8)); CKL(B.locus.ensure(nz * 4)); CKL(B.alt.ensure(nz * 4)); CKL(B.ref.ensure(nz * 4));
+        CKL(B.flags.ensure(sizeof(LoadFlags)));
+        CKL(cudaMemcpyAsync(B.row_ptr.p, row_ptr, (n_cells + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (nnz) {
+            CKL(cudaMemcpyAsync(B.locus.p, locus, nnz * 4, cudaMemcpyHostToDevice, st));
+            CKL(cudaMemcpyAsync(B.alt.p, alt, nnz * 4, cudaMemcpyHostToDevice, st));
+            CKL(cudaMemcpyAsync(B.ref.p, ref, nnz * 4, cudaMemcpyHostToDevice, st));
+        }
+        ctx->stats.h2d_bytes += (n_cells + 1) * 8 + nnz * 12;
+        // validate on the device: loci strictly ascending inside a cell (the order S:663-674 appends in) and in range;
+        // count ref+alt == 0 entries (dropped, S:664) and counts beyond the ln-factorial table
+        CKL(cudaMemsetAsync(B.flags.p, 0, sizeof(LoadFlags), st));
+        if (n_cells) validate_csr_kernel<<<(unsigned)((n_cells + 7) / 8), 256, 0, st>>>((const uint64_t*)B.row_ptr.p, (const uint32_t*)B.locus.p, (const uint32_t*)B.alt.p,
+                                                                                        (const uint32_t*)B.ref.p, (LoadFlags*)B.flags.p, (uint32_t)n_cells, (uint32_t)n_loci);
+        CKL(cudaMemcpyAsync(&flags, B.flags.p, sizeof(LoadFlags), cudaMemcpyDeviceToHost, st));
+        CKL(cudaStreamSynchronize(st));
+        if (flags.bad_range) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: locus index out of range (cell %u)", flags.bad_cell);
+        if (flags.bad_order) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: loci must be strictly ascending inside a cell (cell %u)", flags.bad_cell);
+        if (flags.n_zero == 0 || attempt == 1) break;
+        // rare: explicit all-zero entries -> compact on the host (S:664) and upload again
         rp2.resize(n_cells + 1);
         l2.reserve(nnz_in); a2.reserve(nnz_in); r2.reserve(nnz_in);
         for (uint64_t c = 0; c < n_cells; ++c) {
@@ -228,12 +289,7 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
         nnz = l2.size();
         row_ptr = rp2.data(); locus = l2.data(); alt = a2.data(); ref = r2.data();
     }
-    std::vector<float> big_val;
-    for (uint64_t j = 0; j < nnz; ++j)
-        if ((uint32_t)(alt[j] + ref[j]) > 170u) { big_idx.push_back((uint32_t)j); big_val.push_back(ln_binomial_f32(alt[j] + ref[j], alt[j])); }
-
-    free_matrix(ctx);
-    ws_free(ctx->ws);
+    pt.lap("load: h2d + validate");
     ctx->N = n_cells; ctx->L = n_loci; ctx->nnz = nnz;
     // packed entry words: index bits as needed, the rest split between the two count fields (<= 6 bits each)
     auto make_packing = [](uint64_t n_index) {
@@ -247,118 +303,102 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
         pk.imask = (1u << pk.sh_r) - 1;
         return pk;
     };
-    ctx->pk_csr = make_packing(n_loci);
-    ctx->pk_csc = make_packing(n_cells);
-    {   // ln_binomial table for in-field counts (statrs FCACHE arithmetic, S:669-670)
+    const Packing pk_csr = make_packing(n_loci);
+    if (!same_shape || pk_csr.cbits != ctx->pk_csr.cbits || !ctx->lbc_table_set) {
+        // ln_binomial table for in-field counts (statrs FCACHE arithmetic, S:669-670)
         std::vector<float> tab(4096, 0.0f);
-        const uint32_t cb = ctx->pk_csr.cbits;
+        const uint32_t cb = pk_csr.cbits;
         for (uint32_t a = 0; a < (1u << cb); ++a)
             for (uint32_t r = 0; r < (1u << cb); ++r) tab[(a << cb) | r] = ln_binomial_f32(a + r, a);
-        CK(cudaMemcpyToSymbol(c_lbc, tab.data(), tab.size() * sizeof(float)));
+        CKL(cudaMemcpyToSymbolAsync(c_lbc, tab.data(), tab.size() * sizeof(float), 0, cudaMemcpyHostToDevice, st));
+        CKL(cudaStreamSynchronize(st));
+        ctx->lbc_table_set = true;
     }
-    cudaStream_t st = ctx->stream;
+    ctx->pk_csr = pk_csr;
+    ctx->pk_csc = make_packing(n_cells);
     const size_t nz = std::max<uint64_t>(nnz, 1);
-    uint32_t *d_locus = nullptr, *d_alt = nullptr, *d_ref = nullptr, *d_vals = nullptr, *d_vals2 = nullptr, *d_len = nullptr, *d_len2 = nullptr, *d_idx = nullptr;
-    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
-    void* d_tmp = nullptr;
-    auto cleanup = [&] {
-        cudaFree(d_locus); cudaFree(d_alt); cudaFree(d_ref); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_keys); cudaFree(d_keys2);
-        cudaFree(d_len); cudaFree(d_len2); cudaFree(d_idx); cudaFree(d_tmp);
-    };
-#define CKL(call)                                                                                         \
-    do {                                                                                                  \
-        cudaError_t e_ = (call);                                                                          \
-        if (e_ != cudaSuccess) { cleanup(); free_matrix(ctx); return ctx->fail(e_ == cudaErrorMemoryAllocation ? SOUP_ERR_NOMEM : SOUP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
-    } while (0)
-    CKL(cudaMalloc(&ctx->d_row_ptr, (n_cells + 1) * sizeof(uint64_t)));
-    CKL(cudaMalloc(&ctx->d_col_ptr, (n_loci + 1) * sizeof(uint64_t)));
-    CKL(cudaMalloc(&ctx->d_csr_idx, nz * sizeof(uint32_t)));
-    CKL(cudaMalloc(&ctx->d_csc_idx, nz * sizeof(uint32_t)));
-    CKL(cudaMalloc(&ctx->d_csr_aux, nz * sizeof(float4)));
-    CKL(cudaMalloc(&ctx->d_csc_aux, nz * sizeof(float2)));
-    CKL(cudaMalloc(&ctx->d_cell_order, std::max<uint64_t>(n_cells, 1) * sizeof(uint32_t)));
-    CKL(cudaMalloc(&ctx->d_locus_order, std::max<uint64_t>(n_loci, 1) * sizeof(uint32_t)));
-    CKL(cudaMalloc(&ctx->d_total_alleles, std::max<uint64_t>(n_cells, 1) * sizeof(float)));
-    CKL(cudaMalloc(&d_locus, nz * 4)); CKL(cudaMalloc(&d_alt, nz * 4)); CKL(cudaMalloc(&d_ref, nz * 4));
-    CKL(cudaMalloc(&d_vals, nz * 4)); CKL(cudaMalloc(&d_vals2, nz * 4));
-    CKL(cudaMalloc(&d_keys, nz * 8)); CKL(cudaMalloc(&d_keys2, nz * 8));
     const size_t nmax = std::max<uint64_t>(std::max(n_cells, n_loci), 1);
-    CKL(cudaMalloc(&d_len, nmax * 4)); CKL(cudaMalloc(&d_len2, nmax * 4)); CKL(cudaMalloc(&d_idx, nmax * 4));
-    CKL(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, (n_cells + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    if (nnz) {
-        CKL(cudaMemcpyAsync(d_locus, locus, nnz * 4, cudaMemcpyHostToDevice, st));
-        CKL(cudaMemcpyAsync(d_alt, alt, nnz * 4, cudaMemcpyHostToDevice, st));
-        CKL(cudaMemcpyAsync(d_ref, ref, nnz * 4, cudaMemcpyHostToDevice, st));
-    }
-    ctx->stats.h2d_bytes = (n_cells + 1) * 8 + nnz * 12;
+    CKL(B.col_ptr.ensure((n_loci + 1) * 8)); CKL(B.csr_idx.ensure(nz * 4)); CKL(B.csc_idx.ensure(nz * 4));
+    CKL(B.csr_aux.ensure(nz * sizeof(float4))); CKL(B.csc_aux.ensure(nz * sizeof(float2)));
+    CKL(B.cell_order.ensure(std::max<uint64_t>(n_cells, 1) * 4)); CKL(B.locus_order.ensure(std::max<uint64_t>(n_loci, 1) * 4));
+    CKL(B.total_alleles.ensure(std::max<uint64_t>(n_cells, 1) * 4));
+    CKL(B.vals.ensure(nz * 4)); CKL(B.vals2.ensure(nz * 4)); CKL(B.keys.ensure(nz * 8)); CKL(B.keys2.ensure(nz * 8));
+    CKL(B.len.ensure(nmax * 4)); CKL(B.len2.ensure(nmax * 4)); CKL(B.idx.ensure(nmax * 4)); CKL(B.idx2.ensure(nmax * 4));
+    ctx->d_row_ptr = (uint64_t*)B.row_ptr.p; ctx->d_col_ptr = (uint64_t*)B.col_ptr.p;
+    ctx->d_csr_idx = (uint32_t*)B.csr_idx.p; ctx->d_csc_idx = (uint32_t*)B.csc_idx.p;
+    ctx->d_csr_aux = (float4*)B.csr_aux.p; ctx->d_csc_aux = (float2*)B.csc_aux.p;
+    ctx->d_cell_order = (uint32_t*)B.cell_order.p; ctx->d_locus_order = (uint32_t*)B.locus_order.p;
+    ctx->d_total_alleles = (float*)B.total_alleles.p;
+    uint32_t *d_locus = (uint32_t*)B.locus.p, *d_alt = (uint32_t*)B.alt.p, *d_ref = (uint32_t*)B.ref.p;
+    uint32_t *d_vals = (uint32_t*)B.vals.p, *d_vals2 = (uint32_t*)B.vals2.p, *d_len = (uint32_t*)B.len.p, *d_len2 = (uint32_t*)B.len2.p;
+    uint32_t *d_idx = (uint32_t*)B.idx.p, *d_idx2 = (uint32_t*)B.idx2.p;
+    unsigned long long *d_keys = (unsigned long long*)B.keys.p, *d_keys2 = (unsigned long long*)B.keys2.p;
     if (n_cells) {
         build_csr_kernel<<<(unsigned)((n_cells + 7) / 8), 256, 0, st>>>(ctx->d_row_ptr, d_locus, d_alt, d_ref, ctx->d_csr_idx, ctx->d_csr_aux, d_keys,
                                                                         d_vals, ctx->d_total_alleles, ctx->pk_csr, (uint32_t)n_cells);
         CKL(cudaGetLastError());
     }
-    if (!big_idx.empty()) {   // ln_binomial for n > 170 comes from the host (statrs ln_gamma branch)
-        uint32_t* d_bi = nullptr; float* d_bv = nullptr;
-        CKL(cudaMalloc(&d_bi, big_idx.size() * 4));
-        cudaError_t e2 = cudaMalloc(&d_bv, big_val.size() * 4);
-        if (e2 != cudaSuccess) { cudaFree(d_bi); CKL(e2); }
-        cudaMemcpyAsync(d_bi, big_idx.data(), big_idx.size() * 4, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(d_bv, big_val.data(), big_val.size() * 4, cudaMemcpyHostToDevice, st);
-        patch_lbc_kernel<<<(unsigned)((big_idx.size() + 255) / 256), 256, 0, st>>>(ctx->d_csr_aux, d_bi, d_bv, (uint32_t)big_idx.size());
-        cudaStreamSynchronize(st);
-        cudaFree(d_bi); cudaFree(d_bv);
-        CKL(cudaGetLastError());
+    if (flags.n_big) {   // rare: ln_binomial for n > 170 comes from the host (statrs ln_gamma branch)
+        std::vector<uint32_t> big_idx;
+        std::vector<float> big_val;
+        for (uint64_t j = 0; j < nnz; ++j)
+            if ((uint32_t)(alt[j] + ref[j]) > 170u) { big_idx.push_back((uint32_t)j); big_val.push_back(ln_binomial_f32(alt[j] + ref[j], alt[j])); }
+        DevBuf bi, bv;
+        CKL(bi.ensure(big_idx.size() * 4)); CKL(bv.ensure(big_val.size() * 4));
+        CKL(cudaMemcpyAsync(bi.p, big_idx.data(), big_idx.size() * 4, cudaMemcpyHostToDevice, st));
+        CKL(cudaMemcpyAsync(bv.p, big_val.data(), big_val.size() * 4, cudaMemcpyHostToDevice, st));
+        patch_lbc_kernel<<<(unsigned)((big_idx.size() + 255) / 256), 256, 0, st>>>(ctx->d_csr_aux, (const uint32_t*)bi.p, (const float*)bv.p, (uint32_t)big_idx.size());
+        CKL(cudaStreamSynchronize(st));
         ctx->stats.h2d_bytes += big_idx.size() * 8;
     }
     // CSC transpose: stable radix sort of (locus, cell) keys -> cells ascending inside a locus (S:227 order)
-    int bits_l = 1, bits_total;
+    int bits_l = 1, bits_c = 1;
     while ((1ull << bits_l) < std::max<uint64_t>(n_loci, 2)) ++bits_l;
-    bits_total = 32 + bits_l;
+    while ((1ull << bits_c) < std::max<uint64_t>(n_cells, 2)) ++bits_c;
     size_t tmp_bytes = 0, tmp2 = 0;
     cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys2);
     cub::DoubleBuffer<uint32_t> vb(d_vals, d_vals2);
-    cub::DoubleBuffer<uint32_t> lb(d_len, d_len2), ib(d_idx, d_vals2);
-    CKL(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)nnz, 0, bits_total, st));
-    CKL(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, lb, ib, (int)nmax, 0, 32, st));
-    tmp_bytes = std::max(tmp_bytes, tmp2);
-    CKL(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    {
+        cub::DoubleBuffer<uint32_t> lq(d_len, d_len2), iq(d_idx, d_idx2);
+        CKL(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)nnz, 0, 32 + bits_l, st));
+        CKL(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, lq, iq, (int)nmax, 0, 32, st));
+    }
+    tmp_bytes = std::max<size_t>(std::max(tmp_bytes, tmp2), 16);
+    CKL(B.tmp.ensure(tmp_bytes));
     if (nnz) {
-        CKL(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, kb, vb, (int)nnz, 0, bits_total, st));
+        // the CSR already is sorted by cell, and LSD radix passes are stable: sorting on the locus bits alone is enough
+        CKL(cub::DeviceRadixSort::SortPairs(B.tmp.p, tmp_bytes, kb, vb, (int)nnz, 32, 32 + bits_l, st));
         build_csc_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(kb.Current(), vb.Current(), d_alt, d_ref, ctx->d_csc_idx, ctx->d_csc_aux, ctx->pk_csc, nnz);
         CKL(cudaGetLastError());
     }
+    (void)bits_c;
     col_ptr_kernel<<<(unsigned)((n_loci + 1 + 255) / 256), 256, 0, st>>>(kb.Current(), nnz, ctx->d_col_ptr, (uint32_t)n_loci);
     CKL(cudaGetLastError());
     // longest-first (LPT) visiting orders for the E and M kernels (ties -> ascending index; stable sort)
     auto lpt = [&](const uint64_t* ptr, uint32_t n, uint32_t* order) -> cudaError_t {
         if (n == 0) return cudaSuccess;
-        uint32_t* idx2 = nullptr;
-        cudaError_t e = cudaMalloc(&idx2, (size_t)n * 4);
-        if (e != cudaSuccess) return e;
         seg_len_kernel<<<(n + 255) / 256, 256, 0, st>>>(ptr, d_len, d_idx, n);
-        cub::DoubleBuffer<uint32_t> k(d_len, d_len2), v(d_idx, idx2);
+        cub::DoubleBuffer<uint32_t> k(d_len, d_len2), v(d_idx, d_idx2);
         size_t tb = tmp_bytes;
-        e = cub::DeviceRadixSort::SortPairsDescending(d_tmp, tb, k, v, (int)n, 0, 32, st);
+        cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(B.tmp.p, tb, k, v, (int)n, 0, 32, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(order, v.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
-        cudaStreamSynchronize(st);
-        cudaFree(idx2);
+        if (e == cudaSuccess && k.Current() != d_len) e = cudaMemcpyAsync(d_len, k.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
         return e;
     };
     CKL(lpt(ctx->d_row_ptr, (uint32_t)n_cells, ctx->d_cell_order));
     CKL(lpt(ctx->d_col_ptr, (uint32_t)n_loci, ctx->d_locus_order));
-    {   // long loci: covered by >= 40 % of the cells (and >= 512 entries)
-        std::vector<uint64_t> h_col(n_loci + 1);
-        CKL(cudaMemcpy(h_col.data(), ctx->d_col_ptr, (n_loci + 1) * 8, cudaMemcpyDeviceToHost));
+    {   // long loci: covered by >= 40 % of the cells (and >= 512 entries); d_len now holds the locus lengths, descending
         uint64_t thr = std::max<uint64_t>(512, n_cells * 2 / 5);
         if (const char* e = getenv("SOUP_LONG_THRESHOLD")) thr = std::max<uint64_t>(1, strtoull(e, nullptr, 10));   // tests / tuning
-        uint32_t cnt = 0;
-        for (uint64_t l = 0; l < n_loci; ++l) cnt += (h_col[l + 1] - h_col[l]) >= thr;
-        ctx->n_long = getenv("SOUP_NO_LONG") ? 0 : cnt;
+        count_ge_kernel<<<1, 1, 0, st>>>(d_len, (uint32_t)n_loci, (uint32_t)std::min<uint64_t>(thr, UINT32_MAX), &((LoadFlags*)B.flags.p)->n_long);
+        CKL(cudaMemcpyAsync(&flags, B.flags.p, sizeof(LoadFlags), cudaMemcpyDeviceToHost, st));
+        CKL(cudaStreamSynchronize(st));
+        ctx->n_long = getenv("SOUP_NO_LONG") ? 0 : flags.n_long;
     }
-    CKL(cudaStreamSynchronize(st));
     CKL(cudaGetLastError());
-    cleanup();
+    pt.lap("load: build csr/csc/lpt");
 #undef CKL
-    ctx->stats.kernel_launches = 6;
+    ctx->stats.kernel_launches = 8;
     ctx->loaded = true;
     return SOUP_OK;
 }
@@ -624,9 +664,11 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     while (slots > 1 && (uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32)) --slots;
     if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32))
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: max(cells, loci) * k exceeds the 32-bit row-offset range");
+    PhaseTimer pt;
     const int forced_lanes = (p->lanes == 1 || p->lanes == 2 || p->lanes == 4 || p->lanes == 8 || p->lanes == 16) ? p->lanes : 0;
     int32_t rc = ensure_workspace(ctx, K, slots, forced_lanes, iter_cap, n_local, p->n_streams);
     if (rc != SOUP_OK) return rc;
+    pt.lap("solve: workspace");
     Workspace& w = ctx->ws;
     cudaStream_t st = ctx->stream;
 
@@ -744,6 +786,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
 
+    pt.lap("solve: iterate");
     // ---- results
     Ctl fc;
     CKS(cudaMemcpy(&fc, w.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
@@ -775,6 +818,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         ctx->h_trace_iters = h_iters;
     }
     cleanup();
+    pt.lap("solve: results");
 #undef CKS
     ctx->stats.kernel_launches = launches;
     ctx->stats.estep_launches = iters_enqueued;

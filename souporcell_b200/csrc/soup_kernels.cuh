@@ -777,6 +777,36 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
 // ------------------------------------------------------------------ load-time kernels
 __constant__ double c_ln_factorial[171];   // statrs FCACHE: ln(n!) for n <= 170 (S:669-670)
 
+struct LoadFlags { uint32_t bad_range, bad_order, bad_cell, n_zero, n_big, n_long; };
+
+__global__ void validate_csr_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ locus, const uint32_t* __restrict__ alt,
+                                    const uint32_t* __restrict__ ref, LoadFlags* flags, uint32_t N, uint32_t L) {
+    const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (cell >= N) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t j0 = row_ptr[cell], j1 = row_ptr[cell + 1];
+    uint32_t zeros = 0, big = 0;
+    for (uint64_t j = j0 + lane; j < j1; j += 32) {
+        const uint32_t l = locus[j];
+        if (l >= L) { flags->bad_range = 1; flags->bad_cell = cell; }
+        if (j > j0 && l <= locus[j - 1]) { flags->bad_order = 1; flags->bad_cell = cell; }
+        const uint32_t n = alt[j] + ref[j];
+        zeros += n == 0;
+        big += n > 170u;
+    }
+    if (zeros) atomicAdd(&flags->n_zero, zeros);
+    if (big) atomicAdd(&flags->n_big, big);
+}
+// number of leading elements >= thr in a descending array
+__global__ void count_ge_kernel(const uint32_t* __restrict__ sorted_desc, uint32_t n, uint32_t thr, uint32_t* out) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sorted_desc[mid] >= thr) lo = mid + 1; else hi = mid;
+    }
+    *out = lo;
+}
+
 __device__ __forceinline__ uint32_t pack_word(uint32_t idx, uint32_t c0, uint32_t c1, const Packing& pk) {
     if (c0 >= pk.cmask || c1 >= pk.cmask) c0 = c1 = pk.cmask;   // out-of-field: marker, the side record holds the counts
     return (c0 << pk.sh_a) | (c1 << pk.sh_r) | idx;
