@@ -212,6 +212,12 @@ typedef struct soup_main_result {
     double estep_ms, mstep_ms; /* context 0, time_kernels = 1 */
 } soup_main_result;
 int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_main_params* p, soup_main_result* r, void* log_file);
+/* The per-run cross-process step of soup_main on its own (host only): every rank passes its best
+ * (loss, solve, has_best) and buffers; on return all ranks hold the winner's (higher loss; ties ->
+ * lowest solve index, S:110/S:120).  Buffers may be NULL. */
+int32_t soup_exchange_best(int32_t rank, int32_t world, soup_allgather_fn allgather, soup_bcast_fn bcast, void* user,
+                           float* loss, int32_t* solve, int32_t* has_best, float* log_probs, uint64_t n_log_probs,
+                           float* theta, uint64_t n_theta, int32_t* winner_rank);
 
 /* TSV writer S:133-147 into `out_file` (a FILE*): barcode, FIRST-max cluster, k log-probs. */
 int32_t soup_write_clusters(void* out_file, const char* barcode_blob, uint64_t n_barcodes,

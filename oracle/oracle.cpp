@@ -316,7 +316,7 @@ static void update_final_with_lock(size_t loci, const std::vector<std::vector<fl
         for (size_t c = 0; c < sums.size(); ++c) {
             if (std::find(locked.begin(), locked.end(), c) != locked.end()) continue;
             float update = sums[c][locus] / denoms[c][locus];
-            centers[c][locus] = std::max(std::min(update, 0.99f), 0.01f);
+            centers[c][locus] = fmaxf(fminf(update, 0.99f), 0.01f);   // Rust f32::min / max ignore a NaN operand
         }
 }
 

@@ -31,7 +31,7 @@ EXPORTS = [
     "soup_chacha_words", "soup_thread_seeds", "soup_format_f32", "soup_ln_binomial_f32", "soup_bad_cluster_detection",
     "soup_ctx_create", "soup_ctx_destroy", "soup_load_csr", "soup_get_dims", "soup_get_csc", "soup_get_cell_totals",
     "soup_get_csr_lbc", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
-    "soup_main", "soup_write_clusters",
+    "soup_main", "soup_exchange_best", "soup_write_clusters",
 ]
 
 
@@ -131,6 +131,8 @@ def lib():
         L.soup_mstep.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.soup_device_math.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64]
         L.soup_main.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(_MainParams), C.POINTER(_MainResult), C.c_void_p]
+        L.soup_exchange_best.argtypes = [C.c_int32, C.c_int32, ALLGATHER_FN, BCAST_FN, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32)]
         L.soup_write_clusters.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32]
         _lib = L
     return _lib
@@ -441,6 +443,15 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
     _check(lib().soup_main(arr, len(ctxs), C.byref(p), C.byref(r), None))
     return MainResult(bool(r.has_best), r.runs, float(r.best_loss), lp, th, int(r.nnz_updates), int(r.kernel_launches), float(r.solve_ms),
                       int(r.slot_iterations), int(r.timed_iterations), float(r.estep_ms), float(r.mstep_ms))
+
+
+def exchange_best(rank, world, allgather, bcast, loss, solve, has_best, log_probs=None, theta=None):
+    """soup_exchange_best: returns (loss, solve, has_best, winner_rank); log_probs / theta (float32 arrays) are overwritten in place."""
+    l, s_, h, w = C.c_float(loss), C.c_int32(solve), C.c_int32(int(has_best)), C.c_int32(-1)
+    _check(lib().soup_exchange_best(rank, world, allgather, bcast, None, C.byref(l), C.byref(s_), C.byref(h),
+                                    _ptr(log_probs), 0 if log_probs is None else log_probs.size,
+                                    _ptr(theta), 0 if theta is None else theta.size, C.byref(w)))
+    return float(l.value), int(s_.value), bool(h.value), int(w.value)
 
 
 def torch_exchange_callbacks(dist):

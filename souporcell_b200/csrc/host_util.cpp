@@ -54,7 +54,8 @@ std::string format_f32(float v) {
     if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
     if (v == 0.0f) return std::signbit(v) ? "-0" : "0";
     char buf[48];
-    auto res = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
+    auto res = std::to_chars(buf, buf + sizeof(buf) - 1, v, std::chars_format::scientific);
+    *res.ptr = '\0';   // to_chars does not terminate; the exponent is parsed with atoi below
     const char* p = buf;
     std::string out;
     if (*p == '-') { out.push_back('-'); ++p; }

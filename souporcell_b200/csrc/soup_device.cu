@@ -72,7 +72,6 @@ struct LoadBufs {
 struct soup_ctx {
     int device = 0;
     LoadBufs lb;
-    bool lbc_table_set = false;
     cudaStream_t stream = nullptr, side = nullptr;   // side: loss + control, concurrent with the M pass
     bool own_stream = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -119,14 +118,16 @@ static void ws_free(Workspace& w) {
     for (void* p : w.allocs) cudaFree(p);
     w = Workspace();
 }
+// NB: the zero fill must be enqueued on the context's own (non-blocking) stream: a plain cudaMemset runs on the
+// legacy default stream, which does not order against non-blocking streams, and could land after later uploads.
 template <typename T>
-static cudaError_t ws_alloc(Workspace& w, T** p, size_t count, bool zero) {
+static cudaError_t ws_alloc(Workspace& w, cudaStream_t st, T** p, size_t count, bool zero) {
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     cudaError_t e = cudaMalloc((void**)p, bytes);
     if (e != cudaSuccess) return e;
     w.allocs.push_back(*p);
     w.bytes += bytes;
-    if (zero) e = cudaMemset(*p, 0, bytes);
+    if (zero) e = cudaMemsetAsync(*p, 0, bytes, st);
     return e;
 }
 
@@ -192,6 +193,16 @@ extern "C" int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx**
         set_thread_error("cudaMemcpyToSymbol: %s", cudaGetErrorString(e));
         delete ctx;
         return SOUP_ERR_CUDA;
+    }
+    {   // ln_binomial table for in-field counts (statrs FCACHE arithmetic, S:669-670); identical for every context
+        std::vector<float> tab(4096, 0.0f);
+        for (uint32_t a = 0; a < 64; ++a)
+            for (uint32_t r = 0; r < 64; ++r) tab[(a << 6) | r] = ln_binomial_f32(a + r, a);
+        if ((e = cudaMemcpyToSymbol(c_lbc, tab.data(), tab.size() * sizeof(float))) != cudaSuccess) {
+            set_thread_error("cudaMemcpyToSymbol: %s", cudaGetErrorString(e));
+            delete ctx;
+            return SOUP_ERR_CUDA;
+        }
     }
     *out = ctx;
     return SOUP_OK;
@@ -304,16 +315,6 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
         return pk;
     };
     const Packing pk_csr = make_packing(n_loci);
-    if (!same_shape || pk_csr.cbits != ctx->pk_csr.cbits || !ctx->lbc_table_set) {
-        // ln_binomial table for in-field counts (statrs FCACHE arithmetic, S:669-670)
-        std::vector<float> tab(4096, 0.0f);
-        const uint32_t cb = pk_csr.cbits;
-        for (uint32_t a = 0; a < (1u << cb); ++a)
-            for (uint32_t r = 0; r < (1u << cb); ++r) tab[(a << cb) | r] = ln_binomial_f32(a + r, a);
-        CKL(cudaMemcpyToSymbolAsync(c_lbc, tab.data(), tab.size() * sizeof(float), 0, cudaMemcpyHostToDevice, st));
-        CKL(cudaStreamSynchronize(st));
-        ctx->lbc_table_set = true;
-    }
     ctx->pk_csr = pk_csr;
     ctx->pk_csc = make_packing(n_cells);
     const size_t nz = std::max<uint64_t>(nnz, 1);
@@ -491,7 +492,7 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     w.Cpad = std::max(std::max(w.ep.padded, w.mp.padded), w.lp.padded);
     const size_t L = std::max<uint64_t>(ctx->L, 1), N = std::max<uint64_t>(ctx->N, 1);
     cudaError_t e = cudaSuccess;
-    auto A = [&](auto** p, size_t n, bool zero) { if (e == cudaSuccess) e = ws_alloc(w, p, n, zero); };
+    auto A = [&](auto** p, size_t n, bool zero) { if (e == cudaSuccess) e = ws_alloc(w, ctx->stream, p, n, zero); };
     A(&w.LA, L * w.Cpad, true); A(&w.LB, L * w.Cpad, true); A(&w.TH, L * w.Cpad, true);
     A(&w.ELL, N * w.Cpad, true); A(&w.W, N * w.Cpad, true); A(&w.LSE, N * slots, true);
     A(&w.st, (size_t)slots, true); A(&w.ctl, 1, true); A(&w.loss, (size_t)slots, true);

@@ -44,6 +44,30 @@ void log_solves(FILE* log, const soup_main_params* p, int spt, const std::vector
 
 }  // namespace
 
+// Cross-process winner selection of one run: all-gather (loss, solve, has_best), pick the reference's
+// winner (higher loss; ties -> lowest solve index, S:110/S:120), fetch its buffers from the owning rank.
+extern "C" int32_t soup_exchange_best(int32_t rank, int32_t world, soup_allgather_fn allgather, soup_bcast_fn bcast, void* user,
+                                      float* loss, int32_t* solve, int32_t* has_best, float* log_probs, uint64_t n_log_probs,
+                                      float* theta, uint64_t n_theta, int32_t* winner_rank) {
+    if (world <= 1) { if (winner_rank) *winner_rank = 0; return SOUP_OK; }
+    if (!allgather || !bcast || !loss || !solve || !has_best || rank < 0 || rank >= world) { set_thread_error("soup_exchange_best: bad argument"); return SOUP_ERR_INVALID; }
+    Candidate mine{*loss, *solve, *has_best, 0, 0};
+    std::vector<Candidate> all((size_t)world);
+    int32_t e = allgather(user, &mine, all.data(), sizeof(Candidate));
+    if (e != SOUP_OK) { set_thread_error("soup_exchange_best: allgather callback failed (%d)", e); return e; }
+    Candidate win{-INFINITY, -1, 0, 0, 0};
+    int wr = 0;
+    for (int q = 0; q < world; ++q)
+        if (better(all[q].loss, all[q].solve, all[q].has_best != 0, win.loss, win.solve, win.has_best != 0)) { win = all[q]; wr = q; }
+    if (winner_rank) *winner_rank = wr;
+    *loss = win.loss; *solve = win.solve; *has_best = win.has_best;
+    if (!win.has_best) return SOUP_OK;
+    if (log_probs && n_log_probs) e = bcast(user, log_probs, n_log_probs * sizeof(float), wr);
+    if (e == SOUP_OK && theta && n_theta) e = bcast(user, theta, n_theta * sizeof(float), wr);
+    if (e != SOUP_OK) { set_thread_error("soup_exchange_best: bcast callback failed (%d)", e); return e; }
+    return SOUP_OK;
+}
+
 extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_main_params* p, soup_main_result* r, void* log_file) {
     if (!ctxs || n_ctx <= 0 || !ctxs[0]) { set_thread_error("soup_main: need at least one context"); return SOUP_ERR_INVALID; }
     soup_ctx* ctx0 = ctxs[0];
@@ -162,30 +186,22 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
         }
 
         // ---- winner of this run: local first, then across processes
-        Candidate cand{win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY, win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, win_ctx >= 0 ? 1 : 0, 0, 0};
-        int win_rank = prank;
-        Candidate win = cand;
+        float w_loss = win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY;
+        int32_t w_solve = win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, w_has = win_ctx >= 0 ? 1 : 0;
+        std::vector<float> run_lp, run_th;
+        if (win_ctx >= 0) { run_lp.swap(pc[win_ctx].lp); run_th.swap(pc[win_ctx].th); }
+        else { run_lp.assign((size_t)n_cells * K, 0.0f); run_th.assign((size_t)K * n_loci, 0.0f); }
         if (pworld > 1) {
-            std::vector<Candidate> all(pworld);
-            int32_t e = p->allgather(p->comm_user, &cand, all.data(), sizeof(Candidate));
-            if (e != SOUP_OK) { set_thread_error("soup_main: allgather callback failed (%d)", e); return e; }
-            win = Candidate{-INFINITY, -1, 0, 0, 0};
-            win_rank = 0;
-            for (int q = 0; q < pworld; ++q)
-                if (better(all[q].loss, all[q].solve, all[q].has_best != 0, win.loss, win.solve, win.has_best != 0)) { win = all[q]; win_rank = q; }
+            int32_t e = soup_exchange_best(prank, pworld, p->allgather, p->bcast, p->comm_user, &w_loss, &w_solve, &w_has,
+                                           run_lp.data(), run_lp.size(), run_th.data(), run_th.size(), nullptr);
+            if (e != SOUP_OK) return e;
         }
+        struct { float loss; int32_t has_best; } win{w_loss, w_has};
         // adopt only if strictly better than the best carried over from earlier runs (S:120)
         const bool adopt = win.has_best && win.loss > best_loss;
         if (adopt) {
-            if (win_rank == prank) {
-                memcpy(r->best_log_probs, pc[win_ctx].lp.data(), pc[win_ctx].lp.size() * sizeof(float));
-                best_theta = pc[win_ctx].th;
-            }
-            if (pworld > 1) {
-                int32_t e = p->bcast(p->comm_user, r->best_log_probs, (uint64_t)n_cells * K * sizeof(float), win_rank);
-                if (e == SOUP_OK) e = p->bcast(p->comm_user, best_theta.data(), (uint64_t)K * n_loci * sizeof(float), win_rank);
-                if (e != SOUP_OK) { set_thread_error("soup_main: bcast callback failed (%d)", e); return e; }
-            }
+            memcpy(r->best_log_probs, run_lp.data(), run_lp.size() * sizeof(float));
+            best_theta.swap(run_th);
             best_loss = win.loss;
             have_best = true;
         }

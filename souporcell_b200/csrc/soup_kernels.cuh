@@ -150,7 +150,7 @@ struct Packing {
     uint32_t imask;        // row-index mask (locus in the CSR stream, cell in the CSC stream)
     uint32_t cbits;
 };
-__constant__ float c_lbc[4096];   // ln_binomial(alt + ref, alt) as f32 for in-field counts, index alt << cbits | ref
+__constant__ float c_lbc[4096];   // ln_binomial(alt + ref, alt) as f32 for in-field counts, index alt << 6 | ref (same for every context)
 
 template <int V>
 struct ETile { FVec<V> a, b; };
@@ -177,7 +177,7 @@ __device__ __forceinline__ void e_consume(FVec<V>& acc, const ETile<V>& t, uint3
             const float4 x = __ldg(aux);
             alt = x.x; ref = x.y; lbc = x.z;
         } else {
-            alt = (float)ai; ref = (float)ri; lbc = c_lbc[(ai << pk.cbits) | ri];
+            alt = (float)ai; ref = (float)ri; lbc = c_lbc[(ai << 6) | ri];
         }
         if (EXACT_SKIP && ri == 0) {
 #pragma unroll

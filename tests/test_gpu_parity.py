@@ -11,7 +11,11 @@ pytestmark = pytest.mark.gpu
 
 
 def bits(a):
-    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    """raw f32 bit patterns; NaNs are canonicalised (x86 yields 0xffc00000 for 0*inf, the GPU 0x7fffffff — both print "NaN")."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
 
 
 @pytest.fixture(scope="module", params=["default", "long_role"])
@@ -113,3 +117,194 @@ def test_solve_matches_oracle_per_iteration(small, method):
     assert res.has_best and res.best_solve == best[1]
     assert np.array_equal(bits(res.best_log_probs), bits(best[2]["log_probs"]))
     assert np.array_equal(bits(res.best_theta), bits(best[2]["theta"]))
+
+
+# ---------------------------------------------------------------------------------------------- drivers, edge cases
+def test_main_matches_oracle_with_chacha_seeds(small):
+    """souporcell_main S:60-131 with the reference's own seeding: master StdRng([seed;32]) -> per-thread seeds ->
+    theta0 drawn on the GPU from the ChaCha12 stream; restarts / threads combinations incl. ceil(restarts/threads)."""
+    _, csr, ctx, od = small
+    for method in (sp.METHOD_EM, sp.METHOD_KHM):
+        for restarts, threads, seed, slots in [(5, 2, 4, 0), (4, 4, 9, 3), (3, 1, 200, 2)]:
+            got = sp.main(ctx, 4, method=method, restarts=restarts, threads=threads, seed=seed, max_slots=slots)
+            want = od.main(4, method=method, restarts=restarts, threads=threads, seed=seed)
+            assert got.has_best and got.runs == want["runs"] == 1
+            assert bits([got.best_loss])[0] == bits([want["best_loss"]])[0]
+            assert np.array_equal(bits(got.best_log_probs), bits(want["best_log_probs"]))
+            assert np.array_equal(bits(got.best_theta), bits(want["best_theta"]))
+            assert got.nnz_updates == want["nnz_updates"]
+
+
+def test_theta0_drawn_on_device_equals_stdrng_stream(small):
+    _, csr, ctx, od = small
+    k, seeds = 3, sp.thread_seeds(4, 2, 0)
+    res = ctx.solve(k, n_streams=2, solves_per_stream=2, stream_seeds=seeds, iteration_cap=1, keep_trace=True)
+    for s in range(4):
+        stream, it = divmod(s, 2)
+        th0 = orc.init_uniform(bytes(seeds[stream]), it * k * ctx.n_loci, k, ctx.n_loci)   # word offset it*K*L (S:554-563)
+        want = od.solve(th0, iteration_cap=1)
+        assert bits(res.solve_loss[s:s + 1])[0] == bits([want["loss"]])[0]
+
+
+@pytest.mark.parametrize("method", [sp.METHOD_EM, sp.METHOD_KHM])
+def test_souporcell3_three_runs_match_oracle(method):
+    """-s true with k >= 16: bad-cluster detection, re-draw of the flagged clusters, locked rest (S:70-76, 92-97, 150-187)."""
+    v, csr = synth_csr(n_cells=700, n_loci=2500, k=16, mean_loci=90, seed=5)
+    od = orc.OracleData.from_csr(*csr)
+    with sp.Context(0) as ctx:
+        ctx.load_csr(*csr)
+        got = sp.main(ctx, 16, method=method, restarts=4, threads=2, seed=4, souporcell3=True)
+    want = od.main(16, method=method, restarts=4, threads=2, seed=4, souporcell3=True)
+    assert got.runs == want["runs"] and got.runs >= 2
+    assert bits([got.best_loss])[0] == bits([want["best_loss"]])[0]
+    assert np.array_equal(bits(got.best_log_probs), bits(want["best_log_probs"]))
+    assert np.array_equal(bits(got.best_theta), bits(want["best_theta"]))
+    assert np.array_equal(got.assignments, np.argmax(want["best_log_probs"], axis=1))
+
+
+def test_restart_shards_reproduce_the_single_shard_winner(small):
+    _, csr, ctx, od = small
+    seeds = sp.thread_seeds(4, 6, 0)
+    full = ctx.solve(3, n_streams=6, solves_per_stream=1, stream_seeds=seeds)
+    parts = [ctx.solve(3, n_streams=6, solves_per_stream=1, stream_seeds=seeds, shard_rank=r, shard_world=3) for r in range(3)]
+    for r, p in enumerate(parts):
+        mine = np.arange(r, 6, 3)
+        assert np.array_equal(bits(p.solve_loss[mine]), bits(full.solve_loss[mine]))
+        assert np.isnan(np.delete(p.solve_loss, mine)).all()
+    best = max(parts, key=lambda p: (p.best_loss, -p.best_solve))
+    assert best.best_solve == full.best_solve and np.array_equal(bits(best.best_log_probs), bits(full.best_log_probs))
+
+
+def test_solve_is_deterministic_run_to_run(small):
+    """Same inputs -> identical bits, every time (no atomics on floats, fixed accumulation order, ordered best-of)."""
+    _, csr, ctx, od = small
+    seeds = sp.thread_seeds(4, 5, 0)
+    ref = None
+    for rep in range(12):
+        r = ctx.solve(3, method=rep % 2, n_streams=5, solves_per_stream=2, stream_seeds=seeds, max_slots=[0, 3, 4][rep % 3])
+        key = (rep % 2,)
+        sig = (r.best_solve, bits(r.solve_loss).tobytes(), r.solve_iters.tobytes(), bits(r.best_log_probs).tobytes(), bits(r.best_theta).tobytes())
+        if ref is None:
+            ref = {}
+        if key in ref:
+            assert ref[key] == sig, f"run {rep} differs"
+        ref[key] = sig
+
+
+def test_golden_micro_fixture_on_gpu():
+    import json, os
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    lm = json.load(open(os.path.join(G, "loader_micro.json")))["expect"]
+    g = json.load(open(os.path.join(G, "em_micro.json")))
+    with sp.Context(0) as ctx:
+        ctx.load_csr(4, 3, np.array(lm["row_ptr"]), np.array(lm["locus"]), np.array(lm["alt"]), np.array(lm["ref"]))
+        assert ctx.get_cell_totals().tolist() == lm["total_alleles"]
+        for c in g["cases"]:
+            m = sp.METHOD_KHM if c["method"] == "khm" else sp.METHOD_EM
+            th0 = np.array(c["theta0"], dtype=np.float32)
+            st = ctx.estep(th0[None], [c["temp_step"]], method=m)
+            np.testing.assert_allclose(st["log_probs"][0], np.array(c["log_probs"]), rtol=g["tolerance"])
+            np.testing.assert_allclose(st["loss"][0], c["loss"], rtol=g["tolerance"])
+            res = ctx.solve(th0.shape[0], method=m, theta0=th0[None], keep_trace=True)
+            assert res.solve_iters[0] == c["solve"]["iterations"]
+            np.testing.assert_allclose(res.best_theta, np.array(c["solve"]["theta"]), rtol=400 * g["tolerance"])
+
+
+def test_edge_cases_empty_cells_big_counts_nonfinite_theta():
+    rng = np.random.default_rng(3)
+    n, L = 40, 30
+    rows = []
+    for c in range(n):
+        if c % 7 == 0:
+            rows.append(np.array([], dtype=np.int64))                       # cells with no used locus at all
+        else:
+            rows.append(np.sort(rng.choice(L, size=rng.integers(1, 12), replace=False)))
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.uint64)
+    locus = np.concatenate(rows).astype(np.uint32)
+    alt = rng.integers(0, 4, size=locus.shape[0]).astype(np.uint32)
+    ref = rng.integers(0, 4, size=locus.shape[0]).astype(np.uint32)
+    alt[::5] = rng.integers(60, 400, size=alt[::5].shape[0])               # beyond the packed count field and the ln-factorial table
+    ref[3::11] = 0
+    alt[(alt == 0) & (ref == 0)] = 1
+    zero_at = 4
+    alt[zero_at] = ref[zero_at] = 0                                         # an explicit all-zero entry is dropped (S:664)
+    od = orc.OracleData.from_csr(n, L, row_ptr, locus, alt, ref)
+    with sp.Context(0) as ctx:
+        ctx.load_csr(n, L, row_ptr, locus, alt, ref)
+        assert ctx.nnz == od.nnz == locus.shape[0] - 1
+        ex = od.export()
+        assert np.array_equal(bits(ctx.get_csr_lbc()), bits(ex["lbc"])) and np.array_equal(bits(ctx.get_cell_totals()), bits(ex["total_alleles"]))
+        k = 5
+        theta = random_theta(rng, (2, k, L))
+        theta[1, 0, :3] = [0.0, 1.0, 0.5]                                   # ln(0) = -inf: 0 * -inf = NaN in the reference's literal expression
+        for method in (sp.METHOD_EM, sp.METHOD_KHM):
+            got = ctx.estep(theta, [0, 8], method=method)
+            for s in range(2):
+                want = od.step(theta[s], method=method, temp_step=[0, 8][s])
+                assert np.array_equal(bits(got["log_probs"][s]), bits(want["log_probs"]))
+                assert np.array_equal(bits(got["weights"][s]), bits(want["weights"]))
+                th = ctx.mstep(got["weights"][s:s + 1], theta[s:s + 1])
+                assert np.array_equal(bits(th[0]), bits(want["theta_out"]))
+        res = ctx.solve(k, theta0=theta[:1], keep_trace=True)
+        want = od.solve(theta[0])
+        assert res.solve_iters[0] == want["iterations"] and np.array_equal(bits(res.best_log_probs), bits(want["log_probs"]))
+    # malformed CSR is rejected, not silently clustered
+    with sp.Context(0) as ctx:
+        bad = locus.copy()
+        bad[1], bad[2] = bad[2], bad[1]
+        with pytest.raises(sp.SoupError):
+            ctx.load_csr(n, L, row_ptr, bad, alt, ref)
+        with pytest.raises(sp.SoupError):
+            ctx.load_csr(n, 5, row_ptr, locus, alt, ref)
+    with sp.Context(0) as ctx:
+        with pytest.raises(sp.SoupError):
+            ctx.solve(3, stream_seeds=sp.thread_seeds(4, 1, 0))             # nothing loaded
+
+
+def test_cli_end_to_end_matches_oracle_cli(tmp_path):
+    """The drop-in executable vs the oracle's CLI on the same files and flags: clusters_tmp.tsv byte-identical,
+    per-iteration stderr trace identical as a multiset of lines."""
+    import subprocess
+    from souporcell_b200 import build, synth
+    v = synth.generate(n_cells=250, n_loci=1500, k=3, mean_loci=90, seed=8)
+    alt, ref, bc = synth.write_files(v, str(tmp_path))
+    for extra in (["-k", "3", "--restarts", "4", "-t", "2"], ["-k", "4", "--restarts", "3", "-m", "khm", "--seed", "11", "--min_alt", "6", "--min_ref=6"]):
+        args = ["-a", alt, "-r", ref, "-b", bc] + extra
+        ours = subprocess.run([build.CLI] + args, capture_output=True, text=True)
+        theirs = subprocess.run([orc.CLI_PATH] + args, capture_output=True, text=True)
+        assert ours.returncode == 0 and theirs.returncode == 0, ours.stderr[-500:]
+        assert ours.stdout == theirs.stdout and ours.stdout.count("\n") == v.n_cells
+        pick = lambda s: sorted(l for l in s.splitlines() if l.startswith(("binomial", "total loci", "best total", "thread ")))
+        assert pick(ours.stderr) == pick(theirs.stderr)
+
+
+def test_full_size_properties_config2():
+    """BASELINE configs[1] at full size (10k cells x 50k loci, k=8): too big for the oracle to cluster, so parity is
+    checked on one capped solve (3 iterations, ~10 s of oracle time) bit for bit, plus size-independent properties."""
+    import bench
+    cfg, csr = bench.workload(2)
+    n, L = csr[0], csr[1]
+    rng = np.random.default_rng(0)
+    th0 = random_theta(rng, (1, cfg["k"], L))
+    with sp.Context(0) as ctx:
+        ctx.load_csr(*csr)
+        col_ptr, cell, calt, cref = ctx.get_csc()
+        assert int(col_ptr[-1]) == csr[3].shape[0] and np.all(np.diff(col_ptr.astype(np.int64)) >= 0)
+        seg = np.repeat(np.arange(L), np.diff(col_ptr.astype(np.int64)))
+        same = seg[1:] == seg[:-1]
+        assert np.all(cell[1:][same] > cell[:-1][same])                     # cells strictly ascending inside every locus
+        assert int(calt.sum()) == int(csr[4].sum()) and int(cref.sum()) == int(csr[5].sum())
+        e = ctx.estep(th0, [4])
+        w = e["weights"][0]
+        np.testing.assert_allclose(w.sum(axis=1), 1.0, rtol=1e-4)     # f32 softmax over k = 8, same arithmetic as the reference
+        th1 = ctx.mstep(e["weights"], th0)
+        assert th1.min() >= np.float32(0.01) and th1.max() <= np.float32(0.99)
+        res = ctx.solve(cfg["k"], theta0=th0, iteration_cap=3, keep_trace=True)
+        od = orc.OracleData.from_csr(*csr)
+        want = od.solve(th0[0], iteration_cap=3)
+        assert [bits([t[1]])[0] for t in ctx.get_trace(0)] == [bits([t[1]])[0] for t in want["trace"]]
+        assert np.array_equal(bits(res.best_log_probs), bits(want["log_probs"])) and np.array_equal(bits(res.best_theta), bits(want["theta"]))
+        # all 50 restarts: every solve runs its 9 temperature steps, finishes within the cap, and the winner is the max
+        full = sp.main(ctx, cfg["k"], restarts=50, threads=50)
+        assert full.has_best and full.nnz_updates % ctx.nnz == 0 and 9 * 50 <= full.nnz_updates // ctx.nnz <= 1000 * 50
+        assert np.isfinite(full.best_log_probs).all() and (np.bincount(full.assignments, minlength=cfg["k"]) > 0).sum() >= 4

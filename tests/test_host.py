@@ -1,0 +1,176 @@
+"""CPU: the host side of libsoupgpu (no GPU needed) against the oracle and the golden fixtures; library surface."""
+import ctypes
+import gzip
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import souporcell_b200 as sp
+from souporcell_b200 import api, build, synth
+from oracle import oracle_py as orc
+from test_oracle_golden import load, write_mtx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "soupgpu.h")).read()
+    declared = set(re.findall(r"\b(soup_[a-z0-9_]+)\s*\(", hdr)) - {"soup_allgather_fn", "soup_bcast_fn"}
+    assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
+    L = sp.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.soup_version() == 3000
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sp.SoupError) as e:
+        sp.Context(0)
+    assert e.value.code == api.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_chacha_and_seeds_match_public_vectors_and_oracle():
+    kat = load("chacha_kat.json")
+    key = bytes.fromhex(kat["key"])
+    for rounds, hexs in kat["rounds"].items():
+        assert sp.chacha_words(key, 16, 0, int(rounds)).astype("<u4").tobytes().hex() == hexs
+    seed = bytes((7 * i + 3) % 256 for i in range(32))
+    assert np.array_equal(sp.chacha_words(seed, 1000, 12345, 12), orc.chacha_words(seed, 1000, 12345, 12))
+    for run in range(3):
+        assert np.array_equal(sp.thread_seeds(4, 5, run), orc.thread_seeds(4, 5, run))
+    assert np.array_equal(sp.thread_seeds(200, 1, 0), orc.thread_seeds(200, 1, 0))
+
+
+def test_format_and_ln_binomial():
+    for v, plain, w8 in load("format_f32.json"):
+        assert sp.format_f32(v) == plain and sp.format_f32(v, True) == w8
+    rng = np.random.default_rng(2)
+    for v in np.concatenate([rng.standard_normal(300) * 1e3, rng.random(300), -rng.random(100) * 1e-5]).astype(np.float32):
+        assert sp.format_f32(float(v)) == orc.format_f32(float(v))
+        assert np.float32(float(sp.format_f32(float(v)))) == v            # round-trips
+    for n, k in [(0, 0), (1, 0), (1, 1), (2, 1), (3, 2), (10, 3), (170, 85), (171, 3), (400, 200), (5, 6)]:
+        assert np.float32(sp.ln_binomial_f32(n, k)) == np.float32(orc.ln_binomial(n, k)) or (k > n)
+
+
+def test_loader_golden_and_vs_oracle(tmp_path):
+    g = load("loader_micro.json")
+    alt, ref = write_mtx(tmp_path, g["n_loci"], g["n_cells"], g["entries"])
+    m = sp.load_mtx(alt, ref, g["min_alt"], g["min_ref"])
+    w = g["expect"]
+    assert (m.n_cells, m.n_loci_total, m.n_loci) == (4, 5, 3)
+    for k in ("row_ptr", "locus", "alt", "ref", "index_to_locus"):
+        assert getattr(m, k).tolist() == w[k], k
+    (tmp_path / "d").mkdir()
+    alt, ref = write_mtx(tmp_path / "d", 1, 4, g["dup_entries"])
+    w = g["dup_expect"]
+    m = sp.load_mtx(alt, ref, w["min_alt"], w["min_ref"])
+    for k in ("row_ptr", "locus", "alt", "ref", "index_to_locus"):
+        assert getattr(m, k).tolist() == w[k], k
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+@pytest.mark.parametrize("mins", [(4, 4, 0, 0), (1, 1, 0, 0), (2, 3, 5, 4), (10, 10, 0, 0)])
+def test_loader_matches_oracle_on_synthetic_vartrix(tmp_path, shuffle, mins):
+    v = synth.generate(n_cells=150, n_loci=900, k=3, mean_loci=70, seed=21)
+    if shuffle:                                       # entry order must not matter (hash maps in the reference)
+        p = np.random.default_rng(1).permutation(v.nnz)
+        v.locus, v.cell, v.alt, v.ref = v.locus[p], v.cell[p], v.alt[p], v.ref[p]
+    alt, ref, _ = synth.write_files(v, str(tmp_path))
+    m = sp.load_mtx(alt, ref, *mins)
+    ex = orc.OracleData.from_mtx(alt, ref, *mins).export()
+    assert m.n_loci == ex["index_to_locus"].shape[0]
+    for k in ("row_ptr", "locus", "alt", "ref", "index_to_locus"):
+        assert np.array_equal(getattr(m, k), ex[k]), k
+
+
+def test_loader_edge_cases(tmp_path):
+    # empty body, header only
+    alt, ref = write_mtx(tmp_path, 3, 2, [])
+    m = sp.load_mtx(alt, ref)
+    assert (m.n_cells, m.n_loci, m.nnz) == (2, 0, 0) and m.row_ptr.tolist() == [0, 0, 0]
+    # out-of-range indices abort like the reference's assert!(locus < total_loci) (S:627-628)
+    (tmp_path / "b").mkdir()
+    alt, ref = write_mtx(tmp_path / "b", 3, 2, [[4, 1, 1, 1]])
+    with pytest.raises(sp.SoupError):
+        sp.load_mtx(alt, ref)
+    with pytest.raises(sp.SoupError) as e:
+        sp.load_mtx(str(tmp_path / "missing.mtx"), ref)
+    assert e.value.code == api.ERR_IO
+    # ragged: ref file shorter than alt -> the zip stops at the shorter one (S:616)
+    (tmp_path / "r").mkdir()
+    alt, ref = write_mtx(tmp_path / "r", 2, 2, [[1, 1, 1, 1], [1, 2, 1, 1], [2, 1, 1, 1]])
+    lines = open(ref).read().splitlines()
+    open(ref, "w").write("\n".join(lines[:-1]) + "\n")
+    m = sp.load_mtx(alt, ref, 1, 1)
+    ex = orc.OracleData.from_mtx(alt, ref, 1, 1).export()
+    assert np.array_equal(m.locus, ex["locus"]) and np.array_equal(m.row_ptr, ex["row_ptr"])
+
+
+def test_barcodes_plain_gz_crlf(tmp_path):
+    names = ["AAAC-1", "CCGT-1", "", "TTTT-1"]
+    p = tmp_path / "barcodes.tsv"
+    p.write_text("\r\n".join(names) + "\r\n")
+    assert sp.load_barcodes(str(p)) == names
+    pz = tmp_path / "barcodes.tsv.gz"
+    with gzip.open(pz, "wt") as fh:
+        fh.write("\n".join(names))
+    assert sp.load_barcodes(str(pz)) == names
+    with pytest.raises(sp.SoupError):
+        sp.load_barcodes(str(tmp_path / "nope.tsv"))
+
+
+def test_bad_cluster_detection_matches_golden_and_oracle():
+    for case in load("bad_clusters.json"):
+        k = case["k"]
+        rows = []
+        for c, n in enumerate(case["sizes"]):
+            r = np.full(k, -10.0, dtype=np.float32)
+            r[c] = -1.0
+            rows += [r] * n
+        assert sp.bad_cluster_detection(case["run"], k, np.stack(rows)) == case["expect"]
+    rng = np.random.default_rng(9)
+    lp = -rng.random((4000, 32)).astype(np.float32) * 50
+    lp[:500] = lp[0]                                   # ties and NaN handled by total_cmp like the oracle
+    lp[7, 3] = np.nan
+    for run in (1, 2):
+        assert sp.bad_cluster_detection(run, 32, lp) == orc.bad_cluster_detection(run, 32, lp)
+
+
+def test_write_clusters_tsv_format(tmp_path):
+    lp = np.array([[-1.5, -0.25, -0.25], [np.float32(-1e-7), -3.0, -2.0], [-5.0, -5.0, -5.0]], dtype=np.float32)
+    out = tmp_path / "clusters_tmp.tsv"
+    sp.write_clusters(str(out), ["bc0", "bc1", "bc2", "extra-barcode"], lp)   # zip() truncates to the shorter (S:133)
+    assert out.read_text() == "bc0\t1\t-1.5\t-0.25\t-0.25\nbc1\t0\t-0.0000001\t-3\t-2\nbc2\t0\t-5\t-5\t-5\n"
+
+
+def test_cli_contract_without_gpu(tmp_path):
+    """argv errors / -V / -h never need the GPU; a real run without one must fail loudly with nothing on stdout."""
+    exe = build.CLI
+    assert subprocess.run([exe, "-V"], capture_output=True, text=True).stdout == "souporcell 3.0\n"
+    assert "--clustering_method" in subprocess.run([exe, "-h"], capture_output=True, text=True).stdout
+    r = subprocess.run([exe, "-k", "3"], capture_output=True, text=True)
+    assert r.returncode != 0 and r.stdout == "" and "required arguments" in r.stderr
+    r = subprocess.run([exe, "--bogus", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "wasn't expected" in r.stderr
+    g = load("loader_micro.json")
+    alt, ref = write_mtx(tmp_path, g["n_loci"], g["n_cells"], g["entries"])
+    bc = tmp_path / "bc.tsv"
+    bc.write_text("a\nb\nc\nd\n")
+    base = [exe, "-a", alt, "-r", ref, "-b", str(bc), "-k", "2", "--min_alt", "2", "--min_ref=2"]
+    r = subprocess.run(base + ["-m", "kmeans"], capture_output=True, text=True)
+    assert r.returncode == 101 and "Clustering method must be one of em, khm" in r.stderr and r.stdout == ""
+    r = subprocess.run(base + ["--seed", "256"], capture_output=True, text=True)
+    assert r.returncode == 101 and r.stdout == ""
+    r = subprocess.run(base + ["--initialization_strategy", "kmeans++"], capture_output=True, text=True)
+    assert r.returncode == 101 and "kmeans++ not yet implemented" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run(base, capture_output=True, text=True)
+        assert r.returncode != 0 and r.stdout == "" and "total loci used 3" in r.stderr and "no CPU fallback" in r.stderr
