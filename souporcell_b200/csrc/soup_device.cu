@@ -559,7 +559,7 @@ static void launch_m(soup_ctx* ctx) {
     const uint32_t long_blocks = (long_items + EM_WARPS - 1) / EM_WARPS;
     const uint32_t wide_chunks = (uint32_t)((ctx->L - n_long + EM_WARPS - 1) / EM_WARPS);
     const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
-                  w.m_group_active, w.l_group_active, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main,
+                  w.m_group_active, w.l_group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main,
                   n_long, (uint32_t)w.lp.n_groups, long_blocks};
     const dim3 grid(long_blocks + wide_chunks * w.mp.n_groups);
     if (grid.x == 0) return;
@@ -573,7 +573,8 @@ static void launch_post(soup_ctx* ctx, int method, bool counts) {
 static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
     Workspace& w = ctx->ws;
     const size_t n = (size_t)ctx->L * w.K;
-    if (n) refill_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)w.slots), 256, 0, ctx->stream>>>(a);
+    // a fixed, small number of CTAs per slot (they loop): the launch is a no-op on most iterations
+    if (n) refill_kernel<<<dim3((unsigned)std::min<size_t>((n + 255) / 256, 48), (unsigned)w.slots), 256, 0, ctx->stream>>>(a);
 }
 
 static uint64_t launches_per_iteration(const soup_ctx* ctx) { (void)ctx; return 8; }

@@ -465,19 +465,34 @@ __global__ void __launch_bounds__(1024) control_kernel(ControlArgs a) {
 __device__ __forceinline__ float small_u2f(uint32_t i) {   // exact (float)i for i < 2^23 without the conversion pipe
     return __fadd_rn(__uint_as_float(0x4B000000u | i), -8388608.0f);
 }
-template <int V, bool EXACT_SKIP>
+// SHORTCUT = false: the literal expression, no data-dependent branch (long-locus role: a branch per entry on the
+// critical chain of a lone warp costs more than the multiplies it saves).
+// SHORTCUT = true : single-UMI entries skip the multiplies (p*1 == p) and, for alt == 0, the s update (s + p*0 == s
+// while the weights are finite — Ctl::nonfinite == 0); used by the wide role, which is instruction-issue bound.
+template <int V, bool SHORTCUT>
 __device__ __forceinline__ void m_consume(FVec<V>& s, FVec<V>& d, const FVec<V>& p, uint32_t w, const Packing& pk, const float2* __restrict__ aux) {
     const uint32_t ai = w >> pk.sh_a, ti = (w >> pk.sh_r) & pk.cmask;
+    if (SHORTCUT && ti == 1) {
+        if (ai == 1) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) { s.v[v] = __fadd_rn(s.v[v], p.v[v]); d.v[v] = __fadd_rn(d.v[v], p.v[v]); }
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], p.v[v]);
+        }
+        return;
+    }
     float alt = small_u2f(ai), tot = small_u2f(ti);
     if (ai == pk.cmask && ti == pk.cmask) {          // counts outside the packed fields (rare)
         const float2 x = __ldg(aux);
         alt = x.x; tot = x.y;
     }
+    if (!SHORTCUT || ai != 0) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        s.v[v] = __fadd_rn(s.v[v], __fmul_rn(p.v[v], alt));
-        d.v[v] = __fadd_rn(d.v[v], __fmul_rn(p.v[v], tot));
+        for (int v = 0; v < V; ++v) s.v[v] = __fadd_rn(s.v[v], __fmul_rn(p.v[v], alt));
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], __fmul_rn(p.v[v], tot));
 }
 
 template <int V, int U, bool EXACT_SKIP>
@@ -529,7 +544,7 @@ __device__ __forceinline__ void m_issue(FVec<V> (&p)[U], const uint32_t (&x)[U],
 template <int V, int U>
 __device__ __forceinline__ void m_eat(FVec<V>& s, FVec<V>& d, const FVec<V> (&p)[U], const uint32_t (&x)[U], const Packing& pk, const float2* __restrict__ aux) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) m_consume<V, true>(s, d, p[u], x[u], pk, aux + u);
+    for (int u = 0; u < U; ++u) m_consume<V, false>(s, d, p[u], x[u], pk, aux + u);
 }
 template <int V, int U>
 __device__ __forceinline__ void m_walk_deep(FVec<V>& s, FVec<V>& d, const uint32_t* __restrict__ q, const float2* __restrict__ aux, uint32_t n,
@@ -586,6 +601,7 @@ struct MArgs {
     const float* W; float* TH; float* LA; float* LB; const uint8_t* col_write;
     const int* group_active;        // wide role: column groups of 32*VM (+ one narrower last group)
     const int* long_group_active;   // long role: column groups of 32*SOUP_M_VLONG
+    const Ctl* ctl;
     Packing pk;
     uint32_t L, Cpad, n_groups, n_main;
     uint32_t n_long, long_groups, long_blocks;   // loci [0, n_long) of the LPT order take the long role
@@ -604,11 +620,12 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
 #if SOUP_M_DEEP
         m_walk_deep<V, SOUP_M_ULONG>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
 #else
-        m_walk<V, SOUP_M_ULONG, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+        m_walk<V, SOUP_M_ULONG, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
 #endif
     } else {
         constexpr int U = V <= 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16);
-        m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+        if (!a.ctl->nonfinite) m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+        else m_walk<V, 2, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -684,8 +701,8 @@ __global__ void __launch_bounds__(256) refill_kernel(RefillArgs a) {
     const int slot = blockIdx.y;
     const SlotState s = a.st[slot];
     if (!s.fin || s.pending < 0) return;
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // e = l*K + k (k fastest: coalesced table writes)
-    if (e >= (size_t)a.L * a.K) return;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)a.L * a.K; e += (size_t)gridDim.x * blockDim.x) {
+    // e = l*K + k (k fastest: coalesced table writes)
     const uint32_t l = (uint32_t)(e / a.K);
     const int k = (int)(e - (size_t)l * a.K);
     const int solve = a.queue[s.pending];
@@ -712,6 +729,7 @@ __global__ void __launch_bounds__(256) refill_kernel(RefillArgs a) {
     a.LA[o] = la;
     a.LB[o] = lb;
     if (!isfinite(la) || !isfinite(lb)) a.ctl->nonfinite = 1;
+    }
 }
 
 // after refill: install pending solves, retire finished slots, rebuild the column / group masks
