@@ -40,6 +40,7 @@ struct Workspace {
     int *e_group_active = nullptr, *m_group_active = nullptr, *l_group_active = nullptr, *counts = nullptr, *queue = nullptr, *draw_of_k = nullptr, *solve_iters = nullptr;
     float *solve_loss = nullptr, *best_lp = nullptr, *best_theta = nullptr;
     IterRec* trace = nullptr;
+    int2* moves = nullptr;
     uint32_t* stream_keys = nullptr;
     int n_streams_cap = 0;
     std::vector<void*> allocs;
@@ -504,6 +505,7 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     A(&w.best_lp, N * K, true); A(&w.best_theta, L * K, true);
     A(&w.trace, (size_t)queue_cap * iter_cap, true);
     A(&w.stream_keys, (size_t)std::max(n_streams, 1) * 8, true);
+    A(&w.moves, (size_t)slots, true);
     if (e != cudaSuccess) {
         ws_free(w);
         cudaGetLastError();
@@ -577,7 +579,7 @@ static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
     if (n) refill_kernel<<<dim3((unsigned)std::min<size_t>((n + 255) / 256, 48), (unsigned)w.slots), 256, 0, ctx->stream>>>(a);
 }
 
-static uint64_t launches_per_iteration(const soup_ctx* ctx) { (void)ctx; return 8; }
+static uint64_t launches_per_iteration(const soup_ctx* ctx) { (void)ctx; return 10; }
 
 static void launch_loss_control(soup_ctx* ctx, cudaStream_t st, bool counts, float limit) {
     Workspace& w = ctx->ws;
@@ -608,6 +610,7 @@ static void enqueue_iteration(const IterLaunch& it) {
     harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K);
     launch_refill(ctx, it.refill);
     finalize_kernel<<<1, 1024, 0, ctx->stream>>>(it.fin);
+    migrate_kernel<<<dim3(32, (unsigned)w.slots), 256, 0, ctx->stream>>>(w.ctl, w.moves, w.TH, w.LA, w.LB, (uint32_t)ctx->L, w.Cpad, w.K);
 }
 
 // ------------------------------------------------------------------ soup_solve
@@ -740,7 +743,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
                           {{w.e_group_active, 32 * w.ep.VM, 32 * w.ep.VT, w.ep.n_main, w.ep.n_groups},
                            {w.m_group_active, 32 * w.mp.VM, 32 * w.mp.VT, w.mp.n_main, w.mp.n_groups},
                            {w.l_group_active, 32 * w.lp.VM, 32 * w.lp.VT, w.lp.n_main, w.lp.n_groups}},
-                          K, slots, iter_cap, w.Cpad, limit};
+                          K, slots, iter_cap, w.Cpad, limit, w.moves, getenv("SOUP_NO_COMPACT") ? 0 : 1};
 
     CKS(cudaEventRecord(ctx->ev0, st));
     launch_refill(ctx, it.refill);

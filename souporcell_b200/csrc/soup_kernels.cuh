@@ -83,7 +83,7 @@ struct Ctl {
     float best_loss;
     int nonfinite;      // a ln-table holds a non-finite value: exact zero-count shortcuts are off
     int n_active;
-    int pad0;
+    int n_moves;        // slot migrations decided by finalize_kernel for migrate_kernel (tail compaction)
     unsigned long long slot_iterations;
 };
 
@@ -745,6 +745,8 @@ struct FinalizeArgs {
     int K, slots, iter_cap;
     uint32_t Cpad;
     float limit;
+    int2* moves;               // [slots] (from, to) pairs for migrate_kernel
+    int compact;               // 1: pack the surviving slots into the fewest column groups once the queue is empty
 };
 
 __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
@@ -773,6 +775,47 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
         if (s.active) atomicAdd(&n_active, 1);
     }
     __syncthreads();
+    // Tail compaction.  Solves converge at different iterations; once the queue is empty the survivors are
+    // scattered over all column groups and every group with one live slot still costs a full pass.  When packing
+    // them to the front frees at least one group of the E pass or of the M pass's wide role, the highest live
+    // slots move into the lowest holes (disjoint source / destination sets, so migrate_kernel can copy all
+    // columns in parallel).  Only theta / ln-table columns and the slot state move; everything else is
+    // recomputed every iteration.  Per-solve results do not depend on the slot a solve sits in.
+    if (threadIdx.x == 0) {
+        int moves = 0;
+        if (a.compact && a.ctl->queue_head >= a.ctl->queue_len && n_active > 0) {
+            bool worth = false;
+            for (int t = 0; t < 2 && !worth; ++t) {
+                const FinalizeArgs::Plan pl = a.plan[t];
+                int live = 0;
+                for (int g = 0; g < pl.n_groups; ++g) {
+                    const int c0 = g * pl.WM, c1 = g < pl.n_main ? c0 + pl.WM : c0 + pl.WT;
+                    int last = (c1 - 1) / a.K;
+                    if (last >= a.slots) last = a.slots - 1;
+                    int any = 0;
+                    for (int s = c0 / a.K; s <= last; ++s) any |= a.st[s].active;
+                    live += any;
+                }
+                const int need = (n_active * a.K + pl.WM - 1) / pl.WM;
+                worth = need < live;
+            }
+            if (worth) {
+                int hole = 0, top = a.slots - 1;
+                for (;;) {
+                    while (hole < a.slots && a.st[hole].active) ++hole;
+                    while (top >= 0 && !a.st[top].active) --top;
+                    if (hole >= top) break;
+                    a.moves[moves++] = make_int2(top, hole);
+                    SlotState s = a.st[top];
+                    a.st[hole] = s;
+                    s.active = 0; s.solve = -1;
+                    a.st[top] = s;
+                }
+            }
+        }
+        a.ctl->n_moves = moves;
+    }
+    __syncthreads();
     for (uint32_t c = threadIdx.x; c < a.Cpad; c += blockDim.x) {
         const int slot = (int)(c / a.K), k = (int)(c - (uint32_t)slot * a.K);
         a.col_write[c] = (slot < a.slots && a.st[slot].active && !a.k_locked[k]) ? 1 : 0;
@@ -790,6 +833,19 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
         }
     }
     if (threadIdx.x == 0) a.ctl->n_active = n_active;
+}
+
+// copies the theta / ln-table columns of the migrated slots (blockIdx.y = move index)
+__global__ void __launch_bounds__(256) migrate_kernel(const Ctl* __restrict__ ctl, const int2* __restrict__ moves, float* TH, float* LA, float* LB,
+                                                      uint32_t L, uint32_t Cpad, int K) {
+    if ((int)blockIdx.y >= ctl->n_moves) return;
+    const int2 mv = moves[blockIdx.y];
+    const size_t n = (size_t)L * K;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t l = e / K, k = e - l * K;
+        const size_t src = l * Cpad + (size_t)mv.x * K + k, dst = l * Cpad + (size_t)mv.y * K + k;
+        TH[dst] = TH[src]; LA[dst] = LA[src]; LB[dst] = LB[src];
+    }
 }
 
 // ------------------------------------------------------------------ load-time kernels
