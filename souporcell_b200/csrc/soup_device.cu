@@ -562,7 +562,8 @@ static void launch_m(soup_ctx* ctx) {
     const uint32_t wide_chunks = (uint32_t)((ctx->L - n_long + EM_WARPS - 1) / EM_WARPS);
     const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
                   w.m_group_active, w.l_group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main,
-                  n_long, (uint32_t)w.lp.n_groups, long_blocks};
+                  n_long, (uint32_t)w.lp.n_groups, long_blocks, wide_chunks,
+                  (uint32_t)((uint64_t)ctx->N * w.Cpad * 4 > (48ull << 20))};
     const dim3 grid(long_blocks + wide_chunks * w.mp.n_groups);
     if (grid.x == 0) return;
     SOUP_DISPATCH(mstep_kernel, w.mp, a);

@@ -604,7 +604,7 @@ struct MArgs {
     const Ctl* ctl;
     Packing pk;
     uint32_t L, Cpad, n_groups, n_main;
-    uint32_t n_long, long_groups, long_blocks;   // loci [0, n_long) of the LPT order take the long role
+    uint32_t n_long, long_groups, long_blocks, wide_chunks, group_major;   // loci [0, n_long) of the LPT order take the long role
 };
 
 template <int V, bool DEEP>
@@ -642,7 +642,7 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
 // Two roles in one grid.  Blocks [0, long_blocks): the n_long longest loci (LPT order), each split into
 // narrow column groups so that many warps share a long locus and each warp's sequential chain is
 // short per entry; they launch first.  Remaining blocks: all other loci with wide column groups
-// (locus-major, group fastest) where the per-entry cost is amortised over more columns.
+// where the per-entry cost is amortised over more columns.
 template <int VM, int VT>
 __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2)) mstep_kernel(const MArgs a) {
     const uint32_t warp = threadIdx.x >> 5;
@@ -654,9 +654,12 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2)) mstep
         mstep_body<SOUP_M_VLONG, true>(a, a.locus_order[li], group * (32 * SOUP_M_VLONG));
         return;
     }
+    // wide role: locus-major (group fastest) while the whole weight plane fits L2 — every group's longer loci then start
+    // early; group-major (all loci of group 0, then group 1, ...) once it does not, so one group's slice stays in L2
     const uint32_t bi = blockIdx.x - a.long_blocks;
-    const uint32_t chunk = bi / a.n_groups;
-    const uint32_t group = bi - chunk * a.n_groups;
+    uint32_t group, chunk;
+    if (a.group_major) { group = bi / a.wide_chunks; chunk = bi - group * a.wide_chunks; }
+    else { chunk = bi / a.n_groups; group = bi - chunk * a.n_groups; }
     if (!a.group_active[group]) return;
     const uint32_t li = a.n_long + chunk * EM_WARPS + warp;
     if (li >= a.L) return;
