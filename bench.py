@@ -280,6 +280,66 @@ def ours(args):
         dist.destroy_process_group()
 
 
+def ours_cells(args):
+    """Cell-sharded leg (optional: `--shard cells`, N > 1): every rank holds a contiguous range of the cells,
+    runs all restarts, and all-reduces the M-pass statistics [2][L][columns] + losses over NCCL every iteration.
+    Strong scaling: the job (config restarts on the whole matrix) is fixed, `value` = nnz-updates of the whole job / time."""
+    import torch
+    import torch.distributed as dist
+    import souporcell_b200 as sp
+    from souporcell_b200 import api
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg, csr = workload(args.config)
+    n, L, row_ptr, locus, alt, ref = csr
+    rp = row_ptr.astype(np.int64)
+    cuts = [0] + [int(np.searchsorted(rp, rp[-1] * i // world)) for i in range(1, world)] + [n]
+    a, b = cuts[rank], cuts[rank + 1]
+    shard = (b - a, L, (rp[a:b + 1] - rp[a]).astype(np.uint64), locus[rp[a]:rp[b]], alt[rp[a]:rp[b]], ref[rp[a]:rp[b]])
+    K, restarts = cfg["k"], cfg["restarts"]
+    method = sp.METHOD_KHM if cfg["method"] == "khm" else sp.METHOD_EM
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = sp.Context(local, stream=stream.cuda_stream)
+    ctx.load_csr(*shard)
+    cb = api.torch_allreduce_callback(dist)
+    seeds = sp.thread_seeds(4, restarts, 0)
+
+    def job():
+        return ctx.solve(K, method=method, n_streams=restarts, solves_per_stream=1, stream_seeds=seeds, cell_allreduce=cb, n_cells_global=n)
+
+    ms = upd = launches = 0.0
+    for i in range(args.warmup + args.steps):
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r = job()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if i >= args.warmup:
+            ms += float(t[0]); upd += float(int(locus.shape[0]) * int(r.solve_iters.sum())); launches += r.stats["kernel_launches"]
+    if rank == 0:
+        be, bm = algorithmic_bytes(int(locus.shape[0]), K, L, n)
+        peak, src = measured_peak()
+        value = upd / (ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(config_dict(args, cfg, csr, restarts), sharding="cells (contiguous ranges balanced by nnz) + NCCL all-reduce of the M statistics per iteration"),
+                "gpu_launches": int(launches * world),
+                "roofline": {"bound": "hbm", "achieved": value / world * (be + bm) / int(locus.shape[0]) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": value / world * (be + bm) / int(locus.shape[0]) / 1e9 / peak, "traffic": None, "peak_source": src,
+                             "note": "whole job per GPU"},
+                "allreduce_floats_per_iteration": int(r.stats["padded_cols"]) * L * 2 + int(r.stats["slots"])}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -288,12 +348,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config number (1-based)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="restarts", choices=["restarts", "cells"], help="multi-GPU partition (default: restarts, weak scaling)")
     args = ap.parse_args()
     from souporcell_b200 import build
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         build.build_all()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.shard == "cells" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        ours_cells(args)
     else:
         ours(args)
 

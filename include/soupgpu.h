@@ -102,6 +102,12 @@ int32_t soup_get_csc(soup_ctx* ctx, uint64_t* col_ptr /*[L+1]*/, uint32_t* cell 
 int32_t soup_get_cell_totals(soup_ctx* ctx, float* total_alleles /*[N]*/);
 int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc /*[nnz]: log_binomial_coefficient per stored entry, S:669*/);
 
+/* Cell-sharded mode: sum `n_floats` f32 at device pointer `device_buf` in place over all ranks, enqueued on
+ * `cuda_stream` (e.g. ncclAllReduce, or torch.distributed.all_reduce on a tensor aliasing the buffer).  Called once
+ * per EM iteration with the M pass's sufficient statistics [sum p*alt | sum p*(alt+ref)] of all resident restarts and
+ * their partial losses. */
+typedef int32_t (*soup_allreduce_fn)(void* user, void* device_buf, uint64_t n_floats, void* cuda_stream);
+
 typedef struct soup_solve_params {
     int32_t k;                 /* num_clusters (S:726) */
     int32_t method;            /* SOUP_METHOD_EM | SOUP_METHOD_KHM (S:101-108) */
@@ -121,6 +127,12 @@ typedef struct soup_solve_params {
     int32_t time_kernels;      /* bracket each iteration's E and M launches with CUDA events (soup_get_stats) */
     /* multi-GPU restart sharding: this process runs solves with (solve % world) == rank */
     int32_t shard_rank, shard_world; /* world 0 or 1 = no sharding */
+    /* multi-GPU cell sharding: the loaded matrix holds a contiguous range of the cells (all loci); every rank runs
+     * every restart and the ranks all-reduce the M-pass statistics each iteration.  best_log_probs then covers the
+     * local cells only; results agree with the single-GPU path to tolerance (different summation order), not bitwise. */
+    soup_allreduce_fn cell_allreduce; /* NULL = off */
+    void* comm_user;
+    uint64_t n_cells_global;          /* total cells over all ranks (the convergence limit S:214 uses it) */
 } soup_solve_params;
 
 typedef struct soup_solve_result {

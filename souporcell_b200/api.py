@@ -52,7 +52,8 @@ class _SolveParams(C.Structure):
                 ("stream_seeds", C.c_void_p), ("theta0", C.c_void_p), ("base_theta", C.c_void_p),
                 ("reinit_clusters", C.c_void_p), ("n_reinit", C.c_int32), ("iteration_cap", C.c_int32),
                 ("max_slots", C.c_int32), ("lanes", C.c_int32), ("record_counts", C.c_int32), ("keep_trace", C.c_int32),
-                ("poll_chunk", C.c_int32), ("time_kernels", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
+                ("poll_chunk", C.c_int32), ("time_kernels", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
+                ("cell_allreduce", C.c_void_p), ("comm_user", C.c_void_p), ("n_cells_global", C.c_uint64)]
 
 
 class _SolveResult(C.Structure):
@@ -72,6 +73,7 @@ class _Stats(C.Structure):
                 ("groups", C.c_int32), ("padded_cols", C.c_int32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
 BCAST_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32)
 
@@ -327,7 +329,8 @@ class Context:
 
     def solve(self, k, method=METHOD_EM, n_streams=1, solves_per_stream=1, stream_seeds=None, theta0=None,
               base_theta=None, reinit_clusters=None, iteration_cap=0, max_slots=0, lanes=0, record_counts=False,
-              keep_trace=False, poll_chunk=0, time_kernels=False, shard_rank=0, shard_world=1) -> SolveResult:
+              keep_trace=False, poll_chunk=0, time_kernels=False, shard_rank=0, shard_world=1, cell_allreduce=None,
+              n_cells_global=0) -> SolveResult:
         n_solves = n_streams * solves_per_stream
         p = _SolveParams()
         p.k, p.method, p.n_streams, p.solves_per_stream = k, method, n_streams, solves_per_stream
@@ -352,6 +355,10 @@ class Context:
         p.iteration_cap, p.max_slots, p.lanes = iteration_cap, max_slots, lanes
         p.record_counts, p.keep_trace, p.poll_chunk = int(record_counts), int(keep_trace), poll_chunk
         p.shard_rank, p.shard_world, p.time_kernels = shard_rank, shard_world, int(time_kernels)
+        if cell_allreduce is not None:
+            p.cell_allreduce = C.cast(cell_allreduce, C.c_void_p)
+            p.n_cells_global = n_cells_global
+            keep.append(cell_allreduce)
         r = _SolveResult()
         lp = np.zeros((self.n_cells, k), dtype=np.float32)
         th = np.zeros((k, self.n_loci), dtype=np.float32)
@@ -452,6 +459,26 @@ def exchange_best(rank, world, allgather, bcast, loss, solve, has_best, log_prob
                                     _ptr(log_probs), 0 if log_probs is None else log_probs.size,
                                     _ptr(theta), 0 if theta is None else theta.size, C.byref(w)))
     return float(l.value), int(s_.value), bool(h.value), int(w.value)
+
+
+def torch_allreduce_callback(dist):
+    """soup_allreduce_fn over torch.distributed (NCCL): sums the device buffer in place on torch's current stream —
+    create the Context on that stream (Context(device, stream=torch.cuda.current_stream().cuda_stream))."""
+    import torch
+
+    class _Dev:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+    def _ar(user, buf, n, stream):
+        try:
+            t = torch.as_tensor(_Dev(buf, n), device="cuda")
+            dist.all_reduce(t)
+            return OK
+        except Exception:
+            return ERR_INVALID
+
+    return ALLREDUCE_FN(_ar)
 
 
 def torch_exchange_callbacks(dist):

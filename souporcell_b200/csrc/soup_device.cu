@@ -40,6 +40,8 @@ struct Workspace {
     int *e_group_active = nullptr, *m_group_active = nullptr, *l_group_active = nullptr, *counts = nullptr, *queue = nullptr, *draw_of_k = nullptr, *solve_iters = nullptr;
     float *solve_loss = nullptr, *best_lp = nullptr, *best_theta = nullptr;
     IterRec* trace = nullptr;
+    float* stats = nullptr;     // cell-sharded mode: [SP | DP | per-slot loss], one all-reduce per iteration
+    size_t stats_floats = 0;
     int2* moves = nullptr;
     uint32_t* stream_keys = nullptr;
     int n_streams_cap = 0;
@@ -525,6 +527,9 @@ struct IterLaunch {
     float log_prior, limit;
     bool record_counts;
     int timed_iter = -1;   // >= 0: bracket this iteration's E and M launches with events ev_k[4*i .. 4*i+3]
+    soup_allreduce_fn allreduce = nullptr;   // cell-sharded mode
+    void* comm_user = nullptr;
+    int32_t comm_error = 0;
     RefillArgs refill;
     FinalizeArgs fin;
 };
@@ -561,7 +566,7 @@ static void launch_m(soup_ctx* ctx) {
     const uint32_t long_blocks = (long_items + EM_WARPS - 1) / EM_WARPS;
     const uint32_t wide_chunks = (uint32_t)((ctx->L - n_long + EM_WARPS - 1) / EM_WARPS);
     const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
-                  w.m_group_active, w.l_group_active, w.ctl, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main,
+                  w.m_group_active, w.l_group_active, w.ctl, w.stats, w.stats ? w.stats + (size_t)ctx->L * w.Cpad : nullptr, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main,
                   n_long, (uint32_t)w.lp.n_groups, long_blocks, wide_chunks,
                   (uint32_t)((uint64_t)ctx->N * w.Cpad * 4 > (48ull << 20))};
     const dim3 grid(long_blocks + wide_chunks * w.mp.n_groups);
@@ -592,7 +597,10 @@ static void launch_loss_control(soup_ctx* ctx, cudaStream_t st, bool counts, flo
 
 // E -> post -> { loss + control on the side stream  ||  M on the main stream } -> harvest -> refill -> finalize.
 // The M pass does not depend on the loss, so the strictly sequential loss sum hides behind it.
-static void enqueue_iteration(const IterLaunch& it) {
+// Cell-sharded mode (each rank holds a range of cells): E -> post -> partial loss -> partial M -> ONE all-reduce of
+// [S | D | loss] over the ranks (callback, enqueued on this stream) -> theta -> control -> ...; every rank then takes
+// the same control decisions from the same reduced numbers.
+static void enqueue_iteration(IterLaunch& it) {
     soup_ctx* ctx = it.ctx;
     Workspace& w = ctx->ws;
     cudaEvent_t* ev = it.timed_iter >= 0 ? ctx->ev_k.data() + (size_t)it.timed_iter * 4 : nullptr;
@@ -600,14 +608,27 @@ static void enqueue_iteration(const IterLaunch& it) {
     launch_e(ctx, it.log_prior);
     if (ev) cudaEventRecord(ev[1], ctx->stream);
     launch_post(ctx, it.method, it.record_counts);
-    cudaEventRecord(ctx->ev_fork, ctx->stream);
-    cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
-    launch_loss_control(ctx, ctx->side, it.record_counts, it.limit);
-    cudaEventRecord(ctx->ev_join, ctx->side);
-    if (ev) cudaEventRecord(ev[2], ctx->stream);
-    launch_m(ctx);
-    if (ev) cudaEventRecord(ev[3], ctx->stream);
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    if (it.allreduce) {
+        float* loss = w.stats + 2 * (size_t)ctx->L * w.Cpad;
+        loss_kernel<<<w.slots, 256, 0, ctx->stream>>>(w.LSE, w.st, loss, (uint32_t)ctx->N);
+        if (ev) cudaEventRecord(ev[2], ctx->stream);
+        launch_m(ctx);
+        if (ev) cudaEventRecord(ev[3], ctx->stream);
+        const int32_t e = it.allreduce(it.comm_user, w.stats, w.stats_floats, (void*)ctx->stream);
+        if (e != SOUP_OK && it.comm_error == 0) it.comm_error = e;
+        theta_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(w.stats, w.stats + (size_t)ctx->L * w.Cpad, w.col_write, w.TH, w.LA, w.LB, (uint32_t)ctx->L, w.Cpad);
+        ControlArgs c{loss, w.st, w.ctl, nullptr, w.trace, w.solve_loss, w.solve_iters, (uint32_t)ctx->N, w.K, w.slots, w.iter_cap, it.limit};
+        control_kernel<<<1, std::min(1024, (w.slots + 31) / 32 * 32), 0, ctx->stream>>>(c);
+    } else {
+        cudaEventRecord(ctx->ev_fork, ctx->stream);
+        cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
+        launch_loss_control(ctx, ctx->side, it.record_counts, it.limit);
+        cudaEventRecord(ctx->ev_join, ctx->side);
+        if (ev) cudaEventRecord(ev[2], ctx->stream);
+        launch_m(ctx);
+        if (ev) cudaEventRecord(ev[3], ctx->stream);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    }
     harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K);
     launch_refill(ctx, it.refill);
     finalize_kernel<<<1, 1024, 0, ctx->stream>>>(it.fin);
@@ -642,7 +663,10 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     if (r->solve_iters) for (int i = 0; i < n_solves; ++i) r->solve_iters[i] = 0;
     ctx->h_trace.clear(); ctx->h_trace_solve.clear(); ctx->h_trace_iters.clear(); ctx->h_trace_cap = iter_cap;
 
-    const float limit = 0.01f * (float)ctx->N;                 // S:214
+    const bool cell_mode = p->cell_allreduce != nullptr;
+    if (cell_mode && world > 1) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: cell sharding and restart sharding are exclusive in one call");
+    if (cell_mode && p->n_cells_global < ctx->N) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: n_cells_global must be the total cell count over all ranks");
+    const float limit = 0.01f * (float)(cell_mode ? p->n_cells_global : ctx->N);   // S:214 (all cells)
     const float log_prior = logf(1.0f / (float)K);             // S:202 (host libm = the reference's f32::ln)
     const bool any_iteration = (10000.0f > limit) && iter_cap > 0;
     if (n_local == 0 || !any_iteration) {
@@ -677,6 +701,19 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     pt.lap("solve: workspace");
     Workspace& w = ctx->ws;
     cudaStream_t st = ctx->stream;
+    if (cell_mode) {
+        const size_t need = 2 * (size_t)ctx->L * w.Cpad + (size_t)slots;
+        if (w.stats_floats != need) {
+            float* sp = nullptr;
+            cudaError_t e = ws_alloc(w, st, &sp, need, true);
+            if (e != cudaSuccess) { cudaGetLastError(); return ctx->fail(SOUP_ERR_NOMEM, "soup_solve: cannot allocate the all-reduce buffer: %s", cudaGetErrorString(e)); }
+            w.stats = sp;
+            w.stats_floats = need;
+        }
+    } else {
+        w.stats = nullptr;      // (kept allocated inside the workspace; not used by the M pass in this mode)
+        w.stats_floats = 0;
+    }
 
     // ---- per-call device inputs
     float *d_theta0 = nullptr, *d_base = nullptr;
@@ -737,7 +774,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     CKS(cudaMemsetAsync(w.counts, 0, (size_t)slots * K * 4, st));
 
     IterLaunch it;
-    it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0;
+    it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0 && !cell_mode;
+    it.allreduce = p->cell_allreduce; it.comm_user = p->comm_user;
     it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, w.draw_of_k, w.TH, w.LA, w.LB,
                            (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream};
     it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write,
@@ -783,6 +821,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         CKS(enqueue_chunk(cur ^ 1));
         CKS(cudaEventSynchronize(ctx->ev_poll[cur]));
         ++polls;
+        if (it.comm_error) { cleanup(); return ctx->fail(it.comm_error, "soup_solve: the all-reduce callback failed (%d)", it.comm_error); }
         if (ctx->h_ctl[cur].done_count >= n_local) break;
         if (iters_enqueued > (uint64_t)n_local * (uint64_t)(iter_cap + TEMP_STEPS) + 64) { cleanup(); return ctx->fail(SOUP_ERR_CUDA, "soup_solve: device control loop did not converge"); }
     }
@@ -884,6 +923,8 @@ static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
     int32_t rc = ensure_workspace(ctx, k, n_slots, forced, 1, n_slots, 1);
     if (rc != SOUP_OK) return rc;
     Workspace& w = ctx->ws;
+    w.stats = nullptr;          // the hooks always run the single-GPU M pass
+    w.stats_floats = 0;
     std::vector<int> ga(std::max(std::max(w.ep.n_groups, w.mp.n_groups), w.lp.n_groups), 1);
     cudaMemcpyAsync(w.l_group_active, ga.data(), (size_t)w.lp.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(w.e_group_active, ga.data(), (size_t)w.ep.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);

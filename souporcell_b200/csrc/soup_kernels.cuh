@@ -602,6 +602,7 @@ struct MArgs {
     const int* group_active;        // wide role: column groups of 32*VM (+ one narrower last group)
     const int* long_group_active;   // long role: column groups of 32*SOUP_M_VLONG
     const Ctl* ctl;
+    float* SP; float* DP;           // cell-sharded mode: partial sums of this rank's cells, [L][Cpad] each (else nullptr)
     Packing pk;
     uint32_t L, Cpad, n_groups, n_main;
     uint32_t n_long, long_groups, long_blocks, wide_chunks, group_major;   // loci [0, n_long) of the LPT order take the long role
@@ -613,9 +614,10 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
     const uint32_t col = col0 + lane * lane_cols<V>();
     const uint64_t j0 = a.col_ptr[locus];
     const uint32_t n = (uint32_t)(a.col_ptr[locus + 1] - j0);
+    const bool partial = a.SP != nullptr;
     FVec<V> s, d;
 #pragma unroll
-    for (int v = 0; v < V; ++v) { s.v[v] = 1.0f; d.v[v] = 2.0f; }   // pseudocounts S:197-198, S:456-464
+    for (int v = 0; v < V; ++v) { s.v[v] = partial ? 0.0f : 1.0f; d.v[v] = partial ? 0.0f : 2.0f; }   // pseudocounts S:197-198, S:456-464
     if (DEEP) {
 #if SOUP_M_DEEP
         m_walk_deep<V, SOUP_M_ULONG>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
@@ -626,6 +628,15 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
         constexpr int U = V <= 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16);
         if (!a.ctl->nonfinite) m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
         else m_walk<V, 2, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+    }
+    if (partial) {   // cell-sharded: hand the partial statistics to the all-reduce; theta_kernel finishes the M pass
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const size_t o = (size_t)locus * a.Cpad + col_of<V>(col0, lane, v);
+            a.SP[o] = s.v[v];
+            a.DP[o] = d.v[v];
+        }
+        return;
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -666,6 +677,22 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2)) mstep
     const uint32_t locus = a.locus_order[li];
     if (VM == VT || group < a.n_main) mstep_body<VM, false>(a, locus, group * (32 * VM));
     else mstep_body<VT, false>(a, locus, a.n_main * (32 * VM));
+}
+
+// cell-sharded mode, after the all-reduce of (SP, DP): theta = clamp((1 + S) / (2 + D)) and the ln tables.
+// The pseudocount joins the globally reduced sum here, so the rounding differs from the sequential reference
+// (and from the single-GPU path) in the last bits: this mode agrees to tolerance, not bit for bit.
+__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ SP, const float* __restrict__ DP, const uint8_t* __restrict__ col_write,
+                                                    float* __restrict__ TH, float* __restrict__ LA, float* __restrict__ LB, uint32_t L, uint32_t Cpad) {
+    const size_t n = (size_t)L * Cpad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i % Cpad);
+        if (!col_write[c]) continue;
+        const float th = fmaxf(fminf(__fdiv_rn(__fadd_rn(1.0f, SP[i]), __fadd_rn(2.0f, DP[i])), 0.99f), 0.01f);
+        TH[i] = th;
+        LA[i] = soupmath::glibc_logf(th);
+        LB[i] = soupmath::glibc_logf(1.0f - th);
+    }
 }
 
 // ------------------------------------------------------------------ harvest: keep the best solve (S:110-114)

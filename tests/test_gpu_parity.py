@@ -308,3 +308,91 @@ def test_full_size_properties_config2():
         full = sp.main(ctx, cfg["k"], restarts=50, threads=50)
         assert full.has_best and full.nnz_updates % ctx.nnz == 0 and 9 * 50 <= full.nnz_updates // ctx.nnz <= 1000 * 50
         assert np.isfinite(full.best_log_probs).all() and (np.bincount(full.assignments, minlength=cfg["k"]) > 0).sum() >= 4
+
+
+# ---------------------------------------------------------------------------------------------- cell-sharded mode
+def _split_cells(csr, parts):
+    """contiguous cell ranges balanced by nnz; each shard keeps all loci."""
+    n, L, row_ptr, locus, alt, ref = csr
+    rp = row_ptr.astype(np.int64)
+    cuts = [0] + [int(np.searchsorted(rp, rp[-1] * i // parts)) for i in range(1, parts)] + [n]
+    out = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s, e = rp[a], rp[b]
+        out.append((b - a, L, (rp[a:b + 1] - s).astype(np.uint64), locus[s:e], alt[s:e], ref[s:e]))
+    return cuts, out
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("method", [sp.METHOD_EM, sp.METHOD_KHM])
+def test_cell_sharded_mode_agrees_with_oracle_to_tolerance(world, method):
+    """`world` ranks emulated on one GPU: one context per cell shard, one thread per rank, the all-reduce callback is a
+    rendezvous that sums the ranks' device buffers.  The pseudocount joins the reduced sum, so this mode is checked at
+    north_star's tolerance (1e-5 relative per-iteration loss and theta, up to the first differing control decision)
+    and on hard assignments, not bit for bit."""
+    import threading
+    import torch
+    from souporcell_b200 import api
+
+    v, csr = synth_csr(n_cells=400, n_loci=2500, k=3, mean_loci=110, seed=17)
+    od = orc.OracleData.from_csr(*csr)
+    cuts, shards = _split_cells(csr, world)
+    k, S = 3, 4
+    theta0 = random_theta(np.random.default_rng(2), (S, k, csr[1]))
+    bar = threading.Barrier(world)
+    bufs, tmp = [None] * world, [None]
+
+    class Dev:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+    def make_cb(rank):
+        def cb(user, buf, n, stream):
+            try:
+                torch.cuda.synchronize()                       # this rank's partial statistics are complete
+                bufs[rank] = torch.as_tensor(Dev(buf, n), device="cuda")
+                bar.wait()
+                if rank == 0:
+                    acc = bufs[0].clone()
+                    for t in bufs[1:]:
+                        acc += t                               # fixed rank order -> deterministic
+                    tmp[0] = acc
+                    torch.cuda.synchronize()
+                bar.wait()
+                bufs[rank].copy_(tmp[0])
+                torch.cuda.synchronize()
+                bar.wait()
+                return 0
+            except Exception:
+                bar.abort()
+                return -1
+        return api.ALLREDUCE_FN(cb)
+
+    results = [None] * world
+
+    def run(rank):
+        with sp.Context(0) as ctx:
+            ctx.load_csr(*shards[rank])
+            res = ctx.solve(k, method=method, n_streams=S, solves_per_stream=1, theta0=theta0, keep_trace=True, max_slots=3,
+                            cell_allreduce=make_cb(rank), n_cells_global=csr[0])
+            results[rank] = (res, [ctx.get_trace(s) for s in range(S)])
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert all(r is not None for r in results)
+    res0, traces0 = results[0]
+    want = [od.solve(theta0[s], method=method) for s in range(S)]
+    for s in range(S):
+        got_tr, want_tr = traces0[s], want[s]["trace"]
+        n_same = min(len(got_tr), len(want_tr))
+        np.testing.assert_allclose([t[1] for t in got_tr[:n_same]], [t[1] for t in want_tr[:n_same]], rtol=1e-5)
+        assert abs(len(got_tr) - len(want_tr)) <= 1                      # at most one borderline convergence decision
+        for r in range(1, world):                                         # every rank takes identical decisions
+            assert results[r][1][s] == got_tr
+    best = int(np.argmax([w["loss"] for w in want]))
+    assert res0.best_solve == best
+    np.testing.assert_allclose(res0.best_theta, want[best]["theta"], rtol=1e-5, atol=1e-7)
+    lp = np.concatenate([results[r][0].best_log_probs for r in range(world)])   # each rank returns its own cells
+    np.testing.assert_allclose(lp, want[best]["log_probs"], rtol=1e-5)
+    assert np.array_equal(np.argmax(lp, axis=1), np.argmax(want[best]["log_probs"], axis=1))
