@@ -21,6 +21,7 @@ N > 1 (torchrun, one rank per GPU): restarts shard across ranks with no data-pat
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -51,6 +52,16 @@ def algorithmic_bytes(nnz, K, L, N):
     e = 8 * nnz + 8 * K * L + 4 * K * N + 12 * N
     m = 8 * nnz + 4 * K * N + 8 * K * L + 4 * L
     return e, m
+
+
+def profiled_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as fh:
+            return json.load(fh)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -192,6 +203,7 @@ def ours(args):
 
     def timed(fn):
         flush.zero_()
+        gc.collect()          # collect between steps, never inside one (a gen-2 pass over this process's heap costs ~50 ms)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
@@ -211,6 +223,7 @@ def ours(args):
             dist.all_reduce(t)
         return float(t[0])
 
+    gc.disable()
     # ---- device-resident leg ("value")
     for _ in range(args.warmup):
         timed(job)
@@ -220,6 +233,8 @@ def ours(args):
     dev_ms = wall_ms = updates = launches = 0.0
     for _ in range(args.steps):
         r, ms_d, ms_w = timed(job)
+        if os.environ.get("SOUP_DEBUG_ITERS"):
+            print(f"bench value step: wall {ms_w:.2f} ms device {ms_d:.2f} ms solve {r.solve_ms:.2f} ms", file=sys.stderr)
         dev_ms += ms_d; wall_ms += ms_w
         updates += total(r.nnz_updates); launches += total(r.kernel_launches)
     value = updates / (dev_ms * 1e-3)
@@ -228,7 +243,7 @@ def ours(args):
     # the previous kernel's tail, which costs ~10 % of the step.
     em = [0.0, 0.0, 0, 0]
     ev_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(0 if os.environ.get("SOUP_BENCH_NO_EVENTS") else args.steps):
         r, ms_d, _ = timed(lambda: job(time_kernels=True))
         ev_ms += ms_d
         em[0] += r.estep_ms; em[1] += r.mstep_ms; em[2] += r.timed_iterations; em[3] += r.slot_iterations
@@ -243,6 +258,8 @@ def ours(args):
     e_ms = e_upd = 0.0
     for _ in range(args.steps):
         r, ms_d, ms_w = timed(e2e_job)
+        if os.environ.get("SOUP_DEBUG_ITERS"):
+            print(f"bench e2e step: wall {ms_w:.2f} ms device {ms_d:.2f} ms", file=sys.stderr)
         e_ms += ms_w; e_upd += total(r.nnz_updates)       # wall clock: includes host-side packing and copies
     h2d = (n + 1) * 8 + nnz * 12 + restarts // world * 32
     d2h = n * K * 4 + K * L * 4
@@ -262,7 +279,7 @@ def ours(args):
                     "ms_per_step": e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": per_launch_bytes,
+                         "traffic": profiled_traffic(kern), "peak_source": peak_src, "bytes_per_launch": per_launch_bytes,
                          "avg_launch_ms": k_ms / max(em[2], 1), "estep_ms": em[0], "mstep_ms": em[1], "launches_timed": em[2],
                          "timing": f"per-launch CUDA events on the launching stream over {args.steps} extra steps of the same job ({ev_ms / args.steps:.2f} ms/step with events)",
                          "whole_step": {"bytes_per_nnz_update": (be + bm) / nnz, "achieved_per_gpu": value / world * (be + bm) / nnz / 1e9,

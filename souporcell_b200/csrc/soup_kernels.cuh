@@ -37,7 +37,7 @@ namespace soup {
 #define SOUP_M_U16 2
 #endif
 #ifndef SOUP_M_VLONG
-#define SOUP_M_VLONG 1   // columns per lane for the long loci of the M pass
+#define SOUP_M_VLONG 2   // columns per lane for the long loci of the M pass
 #endif
 #ifndef SOUP_M_ULONG
 #define SOUP_M_ULONG 16  // row gathers in flight per warp in the long role
