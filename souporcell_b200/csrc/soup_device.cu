@@ -465,7 +465,7 @@ static Workspace::GroupPlan plan_groups(int cols, int vmax, int forced_lanes) {
         g.padded = (uint32_t)(g.n_groups * gw);
         return g;
     }
-    auto fit = [](int c) { return c <= 32 ? 1 : (c <= 64 ? 2 : (c <= 128 ? 4 : 8)); };
+    auto fit = [](int c) { return c <= 32 ? 1 : (c <= 64 ? 2 : (c <= 128 ? 4 : (c <= 256 ? 8 : 16))); };
     const int wm = 32 * vmax;
     if (cols <= wm) {                       // one group, as narrow as fits
         g.VM = g.VT = std::min(vmax, fit(cols));
@@ -489,7 +489,7 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     ws_free(w);
     w.K = K; w.slots = slots; w.forced_lanes = forced_lanes; w.iter_cap = iter_cap; w.queue_cap = queue_cap; w.n_streams_cap = n_streams;
     const size_t cols = (size_t)slots * K;
-    w.ep = plan_groups((int)cols, 8, forced_lanes);
+    w.ep = plan_groups((int)cols, SOUP_E_VMAX, forced_lanes);
     w.mp = plan_groups((int)cols, SOUP_M_VWIDE, forced_lanes);
     w.lp = plan_groups((int)cols, SOUP_M_VLONG, SOUP_M_VLONG);
     w.Cpad = std::max(std::max(w.ep.padded, w.mp.padded), w.lp.padded);
@@ -537,7 +537,11 @@ struct IterLaunch {
 #define SOUP_DISPATCH(KERNEL, PLAN, ARGS)                                                                    \
     do {                                                                                                     \
         const int vm_ = (PLAN).VM, vt_ = (PLAN).VT;                                                          \
-        if (vm_ == 16) KERNEL<16, 16><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                           \
+        if (vm_ == 16 && vt_ == 16) KERNEL<16, 16><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);              \
+        else if (vm_ == 16 && vt_ == 8) KERNEL<16, 8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);           \
+        else if (vm_ == 16 && vt_ == 4) KERNEL<16, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);           \
+        else if (vm_ == 16 && vt_ == 2) KERNEL<16, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);           \
+        else if (vm_ == 16 && vt_ == 1) KERNEL<16, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);           \
         else if (vm_ == 8 && vt_ == 8) KERNEL<8, 8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                  \
         else if (vm_ == 8 && vt_ == 4) KERNEL<8, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
         else if (vm_ == 8 && vt_ == 2) KERNEL<8, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \

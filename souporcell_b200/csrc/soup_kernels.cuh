@@ -45,6 +45,9 @@ namespace soup {
 #ifndef SOUP_M_DEEP
 #define SOUP_M_DEEP 0    // 1: ping-pong register tiles in the long role (measured slower); 0: single tile of SOUP_M_ULONG rows
 #endif
+#ifndef SOUP_E_VMAX
+#define SOUP_E_VMAX 8    // widest E-pass column group, in columns per lane
+#endif
 #ifndef SOUP_M_VWIDE
 #define SOUP_M_VWIDE 8   // columns per lane for all other loci
 #endif

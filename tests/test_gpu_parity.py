@@ -396,3 +396,18 @@ def test_cell_sharded_mode_agrees_with_oracle_to_tolerance(world, method):
     lp = np.concatenate([results[r][0].best_log_probs for r in range(world)])   # each rank returns its own cells
     np.testing.assert_allclose(lp, want[best]["log_probs"], rtol=1e-5)
     assert np.array_equal(np.argmax(lp, axis=1), np.argmax(want[best]["log_probs"], axis=1))
+
+
+def test_main_over_two_contexts_equals_one(small):
+    """soup_main's in-process restart sharding (one context per GPU, one thread each), exercised with two contexts on
+    the same device: solves split s mod 2, winner merged with the reference's tie rule -> identical to one context."""
+    _, csr, ctx, od = small
+    with sp.Context(0) as ctx2:
+        ctx2.load_csr(*csr)
+        for method, s3 in ((sp.METHOD_EM, False), (sp.METHOD_KHM, False)):
+            one = sp.main(ctx, 4, method=method, restarts=7, threads=3, seed=4)
+            two = sp.main([ctx, ctx2], 4, method=method, restarts=7, threads=3, seed=4)
+            assert one.has_best and two.has_best and bits([one.best_loss])[0] == bits([two.best_loss])[0]
+            assert np.array_equal(bits(one.best_log_probs), bits(two.best_log_probs))
+            assert np.array_equal(bits(one.best_theta), bits(two.best_theta))
+            assert one.nnz_updates == two.nnz_updates
