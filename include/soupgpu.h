@@ -67,6 +67,11 @@ void soup_mtx_free(soup_mtx* m);
 int32_t soup_barcodes_load(const char* path, char** blob, uint64_t* n_barcodes);
 void soup_free(void* p);
 
+/* init_cluster_centers_known_genotypes S:514-542: centers [k][n_loci] from a (plain or gzipped) VCF; record i is
+ * original locus i (S:523-539).  `sample_names`: n_samples NUL-terminated strings back to back, sample s -> cluster s. */
+int32_t soup_known_genotypes_load(const char* vcf_path, const char* sample_names, int32_t n_samples, int32_t k,
+                                  const uint64_t* index_to_locus, uint64_t n_loci, float* theta /*[k][n_loci]*/);
+
 /* rand 0.9.3 StdRng (= rand_chacha 0.9.0 ChaCha12, key = seed, 64-bit counter from 0):
  * `n` consecutive u32 words starting at absolute word `word_offset` (S:52,62,559,858). */
 int32_t soup_chacha_words(const uint8_t seed[32], int32_t rounds, uint64_t word_offset, uint32_t* out, uint64_t n);
@@ -115,6 +120,8 @@ typedef struct soup_solve_params {
     int32_t solves_per_stream; /* solves_per_thread (S:63); total solves = n_streams * this */
     const uint8_t* stream_seeds; /* [n_streams][32]: ThreadData rng seeds; used when theta0 == NULL */
     const float* theta0;       /* optional host [n_solves][k][L] initial centers, solve = stream*sps + iter */
+    const float* init_theta;   /* optional host [k][L]: deterministic initial centers (known genotypes, S:487): draw d of a solve
+                                * takes row d of it instead of the RNG stream, in every solve */
     const float* base_theta;   /* optional host [k][L]: best_cluster_centers of the previous run (S:93) */
     const int32_t* reinit_clusters; /* bad clusters re-drawn this run (S:92-96); the rest are locked (S:97) */
     int32_t n_reinit;          /* 0 = run 0: draw all k, lock nothing */
@@ -206,6 +213,7 @@ typedef struct soup_main_params {
     int32_t souporcell3;
     int32_t iteration_cap; /* 0 -> 1000 */
     int32_t max_slots, lanes, record_counts, verbose_trace, time_kernels;
+    const float* known_theta;        /* optional host [k][n_loci] from soup_known_genotypes_load (--known_genotypes) */
     int32_t proc_rank, proc_world;   /* process-level shard; world 0/1 = single process */
     soup_allgather_fn allgather;     /* required when proc_world > 1 */
     soup_bcast_fn bcast;

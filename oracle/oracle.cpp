@@ -484,10 +484,87 @@ std::vector<std::vector<float>> init_cluster_centers_uniform(size_t loci, size_t
     return centers;
 }
 
+// S:514-542.  The reference reads the VCF with the `vcf` crate (0.6, not vendored): records in file order, record
+// index = original locus id, record.call[sample]["GT"][0] = the sample's GT string.  Restated here for plain or
+// gzipped text VCF: FORMAT column -> position of GT, sample column from the #CHROM header line.
+static std::string read_text_maybe_gz(const std::string& path) {
+    std::string content;
+    gzFile f = gzopen(path.c_str(), "rb");   // zlib reads plain files transparently
+    if (!f) throw std::runtime_error("couldn't open file " + path);
+    char buf[1 << 16];
+    int n;
+    while ((n = gzread(f, buf, sizeof(buf))) > 0) content.append(buf, n);
+    gzclose(f);
+    return content;
+}
+static std::vector<std::string> split_char(const std::string& s, char c) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    for (;;) {
+        size_t j = s.find(c, i);
+        if (j == std::string::npos) { out.emplace_back(s, i); break; }
+        out.emplace_back(s, i, j - i);
+        i = j + 1;
+    }
+    return out;
+}
+std::vector<std::vector<float>> init_cluster_centers_known_genotypes(size_t loci, const Params& params,
+                                                                      const std::vector<size_t>& locus_to_index) {
+    std::vector<std::vector<float>> centers(params.num_clusters, std::vector<float>(loci, 0.5f));   // S:515-521
+    const std::string text = read_text_maybe_gz(params.known_genotypes);
+    std::vector<std::string> header_samples;
+    size_t locus_id = 0, pos = 0;
+    while (pos < text.size()) {
+        size_t e = text.find('\n', pos);
+        if (e == std::string::npos) e = text.size();
+        std::string line(text, pos, e - pos);
+        pos = e + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '#') {
+            if (line.rfind("#CHROM", 0) == 0) {
+                auto cols = split_char(line, '\t');
+                for (size_t i = 9; i < cols.size(); ++i) header_samples.push_back(cols[i]);
+            }
+            continue;
+        }
+        if (locus_id < locus_to_index.size() && locus_to_index[locus_id] != SIZE_MAX) {   // S:526
+            const size_t loci_index = locus_to_index[locus_id];
+            if (params.known_genotypes_sample_names.empty())
+                throw std::runtime_error("currently requiring known_genotypes_sample_names if known_genotypes set");   // S:537
+            auto cols = split_char(line, '\t');
+            if (cols.size() < 10) throw std::runtime_error("known_genotypes: record without sample columns");
+            auto fmt = split_char(cols[8], ':');
+            size_t gt_pos = SIZE_MAX;
+            for (size_t i = 0; i < fmt.size(); ++i) if (fmt[i] == "GT") gt_pos = i;
+            for (size_t sample_index = 0; sample_index < params.known_genotypes_sample_names.size(); ++sample_index) {
+                const std::string& sample = params.known_genotypes_sample_names[sample_index];
+                size_t col = SIZE_MAX;
+                for (size_t i = 0; i < header_samples.size(); ++i) if (header_samples[i] == sample) col = i;
+                if (col == SIZE_MAX || 9 + col >= cols.size() || gt_pos == SIZE_MAX)
+                    throw std::runtime_error("known_genotypes: sample or GT missing (reference panics on the map lookup)");
+                auto fields = split_char(cols[9 + col], ':');
+                if (gt_pos >= fields.size()) throw std::runtime_error("known_genotypes: GT missing in the sample column");
+                const std::string& gt = fields[gt_pos];
+                if (gt.empty()) throw std::runtime_error("known_genotypes: empty GT (reference unwraps None)");
+                if (gt[0] == '.') continue;                                            // S:532
+                auto hap = [&](size_t i) -> uint32_t {                                   // single-char parse::<u32>().unwrap().min(1)
+                    if (i >= gt.size() || gt[i] < '0' || gt[i] > '9') throw std::runtime_error("known_genotypes: cannot parse GT '" + gt + "'");
+                    return std::min<uint32_t>((uint32_t)(gt[i] - '0'), 1u);
+                };
+                const uint32_t hap0 = hap(0), hap1 = hap(2);                             // S:533-534
+                if (sample_index >= centers.size()) throw std::runtime_error("known_genotypes: more sample names than clusters (index out of bounds)");
+                centers[sample_index][loci_index] = fmaxf(fminf((float)(hap0 + hap1) / 2.0f, 0.99f), 0.01f);   // S:535
+            }
+        }
+        ++locus_id;
+    }
+    return centers;
+}
+
 static std::vector<std::vector<float>> init_cluster_centers(size_t loci_used, const Params& params, ChaChaRng& rng,
-                                                            size_t num_clusters) {   // S:485-498
-    if (params.has_known_genotypes)
-        throw std::runtime_error("oracle: known_genotypes init not restated (SURVEY 8f-3, next row)");
+                                                            size_t num_clusters, const std::vector<size_t>& locus_to_index) {   // S:485-498
+    if (params.has_known_genotypes) return init_cluster_centers_known_genotypes(loci_used, params, locus_to_index);   // S:487
     if (params.has_known_cell_assignments) throw std::runtime_error("known cell assignments not yet implemented");
     switch (params.initialization_strategy) {
         case ClusterInit::KmeansPP: throw std::runtime_error("kmeans++ not yet implemented");
@@ -516,7 +593,7 @@ static void new_seed(ChaChaRng& rng, uint8_t seed[32]) {   // S:855-861
 }
 
 MainResult souporcell_main(size_t loci_used, const std::vector<CellData>& cells, const Params& params,
-                           const std::vector<size_t>& /*locus_to_index*/, Trace* trace, FILE* log,
+                           const std::vector<size_t>& locus_to_index, Trace* trace, FILE* log,
                            const float* theta0_override) {
     uint8_t seed[32];
     memset(seed, params.seed, 32);
@@ -548,14 +625,14 @@ MainResult souporcell_main(size_t loci_used, const std::vector<CellData>& cells,
                     std::vector<std::vector<float>> centers;
                     std::vector<size_t> locked;
                     if (run == 0) {
-                        centers = init_cluster_centers(loci_used, params, td.rng, K);
+                        centers = init_cluster_centers(loci_used, params, td.rng, K, locus_to_index);
                         if (theta0_override) {
                             const float* t0 = theta0_override + (td.thread_num * td.solves_per_thread + iteration) * K * loci_used;
                             for (size_t c = 0; c < K; ++c)
                                 for (size_t l = 0; l < loci_used; ++l) centers[c][l] = t0[c * loci_used + l];
                         }
                     } else {                                                   // S:91-98
-                        auto re = init_cluster_centers(loci_used, params, td.rng, bad.size());
+                        auto re = init_cluster_centers(loci_used, params, td.rng, bad.size(), locus_to_index);
                         centers = res.best_cluster_centers;
                         for (size_t i = 0; i < bad.size(); ++i) centers[bad[i]] = re[i];
                         for (size_t c = 0; c < K; ++c)

@@ -131,6 +131,8 @@ std::vector<size_t> bad_cluster_detection(size_t run, size_t num_clusters,
                                           const std::vector<std::vector<float>>& best_lp, FILE* log);  // S:150-187
 
 std::vector<std::vector<float>> init_cluster_centers_uniform(size_t loci, size_t k, ChaChaRng& rng);   // S:554-563
+std::vector<std::vector<float>> init_cluster_centers_known_genotypes(size_t loci, const Params& params,
+                                                                      const std::vector<size_t>& locus_to_index);   // S:514-542
 
 struct MainResult {
     float best_log_probability;

@@ -137,6 +137,22 @@ int orc_main(void* dv, int K, int method, uint32_t restarts, uint32_t threads, u
     } catch (const std::exception& e) { set_err(err, errlen, e.what()); return -1; }
 }
 
+// init_cluster_centers_known_genotypes S:514-542.  sample_names: n NUL-terminated strings back to back.  theta [K][L].
+int orc_known_genotypes(void* dv, const char* vcf_path, const char* sample_names, int n_samples, int K, float* theta, char* err, int errlen) {
+    try {
+        LoadedData* d = (LoadedData*)dv;
+        Params p;
+        p.num_clusters = K;
+        p.has_known_genotypes = true;
+        p.known_genotypes = vcf_path;
+        const char* q = sample_names;
+        for (int i = 0; i < n_samples; ++i) { p.known_genotypes_sample_names.emplace_back(q); q += strlen(q) + 1; }
+        auto c = init_cluster_centers_known_genotypes(d->loci_used, p, d->locus_to_index);
+        from_vv(c, theta, d->loci_used);
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errlen, e.what()); return -1; }
+}
+
 void orc_chacha_words(const uint8_t* seed, int rounds, uint64_t word_offset, uint32_t* out, uint64_t n) {
     ChaChaRng r = ChaChaRng::from_seed(seed, rounds);
     if (word_offset) r.seek_word(word_offset);

@@ -43,6 +43,7 @@ def lib():
         L.orc_main.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint8, C.c_int, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_char_p, C.c_int]
+        L.orc_known_genotypes.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
         L.orc_chacha_words.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_uint64]
         L.orc_chacha_words.restype = None
         L.orc_thread_seeds.argtypes = [C.c_uint8, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -111,6 +112,15 @@ class OracleData:
         i2l = np.empty(self.n_loci, dtype=np.uint64)
         lib().orc_data_export(self._h, _p(row_ptr), _p(locus), _p(alt), _p(ref), _p(lbc), _p(tot), _p(i2l))
         return dict(row_ptr=row_ptr, locus=locus, alt=alt, ref=ref, lbc=lbc, total_alleles=tot, index_to_locus=i2l)
+
+    def known_genotypes(self, vcf_path, sample_names, k):
+        """init_cluster_centers_known_genotypes S:514-542 -> centers [k][n_loci]."""
+        th = np.empty((k, self.n_loci), dtype=np.float32)
+        blob = b"".join(s.encode() + b"\0" for s in sample_names) + b"\0"
+        err = C.create_string_buffer(512)
+        if lib().orc_known_genotypes(self._h, os.fsencode(vcf_path), blob, len(sample_names), k, _p(th), err, 512) != 0:
+            raise RuntimeError("oracle: " + err.value.decode())
+        return th
 
     def step(self, theta, method=0, temp_step=0, locked=()):
         """One E pass + M pass (S:226-249).  theta [K][L] -> dict(theta_out, log_probs, weights, lse, loss)."""

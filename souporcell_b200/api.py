@@ -28,7 +28,7 @@ MTX_PINNED = 1
 
 EXPORTS = [
     "soup_version", "soup_last_error", "soup_mtx_load", "soup_mtx_free", "soup_barcodes_load", "soup_free",
-    "soup_chacha_words", "soup_thread_seeds", "soup_format_f32", "soup_ln_binomial_f32", "soup_bad_cluster_detection",
+    "soup_known_genotypes_load", "soup_chacha_words", "soup_thread_seeds", "soup_format_f32", "soup_ln_binomial_f32", "soup_bad_cluster_detection",
     "soup_ctx_create", "soup_ctx_destroy", "soup_load_csr", "soup_get_dims", "soup_get_csc", "soup_get_cell_totals",
     "soup_get_csr_lbc", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
     "soup_main", "soup_exchange_best", "soup_write_clusters",
@@ -49,7 +49,7 @@ class _Mtx(C.Structure):
 
 class _SolveParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("method", C.c_int32), ("n_streams", C.c_int32), ("solves_per_stream", C.c_int32),
-                ("stream_seeds", C.c_void_p), ("theta0", C.c_void_p), ("base_theta", C.c_void_p),
+                ("stream_seeds", C.c_void_p), ("theta0", C.c_void_p), ("init_theta", C.c_void_p), ("base_theta", C.c_void_p),
                 ("reinit_clusters", C.c_void_p), ("n_reinit", C.c_int32), ("iteration_cap", C.c_int32),
                 ("max_slots", C.c_int32), ("lanes", C.c_int32), ("record_counts", C.c_int32), ("keep_trace", C.c_int32),
                 ("poll_chunk", C.c_int32), ("time_kernels", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
@@ -82,7 +82,7 @@ class _MainParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("method", C.c_int32), ("restarts", C.c_uint32), ("threads", C.c_uint32),
                 ("seed", C.c_uint8), ("souporcell3", C.c_int32), ("iteration_cap", C.c_int32), ("max_slots", C.c_int32),
                 ("lanes", C.c_int32), ("record_counts", C.c_int32), ("verbose_trace", C.c_int32), ("time_kernels", C.c_int32),
-                ("proc_rank", C.c_int32), ("proc_world", C.c_int32), ("allgather", ALLGATHER_FN), ("bcast", BCAST_FN),
+                ("known_theta", C.c_void_p), ("proc_rank", C.c_int32), ("proc_world", C.c_int32), ("allgather", ALLGATHER_FN), ("bcast", BCAST_FN),
                 ("comm_user", C.c_void_p)]
 
 
@@ -115,6 +115,7 @@ def lib():
         L.soup_free.argtypes = [C.c_void_p]
         L.soup_free.restype = None
         L.soup_barcodes_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.soup_known_genotypes_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]
         L.soup_chacha_words.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_uint64]
         L.soup_thread_seeds.argtypes = [C.c_uint8, C.c_uint32, C.c_uint32, C.c_void_p]
         L.soup_bad_cluster_detection.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -199,6 +200,15 @@ def load_barcodes(path):
         return out
     finally:
         L.soup_free(blob)
+
+
+def known_genotypes(vcf_path, sample_names, k: int, index_to_locus) -> np.ndarray:
+    """init_cluster_centers_known_genotypes S:514-542 -> centers [k][n_loci]."""
+    i2l = np.ascontiguousarray(index_to_locus, dtype=np.uint64)
+    out = np.empty((k, i2l.shape[0]), dtype=np.float32)
+    blob = b"".join(s.encode() + b"\0" for s in sample_names) + b"\0"
+    _check(lib().soup_known_genotypes_load(os.fsencode(vcf_path), blob, len(sample_names), k, _ptr(i2l), i2l.shape[0], _ptr(out)))
+    return out
 
 
 def chacha_words(seed: bytes, n: int, word_offset: int = 0, rounds: int = 12) -> np.ndarray:
@@ -428,7 +438,7 @@ class MainResult:
 
 def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3=False, iteration_cap=0, max_slots=0,
          lanes=0, record_counts=False, verbose_trace=False, time_kernels=False, proc_rank=0, proc_world=1, allgather=None,
-         bcast=None) -> MainResult:
+         bcast=None, known_theta=None) -> MainResult:
     """souporcell_main S:60-131 over one context per GPU (restart-sharded)."""
     if isinstance(ctxs, Context):
         ctxs = [ctxs]
@@ -438,6 +448,9 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
     p.souporcell3, p.iteration_cap, p.max_slots, p.lanes = int(souporcell3), iteration_cap, max_slots, lanes
     p.record_counts, p.verbose_trace, p.time_kernels = int(record_counts), int(verbose_trace), int(time_kernels)
     p.proc_rank, p.proc_world = proc_rank, proc_world
+    if known_theta is not None:
+        kt = np.ascontiguousarray(known_theta, dtype=np.float32).reshape(k, ctxs[0].n_loci)
+        p.known_theta = _ptr(kt)
     if allgather is not None:
         p.allgather = allgather
     if bcast is not None:

@@ -165,6 +165,101 @@ int32_t soup_barcodes_load(const char* path, char** blob, uint64_t* n_barcodes) 
     return SOUP_OK;
 }
 
+// init_cluster_centers_known_genotypes S:514-542: theta[k][l] = 0.5, then for every VCF record whose index is a used
+// locus and every named sample: (min(hap0,1) + min(hap1,1)) / 2 clamped to [0.01, 0.99]; a GT starting with '.' keeps 0.5.
+int32_t soup_known_genotypes_load(const char* vcf_path, const char* sample_names, int32_t n_samples, int32_t k,
+                                  const uint64_t* index_to_locus, uint64_t n_loci, float* theta) {
+    if (!vcf_path || !theta || k <= 0 || n_samples < 0 || (n_samples && !sample_names) || (n_loci && !index_to_locus)) {
+        set_thread_error("soup_known_genotypes_load: bad argument");
+        return SOUP_ERR_INVALID;
+    }
+    if (n_samples == 0) { set_thread_error("currently requiring known_genotypes_sample_names if known_genotypes set"); return SOUP_ERR_INVALID; }   // S:537
+    if (n_samples > k) { set_thread_error("known_genotypes: more sample names than clusters (the reference indexes out of bounds)"); return SOUP_ERR_INVALID; }
+    std::vector<std::string> names;
+    for (const char* q = sample_names; (int32_t)names.size() < n_samples; q += strlen(q) + 1) names.emplace_back(q);
+    gzFile f = gzopen(vcf_path, "rb");   // plain text is read transparently; the reference's reader() keys on ".gz" (S:506)
+    if (!f) { set_thread_error("couldn't open file %s", vcf_path); return SOUP_ERR_IO; }
+    std::string text;
+    {
+        char buf[1 << 16];
+        int n;
+        while ((n = gzread(f, buf, sizeof(buf))) > 0) text.append(buf, (size_t)n);
+        gzclose(f);
+    }
+    for (size_t i = 0; i < (size_t)k * n_loci; ++i) theta[i] = 0.5f;
+    std::vector<int> sample_col(names.size(), -1);
+    uint64_t record = 0, next_used = 0;          // index_to_locus is ascending: walk it alongside the records
+    size_t pos = 0;
+    auto field = [](const std::string& line, size_t idx, size_t* b, size_t* e) {   // idx-th tab-separated field
+        size_t s0 = 0;
+        for (size_t i = 0; i < idx; ++i) {
+            size_t t = line.find('\t', s0);
+            if (t == std::string::npos) return false;
+            s0 = t + 1;
+        }
+        size_t t = line.find('\t', s0);
+        *b = s0;
+        *e = t == std::string::npos ? line.size() : t;
+        return true;
+    };
+    while (pos < text.size()) {
+        size_t e = text.find('\n', pos);
+        if (e == std::string::npos) e = text.size();
+        std::string line(text, pos, e - pos);
+        pos = e + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '#') {
+            if (line.compare(0, 6, "#CHROM") == 0) {
+                size_t b, en;
+                for (size_t c = 9; field(line, c, &b, &en); ++c)
+                    for (size_t s = 0; s < names.size(); ++s)
+                        if (line.compare(b, en - b, names[s]) == 0) sample_col[s] = (int)c;
+            }
+            continue;
+        }
+        while (next_used < n_loci && index_to_locus[next_used] < record) ++next_used;
+        if (next_used < n_loci && index_to_locus[next_used] == record) {
+            size_t fb, fe;
+            if (!field(line, 8, &fb, &fe)) { set_thread_error("known_genotypes: record %llu has no FORMAT column", (unsigned long long)record); return SOUP_ERR_INVALID; }
+            int gt_pos = -1, cur = 0;
+            for (size_t i = fb; i <= fe; ++cur) {
+                size_t c = line.find(':', i);
+                if (c == std::string::npos || c > fe) c = fe;
+                if (line.compare(i, c - i, "GT") == 0) gt_pos = cur;
+                i = c + 1;
+            }
+            for (size_t s = 0; s < names.size(); ++s) {
+                size_t b, en;
+                if (sample_col[s] < 0 || gt_pos < 0 || !field(line, (size_t)sample_col[s], &b, &en)) {
+                    set_thread_error("known_genotypes: sample %s or its GT is missing at record %llu (the reference panics on the lookup)", names[s].c_str(), (unsigned long long)record);
+                    return SOUP_ERR_INVALID;
+                }
+                size_t gb = b;
+                for (int i = 0; i < gt_pos; ++i) {
+                    size_t c = line.find(':', gb);
+                    if (c == std::string::npos || c >= en) { gb = en; break; }
+                    gb = c + 1;
+                }
+                size_t ge = line.find(':', gb);
+                if (ge == std::string::npos || ge > en) ge = en;
+                if (gb >= ge) { set_thread_error("known_genotypes: empty GT at record %llu", (unsigned long long)record); return SOUP_ERR_INVALID; }
+                if (line[gb] == '.') continue;                                             // S:532
+                auto hap = [&](size_t i, uint32_t* out) {
+                    if (gb + i >= ge || line[gb + i] < '0' || line[gb + i] > '9') return false;
+                    *out = std::min<uint32_t>((uint32_t)(line[gb + i] - '0'), 1u);        // parse::<u32>().min(1)  S:533-534
+                    return true;
+                };
+                uint32_t h0, h1;
+                if (!hap(0, &h0) || !hap(2, &h1)) { set_thread_error("known_genotypes: cannot parse GT '%s' at record %llu", line.substr(gb, ge - gb).c_str(), (unsigned long long)record); return SOUP_ERR_INVALID; }
+                theta[s * n_loci + next_used] = fmaxf(fminf((float)(h0 + h1) / 2.0f, 0.99f), 0.01f);   // S:535
+            }
+        }
+        ++record;
+    }
+    return SOUP_OK;
+}
+
 // S:133-147: zip(barcodes, best_log_probabilities), FIRST max (strict >), Rust {} floats.
 int32_t soup_write_clusters(void* out_file, const char* barcode_blob, uint64_t n_barcodes, const float* lp,
                             uint64_t n_cells, int32_t k) {

@@ -647,7 +647,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     if (p->k <= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: k must be >= 1");
     if (p->method != SOUP_METHOD_EM && p->method != SOUP_METHOD_KHM) return ctx->fail(SOUP_ERR_INVALID, "Clustering method must be one of em, khm");
     if (p->n_streams <= 0 || p->solves_per_stream <= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: n_streams and solves_per_stream must be >= 1");
-    if (!p->theta0 && !p->stream_seeds) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: need stream_seeds or theta0");
+    if (!p->theta0 && !p->stream_seeds && !p->init_theta) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: need stream_seeds, theta0 or init_theta");
     if (p->n_reinit < 0 || p->n_reinit > p->k || (p->n_reinit > 0 && (!p->reinit_clusters || !p->base_theta)))
         return ctx->fail(SOUP_ERR_INVALID, "soup_solve: bad reinit_clusters / base_theta");
     if ((uint64_t)p->n_streams * (uint64_t)p->solves_per_stream > (1u << 30)) return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: too many solves");
@@ -720,8 +720,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     }
 
     // ---- per-call device inputs
-    float *d_theta0 = nullptr, *d_base = nullptr;
-    auto cleanup = [&] { cudaFree(d_theta0); cudaFree(d_base); };
+    float *d_theta0 = nullptr, *d_base = nullptr, *d_init = nullptr;
+    auto cleanup = [&] { cudaFree(d_theta0); cudaFree(d_base); cudaFree(d_init); };
 #define CKS(call)                                                                                        \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -756,6 +756,12 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         CKS(cudaMemcpyAsync(d_base, p->base_theta, n * 4, cudaMemcpyHostToDevice, st));
         h2d += n * 4;
     }
+    if (p->init_theta) {
+        size_t n = (size_t)K * ctx->L;
+        CKS(cudaMalloc(&d_init, std::max<size_t>(n, 1) * 4));
+        CKS(cudaMemcpyAsync(d_init, p->init_theta, n * 4, cudaMemcpyHostToDevice, st));
+        h2d += n * 4;
+    }
     std::vector<uint32_t> keys((size_t)p->n_streams * 8, 0);
     if (p->stream_seeds)
         for (int t = 0; t < p->n_streams; ++t) seed_to_key(p->stream_seeds + (size_t)t * 32, keys.data() + (size_t)t * 8);
@@ -780,7 +786,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     IterLaunch it;
     it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0 && !cell_mode;
     it.allreduce = p->cell_allreduce; it.comm_user = p->comm_user;
-    it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, w.draw_of_k, w.TH, w.LA, w.LB,
+    it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, d_init, w.draw_of_k, w.TH, w.LA, w.LB,
                            (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream};
     it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write,
                           {{w.e_group_active, 32 * w.ep.VM, 32 * w.ep.VT, w.ep.n_main, w.ep.n_groups},

@@ -724,6 +724,7 @@ struct RefillArgs {
     const uint32_t* stream_keys;  // [n_streams][8] ChaCha keys of the ThreadData rngs (S:52)
     const float* theta0;          // [n_solves][K][L] or nullptr
     const float* base_theta;      // [K][L] or nullptr (S:93)
+    const float* init_theta;      // [K][L] or nullptr: deterministic initial centers (known genotypes, S:487)
     const int* draw_of_k;         // [K]: position of cluster k in this run's draw order, -1 = locked (S:92-97)
     float *TH, *LA, *LB;
     uint32_t L, Cpad;
@@ -745,6 +746,8 @@ __global__ void __launch_bounds__(256) refill_kernel(RefillArgs a) {
         th = a.theta0[((size_t)solve * a.K + k) * a.L + l];
     } else if (d < 0) {
         th = a.base_theta[(size_t)k * a.L + l];
+    } else if (a.init_theta) {
+        th = a.init_theta[(size_t)d * a.L + l];       // run 0: d == k; later runs: re-drawn cluster i takes row i (S:92-96)
     } else {
         // init_cluster_centers_uniform S:554-563: cluster-major then locus draw order, one u32 word per f32
         const int stream = solve / a.solves_per_stream, it = solve - stream * a.solves_per_stream;

@@ -125,7 +125,6 @@ int main(int argc, char** argv) {
         fprintf(stderr, "For k > 16, using souporcell3 (with '-s true' flag) is recommended with khm clustering method (with '-m khm' flag)\n");
     if (k == 0 || threads == 0) die("thread 'main' panicked: num_clusters and threads must be positive (the reference divides by them)", 101);
     // initialisation paths: S:485-498
-    if (known_gt) die("thread 'main' panicked: --known_genotypes initialisation is not built in this release (SURVEY 8f-3)", 101);
     if (known_cells) die("thread 'main' panicked: known cell assignments not yet implemented", 101);   // S:545
     if (init == "kmeans++") die("thread 'main' panicked: kmeans++ not yet implemented", 101);           // S:550
     if (init == "middle_variance") die("thread 'main' panicked: middle variance not yet implemented", 101);   // S:597
@@ -156,8 +155,21 @@ int main(int argc, char** argv) {
             die(std::string("souporcell (soupgpu): ") + soup_last_error(ctxs[g]), 101);
     }
 
+    // ---- init_cluster_centers_known_genotypes S:514-542
+    std::vector<float> known_theta;
+    if (known_gt) {
+        std::string blob;
+        int n_names = 0;
+        if (vals.count("known_genotypes_sample_names"))
+            for (const std::string& nm : vals["known_genotypes_sample_names"]) { blob += nm; blob.push_back('\0'); ++n_names; }
+        known_theta.resize((size_t)k * m->n_loci);
+        if (soup_known_genotypes_load(get("known_genotypes", "").c_str(), blob.c_str(), n_names, (int32_t)k, m->index_to_locus, m->n_loci, known_theta.data()) != SOUP_OK)
+            die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    }
+
     // ---- souporcell_main S:60-148
     soup_main_params mp{};
+    mp.known_theta = known_gt ? known_theta.data() : nullptr;
     mp.k = (int32_t)k; mp.method = method_s == "khm" ? SOUP_METHOD_KHM : SOUP_METHOD_EM;
     mp.restarts = restarts; mp.threads = (uint32_t)threads; mp.seed = seed; mp.souporcell3 = s3 ? 1 : 0;
     mp.max_slots = (int32_t)parse_num(get("max_slots", "0"), "max_slots", 1024);

@@ -411,3 +411,20 @@ def test_main_over_two_contexts_equals_one(small):
             assert np.array_equal(bits(one.best_log_probs), bits(two.best_log_probs))
             assert np.array_equal(bits(one.best_theta), bits(two.best_theta))
             assert one.nnz_updates == two.nnz_updates
+
+
+def test_cli_known_genotypes_matches_oracle_cli(tmp_path):
+    """--known_genotypes / --known_genotypes_sample_names (souporcell_pipeline.py:532-535): every restart starts from
+    the VCF-derived centers (S:487); TSV byte-identical to the oracle CLI, also under souporcell3's re-draw rule."""
+    import subprocess
+    from souporcell_b200 import build, synth
+    from test_host import write_vcf
+    v = synth.generate(n_cells=300, n_loci=1200, k=3, mean_loci=90, seed=12)
+    alt, ref, bc = synth.write_files(v, str(tmp_path))
+    vcf = str(tmp_path / "known.vcf")
+    write_vcf(vcf, 1200, ["s0", "s1", "s2"], np.random.default_rng(6))
+    args = ["-a", alt, "-r", ref, "-b", bc, "-k", "3", "--restarts", "2", "-t", "2", "-g", vcf, "--known_genotypes_sample_names", "s2", "s0", "s1"]
+    ours = subprocess.run([build.CLI] + args, capture_output=True, text=True)
+    theirs = subprocess.run([orc.CLI_PATH] + args, capture_output=True, text=True)
+    assert ours.returncode == 0 and theirs.returncode == 0, ours.stderr[-400:] + theirs.stderr[-400:]
+    assert ours.stdout == theirs.stdout and ours.stdout.count("\n") == v.n_cells

@@ -174,3 +174,46 @@ def test_cli_contract_without_gpu(tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run(base, capture_output=True, text=True)
         assert r.returncode != 0 and r.stdout == "" and "total loci used 3" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def write_vcf(path, n_records, samples, rng, gz=False):
+    gts = ["0/0", "0/1", "1/1", "0|1", "1|0", "./.", "1/2", "2/2", ".|."]
+    lines = ["##fileformat=VCFv4.2", "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">",
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples)]
+    for i in range(n_records):
+        fmt = "GT:DP" if i % 3 else "DP:GT"                       # GT is looked up by key, not by position
+        cols = []
+        for _ in samples:
+            gt = gts[rng.integers(0, len(gts))]
+            cols.append(f"{gt}:7" if i % 3 else f"7:{gt}")
+        lines.append(f"chr1\t{100 + i}\t.\tA\tC,G\t50\tPASS\t.\t{fmt}\t" + "\t".join(cols))
+    data = "\n".join(lines) + "\n"
+    if gz:
+        with gzip.open(path, "wt") as fh:
+            fh.write(data)
+    else:
+        open(path, "w").write(data)
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_known_genotypes_init_matches_oracle(tmp_path, gz):
+    """init_cluster_centers_known_genotypes S:514-542: record i <-> original locus i, named sample s -> cluster s,
+    (min(hap0,1)+min(hap1,1))/2 clamped to [.01,.99], '.' keeps 0.5, clusters without a sample stay 0.5."""
+    v = synth.generate(n_cells=120, n_loci=400, k=3, mean_loci=60, seed=4)
+    alt, ref, _ = synth.write_files(v, str(tmp_path))
+    m = sp.load_mtx(alt, ref)
+    od = orc.OracleData.from_mtx(alt, ref)
+    vcf = str(tmp_path / ("known.vcf.gz" if gz else "known.vcf"))
+    samples = ["donorB", "donorA", "donorC"]
+    write_vcf(vcf, 400, samples, np.random.default_rng(5), gz)
+    for names, k in ((["donorA", "donorC"], 4), (samples, 3)):
+        got = sp.known_genotypes(vcf, names, k, m.index_to_locus)
+        want = od.known_genotypes(vcf, names, k)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert set(np.unique(got)) <= {np.float32(0.01), np.float32(0.5), np.float32(0.99)}
+        assert np.all(got[len(names):] == np.float32(0.5))
+    for bad_names, k in ((["nobody"], 3), ([], 3), (samples, 2)):
+        with pytest.raises(sp.SoupError):
+            sp.known_genotypes(vcf, bad_names, k, m.index_to_locus)
+    with pytest.raises(sp.SoupError):
+        sp.known_genotypes(str(tmp_path / "missing.vcf"), samples, 3, m.index_to_locus)
