@@ -14,6 +14,9 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+#include <future>
+
 #include <cuda_runtime_api.h>
 
 #include "soup_common.hpp"
@@ -70,9 +73,20 @@ uint64_t parse_num(const std::string& s, const char* what, uint64_t maxv) {
     return v;
 }
 
+struct Stopwatch {
+    bool on = getenv("SOUP_DEBUG_ITERS") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        auto t1 = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "soup_debug cli %-24s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 }  // namespace
 
 int main(int argc, char** argv) {
+    Stopwatch sw;
     std::map<std::string, std::vector<std::string>> vals;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -130,6 +144,15 @@ int main(int argc, char** argv) {
     if (init == "middle_variance") die("thread 'main' panicked: middle variance not yet implemented", 101);   // S:597
     if (init == "random_cell_assignment") die("thread 'main' panicked: random_cell_assignment initialisation is not built in this release (SURVEY 8f-3)", 101);
 
+    // The CUDA driver context takes a few hundred ms to come up: start it now, in the background, while the text
+    // matrices are parsed on the CPU.
+    std::future<int> cuda_up = std::async(std::launch::async, [] {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+        for (int g = 0; g < n; ++g) { cudaSetDevice(g); cudaFree(nullptr); }
+        return n;
+    });
+
     // ---- load_barcodes S:707-718, load_cell_data S:601-681
     char* bc_blob = nullptr;
     uint64_t n_bc = 0;
@@ -140,10 +163,12 @@ int main(int argc, char** argv) {
     if (soup_mtx_load(alt_mtx.c_str(), ref_mtx.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, &m) != SOUP_OK)
         die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
     fprintf(stderr, "total loci used %llu\n", (unsigned long long)m->n_loci);   // S:678
+    sw.lap("parse mtx + barcodes");
 
     // ---- GPUs
-    int visible = 0;
-    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) die("souporcell (soupgpu): no CUDA device available; this build has no CPU fallback", 101);
+    int visible = cuda_up.get();
+    sw.lap("wait for CUDA context");
+    if (visible == 0) die("souporcell (soupgpu): no CUDA device available; this build has no CPU fallback", 101);
     int n_gpu = vals.count("gpus") ? (int)parse_num(get("gpus", "1"), "gpus", 1024) : visible;
     if (n_gpu < 1 || n_gpu > visible) die("souporcell (soupgpu): --gpus out of range", 1);
     const uint64_t spt = (restarts + threads - 1) / threads;
@@ -155,6 +180,7 @@ int main(int argc, char** argv) {
             die(std::string("souporcell (soupgpu): ") + soup_last_error(ctxs[g]), 101);
     }
 
+    sw.lap("upload + GPU transpose");
     // ---- init_cluster_centers_known_genotypes S:514-542
     std::vector<float> known_theta;
     if (known_gt) {
@@ -179,11 +205,13 @@ int main(int argc, char** argv) {
     soup_main_result res{};
     res.best_log_probs = best_lp.data();
     if (soup_main(ctxs.data(), n_gpu, &mp, &res, stderr) != SOUP_OK) die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    sw.lap("soup_main");
     fprintf(stderr, "soupgpu\tgpus\t%d\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, res.solve_ms, (unsigned long long)res.nnz_updates);
     // zip(barcodes, best_log_probabilities): an empty best (nothing beat -inf) prints nothing (S:133)
     if (res.has_best && soup_write_clusters(stdout, bc_blob, n_bc, best_lp.data(), m->n_cells, (int32_t)k) != SOUP_OK)
         die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
     if (fflush(stdout) != 0) die("thread 'main' panicked: failed printing to stdout", 101);
+    sw.lap("write TSV");
     for (soup_ctx* c : ctxs) soup_ctx_destroy(c);
     soup_mtx_free(m);
     soup_free(bc_blob);

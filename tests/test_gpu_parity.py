@@ -428,3 +428,28 @@ def test_cli_known_genotypes_matches_oracle_cli(tmp_path):
     theirs = subprocess.run([orc.CLI_PATH] + args, capture_output=True, text=True)
     assert ours.returncode == 0 and theirs.returncode == 0, ours.stderr[-400:] + theirs.stderr[-400:]
     assert ours.stdout == theirs.stdout and ours.stdout.count("\n") == v.n_cells
+
+
+@pytest.mark.parametrize("k,n_solves,slots", [(5, 30, 0), (7, 20, 13), (64, 3, 0), (33, 9, 4), (2, 70, 0)])
+def test_many_columns_straddling_groups(k, n_solves, slots):
+    """Column counts that are not multiples of the 256 / 64 / 32-column group widths (slots straddle groups, narrow last
+    groups, several wide groups) with refills and tail compaction: every solve bit-identical to the oracle."""
+    v, csr = synth_csr(n_cells=220, n_loci=1400, k=4, mean_loci=80, seed=29)
+    od = orc.OracleData.from_csr(*csr)
+    theta0 = random_theta(np.random.default_rng(k), (n_solves, k, csr[1]))
+    os_env = __import__("os").environ
+    os_env["SOUP_LONG_THRESHOLD"] = "40"
+    try:
+        ctx = sp.Context(0).load_csr(*csr)
+    finally:
+        os_env.pop("SOUP_LONG_THRESHOLD", None)
+    with ctx:
+        res = ctx.solve(k, method=sp.METHOD_KHM if k % 2 else sp.METHOD_EM, n_streams=n_solves, solves_per_stream=1, theta0=theta0, max_slots=slots)
+        check = range(n_solves) if n_solves <= 10 else list(range(0, n_solves, 7)) + [n_solves - 1]
+        for s in check:
+            want = od.solve(theta0[s], method=1 if k % 2 else 0)
+            assert res.solve_iters[s] == want["iterations"] and bits(res.solve_loss[s:s + 1])[0] == bits([want["loss"]])[0], s
+        b = res.best_solve
+        want = od.solve(theta0[b], method=1 if k % 2 else 0)
+        assert np.array_equal(bits(res.best_log_probs), bits(want["log_probs"])) and np.array_equal(bits(res.best_theta), bits(want["theta"]))
+        assert res.best_loss == np.nanmax(res.solve_loss)
