@@ -73,39 +73,63 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled in-process
+    (a sampling thread, 4 Hz): spawning `nvidia-smi -lms 200` measurably stalls kernel launches on multi-GPU boxes,
+    which would perturb the very number it is there to vouch for.  Falls back to nvidia-smi when pynvml is missing."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.max_mhz, self.reasons, self._stop, self._thr, self.proc = index, [], None, set(), False, None, None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        get = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+                        mask = int(get(h))
+                        for bit, name in self.REASONS.items():
+                            if mask & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.25)
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
         except Exception:
-            self.proc = None
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.hw_thermal_slowdown"
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "500"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                threading.Thread(target=self._read, daemon=True).start()
+            except Exception:
+                self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+            r = [t.strip() for t in line.split(",")]
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                self.sm.append(float(r[0])); self.max_mhz = float(r[1])
             except Exception:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            for name, val in zip(("sw_power_cap", "hw_slowdown", "sw_thermal_slowdown", "hw_thermal_slowdown"), r[2:6]):
                 if val.lower().startswith("active"):
-                    reasons.add(name)
-        busy = [x for x in sm if mx and x > 0.3 * mx] or sm
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "samples": 0}
+        busy = [x for x in self.sm if self.max_mhz and x > 0.3 * self.max_mhz] or self.sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ---------------------------------------------------------------------------------- reference arm (CPU oracle)
