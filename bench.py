@@ -257,7 +257,7 @@ def ours(args):
     dev_ms = wall_ms = updates = launches = 0.0
     for _ in range(args.steps):
         r, ms_d, ms_w = timed(job)
-        if os.environ.get("SOUP_DEBUG_ITERS"):
+        if os.environ.get("SOUP_BENCH_VERBOSE"):
             print(f"bench value step: wall {ms_w:.2f} ms device {ms_d:.2f} ms solve {r.solve_ms:.2f} ms", file=sys.stderr)
         dev_ms += ms_d; wall_ms += ms_w
         updates += total(r.nnz_updates); launches += total(r.kernel_launches)
@@ -285,7 +285,7 @@ def ours(args):
     e_ms = e_upd = 0.0
     for _ in range(args.steps):
         r, ms_d, ms_w = timed(e2e_job)
-        if os.environ.get("SOUP_DEBUG_ITERS"):
+        if os.environ.get("SOUP_BENCH_VERBOSE"):
             print(f"bench e2e step: wall {ms_w:.2f} ms device {ms_d:.2f} ms", file=sys.stderr)
         e_ms += ms_w; e_upd += total(r.nnz_updates)       # wall clock: includes host-side packing and copies
     h2d = (n + 1) * 8 + nnz * 12 + restarts // world * 32

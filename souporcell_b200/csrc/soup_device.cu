@@ -233,8 +233,16 @@ extern "C" void soup_ctx_destroy(soup_ctx* ctx) {
 #include <chrono>
 struct PhaseTimer {
     bool on = getenv("SOUP_DEBUG_ITERS") != nullptr;
+    bool slow_only = getenv("SOUP_DEBUG_SLOW") != nullptr;   // no extra syncs; report only phases above 5 ms
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     void lap(const char* what) {
+        if (slow_only) {
+            auto t1 = std::chrono::steady_clock::now();
+            double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+            if (ms > 5.0 && strncmp(what, "solve: iterate", 14) != 0) fprintf(stderr, "soup_slow phase %-28s %.3f ms\n", what, ms);
+            t0 = t1;
+            return;
+        }
         if (!on) return;
         cudaDeviceSynchronize();
         auto t1 = std::chrono::steady_clock::now();
@@ -794,6 +802,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
                            {w.l_group_active, 32 * w.lp.VM, 32 * w.lp.VT, w.lp.n_main, w.lp.n_groups}},
                           K, slots, iter_cap, w.Cpad, limit, w.moves, getenv("SOUP_NO_COMPACT") ? 0 : 1};
 
+    pt.lap("solve: setup uploads");
     CKS(cudaEventRecord(ctx->ev0, st));
     launch_refill(ctx, it.refill);
     finalize_kernel<<<1, 1024, 0, st>>>(it.fin);
@@ -802,7 +811,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
 
     // ---- iterate: chunk i+1 is enqueued before the host waits for chunk i's done counter, so the
     // GPU never idles on the poll; kernels of chunks past the end find no active slot and exit.
-    const int chunk = p->poll_chunk > 0 ? p->poll_chunk : 4;
+    int chunk = p->poll_chunk > 0 ? p->poll_chunk : 4;
+    if (const char* e = getenv("SOUP_POLL_CHUNK")) chunk = std::max(1, atoi(e));   // tuning knob
     uint64_t iters_enqueued = 0;
     int polls = 0;
     const size_t max_timed = 4096;

@@ -1,7 +1,9 @@
 // soup_main: souporcell_main (/root/reference/souporcell/src/main.rs:60-131, "S:") on top of
 // soup_solve.  Host-only logic: seed fan-out, the souporcell3 three-run loop, bad-cluster
 // detection, best-of bookkeeping, restart sharding over contexts (GPUs) and processes.
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -143,11 +145,16 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             c.rc = soup_solve(ctxs[i], &sp, &c.res);
             if (c.rc == SOUP_OK) soup_get_stats(ctxs[i], &c.stats);
         };
+        const auto tw0 = std::chrono::steady_clock::now();
         if (n_ctx == 1) work(0);
         else {
             std::vector<std::thread> pool;
             for (int i = 0; i < n_ctx; ++i) pool.emplace_back(work, i);
             for (auto& t : pool) t.join();
+        }
+        if (getenv("SOUP_DEBUG_SLOW")) {
+            double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+            if (ms > 50) fprintf(stderr, "soup_slow soup_main: solve call took %.1f ms\n", ms);
         }
         double run_ms = 0;
         std::vector<float> loss(n_solves, NAN);
