@@ -256,8 +256,8 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     if (!ctx) return SOUP_ERR_INVALID;
     PhaseTimer pt;
     if (!row_ptr || (nnz_in && (!locus || !alt || !ref))) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: null pointer");
-    if (n_cells >= (1u << 30) || n_loci >= (1u << 30) || nnz_in >= INT32_MAX)
-        return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_load_csr: more than 2^30 cells / loci or 2^31 entries are not supported");
+    if (n_cells >= (1u << 29) || n_loci >= (1u << 29) || nnz_in >= INT32_MAX)
+        return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_load_csr: more than 2^29 cells / loci or 2^31 entries are not supported");
     if (row_ptr[0] != 0 || row_ptr[n_cells] != nnz_in) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: row_ptr does not span [0, nnz]");
     for (uint64_t c = 0; c < n_cells; ++c)
         if (row_ptr[c + 1] < row_ptr[c]) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: row_ptr not monotone at cell %llu", (unsigned long long)c);
@@ -313,20 +313,23 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     }
     pt.lap("load: h2d + validate");
     ctx->N = n_cells; ctx->L = n_loci; ctx->nnz = nnz;
-    // packed entry words: index bits as needed, the rest split between the two count fields (<= 6 bits each)
+    // entry words (soup_kernels.cuh "entry words"): bit 31 = general; index bits as needed, the rest split between
+    // the two count fields (<= 6 bits each)
     auto make_packing = [](uint64_t n_index) {
         uint32_t ib = 1;
         while ((1ull << ib) < std::max<uint64_t>(n_index, 2)) ++ib;
         Packing pk;
-        pk.cbits = std::min<uint32_t>(6, (32 - ib) / 2);
+        pk.cbits = std::min<uint32_t>(6, (31 - ib) / 2);
         pk.cmask = (1u << pk.cbits) - 1;
-        pk.sh_a = 32 - pk.cbits;
-        pk.sh_r = 32 - 2 * pk.cbits;
+        pk.sh_a = 31 - pk.cbits;
+        pk.sh_r = 31 - 2 * pk.cbits;
         pk.imask = (1u << pk.sh_r) - 1;
+        pk.plane_rows = 0;
+        pk.alt_bit = 1u << pk.sh_a;
         return pk;
     };
-    const Packing pk_csr = make_packing(n_loci);
-    ctx->pk_csr = pk_csr;
+    ctx->pk_csr = make_packing(n_loci);
+    ctx->pk_csr.plane_rows = (uint32_t)std::max<uint64_t>(n_loci, 1);   // = the row count ensure_workspace gives each ln-table plane
     ctx->pk_csc = make_packing(n_cells);
     const size_t nz = std::max<uint64_t>(nnz, 1);
     const size_t nmax = std::max<uint64_t>(std::max(n_cells, n_loci), 1);
@@ -504,7 +507,8 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     const size_t L = std::max<uint64_t>(ctx->L, 1), N = std::max<uint64_t>(ctx->N, 1);
     cudaError_t e = cudaSuccess;
     auto A = [&](auto** p, size_t n, bool zero) { if (e == cudaSuccess) e = ws_alloc(w, ctx->stream, p, n, zero); };
-    A(&w.LA, L * w.Cpad, true); A(&w.LB, L * w.Cpad, true); A(&w.TH, L * w.Cpad, true);
+    A(&w.LA, 2 * L * w.Cpad, true); A(&w.TH, L * w.Cpad, true);   // LA | LB: one joint table (a simple CSR word is a row of it)
+    if (e == cudaSuccess) w.LB = w.LA + L * w.Cpad;
     A(&w.ELL, N * w.Cpad, true); A(&w.W, N * w.Cpad, true); A(&w.LSE, N * slots, true);
     A(&w.st, (size_t)slots, true); A(&w.ctl, 1, true); A(&w.loss, (size_t)slots, true);
     A(&w.col_write, w.Cpad, true); A(&w.k_locked, (size_t)K, true);
@@ -542,23 +546,15 @@ struct IterLaunch {
     FinalizeArgs fin;
 };
 
-#define SOUP_DISPATCH(KERNEL, PLAN, ARGS)                                                                    \
-    do {                                                                                                     \
-        const int vm_ = (PLAN).VM, vt_ = (PLAN).VT;                                                          \
-        if (vm_ == 16 && vt_ == 16) KERNEL<16, 16><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);              \
-        else if (vm_ == 16 && vt_ == 8) KERNEL<16, 8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);           \
-        else if (vm_ == 16 && vt_ == 4) KERNEL<16, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);           \
-        else if (vm_ == 16 && vt_ == 2) KERNEL<16, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);           \
-        else if (vm_ == 16 && vt_ == 1) KERNEL<16, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);           \
-        else if (vm_ == 8 && vt_ == 8) KERNEL<8, 8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                  \
-        else if (vm_ == 8 && vt_ == 4) KERNEL<8, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
-        else if (vm_ == 8 && vt_ == 2) KERNEL<8, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
-        else if (vm_ == 8 && vt_ == 1) KERNEL<8, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
-        else if (vm_ == 4 && vt_ == 4) KERNEL<4, 4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
-        else if (vm_ == 4 && vt_ == 2) KERNEL<4, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
-        else if (vm_ == 4 && vt_ == 1) KERNEL<4, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);             \
-        else if (vm_ == 2) KERNEL<2, 2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                         \
-        else KERNEL<1, 1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS);                                       \
+#define SOUP_DISPATCH(KERNEL, PLAN, ARGS)                                                       \
+    do {                                                                                        \
+        switch ((PLAN).VM) {                                                                    \
+            case 16: KERNEL<16><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;             \
+            case 8: KERNEL<8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;               \
+            case 4: KERNEL<4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;               \
+            case 2: KERNEL<2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;               \
+            default: KERNEL<1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;              \
+        }                                                                                       \
     } while (0)
 
 static void launch_e(soup_ctx* ctx, float log_prior) {
@@ -566,7 +562,7 @@ static void launch_e(soup_ctx* ctx, float log_prior) {
     const uint32_t bpg = (uint32_t)((ctx->N + EM_WARPS - 1) / EM_WARPS);
     if (bpg == 0) return;
     const EArgs a{ctx->d_csr_idx, ctx->d_csr_aux, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB, w.ELL, w.e_group_active, w.ctl,
-                  ctx->pk_csr, (uint32_t)ctx->N, w.Cpad, bpg, (uint32_t)w.ep.n_main, log_prior};
+                  ctx->pk_csr, (uint32_t)ctx->N, w.Cpad, bpg, (uint32_t)(w.forced_lanes != 0), log_prior};
     const dim3 grid(bpg * w.ep.n_groups);
     SOUP_DISPATCH(estep_kernel, w.ep, a);
 }
@@ -578,9 +574,9 @@ static void launch_m(soup_ctx* ctx) {
     const uint32_t long_blocks = (long_items + EM_WARPS - 1) / EM_WARPS;
     const uint32_t wide_chunks = (uint32_t)((ctx->L - n_long + EM_WARPS - 1) / EM_WARPS);
     const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
-                  w.m_group_active, w.l_group_active, w.ctl, w.stats, w.stats ? w.stats + (size_t)ctx->L * w.Cpad : nullptr, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups, (uint32_t)w.mp.n_main,
+                  w.m_group_active, w.l_group_active, w.ctl, w.stats, w.stats ? w.stats + (size_t)ctx->L * w.Cpad : nullptr, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups,
                   n_long, (uint32_t)w.lp.n_groups, long_blocks, wide_chunks,
-                  (uint32_t)((uint64_t)ctx->N * w.Cpad * 4 > (48ull << 20))};
+                  (uint32_t)((uint64_t)ctx->N * w.Cpad * 4 > (48ull << 20)), (uint32_t)(w.forced_lanes != 0)};
     const dim3 grid(long_blocks + wide_chunks * w.mp.n_groups);
     if (grid.x == 0) return;
     SOUP_DISPATCH(mstep_kernel, w.mp, a);
@@ -950,7 +946,7 @@ static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
     cudaMemcpyAsync(w.e_group_active, ga.data(), (size_t)w.ep.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(w.m_group_active, ga.data(), (size_t)w.mp.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);
     Ctl hc{};
-    hc.copy_slot = -1; hc.best_solve = -1; hc.best_loss = -INFINITY;
+    hc.copy_slot = -1; hc.best_solve = -1; hc.best_loss = -INFINITY; hc.live_cols = (uint32_t)(n_slots * k);
     cudaMemcpyAsync(w.ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     return SOUP_OK;
@@ -1051,7 +1047,7 @@ extern "C" int32_t soup_mstep(soup_ctx* ctx, int32_t k, int32_t n_slots, int32_t
     if (nw) host_to_plane_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(d_w, w.W, (uint32_t)ctx->N, w.Cpad, k, n_slots);
     // arbitrary caller weights may be non-finite: use the literal (no-shortcut) path
     Ctl hc{};
-    hc.copy_slot = -1; hc.nonfinite = 1; hc.best_loss = -INFINITY;
+    hc.copy_slot = -1; hc.nonfinite = 1; hc.best_loss = -INFINITY; hc.live_cols = (uint32_t)(n_slots * k);
     CKH(cudaMemcpyAsync(w.ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, st));
     launch_m(ctx);
     CKH(cudaGetLastError());

@@ -21,14 +21,22 @@
 
 namespace soup {
 
-#ifndef SOUP_E_U
-#define SOUP_E_U 4       // entries (row gathers) in flight per warp in the E walk
+// entries (row gathers) in flight per warp in the E walk, by columns per lane: a narrow body runs when few solves are
+// still live, and then the walk is a latency chain per warp, so narrow bodies go deeper
+#ifndef SOUP_E_U1
+#define SOUP_E_U1 16
+#endif
+#ifndef SOUP_E_U2
+#define SOUP_E_U2 8
+#endif
+#ifndef SOUP_E_U4
+#define SOUP_E_U4 6
 #endif
 #ifndef SOUP_E_U8
-#define SOUP_E_U8 2      // ... at 8 columns per lane
+#define SOUP_E_U8 3
 #endif
 #ifndef SOUP_E_U16
-#define SOUP_E_U16 2     // ... at 12 / 16 columns per lane
+#define SOUP_E_U16 2
 #endif
 #ifndef SOUP_M_U8
 #define SOUP_M_U8 4
@@ -42,8 +50,8 @@ namespace soup {
 #ifndef SOUP_M_ULONG
 #define SOUP_M_ULONG 16  // row gathers in flight per warp in the long role
 #endif
-#ifndef SOUP_M_DEEP
-#define SOUP_M_DEEP 0    // 1: ping-pong register tiles in the long role (measured slower); 0: single tile of SOUP_M_ULONG rows
+#ifndef SOUP_M_LONG_SHORTCUT
+#define SOUP_M_LONG_SHORTCUT 0   // 1: the long role also takes the single-UMI shortcuts (sign test + predicated adds)
 #endif
 #ifndef SOUP_E_VMAX
 #define SOUP_E_VMAX 8    // widest E-pass column group, in columns per lane
@@ -57,10 +65,16 @@ namespace soup {
 #ifndef SOUP_M_U
 #define SOUP_M_U 8
 #endif
+#ifndef SOUP_M_U2
+#define SOUP_M_U2 8   // 1 / 2 columns per lane (few live solves: a latency chain per warp)
+#endif
 #ifndef SOUP_M_MINB
 #define SOUP_M_MINB 3
 #endif
-constexpr int EM_THREADS = 256;            // 8 warps per CTA in the E / M kernels
+#ifndef SOUP_EM_THREADS
+#define SOUP_EM_THREADS 256
+#endif
+constexpr int EM_THREADS = SOUP_EM_THREADS;   // threads per CTA in the E / M kernels (one warp per row)
 constexpr int EM_WARPS = EM_THREADS / 32;
 constexpr int TEMP_STEPS = 9;              // S:215
 
@@ -87,6 +101,7 @@ struct Ctl {
     int nonfinite;      // a ln-table holds a non-finite value: exact zero-count shortcuts are off
     int n_active;
     int n_moves;        // slot migrations decided by finalize_kernel for migrate_kernel (tail compaction)
+    uint32_t live_cols; // columns [0, live_cols) hold every active slot: (highest active slot + 1) * K
     unsigned long long slot_iterations;
 };
 
@@ -96,33 +111,58 @@ struct IterRec { int temp_step; float loss; float change; int above; };
 // V = columns per lane.  V <= 4: one vector load per row, lane l owns columns [l*V, l*V+V) of its group.
 // V = 4*H (8, 12, 16): the group is H adjacent 128-column sub-blocks and lane l owns columns
 // [h*128 + 4*l, +4) of every sub-block, so each of the H loads is one fully coalesced 512-byte row piece.
+//
+// Live columns.  The resident solves occupy a PREFIX of the columns (Ctl::live_cols, kept by finalize_kernel's
+// compaction); a group picks the narrowest body that covers its live columns at run time, and inside the body
+//   * a lane whose first column is dead re-reads the group's first column (the same sectors lane 0 fetches: no
+//     extra traffic, no predicate in the loop) and stores nothing,
+//   * sub-blocks h >= 1 are loaded under a loop-invariant per-lane predicate (bit h of `hm`).
+// Dead lanes compute on whatever their registers hold; lanes never exchange data, so this cannot reach a result.
 template <int V> struct FVec { float v[V]; };
 template <int V> __device__ __forceinline__ constexpr uint32_t lane_cols() { return V < 4 ? V : 4; }
-template <int V> __device__ __forceinline__ FVec<V> ld_row(const float* p) {
+template <int V> __device__ __forceinline__ void ld_row(FVec<V>& r, const float* p, uint32_t hm) {
     static_assert(V % 4 == 0, "wide rows are multiples of 4 columns per lane");
-    FVec<V> r;
 #pragma unroll
     for (int h = 0; h < V / 4; ++h) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p + h * 128));
-        r.v[4 * h] = t.x; r.v[4 * h + 1] = t.y; r.v[4 * h + 2] = t.z; r.v[4 * h + 3] = t.w;
+        if (h == 0 || ((hm >> h) & 1u)) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p + h * 128));
+            r.v[4 * h] = t.x; r.v[4 * h + 1] = t.y; r.v[4 * h + 2] = t.z; r.v[4 * h + 3] = t.w;
+        }
     }
-    return r;
 }
-template <> __device__ __forceinline__ FVec<1> ld_row<1>(const float* p) { FVec<1> r; r.v[0] = __ldg(p); return r; }
-template <> __device__ __forceinline__ FVec<2> ld_row<2>(const float* p) {
-    float2 t = __ldg(reinterpret_cast<const float2*>(p)); FVec<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
+template <> __device__ __forceinline__ void ld_row<1>(FVec<1>& r, const float* p, uint32_t) { r.v[0] = __ldg(p); }
+template <> __device__ __forceinline__ void ld_row<2>(FVec<2>& r, const float* p, uint32_t) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p)); r.v[0] = t.x; r.v[1] = t.y;
 }
-template <int V> __device__ __forceinline__ void st_row(float* p, const FVec<V>& x) {
+template <int V> __device__ __forceinline__ void st_row(float* p, const FVec<V>& x, uint32_t hm) {
     static_assert(V % 4 == 0, "wide rows are multiples of 4 columns per lane");
 #pragma unroll
     for (int h = 0; h < V / 4; ++h)
-        *reinterpret_cast<float4*>(p + h * 128) = make_float4(x.v[4 * h], x.v[4 * h + 1], x.v[4 * h + 2], x.v[4 * h + 3]);
+        if (h == 0 || ((hm >> h) & 1u))
+            *reinterpret_cast<float4*>(p + h * 128) = make_float4(x.v[4 * h], x.v[4 * h + 1], x.v[4 * h + 2], x.v[4 * h + 3]);
 }
-template <> __device__ __forceinline__ void st_row<1>(float* p, const FVec<1>& x) { *p = x.v[0]; }
-template <> __device__ __forceinline__ void st_row<2>(float* p, const FVec<2>& x) { *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]); }
+template <> __device__ __forceinline__ void st_row<1>(float* p, const FVec<1>& x, uint32_t) { *p = x.v[0]; }
+template <> __device__ __forceinline__ void st_row<2>(float* p, const FVec<2>& x, uint32_t) { *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]); }
 // global column of slot v of lane `lane` in a group starting at col0
 template <int V> __device__ __forceinline__ uint32_t col_of(uint32_t col0, uint32_t lane, int v) {
     return V < 4 ? col0 + lane * V + v : col0 + (v >> 2) * 128 + lane * 4 + (v & 3);
+}
+template <int V> struct LaneCols {
+    uint32_t col;    // first column this lane reads (redirected to the group's first column when the lane is dead)
+    uint32_t hm;     // bit h (h >= 1): sub-block h of this lane holds live columns
+    bool live;       // the lane's first sub-block holds live columns
+};
+template <int V> __device__ __forceinline__ LaneCols<V> lane_setup(uint32_t col0, uint32_t live_cols) {
+    const uint32_t lane = threadIdx.x & 31;
+    LaneCols<V> lc;
+    lc.col = col0 + lane * lane_cols<V>();
+    lc.live = lc.col < live_cols;
+    lc.hm = 0;
+#pragma unroll
+    for (int h = 1; h < V / 4; ++h)
+        if (lc.col + h * 128 < live_cols) lc.hm |= 1u << h;
+    if (!lc.live) lc.col = col0;
+    return lc;
 }
 
 // base + row * row_bytes in ONE instruction (IMAD.WIDE.U32); the compiler otherwise widens the
@@ -133,77 +173,198 @@ __device__ __forceinline__ const float* row_at(const float* base, uint32_t row, 
     return r;
 }
 
+// Packed f32x2 addition (sm_100: FADD2): each half is the same IEEE round-to-nearest operation as the
+// scalar instruction (checked bit for bit on random patterns, profiles/probes/f32x2_probe.cu); the FP32 lanes run
+// at the same rate, but one instruction carries two columns, which frees issue slots for the address / decode work.
+#ifndef SOUP_PACKED_FP
+#define SOUP_PACKED_FP 1
+#endif
+__device__ __forceinline__ void add2(float& x0, float& x1, float a0, float a1) {
+#if SOUP_PACKED_FP
+    uint64_t x, a;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(a));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+#else
+    x0 = __fadd_rn(x0, a0); x1 = __fadd_rn(x1, a1);
+#endif
+}
+// acc += t
+template <int V> __device__ __forceinline__ void vadd(FVec<V>& acc, const FVec<V>& t) {
+    if constexpr (V == 1) acc.v[0] = __fadd_rn(acc.v[0], t.v[0]);
+    else {
+#pragma unroll
+        for (int v = 0; v + 1 < V; v += 2) add2(acc.v[v], acc.v[v + 1], t.v[v], t.v[v + 1]);
+    }
+}
+// r = t * c and r = t + c (c the same for every column): scalar on purpose — ptxas contracts a packed multiply that
+// feeds a packed add into FFMA2 even with explicit .rn and -fmad=false, which would change the rounding
+template <int V> __device__ __forceinline__ FVec<V> vscale(const FVec<V>& t, float c) {
+    FVec<V> r;
+#pragma unroll
+    for (int v = 0; v < V; ++v) r.v[v] = __fmul_rn(t.v[v], c);
+    return r;
+}
+template <int V> __device__ __forceinline__ FVec<V> vshift(const FVec<V>& t, float c) {
+    FVec<V> r = t;
+    if constexpr (V == 1) r.v[0] = __fadd_rn(c, r.v[0]);
+    else {
+#pragma unroll
+        for (int v = 0; v + 1 < V; v += 2) add2(r.v[v], r.v[v + 1], c, c);
+    }
+    return r;
+}
+
+// r = t + t  (== 2*t exactly)
+template <int V> __device__ __forceinline__ FVec<V> vdouble(const FVec<V>& t) {
+    FVec<V> r = t;
+    vadd<V>(r, t);
+    return r;
+}
+// r = c * t for a small count c: 1 and 2 need no multiply (1*t == t, 2*t == t+t, both exact)
+template <int V> __device__ __forceinline__ FVec<V> vcount(const FVec<V>& t, uint32_t ci, float c) {
+    if (ci == 1) return t;
+    if (ci == 2) return vdouble<V>(t);
+    return vscale<V>(t, c);
+}
+
+// ------------------------------------------------------------------ entry words
+// ONE 32-bit word per stored entry.  70 % of vartrix entries are single-UMI (alt + ref == 1), so those get the
+// cheapest possible form — bit 31 clear and the word is directly usable as an index:
+//   CSR stream (E pass): word = row of the joint ln table [ln th rows | ln(1-th) rows] this entry adds,
+//                        i.e. locus (alt == 1) or plane_rows + locus (ref == 1);
+//   CSC stream (M pass): word = cell | 1 << sh_r | alt << sh_a (the general layout with bit 31 clear).
+// Every other entry has bit 31 set:  1 | c0 << sh_a | c1 << sh_r | index  with (c0, c1) = (alt, ref) in the CSR
+// stream and (alt, alt+ref) in the CSC stream; counts that do not fit their field set both fields to the all-ones
+// marker and live in a side record (float4 {alt, ref, lbc, 0} / float2 {alt, alt+ref}).
+struct Packing {
+    uint32_t sh_a, sh_r;   // shifts of the two count fields of a general word
+    uint32_t cmask;        // (1 << count_bits) - 1: field mask and overflow marker
+    uint32_t imask;        // index mask (general CSR words, and every CSC word)
+    uint32_t cbits;
+    uint32_t plane_rows;   // CSR stream: rows of one ln-table plane (max(L, 1))
+    uint32_t alt_bit;      // CSC stream: 1 << sh_a, the alt bit of a simple word
+};
+__device__ __forceinline__ bool word_simple(uint32_t w) { return (int32_t)w >= 0; }
+
+__constant__ float c_lbc[4096];   // ln_binomial(alt + ref, alt) as f32 for in-field counts, index alt << 6 | ref (same for every context)
+
 // ------------------------------------------------------------------ E pass  (S:409-426)
 // acc_k = ln(1/K); for each entry j (ascending locus): acc_k += (lbc_j + alt_j*ln th) + ref_j*ln(1-th).
-//
-// Entry stream: ONE 32-bit word per stored entry,  alt << sh_a | ref << sh_r | locus  (Packing below);
-// counts that do not fit their field set both fields to the all-ones marker and live in a float4 side
-// record {alt, ref, lbc, 0}.  ln_binomial of in-field counts comes from a constant-memory table.
-// 70 % of vartrix entries are single-UMI, so the common case is: one word, one row gather, V adds.
 // Exact shortcuts, all bit-identical to the literal expression:
 //   alt 1, ref 0 : acc += ln th          (1*x == x, lbc == +0, 0 + x == x, and "+ 0*ln(1-th)" adds -0.0)
-//   alt 0, ref 1 : acc += ln(1-th)
+//   alt 0, ref 1 : acc += ln(1-th)         -> both are "simple" words: one row gather, V adds
 //   ref 0        : acc += lbc + alt*ln th
 //   alt 0        : acc += lbc + ref*ln(1-th)
 // Dropping a zero-count product is valid only while every table value is finite (0*inf = NaN), so
 // Ctl::nonfinite switches every entry to the literal expression.
-struct Packing {
-    uint32_t sh_a, sh_r;   // shifts of the two count fields
-    uint32_t cmask;        // (1 << count_bits) - 1: field mask and overflow marker
-    uint32_t imask;        // row-index mask (locus in the CSR stream, cell in the CSC stream)
-    uint32_t cbits;
-};
-__constant__ float c_lbc[4096];   // ln_binomial(alt + ref, alt) as f32 for in-field counts, index alt << 6 | ref (same for every context)
+struct EDec { uint32_t locus, ai, ri; };
+__device__ __forceinline__ EDec e_decode(uint32_t w, const Packing& pk) {
+    EDec d;
+    if (word_simple(w)) {
+        const bool isref = w >= pk.plane_rows;
+        d.locus = isref ? w - pk.plane_rows : w;
+        d.ai = isref ? 0u : 1u;
+        d.ri = isref ? 1u : 0u;
+    } else {
+        d.locus = w & pk.imask;
+        d.ai = (w >> pk.sh_a) & pk.cmask;
+        d.ri = (w >> pk.sh_r) & pk.cmask;
+    }
+    return d;
+}
 
 template <int V>
 struct ETile { FVec<V> a, b; };
 
 template <int V, bool EXACT_SKIP>
 __device__ __forceinline__ void e_issue(ETile<V>& t, uint32_t w, const Packing& pk, const float* __restrict__ la,
-                                        const float* __restrict__ lb, uint32_t row_bytes) {
-    const uint32_t locus = w & pk.imask;
-    if (!EXACT_SKIP || (w >> pk.sh_a) != 0) t.a = ld_row<V>(row_at(la, locus, row_bytes));
-    if (!EXACT_SKIP || ((w >> pk.sh_r) & pk.cmask) != 0) t.b = ld_row<V>(row_at(lb, locus, row_bytes));
+                                        const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
+    if (EXACT_SKIP && word_simple(w)) {
+        ld_row<V>(t.a, row_at(la, w, row_bytes), hm);   // the two planes are one allocation: row w of the joint table
+        return;
+    }
+    const EDec d = e_decode(w, pk);
+    if (!EXACT_SKIP || d.ai != 0) ld_row<V>(t.a, row_at(la, d.locus, row_bytes), hm);
+    if (!EXACT_SKIP || d.ri != 0) ld_row<V>(t.b, row_at(lb, d.locus, row_bytes), hm);
 }
 template <int V, bool EXACT_SKIP>
 __device__ __forceinline__ void e_consume(FVec<V>& acc, const ETile<V>& t, uint32_t w, const Packing& pk, const float4* __restrict__ aux) {
-    const uint32_t ai = w >> pk.sh_a, ri = (w >> pk.sh_r) & pk.cmask;
-    if (EXACT_SKIP && ri == 0 && ai == 1) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc.v[v] = __fadd_rn(acc.v[v], t.a.v[v]);
-    } else if (EXACT_SKIP && ai == 0 && ri == 1) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc.v[v] = __fadd_rn(acc.v[v], t.b.v[v]);
+    if (EXACT_SKIP && word_simple(w)) { vadd<V>(acc, t.a); return; }
+    const EDec d = e_decode(w, pk);
+    float alt, ref, lbc;
+    if (d.ai == pk.cmask && d.ri == pk.cmask && !word_simple(w)) {          // counts outside the packed fields (rare)
+        const float4 x = __ldg(aux);
+        alt = x.x; ref = x.y; lbc = x.z;
     } else {
-        float alt, ref, lbc;
-        if (ai == pk.cmask && ri == pk.cmask) {          // counts outside the packed fields (rare)
-            const float4 x = __ldg(aux);
-            alt = x.x; ref = x.y; lbc = x.z;
-        } else {
-            alt = (float)ai; ref = (float)ri; lbc = c_lbc[(ai << 6) | ri];
-        }
-        if (EXACT_SKIP && ri == 0) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc.v[v] = __fadd_rn(acc.v[v], __fadd_rn(lbc, __fmul_rn(alt, t.a.v[v])));
-        } else if (EXACT_SKIP && ai == 0) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc.v[v] = __fadd_rn(acc.v[v], __fadd_rn(lbc, __fmul_rn(ref, t.b.v[v])));
-        } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                acc.v[v] = __fadd_rn(acc.v[v], __fadd_rn(__fadd_rn(lbc, __fmul_rn(alt, t.a.v[v])), __fmul_rn(ref, t.b.v[v])));
-        }
+        alt = (float)d.ai; ref = (float)d.ri; lbc = c_lbc[(d.ai << 6) | d.ri];
+    }
+    if (EXACT_SKIP && d.ri == 0) {
+        vadd<V>(acc, vshift<V>(vscale<V>(t.a, alt), lbc));
+    } else if (EXACT_SKIP && d.ai == 0) {
+        vadd<V>(acc, vshift<V>(vscale<V>(t.b, ref), lbc));
+    } else {
+        FVec<V> x = vshift<V>(vscale<V>(t.a, alt), lbc);
+        vadd<V>(x, vscale<V>(t.b, ref));
+        vadd<V>(acc, x);
     }
 }
 
 template <int V, int U, bool EXACT_SKIP>
 __device__ __forceinline__ void e_batch(FVec<V>& acc, const uint32_t (&cur)[U], const Packing& pk, const float4* __restrict__ aux,
-                                        const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes) {
-    ETile<V> t[U];
+                                        const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
+    if (!EXACT_SKIP) {   // literal expression for every entry (non-finite tables): both rows of every entry
+        ETile<V> t[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) e_issue<V, EXACT_SKIP>(t[u], cur[u], pk, la, lb, row_bytes);
+        for (int u = 0; u < U; ++u) e_issue<V, false>(t[u], cur[u], pk, la, lb, row_bytes, hm);
 #pragma unroll
-    for (int u = 0; u < U; ++u) e_consume<V, EXACT_SKIP>(acc, t[u], cur[u], pk, aux + u);
+        for (int u = 0; u < U; ++u) e_consume<V, false>(acc, t[u], cur[u], pk, aux + u);
+        return;
+    }
+    // Exact-shortcut path.  The pass is bound by the row gathers a warp keeps in flight, and ~93 % of the entries need
+    // ONE row (single-UMI, or several UMIs of one allele), so a tile slot is one row: twice the entries in flight for
+    // the same registers.  The second row of a two-allele entry goes to the shared tile `tb` — early for the first such
+    // entry of the batch, late (an exposed load) for the rare further ones.
+    FVec<V> t[U], tb;
+    int owner = -1;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t w = cur[u];
+        if (word_simple(w)) { ld_row<V>(t[u], row_at(la, w, row_bytes), hm); continue; }
+        const uint32_t locus = w & pk.imask, ai = (w >> pk.sh_a) & pk.cmask, ri = (w >> pk.sh_r) & pk.cmask;
+        if (ai != 0) {
+            ld_row<V>(t[u], row_at(la, locus, row_bytes), hm);
+            if (ri != 0 && owner < 0) { ld_row<V>(tb, row_at(lb, locus, row_bytes), hm); owner = u; }
+        } else {
+            ld_row<V>(t[u], row_at(lb, locus, row_bytes), hm);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t w = cur[u];
+        if (word_simple(w)) { vadd<V>(acc, t[u]); continue; }
+        const uint32_t ai = (w >> pk.sh_a) & pk.cmask, ri = (w >> pk.sh_r) & pk.cmask;
+        float alt, ref, lbc;
+        if (ai == pk.cmask && ri == pk.cmask) {          // counts outside the packed fields (rare)
+            const float4 x = __ldg(aux + u);
+            alt = x.x; ref = x.y; lbc = x.z;
+        } else {
+            alt = (float)ai; ref = (float)ri; lbc = c_lbc[(ai << 6) | ri];
+        }
+        const bool marker = ai == pk.cmask && ri == pk.cmask;
+        if (ri == 0) {
+            // one allele only: lbc = ln C(n, n) = +0 and 0 + x == x (x = alt * ln th is never -0), so acc += alt * ln th
+            vadd<V>(acc, vcount<V>(t[u], ai, alt));
+        } else if (ai == 0) {
+            vadd<V>(acc, vcount<V>(t[u], ri, ref));
+        } else {
+            if (owner != u) ld_row<V>(tb, row_at(lb, w & pk.imask, row_bytes), hm);
+            FVec<V> x = vshift<V>(marker ? vscale<V>(t[u], alt) : vcount<V>(t[u], ai, alt), lbc);
+            vadd<V>(x, marker ? vscale<V>(tb, ref) : vcount<V>(tb, ri, ref));
+            vadd<V>(acc, x);
+        }
+    }
 }
 
 // Software-pipelined walk: the next U entry words are fetched while the current U row gathers are in
@@ -212,7 +373,7 @@ __device__ __forceinline__ void e_batch(FVec<V>& acc, const uint32_t (&cur)[U], 
 // more to instruction-cache misses than it saved in register moves.
 template <int V, int U, bool EXACT_SKIP>
 __device__ __forceinline__ void e_walk(FVec<V>& acc, const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t n,
-                                       const Packing& pk, const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes) {
+                                       const Packing& pk, const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
     uint32_t x[U], y[U];
     uint32_t done = 0;
     if (n >= U) {
@@ -225,7 +386,7 @@ __device__ __forceinline__ void e_walk(FVec<V>& acc, const uint32_t* __restrict_
 #pragma unroll
                 for (int u = 0; u < U; ++u) y[u] = __ldg(p + done + U + u);
             }
-            e_batch<V, U, EXACT_SKIP>(acc, x, pk, aux + done, la, lb, row_bytes);
+            e_batch<V, U, EXACT_SKIP>(acc, x, pk, aux + done, la, lb, row_bytes, hm);
             done += U;
             if (!more) break;
 #pragma unroll
@@ -235,7 +396,7 @@ __device__ __forceinline__ void e_walk(FVec<V>& acc, const uint32_t* __restrict_
 #pragma unroll 1
     for (; done < n; ++done) {
         const uint32_t w[1] = {__ldg(p + done)};
-        e_batch<V, 1, EXACT_SKIP>(acc, w, pk, aux + done, la, lb, row_bytes);
+        e_batch<V, 1, EXACT_SKIP>(acc, w, pk, aux + done, la, lb, row_bytes, hm);
     }
 }
 
@@ -243,37 +404,54 @@ struct EArgs {
     const uint32_t* csr_idx; const float4* csr_aux; const uint64_t* row_ptr; const uint32_t* cell_order;
     const float* LA; const float* LB; float* ELL; const int* group_active; const Ctl* ctl;
     Packing pk;
-    uint32_t N, Cpad, blocks_per_group, n_main;   // groups [0, n_main) are VM columns per lane wide, group n_main (if any) VT
+    uint32_t N, Cpad, blocks_per_group;
+    uint32_t no_narrow;    // tests: every group runs the full-width body whatever its live columns
     float log_prior;
 };
 
 template <int V>
-__device__ __forceinline__ void estep_body(const EArgs& a, uint32_t cell, uint32_t col0) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t col = col0 + lane * lane_cols<V>();
+__device__ __forceinline__ void estep_body(const EArgs& a, uint32_t cell, uint32_t col0, uint32_t live_cols) {
+    const LaneCols<V> lc = lane_setup<V>(col0, live_cols);
     const uint64_t j0 = a.row_ptr[cell];
     const uint32_t n = (uint32_t)(a.row_ptr[cell + 1] - j0);
     FVec<V> acc;
 #pragma unroll
     for (int v = 0; v < V; ++v) acc.v[v] = a.log_prior;
-    constexpr int U = V <= 4 ? SOUP_E_U : (V == 8 ? SOUP_E_U8 : SOUP_E_U16);
-    if (!a.ctl->nonfinite) e_walk<V, U, true>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + col, a.LB + col, a.Cpad * 4u);
-    else e_walk<V, 2, false>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + col, a.LB + col, a.Cpad * 4u);
-    st_row<V>(a.ELL + (size_t)cell * a.Cpad + col, acc);
+    constexpr int U = V == 1 ? SOUP_E_U1 : (V == 2 ? SOUP_E_U2 : (V == 4 ? SOUP_E_U4 : (V == 8 ? SOUP_E_U8 : SOUP_E_U16)));
+    if (!a.ctl->nonfinite) e_walk<V, U, true>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.LB + lc.col, a.Cpad * 4u, lc.hm);
+    else e_walk<V, 2, false>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.LB + lc.col, a.Cpad * 4u, lc.hm);
+    if (lc.live) st_row<V>(a.ELL + (size_t)cell * a.Cpad + lc.col, acc, lc.hm);
+}
+
+// the narrowest body (columns per lane) whose 32*V columns cover `rem` live columns, at most VM
+template <int VM> __device__ __forceinline__ int fit_lanes(uint32_t rem, uint32_t no_narrow) {
+    if (no_narrow) return VM;
+    if (VM >= 16 && rem > 256) return 16;
+    if (VM >= 8 && rem > 128) return 8;
+    if (VM >= 4 && rem > 64) return 4;
+    if (VM >= 2 && rem > 32) return 2;
+    return 1;
 }
 
 // grid: group-major (all cells of group 0, then group 1, ...) so one group's table slice stays hot in L2;
-// inside a group the cells are visited longest-first.
-template <int VM, int VT>
-__global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_E_MINB : 2)) estep_kernel(const EArgs a) {
+// inside a group the cells are visited longest-first.  Groups are 32*VM columns wide; a group beyond the live
+// prefix exits, a partly live one runs the narrowest body that covers what is live (the tail of a job, when
+// a handful of solves are still iterating, then costs a fraction of a full pass).
+template <int VM>
+__global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_E_MINB : 2) * (256 / EM_THREADS)) estep_kernel(const EArgs a) {
     const uint32_t group = blockIdx.x / a.blocks_per_group;
-    if (!a.group_active[group]) return;
+    const uint32_t live = a.ctl->live_cols, col0 = group * (32 * VM);
+    if (col0 >= live || !a.group_active[group]) return;
     const uint32_t chunk = blockIdx.x - group * a.blocks_per_group;
-    const uint32_t ci = chunk * EM_WARPS + (threadIdx.x >> 5);
+    const uint32_t ci = chunk * EM_WARPS + (EM_WARPS > 1 ? threadIdx.x >> 5 : 0);
     if (ci >= a.N) return;
     const uint32_t cell = a.cell_order[ci];
-    if (VM == VT || group < a.n_main) estep_body<VM>(a, cell, group * (32 * VM));
-    else estep_body<VT>(a, cell, a.n_main * (32 * VM));
+    const int v = fit_lanes<VM>(live - col0, a.no_narrow);
+    if (VM >= 16 && v == 16) estep_body<(VM >= 16 ? 16 : VM)>(a, cell, col0, live);
+    else if (VM >= 8 && v == 8) estep_body<(VM >= 8 ? 8 : VM)>(a, cell, col0, live);
+    else if (VM >= 4 && v == 4) estep_body<(VM >= 4 ? 4 : VM)>(a, cell, col0, live);
+    else if (VM >= 2 && v == 2) estep_body<(VM >= 2 ? 2 : VM)>(a, cell, col0, live);
+    else estep_body<1>(a, cell, col0, live);
 }
 
 // ------------------------------------------------------------------ per-cell pass (S:230-236 / S:318-330)
@@ -461,56 +639,53 @@ __global__ void __launch_bounds__(1024) control_kernel(ControlArgs a) {
 
 // ------------------------------------------------------------------ M pass (S:476-483, S:386-396)
 // s = 1 + sum_cells p*alt ; d = 2 + sum_cells p*(alt+ref), cells ascending; theta = clamp(s/d).
-// Entry stream: alt << sh_a | (alt+ref) << sh_r | cell; out-of-field counts -> float2 side record {alt, alt+ref}.
-// The inner loop is the reference's literal expression with NO data-dependent branch: a locus covered
-// by every cell is a 10^4..10^5-long strictly sequential chain owned by one warp, and on that critical
-// path a branch per entry (resolve latency, no ILP across it) costs more than the multiplies it saves.
+// Entry stream: see "entry words" above (simple: cell | alt << 30; general: 1 | alt | alt+ref | cell).
 __device__ __forceinline__ float small_u2f(uint32_t i) {   // exact (float)i for i < 2^23 without the conversion pipe
     return __fadd_rn(__uint_as_float(0x4B000000u | i), -8388608.0f);
 }
-// SHORTCUT = false: the literal expression, no data-dependent branch (long-locus role: a branch per entry on the
-// critical chain of a lone warp costs more than the multiplies it saves).
+// SHORTCUT = false: the literal expression for every entry, no data-dependent branch (long-locus role: a locus covered
+// by every cell is a 10^4..10^5-long strictly sequential chain owned by one warp, and on that critical path a branch per
+// entry costs more than the multiplies it saves; also the path for non-finite weights).
 // SHORTCUT = true : single-UMI entries skip the multiplies (p*1 == p) and, for alt == 0, the s update (s + p*0 == s
 // while the weights are finite — Ctl::nonfinite == 0); used by the wide role, which is instruction-issue bound.
 template <int V, bool SHORTCUT>
 __device__ __forceinline__ void m_consume(FVec<V>& s, FVec<V>& d, const FVec<V>& p, uint32_t w, const Packing& pk, const float2* __restrict__ aux) {
-    const uint32_t ai = w >> pk.sh_a, ti = (w >> pk.sh_r) & pk.cmask;
-    if (SHORTCUT && ti == 1) {
-        if (ai == 1) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) { s.v[v] = __fadd_rn(s.v[v], p.v[v]); d.v[v] = __fadd_rn(d.v[v], p.v[v]); }
-        } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], p.v[v]);
-        }
+    if (SHORTCUT && word_simple(w)) {
+        vadd<V>(d, p);
+        if (w & pk.alt_bit) vadd<V>(s, p);
+        return;
+    }
+    // every CSC word carries both count fields (a simple word: alt 0/1, alt+ref 1), so the decode is uniform
+    const uint32_t ai = (w >> pk.sh_a) & pk.cmask, ti = (w >> pk.sh_r) & pk.cmask;
+    if (SHORTCUT && ti == 2) {                               // two UMIs: p*2 == p+p exactly, p*1 == p, and s + p*0 == s
+        const FVec<V> p2 = vdouble<V>(p);
+        vadd<V>(d, p2);
+        if (ai == 1) vadd<V>(s, p);
+        else if (ai == 2) vadd<V>(s, p2);
         return;
     }
     float alt = small_u2f(ai), tot = small_u2f(ti);
-    if (ai == pk.cmask && ti == pk.cmask) {          // counts outside the packed fields (rare)
+    if (ai == pk.cmask && ti == pk.cmask) {                  // counts outside the packed fields (rare)
         const float2 x = __ldg(aux);
         alt = x.x; tot = x.y;
     }
-    if (!SHORTCUT || ai != 0) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) s.v[v] = __fadd_rn(s.v[v], __fmul_rn(p.v[v], alt));
-    }
-#pragma unroll
-    for (int v = 0; v < V; ++v) d.v[v] = __fadd_rn(d.v[v], __fmul_rn(p.v[v], tot));
+    if (!SHORTCUT || ai != 0) vadd<V>(s, vscale<V>(p, alt));
+    vadd<V>(d, vscale<V>(p, tot));
 }
 
 template <int V, int U, bool EXACT_SKIP>
 __device__ __forceinline__ void m_batch(FVec<V>& s, FVec<V>& d, const uint32_t (&cur)[U], const Packing& pk, const float2* __restrict__ aux,
-                                        const float* __restrict__ w, uint32_t row_bytes) {
+                                        const float* __restrict__ w, uint32_t row_bytes, uint32_t hm) {
     FVec<V> p[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) p[u] = ld_row<V>(row_at(w, cur[u] & pk.imask, row_bytes));
+    for (int u = 0; u < U; ++u) ld_row<V>(p[u], row_at(w, cur[u] & pk.imask, row_bytes), hm);
 #pragma unroll
     for (int u = 0; u < U; ++u) m_consume<V, EXACT_SKIP>(s, d, p[u], cur[u], pk, aux + u);
 }
 
 template <int V, int U, bool EXACT_SKIP>
 __device__ __forceinline__ void m_walk(FVec<V>& s, FVec<V>& d, const uint32_t* __restrict__ q, const float2* __restrict__ aux, uint32_t n,
-                                       const Packing& pk, const float* __restrict__ w, uint32_t row_bytes) {
+                                       const Packing& pk, const float* __restrict__ w, uint32_t row_bytes, uint32_t hm) {
     uint32_t x[U], y[U];
     uint32_t done = 0;
     if (n >= U) {
@@ -523,7 +698,7 @@ __device__ __forceinline__ void m_walk(FVec<V>& s, FVec<V>& d, const uint32_t* _
 #pragma unroll
                 for (int u = 0; u < U; ++u) y[u] = __ldg(q + done + U + u);
             }
-            m_batch<V, U, EXACT_SKIP>(s, d, x, pk, aux + done, w, row_bytes);
+            m_batch<V, U, EXACT_SKIP>(s, d, x, pk, aux + done, w, row_bytes, hm);
             done += U;
             if (!more) break;
 #pragma unroll
@@ -533,88 +708,27 @@ __device__ __forceinline__ void m_walk(FVec<V>& s, FVec<V>& d, const uint32_t* _
 #pragma unroll 1
     for (; done < n; ++done) {
         const uint32_t wd[1] = {__ldg(q + done)};
-        m_batch<V, 1, EXACT_SKIP>(s, d, wd, pk, aux + done, w, row_bytes);
-    }
-}
-
-// Deep walk for the long loci (the M pass's critical path): two register tiles of U gathered rows are
-// kept in flight in ping-pong, so a lone warp always has U..2U row gathers outstanding while it adds.
-template <int V, int U>
-__device__ __forceinline__ void m_issue(FVec<V> (&p)[U], const uint32_t (&x)[U], const Packing& pk, const float* __restrict__ w, uint32_t row_bytes) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) p[u] = ld_row<V>(row_at(w, x[u] & pk.imask, row_bytes));
-}
-template <int V, int U>
-__device__ __forceinline__ void m_eat(FVec<V>& s, FVec<V>& d, const FVec<V> (&p)[U], const uint32_t (&x)[U], const Packing& pk, const float2* __restrict__ aux) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) m_consume<V, false>(s, d, p[u], x[u], pk, aux + u);
-}
-template <int V, int U>
-__device__ __forceinline__ void m_walk_deep(FVec<V>& s, FVec<V>& d, const uint32_t* __restrict__ q, const float2* __restrict__ aux, uint32_t n,
-                                            const Packing& pk, const float* __restrict__ w, uint32_t row_bytes) {
-    const uint32_t nb = n / U;
-    uint32_t done = 0;
-    if (nb >= 2) {
-        uint32_t xa[U], xb[U], xn[U];
-        FVec<V> pa[U], pb[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { xa[u] = __ldg(q + u); xb[u] = __ldg(q + U + u); }
-        m_issue<V, U>(pa, xa, pk, w, row_bytes);
-        m_issue<V, U>(pb, xb, pk, w, row_bytes);
-        uint32_t b = 0;
-#pragma unroll 1
-        for (;;) {
-            bool more = b + 2 < nb;
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) xn[u] = __ldg(q + (b + 2) * U + u);
-            }
-            m_eat<V, U>(s, d, pa, xa, pk, aux + b * U);
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) xa[u] = xn[u];
-                m_issue<V, U>(pa, xa, pk, w, row_bytes);
-            }
-            if (b + 1 >= nb) { b += 1; break; }
-            more = b + 3 < nb;
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) xn[u] = __ldg(q + (b + 3) * U + u);
-            }
-            m_eat<V, U>(s, d, pb, xb, pk, aux + (b + 1) * U);
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) xb[u] = xn[u];
-                m_issue<V, U>(pb, xb, pk, w, row_bytes);
-            }
-            b += 2;
-            if (b >= nb) break;
-        }
-        done = b * U;
-    }
-#pragma unroll 1
-    for (; done < n; ++done) {
-        const uint32_t wd[1] = {__ldg(q + done)};
-        m_batch<V, 1, true>(s, d, wd, pk, aux + done, w, row_bytes);
+        m_batch<V, 1, EXACT_SKIP>(s, d, wd, pk, aux + done, w, row_bytes, hm);
     }
 }
 
 struct MArgs {
     const uint32_t* csc_idx; const float2* csc_aux; const uint64_t* col_ptr; const uint32_t* locus_order;
     const float* W; float* TH; float* LA; float* LB; const uint8_t* col_write;
-    const int* group_active;        // wide role: column groups of 32*VM (+ one narrower last group)
+    const int* group_active;        // wide role: column groups of 32*VM
     const int* long_group_active;   // long role: column groups of 32*SOUP_M_VLONG
     const Ctl* ctl;
     float* SP; float* DP;           // cell-sharded mode: partial sums of this rank's cells, [L][Cpad] each (else nullptr)
     Packing pk;
-    uint32_t L, Cpad, n_groups, n_main;
+    uint32_t L, Cpad, n_groups;
     uint32_t n_long, long_groups, long_blocks, wide_chunks, group_major;   // loci [0, n_long) of the LPT order take the long role
+    uint32_t no_narrow;
 };
 
 template <int V, bool DEEP>
-__device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint32_t col0) {
+__device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint32_t col0, uint32_t live_cols) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t col = col0 + lane * lane_cols<V>();
+    const LaneCols<V> lc = lane_setup<V>(col0, live_cols);
     const uint64_t j0 = a.col_ptr[locus];
     const uint32_t n = (uint32_t)(a.col_ptr[locus + 1] - j0);
     const bool partial = a.SP != nullptr;
@@ -622,31 +736,26 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
 #pragma unroll
     for (int v = 0; v < V; ++v) { s.v[v] = partial ? 0.0f : 1.0f; d.v[v] = partial ? 0.0f : 2.0f; }   // pseudocounts S:197-198, S:456-464
     if (DEEP) {
-#if SOUP_M_DEEP
-        m_walk_deep<V, SOUP_M_ULONG>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
-#else
-        m_walk<V, SOUP_M_ULONG, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
-#endif
+        if (SOUP_M_LONG_SHORTCUT && !a.ctl->nonfinite) m_walk<V, SOUP_M_ULONG, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
+        else m_walk<V, SOUP_M_ULONG, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
     } else {
-        constexpr int U = V <= 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16);
-        if (!a.ctl->nonfinite) m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
-        else m_walk<V, 2, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + col, a.Cpad * 4u);
+        constexpr int U = V <= 2 ? SOUP_M_U2 : (V == 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16));
+        if (!a.ctl->nonfinite) m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
+        else m_walk<V, 2, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
     }
-    if (partial) {   // cell-sharded: hand the partial statistics to the all-reduce; theta_kernel finishes the M pass
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const size_t o = (size_t)locus * a.Cpad + col_of<V>(col0, lane, v);
-            a.SP[o] = s.v[v];
-            a.DP[o] = d.v[v];
-        }
-        return;
-    }
+    if (!lc.live) return;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
+        if ((v >> 2) >= 1 && !((lc.hm >> (v >> 2)) & 1u)) continue;   // dead sub-block
         const uint32_t c = col_of<V>(col0, lane, v);
+        const size_t o = (size_t)locus * a.Cpad + c;
+        if (partial) {   // cell-sharded: hand the partial statistics to the all-reduce; theta_kernel finishes the M pass
+            a.SP[o] = s.v[v];
+            a.DP[o] = d.v[v];
+            continue;
+        }
         if (!a.col_write[c]) continue;                // locked cluster (S:389) or idle column
         const float th = fmaxf(fminf(__fdiv_rn(s.v[v], d.v[v]), 0.99f), 0.01f);   // S:392-393
-        const size_t o = (size_t)locus * a.Cpad + c;
         a.TH[o] = th;
         a.LA[o] = soupmath::glibc_logf(th);
         a.LB[o] = soupmath::glibc_logf(1.0f - th);
@@ -656,16 +765,18 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
 // Two roles in one grid.  Blocks [0, long_blocks): the n_long longest loci (LPT order), each split into
 // narrow column groups so that many warps share a long locus and each warp's sequential chain is
 // short per entry; they launch first.  Remaining blocks: all other loci with wide column groups
-// where the per-entry cost is amortised over more columns.
-template <int VM, int VT>
-__global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2)) mstep_kernel(const MArgs a) {
-    const uint32_t warp = threadIdx.x >> 5;
+// where the per-entry cost is amortised over more columns (narrowed to the live columns like the E pass).
+template <int VM>
+__global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256 / EM_THREADS)) mstep_kernel(const MArgs a) {
+    const uint32_t warp = EM_WARPS > 1 ? threadIdx.x >> 5 : 0;
+    const uint32_t live = a.ctl->live_cols;
     if (blockIdx.x < a.long_blocks) {
         const uint32_t item = blockIdx.x * EM_WARPS + warp;
         if (item >= a.n_long * a.long_groups) return;
         const uint32_t li = item / a.long_groups, group = item - li * a.long_groups;
-        if (!a.long_group_active[group]) return;
-        mstep_body<SOUP_M_VLONG, true>(a, a.locus_order[li], group * (32 * SOUP_M_VLONG));
+        const uint32_t col0 = group * (32 * SOUP_M_VLONG);
+        if (col0 >= live || !a.long_group_active[group]) return;
+        mstep_body<SOUP_M_VLONG, true>(a, a.locus_order[li], col0, live);
         return;
     }
     // wide role: locus-major (group fastest) while the whole weight plane fits L2 — every group's longer loci then start
@@ -674,12 +785,17 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2)) mstep
     uint32_t group, chunk;
     if (a.group_major) { group = bi / a.wide_chunks; chunk = bi - group * a.wide_chunks; }
     else { chunk = bi / a.n_groups; group = bi - chunk * a.n_groups; }
-    if (!a.group_active[group]) return;
+    const uint32_t col0 = group * (32 * VM);
+    if (col0 >= live || !a.group_active[group]) return;
     const uint32_t li = a.n_long + chunk * EM_WARPS + warp;
     if (li >= a.L) return;
     const uint32_t locus = a.locus_order[li];
-    if (VM == VT || group < a.n_main) mstep_body<VM, false>(a, locus, group * (32 * VM));
-    else mstep_body<VT, false>(a, locus, a.n_main * (32 * VM));
+    const int v = fit_lanes<VM>(live - col0, a.no_narrow);
+    if (VM >= 16 && v == 16) mstep_body<(VM >= 16 ? 16 : VM), false>(a, locus, col0, live);
+    else if (VM >= 8 && v == 8) mstep_body<(VM >= 8 ? 8 : VM), false>(a, locus, col0, live);
+    else if (VM >= 4 && v == 4) mstep_body<(VM >= 4 ? 4 : VM), false>(a, locus, col0, live);
+    else if (VM >= 2 && v == 2) mstep_body<(VM >= 2 ? 2 : VM), false>(a, locus, col0, live);
+    else mstep_body<1, false>(a, locus, col0, live);
 }
 
 // cell-sharded mode, after the all-reduce of (SP, DP): theta = clamp((1 + S) / (2 + D)) and the ln tables.
@@ -811,45 +927,31 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
         if (s.active) atomicAdd(&n_active, 1);
     }
     __syncthreads();
-    // Tail compaction.  Solves converge at different iterations; once the queue is empty the survivors are
-    // scattered over all column groups and every group with one live slot still costs a full pass.  When packing
-    // them to the front frees at least one group of the E pass or of the M pass's wide role, the highest live
-    // slots move into the lowest holes (disjoint source / destination sets, so migrate_kernel can copy all
-    // columns in parallel).  Only theta / ln-table columns and the slot state move; everything else is
-    // recomputed every iteration.  Per-solve results do not depend on the slot a solve sits in.
+    // Tail compaction.  Solves converge at different iterations; once the queue is empty the survivors would sit
+    // scattered over all column groups, and a group with one live slot costs a full pass.  So the highest live slots
+    // move into the lowest holes (disjoint source / destination sets: migrate_kernel copies all columns in parallel)
+    // and the live slots always form a prefix; the E / M kernels size their work by Ctl::live_cols.  Only theta /
+    // ln-table columns and the slot state move; everything else is recomputed every iteration.  Per-solve results do
+    // not depend on the slot a solve sits in.
     if (threadIdx.x == 0) {
         int moves = 0;
         if (a.compact && a.ctl->queue_head >= a.ctl->queue_len && n_active > 0) {
-            bool worth = false;
-            for (int t = 0; t < 2 && !worth; ++t) {
-                const FinalizeArgs::Plan pl = a.plan[t];
-                int live = 0;
-                for (int g = 0; g < pl.n_groups; ++g) {
-                    const int c0 = g * pl.WM, c1 = g < pl.n_main ? c0 + pl.WM : c0 + pl.WT;
-                    int last = (c1 - 1) / a.K;
-                    if (last >= a.slots) last = a.slots - 1;
-                    int any = 0;
-                    for (int s = c0 / a.K; s <= last; ++s) any |= a.st[s].active;
-                    live += any;
-                }
-                const int need = (n_active * a.K + pl.WM - 1) / pl.WM;
-                worth = need < live;
-            }
-            if (worth) {
-                int hole = 0, top = a.slots - 1;
-                for (;;) {
-                    while (hole < a.slots && a.st[hole].active) ++hole;
-                    while (top >= 0 && !a.st[top].active) --top;
-                    if (hole >= top) break;
-                    a.moves[moves++] = make_int2(top, hole);
-                    SlotState s = a.st[top];
-                    a.st[hole] = s;
-                    s.active = 0; s.solve = -1;
-                    a.st[top] = s;
-                }
+            int hole = 0, top = a.slots - 1;
+            for (;;) {
+                while (hole < a.slots && a.st[hole].active) ++hole;
+                while (top >= 0 && !a.st[top].active) --top;
+                if (hole >= top) break;
+                a.moves[moves++] = make_int2(top, hole);
+                SlotState s = a.st[top];
+                a.st[hole] = s;
+                s.active = 0; s.solve = -1;
+                a.st[top] = s;
             }
         }
         a.ctl->n_moves = moves;
+        int top = a.slots - 1;
+        while (top >= 0 && !a.st[top].active) --top;
+        a.ctl->live_cols = (uint32_t)((top + 1) * a.K);
     }
     __syncthreads();
     for (uint32_t c = threadIdx.x; c < a.Cpad; c += blockDim.x) {
@@ -917,9 +1019,20 @@ __global__ void count_ge_kernel(const uint32_t* __restrict__ sorted_desc, uint32
     *out = lo;
 }
 
-__device__ __forceinline__ uint32_t pack_word(uint32_t idx, uint32_t c0, uint32_t c1, const Packing& pk) {
+// entry words (see "entry words" above); `simple` = exactly one UMI in total
+__device__ __forceinline__ uint32_t pack_general(uint32_t idx, uint32_t c0, uint32_t c1, const Packing& pk) {
     if (c0 >= pk.cmask || c1 >= pk.cmask) c0 = c1 = pk.cmask;   // out-of-field: marker, the side record holds the counts
-    return (c0 << pk.sh_a) | (c1 << pk.sh_r) | idx;
+    return 0x80000000u | (c0 << pk.sh_a) | (c1 << pk.sh_r) | idx;
+}
+__device__ __forceinline__ uint32_t pack_csr_word(uint32_t locus, uint32_t alt, uint32_t ref, const Packing& pk) {
+    if (alt == 1 && ref == 0) return locus;
+    if (alt == 0 && ref == 1) return pk.plane_rows + locus;
+    return pack_general(locus, alt, ref, pk);
+}
+__device__ __forceinline__ uint32_t pack_csc_word(uint32_t cell, uint32_t alt, uint32_t ref, const Packing& pk) {
+    if (alt == 1 && ref == 0) return cell | (1u << pk.sh_r) | (1u << pk.sh_a);
+    if (alt == 0 && ref == 1) return cell | (1u << pk.sh_r);
+    return pack_general(cell, alt, alt + ref, pk);   // alt + ref: the reference's wrapping integer add, then cast (S:480)
 }
 
 __global__ void build_csr_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ locus,
@@ -934,7 +1047,7 @@ __global__ void build_csr_kernel(const uint64_t* __restrict__ row_ptr, const uin
         const uint32_t a = alt[j], r = ref[j], n = a + r;   // wrapping u32 add as in release-mode Rust (S:664, S:670)
         float lbc = 0.0f;
         if (n <= 170u) lbc = (float)(c_ln_factorial[n] - c_ln_factorial[a] - c_ln_factorial[n - a]);   // n > 170 patched from the host
-        csr_idx[j] = pack_word(locus[j], a, r, pk);
+        csr_idx[j] = pack_csr_word(locus[j], a, r, pk);
         csr_aux[j] = make_float4((float)a, (float)r, lbc, 0.0f);
         keys[j] = ((unsigned long long)locus[j] << 32) | cell;
         vals[j] = (uint32_t)j;
@@ -959,7 +1072,7 @@ __global__ void build_csc_kernel(const unsigned long long* __restrict__ keys, co
     if (i >= nnz) return;
     const uint32_t j = vals[i];
     const uint32_t a = alt[j], t = a + ref[j];
-    csc_idx[i] = pack_word((uint32_t)(keys[i] & 0xffffffffu), a, t, pk);
+    csc_idx[i] = pack_csc_word((uint32_t)(keys[i] & 0xffffffffu), a, t - a, pk);
     csc_aux[i] = make_float2((float)a, (float)t);
 }
 
