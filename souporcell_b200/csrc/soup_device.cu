@@ -76,6 +76,10 @@ struct soup_ctx {
     int device = 0;
     LoadBufs lb;
     cudaStream_t stream = nullptr, side = nullptr;   // side: loss + control, concurrent with the M pass
+    cudaStream_t side_long = nullptr;                // the M pass's long-locus kernel, concurrent with its wide role
+    cudaEvent_t ev_mfork = nullptr, ev_mjoin = nullptr;
+    int long_coop = 1;          // 0 never, 1 while few columns are live (the tail of a job), 2 always (SOUP_LONG_COOP)
+    uint32_t tail_cols = 128;   // "few": at most this many live columns (SOUP_TAIL_COLS, <= 256)
     bool own_stream = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
@@ -91,6 +95,7 @@ struct soup_ctx {
     float* d_total_alleles = nullptr;
     bool loaded = false;
     uint32_t n_long = 0;   // loci (in LPT order) whose M-pass chain is long enough for the narrow deep-walk role
+    uint32_t n_long_tail = 0;   // ... for the cooperative kernel while few columns are live (>= n_long)
     Workspace ws;
     // pinned staging for the polling loop
     Ctl* h_ctl = nullptr;
@@ -177,6 +182,19 @@ extern "C" int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx**
         ctx->own_stream = true;
     }
     cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    {   // the long-locus chains are the M pass's critical path: their CTAs go first
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&ctx->side_long, cudaStreamNonBlocking, hi);
+        cudaEventCreateWithFlags(&ctx->ev_mfork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_mjoin, cudaEventDisableTiming);
+        if (const char* e = getenv("SOUP_LONG_COOP")) ctx->long_coop = std::min(2, std::max(0, atoi(e)));
+        if (const char* e = getenv("SOUP_TAIL_COLS")) ctx->tail_cols = (uint32_t)std::min(256, std::max(1, atoi(e)));
+        if (cudaFuncSetAttribute(mstep_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ML_SMEM_FLOATS * sizeof(float))) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->long_coop = 0;
+        }
+    }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev0);
@@ -225,6 +243,9 @@ extern "C" void soup_ctx_destroy(soup_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->side_long) cudaStreamDestroy(ctx->side_long);
+    if (ctx->ev_mfork) cudaEventDestroy(ctx->ev_mfork);
+    if (ctx->ev_mjoin) cudaEventDestroy(ctx->ev_mjoin);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -406,9 +427,14 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
         uint64_t thr = std::max<uint64_t>(512, n_cells * 2 / 5);
         if (const char* e = getenv("SOUP_LONG_THRESHOLD")) thr = std::max<uint64_t>(1, strtoull(e, nullptr, 10));   // tests / tuning
         count_ge_kernel<<<1, 1, 0, st>>>(d_len, (uint32_t)n_loci, (uint32_t)std::min<uint64_t>(thr, UINT32_MAX), &((LoadFlags*)B.flags.p)->n_long);
+        uint64_t thr_tail = std::min<uint64_t>(thr, 2048);   // with few live columns every chain longer than this goes to the cooperative kernel
+        if (const char* e = getenv("SOUP_TAIL_THRESHOLD")) thr_tail = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+        thr_tail = std::min(thr_tail, thr);
+        count_ge_kernel<<<1, 1, 0, st>>>(d_len, (uint32_t)n_loci, (uint32_t)thr_tail, &((LoadFlags*)B.flags.p)->n_long_tail);
         CKL(cudaMemcpyAsync(&flags, B.flags.p, sizeof(LoadFlags), cudaMemcpyDeviceToHost, st));
         CKL(cudaStreamSynchronize(st));
         ctx->n_long = getenv("SOUP_NO_LONG") ? 0 : flags.n_long;
+        ctx->n_long_tail = getenv("SOUP_NO_LONG") ? 0 : std::max(flags.n_long, flags.n_long_tail);
     }
     CKL(cudaGetLastError());
     pt.lap("load: build csr/csc/lpt");
@@ -571,15 +597,26 @@ static void launch_m(soup_ctx* ctx) {
     const uint32_t chunks = (uint32_t)((ctx->L + EM_WARPS - 1) / EM_WARPS);
     if (chunks == 0) return;
     const uint32_t n_long = ctx->n_long, long_items = n_long * (uint32_t)w.lp.n_groups;
+    const uint32_t n_tail = ctx->n_long_tail;
+    const bool coop = ctx->long_coop != 0 && n_tail > 0;   // long loci by mstep_long_kernel on its own high-priority stream (MArgs::coop_mode)
     const uint32_t long_blocks = (long_items + EM_WARPS - 1) / EM_WARPS;
     const uint32_t wide_chunks = (uint32_t)((ctx->L - n_long + EM_WARPS - 1) / EM_WARPS);
     const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
                   w.m_group_active, w.l_group_active, w.ctl, w.stats, w.stats ? w.stats + (size_t)ctx->L * w.Cpad : nullptr, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups,
                   n_long, (uint32_t)w.lp.n_groups, long_blocks, wide_chunks,
-                  (uint32_t)((uint64_t)ctx->N * w.Cpad * 4 > (48ull << 20)), (uint32_t)(w.forced_lanes != 0)};
+                  (uint32_t)((uint64_t)ctx->N * w.Cpad * 4 > (48ull << 20)), (uint32_t)(w.forced_lanes != 0),
+                  coop ? (uint32_t)ctx->long_coop : 0u, ctx->tail_cols, n_tail};
+    if (coop) {
+        const uint32_t groups256 = (w.Cpad + ML_THREADS - 1) / ML_THREADS;
+        const uint32_t blocks = ctx->long_coop == 2 ? std::max(n_tail, n_long * groups256) : n_tail;
+        cudaEventRecord(ctx->ev_mfork, ctx->stream);
+        cudaStreamWaitEvent(ctx->side_long, ctx->ev_mfork, 0);
+        mstep_long_kernel<<<blocks, ML_THREADS, ML_SMEM_FLOATS * sizeof(float), ctx->side_long>>>(a);
+        cudaEventRecord(ctx->ev_mjoin, ctx->side_long);
+    }
     const dim3 grid(long_blocks + wide_chunks * w.mp.n_groups);
-    if (grid.x == 0) return;
-    SOUP_DISPATCH(mstep_kernel, w.mp, a);
+    if (grid.x != 0) SOUP_DISPATCH(mstep_kernel, w.mp, a);
+    if (coop) cudaStreamWaitEvent(ctx->stream, ctx->ev_mjoin, 0);
 }
 static void launch_post(soup_ctx* ctx, int method, bool counts) {
     Workspace& w = ctx->ws;

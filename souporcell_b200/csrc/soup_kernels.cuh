@@ -723,7 +723,12 @@ struct MArgs {
     uint32_t L, Cpad, n_groups;
     uint32_t n_long, long_groups, long_blocks, wide_chunks, group_major;   // loci [0, n_long) of the LPT order take the long role
     uint32_t no_narrow;
+    // long loci by the cooperative kernel (mstep_long_kernel): 0 never, 1 while at most tail_cols columns are live, 2 always.
+    // With few live columns it also takes the shorter loci [n_long, n_long_tail) — their one-warp chains would be the tail's critical path.
+    uint32_t coop_mode, tail_cols, n_long_tail;
 };
+__device__ __forceinline__ bool m_coop(const MArgs& a, uint32_t live) { return a.coop_mode == 2 || (a.coop_mode == 1 && live <= a.tail_cols); }
+__device__ __forceinline__ uint32_t m_coop_loci(const MArgs& a, uint32_t live) { return live <= a.tail_cols ? a.n_long_tail : a.n_long; }
 
 template <int V, bool DEEP>
 __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint32_t col0, uint32_t live_cols) {
@@ -770,7 +775,9 @@ template <int VM>
 __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256 / EM_THREADS)) mstep_kernel(const MArgs a) {
     const uint32_t warp = EM_WARPS > 1 ? threadIdx.x >> 5 : 0;
     const uint32_t live = a.ctl->live_cols;
+    const bool coop = m_coop(a, live);
     if (blockIdx.x < a.long_blocks) {
+        if (coop) return;                       // mstep_long_kernel owns the long loci
         const uint32_t item = blockIdx.x * EM_WARPS + warp;
         if (item >= a.n_long * a.long_groups) return;
         const uint32_t li = item / a.long_groups, group = item - li * a.long_groups;
@@ -787,7 +794,7 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256
     else { chunk = bi / a.n_groups; group = bi - chunk * a.n_groups; }
     const uint32_t col0 = group * (32 * VM);
     if (col0 >= live || !a.group_active[group]) return;
-    const uint32_t li = a.n_long + chunk * EM_WARPS + warp;
+    const uint32_t li = (coop ? m_coop_loci(a, live) : a.n_long) + chunk * EM_WARPS + warp;
     if (li >= a.L) return;
     const uint32_t locus = a.locus_order[li];
     const int v = fit_lanes<VM>(live - col0, a.no_narrow);
@@ -796,6 +803,141 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256
     else if (VM >= 4 && v == 4) mstep_body<(VM >= 4 ? 4 : VM), false>(a, locus, col0, live);
     else if (VM >= 2 && v == 2) mstep_body<(VM >= 2 ? 2 : VM), false>(a, locus, col0, live);
     else mstep_body<1, false>(a, locus, col0, live);
+}
+
+// ------------------------------------------------------------------ M pass, long loci: one CTA per (locus, 256 columns)
+// A locus covered by most cells is a 10^4..10^5-long strictly sequential chain per column.  Walked by one warp
+// (mstep_kernel's long role) every entry costs that warp its whole decode + address + gather sequence, and the row
+// gathers of a batch cannot overlap the adds of the previous one.  Here the chain is split by function instead:
+//   * all 256 threads stream the weight rows of the next chunks of entries into shared memory with cp.async
+//     (16-byte pieces, L2 -> smem, no registers held while in flight) and pre-decode the chunk's counts to floats;
+//   * thread t then owns column col0 + t and adds the staged rows strictly in entry order with the reference's
+//     literal expression  s += p*alt; d += p*(alt+ref)  — 6 instructions per entry on the critical path.
+// Results are bit-identical to the one-warp walk (same operations in the same order per column).
+constexpr int ML_THREADS = 256;
+constexpr int ML_MAX_STAGES = 8;
+constexpr int ML_MAX_CHUNK = 64;
+constexpr uint32_t ML_ROWS = 8;                 // rows of a chunk one thread copies, at most
+#ifndef SOUP_ML_SMEM_KB
+#define SOUP_ML_SMEM_KB 96                     // dynamic shared memory of the row stages (opt-in above 48 KB)
+#endif
+constexpr int ML_SMEM_FLOATS = SOUP_ML_SMEM_KB * 256;
+#ifndef SOUP_ML_FULL_STAGES
+#define SOUP_ML_FULL_STAGES 4                  // stages when all 256 columns are live (chunk = smem / stages / 1 KB)
+#endif
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(uint32_t pending) {   // the immediate form only: dispatch on the (CTA-uniform) count
+    switch (pending) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        case 6: cp_async_wait<6>(); break;
+        default: cp_async_wait<7>(); break;
+    }
+}
+
+__global__ void __launch_bounds__(ML_THREADS) mstep_long_kernel(const MArgs a) {
+    extern __shared__ __align__(16) float rows[];                 // ML_SMEM_FLOATS floats of row stages
+    __shared__ float2 counts[ML_MAX_STAGES][ML_MAX_CHUNK];
+    const uint32_t live = min(a.ctl->live_cols, a.Cpad);
+    if (!m_coop(a, live)) return;
+    // few live columns: one CTA per locus (the live columns fit one CTA); otherwise one per (locus, 256 columns)
+    const uint32_t n_groups = live <= a.tail_cols ? 1 : (a.Cpad + ML_THREADS - 1) / ML_THREADS;
+    const uint32_t li = blockIdx.x / n_groups, group = blockIdx.x - li * n_groups;
+    const uint32_t col0 = group * ML_THREADS;
+    if (li >= m_coop_loci(a, live) || col0 >= live) return;
+    const uint32_t locus = a.locus_order[li];
+    const uint32_t rem = min(live - col0, (uint32_t)ML_THREADS);
+    const uint32_t pieces = (rem + 3) >> 2;              // 16-byte pieces per staged row
+    const uint32_t stride = pieces << 2;                 // floats per staged row
+    // entries per chunk and chunks in flight: SOUP_ML_FULL_STAGES stages when every column is live; narrower rows
+    // (few live solves: the chain is then pure latency) first lengthen the chunk to 64 entries, then add stages
+    const uint32_t rows_per_pass = ML_THREADS / pieces;  // rows the CTA copies per pass (thread -> one 16-byte piece)
+    const uint32_t chunk = min(min((uint32_t)ML_SMEM_FLOATS / (SOUP_ML_FULL_STAGES * stride), (uint32_t)ML_MAX_CHUNK), ML_ROWS * rows_per_pass);
+    const uint32_t stages = min((uint32_t)ML_SMEM_FLOATS / (chunk * stride), (uint32_t)ML_MAX_STAGES);
+    const uint64_t j0 = a.col_ptr[locus];
+    const uint32_t n = (uint32_t)(a.col_ptr[locus + 1] - j0);
+    const uint32_t* __restrict__ q = a.csc_idx + j0;
+    const float2* __restrict__ aux = a.csc_aux + j0;
+    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    const uint32_t t = threadIdx.x;
+    const bool partial = a.SP != nullptr;
+    float s = partial ? 0.0f : 1.0f, d = partial ? 0.0f : 2.0f;   // pseudocounts S:197-198, S:456-464
+    const uint32_t r0 = t / pieces, pc = t - r0 * pieces;   // thread -> (row, piece) of a pass
+
+    // A thread copies piece `pc` of rows r0, r0 + rows_per_pass, ... of a chunk: at most ML_ROWS of them
+    // (the chunk length is clamped to that).  Their entry words are fetched one chunk ahead (`wn`), so the
+    // address of a copy never waits on the index stream.
+    uint32_t wn[ML_ROWS];
+    const bool copier = t < rows_per_pass * pieces;
+    auto fetch_words = [&](uint32_t c) {
+        const uint32_t base = c * chunk, cnt = c < n_chunks ? min(chunk, n - base) : 0;
+#pragma unroll
+        for (int k = 0; k < (int)ML_ROWS; ++k) {
+            const uint32_t r = r0 + k * rows_per_pass;
+            if (copier && r < cnt) wn[k] = __ldg(q + base + r);
+        }
+    };
+    auto issue = [&](uint32_t c) {   // wn holds the words of chunk c; leaves those of chunk c + 1 behind
+        const uint32_t base = c * chunk, cnt = min(chunk, n - base), stage = c % stages;
+        float* dst = rows + stage * chunk * stride;
+#pragma unroll
+        for (int k = 0; k < (int)ML_ROWS; ++k) {
+            const uint32_t r = r0 + k * rows_per_pass;
+            if (copier && r < cnt)
+                cp_async16(dst + r * stride + (pc << 2), a.W + (size_t)(wn[k] & a.pk.imask) * a.Cpad + col0 + (pc << 2));
+        }
+        if (t < cnt) {
+            const uint32_t w = __ldg(q + base + t);
+            const uint32_t ai = (w >> a.pk.sh_a) & a.pk.cmask, ti = (w >> a.pk.sh_r) & a.pk.cmask;
+            float2 x = make_float2(small_u2f(ai), small_u2f(ti));
+            if (ai == a.pk.cmask && ti == a.pk.cmask) x = __ldg(aux + base + t);   // counts outside the packed fields (rare)
+            counts[stage][t] = x;
+        }
+        fetch_words(c + 1);
+    };
+
+    fetch_words(0);
+    for (uint32_t c = 0; c < stages - 1; ++c) {
+        if (c < n_chunks) issue(c);
+        cp_async_commit();
+    }
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        if (c + stages - 1 < n_chunks) issue(c + stages - 1);          // its stage was consumed in iteration c - 1 (barrier below)
+        cp_async_commit();
+        cp_async_wait_dyn(stages - 1);                                 // this thread's pieces of chunk c have landed
+        __syncthreads();                                               // ... and everybody else's, and the decoded counts
+        if (t < rem) {
+            const uint32_t base = c * chunk, cnt = min(chunk, n - base), stage = c % stages;
+            const float* src = rows + stage * chunk * stride + t;
+#pragma unroll 4
+            for (uint32_t r = 0; r < cnt; ++r) {
+                const float p = src[r * stride];
+                const float2 x = counts[stage][r];
+                s = __fadd_rn(s, __fmul_rn(p, x.x));                   // S:478-481, literal
+                d = __fadd_rn(d, __fmul_rn(p, x.y));
+            }
+        }
+        __syncthreads();
+    }
+    if (t >= rem) return;
+    const uint32_t col = col0 + t;
+    const size_t o = (size_t)locus * a.Cpad + col;
+    if (partial) { a.SP[o] = s; a.DP[o] = d; return; }
+    if (!a.col_write[col]) return;                                     // locked cluster (S:389) or idle column
+    const float th = fmaxf(fminf(__fdiv_rn(s, d), 0.99f), 0.01f);      // S:392-393
+    a.TH[o] = th;
+    a.LA[o] = soupmath::glibc_logf(th);
+    a.LB[o] = soupmath::glibc_logf(1.0f - th);
 }
 
 // cell-sharded mode, after the all-reduce of (SP, DP): theta = clamp((1 + S) / (2 + D)) and the ln tables.
@@ -989,7 +1131,7 @@ __global__ void __launch_bounds__(256) migrate_kernel(const Ctl* __restrict__ ct
 // ------------------------------------------------------------------ load-time kernels
 __constant__ double c_ln_factorial[171];   // statrs FCACHE: ln(n!) for n <= 170 (S:669-670)
 
-struct LoadFlags { uint32_t bad_range, bad_order, bad_cell, n_zero, n_big, n_long; };
+struct LoadFlags { uint32_t bad_range, bad_order, bad_cell, n_zero, n_big, n_long, n_long_tail; };
 
 __global__ void validate_csr_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ locus, const uint32_t* __restrict__ alt,
                                     const uint32_t* __restrict__ ref, LoadFlags* flags, uint32_t N, uint32_t L) {

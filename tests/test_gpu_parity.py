@@ -18,17 +18,33 @@ def bits(a):
     return b
 
 
-@pytest.fixture(scope="module", params=["default", "long_role"])
-def small(request):
-    """`long_role` lowers the long-locus threshold so the M kernel's deep narrow-group role runs on this small matrix."""
+LONG_MODES = {
+    # name: environment while the context is created and the matrix loaded
+    "default": {},
+    # the M kernel's one-warp long-locus role on this small matrix (threshold lowered), cooperative kernel off
+    "long_role": {"SOUP_LONG_THRESHOLD": "12", "SOUP_LONG_COOP": "0"},
+    # cooperative long-locus kernel (one CTA per locus, rows staged in shared memory) for every locus with >= 12 entries
+    "long_coop": {"SOUP_LONG_THRESHOLD": "12", "SOUP_TAIL_THRESHOLD": "12", "SOUP_LONG_COOP": "2"},
+    # the shipped policy (cooperative kernel only while <= 128 columns are live), thresholds lowered so that it is exercised
+    "tail_coop": {"SOUP_LONG_THRESHOLD": "30", "SOUP_TAIL_THRESHOLD": "8"},
+}
+
+
+def make_ctx(csr, mode):
     import os
-    v, csr = synth_csr()
-    if request.param == "long_role":
-        os.environ["SOUP_LONG_THRESHOLD"] = "12"
+    env = LONG_MODES[mode]
+    os.environ.update(env)
     try:
-        ctx = sp.Context(0).load_csr(*csr)
+        return sp.Context(0).load_csr(*csr)
     finally:
-        os.environ.pop("SOUP_LONG_THRESHOLD", None)
+        for key in env:
+            os.environ.pop(key, None)
+
+
+@pytest.fixture(scope="module", params=list(LONG_MODES))
+def small(request):
+    v, csr = synth_csr()
+    ctx = make_ctx(csr, request.param)
     od = orc.OracleData.from_csr(*csr)
     yield v, csr, ctx, od
     ctx.close()
@@ -430,19 +446,15 @@ def test_cli_known_genotypes_matches_oracle_cli(tmp_path):
     assert ours.stdout == theirs.stdout and ours.stdout.count("\n") == v.n_cells
 
 
+@pytest.mark.parametrize("mode", ["long_role", "long_coop", "tail_coop"])
 @pytest.mark.parametrize("k,n_solves,slots", [(5, 30, 0), (7, 20, 13), (64, 3, 0), (33, 9, 4), (2, 70, 0)])
-def test_many_columns_straddling_groups(k, n_solves, slots):
+def test_many_columns_straddling_groups(k, n_solves, slots, mode):
     """Column counts that are not multiples of the 256 / 64 / 32-column group widths (slots straddle groups, narrow last
     groups, several wide groups) with refills and tail compaction: every solve bit-identical to the oracle."""
     v, csr = synth_csr(n_cells=220, n_loci=1400, k=4, mean_loci=80, seed=29)
     od = orc.OracleData.from_csr(*csr)
     theta0 = random_theta(np.random.default_rng(k), (n_solves, k, csr[1]))
-    os_env = __import__("os").environ
-    os_env["SOUP_LONG_THRESHOLD"] = "40"
-    try:
-        ctx = sp.Context(0).load_csr(*csr)
-    finally:
-        os_env.pop("SOUP_LONG_THRESHOLD", None)
+    ctx = make_ctx(csr, mode)
     with ctx:
         res = ctx.solve(k, method=sp.METHOD_KHM if k % 2 else sp.METHOD_EM, n_streams=n_solves, solves_per_stream=1, theta0=theta0, max_slots=slots)
         check = range(n_solves) if n_solves <= 10 else list(range(0, n_solves, 7)) + [n_solves - 1]
