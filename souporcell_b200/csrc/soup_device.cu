@@ -723,7 +723,12 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     // ---- shape: resident slots and vector width
     int slots = p->max_slots > 0 ? p->max_slots : std::max(1, 2048 / K);
     slots = std::min(slots, n_local);
-    {
+    PhaseTimer pt;
+    // a workspace of exactly this shape already exists (a repeated job): nothing to size, and cudaMemGetInfo — a driver
+    // call that was seen to take tens of milliseconds now and then — stays off the repeated path
+    const bool reuse = !p->theta0 && ctx->ws.K == K && ctx->ws.slots == std::min(slots, 1024) && ctx->ws.iter_cap == iter_cap &&
+                       ctx->ws.queue_cap >= n_local && ctx->ws.n_streams_cap >= p->n_streams;
+    if (!reuse) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         free_b += ctx->ws.bytes;
@@ -739,7 +744,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     while (slots > 1 && (uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32)) --slots;
     if ((uint64_t)std::max(ctx->L, ctx->N) * ((uint64_t)slots * K + 128) >= (1ull << 32))
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: max(cells, loci) * k exceeds the 32-bit row-offset range");
-    PhaseTimer pt;
+    pt.lap("solve: shape");
     const int forced_lanes = (p->lanes == 1 || p->lanes == 2 || p->lanes == 4 || p->lanes == 8 || p->lanes == 16) ? p->lanes : 0;
     int32_t rc = ensure_workspace(ctx, K, slots, forced_lanes, iter_cap, n_local, p->n_streams);
     if (rc != SOUP_OK) return rc;
@@ -868,21 +873,32 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_poll[which], st);
         return e;
     };
+    const bool slow_dbg = getenv("SOUP_DEBUG_SLOW") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_loop0 = now_ms();
+    double t_enq = 0, t_wait = 0, worst_enq = 0, worst_wait = 0;
     CKS(enqueue_chunk(0));
     for (;;) {
         const int cur = polls & 1;
+        const double ta = slow_dbg ? now_ms() : 0;
         CKS(enqueue_chunk(cur ^ 1));
+        const double tb = slow_dbg ? now_ms() : 0;
         CKS(cudaEventSynchronize(ctx->ev_poll[cur]));
+        if (slow_dbg) { const double tc = now_ms(); t_enq += tb - ta; t_wait += tc - tb; worst_enq = std::max(worst_enq, tb - ta); worst_wait = std::max(worst_wait, tc - tb); }
         ++polls;
         if (it.comm_error) { cleanup(); return ctx->fail(it.comm_error, "soup_solve: the all-reduce callback failed (%d)", it.comm_error); }
         if (ctx->h_ctl[cur].done_count >= n_local) break;
         if (iters_enqueued > (uint64_t)n_local * (uint64_t)(iter_cap + TEMP_STEPS) + 64) { cleanup(); return ctx->fail(SOUP_ERR_CUDA, "soup_solve: device control loop did not converge"); }
     }
+    const double t_loop1 = now_ms();
     CKS(cudaEventRecord(ctx->ev1, st));
     CKS(cudaStreamSynchronize(st));
     CKS(cudaGetLastError());
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    if (slow_dbg && now_ms() - t_loop0 > ms + 3.0)
+        fprintf(stderr, "soup_slow iterate: host %.2f ms (loop %.2f, final sync %.2f) vs device %.2f ms; polls %d, enqueue total %.2f worst %.2f, wait total %.2f worst %.2f\n",
+                now_ms() - t_loop0, t_loop1 - t_loop0, now_ms() - t_loop1, ms, polls, t_enq, worst_enq, t_wait, worst_wait);
 
     pt.lap("solve: iterate");
     // ---- results
