@@ -677,7 +677,7 @@ static void enqueue_iteration(IterLaunch& it) {
     harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K);
     launch_refill(ctx, it.refill);
     finalize_kernel<<<1, 1024, 0, ctx->stream>>>(it.fin);
-    migrate_kernel<<<dim3(32, (unsigned)w.slots), 256, 0, ctx->stream>>>(w.ctl, w.moves, w.TH, w.LA, w.LB, (uint32_t)ctx->L, w.Cpad, w.K);
+    migrate_kernel<<<dim3(96, (unsigned)w.slots), 256, 0, ctx->stream>>>(w.ctl, w.moves, w.TH, w.LA, w.LB, (uint32_t)ctx->L, w.Cpad, w.K);
 }
 
 // ------------------------------------------------------------------ soup_solve
