@@ -113,6 +113,11 @@ int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc /*[nnz]: log_binomial_coeffic
  * their partial losses. */
 typedef int32_t (*soup_allreduce_fn)(void* user, void* device_buf, uint64_t n_floats, void* cuda_stream);
 
+/* cluster-center initialisation (ClusterInit S:749-754).  kmeans++ / middle_variance / known cell assignments are
+ * `assert!(false)` in the reference (S:545,550,597) and are rejected by the CLI with the same message. */
+#define SOUP_INIT_RANDOM_UNIFORM 0      /* init_cluster_centers_uniform S:554-563 (the default) */
+#define SOUP_INIT_RANDOM_ASSIGNMENT 1   /* init_cluster_centers_random_assignment S:565-594 */
+
 typedef struct soup_solve_params {
     int32_t k;                 /* num_clusters (S:726) */
     int32_t method;            /* SOUP_METHOD_EM | SOUP_METHOD_KHM (S:101-108) */
@@ -140,6 +145,8 @@ typedef struct soup_solve_params {
     soup_allreduce_fn cell_allreduce; /* NULL = off */
     void* comm_user;
     uint64_t n_cells_global;          /* total cells over all ranks (the convergence limit S:214 uses it) */
+    int32_t init_strategy;            /* SOUP_INIT_* : how a solve's centers are drawn from its seed stream when neither theta0
+                                       * nor init_theta is given (--initialization_strategy, S:491-496) */
 } soup_solve_params;
 
 typedef struct soup_solve_result {
@@ -218,6 +225,7 @@ typedef struct soup_main_params {
     soup_allgather_fn allgather;     /* required when proc_world > 1 */
     soup_bcast_fn bcast;
     void* comm_user;
+    int32_t init_strategy;           /* SOUP_INIT_* (--initialization_strategy) */
 } soup_main_params;
 typedef struct soup_main_result {
     int32_t has_best, runs;

@@ -484,6 +484,54 @@ std::vector<std::vector<float>> init_cluster_centers_uniform(size_t loci, size_t
     return centers;
 }
 
+// rand 0.9.3 `rng.gen_range(0..n)` for usize (third-party arithmetic, NOT under /root/reference, unpinned: restated
+// from the published rand 0.9 sources).  `UniformUsize::sample_single` samples as u32 whenever the upper bound fits
+// in u32 (portability fix of 0.9.0), and `UniformInt::<u32>::sample_single_inclusive` is Canon's method with one
+// bias-reducing extra draw:  (hi, lo) = wmul(next_u32, range); if lo > 2^32 - range { hi += carry(lo + wmul(next_u32,
+// range).hi) }.  For the cluster counts souporcell uses the extra draw has probability ~ n / 2^32 per call.
+uint32_t gen_range_u32(ChaChaRng& rng, uint32_t n) {
+    const uint32_t range = n;                                   // low = 0, high = n - 1, range = high - low + 1
+    if (range == 0) return rng.next_u32();
+    const uint64_t m = (uint64_t)rng.next_u32() * range;
+    uint32_t result = (uint32_t)(m >> 32);
+    const uint32_t lo_order = (uint32_t)m;
+    if (lo_order > (uint32_t)(0u - range)) {
+        const uint32_t new_hi_order = (uint32_t)(((uint64_t)rng.next_u32() * range) >> 32);
+        if ((uint64_t)lo_order + new_hi_order > 0xffffffffull) result += 1;
+    }
+    return result;
+}
+
+// S:565-594
+std::vector<std::vector<float>> init_cluster_centers_random_assignment(size_t loci, const std::vector<CellData>& cell_data,
+                                                                       size_t num_clusters, ChaChaRng& rng) {
+    std::vector<std::vector<float>> sums, denoms;
+    for (size_t cluster = 0; cluster < num_clusters; ++cluster) {
+        sums.emplace_back();
+        denoms.emplace_back();
+        for (size_t l = 0; l < loci; ++l) {
+            sums[cluster].push_back(rng.gen_f32() * 0.01f);     // S:572
+            denoms[cluster].push_back(0.01f);
+        }
+    }
+    for (const CellData& cell : cell_data) {
+        const size_t cluster = gen_range_u32(rng, (uint32_t)num_clusters);   // S:577
+        for (size_t j = 0; j < cell.loci.size(); ++j) {
+            const float alt_c = (float)cell.alt_counts[j];
+            const float total = alt_c + (float)cell.ref_counts[j];
+            sums[cluster][cell.loci[j]] += alt_c;
+            denoms[cluster][cell.loci[j]] += total;
+        }
+    }
+    for (size_t cluster = 0; cluster < num_clusters; ++cluster)
+        for (size_t l = 0; l < loci; ++l) {
+            float v = sums[cluster][l] / denoms[cluster][l] + (rng.gen_f32() / 2.0f - 0.25f);   // S:588
+            v = fmaxf(fminf(v, 0.9999f), 0.0001f);                                                // S:589 (Rust f32::min / max ignore a NaN operand)
+            sums[cluster][l] = v;
+        }
+    return sums;
+}
+
 // S:514-542.  The reference reads the VCF with the `vcf` crate (0.6, not vendored): records in file order, record
 // index = original locus id, record.call[sample]["GT"][0] = the sample's GT string.  Restated here for plain or
 // gzipped text VCF: FORMAT column -> position of GT, sample column from the #CHROM header line.
@@ -562,15 +610,14 @@ std::vector<std::vector<float>> init_cluster_centers_known_genotypes(size_t loci
     return centers;
 }
 
-static std::vector<std::vector<float>> init_cluster_centers(size_t loci_used, const Params& params, ChaChaRng& rng,
+static std::vector<std::vector<float>> init_cluster_centers(size_t loci_used, const std::vector<CellData>& cell_data, const Params& params, ChaChaRng& rng,
                                                             size_t num_clusters, const std::vector<size_t>& locus_to_index) {   // S:485-498
     if (params.has_known_genotypes) return init_cluster_centers_known_genotypes(loci_used, params, locus_to_index);   // S:487
     if (params.has_known_cell_assignments) throw std::runtime_error("known cell assignments not yet implemented");
     switch (params.initialization_strategy) {
         case ClusterInit::KmeansPP: throw std::runtime_error("kmeans++ not yet implemented");
         case ClusterInit::RandomUniform: return init_cluster_centers_uniform(loci_used, num_clusters, rng);
-        case ClusterInit::RandomAssignment:
-            throw std::runtime_error("oracle: random_cell_assignment init not restated (rand 0.9 gen_range unpinned)");
+        case ClusterInit::RandomAssignment: return init_cluster_centers_random_assignment(loci_used, cell_data, num_clusters, rng);
         case ClusterInit::MiddleVariance: throw std::runtime_error("middle variance not yet implemented");
     }
     return {};
@@ -625,14 +672,14 @@ MainResult souporcell_main(size_t loci_used, const std::vector<CellData>& cells,
                     std::vector<std::vector<float>> centers;
                     std::vector<size_t> locked;
                     if (run == 0) {
-                        centers = init_cluster_centers(loci_used, params, td.rng, K, locus_to_index);
+                        centers = init_cluster_centers(loci_used, cells, params, td.rng, K, locus_to_index);
                         if (theta0_override) {
                             const float* t0 = theta0_override + (td.thread_num * td.solves_per_thread + iteration) * K * loci_used;
                             for (size_t c = 0; c < K; ++c)
                                 for (size_t l = 0; l < loci_used; ++l) centers[c][l] = t0[c * loci_used + l];
                         }
                     } else {                                                   // S:91-98
-                        auto re = init_cluster_centers(loci_used, params, td.rng, bad.size(), locus_to_index);
+                        auto re = init_cluster_centers(loci_used, cells, params, td.rng, bad.size(), locus_to_index);
                         centers = res.best_cluster_centers;
                         for (size_t i = 0; i < bad.size(); ++i) centers[bad[i]] = re[i];
                         for (size_t c = 0; c < K; ++c)

@@ -131,6 +131,9 @@ std::vector<size_t> bad_cluster_detection(size_t run, size_t num_clusters,
                                           const std::vector<std::vector<float>>& best_lp, FILE* log);  // S:150-187
 
 std::vector<std::vector<float>> init_cluster_centers_uniform(size_t loci, size_t k, ChaChaRng& rng);   // S:554-563
+struct CellData;
+uint32_t gen_range_u32(ChaChaRng& rng, uint32_t n);   // rand 0.9.3 gen_range(0..n) for usize (restated, unpinned)
+std::vector<std::vector<float>> init_cluster_centers_random_assignment(size_t loci, const std::vector<CellData>& cell_data, size_t num_clusters, ChaChaRng& rng);   // S:565-594
 std::vector<std::vector<float>> init_cluster_centers_known_genotypes(size_t loci, const Params& params,
                                                                       const std::vector<size_t>& locus_to_index);   // S:514-542
 

@@ -24,6 +24,7 @@ LIB_PATH = os.environ.get("SOUP_LIB") or os.path.join(_HERE, "lib", "libsoupgpu.
 
 OK, ERR_INVALID, ERR_CUDA, ERR_IO, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 METHOD_EM, METHOD_KHM = 0, 1
+INIT_RANDOM_UNIFORM, INIT_RANDOM_ASSIGNMENT = 0, 1
 MTX_PINNED = 1
 
 EXPORTS = [
@@ -53,7 +54,7 @@ class _SolveParams(C.Structure):
                 ("reinit_clusters", C.c_void_p), ("n_reinit", C.c_int32), ("iteration_cap", C.c_int32),
                 ("max_slots", C.c_int32), ("lanes", C.c_int32), ("record_counts", C.c_int32), ("keep_trace", C.c_int32),
                 ("poll_chunk", C.c_int32), ("time_kernels", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
-                ("cell_allreduce", C.c_void_p), ("comm_user", C.c_void_p), ("n_cells_global", C.c_uint64)]
+                ("cell_allreduce", C.c_void_p), ("comm_user", C.c_void_p), ("n_cells_global", C.c_uint64), ("init_strategy", C.c_int32)]
 
 
 class _SolveResult(C.Structure):
@@ -83,7 +84,7 @@ class _MainParams(C.Structure):
                 ("seed", C.c_uint8), ("souporcell3", C.c_int32), ("iteration_cap", C.c_int32), ("max_slots", C.c_int32),
                 ("lanes", C.c_int32), ("record_counts", C.c_int32), ("verbose_trace", C.c_int32), ("time_kernels", C.c_int32),
                 ("known_theta", C.c_void_p), ("proc_rank", C.c_int32), ("proc_world", C.c_int32), ("allgather", ALLGATHER_FN), ("bcast", BCAST_FN),
-                ("comm_user", C.c_void_p)]
+                ("comm_user", C.c_void_p), ("init_strategy", C.c_int32)]
 
 
 class _MainResult(C.Structure):
@@ -340,7 +341,7 @@ class Context:
     def solve(self, k, method=METHOD_EM, n_streams=1, solves_per_stream=1, stream_seeds=None, theta0=None,
               base_theta=None, reinit_clusters=None, iteration_cap=0, max_slots=0, lanes=0, record_counts=False,
               keep_trace=False, poll_chunk=0, time_kernels=False, shard_rank=0, shard_world=1, cell_allreduce=None,
-              n_cells_global=0) -> SolveResult:
+              n_cells_global=0, init_strategy=INIT_RANDOM_UNIFORM) -> SolveResult:
         n_solves = n_streams * solves_per_stream
         p = _SolveParams()
         p.k, p.method, p.n_streams, p.solves_per_stream = k, method, n_streams, solves_per_stream
@@ -365,6 +366,7 @@ class Context:
         p.iteration_cap, p.max_slots, p.lanes = iteration_cap, max_slots, lanes
         p.record_counts, p.keep_trace, p.poll_chunk = int(record_counts), int(keep_trace), poll_chunk
         p.shard_rank, p.shard_world, p.time_kernels = shard_rank, shard_world, int(time_kernels)
+        p.init_strategy = init_strategy
         if cell_allreduce is not None:
             p.cell_allreduce = C.cast(cell_allreduce, C.c_void_p)
             p.n_cells_global = n_cells_global
@@ -438,7 +440,7 @@ class MainResult:
 
 def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3=False, iteration_cap=0, max_slots=0,
          lanes=0, record_counts=False, verbose_trace=False, time_kernels=False, proc_rank=0, proc_world=1, allgather=None,
-         bcast=None, known_theta=None) -> MainResult:
+         bcast=None, known_theta=None, init_strategy=INIT_RANDOM_UNIFORM) -> MainResult:
     """souporcell_main S:60-131 over one context per GPU (restart-sharded)."""
     if isinstance(ctxs, Context):
         ctxs = [ctxs]
@@ -448,6 +450,7 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
     p.souporcell3, p.iteration_cap, p.max_slots, p.lanes = int(souporcell3), iteration_cap, max_slots, lanes
     p.record_counts, p.verbose_trace, p.time_kernels = int(record_counts), int(verbose_trace), int(time_kernels)
     p.proc_rank, p.proc_world = proc_rank, proc_world
+    p.init_strategy = init_strategy
     if known_theta is not None:
         kt = np.ascontiguousarray(known_theta, dtype=np.float32).reshape(k, ctxs[0].n_loci)
         p.known_theta = _ptr(kt)

@@ -767,7 +767,9 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
 
     // ---- per-call device inputs
     float *d_theta0 = nullptr, *d_base = nullptr, *d_init = nullptr;
-    auto cleanup = [&] { cudaFree(d_theta0); cudaFree(d_base); cudaFree(d_init); };
+    uint16_t* d_assign_free = nullptr;
+    uint64_t* d_words_free = nullptr;
+    auto cleanup = [&] { cudaFree(d_theta0); cudaFree(d_base); cudaFree(d_init); cudaFree(d_assign_free); cudaFree(d_words_free); };
 #define CKS(call)                                                                                        \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -816,6 +818,58 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     CKS(cudaMemcpyAsync(w.draw_of_k, draw_of_k.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
     CKS(cudaMemcpyAsync(w.k_locked, k_locked.data(), (size_t)K, cudaMemcpyHostToDevice, st));
     h2d += keys.size() * 4 + (size_t)n_local * 4 + (size_t)K * 5;
+    // ---- init_cluster_centers_random_assignment S:565-594: place the three phases of every solve in its seed stream.
+    // Solve `it` of a stream starts where solve it-1 ended; the middle phase (one gen_range per cell, S:577) consumes a
+    // data-dependent number of words, so the host walks it (N words per solve) and the device does the rest.
+    uint16_t* d_assign = nullptr;
+    uint64_t* d_words = nullptr;
+    const bool random_assignment = p->init_strategy == SOUP_INIT_RANDOM_ASSIGNMENT && !p->theta0 && !p->init_theta;
+    if (p->init_strategy != SOUP_INIT_RANDOM_UNIFORM && p->init_strategy != SOUP_INIT_RANDOM_ASSIGNMENT)
+    { cleanup(); return ctx->fail(SOUP_ERR_INVALID, "soup_solve: unknown init_strategy %d", p->init_strategy); }
+    if (random_assignment) {
+        if (cell_mode) { cleanup(); return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: random_cell_assignment needs every cell on one GPU (not available with cell sharding)"); }
+        if (!p->stream_seeds) { cleanup(); return ctx->fail(SOUP_ERR_INVALID, "soup_solve: random_cell_assignment needs stream_seeds"); }
+        if (n_draw > 65535) { cleanup(); return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: random_cell_assignment supports at most 65535 clusters"); }
+        const uint64_t N = ctx->N, phase = (uint64_t)n_draw * ctx->L;
+        std::vector<uint16_t> assign((size_t)n_local * N);
+        std::vector<uint64_t> words((size_t)n_local * 2);
+        std::vector<int> local_of(n_solves, -1);
+        for (int i = 0; i < n_local; ++i) local_of[queue[i]] = i;
+        for (int t = 0; t < p->n_streams; ++t) {
+            uint64_t pos = 0;
+            uint32_t blk[16];
+            uint64_t have = UINT64_MAX;
+            auto word_at = [&](uint64_t wpos) {
+                if ((wpos >> 4) != have) { have = wpos >> 4; chacha_block(keys.data() + (size_t)t * 8, have, 12, blk); }
+                return blk[wpos & 15];
+            };
+            for (int it2 = 0; it2 < p->solves_per_stream; ++it2) {
+                const int li = local_of[t * p->solves_per_stream + it2];
+                const uint64_t w_sums = pos;
+                pos += phase;
+                for (uint64_t c = 0; c < N; ++c) {                       // rand 0.9.3 gen_range(0..n_draw): Canon's method on u32
+                    const uint64_t m = (uint64_t)word_at(pos++) * (uint32_t)n_draw;
+                    uint32_t res = (uint32_t)(m >> 32);
+                    const uint32_t lo = (uint32_t)m;
+                    if (lo > (uint32_t)(0u - (uint32_t)n_draw)) {
+                        const uint32_t hi2 = (uint32_t)(((uint64_t)word_at(pos++) * (uint32_t)n_draw) >> 32);
+                        if ((uint64_t)lo + hi2 > 0xffffffffull) res += 1;
+                    }
+                    if (li >= 0) assign[(size_t)li * N + c] = (uint16_t)res;
+                }
+                if (li >= 0) { words[(size_t)li] = w_sums; words[(size_t)n_local + li] = pos; }
+                pos += phase;
+            }
+        }
+        CKS(cudaMalloc(&d_assign, std::max<size_t>(assign.size(), 1) * 2));
+        d_assign_free = d_assign;
+        CKS(cudaMalloc(&d_words, std::max<size_t>(words.size(), 1) * 8));
+        d_words_free = d_words;
+        CKS(cudaMemcpyAsync(d_assign, assign.data(), assign.size() * 2, cudaMemcpyHostToDevice, st));
+        CKS(cudaMemcpyAsync(d_words, words.data(), words.size() * 8, cudaMemcpyHostToDevice, st));
+        CKS(cudaStreamSynchronize(st));                                   // the staging vectors go out of scope here
+        h2d += assign.size() * 2 + words.size() * 8;
+    }
     // initial slot table: every slot "finished" with its first queue entry pending -> refill + finalize install them
     std::vector<SlotState> hst(slots);
     for (int s = 0; s < slots; ++s) {
@@ -833,7 +887,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0 && !cell_mode;
     it.allreduce = p->cell_allreduce; it.comm_user = p->comm_user;
     it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, d_init, w.draw_of_k, w.TH, w.LA, w.LB,
-                           (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream};
+                           (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream,
+                           d_assign, d_words, d_words ? d_words + n_local : nullptr, ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->pk_csc, (uint32_t)ctx->N};
     it.fin = FinalizeArgs{w.st, w.ctl, w.queue, w.k_locked, w.col_write,
                           {{w.e_group_active, 32 * w.ep.VM, 32 * w.ep.VT, w.ep.n_main, w.ep.n_groups},
                            {w.m_group_active, 32 * w.mp.VM, 32 * w.mp.VT, w.mp.n_main, w.mp.n_groups},

@@ -134,6 +134,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             sp.k = K; sp.method = p->method; sp.n_streams = (int)p->threads; sp.solves_per_stream = spt;
             sp.stream_seeds = seeds.data();
             sp.init_theta = p->known_theta;
+            sp.init_strategy = p->init_strategy;
             sp.base_theta = run > 0 ? best_theta.data() : nullptr;
             sp.reinit_clusters = run > 0 ? bad.data() : nullptr;
             sp.n_reinit = run > 0 ? n_bad : 0;

@@ -987,7 +987,43 @@ struct RefillArgs {
     float *TH, *LA, *LB;
     uint32_t L, Cpad;
     int K, n_draw, solves_per_stream;
+    // init_cluster_centers_random_assignment (S:565-594): the host walks each seed stream once to place its three
+    // phases — n_draw*L f32 draws, one gen_range per cell (its word count is data dependent), n_draw*L f32 draws —
+    // and hands over, per queued solve, the cells' clusters and the word offsets of the two f32 phases
+    const uint16_t* assign;       // [queue_len][N] or nullptr
+    const uint64_t* word_sums;    // [queue_len]: stream word of `rng.gen::<f32>()*0.01` for (draw 0, locus 0)   S:572
+    const uint64_t* word_noise;   // [queue_len]: stream word of `rng.gen::<f32>()/2.0 - 0.25` for (draw 0, locus 0)   S:588
+    const uint32_t* csc_idx; const float2* csc_aux; const uint64_t* col_ptr;
+    Packing pk;
+    uint32_t N;
 };
+
+__device__ __forceinline__ float chacha_f32(const uint32_t* key, uint64_t word) {   // rand 0.9 StandardUniform f32 at an absolute stream word
+    uint32_t blk[16];
+    chacha_block(key, word >> 4, 12, blk);
+    uint32_t wv = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) if ((int)(word & 15) == i) wv = blk[i];
+    return (float)(wv >> 8) * (1.0f / 16777216.0f);
+}
+
+// theta0[d][l] of the random-assignment init: sums = gen*0.01 then += alt of every cell assigned to d, cells ascending
+// (the order `for cell in cell_data` visits them); denoms = 0.01 then += alt + ref (f32 adds of integer-valued floats)
+__device__ __forceinline__ float random_assignment_theta(const RefillArgs& a, const uint32_t* key, int pending, int d, uint32_t l) {
+    float sum = __fmul_rn(chacha_f32(key, a.word_sums[pending] + (uint64_t)d * a.L + l), 0.01f), den = 0.01f;
+    const uint16_t* as = a.assign + (size_t)pending * a.N;
+    for (uint64_t j = a.col_ptr[l]; j < a.col_ptr[l + 1]; ++j) {
+        const uint32_t w = a.csc_idx[j];
+        if (as[w & a.pk.imask] != (uint16_t)d) continue;
+        const uint32_t ai = (w >> a.pk.sh_a) & a.pk.cmask, ti = (w >> a.pk.sh_r) & a.pk.cmask;
+        float alt = (float)ai, ref = (float)(ti - ai);
+        if (ai == a.pk.cmask && ti == a.pk.cmask) { const float2 x = a.csc_aux[j]; alt = x.x; ref = __fsub_rn(x.y, x.x); }
+        sum = __fadd_rn(sum, alt);                       // S:582
+        den = __fadd_rn(den, __fadd_rn(alt, ref));       // S:580, S:583
+    }
+    const float noise = __fsub_rn(__fdiv_rn(chacha_f32(key, a.word_noise[pending] + (uint64_t)d * a.L + l), 2.0f), 0.25f);
+    return fmaxf(fminf(__fadd_rn(__fdiv_rn(sum, den), noise), 0.9999f), 0.0001f);   // S:588-589
+}
 
 __global__ void __launch_bounds__(256) refill_kernel(RefillArgs a) {
     const int slot = blockIdx.y;
@@ -1006,6 +1042,8 @@ __global__ void __launch_bounds__(256) refill_kernel(RefillArgs a) {
         th = a.base_theta[(size_t)k * a.L + l];
     } else if (a.init_theta) {
         th = a.init_theta[(size_t)d * a.L + l];       // run 0: d == k; later runs: re-drawn cluster i takes row i (S:92-96)
+    } else if (a.assign) {
+        th = random_assignment_theta(a, a.stream_keys + (size_t)(solve / a.solves_per_stream) * 8, s.pending, d, l);
     } else {
         // init_cluster_centers_uniform S:554-563: cluster-major then locus draw order, one u32 word per f32
         const int stream = solve / a.solves_per_stream, it = solve - stream * a.solves_per_stream;

@@ -142,7 +142,6 @@ int main(int argc, char** argv) {
     if (known_cells) die("thread 'main' panicked: known cell assignments not yet implemented", 101);   // S:545
     if (init == "kmeans++") die("thread 'main' panicked: kmeans++ not yet implemented", 101);           // S:550
     if (init == "middle_variance") die("thread 'main' panicked: middle variance not yet implemented", 101);   // S:597
-    if (init == "random_cell_assignment") die("thread 'main' panicked: random_cell_assignment initialisation is not built in this release (SURVEY 8f-3)", 101);
 
     // The CUDA driver context takes a few hundred ms to come up: start it now, in the background, while the text
     // matrices are parsed on the CPU.
@@ -196,6 +195,7 @@ int main(int argc, char** argv) {
     // ---- souporcell_main S:60-148
     soup_main_params mp{};
     mp.known_theta = known_gt ? known_theta.data() : nullptr;
+    mp.init_strategy = init == "random_cell_assignment" ? SOUP_INIT_RANDOM_ASSIGNMENT : SOUP_INIT_RANDOM_UNIFORM;   // S:491-496
     mp.k = (int32_t)k; mp.method = method_s == "khm" ? SOUP_METHOD_KHM : SOUP_METHOD_EM;
     mp.restarts = restarts; mp.threads = (uint32_t)threads; mp.seed = seed; mp.souporcell3 = s3 ? 1 : 0;
     mp.max_slots = (int32_t)parse_num(get("max_slots", "0"), "max_slots", 1024);

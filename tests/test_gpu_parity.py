@@ -284,7 +284,10 @@ def test_cli_end_to_end_matches_oracle_cli(tmp_path):
     from souporcell_b200 import build, synth
     v = synth.generate(n_cells=250, n_loci=1500, k=3, mean_loci=90, seed=8)
     alt, ref, bc = synth.write_files(v, str(tmp_path))
-    for extra in (["-k", "3", "--restarts", "4", "-t", "2"], ["-k", "4", "--restarts", "3", "-m", "khm", "--seed", "11", "--min_alt", "6", "--min_ref=6"]):
+    for extra in (["-k", "3", "--restarts", "4", "-t", "2"], ["-k", "4", "--restarts", "3", "-m", "khm", "--seed", "11", "--min_alt", "6", "--min_ref=6"],
+                  # init_cluster_centers_random_assignment S:565-594 (gen_range restated from rand 0.9.3, unpinned)
+                  ["-k", "3", "--restarts", "5", "-t", "2", "--initialization_strategy", "random_cell_assignment"],
+                  ["-k", "16", "--restarts", "2", "-t", "1", "-m", "khm", "-s", "true", "--seed", "7", "--initialization_strategy=random_cell_assignment"]):
         args = ["-a", alt, "-r", ref, "-b", bc] + extra
         ours = subprocess.run([build.CLI] + args, capture_output=True, text=True)
         theirs = subprocess.run([orc.CLI_PATH] + args, capture_output=True, text=True)
