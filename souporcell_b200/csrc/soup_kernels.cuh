@@ -232,8 +232,9 @@ template <int V> __device__ __forceinline__ FVec<V> vcount(const FVec<V>& t, uin
 // ------------------------------------------------------------------ entry words
 // ONE 32-bit word per stored entry.  70 % of vartrix entries are single-UMI (alt + ref == 1), so those get the
 // cheapest possible form — bit 31 clear and the word is directly usable as an index:
-//   CSR stream (E pass): word = row of the joint ln table [ln th rows | ln(1-th) rows] this entry adds,
-//                        i.e. locus (alt == 1) or plane_rows + locus (ref == 1);
+//   CSR stream (E pass): bits 0..29 = row of the joint ln table [ln th rows | ln(1-th) rows] this entry adds,
+//                        i.e. locus (alt only) or plane_rows + locus (ref only); bit 30 = the row counts twice
+//                        (two UMIs of one allele, another 15 % of the entries: 2*x == x + x exactly and lbc == +0);
 //   CSC stream (M pass): word = cell | 1 << sh_r | alt << sh_a (the general layout with bit 31 clear).
 // Every other entry has bit 31 set:  1 | c0 << sh_a | c1 << sh_r | index  with (c0, c1) = (alt, ref) in the CSR
 // stream and (alt, alt+ref) in the CSC stream; counts that do not fit their field set both fields to the all-ones
@@ -247,6 +248,7 @@ struct Packing {
     uint32_t alt_bit;      // CSC stream: 1 << sh_a, the alt bit of a simple word
 };
 __device__ __forceinline__ bool word_simple(uint32_t w) { return (int32_t)w >= 0; }
+constexpr uint32_t CSR_DOUBLE = 0x40000000u, CSR_ROW_MASK = 0x3fffffffu;
 
 __constant__ float c_lbc[4096];   // ln_binomial(alt + ref, alt) as f32 for in-field counts, index alt << 6 | ref (same for every context)
 
@@ -263,10 +265,11 @@ struct EDec { uint32_t locus, ai, ri; };
 __device__ __forceinline__ EDec e_decode(uint32_t w, const Packing& pk) {
     EDec d;
     if (word_simple(w)) {
-        const bool isref = w >= pk.plane_rows;
-        d.locus = isref ? w - pk.plane_rows : w;
-        d.ai = isref ? 0u : 1u;
-        d.ri = isref ? 1u : 0u;
+        const uint32_t row = w & CSR_ROW_MASK, n = (w & CSR_DOUBLE) ? 2u : 1u;
+        const bool isref = row >= pk.plane_rows;
+        d.locus = isref ? row - pk.plane_rows : row;
+        d.ai = isref ? 0u : n;
+        d.ri = isref ? n : 0u;
     } else {
         d.locus = w & pk.imask;
         d.ai = (w >> pk.sh_a) & pk.cmask;
@@ -282,7 +285,7 @@ template <int V, bool EXACT_SKIP>
 __device__ __forceinline__ void e_issue(ETile<V>& t, uint32_t w, const Packing& pk, const float* __restrict__ la,
                                         const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
     if (EXACT_SKIP && word_simple(w)) {
-        ld_row<V>(t.a, row_at(la, w, row_bytes), hm);   // the two planes are one allocation: row w of the joint table
+        ld_row<V>(t.a, row_at(la, w & CSR_ROW_MASK, row_bytes), hm);   // the two planes are one allocation: a row of the joint table
         return;
     }
     const EDec d = e_decode(w, pk);
@@ -291,7 +294,7 @@ __device__ __forceinline__ void e_issue(ETile<V>& t, uint32_t w, const Packing& 
 }
 template <int V, bool EXACT_SKIP>
 __device__ __forceinline__ void e_consume(FVec<V>& acc, const ETile<V>& t, uint32_t w, const Packing& pk, const float4* __restrict__ aux) {
-    if (EXACT_SKIP && word_simple(w)) { vadd<V>(acc, t.a); return; }
+    if (EXACT_SKIP && word_simple(w)) { vadd<V>(acc, (w & CSR_DOUBLE) ? vdouble<V>(t.a) : t.a); return; }
     const EDec d = e_decode(w, pk);
     float alt, ref, lbc;
     if (d.ai == pk.cmask && d.ri == pk.cmask && !word_simple(w)) {          // counts outside the packed fields (rare)
@@ -331,7 +334,7 @@ __device__ __forceinline__ void e_batch(FVec<V>& acc, const uint32_t (&cur)[U], 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const uint32_t w = cur[u];
-        if (word_simple(w)) { ld_row<V>(t[u], row_at(la, w, row_bytes), hm); continue; }
+        if (word_simple(w)) { ld_row<V>(t[u], row_at(la, w & CSR_ROW_MASK, row_bytes), hm); continue; }
         const uint32_t locus = w & pk.imask, ai = (w >> pk.sh_a) & pk.cmask, ri = (w >> pk.sh_r) & pk.cmask;
         if (ai != 0) {
             ld_row<V>(t[u], row_at(la, locus, row_bytes), hm);
@@ -343,7 +346,11 @@ __device__ __forceinline__ void e_batch(FVec<V>& acc, const uint32_t (&cur)[U], 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const uint32_t w = cur[u];
-        if (word_simple(w)) { vadd<V>(acc, t[u]); continue; }
+        if (word_simple(w)) {
+            if (w & CSR_DOUBLE) vadd<V>(acc, vdouble<V>(t[u]));
+            else vadd<V>(acc, t[u]);
+            continue;
+        }
         const uint32_t ai = (w >> pk.sh_a) & pk.cmask, ri = (w >> pk.sh_r) & pk.cmask;
         float alt, ref, lbc;
         if (ai == pk.cmask && ri == pk.cmask) {          // counts outside the packed fields (rare)
@@ -1205,8 +1212,8 @@ __device__ __forceinline__ uint32_t pack_general(uint32_t idx, uint32_t c0, uint
     return 0x80000000u | (c0 << pk.sh_a) | (c1 << pk.sh_r) | idx;
 }
 __device__ __forceinline__ uint32_t pack_csr_word(uint32_t locus, uint32_t alt, uint32_t ref, const Packing& pk) {
-    if (alt == 1 && ref == 0) return locus;
-    if (alt == 0 && ref == 1) return pk.plane_rows + locus;
+    if (ref == 0 && (alt == 1 || alt == 2)) return locus | (alt == 2 ? CSR_DOUBLE : 0u);
+    if (alt == 0 && (ref == 1 || ref == 2)) return (pk.plane_rows + locus) | (ref == 2 ? CSR_DOUBLE : 0u);
     return pack_general(locus, alt, ref, pk);
 }
 __device__ __forceinline__ uint32_t pack_csc_word(uint32_t cell, uint32_t alt, uint32_t ref, const Packing& pk) {
