@@ -107,6 +107,14 @@ int32_t soup_get_csc(soup_ctx* ctx, uint64_t* col_ptr /*[L+1]*/, uint32_t* cell 
 int32_t soup_get_cell_totals(soup_ctx* ctx, float* total_alleles /*[N]*/);
 int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc /*[nnz]: log_binomial_coefficient per stored entry, S:669*/);
 
+/* Per-cluster, per-locus allele counts of hard cell assignments over the loaded matrix: the sufficient statistics
+ * the downstream stages rebuild from the text matrices today — consensus.py:296-331 (`cluster_allele_counts[locus][cluster]
+ * = [ref, alt]`, cells of `doublets` skipped) and troublet's load_allele_data (/root/reference/troublet/src/main.rs:261-412).
+ * `cell_cluster[c]` < 0 (or >= k) skips cell c.  Exact integer sums (u64), one atomic add per stored entry; loci are the
+ * used-locus indices of the loaded matrix (soup_mtx::index_to_locus maps them back to file rows). */
+int32_t soup_cluster_allele_counts(soup_ctx* ctx, const int32_t* cell_cluster /*[n_cells]*/, int32_t k,
+                                   uint64_t* counts /*[n_loci][k][2] = {ref, alt}*/);
+
 /* Cell-sharded mode: sum `n_floats` f32 at device pointer `device_buf` in place over all ranks, enqueued on
  * `cuda_stream` (e.g. ncclAllReduce, or torch.distributed.all_reduce on a tensor aliasing the buffer).  Called once
  * per EM iteration with the M pass's sufficient statistics [sum p*alt | sum p*(alt+ref)] of all resident restarts and

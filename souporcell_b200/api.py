@@ -31,7 +31,7 @@ EXPORTS = [
     "soup_version", "soup_last_error", "soup_mtx_load", "soup_mtx_free", "soup_barcodes_load", "soup_free",
     "soup_known_genotypes_load", "soup_chacha_words", "soup_thread_seeds", "soup_format_f32", "soup_ln_binomial_f32", "soup_bad_cluster_detection",
     "soup_ctx_create", "soup_ctx_destroy", "soup_load_csr", "soup_get_dims", "soup_get_csc", "soup_get_cell_totals",
-    "soup_get_csr_lbc", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
+    "soup_get_csr_lbc", "soup_cluster_allele_counts", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
     "soup_main", "soup_exchange_best", "soup_write_clusters",
 ]
 
@@ -128,6 +128,7 @@ def lib():
         L.soup_get_csc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.soup_get_cell_totals.argtypes = [C.c_void_p, C.c_void_p]
         L.soup_get_csr_lbc.argtypes = [C.c_void_p, C.c_void_p]
+        L.soup_cluster_allele_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.soup_solve.argtypes = [C.c_void_p, C.POINTER(_SolveParams), C.POINTER(_SolveResult)]
         L.soup_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.soup_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
@@ -331,6 +332,13 @@ class Context:
     def get_csr_lbc(self):
         out = np.empty(self.nnz, dtype=np.float32)
         self._ck(lib().soup_get_csr_lbc(self._h, _ptr(out)))
+        return out
+
+    def cluster_allele_counts(self, cell_cluster, k):
+        """[n_loci][k][2] = (ref, alt) sums over the cells assigned to each cluster (consensus.py:296-331); cluster < 0 skips a cell."""
+        cl = np.ascontiguousarray(cell_cluster, dtype=np.int32).reshape(self.n_cells)
+        out = np.zeros((self.n_loci, k, 2), dtype=np.uint64)
+        self._ck(lib().soup_cluster_allele_counts(self._h, _ptr(cl), k, _ptr(out)))
         return out
 
     def stats(self) -> dict:

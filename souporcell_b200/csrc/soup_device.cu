@@ -486,6 +486,30 @@ extern "C" int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc) {
     return SOUP_OK;
 }
 
+extern "C" int32_t soup_cluster_allele_counts(soup_ctx* ctx, const int32_t* cell_cluster, int32_t k, uint64_t* counts) {
+    if (!ctx) return SOUP_ERR_INVALID;
+    if (!ctx->loaded) return ctx->fail(SOUP_ERR_INVALID, "no matrix loaded (call soup_load_csr first)");
+    if (!cell_cluster || !counts || k <= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_cluster_allele_counts: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n_out = (size_t)ctx->L * (size_t)k * 2;
+    if (n_out == 0) return SOUP_OK;
+    int32_t* d_cl = nullptr;
+    unsigned long long* d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_cl, std::max<uint64_t>(ctx->N, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, n_out * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_cl, cell_cluster, ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, n_out * 8, ctx->stream);
+    if (e == cudaSuccess && ctx->N)
+        cluster_counts_kernel<<<(unsigned)((ctx->N + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_row_ptr, (const uint32_t*)ctx->lb.locus.p, (const uint32_t*)ctx->lb.alt.p,
+                                                                                    (const uint32_t*)ctx->lb.ref.p, d_cl, d_out, (uint32_t)ctx->N, k);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_out, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_cl); cudaFree(d_out);
+    if (e != cudaSuccess) { cudaGetLastError(); return ctx->fail(e == cudaErrorMemoryAllocation ? SOUP_ERR_NOMEM : SOUP_ERR_CUDA, "soup_cluster_allele_counts: %s", cudaGetErrorString(e)); }
+    return SOUP_OK;
+}
+
 // ------------------------------------------------------------------ workspace
 // Column groups of one kernel: `n_main` groups of 32*VM columns and, if the column count is not a
 // multiple of that, one narrower last group (the smallest of 1/2/4/8 columns per lane that holds the

@@ -1281,6 +1281,24 @@ __global__ void seg_len_kernel(const uint64_t* __restrict__ ptr, uint32_t* __res
     idx[i] = i;
 }
 
+// ------------------------------------------------------------------ downstream sufficient statistics
+// cluster_allele_counts[locus][cluster] = {sum ref, sum alt} over the cells assigned to the cluster (consensus.py:296-331):
+// one warp per cell over the raw CSR arrays, exact 64-bit integer atomics (order cannot matter)
+__global__ void cluster_counts_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ locus, const uint32_t* __restrict__ alt,
+                                      const uint32_t* __restrict__ ref, const int32_t* __restrict__ cell_cluster, unsigned long long* counts,
+                                      uint32_t N, int K) {
+    const uint32_t cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (cell >= N) return;
+    const int c = cell_cluster[cell];
+    if (c < 0 || c >= K) return;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t j = row_ptr[cell] + lane; j < row_ptr[cell + 1]; j += 32) {
+        unsigned long long* o = counts + ((size_t)locus[j] * K + c) * 2;
+        if (ref[j]) atomicAdd(o, (unsigned long long)ref[j]);
+        if (alt[j]) atomicAdd(o + 1, (unsigned long long)alt[j]);
+    }
+}
+
 // ------------------------------------------------------------------ test hooks
 __global__ void math_kernel(int op, const float* __restrict__ in, float* __restrict__ out, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -342,9 +342,10 @@ def _split_cells(csr, parts):
     return cuts, out
 
 
+@pytest.mark.parametrize("mode", ["default", "long_coop"])
 @pytest.mark.parametrize("world", [1, 2, 3])
 @pytest.mark.parametrize("method", [sp.METHOD_EM, sp.METHOD_KHM])
-def test_cell_sharded_mode_agrees_with_oracle_to_tolerance(world, method):
+def test_cell_sharded_mode_agrees_with_oracle_to_tolerance(world, method, mode):
     """`world` ranks emulated on one GPU: one context per cell shard, one thread per rank, the all-reduce callback is a
     rendezvous that sums the ranks' device buffers.  The pseudocount joins the reduced sum, so this mode is checked at
     north_star's tolerance (1e-5 relative per-iteration loss and theta, up to the first differing control decision)
@@ -396,9 +397,15 @@ def test_cell_sharded_mode_agrees_with_oracle_to_tolerance(world, method):
                             cell_allreduce=make_cb(rank), n_cells_global=csr[0])
             results[rank] = (res, [ctx.get_trace(s) for s in range(S)])
 
-    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
-    [t.start() for t in threads]
-    [t.join() for t in threads]
+    import os
+    os.environ.update(LONG_MODES[mode])       # read when the contexts are created / the shards loaded (inside the threads)
+    try:
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+    finally:
+        for key in LONG_MODES[mode]:
+            os.environ.pop(key, None)
     assert all(r is not None for r in results)
     res0, traces0 = results[0]
     want = [od.solve(theta0[s], method=method) for s in range(S)]
@@ -415,6 +422,23 @@ def test_cell_sharded_mode_agrees_with_oracle_to_tolerance(world, method):
     lp = np.concatenate([results[r][0].best_log_probs for r in range(world)])   # each rank returns its own cells
     np.testing.assert_allclose(lp, want[best]["log_probs"], rtol=1e-5)
     assert np.array_equal(np.argmax(lp, axis=1), np.argmax(want[best]["log_probs"], axis=1))
+
+
+def test_cluster_allele_counts_exact(small):
+    """soup_cluster_allele_counts vs a numpy restatement of consensus.py:296-331 (cells with cluster -1, the doublets there, skipped)."""
+    _, csr, ctx, _ = small
+    n, L, row_ptr, locus, alt, ref = csr
+    rng = np.random.default_rng(12)
+    k = 5
+    cl = rng.integers(-1, k, size=n).astype(np.int32)
+    got = ctx.cluster_allele_counts(cl, k)
+    want = np.zeros((L, k, 2), dtype=np.uint64)
+    cell_of = np.repeat(np.arange(n), np.diff(row_ptr).astype(np.int64))
+    keep = cl[cell_of] >= 0
+    np.add.at(want, (locus[keep].astype(np.int64), cl[cell_of][keep].astype(np.int64), 0), ref[keep].astype(np.uint64))
+    np.add.at(want, (locus[keep].astype(np.int64), cl[cell_of][keep].astype(np.int64), 1), alt[keep].astype(np.uint64))
+    assert np.array_equal(got, want)
+    assert got.sum() == int(ref[keep].sum()) + int(alt[keep].sum())
 
 
 def test_main_over_two_contexts_equals_one(small):
