@@ -594,6 +594,7 @@ struct IterLaunch {
     int32_t comm_error = 0;
     RefillArgs refill;
     FinalizeArgs fin;
+    bool queue_drained = false;   // the host has SEEN queue_head >= queue_len: no slot can get a pending solve any more, so refill launches stop
 };
 
 #define SOUP_DISPATCH(KERNEL, PLAN, ARGS)                                                       \
@@ -644,8 +645,8 @@ static void launch_m(soup_ctx* ctx) {
 }
 static void launch_post(soup_ctx* ctx, int method, bool counts) {
     Workspace& w = ctx->ws;
-    PostArgs a{w.ELL, w.W, w.LSE, ctx->d_total_alleles, w.st, counts ? w.counts : nullptr, (uint32_t)ctx->N, w.Cpad, w.K, w.slots, method};
-    if (ctx->N) post_kernel<<<dim3((unsigned)((ctx->N + 127) / 128), (unsigned)w.slots), 128, 0, ctx->stream>>>(a);
+    PostArgs a{w.ELL, w.W, w.LSE, ctx->d_total_alleles, w.st, w.ctl, counts ? w.counts : nullptr, (uint32_t)ctx->N, w.Cpad, w.K, w.slots, method};
+    if (ctx->N) post_kernel<<<dim3((unsigned)((ctx->N + POST_WARPS - 1) / POST_WARPS), (unsigned)((w.slots + 31) / 32)), 32 * POST_WARPS, 0, ctx->stream>>>(a);
 }
 static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
     Workspace& w = ctx->ws;
@@ -699,7 +700,7 @@ static void enqueue_iteration(IterLaunch& it) {
         cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     }
     harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K);
-    launch_refill(ctx, it.refill);
+    if (!it.queue_drained) launch_refill(ctx, it.refill);
     finalize_kernel<<<1, 1024, 0, ctx->stream>>>(it.fin);
     migrate_kernel<<<dim3(96, (unsigned)w.slots), 256, 0, ctx->stream>>>(w.ctl, w.moves, w.TH, w.LA, w.LB, (uint32_t)ctx->L, w.Cpad, w.K);
 }
@@ -967,6 +968,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         ++polls;
         if (it.comm_error) { cleanup(); return ctx->fail(it.comm_error, "soup_solve: the all-reduce callback failed (%d)", it.comm_error); }
         if (ctx->h_ctl[cur].done_count >= n_local) break;
+        if (ctx->h_ctl[cur].queue_head >= ctx->h_ctl[cur].queue_len) it.queue_drained = true;
         if (iters_enqueued > (uint64_t)n_local * (uint64_t)(iter_cap + TEMP_STEPS) + 64) { cleanup(); return ctx->fail(SOUP_ERR_CUDA, "soup_solve: device control loop did not converge"); }
     }
     const double t_loop1 = now_ms();

@@ -468,6 +468,7 @@ struct PostArgs {
     float* LSE;
     const float* total_alleles;
     const SlotState* st;
+    const Ctl* ctl;
     int* counts;          // [slots][K] cells per cluster (LAST max, S:254), or nullptr
     uint32_t N, Cpad;
     int K, slots, method;
@@ -481,10 +482,18 @@ __device__ __forceinline__ float rust_lse(const float* x, int K) {   // log_sum_
     return m + soupmath::glibc_logf(s);
 }
 
-__global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
-    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;   // cell fastest: coalesced LSE / total_alleles
-    const int slot = blockIdx.y;
-    if (cell >= a.N) return;
+// thread = (cell, slot), slot fastest: a warp covers `sw` neighbouring slots of 32 / sw cells, so its ELL / W accesses —
+// nearly all of this kernel's traffic — are contiguous runs of sw*K*4 bytes (the LSE store, 4 bytes per thread, is the
+// strided one).  sw = 32 while many solves are live, the next power of two above the live slots in the tail of a job.
+constexpr int POST_WARPS = 4;
+__global__ void __launch_bounds__(32 * POST_WARPS) post_kernel(PostArgs a) {
+    const uint32_t live_slots = min((a.ctl->live_cols + (uint32_t)a.K - 1) / (uint32_t)a.K, (uint32_t)a.slots);
+    uint32_t sw = 32;
+    while (sw > 1 && (sw >> 1) >= live_slots) sw >>= 1;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cw = 32 / sw;
+    const uint32_t cell = (blockIdx.x * POST_WARPS + warp) * cw + lane / sw;
+    const int slot = (int)(blockIdx.y * 32 + (lane & (sw - 1)));
+    if (cell >= a.N || slot >= a.slots || (uint32_t)slot >= live_slots) return;
     const SlotState s = a.st[slot];
     if (!s.active) return;
     const int K = a.K;
