@@ -655,7 +655,11 @@ static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
     if (n) refill_kernel<<<dim3((unsigned)std::min<size_t>((n + 255) / 256, 48), (unsigned)w.slots), 256, 0, ctx->stream>>>(a);
 }
 
-static uint64_t launches_per_iteration(const soup_ctx* ctx) { (void)ctx; return 10; }
+// kernels one iteration enqueues: E, post, loss, control, M (+ the long-locus kernel), harvest, finalize, migrate
+// (+ refill while the queue is not known to be drained, + theta in cell-sharded mode)
+static uint64_t launches_per_iteration(const soup_ctx* ctx, bool refill, bool cell_mode) {
+    return 8 + (ctx->long_coop != 0 && ctx->n_long_tail > 0 ? 1 : 0) + (refill ? 1 : 0) + (cell_mode ? 1 : 0);
+}
 
 static void launch_loss_control(soup_ctx* ctx, cudaStream_t st, bool counts, float limit) {
     Workspace& w = ctx->ws;
@@ -948,7 +952,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
             enqueue_iteration(it);
         }
         iters_enqueued += chunk;
-        launches += (uint64_t)chunk * launches_per_iteration(ctx);
+        launches += (uint64_t)chunk * launches_per_iteration(ctx, !it.queue_drained, it.allreduce != nullptr);
         cudaError_t e = cudaMemcpyAsync(ctx->h_ctl + which, w.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_poll[which], st);
         return e;
