@@ -58,6 +58,8 @@ typedef struct soup_mtx {
     int32_t pinned;            /* buffers are cudaHostAlloc'ed */
 } soup_mtx;
 #define SOUP_MTX_PINNED 1 /* allocate the CSR in page-locked memory (needs a CUDA driver) */
+#define SOUP_MTX_RAW 2    /* troublet's view of the files (T:283-334): every line kept (zeros and duplicates too), no locus filter or
+                          * re-index (n_loci = header rows), file order inside a cell; the min_* arguments are ignored */
 int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uint32_t min_alt, uint32_t min_ref,
                       uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags, soup_mtx** out);
 void soup_mtx_free(soup_mtx* m);
@@ -208,6 +210,47 @@ int32_t soup_mstep(soup_ctx* ctx, int32_t k, int32_t n_slots, int32_t lanes, con
 /* Device math self-test hook: applies the on-device ln / exp used by the kernels to n
  * host floats (parity check against the host libm the oracle uses). op 0 = ln, 1 = exp. */
 int32_t soup_device_math(soup_ctx* ctx, int32_t op, const float* in, float* out, uint64_t n);
+
+/* ------------------------------------------------------------------ troublet
+ * The doublet caller that consumes clusters_tmp.tsv and the same two matrices: /root/reference/troublet/src/main.rs ("T:"). */
+
+/* load_clusters T:414-449: `barcode \t cluster \t lp_0 .. lp_{k-1}` per line.  losses [n_cells][k] (f64), barcodes as one
+ * NUL-separated blob; free both with soup_free().  n_clusters = max of column 2, plus one (T:426,448). */
+int32_t soup_clusters_load(const char* path, char** barcode_blob, double** losses, uint64_t* n_cells, int32_t* k, int32_t* n_clusters);
+
+typedef struct soup_troublet_params {
+    double p_soup;             /* T:475-476: not a CLI flag of the reference, always 0.0 there */
+    double doublet_prior;      /* T:477-478, default 0.5 */
+    double doublet_threshold;  /* T:489-490, default 0.9 */
+    double singlet_threshold;  /* T:491-492, default 0.9 */
+} soup_troublet_params;
+#define SOUP_TROUBLET_SINGLET 0
+#define SOUP_TROUBLET_UNASSIGNED 1           /* best singlet beats best doublet, posterior below the threshold (T:183) */
+#define SOUP_TROUBLET_DOUBLET 2
+#define SOUP_TROUBLET_UNASSIGNED_DOUBLET 3   /* T:201 */
+typedef struct soup_troublet_result {   /* caller-allocated, [n_cells] each unless noted */
+    int32_t* status;
+    int32_t* best_singlet;     /* T:83-86 */
+    int32_t* doublet1;         /* T:127-131 */
+    int32_t* doublet2;
+    double* singlet_posterior; /* T:166 */
+    double* doublet_posterior; /* T:167 */
+    double* log_prob_singleton;
+    double* log_prob_doublet;
+    double* cluster_logprobs;  /* [n_cells][k] T:88-90 */
+    int32_t rounds;            /* passes of the `while any_removed > 0` loop T:46 */
+    uint64_t removed;          /* cells removed as doublets over all rounds */
+    double device_ms;          /* CUDA-event time of the singlet + doublet kernels, all rounds */
+} soup_troublet_result;
+/* call_doublets T:32-244 + the count tables of load_allele_data T:261-412 on the GPU.  The matrix is the RAW one
+ * (soup_mtx_load with SOUP_MTX_RAW: every line, no locus filter, file order inside a cell), `losses` the [n_cells][k]
+ * log-probability columns of the clusters file.  Per-cell sums are accumulated in file order in f64 like the reference;
+ * `ln` on the device is within 1 ulp of the host's, so log-probabilities agree to ~1e-13 relative, not bit for bit. */
+int32_t soup_troublet(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loci, uint64_t nnz, const uint64_t* row_ptr, const uint32_t* locus,
+                      const uint32_t* alt, const uint32_t* ref, const double* losses, int32_t k, int32_t n_clusters,
+                      const soup_troublet_params* p, soup_troublet_result* r, const char* barcode_blob, void* log_file);
+/* the TSV troublet prints (T:36-41, T:233-243), Rust `{}` formatting of f64 */
+int32_t soup_troublet_write(void* out_file, const char* barcode_blob, uint64_t n_cells, int32_t k, const soup_troublet_result* r);
 
 /* ------------------------------------------------------------------ driver */
 

@@ -32,7 +32,7 @@ EXPORTS = [
     "soup_known_genotypes_load", "soup_chacha_words", "soup_thread_seeds", "soup_format_f32", "soup_ln_binomial_f32", "soup_bad_cluster_detection",
     "soup_ctx_create", "soup_ctx_destroy", "soup_load_csr", "soup_get_dims", "soup_get_csc", "soup_get_cell_totals",
     "soup_get_csr_lbc", "soup_cluster_allele_counts", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
-    "soup_main", "soup_exchange_best", "soup_write_clusters",
+    "soup_main", "soup_exchange_best", "soup_write_clusters", "soup_clusters_load", "soup_troublet", "soup_troublet_write",
 ]
 
 
@@ -139,6 +139,10 @@ def lib():
         L.soup_exchange_best.argtypes = [C.c_int32, C.c_int32, ALLGATHER_FN, BCAST_FN, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32)]
         L.soup_write_clusters.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int32]
+        L.soup_clusters_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.soup_troublet.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
+        L.soup_troublet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -172,11 +176,14 @@ class CellCSR:
         return int(self.locus.shape[0])
 
 
-def load_mtx(alt_path, ref_path, min_alt=4, min_ref=4, min_alt_umis=0, min_ref_umis=0) -> CellCSR:
-    """load_cell_data S:601-681 (defaults S:764-767, 811-816)."""
+MTX_RAW = 2
+
+
+def load_mtx(alt_path, ref_path, min_alt=4, min_ref=4, min_alt_umis=0, min_ref_umis=0, raw=False) -> CellCSR:
+    """load_cell_data S:601-681 (defaults S:764-767, 811-816); raw=True: troublet's view of the files (SOUP_MTX_RAW)."""
     L = lib()
     m = C.POINTER(_Mtx)()
-    _check(L.soup_mtx_load(os.fsencode(alt_path), os.fsencode(ref_path), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, C.byref(m)))
+    _check(L.soup_mtx_load(os.fsencode(alt_path), os.fsencode(ref_path), min_alt, min_ref, min_alt_umis, min_ref_umis, MTX_RAW if raw else 0, C.byref(m)))
     try:
         s = m.contents
         n, nnz, nl = int(s.n_cells), int(s.nnz), int(s.n_loci)
@@ -241,6 +248,66 @@ def bad_cluster_detection(run: int, k: int, best_log_probs: np.ndarray):
     out = np.empty(max(k, 1), dtype=np.int32)
     n = _check(lib().soup_bad_cluster_detection(run, k, _ptr(lp), lp.shape[0] if lp.ndim == 2 else 0, _ptr(out), None))
     return out[:n].tolist()
+
+
+class _TroubletParams(C.Structure):
+    _fields_ = [("p_soup", C.c_double), ("doublet_prior", C.c_double), ("doublet_threshold", C.c_double), ("singlet_threshold", C.c_double)]
+
+
+class _TroubletResult(C.Structure):
+    _fields_ = [("status", C.c_void_p), ("best_singlet", C.c_void_p), ("doublet1", C.c_void_p), ("doublet2", C.c_void_p),
+                ("singlet_posterior", C.c_void_p), ("doublet_posterior", C.c_void_p), ("log_prob_singleton", C.c_void_p),
+                ("log_prob_doublet", C.c_void_p), ("cluster_logprobs", C.c_void_p), ("rounds", C.c_int32), ("removed", C.c_uint64),
+                ("device_ms", C.c_double)]
+
+
+def load_clusters(path):
+    """load_clusters T:414-449 -> (barcodes, losses f64 [n_cells][k], n_clusters)."""
+    L = lib()
+    blob, losses = C.c_void_p(), C.c_void_p()
+    n, k, nc = C.c_uint64(), C.c_int32(), C.c_int32()
+    _check(L.soup_clusters_load(os.fsencode(path), C.byref(blob), C.byref(losses), C.byref(n), C.byref(k), C.byref(nc)))
+    try:
+        names, off = [], 0
+        for _ in range(n.value):
+            sname = C.string_at(blob.value + off)
+            names.append(sname.decode())
+            off += len(sname) + 1
+        arr = np.ctypeslib.as_array(C.cast(losses, C.POINTER(C.c_double)), shape=(max(n.value * k.value, 1),))[:n.value * k.value]
+        return names, arr.reshape(n.value, k.value).copy(), nc.value
+    finally:
+        L.soup_free(blob)
+        L.soup_free(losses)
+
+
+def troublet(ctx, raw: "CellCSR", losses, n_clusters=None, barcodes=None, p_soup=0.0, doublet_prior=0.5, doublet_threshold=0.9,
+             singlet_threshold=0.9, out_path=None):
+    """call_doublets T:32-244 on the GPU over the RAW matrix (load_mtx(..., raw=True)).  Returns a dict of per-cell arrays."""
+    losses = np.ascontiguousarray(losses, dtype=np.float64)
+    n, k = losses.shape
+    assert n == raw.n_cells
+    p = _TroubletParams(p_soup, doublet_prior, doublet_threshold, singlet_threshold)
+    out = dict(status=np.zeros(n, np.int32), best_singlet=np.zeros(n, np.int32), doublet1=np.zeros(n, np.int32), doublet2=np.zeros(n, np.int32),
+               singlet_posterior=np.zeros(n), doublet_posterior=np.zeros(n), log_prob_singleton=np.zeros(n), log_prob_doublet=np.zeros(n),
+               cluster_logprobs=np.zeros((n, k)))
+    r = _TroubletResult(*[_ptr(out[f]) for f, _ in _TroubletResult._fields_[:9]])
+    blob = None if barcodes is None else b"".join(b.encode() + b"\0" for b in barcodes) + b"\0"
+    ctx._ck(lib().soup_troublet(ctx._h, raw.n_cells, raw.n_loci, raw.nnz, _ptr(raw.row_ptr), _ptr(raw.locus), _ptr(raw.alt), _ptr(raw.ref),
+                                        _ptr(losses), k, k if n_clusters is None else n_clusters, C.byref(p), C.byref(r), blob, None))
+    out.update(rounds=r.rounds, removed=int(r.removed), device_ms=float(r.device_ms))
+    if out_path is not None:
+        libc = C.CDLL(None)
+        libc.fopen.restype = C.c_void_p
+        libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+        libc.fclose.argtypes = [C.c_void_p]
+        f = libc.fopen(os.fsencode(out_path), b"w")
+        if not f:
+            raise OSError(f"cannot open {out_path}")
+        try:
+            _check(lib().soup_troublet_write(f, blob if blob is not None else b"\0" * (n + 1), n, k, C.byref(r)))
+        finally:
+            libc.fclose(f)
+    return out
 
 
 def write_clusters(path, barcodes, best_log_probs: np.ndarray):

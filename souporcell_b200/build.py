@@ -16,6 +16,7 @@ LIB_DIR = os.path.join(ROOT, "souporcell_b200", "lib")
 BIN_DIR = os.path.join(ROOT, "souporcell_b200", "bin")
 LIB = os.path.join(LIB_DIR, "libsoupgpu.so")
 CLI = os.path.join(BIN_DIR, "souporcell")
+TROUBLET_CLI = os.path.join(BIN_DIR, "troublet")
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 ORACLE_CLI = os.path.join(ORACLE_DIR, "_build", "souporcell_oracle")
@@ -28,7 +29,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-pthread",
 ]
 LIB_SOURCES = ["soup_device.cu", "host_loader.cpp", "host_util.cpp", "soup_driver.cpp"]
-LIB_HEADERS = ["soup_kernels.cuh", "soup_common.hpp", "glibc_flt32.h", os.path.join("..", "..", "include", "soupgpu.h")]
+LIB_HEADERS = ["soup_kernels.cuh", "troublet_kernels.cuh", "soup_common.hpp", "glibc_flt32.h", os.path.join("..", "..", "include", "soupgpu.h")]
 
 
 def _newer(target: str, deps) -> bool:
@@ -61,12 +62,16 @@ def build_cli(force: bool = False) -> str:
         os.makedirs(BIN_DIR, exist_ok=True)
         _run([NVCC, "-O2", "-std=c++17", "-Xcompiler", "-Wall", "-o", CLI, src, "-L" + LIB_DIR, "-lsoupgpu",
               "-Xlinker", "-rpath,$ORIGIN/../lib"])
+    tsrc = os.path.join(CSRC, "troublet_cli.cpp")
+    if force or _newer(TROUBLET_CLI, [tsrc, LIB]):
+        _run([NVCC, "-O2", "-std=c++17", "-Xcompiler", "-Wall", "-o", TROUBLET_CLI, tsrc, "-L" + LIB_DIR, "-lsoupgpu",
+              "-Xlinker", "-rpath,$ORIGIN/../lib"])
     return CLI
 
 
 def build_oracle(force: bool = False) -> str:
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle.cpp", "oracle_capi.cpp", "oracle_cli.cpp", "oracle.hpp", "Makefile")]
-    if force or _newer(ORACLE_LIB, srcs) or _newer(ORACLE_CLI, srcs):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle.cpp", "oracle_capi.cpp", "oracle_cli.cpp", "oracle.hpp", "troublet_oracle.cpp", "troublet_oracle.hpp", "Makefile")]
+    if force or _newer(ORACLE_LIB, srcs) or _newer(ORACLE_CLI, srcs) or _newer(os.path.join(ORACLE_DIR, "_build", "troublet_oracle"), srcs):
         _run(["make", "-C", ORACLE_DIR] + (["-B"] if force else []))
     return ORACLE_LIB
 

@@ -266,8 +266,9 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
     }
     std::vector<uint32_t> remap(total_loci, UINT32_MAX);
     std::vector<uint64_t> index_to_locus;
+    const bool raw = (flags & SOUP_MTX_RAW) != 0;
     for (uint64_t l = 0; l < total_loci; ++l)
-        if (seen[l] && cells_ref[l] >= min_ref && cells_alt[l] >= min_alt && umis_ref[l] >= min_ref_umis && umis_alt[l] >= min_alt_umis) {
+        if (raw || (seen[l] && cells_ref[l] >= min_ref && cells_alt[l] >= min_alt && umis_ref[l] >= min_ref_umis && umis_alt[l] >= min_alt_umis)) {
             remap[l] = (uint32_t)index_to_locus.size();
             index_to_locus.push_back(l);
         }
@@ -302,6 +303,7 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
                     for (uint64_t c = c0; c < std::min(total_cells, c0 + step); ++c) {
                         Ent* b = ents.data() + start[c];
                         Ent* e = ents.data() + start[c + 1];
+                        if (raw) { row_len[c] = (uint64_t)(e - b); continue; }   // T:334: every line, in file order
                         bool sorted = true;
                         for (Ent* q = b; q + 1 < e; ++q)
                             if (q[0].locus >= q[1].locus) { sorted = false; break; }

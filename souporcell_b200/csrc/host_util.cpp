@@ -117,6 +117,111 @@ int32_t soup_thread_seeds(uint8_t seed, uint32_t threads, uint32_t run, uint8_t*
     return SOUP_OK;
 }
 
+// ---- troublet host side: load_clusters T:414-449 and the TSV writer T:36-41, T:233-243
+static std::string format_f64(double v) {   // Rust `{}` for f64: shortest round-trip digits, never scientific
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    if (v == 0.0) return std::signbit(v) ? "-0" : "0";
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof(buf) - 1, v, std::chars_format::scientific);
+    *res.ptr = '\0';
+    const char* p = buf;
+    std::string out;
+    if (*p == '-') { out.push_back('-'); ++p; }
+    std::string digits;
+    const char* e = p;
+    while (e < res.ptr && *e != 'e') { if (*e != '.') digits.push_back(*e); ++e; }
+    const int exp10 = atoi(e + 1), nd = (int)digits.size();
+    if (exp10 >= 0) {
+        if (nd <= exp10 + 1) { out += digits; out.append((size_t)(exp10 + 1 - nd), '0'); }
+        else { out.append(digits, 0, (size_t)exp10 + 1); out.push_back('.'); out.append(digits, (size_t)exp10 + 1, std::string::npos); }
+    } else {
+        out += "0.";
+        out.append((size_t)(-exp10 - 1), '0');
+        out += digits;
+    }
+    return out;
+}
+
+int32_t soup_clusters_load(const char* path, char** barcode_blob, double** losses, uint64_t* n_cells, int32_t* k, int32_t* n_clusters) {
+    if (!path || !barcode_blob || !losses || !n_cells || !k || !n_clusters) { set_thread_error("soup_clusters_load: bad argument"); return SOUP_ERR_INVALID; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_thread_error("Unable to open file %s", path); return SOUP_ERR_IO; }
+    std::string content;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) content.append(buf, n);
+    fclose(f);
+    std::string blob;
+    std::vector<double> vals;
+    uint64_t cells = 0;
+    int32_t cols = -1;
+    uint64_t max_cluster = 0;
+    size_t pos = 0;
+    while (pos < content.size()) {
+        size_t e = content.find('\n', pos);
+        if (e == std::string::npos) e = content.size();
+        std::string line = content.substr(pos, e - pos);
+        pos = e + 1;
+        size_t b0 = line.find_first_not_of(" \t\r\n"), e0 = line.find_last_not_of(" \t\r\n");   // line.trim()
+        line = b0 == std::string::npos ? std::string() : line.substr(b0, e0 - b0 + 1);
+        std::vector<std::string> tok;
+        for (size_t q = 0;;) {
+            size_t t = line.find('\t', q);
+            tok.push_back(line.substr(q, t == std::string::npos ? std::string::npos : t - q));
+            if (t == std::string::npos) break;
+            q = t + 1;
+        }
+        if (tok.size() < 2) { set_thread_error("clusters file line %llu: index out of bounds: the len is %zu but the index is 1", (unsigned long long)cells + 1, tok.size()); return SOUP_ERR_INVALID; }
+        char* endp = nullptr;
+        const unsigned long long c1 = strtoull(tok[1].c_str(), &endp, 10);
+        if (tok[1].empty() || *endp) { set_thread_error("clusters file line %llu: cannot parse the cluster column", (unsigned long long)cells + 1); return SOUP_ERR_INVALID; }
+        max_cluster = std::max<uint64_t>(max_cluster, c1);
+        const int32_t here = (int32_t)tok.size() - 2;
+        if (cols < 0) cols = here;
+        if (here != cols) { set_thread_error("clusters file line %llu: %d log-probability columns, expected %d", (unsigned long long)cells + 1, here, cols); return SOUP_ERR_INVALID; }
+        for (size_t i = 2; i < tok.size(); ++i) {
+            const double v = strtod(tok[i].c_str(), &endp);
+            if (tok[i].empty() || *endp) { set_thread_error("clusters file line %llu: cannot parse '%s' as f64", (unsigned long long)cells + 1, tok[i].c_str()); return SOUP_ERR_INVALID; }
+            vals.push_back(v);
+        }
+        blob.append(tok[0]);
+        blob.push_back('\0');
+        ++cells;
+    }
+    *barcode_blob = (char*)malloc(std::max<size_t>(blob.size(), 1));
+    *losses = (double*)malloc(std::max<size_t>(vals.size(), 1) * sizeof(double));
+    if (!*barcode_blob || !*losses) { free(*barcode_blob); free(*losses); set_thread_error("out of memory"); return SOUP_ERR_NOMEM; }
+    memcpy(*barcode_blob, blob.data(), blob.size());
+    memcpy(*losses, vals.data(), vals.size() * sizeof(double));
+    *n_cells = cells; *k = cols < 0 ? 0 : cols; *n_clusters = (int32_t)max_cluster + 1;
+    return SOUP_OK;
+}
+
+int32_t soup_troublet_write(void* out_file, const char* barcode_blob, uint64_t n_cells, int32_t k, const soup_troublet_result* r) {
+    FILE* f = (FILE*)out_file;
+    if (!f || !barcode_blob || !r || k <= 0) { set_thread_error("soup_troublet_write: bad argument"); return SOUP_ERR_INVALID; }
+    static const char* NAME[4] = {"singlet", "unassigned", "doublet", "unassigned"};
+    std::string out = "barcode\tstatus\tassignment\tsinglet_posterior\tdoublet_posterior\tlog_prob_singleton\tlog_prob_doublet\t";
+    for (int32_t c = 0; c < k; ++c) { out += "cluster" + std::to_string(c); out += c + 1 == k ? "\n" : "\t"; }
+    const char* q = barcode_blob;
+    for (uint64_t cell = 0; cell < n_cells; ++cell) {
+        out += q;
+        q += strlen(q) + 1;
+        const int st = r->status[cell];
+        out += "\t"; out += NAME[st & 3]; out += "\t";
+        if (st == SOUP_TROUBLET_SINGLET || st == SOUP_TROUBLET_UNASSIGNED) out += std::to_string(r->best_singlet[cell]);
+        else out += std::to_string(r->doublet1[cell]) + "/" + std::to_string(r->doublet2[cell]);
+        out += "\t" + format_f64(r->singlet_posterior[cell]) + "\t" + format_f64(r->doublet_posterior[cell]) + "\t" +
+               format_f64(r->log_prob_singleton[cell]) + "\t" + format_f64(r->log_prob_doublet[cell]) + "\t";
+        for (int32_t c = 0; c < k; ++c) { out += format_f64(r->cluster_logprobs[cell * (uint64_t)k + c]); if (c + 1 < k) out += "\t"; }
+        out += "\n";
+        if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), f); out.clear(); }
+    }
+    fwrite(out.data(), 1, out.size(), f);
+    return ferror(f) ? SOUP_ERR_IO : SOUP_OK;
+}
+
 int32_t soup_format_f32(float v, int32_t width8, char* buf, int32_t buflen) {
     std::string s = width8 ? format_f32_w8(v) : format_f32(v);
     if (!buf || (int32_t)s.size() + 1 > buflen) { set_thread_error("soup_format_f32: buffer too small"); return SOUP_ERR_INVALID; }

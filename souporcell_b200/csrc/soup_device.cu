@@ -1220,3 +1220,170 @@ extern "C" int32_t soup_device_math(soup_ctx* ctx, int32_t op, const float* in, 
     if (e != cudaSuccess) return ctx->fail(SOUP_ERR_CUDA, "soup_device_math: %s", cudaGetErrorString(e));
     return SOUP_OK;
 }
+
+// ------------------------------------------------------------------ troublet: call_doublets T:32-244 on the GPU
+#include "troublet_kernels.cuh"
+
+extern "C" int32_t soup_troublet(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loci, uint64_t nnz, const uint64_t* row_ptr, const uint32_t* locus,
+                                 const uint32_t* alt, const uint32_t* ref, const double* losses, int32_t k, int32_t n_clusters,
+                                 const soup_troublet_params* p, soup_troublet_result* r, const char* barcode_blob, void* log_file) {
+    using namespace troublet_dev;
+    if (!ctx) return SOUP_ERR_INVALID;
+    if (!row_ptr || !losses || !p || !r || k <= 0 || (nnz && (!locus || !alt || !ref))) return ctx->fail(SOUP_ERR_INVALID, "soup_troublet: bad argument");
+    if (!r->status || !r->best_singlet || !r->doublet1 || !r->doublet2 || !r->singlet_posterior || !r->doublet_posterior || !r->log_prob_singleton ||
+        !r->log_prob_doublet || !r->cluster_logprobs)
+        return ctx->fail(SOUP_ERR_INVALID, "soup_troublet: every result array must be allocated by the caller");
+    // the reference keys its count tables by clusters 0..=max(column 2) and indexes them with the loss columns (T:33, T:61): a loss column
+    // beyond them is `unwrap()` on None
+    if (k > n_clusters) return ctx->fail(SOUP_ERR_INVALID, "called `Option::unwrap()` on a `None` value (more log-probability columns than clusters)");
+    if (n_cells >= (1ull << 31) || n_loci >= (1ull << 31)) return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_troublet: more than 2^31 cells / loci");
+    CK(cudaSetDevice(ctx->device));
+    FILE* log = (FILE*)log_file;
+    cudaStream_t st = ctx->stream;
+    const int K = k;
+    const size_t N = n_cells, L = std::max<uint64_t>(n_loci, 1);
+    std::vector<const char*> names(N, "");
+    if (barcode_blob) { const char* q = barcode_blob; for (size_t c = 0; c < N; ++c) { names[c] = q; q += strlen(q) + 1; } }
+
+    // load_clusters' best index = the singlet_assignment of T:154-160: first maximum of the loss columns
+    std::vector<int32_t> cluster(N, 0);
+    for (size_t c = 0; c < N; ++c) {
+        double best = -10000000000.0;   // T:427
+        int bi = 0;
+        for (int j = 0; j < K; ++j) if (losses[c * K + j] > best) { best = losses[c * K + j]; bi = j; }
+        cluster[c] = bi;
+    }
+
+    struct Bufs {
+        uint64_t* row_ptr = nullptr; uint32_t *locus = nullptr, *ref = nullptr, *alt = nullptr, *lines = nullptr, *removed = nullptr;
+        int32_t *cluster = nullptr, *pairs = nullptr;
+        unsigned long long *S0 = nullptr, *A = nullptr;
+        double *soup = nullptr, *sing = nullptr, *dbl = nullptr;
+        ~Bufs() { for (void* q : {(void*)row_ptr, (void*)locus, (void*)ref, (void*)alt, (void*)lines, (void*)removed, (void*)cluster, (void*)pairs, (void*)S0, (void*)A, (void*)soup, (void*)sing, (void*)dbl}) cudaFree(q); }
+    } b;
+#define CKT(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) { cudaGetLastError(); return ctx->fail(e_ == cudaErrorMemoryAllocation ? SOUP_ERR_NOMEM : SOUP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    const size_t nz = std::max<uint64_t>(nnz, 1), tab = L * (size_t)K * 2;
+    CKT(cudaMalloc(&b.row_ptr, (N + 1) * 8)); CKT(cudaMalloc(&b.locus, nz * 4)); CKT(cudaMalloc(&b.ref, nz * 4)); CKT(cudaMalloc(&b.alt, nz * 4));
+    CKT(cudaMalloc(&b.lines, L * 4)); CKT(cudaMalloc(&b.removed, std::max<size_t>(N, 1) * 4)); CKT(cudaMalloc(&b.cluster, std::max<size_t>(N, 1) * 4));
+    CKT(cudaMalloc(&b.pairs, std::max<size_t>(N, 1) * PAIRS * 2 * 4)); CKT(cudaMalloc(&b.S0, tab * 8)); CKT(cudaMalloc(&b.A, tab * 8));
+    CKT(cudaMalloc(&b.soup, L * 8)); CKT(cudaMalloc(&b.sing, std::max<size_t>(N, 1) * K * 8)); CKT(cudaMalloc(&b.dbl, std::max<size_t>(N, 1) * PAIRS * 8));
+    CKT(cudaMemcpyAsync(b.row_ptr, row_ptr, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CKT(cudaMemcpyAsync(b.locus, locus, nnz * 4, cudaMemcpyHostToDevice, st));
+        CKT(cudaMemcpyAsync(b.ref, ref, nnz * 4, cudaMemcpyHostToDevice, st));
+        CKT(cudaMemcpyAsync(b.alt, alt, nnz * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (N) CKT(cudaMemcpyAsync(b.cluster, cluster.data(), N * 4, cudaMemcpyHostToDevice, st));
+    CKT(cudaMemsetAsync(b.lines, 0, L * 4, st));
+    CKT(cudaMemsetAsync(b.S0, 0, tab * 8, st));
+    {   // statrs tables with the HOST libm (FCACHE[n].ln())
+        double lf[171], f = 1.0;
+        lf[0] = std::log(1.0);
+        for (int i = 1; i <= 170; ++i) { f *= (double)i; lf[i] = std::log(f); }
+        static const double dk[11] = {2.48574089138753565546e-5, 1.05142378581721974210, -3.45687097222016235469, 4.51227709466894823700,
+                                      -2.98285225323576655721, 1.05639711577126713077, -1.95428773191645869583e-1, 1.70970543404441224307e-2,
+                                      -5.71926117404305781283e-4, 4.63399473359905636708e-6, -2.71994908488607703910e-9};
+        CKT(cudaMemcpyToSymbolAsync(c_ln_fact, lf, sizeof(lf), 0, cudaMemcpyHostToDevice, st));
+        CKT(cudaMemcpyToSymbolAsync(c_gamma_dk, dk, sizeof(dk), 0, cudaMemcpyHostToDevice, st));
+    }
+    if (N) tally_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(b.row_ptr, b.locus, b.ref, b.alt, b.cluster, b.S0, b.lines, (uint32_t)N, K);
+    soup_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(b.S0, b.soup, (uint32_t)L, K);
+    CKT(cudaMemcpyAsync(b.A, b.S0, tab * 8, cudaMemcpyDeviceToDevice, st));
+    CKT(cudaGetLastError());
+
+    Args a{b.row_ptr, b.locus, b.ref, b.alt, b.S0, b.A, b.soup, b.lines, (uint32_t)N, K, 0,
+           Consts{p->p_soup, std::log(1.0 - p->doublet_prior), std::log(p->doublet_prior), 20u}};
+    std::vector<double> sing(N * (size_t)K), dbl(N * (size_t)PAIRS);
+    std::vector<int32_t> pairs(N * (size_t)PAIRS * 2);
+    std::vector<uint8_t> all_removed(N, 0);
+    std::vector<uint32_t> new_removed;
+    auto lse = [](const double* x, int n) {   // log_sum_exp T:246-250 (host libm, as the reference)
+        double m = -INFINITY;
+        for (int i = 0; i < n; ++i) m = (x[i] > m || std::isnan(m)) ? x[i] : m;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += std::exp(x[i] - m);
+        return m + std::log(s);
+    };
+    r->rounds = 0; r->removed = 0; r->device_ms = 0;
+    size_t any_removed = 1;
+    while (any_removed > 0) {   // T:46
+        a.round = r->rounds;
+        r->rounds += 1;
+        CKT(cudaEventRecord(ctx->ev0, st));
+        if (N) singlet_kernel<<<(unsigned)((N * K + 127) / 128), 128, 0, st>>>(a, b.sing);
+        CKT(cudaMemcpyAsync(sing.data(), b.sing, sing.size() * 8, cudaMemcpyDeviceToHost, st));
+        CKT(cudaStreamSynchronize(st));
+        CKT(cudaGetLastError());
+        // T:88-92: stable descending sort of the singlets, the pairs among the top four
+        std::vector<std::pair<double, int>> order(K);
+        for (size_t c = 0; c < N; ++c) {
+            for (int j = 0; j < K; ++j) {
+                if (std::isnan(sing[c * K + j])) return ctx->fail(SOUP_ERR_INVALID, "called `Option::unwrap()` on a `None` value (NaN log-probability, T:90)");
+                order[j] = {sing[c * K + j], j};
+            }
+            std::stable_sort(order.begin(), order.end(), [](const auto& x, const auto& y) { return -x.first < -y.first; });
+            const int top = std::min(K, 4);
+            int q = 0;
+            for (int i = 0; i < top; ++i)
+                for (int j = i + 1; j < top; ++j, ++q) { pairs[(c * PAIRS + q) * 2] = order[i].second; pairs[(c * PAIRS + q) * 2 + 1] = order[j].second; }
+            for (; q < PAIRS; ++q) pairs[(c * PAIRS + q) * 2] = pairs[(c * PAIRS + q) * 2 + 1] = -1;
+        }
+        if (N) {
+            CKT(cudaMemcpyAsync(b.pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, st));
+            doublet_kernel<<<(unsigned)((N * PAIRS + 127) / 128), 128, 0, st>>>(a, b.pairs, b.dbl);
+            CKT(cudaMemcpyAsync(dbl.data(), b.dbl, dbl.size() * 8, cudaMemcpyDeviceToHost, st));
+        }
+        CKT(cudaEventRecord(ctx->ev1, st));
+        CKT(cudaStreamSynchronize(st));
+        CKT(cudaGetLastError());
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            r->device_ms += ms;
+        }
+        new_removed.clear();
+        for (size_t c = 0; c < N; ++c) {
+            int best_singlet = 0, d1 = 0, d2 = 0;
+            double best_s = -INFINITY, best_d = -INFINITY;
+            for (int j = 0; j < K; ++j) if (sing[c * K + j] > best_s) { best_s = sing[c * K + j]; best_singlet = j; }   // T:83-86
+            for (int q = 0; q < PAIRS; ++q)
+                if (pairs[(c * PAIRS + q) * 2] >= 0 && dbl[c * PAIRS + q] > best_d) { best_d = dbl[c * PAIRS + q]; d1 = pairs[(c * PAIRS + q) * 2]; d2 = pairs[(c * PAIRS + q) * 2 + 1]; }   // T:127-131
+            const double dq[2] = {best_s, best_d};
+            const double dq_denom = lse(dq, 2);                                   // T:145-151
+            double top_singlet = -INFINITY;
+            int singlet_assignment = 0;
+            for (int j = 0; j < K; ++j) if (losses[c * K + j] > top_singlet) { top_singlet = losses[c * K + j]; singlet_assignment = j; }   // T:154-160
+            const double sq_denom = lse(losses + c * K, K);
+            const double sp = std::exp(top_singlet - sq_denom), dp = std::exp(best_d - dq_denom);   // T:166-167
+            int status;
+            if (best_s > best_d) status = sp > p->singlet_threshold ? SOUP_TROUBLET_SINGLET : SOUP_TROUBLET_UNASSIGNED;   // T:169-184
+            else if (dp >= p->doublet_threshold) {                                                                          // T:186-195
+                if (!all_removed[c]) {
+                    all_removed[c] = 1;
+                    new_removed.push_back((uint32_t)c);
+                    if (log) fprintf(log, "removing %s as doublet\n", names[c]);
+                }
+                status = SOUP_TROUBLET_DOUBLET;
+            } else status = SOUP_TROUBLET_UNASSIGNED_DOUBLET;
+            r->status[c] = status; r->best_singlet[c] = best_singlet; r->doublet1[c] = d1; r->doublet2[c] = d2;
+            r->singlet_posterior[c] = sp; r->doublet_posterior[c] = dp; r->log_prob_singleton[c] = best_s; r->log_prob_doublet[c] = best_d;
+            if (singlet_assignment != best_singlet && !all_removed[c] && log) fprintf(log, "error\t%s\t%d\t%d\n", names[c], singlet_assignment, best_singlet);   // T:205-209
+        }
+        memcpy(r->cluster_logprobs, sing.data(), sing.size() * 8);
+        if (log) fprintf(log, "%zu cells removed this round\n", new_removed.size());   // T:216
+        any_removed = new_removed.size();
+        r->removed += new_removed.size();
+        if (any_removed) {   // T:218-236: the removed cells leave their cluster's counts; the fractions follow (computed on the fly from A)
+            CKT(cudaMemcpyAsync(b.removed, new_removed.data(), new_removed.size() * 4, cudaMemcpyHostToDevice, st));
+            remove_kernel<<<(unsigned)((new_removed.size() + 7) / 8), 256, 0, st>>>(b.row_ptr, b.locus, b.ref, b.alt, b.cluster, b.removed, (uint32_t)new_removed.size(), b.A, K);
+            CKT(cudaStreamSynchronize(st));
+            CKT(cudaGetLastError());
+        }
+    }
+#undef CKT
+    return SOUP_OK;
+}

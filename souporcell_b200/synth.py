@@ -46,9 +46,16 @@ class Vartrix:
 
 
 def generate(n_cells: int, n_loci: int, k: int, mean_loci: float, max_loci: int = 2048, seed: int = BASE_SEED,
-             **_unused) -> Vartrix:
+             doublet_frac: float = 0.0, **_unused) -> Vartrix:
+    """`doublet_frac` > 0 turns that fraction of the cells into inter-donor doublets (genotype = mean of two donors; for the
+    troublet tests).  They are drawn from a separate generator, so doublet_frac = 0 reproduces the historical data bit for bit."""
     rng = np.random.default_rng(seed)
     donor = rng.integers(0, k, size=n_cells).astype(np.int32)
+    donor2 = donor.copy()
+    if doublet_frac > 0 and k > 1:
+        rng2 = np.random.default_rng(seed + 777)
+        dbl = rng2.random(n_cells) < doublet_frac
+        donor2[dbl] = (donor[dbl] + rng2.integers(1, k, size=int(dbl.sum()))) % k
     f = np.clip(rng.beta(0.5, 0.5, size=n_loci), 0.05, 0.95)
     geno = rng.binomial(2, f[None, :].repeat(k, axis=0)) / 2.0            # [k][L] in {0, .5, 1}
     w = np.arange(1, n_loci + 1, dtype=np.float64) ** -0.8
@@ -73,7 +80,7 @@ def generate(n_cells: int, n_loci: int, k: int, mean_loci: float, max_loci: int 
         cell, locus = cell[keep], locus[keep]
     depth = rng.geometric(0.7, size=cell.shape[0])
     eps = 0.01
-    g = geno[donor[cell], locus]
+    g = geno[donor[cell], locus] if doublet_frac <= 0 else 0.5 * (geno[donor[cell], locus] + geno[donor2[cell], locus])
     p_alt = 0.95 * (g * (1 - 2 * eps) + eps) + 0.05 * f[locus]
     alt = rng.binomial(depth, p_alt).astype(np.uint32)
     ref = (depth - alt).astype(np.uint32)

@@ -1,0 +1,159 @@
+"""troublet (/root/reference/troublet/src/main.rs "T:"): the CPU restatement (oracle/troublet_oracle.cpp), the host
+pieces of libsoupgpu, and — on a GPU — soup_troublet / the `troublet` CLI against the oracle.
+
+The reference holds no fixture for troublet and its third-party arithmetic (statrs ln_gamma / ln_binomial) is restated from the
+published source: PARITY UNPINNED.  f64 tolerance: the device `log` is within 1 ulp of the host's, sums run over a few hundred
+terms, so log-probabilities are compared at 1e-10 relative; calls (status / assignment) must be identical except where a
+posterior sits within 1e-9 of a threshold."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import souporcell_b200 as sp
+from souporcell_b200 import build, synth
+from oracle import oracle_py as orc
+
+TRB_LIB = os.path.join(os.path.dirname(orc.CLI_PATH), "libtroublet_oracle.so")
+TRB_CLI = os.path.join(os.path.dirname(orc.CLI_PATH), "troublet_oracle")
+
+
+def trb():
+    orc.build()
+    L = C.CDLL(TRB_LIB)
+    L.trb_ln_gamma.restype = C.c_double
+    L.trb_ln_gamma.argtypes = [C.c_double]
+    L.trb_ln_binomial.restype = C.c_double
+    L.trb_ln_binomial.argtypes = [C.c_uint64, C.c_uint64]
+    L.trb_run.restype = C.c_int64
+    return L
+
+
+def oracle_run(alt, ref, clusters, n, k, **kw):
+    L = trb()
+    out = dict(status=np.zeros(n, np.int32), best_singlet=np.zeros(n, np.int32), doublet1=np.zeros(n, np.int32), doublet2=np.zeros(n, np.int32),
+               singlet_posterior=np.zeros(n), doublet_posterior=np.zeros(n), log_prob_singleton=np.zeros(n), log_prob_doublet=np.zeros(n),
+               cluster_logprobs=np.zeros((n, k)))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ko, rounds, removed = C.c_int32(), C.c_int32(), C.c_int64()
+    err = C.create_string_buffer(256)
+    L.trb_run.argtypes = [C.c_char_p] * 3 + [C.c_double] * 4 + [C.c_int64, C.c_int32] + [C.c_void_p] * 9 + [C.POINTER(C.c_int32)] * 2 + [C.POINTER(C.c_int64), C.c_char_p, C.c_int32]
+    rc = L.trb_run(os.fsencode(alt), os.fsencode(ref), os.fsencode(clusters), kw.get("p_soup", 0.0), kw.get("doublet_prior", 0.5),
+                   kw.get("doublet_threshold", 0.9), kw.get("singlet_threshold", 0.9), n, k, *[p(out[f]) for f in
+                   ("status", "best_singlet", "doublet1", "doublet2", "singlet_posterior", "doublet_posterior", "log_prob_singleton", "log_prob_doublet", "cluster_logprobs")],
+                   C.byref(ko), C.byref(rounds), C.byref(removed), err, 256)
+    if rc < 0:
+        raise RuntimeError(err.value.decode())
+    out.update(rounds=rounds.value, removed=removed.value)
+    return out
+
+
+@pytest.fixture(scope="module")
+def dataset(tmp_path_factory):
+    """A small matrix with 12 % inter-donor doublets, clustered by the CPU oracle of the clustering step (clusters_tmp.tsv)."""
+    d = str(tmp_path_factory.mktemp("trb"))
+    v = synth.generate(n_cells=500, n_loci=2500, k=4, mean_loci=220, seed=31, doublet_frac=0.12)
+    alt, ref, bc = synth.write_files(v, d)
+    orc.build()
+    r = subprocess.run([orc.CLI_PATH, "-a", alt, "-r", ref, "-b", bc, "-k", "4", "--restarts", "6", "-t", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-300:]
+    clusters = os.path.join(d, "clusters_tmp.tsv")
+    with open(clusters, "w") as fh:
+        fh.write(r.stdout)
+    return dict(alt=alt, ref=ref, clusters=clusters, v=v)
+
+
+# ------------------------------------------------------------------ CPU: oracle + host logic
+def test_statrs_restatement_against_math():
+    L = trb()
+    for x in [1.0, 1.5, 2.0, 3.25, 10.0, 57.3, 171.0, 1234.5, 1e5]:
+        assert L.trb_ln_gamma(x) == pytest.approx(math.lgamma(x), rel=1e-13, abs=1e-14)
+    for n, k in [(0, 0), (1, 0), (1, 1), (5, 2), (40, 17), (170, 85), (171, 3), (400, 200)]:
+        want = math.lgamma(n + 1) - math.lgamma(k + 1) - math.lgamma(n - k + 1)
+        assert L.trb_ln_binomial(n, k) == pytest.approx(want, rel=1e-12, abs=1e-12)
+    assert L.trb_ln_binomial(3, 4) == -math.inf
+
+
+def test_clusters_loader_and_raw_matrix(dataset):
+    names, losses, n_clusters = sp.load_clusters(dataset["clusters"])
+    lines = open(dataset["clusters"]).read().splitlines()
+    assert len(names) == len(lines) == dataset["v"].n_cells and n_clusters == 4
+    for i in (0, 7, len(lines) - 1):
+        tok = lines[i].split("\t")
+        assert names[i] == tok[0] and np.array_equal(losses[i], np.array([float(t) for t in tok[2:]]))
+    raw = sp.load_mtx(dataset["alt"], dataset["ref"], raw=True)
+    v = dataset["v"]
+    assert raw.n_loci == v.n_loci and raw.nnz == v.nnz          # no filter, every line
+    order = np.lexsort((v.locus, v.cell))                        # file order is (locus, cell): per cell, ascending locus
+    assert np.array_equal(raw.locus, v.locus[order].astype(np.uint32)) and np.array_equal(raw.alt, v.alt[order]) and np.array_equal(raw.ref, v.ref[order])
+
+
+def test_oracle_calls_doublets_and_iterates(dataset):
+    v = dataset["v"]
+    got = oracle_run(dataset["alt"], dataset["ref"], dataset["clusters"], v.n_cells, 4)
+    assert got["rounds"] >= 2 and got["removed"] > 0                  # at least one removal round, then a clean one
+    assert (got["status"] == 2).sum() == got["removed"]
+    # the doublet posterior is a two-way softmax of the best singlet and the best doublet (T:145-167)
+    m = np.maximum(got["log_prob_singleton"], got["log_prob_doublet"])
+    lse = m + np.log(np.exp(got["log_prob_singleton"] - m) + np.exp(got["log_prob_doublet"] - m))
+    np.testing.assert_allclose(got["doublet_posterior"], np.exp(got["log_prob_doublet"] - lse), rtol=1e-12)
+    assert np.array_equal(got["best_singlet"], np.argmax(got["cluster_logprobs"], axis=1))
+
+
+def test_oracle_cli_output_shape(dataset):
+    r = subprocess.run([TRB_CLI, "--alts", dataset["alt"], "--refs", dataset["ref"], "--clusters", dataset["clusters"]], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-300:]
+    rows = r.stdout.splitlines()
+    assert rows[0].split("\t")[:7] == ["barcode", "status", "assignment", "singlet_posterior", "doublet_posterior", "log_prob_singleton", "log_prob_doublet"]
+    assert len(rows) == dataset["v"].n_cells + 1 and all(len(x.split("\t")) == 7 + 4 for x in rows[1:])
+    assert "cells removed this round" in r.stderr
+
+
+# ------------------------------------------------------------------ GPU: parity with the oracle
+def _compare(got, want, thresholds=(0.9, 0.9)):
+    assert got["rounds"] == want["rounds"] and got["removed"] == want["removed"]
+    np.testing.assert_allclose(got["cluster_logprobs"], want["cluster_logprobs"], rtol=1e-10)
+    np.testing.assert_allclose(got["log_prob_singleton"], want["log_prob_singleton"], rtol=1e-10)
+    np.testing.assert_allclose(got["log_prob_doublet"], want["log_prob_doublet"], rtol=1e-10)
+    np.testing.assert_allclose(got["singlet_posterior"], want["singlet_posterior"], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(got["doublet_posterior"], want["doublet_posterior"], rtol=1e-7, atol=1e-300)
+    edge = (np.abs(want["singlet_posterior"] - thresholds[1]) < 1e-9) | (np.abs(want["doublet_posterior"] - thresholds[0]) < 1e-9) | \
+           (np.abs(want["log_prob_singleton"] - want["log_prob_doublet"]) < 1e-9 * np.abs(want["log_prob_singleton"]))
+    for f in ("status", "best_singlet", "doublet1", "doublet2"):
+        assert np.array_equal(got[f][~edge], want[f][~edge]), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [{}, {"doublet_prior": 0.2, "doublet_threshold": 0.8, "singlet_threshold": 0.95}])
+def test_gpu_troublet_matches_oracle(dataset, kw):
+    v = dataset["v"]
+    want = oracle_run(dataset["alt"], dataset["ref"], dataset["clusters"], v.n_cells, 4, **kw)
+    names, losses, n_clusters = sp.load_clusters(dataset["clusters"])
+    raw = sp.load_mtx(dataset["alt"], dataset["ref"], raw=True)
+    with sp.Context(0) as ctx:
+        got = sp.troublet(ctx, raw, losses, n_clusters=n_clusters, barcodes=names, **kw)
+    assert want["removed"] > 0
+    _compare(got, want, (kw.get("doublet_threshold", 0.9), kw.get("singlet_threshold", 0.9)))
+    assert got["device_ms"] > 0
+
+
+@pytest.mark.gpu
+def test_gpu_troublet_cli_matches_oracle_cli(dataset):
+    args = ["--alts", dataset["alt"], "--refs", dataset["ref"], "--clusters", dataset["clusters"]]
+    ours = subprocess.run([build.TROUBLET_CLI] + args, capture_output=True, text=True)
+    theirs = subprocess.run([TRB_CLI] + args, capture_output=True, text=True)
+    assert ours.returncode == 0 and theirs.returncode == 0, ours.stderr[-400:] + theirs.stderr[-400:]
+    a, b = ours.stdout.splitlines(), theirs.stdout.splitlines()
+    assert a[0] == b[0] and len(a) == len(b)
+    same_calls = 0
+    for x, y in zip(a[1:], b[1:]):
+        tx, ty = x.split("\t"), y.split("\t")
+        assert tx[0] == ty[0]
+        same_calls += tx[1:3] == ty[1:3]
+        np.testing.assert_allclose([float(t) for t in tx[5:]], [float(t) for t in ty[5:]], rtol=1e-10)
+    assert same_calls >= len(a) - 2                     # a call may differ only for a posterior sitting on a threshold
+    pick = lambda s: sorted(l for l in s.splitlines() if l.startswith("removing") or "cells removed" in l)
+    assert pick(ours.stderr) == pick(theirs.stderr)
