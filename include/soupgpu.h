@@ -97,7 +97,7 @@ int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx** out);
 void soup_ctx_destroy(soup_ctx* ctx);
 
 /* Upload the filtered CSR (host pointers; what load_cell_data returns as Vec<CellData>,
- * S:663-674) and build on the GPU: packed 8-byte entries, the CSC transpose (cells
+ * S:663-674) and build on the GPU: one packed 32-bit word per entry (+ side records for large counts), the CSC transpose (cells
  * ascending inside a locus = the order update_centers_average S:476-483 accumulates in),
  * per-cell total_alleles (S:671, f32, ascending locus) and the ln_binomial table (S:669). */
 int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loci, uint64_t nnz, const uint64_t* row_ptr,
@@ -142,7 +142,8 @@ typedef struct soup_solve_params {
     int32_t n_reinit;          /* 0 = run 0: draw all k, lock nothing */
     int32_t iteration_cap;     /* 0 -> 1000 (S:222) */
     int32_t max_slots;         /* solves resident on the GPU at once; 0 = auto */
-    int32_t lanes;             /* columns per lane (1, 2, 4); 0 = auto */
+    int32_t lanes;             /* tests: force this many columns per lane (1, 2, 4, 8, 16) in every group and switch the run-time
+                                * narrowing off; 0 = auto */
     int32_t record_counts;     /* also record clusters-with->200-cells per iteration (S:252-263) */
     int32_t keep_trace;        /* copy the per-iteration trace back (soup_get_trace) */
     int32_t poll_chunk;        /* iterations enqueued between host polls of the done counter; 0 = 4 */

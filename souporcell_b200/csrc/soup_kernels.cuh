@@ -2,16 +2,17 @@
 //
 // Layout in HBM.  A *column* is one (slot, cluster) pair, col = slot*K + k; a
 // *slot* is one resident solve (one em()/khm() call, S:189/S:280).  Columns are padded to a
-// multiple of the group width GW = 32*V (V = columns per lane, 1/2/4).
-//   LA, LB, TH : [L][Cpad] f32   ln(theta), ln(1-theta), theta          (row = used locus)
+// multiple of the group width GW = 32*V (V = columns per lane: 1, 2, 4, 8 or 16).
+//   LA | LB    : [2L][Cpad] f32  ONE joint table: rows [0, L) ln(theta), rows [L, 2L) ln(1-theta)   (row = used locus)
+//   TH         : [L][Cpad] f32   theta
 //   ELL, W     : [N][Cpad] f32   per-cell log-likelihoods, M-step weights (row = cell)
 //   LSE        : [slots][N] f32  per-cell log_sum_exp (S:230)
-//   csr_idx    : [nnz] u32 alt|ref|locus packed       rows = cells, loci ascending;  csr_aux [nnz] float4 {alt, ref, ln_binomial, 0}
-//   csc_idx    : [nnz] u32 alt|alt+ref|cell packed    cols = loci, cells ascending;  csc_aux [nnz] float2 {alt, alt+ref}
-//   (the side records are only read for counts that do not fit the packed fields)
-// One warp owns one (row, column-group) pair and walks the row's entries strictly in order,
-// so every (cell,k) / (locus,k) sum is accumulated in the reference's own order (S:415-418,
-// S:476-483) and the results are bit-identical to the scalar code; lanes never exchange data.
+//   csr_idx    : [nnz] u32 entry words, rows = cells, loci ascending;  csr_aux [nnz] float4 {alt, ref, ln_binomial, 0}
+//   csc_idx    : [nnz] u32 entry words, cols = loci, cells ascending;  csc_aux [nnz] float2 {alt, alt+ref}
+//   (entry words: see "entry words" below; the side records are only read for counts that do not fit the packed fields)
+// One owner per (row, column) chain — a warp lane in estep_kernel / mstep_kernel, a thread in mstep_long_kernel — walks the
+// row's entries strictly in order, so every (cell,k) / (locus,k) sum is accumulated in the reference's own order (S:415-418,
+// S:476-483) and the results are bit-identical to the scalar code; columns never exchange data.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
