@@ -1314,7 +1314,7 @@ extern "C" int32_t soup_troublet(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
         a.round = r->rounds;
         r->rounds += 1;
         CKT(cudaEventRecord(ctx->ev0, st));
-        if (N) singlet_kernel<<<(unsigned)((N * K + 127) / 128), 128, 0, st>>>(a, b.sing);
+        if (N) singlet_kernel<<<(unsigned)((N * K + 3) / 4), 128, 0, st>>>(a, b.sing);   // one warp per (cell, cluster)
         CKT(cudaMemcpyAsync(sing.data(), b.sing, sing.size() * 8, cudaMemcpyDeviceToHost, st));
         CKT(cudaStreamSynchronize(st));
         CKT(cudaGetLastError());
@@ -1334,7 +1334,7 @@ extern "C" int32_t soup_troublet(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
         }
         if (N) {
             CKT(cudaMemcpyAsync(b.pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, st));
-            doublet_kernel<<<(unsigned)((N * PAIRS + 127) / 128), 128, 0, st>>>(a, b.pairs, b.dbl);
+            doublet_kernel<<<(unsigned)((N * PAIRS + 3) / 4), 128, 0, st>>>(a, b.pairs, b.dbl);   // one warp per (cell, pair)
             CKT(cudaMemcpyAsync(dbl.data(), b.dbl, dbl.size() * 8, cudaMemcpyDeviceToHost, st));
         }
         CKT(cudaEventRecord(ctx->ev1, st));

@@ -42,52 +42,75 @@ struct Args {
     Consts c;
 };
 
+// A warp owns one (cell, cluster) or (cell, pair) sum.  Its lanes evaluate the terms of 32 consecutive entries in parallel (the
+// expensive part: six Lanczos ln_gamma each), then the terms are added to the running sum one by one in entry order, so the f64
+// sum is the reference's sequential `log_prob += ...` (T:82, T:125) — a skipped locus contributes +0.0, which changes nothing.
+__device__ __forceinline__ double ordered_add(double lp, double term) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) lp += __shfl_sync(0xffffffffu, term, i);
+    return lp;
+}
+
 // counts[(c1, c2)] of the reference's K x K tables, never materialised: (c, c) = A[c]; (a, b) = A[a] + S0[b]  (T:305-313, T:219-222)
-__global__ void singlet_kernel(Args a, double* __restrict__ out /*[N][K]*/) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) singlet_kernel(Args a, double* __restrict__ out /*[N][K]*/) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp = (cell, cluster), cluster fastest
     if (i >= (uint64_t)a.N * a.K) return;
-    const uint32_t cell = (uint32_t)(i / a.K);
+    const uint32_t cell = (uint32_t)(i / a.K), lane = threadIdx.x & 31;
     const int c = (int)(i - (uint64_t)cell * a.K);
     double lp = a.c.ln_singlet_prior;
-    for (uint64_t j = a.row_ptr[cell]; j < a.row_ptr[cell + 1]; ++j) {
-        const uint32_t l = a.locus[j];
-        if (a.locus_lines[l] < a.c.min_locus_lines) continue;
-        const size_t o = ((size_t)l * a.K + c) * 2;
-        const double r = (double)a.A[o], al = (double)a.A[o + 1], t = r + al;
-        double frac = 0.5;                                   // T:375; with t == 0 the value cannot matter (it multiplies count == 0)
-        if (t > 0.0) frac = a.round == 0 ? clamp_frac(0.5 * (r / t) + 0.5 * (r / t)) : clamp_frac(r / t);   // T:359-363 / T:232
-        const double af = (1.0 - a.c.p_soup) * frac + a.c.p_soup * a.soup[l];
-        lp += term(a.ref[j], a.alt[j], af, t);
+    const uint64_t j1 = a.row_ptr[cell + 1];
+    for (uint64_t j0 = a.row_ptr[cell]; j0 < j1; j0 += 32) {
+        const uint64_t j = j0 + lane;
+        double t = 0.0;
+        if (j < j1) {
+            const uint32_t l = a.locus[j];
+            if (a.locus_lines[l] >= a.c.min_locus_lines) {
+                const size_t o = ((size_t)l * a.K + c) * 2;
+                const double r = (double)a.A[o], al = (double)a.A[o + 1], tot = r + al;
+                double frac = 0.5;                               // T:375; with tot == 0 the value cannot matter (it multiplies count == 0)
+                if (tot > 0.0) frac = a.round == 0 ? clamp_frac(0.5 * (r / tot) + 0.5 * (r / tot)) : clamp_frac(r / tot);   // T:359-363 / T:232
+                const double af = (1.0 - a.c.p_soup) * frac + a.c.p_soup * a.soup[l];
+                t = term(a.ref[j], a.alt[j], af, tot);
+            }
+        }
+        lp = ordered_add(lp, t);
     }
-    out[i] = lp;
+    if (lane == 0) out[i] = lp;
 }
 
 constexpr int PAIRS = 6;   // pairs among the top min(K, 4) singlets (T:91-92)
-__global__ void doublet_kernel(Args a, const int32_t* __restrict__ pairs /*[N][6][2], -1 = unused*/, double* __restrict__ out /*[N][6]*/) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) doublet_kernel(Args a, const int32_t* __restrict__ pairs /*[N][6][2], -1 = unused*/, double* __restrict__ out /*[N][6]*/) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp = (cell, pair)
     if (i >= (uint64_t)a.N * PAIRS) return;
-    const uint32_t cell = (uint32_t)(i / PAIRS);
+    const uint32_t cell = (uint32_t)(i / PAIRS), lane = threadIdx.x & 31;
     const int c1 = pairs[i * 2], c2 = pairs[i * 2 + 1];
-    if (c1 < 0) { out[i] = -INFINITY; return; }
+    if (c1 < 0) { if (lane == 0) out[i] = -INFINITY; return; }
     double lp = a.c.ln_doublet_prior;
-    for (uint64_t j = a.row_ptr[cell]; j < a.row_ptr[cell + 1]; ++j) {
-        const uint32_t l = a.locus[j];
-        if (a.locus_lines[l] < a.c.min_locus_lines) continue;
-        const size_t o1 = ((size_t)l * a.K + c1) * 2, o2 = ((size_t)l * a.K + c2) * 2;
-        const double r1 = (double)a.A[o1], a1 = (double)a.A[o1 + 1], r3 = (double)a.A[o2], a3 = (double)a.A[o2 + 1];
-        double frac = 0.5;
-        if (a.round == 0) {                                  // T:351-377 on the counts as loaded
-            const double t1 = r1 + a1, t2 = r3 + a3;
-            if (t1 > 0.0) frac = t2 > 0.0 ? clamp_frac(0.5 * (r1 / t1) + 0.5 * (r3 / t2)) : clamp_frac(r1 / t1);
-        } else {                                             // T:226-235 on counts[(c1, c2)] = A[c1] + S0[c2]
-            const double r = r1 + (double)a.S0[o2], al = a1 + (double)a.S0[o2 + 1];
-            if (r + al > 0.0) frac = clamp_frac(r / (r + al));
+    const uint64_t j1 = a.row_ptr[cell + 1];
+    for (uint64_t j0 = a.row_ptr[cell]; j0 < j1; j0 += 32) {
+        const uint64_t j = j0 + lane;
+        double t = 0.0;
+        if (j < j1) {
+            const uint32_t l = a.locus[j];
+            if (a.locus_lines[l] >= a.c.min_locus_lines) {
+                const size_t o1 = ((size_t)l * a.K + c1) * 2, o2 = ((size_t)l * a.K + c2) * 2;
+                const double r1 = (double)a.A[o1], a1 = (double)a.A[o1 + 1], r3 = (double)a.A[o2], a3 = (double)a.A[o2 + 1];
+                double frac = 0.5;
+                if (a.round == 0) {                              // T:351-377 on the counts as loaded
+                    const double t1 = r1 + a1, t2 = r3 + a3;
+                    if (t1 > 0.0) frac = t2 > 0.0 ? clamp_frac(0.5 * (r1 / t1) + 0.5 * (r3 / t2)) : clamp_frac(r1 / t1);
+                } else {                                         // T:226-235 on counts[(c1, c2)] = A[c1] + S0[c2]
+                    const double r = r1 + (double)a.S0[o2], al = a1 + (double)a.S0[o2 + 1];
+                    if (r + al > 0.0) frac = clamp_frac(r / (r + al));
+                }
+                const double af = (1.0 - a.c.p_soup) * frac + a.c.p_soup * a.soup[l];
+                const double count = ((r1 + a1) + (r3 + a3)) / 2.0;   // T:117
+                t = term(a.ref[j], a.alt[j], af, count);
+            }
         }
-        const double af = (1.0 - a.c.p_soup) * frac + a.c.p_soup * a.soup[l];
-        const double count = ((r1 + a1) + (r3 + a3)) / 2.0;   // T:117
-        lp += term(a.ref[j], a.alt[j], af, count);
+        lp = ordered_add(lp, t);
     }
-    out[i] = lp;
+    if (lane == 0) out[i] = lp;
 }
 
 // S0[l][cluster(cell)] += (ref, alt); lines per locus; exact integer atomics (the reference adds integer-valued f64)
