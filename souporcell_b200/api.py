@@ -32,7 +32,7 @@ EXPORTS = [
     "soup_known_genotypes_load", "soup_chacha_words", "soup_thread_seeds", "soup_format_f32", "soup_ln_binomial_f32", "soup_bad_cluster_detection",
     "soup_ctx_create", "soup_ctx_destroy", "soup_load_csr", "soup_get_dims", "soup_get_csc", "soup_get_cell_totals",
     "soup_get_csr_lbc", "soup_cluster_allele_counts", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
-    "soup_main", "soup_exchange_best", "soup_write_clusters", "soup_clusters_load", "soup_troublet", "soup_troublet_write",
+    "soup_main", "soup_exchange_best", "soup_write_clusters", "soup_clusters_load", "soup_troublet", "soup_troublet_write", "soup_mtx_save", "soup_mtx_load_cache",
 ]
 
 
@@ -179,11 +179,20 @@ class CellCSR:
 MTX_RAW = 2
 
 
-def load_mtx(alt_path, ref_path, min_alt=4, min_ref=4, min_alt_umis=0, min_ref_umis=0, raw=False) -> CellCSR:
-    """load_cell_data S:601-681 (defaults S:764-767, 811-816); raw=True: troublet's view of the files (SOUP_MTX_RAW)."""
+def load_mtx(alt_path, ref_path, min_alt=4, min_ref=4, min_alt_umis=0, min_ref_umis=0, raw=False, cache=None) -> CellCSR:
+    """load_cell_data S:601-681 (defaults S:764-767, 811-816); raw=True: troublet's view of the files (SOUP_MTX_RAW).
+    `cache`: path of a .soupcsr file — read if present (and built with the same filter), else written after the text parse."""
     L = lib()
     m = C.POINTER(_Mtx)()
-    _check(L.soup_mtx_load(os.fsencode(alt_path), os.fsencode(ref_path), min_alt, min_ref, min_alt_umis, min_ref_umis, MTX_RAW if raw else 0, C.byref(m)))
+    flags = MTX_RAW if raw else 0
+    L.soup_mtx_load_cache.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.POINTER(_Mtx))]
+    L.soup_mtx_save.argtypes = [C.POINTER(_Mtx), C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    if cache is not None and os.path.exists(cache):
+        _check(L.soup_mtx_load_cache(os.fsencode(cache), min_alt, min_ref, min_alt_umis, min_ref_umis, flags, C.byref(m)))
+    else:
+        _check(L.soup_mtx_load(os.fsencode(alt_path), os.fsencode(ref_path), min_alt, min_ref, min_alt_umis, min_ref_umis, flags, C.byref(m)))
+        if cache is not None:
+            _check(L.soup_mtx_save(m, os.fsencode(cache), min_alt, min_ref, min_alt_umis, min_ref_umis, flags))
     try:
         s = m.contents
         n, nnz, nl = int(s.n_cells), int(s.nnz), int(s.n_loci)

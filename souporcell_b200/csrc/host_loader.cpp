@@ -13,6 +13,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
@@ -35,7 +36,23 @@ struct Mapped {
     const char* p = nullptr;
     size_t n = 0;
     int fd = -1;
+    std::vector<char> inflated;   // ".gz" input (an extension: the reference opens the matrices uncompressed, S:602-607)
     bool open(const char* path) {
+        const size_t plen = strlen(path);
+        if (plen >= 3 && !strcmp(path + plen - 3, ".gz")) {
+            gzFile f = gzopen(path, "rb");
+            if (!f) return false;
+            gzbuffer(f, 1 << 20);
+            char buf[1 << 16];
+            int got;
+            while ((got = gzread(f, buf, sizeof(buf))) > 0) inflated.insert(inflated.end(), buf, buf + got);
+            const bool ok = got == 0;
+            gzclose(f);
+            if (!ok) return false;
+            n = inflated.size();
+            p = n ? inflated.data() : "";
+            return true;
+        }
         fd = ::open(path, O_RDONLY);
         if (fd < 0) return false;
         struct stat st;
@@ -49,7 +66,7 @@ struct Mapped {
         return true;
     }
     ~Mapped() {
-        if (p && n) munmap((void*)p, n);
+        if (p && n && inflated.empty()) munmap((void*)p, n);
         if (fd >= 0) close(fd);
     }
 };
@@ -352,6 +369,81 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
     }
     m->row_ptr[total_cells] = pos;
     if (!index_to_locus.empty()) memcpy(m->index_to_locus, index_to_locus.data(), index_to_locus.size() * sizeof(uint64_t));
+    *out = m;
+    return SOUP_OK;
+}
+
+
+// ------------------------------------------------------------------ binary CSR cache
+// `.soupcsr`: what soup_mtx_load produced, so that re-runs of the pipeline (and troublet / consensus, which parse the same two
+// text matrices again) skip the text parse.  Little-endian, 64-byte header, then the five arrays back to back.
+namespace {
+struct CacheHeader {
+    char magic[8];            // "SOUPCSR1"
+    uint64_t n_cells, n_loci_total, n_loci, nnz;
+    uint32_t min_alt, min_ref, min_alt_umis, min_ref_umis;   // the filter the matrix was built with (S:659)
+    uint32_t flags;           // SOUP_MTX_RAW or 0
+    uint32_t reserved;
+};
+static_assert(sizeof(CacheHeader) == 64, "cache header layout");
+}  // namespace
+
+extern "C" int32_t soup_mtx_save(const soup_mtx* m, const char* path, uint32_t min_alt, uint32_t min_ref, uint32_t min_alt_umis,
+                                 uint32_t min_ref_umis, uint32_t flags) {
+    if (!m || !path) { set_thread_error("soup_mtx_save: bad argument"); return SOUP_ERR_INVALID; }
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { set_thread_error("soup_mtx_save: cannot create %s", tmp.c_str()); return SOUP_ERR_IO; }
+    CacheHeader h{};
+    memcpy(h.magic, "SOUPCSR1", 8);
+    h.n_cells = m->n_cells; h.n_loci_total = m->n_loci_total; h.n_loci = m->n_loci; h.nnz = m->nnz;
+    h.min_alt = min_alt; h.min_ref = min_ref; h.min_alt_umis = min_alt_umis; h.min_ref_umis = min_ref_umis; h.flags = flags & SOUP_MTX_RAW;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    auto put = [&](const void* p, size_t bytes) { if (ok && bytes) ok = fwrite(p, 1, bytes, f) == bytes; };
+    put(m->row_ptr, (m->n_cells + 1) * 8); put(m->locus, m->nnz * 4); put(m->alt, m->nnz * 4); put(m->ref, m->nnz * 4); put(m->index_to_locus, m->n_loci * 8);
+    ok = (fclose(f) == 0) && ok;
+    if (ok) ok = rename(tmp.c_str(), path) == 0;     // readers never see a half-written cache
+    if (!ok) { remove(tmp.c_str()); set_thread_error("soup_mtx_save: write to %s failed", path); return SOUP_ERR_IO; }
+    return SOUP_OK;
+}
+
+extern "C" int32_t soup_mtx_load_cache(const char* path, uint32_t min_alt, uint32_t min_ref, uint32_t min_alt_umis, uint32_t min_ref_umis,
+                                       uint32_t flags, soup_mtx** out) {
+    if (!path || !out) { set_thread_error("soup_mtx_load_cache: bad argument"); return SOUP_ERR_INVALID; }
+    *out = nullptr;
+    Mapped F;
+    if (!F.open(path)) { set_thread_error("cannot open %s", path); return SOUP_ERR_IO; }
+    if (F.n < sizeof(CacheHeader)) { set_thread_error("%s: not a .soupcsr file", path); return SOUP_ERR_INVALID; }
+    CacheHeader h;
+    memcpy(&h, F.p, sizeof(h));
+    if (memcmp(h.magic, "SOUPCSR1", 8) != 0) { set_thread_error("%s: not a .soupcsr file", path); return SOUP_ERR_INVALID; }
+    if (h.min_alt != min_alt || h.min_ref != min_ref || h.min_alt_umis != min_alt_umis || h.min_ref_umis != min_ref_umis || h.flags != (flags & SOUP_MTX_RAW)) {
+        set_thread_error("%s was built with another filter (min_alt %u min_ref %u min_alt_umis %u min_ref_umis %u raw %u)", path, h.min_alt, h.min_ref,
+                         h.min_alt_umis, h.min_ref_umis, h.flags);
+        return SOUP_ERR_INVALID;
+    }
+    const uint64_t need = sizeof(h) + (h.n_cells + 1) * 8 + h.nnz * 12 + h.n_loci * 8;
+    if (h.n_cells > (1ull << 32) || h.nnz > (1ull << 40) || h.n_loci > h.n_loci_total || F.n != need) { set_thread_error("%s: truncated or corrupt", path); return SOUP_ERR_INVALID; }
+    const bool pinned = (flags & SOUP_MTX_PINNED) != 0;
+    soup_mtx* m = (soup_mtx*)calloc(1, sizeof(soup_mtx));
+    if (!m) { set_thread_error("out of memory"); return SOUP_ERR_NOMEM; }
+    m->pinned = pinned ? 1 : 0;
+    m->n_cells = h.n_cells; m->n_loci_total = h.n_loci_total; m->n_loci = h.n_loci; m->nnz = h.nnz;
+    m->row_ptr = (uint64_t*)alloc_out((h.n_cells + 1) * 8, pinned);
+    m->locus = (uint32_t*)alloc_out(h.nnz * 4, pinned);
+    m->alt = (uint32_t*)alloc_out(h.nnz * 4, pinned);
+    m->ref = (uint32_t*)alloc_out(h.nnz * 4, pinned);
+    m->index_to_locus = (uint64_t*)alloc_out(h.n_loci * 8, pinned);
+    if (!m->row_ptr || !m->locus || !m->alt || !m->ref || !m->index_to_locus) { soup_mtx_free(m); set_thread_error("out of memory"); return pinned ? SOUP_ERR_CUDA : SOUP_ERR_NOMEM; }
+    const char* q = F.p + sizeof(h);
+    auto get = [&](void* dst, size_t bytes) { if (bytes) memcpy(dst, q, bytes); q += bytes; };
+    get(m->row_ptr, (h.n_cells + 1) * 8); get(m->locus, h.nnz * 4); get(m->alt, h.nnz * 4); get(m->ref, h.nnz * 4); get(m->index_to_locus, h.n_loci * 8);
+    // structural checks: a cache is an input like any other
+    bool ok = m->row_ptr[0] == 0 && m->row_ptr[h.n_cells] == h.nnz;
+    for (uint64_t c = 0; ok && c < h.n_cells; ++c) ok = m->row_ptr[c] <= m->row_ptr[c + 1];
+    for (uint64_t j = 0; ok && j < h.nnz; ++j) ok = m->locus[j] < h.n_loci;
+    for (uint64_t l = 0; ok && l < h.n_loci; ++l) ok = m->index_to_locus[l] < h.n_loci_total && (l == 0 || m->index_to_locus[l] > m->index_to_locus[l - 1]);
+    if (!ok) { soup_mtx_free(m); set_thread_error("%s: inconsistent contents", path); return SOUP_ERR_INVALID; }
     *out = m;
     return SOUP_OK;
 }

@@ -7,6 +7,8 @@
 //   --gpus N           use the first N visible GPUs (restart-sharded); default: all visible
 //   --max_slots N      resident solves per GPU (0 = auto)
 //   --quiet_iterations do not print the per-iteration "binomial" lines
+//   --csr_cache FILE   binary cache of the parsed + filtered matrix (.soupcsr): read when it exists and was built
+//                      with the same filter, written after the text parse otherwise
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +47,7 @@ const Opt kOpts[] = {
     {"gpus", 0, false, false, "[soupgpu] number of GPUs to shard restarts over (default: all visible)"},
     {"max_slots", 0, false, false, "[soupgpu] resident solves per GPU (default: auto)"},
     {"quiet_iterations", 0, false, true, "[soupgpu] do not log per-iteration lines"},
+    {"csr_cache", 0, false, false, "[soupgpu] .soupcsr cache of the parsed matrix (read if present, else written)"},
 };
 
 void usage(FILE* f) {
@@ -159,8 +162,22 @@ int main(int argc, char** argv) {
     if (n_bc > 200000)
         fprintf(stderr, "More than 200_000 barcodes in barcodes file? is this the filtered barcode file? (do not use raw barcode file)\n");
     soup_mtx* m = nullptr;
-    if (soup_mtx_load(alt_mtx.c_str(), ref_mtx.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, &m) != SOUP_OK)
-        die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    const std::string cache = get("csr_cache", "");
+    bool from_cache = false;
+    if (!cache.empty()) {
+        FILE* probe = fopen(cache.c_str(), "rb");
+        if (probe) {
+            fclose(probe);
+            if (soup_mtx_load_cache(cache.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, &m) == SOUP_OK) from_cache = true;
+            else fprintf(stderr, "csr_cache ignored: %s\n", soup_last_error(nullptr));
+        }
+    }
+    if (!from_cache) {
+        if (soup_mtx_load(alt_mtx.c_str(), ref_mtx.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, &m) != SOUP_OK)
+            die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+        if (!cache.empty() && soup_mtx_save(m, cache.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0) != SOUP_OK)
+            fprintf(stderr, "csr_cache not written: %s\n", soup_last_error(nullptr));
+    }
     fprintf(stderr, "total loci used %llu\n", (unsigned long long)m->n_loci);   // S:678
     sw.lap("parse mtx + barcodes");
 

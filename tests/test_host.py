@@ -217,3 +217,39 @@ def test_known_genotypes_init_matches_oracle(tmp_path, gz):
             sp.known_genotypes(vcf, bad_names, k, m.index_to_locus)
     with pytest.raises(sp.SoupError):
         sp.known_genotypes(str(tmp_path / "missing.vcf"), samples, 3, m.index_to_locus)
+
+
+def test_gz_input_and_binary_cache_roundtrip(tmp_path):
+    """`.mtx.gz` inputs parse like the plain files, and a `.soupcsr` cache gives back exactly the parsed matrix
+    (and refuses to be used for another filter, or when damaged)."""
+    import gzip
+    import shutil
+    v = synth.generate(n_cells=120, n_loci=900, k=3, mean_loci=60, seed=5)
+    alt, ref, _ = synth.write_files(v, str(tmp_path))
+    plain = sp.load_mtx(alt, ref)
+    for src in (alt, ref):
+        with open(src, "rb") as fi, gzip.open(src + ".gz", "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+    gz = sp.load_mtx(alt + ".gz", ref + ".gz")
+    fields = ("n_cells", "n_loci_total", "n_loci")
+    same = lambda a, b: all(getattr(a, f) == getattr(b, f) for f in fields) and all(
+        np.array_equal(getattr(a, f), getattr(b, f)) for f in ("row_ptr", "locus", "alt", "ref", "index_to_locus"))
+    assert same(plain, gz)
+    cache = str(tmp_path / "m.soupcsr")
+    first = sp.load_mtx(alt, ref, cache=cache)                     # parses the text, writes the cache
+    assert os.path.exists(cache) and same(plain, first)
+    os.remove(alt); os.remove(ref)
+    again = sp.load_mtx(alt, ref, cache=cache)                     # the text files are gone: this is the cache
+    assert same(plain, again)
+    with pytest.raises(sp.SoupError):
+        sp.load_mtx(alt, ref, min_alt=6, cache=cache)              # built with another filter
+    raw_cache = str(tmp_path / "raw.soupcsr")
+    raw = sp.load_mtx(alt + ".gz", ref + ".gz", raw=True, cache=raw_cache)
+    assert raw.nnz == v.nnz and same(raw, sp.load_mtx(alt, ref, raw=True, cache=raw_cache))
+    with pytest.raises(sp.SoupError):
+        sp.load_mtx(alt, ref, cache=raw_cache)                     # RAW view asked for as the filtered one
+    blob = bytearray(open(cache, "rb").read())
+    with open(cache, "wb") as fh:
+        fh.write(blob[:-8])                                        # truncated
+    with pytest.raises(sp.SoupError):
+        sp.load_mtx(alt, ref, cache=cache)
