@@ -286,6 +286,17 @@ typedef struct soup_main_params {
     soup_bcast_fn bcast;
     void* comm_user;
     int32_t init_strategy;           /* SOUP_INIT_* (--initialization_strategy) */
+    /* Cell sharding under the driver: this process holds a contiguous range of the cells in its ONE context;
+     * every process of the cell group runs the same restarts and all-reduces the M-pass statistics each iteration (soup_solve_params).
+     * `cell_allgather` (host memory, over the cell group) is used once per souporcell3 run to add up the per-cluster cell counts that
+     * bad_cluster_detection (S:150-187) ranks.  best_log_probs then covers the local cells only.  Combined with proc_world > 1 this is the
+     * hybrid mode: proc_rank / proc_world number the cell GROUPS (restarts shard over groups), and allgather / bcast run over the
+     * processes that hold the SAME cell range in every group. */
+    soup_allreduce_fn cell_allreduce; /* NULL = off */
+    void* cell_comm_user;
+    uint64_t n_cells_global;
+    soup_allgather_fn cell_allgather;
+    int32_t cell_group_size;          /* processes in the cell group (what cell_allgather gathers over) */
 } soup_main_params;
 typedef struct soup_main_result {
     int32_t has_best, runs;

@@ -84,7 +84,8 @@ class _MainParams(C.Structure):
                 ("seed", C.c_uint8), ("souporcell3", C.c_int32), ("iteration_cap", C.c_int32), ("max_slots", C.c_int32),
                 ("lanes", C.c_int32), ("record_counts", C.c_int32), ("verbose_trace", C.c_int32), ("time_kernels", C.c_int32),
                 ("known_theta", C.c_void_p), ("proc_rank", C.c_int32), ("proc_world", C.c_int32), ("allgather", ALLGATHER_FN), ("bcast", BCAST_FN),
-                ("comm_user", C.c_void_p), ("init_strategy", C.c_int32)]
+                ("comm_user", C.c_void_p), ("init_strategy", C.c_int32), ("cell_allreduce", C.c_void_p), ("cell_comm_user", C.c_void_p),
+                ("n_cells_global", C.c_uint64), ("cell_allgather", ALLGATHER_FN), ("cell_group_size", C.c_int32)]
 
 
 class _MainResult(C.Structure):
@@ -524,7 +525,8 @@ class MainResult:
 
 def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3=False, iteration_cap=0, max_slots=0,
          lanes=0, record_counts=False, verbose_trace=False, time_kernels=False, proc_rank=0, proc_world=1, allgather=None,
-         bcast=None, known_theta=None, init_strategy=INIT_RANDOM_UNIFORM) -> MainResult:
+         bcast=None, known_theta=None, init_strategy=INIT_RANDOM_UNIFORM, cell_allreduce=None, cell_allgather=None, cell_group_size=0,
+         n_cells_global=0) -> MainResult:
     """souporcell_main S:60-131 over one context per GPU (restart-sharded)."""
     if isinstance(ctxs, Context):
         ctxs = [ctxs]
@@ -535,6 +537,10 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
     p.record_counts, p.verbose_trace, p.time_kernels = int(record_counts), int(verbose_trace), int(time_kernels)
     p.proc_rank, p.proc_world = proc_rank, proc_world
     p.init_strategy = init_strategy
+    if cell_allreduce is not None:   # cell sharding under the driver (hybrid when proc_world > 1)
+        p.cell_allreduce = C.cast(cell_allreduce, C.c_void_p)
+        p.cell_allgather = cell_allgather
+        p.cell_group_size, p.n_cells_global = cell_group_size, n_cells_global
     if known_theta is not None:
         kt = np.ascontiguousarray(known_theta, dtype=np.float32).reshape(k, ctxs[0].n_loci)
         p.known_theta = _ptr(kt)

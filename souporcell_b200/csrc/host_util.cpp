@@ -80,6 +80,36 @@ std::string format_f32_w8(float v) {
     return s;
 }
 
+// bad_cluster_detection S:150-187 in two halves, so that cell-sharded processes can add their counts up in between
+void count_cluster_cells(const float* best_lp, uint64_t n_cells, int32_t k, uint64_t* counts) {
+    for (uint64_t i = 0; i < n_cells; ++i) {             // max_by(total_cmp) = LAST maximum (S:159)
+        const float* row = best_lp + i * (uint64_t)k;
+        int32_t best = 0;
+        for (int32_t c = 1; c < k; ++c)
+            if (total_key(row[c]) >= total_key(row[best])) best = c;
+        counts[(size_t)best] += 1;
+    }
+}
+int32_t bad_clusters_from_counts(int32_t run, int32_t k, const uint64_t* counts, int32_t* out_idx, void* log_file) {
+    FILE* log = (FILE*)log_file;
+    if (k < 16 || run == 0) return 0;
+    std::vector<std::pair<int32_t, uint64_t>> assigned((size_t)k);
+    for (int32_t c = 0; c < k; ++c) assigned[(size_t)c] = {c, counts[c]};
+    std::stable_sort(assigned.begin(), assigned.end(),
+                     [](const std::pair<int32_t, uint64_t>& a, const std::pair<int32_t, uint64_t>& b) { return a.second < b.second; });
+    size_t run_value = (size_t)(3 - run);
+    size_t low = run_value * ((size_t)k / 16), high = (16 - run_value) * ((size_t)k / 16);
+    int32_t n_out = 0;
+    if (log) fprintf(log, "Cluster Analysis\n");
+    for (size_t index = 0; index < assigned.size(); ++index) {
+        int32_t cluster = assigned[index].first;
+        bool outlier = index < low || index > high;
+        if (log) fprintf(log, "%zu:\tcluster\t%d\tloss\t%llu%s\n", index, cluster, (unsigned long long)assigned[index].second, outlier ? " outlier" : "");
+        if (outlier && std::find(out_idx, out_idx + n_out, cluster) == out_idx + n_out) out_idx[n_out++] = cluster;
+    }
+    return n_out;
+}
+
 }  // namespace soup
 
 using namespace soup;
@@ -397,31 +427,11 @@ int32_t soup_write_clusters(void* out_file, const char* barcode_blob, uint64_t n
 // S:150-187
 int32_t soup_bad_cluster_detection(int32_t run, int32_t k, const float* best_lp, uint64_t n_cells, int32_t* out_idx,
                                    void* log_file) {
-    FILE* log = (FILE*)log_file;
     if (k <= 0 || run < 0 || !out_idx) { set_thread_error("soup_bad_cluster_detection: bad argument"); return SOUP_ERR_INVALID; }
     if (k < 16 || run == 0) return 0;
-    std::vector<std::pair<int32_t, uint64_t>> assigned((size_t)k);
-    for (int32_t c = 0; c < k; ++c) assigned[(size_t)c] = {c, 0};
-    for (uint64_t i = 0; i < n_cells; ++i) {             // max_by(total_cmp) = LAST maximum (S:159)
-        const float* row = best_lp + i * (uint64_t)k;
-        int32_t best = 0;
-        for (int32_t c = 1; c < k; ++c)
-            if (total_key(row[c]) >= total_key(row[best])) best = c;
-        assigned[(size_t)best].second += 1;
-    }
-    std::stable_sort(assigned.begin(), assigned.end(),
-                     [](const std::pair<int32_t, uint64_t>& a, const std::pair<int32_t, uint64_t>& b) { return a.second < b.second; });
-    size_t run_value = (size_t)(3 - run);
-    size_t low = run_value * ((size_t)k / 16), high = (16 - run_value) * ((size_t)k / 16);
-    int32_t n_out = 0;
-    if (log) fprintf(log, "Cluster Analysis\n");
-    for (size_t index = 0; index < assigned.size(); ++index) {
-        int32_t cluster = assigned[index].first;
-        bool outlier = index < low || index > high;
-        if (log) fprintf(log, "%zu:\tcluster\t%d\tloss\t%llu%s\n", index, cluster, (unsigned long long)assigned[index].second, outlier ? " outlier" : "");
-        if (outlier && std::find(out_idx, out_idx + n_out, cluster) == out_idx + n_out) out_idx[n_out++] = cluster;
-    }
-    return n_out;
+    std::vector<uint64_t> counts((size_t)k, 0);
+    soup::count_cluster_cells(best_lp, n_cells, k, counts.data());
+    return soup::bad_clusters_from_counts(run, k, counts.data(), out_idx, log_file);
 }
 
 }  // extern "C"

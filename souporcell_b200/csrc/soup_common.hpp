@@ -70,6 +70,10 @@ struct StdRng {
     float gen_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }          // 24-bit mantissa draw
 };
 
+// ---- bad_cluster_detection S:150-187 in two halves (cell-sharded processes add their counts up in between)
+void count_cluster_cells(const float* best_lp, uint64_t n_cells, int32_t k, uint64_t* counts);
+int32_t bad_clusters_from_counts(int32_t run, int32_t k, const uint64_t* counts, int32_t* out_idx, void* log_file);
+
 // ---- host math / formatting
 float ln_binomial_f32(uint32_t n, uint32_t k);        // statrs 0.11.0 ln_binomial -> f32
 std::string format_f32(float v);                      // Rust `{}`

@@ -738,7 +738,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     ctx->h_trace.clear(); ctx->h_trace_solve.clear(); ctx->h_trace_iters.clear(); ctx->h_trace_cap = iter_cap;
 
     const bool cell_mode = p->cell_allreduce != nullptr;
-    if (cell_mode && world > 1) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: cell sharding and restart sharding are exclusive in one call");
+    // cell_mode with world > 1 is the hybrid mode: every process of a cell group passes the same shard_rank (its
+    // group), runs the same subset of the solves, and the all-reduce callback spans that group only
     if (cell_mode && p->n_cells_global < ctx->N) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: n_cells_global must be the total cell count over all ranks");
     const float limit = 0.01f * (float)(cell_mode ? p->n_cells_global : ctx->N);   // S:214 (all cells)
     const float log_prior = logf(1.0f / (float)K);             // S:202 (host libm = the reference's f32::ln)

@@ -76,6 +76,9 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
     if (!p || !r || !r->best_log_probs) { set_thread_error("soup_main: null argument"); return SOUP_ERR_INVALID; }
     if (p->threads == 0 || p->k <= 0) { set_thread_error("soup_main: threads and k must be >= 1"); return SOUP_ERR_INVALID; }
     const int pworld = p->proc_world > 1 ? p->proc_world : 1, prank = pworld > 1 ? p->proc_rank : 0;
+    const bool cell_mode = p->cell_allreduce != nullptr;
+    if (cell_mode && n_ctx != 1) { set_thread_error("soup_main: cell sharding takes ONE context per process"); return SOUP_ERR_INVALID; }
+    if (cell_mode && (!p->cell_allgather || p->cell_group_size <= 0)) { set_thread_error("soup_main: cell sharding needs cell_allgather and cell_group_size"); return SOUP_ERR_INVALID; }
     if (pworld > 1 && (!p->allgather || !p->bcast)) { set_thread_error("soup_main: proc_world > 1 needs the allgather and bcast callbacks"); return SOUP_ERR_INVALID; }
     FILE* log = (FILE*)log_file;
     const int K = p->k;
@@ -100,7 +103,20 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
     for (int run = 0; run < 3; ++run) {          // S:70
         int n_bad = 0;
         if (have_best || run == 0) {
-            n_bad = soup_bad_cluster_detection(run, K, r->best_log_probs, have_best ? n_cells : 0, bad.data(), log);
+            if (cell_mode && K >= 16 && run > 0) {
+                // the cluster sizes S:156-162 over ALL cells: add the cell group's counts up (host all-gather, K u64 per process)
+                std::vector<uint64_t> mine((size_t)K, 0);
+                count_cluster_cells(r->best_log_probs, have_best ? n_cells : 0, K, mine.data());
+                int32_t group = p->cell_group_size > 0 ? p->cell_group_size : 1;
+                std::vector<uint64_t> all((size_t)K * group, 0);
+                int32_t e = p->cell_allgather(p->cell_comm_user, mine.data(), all.data(), (uint64_t)K * sizeof(uint64_t));
+                if (e != SOUP_OK) { set_thread_error("soup_main: the cell_allgather callback failed (%d)", e); return e; }
+                for (int32_t g = 1; g < group; ++g)
+                    for (int c = 0; c < K; ++c) all[c] += all[(size_t)g * K + c];
+                n_bad = bad_clusters_from_counts(run, K, all.data(), bad.data(), log);
+            } else {
+                n_bad = soup_bad_cluster_detection(run, K, r->best_log_probs, have_best ? n_cells : 0, bad.data(), log);
+            }
         } else {
             // S:93 would index an empty best_cluster_centers and panic
             set_thread_error("souporcell3 run %d: no finite solve in the previous run (the reference panics here)", run + 1);
@@ -135,6 +151,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             sp.stream_seeds = seeds.data();
             sp.init_theta = p->known_theta;
             sp.init_strategy = p->init_strategy;
+            sp.cell_allreduce = p->cell_allreduce; sp.comm_user = p->cell_comm_user; sp.n_cells_global = p->n_cells_global;
             sp.base_theta = run > 0 ? best_theta.data() : nullptr;
             sp.reinit_clusters = run > 0 ? bad.data() : nullptr;
             sp.n_reinit = run > 0 ? n_bad : 0;

@@ -492,3 +492,114 @@ def test_many_columns_straddling_groups(k, n_solves, slots, mode):
         want = od.solve(theta0[b], method=1 if k % 2 else 0)
         assert np.array_equal(bits(res.best_log_probs), bits(want["log_probs"])) and np.array_equal(bits(res.best_theta), bits(want["theta"]))
         assert res.best_loss == np.nanmax(res.solve_loss)
+
+
+@pytest.mark.parametrize("groups,shards", [(1, 2), (2, 2)])
+def test_driver_cell_sharded_and_hybrid_souporcell3(groups, shards):
+    """soup_main with cell sharding and the hybrid restarts x cells mode (row 3), emulated on one GPU: `groups` cell
+    groups of `shards` processes (threads here, one context each).  k = 16 with souporcell3, so bad_cluster_detection runs on cluster
+    sizes gathered over the cell group.  Checked against the single-context driver on the whole matrix at north_star's tolerance."""
+    import ctypes as C
+    import threading
+    import torch
+    from souporcell_b200 import api
+
+    v, csr = synth_csr(n_cells=420, n_loci=2600, k=5, mean_loci=130, seed=23)
+    K, restarts = 16, 4
+    with sp.Context(0) as whole:
+        whole.load_csr(*csr)
+        want = sp.main(whole, K, method=sp.METHOD_KHM, restarts=restarts, threads=restarts, seed=9, souporcell3=True)
+    assert want.runs >= 2                                   # the re-initialisation runs happened
+    cuts, parts = _split_cells(csr, shards)
+
+    class Dev:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+    class Rendezvous:
+        def __init__(self, n):
+            self.bar, self.slots, self.tmp = threading.Barrier(n), [None] * n, None
+
+    cell_groups = [Rendezvous(shards) for _ in range(groups)]       # the processes of one cell group
+    positions = [Rendezvous(groups) for _ in range(shards)]         # the processes holding the same cell range in every group
+
+    def allreduce_cb(g, s):
+        rv = cell_groups[g]
+        def cb(user, buf, n, stream):
+            try:
+                torch.cuda.synchronize()
+                rv.slots[s] = torch.as_tensor(Dev(buf, n), device="cuda")
+                rv.bar.wait()
+                if s == 0:
+                    acc = rv.slots[0].clone()
+                    for t in rv.slots[1:]:
+                        acc += t
+                    rv.tmp = acc
+                    torch.cuda.synchronize()
+                rv.bar.wait()
+                rv.slots[s].copy_(rv.tmp)
+                torch.cuda.synchronize()
+                rv.bar.wait()
+                return 0
+            except Exception:
+                rv.bar.abort()
+                return -1
+        return api.ALLREDUCE_FN(cb)
+
+    def allgather_cb(rv, me):
+        def cb(user, send, recv, nbytes):
+            try:
+                rv.slots[me] = C.string_at(send, nbytes)
+                rv.bar.wait()
+                data = b"".join(rv.slots)
+                C.memmove(recv, data, len(data))
+                rv.bar.wait()
+                return 0
+            except Exception:
+                rv.bar.abort()
+                return -1
+        return api.ALLGATHER_FN(cb)
+
+    def bcast_cb(rv, me):
+        def cb(user, buf, nbytes, root):
+            try:
+                if me == root:
+                    rv.tmp = C.string_at(buf, nbytes)
+                rv.bar.wait()
+                if me != root:
+                    C.memmove(buf, rv.tmp, nbytes)
+                rv.bar.wait()
+                return 0
+            except Exception:
+                rv.bar.abort()
+                return -1
+        return api.BCAST_FN(cb)
+
+    results, errors = {}, []
+
+    def run(g, s):
+        try:
+            keep = (allreduce_cb(g, s), allgather_cb(cell_groups[g], s), allgather_cb(positions[s], g), bcast_cb(positions[s], g))
+            with sp.Context(0) as ctx:
+                ctx.load_csr(*parts[s])
+                results[(g, s)] = sp.main(ctx, K, method=sp.METHOD_KHM, restarts=restarts, threads=restarts, seed=9, souporcell3=True,
+                                          proc_rank=g, proc_world=groups, allgather=keep[2] if groups > 1 else None,
+                                          bcast=keep[3] if groups > 1 else None, cell_allreduce=keep[0], cell_allgather=keep[1],
+                                          cell_group_size=shards, n_cells_global=csr[0])
+        except Exception as e:                              # noqa: BLE001
+            errors.append(e)
+            for rv in cell_groups + positions:
+                rv.bar.abort()
+
+    threads = [threading.Thread(target=run, args=(g, s)) for g in range(groups) for s in range(shards)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for g in range(groups):
+        lp = np.concatenate([results[(g, s)].best_log_probs for s in range(shards)])
+        r0 = results[(g, 0)]
+        assert r0.runs == want.runs
+        np.testing.assert_allclose(r0.best_loss, want.best_loss, rtol=1e-5)
+        np.testing.assert_allclose(r0.best_theta, want.best_theta, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(lp, want.best_log_probs, rtol=1e-4, atol=1e-3)
+        assert np.array_equal(np.argmax(lp, axis=1), np.argmax(want.best_log_probs, axis=1))
