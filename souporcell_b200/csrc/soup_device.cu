@@ -1238,6 +1238,11 @@ extern "C" int32_t soup_troublet(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     // beyond them is `unwrap()` on None
     if (k > n_clusters) return ctx->fail(SOUP_ERR_INVALID, "called `Option::unwrap()` on a `None` value (more log-probability columns than clusters)");
     if (n_cells >= (1ull << 31) || n_loci >= (1ull << 31)) return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_troublet: more than 2^31 cells / loci");
+    if (row_ptr[0] != 0 || row_ptr[n_cells] != nnz) return ctx->fail(SOUP_ERR_INVALID, "soup_troublet: row_ptr does not span [0, nnz]");
+    for (uint64_t c = 0; c < n_cells; ++c)
+        if (row_ptr[c + 1] < row_ptr[c]) return ctx->fail(SOUP_ERR_INVALID, "soup_troublet: row_ptr not monotone at cell %llu", (unsigned long long)c);
+    for (uint64_t j = 0; j < nnz; ++j)
+        if (locus[j] >= n_loci) return ctx->fail(SOUP_ERR_INVALID, "soup_troublet: locus index out of range at entry %llu", (unsigned long long)j);
     CK(cudaSetDevice(ctx->device));
     FILE* log = (FILE*)log_file;
     cudaStream_t st = ctx->stream;
