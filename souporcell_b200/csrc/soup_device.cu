@@ -43,6 +43,8 @@ struct Workspace {
     float* stats = nullptr;     // cell-sharded mode: [SP | DP | per-slot loss], one all-reduce per iteration
     size_t stats_floats = 0;
     int2* moves = nullptr;
+    int* k_of_draw = nullptr;   // [K] cluster of compact weight column d (locked clusters keep no weight column)
+    int nd = 0;                 // weight columns per slot: K, or the re-drawn clusters of a souporcell3 re-run
     uint32_t* stream_keys = nullptr;
     int n_streams_cap = 0;
     std::vector<void*> allocs;
@@ -564,7 +566,7 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     A(&w.col_write, w.Cpad, true); A(&w.k_locked, (size_t)K, true);
     A(&w.e_group_active, (size_t)w.ep.n_groups, true); A(&w.m_group_active, (size_t)w.mp.n_groups, true);
     A(&w.l_group_active, (size_t)w.lp.n_groups, true); A(&w.counts, cols, true);
-    A(&w.queue, (size_t)queue_cap, true); A(&w.draw_of_k, (size_t)K, true);
+    A(&w.queue, (size_t)queue_cap, true); A(&w.draw_of_k, (size_t)K, true); A(&w.k_of_draw, (size_t)K, true);
     A(&w.solve_iters, (size_t)queue_cap, true); A(&w.solve_loss, (size_t)queue_cap, true);
     A(&w.best_lp, N * K, true); A(&w.best_theta, L * K, true);
     A(&w.trace, (size_t)queue_cap * iter_cap, true);
@@ -630,7 +632,7 @@ static void launch_m(soup_ctx* ctx) {
                   w.m_group_active, w.l_group_active, w.ctl, w.stats, w.stats ? w.stats + (size_t)ctx->L * w.Cpad : nullptr, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups,
                   n_long, (uint32_t)w.lp.n_groups, long_blocks, wide_chunks,
                   (uint32_t)((uint64_t)ctx->N * w.Cpad * 4 > (48ull << 20)), (uint32_t)(w.forced_lanes != 0),
-                  coop ? (uint32_t)ctx->long_coop : 0u, ctx->tail_cols, n_tail};
+                  coop ? (uint32_t)ctx->long_coop : 0u, ctx->tail_cols, n_tail, w.k_of_draw, (uint32_t)w.K, (uint32_t)(w.nd > 0 ? w.nd : w.K)};
     if (coop) {
         const uint32_t groups256 = (w.Cpad + ML_THREADS - 1) / ML_THREADS;
         const uint32_t blocks = ctx->long_coop == 2 ? std::max(n_tail, n_long * groups256) : n_tail;
@@ -645,7 +647,8 @@ static void launch_m(soup_ctx* ctx) {
 }
 static void launch_post(soup_ctx* ctx, int method, bool counts) {
     Workspace& w = ctx->ws;
-    PostArgs a{w.ELL, w.W, w.LSE, ctx->d_total_alleles, w.st, w.ctl, counts ? w.counts : nullptr, (uint32_t)ctx->N, w.Cpad, w.K, w.slots, method};
+    PostArgs a{w.ELL, w.W, w.LSE, ctx->d_total_alleles, w.st, w.ctl, counts ? w.counts : nullptr, (uint32_t)ctx->N, w.Cpad, w.K, w.slots, method,
+               w.draw_of_k, w.nd > 0 ? w.nd : w.K};
     if (ctx->N) post_kernel<<<dim3((unsigned)((ctx->N + POST_WARPS - 1) / POST_WARPS), (unsigned)((w.slots + 31) / 32)), 32 * POST_WARPS, 0, ctx->stream>>>(a);
 }
 static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
@@ -846,6 +849,13 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     CKS(cudaMemcpyAsync(w.stream_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, st));
     CKS(cudaMemcpyAsync(w.queue, queue.data(), (size_t)n_local * 4, cudaMemcpyHostToDevice, st));
     CKS(cudaMemcpyAsync(w.draw_of_k, draw_of_k.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    {   // weight columns: only the clusters this run draws (S:92-97 locks the rest); SOUP_NO_COMPACT_W keeps all K (tests / comparison)
+        std::vector<int> k_of_draw(K, 0);
+        for (int k = 0; k < K; ++k) if (draw_of_k[k] >= 0) k_of_draw[draw_of_k[k]] = k;
+        w.nd = getenv("SOUP_NO_COMPACT_W") ? K : n_draw;
+        if (w.nd == K && n_draw != K) for (int k = 0; k < K; ++k) k_of_draw[k] = k;
+        CKS(cudaMemcpyAsync(w.k_of_draw, k_of_draw.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+    }
     CKS(cudaMemcpyAsync(w.k_locked, k_locked.data(), (size_t)K, cudaMemcpyHostToDevice, st));
     h2d += keys.size() * 4 + (size_t)n_local * 4 + (size_t)K * 5;
     // ---- init_cluster_centers_random_assignment S:565-594: place the three phases of every solve in its seed stream.
@@ -1079,6 +1089,7 @@ static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
     if (rc != SOUP_OK) return rc;
     Workspace& w = ctx->ws;
     w.stats = nullptr;          // the hooks always run the single-GPU M pass
+    w.nd = k;                   // ... with a weight column for every cluster
     w.stats_floats = 0;
     std::vector<int> ga(std::max(std::max(w.ep.n_groups, w.mp.n_groups), w.lp.n_groups), 1);
     cudaMemcpyAsync(w.l_group_active, ga.data(), (size_t)w.lp.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);

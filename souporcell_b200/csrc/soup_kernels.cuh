@@ -473,6 +473,10 @@ struct PostArgs {
     int* counts;          // [slots][K] cells per cluster (LAST max, S:254), or nullptr
     uint32_t N, Cpad;
     int K, slots, method;
+    // Locked clusters (souporcell3 re-runs, S:92-97) take no part in the M pass: the weights of the nd re-drawn clusters of a slot are
+    // stored compactly, W[cell][slot*nd + draw_of_k[k]], and the M kernels map their columns back (MArgs::k_of_draw).  nd == K: plain layout.
+    const int* draw_of_k; // [K]: compact index of cluster k, -1 = locked
+    int nd;
 };
 
 __device__ __forceinline__ float rust_lse(const float* x, int K) {   // log_sum_exp S:428-432
@@ -499,7 +503,9 @@ __global__ void __launch_bounds__(32 * POST_WARPS) post_kernel(PostArgs a) {
     if (!s.active) return;
     const int K = a.K;
     const float* x = a.ELL + (size_t)cell * a.Cpad + (size_t)slot * K;
-    float* w = a.W + (size_t)cell * a.Cpad + (size_t)slot * K;
+    float* w = a.W + (size_t)cell * a.Cpad + (size_t)slot * a.nd;
+    const bool compact = a.nd != K;   // write p_k at its compact position, skip locked clusters
+#define SOUP_STORE_W(k, val) do { const float v_ = (val); if (!compact) w[k] = v_; else { const int d_ = a.draw_of_k[k]; if (d_ >= 0) w[d_] = v_; } } while (0)
     a.LSE[(size_t)slot * a.N + cell] = rust_lse(x, K);
     const float total = a.total_alleles[cell];
     float temp;
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(32 * POST_WARPS) post_kernel(PostArgs a) {
         float sum = 0.0f;
         for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf(x[k] / temp - m);
         const float lse = m + soupmath::glibc_logf(sum);
-        for (int k = 0; k < K; ++k) w[k] = soupmath::glibc_expf(x[k] / temp - lse);
+        for (int k = 0; k < K; ++k) SOUP_STORE_W(k, soupmath::glibc_expf(x[k] / temp - lse));
     } else {
         // calculate_q_for_current_cell S:360-384 in the reference's literal operation order
         int win = 0;
@@ -538,9 +544,10 @@ __global__ void __launch_bounds__(32 * POST_WARPS) post_kernel(PostArgs a) {
         sum = 0.0f;
         for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf((SOUP_Q(k) - q_sum) / temp - m);
         const float lse = m + soupmath::glibc_logf(sum);
-        for (int k = 0; k < K; ++k) w[k] = soupmath::glibc_expf((SOUP_Q(k) - q_sum) / temp - lse);
+        for (int k = 0; k < K; ++k) SOUP_STORE_W(k, soupmath::glibc_expf((SOUP_Q(k) - q_sum) / temp - lse));
 #undef SOUP_Q
     }
+#undef SOUP_STORE_W
     if (a.counts) {   // max_by(total_cmp) keeps the LAST maximum (S:254)
         int bi = 0;
         int32_t bk = total_key(x[0]);
@@ -743,7 +750,17 @@ struct MArgs {
     // long loci by the cooperative kernel (mstep_long_kernel): 0 never, 1 while at most tail_cols columns are live, 2 always.
     // With few live columns it also takes the shorter loci [n_long, n_long_tail) — their one-warp chains would be the tail's critical path.
     uint32_t coop_mode, tail_cols, n_long_tail;
+    // compact weight columns when clusters are locked (PostArgs): column cc of W is (slot cc / nd, re-drawn cluster k_of_draw[cc % nd])
+    const int* k_of_draw;
+    uint32_t K, nd;
 };
+// the prefix of W's columns that holds live weights, and the table column a weight column belongs to
+__device__ __forceinline__ uint32_t m_live_cols(const MArgs& a) { return a.nd == a.K ? a.ctl->live_cols : a.ctl->live_cols / a.K * a.nd; }
+__device__ __forceinline__ uint32_t m_table_col(const MArgs& a, uint32_t cc) {
+    if (a.nd == a.K) return cc;
+    const uint32_t slot = cc / a.nd;
+    return slot * a.K + (uint32_t)a.k_of_draw[cc - slot * a.nd];
+}
 __device__ __forceinline__ bool m_coop(const MArgs& a, uint32_t live) { return a.coop_mode == 2 || (a.coop_mode == 1 && live <= a.tail_cols); }
 __device__ __forceinline__ uint32_t m_coop_loci(const MArgs& a, uint32_t live) { return live <= a.tail_cols ? a.n_long_tail : a.n_long; }
 
@@ -769,7 +786,9 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         if ((v >> 2) >= 1 && !((lc.hm >> (v >> 2)) & 1u)) continue;   // dead sub-block
-        const uint32_t c = col_of<V>(col0, lane, v);
+        const uint32_t cc = col_of<V>(col0, lane, v);
+        if (cc >= live_cols) continue;                  // beyond the live weight columns (compact layouts leave the rest of W stale)
+        const uint32_t c = m_table_col(a, cc);
         const size_t o = (size_t)locus * a.Cpad + c;
         if (partial) {   // cell-sharded: hand the partial statistics to the all-reduce; theta_kernel finishes the M pass
             a.SP[o] = s.v[v];
@@ -791,7 +810,7 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
 template <int VM>
 __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256 / EM_THREADS)) mstep_kernel(const MArgs a) {
     const uint32_t warp = EM_WARPS > 1 ? threadIdx.x >> 5 : 0;
-    const uint32_t live = a.ctl->live_cols;
+    const uint32_t live = m_live_cols(a);
     const bool coop = m_coop(a, live);
     if (blockIdx.x < a.long_blocks) {
         if (coop) return;                       // mstep_long_kernel owns the long loci
@@ -799,7 +818,7 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256
         if (item >= a.n_long * a.long_groups) return;
         const uint32_t li = item / a.long_groups, group = item - li * a.long_groups;
         const uint32_t col0 = group * (32 * SOUP_M_VLONG);
-        if (col0 >= live || !a.long_group_active[group]) return;
+        if (col0 >= live || (a.nd == a.K && !a.long_group_active[group])) return;   // (the activity masks are in table columns)
         mstep_body<SOUP_M_VLONG, true>(a, a.locus_order[li], col0, live);
         return;
     }
@@ -810,7 +829,7 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256
     if (a.group_major) { group = bi / a.wide_chunks; chunk = bi - group * a.wide_chunks; }
     else { chunk = bi / a.n_groups; group = bi - chunk * a.n_groups; }
     const uint32_t col0 = group * (32 * VM);
-    if (col0 >= live || !a.group_active[group]) return;
+    if (col0 >= live || (a.nd == a.K && !a.group_active[group])) return;
     const uint32_t li = (coop ? m_coop_loci(a, live) : a.n_long) + chunk * EM_WARPS + warp;
     if (li >= a.L) return;
     const uint32_t locus = a.locus_order[li];
@@ -865,7 +884,7 @@ __device__ __forceinline__ void cp_async_wait_dyn(uint32_t pending) {   // the i
 __global__ void __launch_bounds__(ML_THREADS) mstep_long_kernel(const MArgs a) {
     extern __shared__ __align__(16) float rows[];                 // ML_SMEM_FLOATS floats of row stages
     __shared__ float2 counts[ML_MAX_STAGES][ML_MAX_CHUNK];
-    const uint32_t live = min(a.ctl->live_cols, a.Cpad);
+    const uint32_t live = min(m_live_cols(a), a.Cpad);
     if (!m_coop(a, live)) return;
     // few live columns: one CTA per locus (the live columns fit one CTA); otherwise one per (locus, 256 columns)
     const uint32_t n_groups = live <= a.tail_cols ? 1 : (a.Cpad + ML_THREADS - 1) / ML_THREADS;
@@ -947,7 +966,7 @@ __global__ void __launch_bounds__(ML_THREADS) mstep_long_kernel(const MArgs a) {
         __syncthreads();
     }
     if (t >= rem) return;
-    const uint32_t col = col0 + t;
+    const uint32_t col = m_table_col(a, col0 + t);
     const size_t o = (size_t)locus * a.Cpad + col;
     if (partial) { a.SP[o] = s; a.DP[o] = d; return; }
     if (!a.col_write[col]) return;                                     // locked cluster (S:389) or idle column
