@@ -45,6 +45,12 @@ struct Workspace {
     int2* moves = nullptr;
     int* k_of_draw = nullptr;   // [K] cluster of compact weight column d (locked clusters keep no weight column)
     int nd = 0;                 // weight columns per slot: K, or the re-drawn clusters of a souporcell3 re-run
+    // compact re-run (PostArgs): the engine holds Kx = K columns per slot for the re-drawn clusters of a model with K_out clusters
+    int K_out = 0, Kf = 0;
+    uint32_t min_cols = 0;
+    int *src_of_k = nullptr, *w_of_k = nullptr, *fix_k = nullptr;   // [K_out]
+    float* ELLfix = nullptr;    // [N][K_out] (first Kf columns of a row used)
+    bool mapped = false;        // src_of_k / w_of_k are not the identity
     uint32_t* stream_keys = nullptr;
     int n_streams_cap = 0;
     std::vector<void*> allocs;
@@ -546,12 +552,16 @@ static Workspace::GroupPlan plan_groups(int cols, int vmax, int forced_lanes) {
     return g;
 }
 
-static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lanes, int iter_cap, int queue_cap, int n_streams) {
+// K = clusters per slot in the engine's tables; K_out = clusters of the model (results, counts); min_cols = columns the planes must have at least
+static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lanes, int iter_cap, int queue_cap, int n_streams, int K_out = 0, uint32_t min_cols = 0) {
     Workspace& w = ctx->ws;
-    if (w.K == K && w.slots == slots && w.forced_lanes == forced_lanes && w.iter_cap == iter_cap && w.queue_cap >= queue_cap && w.n_streams_cap >= n_streams) return SOUP_OK;
+    if (K_out <= 0) K_out = K;
+    if (w.K == K && w.slots == slots && w.forced_lanes == forced_lanes && w.iter_cap == iter_cap && w.queue_cap >= queue_cap && w.n_streams_cap >= n_streams &&
+        w.K_out == K_out && w.min_cols == min_cols) return SOUP_OK;
     ws_free(w);
     w.K = K; w.slots = slots; w.forced_lanes = forced_lanes; w.iter_cap = iter_cap; w.queue_cap = queue_cap; w.n_streams_cap = n_streams;
-    const size_t cols = (size_t)slots * K;
+    w.K_out = K_out; w.min_cols = min_cols;
+    const size_t cols = std::max<size_t>((size_t)slots * K, min_cols);
     w.ep = plan_groups((int)cols, SOUP_E_VMAX, forced_lanes);
     w.mp = plan_groups((int)cols, SOUP_M_VWIDE, forced_lanes);
     w.lp = plan_groups((int)cols, SOUP_M_VLONG, SOUP_M_VLONG);
@@ -565,10 +575,12 @@ static int32_t ensure_workspace(soup_ctx* ctx, int K, int slots, int forced_lane
     A(&w.st, (size_t)slots, true); A(&w.ctl, 1, true); A(&w.loss, (size_t)slots, true);
     A(&w.col_write, w.Cpad, true); A(&w.k_locked, (size_t)K, true);
     A(&w.e_group_active, (size_t)w.ep.n_groups, true); A(&w.m_group_active, (size_t)w.mp.n_groups, true);
-    A(&w.l_group_active, (size_t)w.lp.n_groups, true); A(&w.counts, cols, true);
+    A(&w.l_group_active, (size_t)w.lp.n_groups, true); A(&w.counts, (size_t)slots * K_out, true);
+    A(&w.src_of_k, (size_t)K_out, true); A(&w.w_of_k, (size_t)K_out, true); A(&w.fix_k, (size_t)K_out, true);
+    if (K_out != K) A(&w.ELLfix, N * (size_t)K_out, true);
     A(&w.queue, (size_t)queue_cap, true); A(&w.draw_of_k, (size_t)K, true); A(&w.k_of_draw, (size_t)K, true);
     A(&w.solve_iters, (size_t)queue_cap, true); A(&w.solve_loss, (size_t)queue_cap, true);
-    A(&w.best_lp, N * K, true); A(&w.best_theta, L * K, true);
+    A(&w.best_lp, N * K_out, true); A(&w.best_theta, L * K_out, true);
     A(&w.trace, (size_t)queue_cap * iter_cap, true);
     A(&w.stream_keys, (size_t)std::max(n_streams, 1) * 8, true);
     A(&w.moves, (size_t)slots, true);
@@ -596,6 +608,7 @@ struct IterLaunch {
     int32_t comm_error = 0;
     RefillArgs refill;
     FinalizeArgs fin;
+    const float* base_theta_dev = nullptr;   // [K_out][L] centers of the previous run (compact re-run: the locked clusters' rows)
     bool queue_drained = false;   // the host has SEEN queue_head >= queue_len: no slot can get a pending solve any more, so refill launches stop
 };
 
@@ -647,8 +660,8 @@ static void launch_m(soup_ctx* ctx) {
 }
 static void launch_post(soup_ctx* ctx, int method, bool counts) {
     Workspace& w = ctx->ws;
-    PostArgs a{w.ELL, w.W, w.LSE, ctx->d_total_alleles, w.st, w.ctl, counts ? w.counts : nullptr, (uint32_t)ctx->N, w.Cpad, w.K, w.slots, method,
-               w.draw_of_k, w.nd > 0 ? w.nd : w.K};
+    PostArgs a{w.ELL, w.W, w.LSE, ctx->d_total_alleles, w.st, w.ctl, counts ? w.counts : nullptr, (uint32_t)ctx->N, w.Cpad, w.K_out, w.slots, method,
+               w.K, w.nd > 0 ? w.nd : w.K, w.mapped ? w.src_of_k : nullptr, w.mapped ? w.w_of_k : nullptr, w.ELLfix, w.Kf};
     if (ctx->N) post_kernel<<<dim3((unsigned)((ctx->N + POST_WARPS - 1) / POST_WARPS), (unsigned)((w.slots + 31) / 32)), 32 * POST_WARPS, 0, ctx->stream>>>(a);
 }
 static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
@@ -668,7 +681,7 @@ static void launch_loss_control(soup_ctx* ctx, cudaStream_t st, bool counts, flo
     Workspace& w = ctx->ws;
     loss_kernel<<<w.slots, 256, 0, st>>>(w.LSE, w.st, w.loss, (uint32_t)ctx->N);
     ControlArgs c{w.loss, w.st, w.ctl, counts ? w.counts : nullptr, w.trace, w.solve_loss, w.solve_iters,
-                  (uint32_t)ctx->N, w.K, w.slots, w.iter_cap, limit};
+                  (uint32_t)ctx->N, w.K_out, w.slots, w.iter_cap, limit};
     control_kernel<<<1, std::min(1024, (w.slots + 31) / 32 * 32), 0, st>>>(c);
 }
 
@@ -706,7 +719,8 @@ static void enqueue_iteration(IterLaunch& it) {
         if (ev) cudaEventRecord(ev[3], ctx->stream);
         cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     }
-    harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K);
+    harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K_out, w.K,
+                                                               w.mapped ? w.src_of_k : nullptr, w.ELLfix, w.Kf, it.base_theta_dev);
     if (!it.queue_drained) launch_refill(ctx, it.refill);
     finalize_kernel<<<1, 1024, 0, ctx->stream>>>(it.fin);
     migrate_kernel<<<dim3(96, (unsigned)w.slots), 256, 0, ctx->stream>>>(w.ctl, w.moves, w.TH, w.LA, w.LB, (uint32_t)ctx->L, w.Cpad, w.K);
@@ -725,7 +739,14 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         return ctx->fail(SOUP_ERR_INVALID, "soup_solve: bad reinit_clusters / base_theta");
     if ((uint64_t)p->n_streams * (uint64_t)p->solves_per_stream > (1u << 30)) return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: too many solves");
     CK(cudaSetDevice(ctx->device));
-    const int K = p->k;
+    const int Kt = p->k;   // clusters of the model
+    // Compact re-run (souporcell3 runs 1 and 2, S:92-97): every solve of the run shares the locked clusters' centers (base_theta), so
+    // their log-likelihood columns are computed once (ELLfix) and the engine — tables, E pass, M pass, memory per slot — holds only the
+    // re-drawn clusters.  Bit-identical: per-cluster arithmetic does not depend on the other clusters.  (With explicit theta0 the locked
+    // clusters may differ per solve: those calls keep all K columns and only drop the locked ones from the M pass.)
+    const bool compact_run = p->n_reinit > 0 && p->n_reinit < Kt && !p->theta0 && p->base_theta && !getenv("SOUP_NO_COMPACT_RUN");
+    const int K = compact_run ? p->n_reinit : Kt;   // clusters per slot in the engine
+    const int Kf = compact_run ? Kt - K : 0;
     const int n_solves = p->n_streams * p->solves_per_stream;
     const int world = p->shard_world > 1 ? p->shard_world : 1, rank = world > 1 ? p->shard_rank : 0;
     if (rank < 0 || rank >= world) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: shard_rank out of range");
@@ -745,7 +766,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     // group), runs the same subset of the solves, and the all-reduce callback spans that group only
     if (cell_mode && p->n_cells_global < ctx->N) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: n_cells_global must be the total cell count over all ranks");
     const float limit = 0.01f * (float)(cell_mode ? p->n_cells_global : ctx->N);   // S:214 (all cells)
-    const float log_prior = logf(1.0f / (float)K);             // S:202 (host libm = the reference's f32::ln)
+    const float log_prior = logf(1.0f / (float)Kt);            // S:202 (host libm = the reference's f32::ln)
     const bool any_iteration = (10000.0f > limit) && iter_cap > 0;
     if (n_local == 0 || !any_iteration) {
         // em()/khm() with no iteration returns (-inf, empty): nothing can beat -inf (S:65, S:110)
@@ -759,14 +780,14 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     PhaseTimer pt;
     // a workspace of exactly this shape already exists (a repeated job): nothing to size, and cudaMemGetInfo — a driver
     // call that was seen to take tens of milliseconds now and then — stays off the repeated path
-    const bool reuse = !p->theta0 && ctx->ws.K == K && ctx->ws.slots == std::min(slots, 1024) && ctx->ws.iter_cap == iter_cap &&
-                       ctx->ws.queue_cap >= n_local && ctx->ws.n_streams_cap >= p->n_streams;
+    const bool reuse = !p->theta0 && ctx->ws.K == K && ctx->ws.K_out == Kt && ctx->ws.min_cols == (uint32_t)Kf && ctx->ws.slots == std::min(slots, 1024) &&
+                       ctx->ws.iter_cap == iter_cap && ctx->ws.queue_cap >= n_local && ctx->ws.n_streams_cap >= p->n_streams;
     if (!reuse) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         free_b += ctx->ws.bytes;
-        size_t fixed = (size_t)K * (ctx->L + ctx->N) * 4 + (size_t)n_local * iter_cap * sizeof(IterRec) + (64u << 20);
-        if (p->theta0) fixed += (size_t)n_solves * K * ctx->L * 4;
+        size_t fixed = (size_t)Kt * (ctx->L + 2 * ctx->N) * 4 + (size_t)n_local * iter_cap * sizeof(IterRec) + (64u << 20);
+        if (p->theta0) fixed += (size_t)n_solves * Kt * ctx->L * 4;
         size_t per = bytes_per_slot(ctx, K);
         if (free_b < fixed + per) return ctx->fail(SOUP_ERR_NOMEM, "soup_solve: not enough device memory for one resident solve");
         size_t cap = (size_t)((double)(free_b - fixed) * 0.85 / (double)per);
@@ -779,7 +800,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         return ctx->fail(SOUP_ERR_UNSUPPORTED, "soup_solve: max(cells, loci) * k exceeds the 32-bit row-offset range");
     pt.lap("solve: shape");
     const int forced_lanes = (p->lanes == 1 || p->lanes == 2 || p->lanes == 4 || p->lanes == 8 || p->lanes == 16) ? p->lanes : 0;
-    int32_t rc = ensure_workspace(ctx, K, slots, forced_lanes, iter_cap, n_local, p->n_streams);
+    int32_t rc = ensure_workspace(ctx, K, slots, forced_lanes, iter_cap, n_local, p->n_streams, Kt, (uint32_t)Kf);
     if (rc != SOUP_OK) return rc;
     pt.lap("solve: workspace");
     Workspace& w = ctx->ws;
@@ -810,35 +831,48 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     } while (0)
     std::vector<int> draw_of_k(K);
     std::vector<uint8_t> k_locked(K, 0);
+    std::vector<int> src_of_k(Kt), w_of_k(Kt), fix_k(Kt, 0);
+    for (int k = 0; k < Kt; ++k) src_of_k[k] = w_of_k[k] = k;
     int n_draw = K;
+    bool mapped = false;
     if (p->n_reinit > 0) {   // S:92-97: re-draw the flagged clusters in list order, lock the rest
-        std::fill(draw_of_k.begin(), draw_of_k.end(), -1);
-        std::fill(k_locked.begin(), k_locked.end(), 1);
+        std::vector<int> pos(Kt, -1);
         for (int i = 0; i < p->n_reinit; ++i) {
             int c = p->reinit_clusters[i];
-            if (c < 0 || c >= K || draw_of_k[c] >= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: bad reinit_clusters entry");
-            draw_of_k[c] = i;
-            k_locked[c] = 0;
+            if (c < 0 || c >= Kt || pos[c] >= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: bad reinit_clusters entry");
+            pos[c] = i;
         }
         n_draw = p->n_reinit;
+        if (compact_run) {   // the engine's cluster d is the model's cluster reinit_clusters[d]; nothing is locked inside the engine
+            for (int d = 0; d < K; ++d) draw_of_k[d] = d;
+            int j = 0;
+            for (int k = 0; k < Kt; ++k) {
+                if (pos[k] >= 0) { src_of_k[k] = w_of_k[k] = pos[k]; }
+                else { src_of_k[k] = -(j + 1); w_of_k[k] = -1; fix_k[j++] = k; }
+            }
+            mapped = true;
+        } else {
+            for (int k = 0; k < Kt; ++k) { draw_of_k[k] = pos[k]; k_locked[k] = pos[k] < 0; }
+            if (!getenv("SOUP_NO_COMPACT_W")) { for (int k = 0; k < Kt; ++k) w_of_k[k] = pos[k]; mapped = true; }
+        }
     } else {
         for (int k = 0; k < K; ++k) draw_of_k[k] = k;
     }
     uint64_t h2d = 0;
     if (p->theta0) {
-        size_t n = (size_t)n_solves * K * ctx->L;
+        size_t n = (size_t)n_solves * Kt * ctx->L;
         CKS(cudaMalloc(&d_theta0, std::max<size_t>(n, 1) * 4));
         CKS(cudaMemcpyAsync(d_theta0, p->theta0, n * 4, cudaMemcpyHostToDevice, st));
         h2d += n * 4;
     }
     if (p->base_theta && p->n_reinit > 0) {
-        size_t n = (size_t)K * ctx->L;
+        size_t n = (size_t)Kt * ctx->L;
         CKS(cudaMalloc(&d_base, std::max<size_t>(n, 1) * 4));
         CKS(cudaMemcpyAsync(d_base, p->base_theta, n * 4, cudaMemcpyHostToDevice, st));
         h2d += n * 4;
     }
     if (p->init_theta) {
-        size_t n = (size_t)K * ctx->L;
+        size_t n = (size_t)Kt * ctx->L;
         CKS(cudaMalloc(&d_init, std::max<size_t>(n, 1) * 4));
         CKS(cudaMemcpyAsync(d_init, p->init_theta, n * 4, cudaMemcpyHostToDevice, st));
         h2d += n * 4;
@@ -849,12 +883,29 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     CKS(cudaMemcpyAsync(w.stream_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, st));
     CKS(cudaMemcpyAsync(w.queue, queue.data(), (size_t)n_local * 4, cudaMemcpyHostToDevice, st));
     CKS(cudaMemcpyAsync(w.draw_of_k, draw_of_k.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
-    {   // weight columns: only the clusters this run draws (S:92-97 locks the rest); SOUP_NO_COMPACT_W keeps all K (tests / comparison)
+    {   // weight columns: only the clusters this run draws (S:92-97 locks the rest); in a compact re-run the engine holds nothing else anyway
         std::vector<int> k_of_draw(K, 0);
         for (int k = 0; k < K; ++k) if (draw_of_k[k] >= 0) k_of_draw[draw_of_k[k]] = k;
-        w.nd = getenv("SOUP_NO_COMPACT_W") ? K : n_draw;
-        if (w.nd == K && n_draw != K) for (int k = 0; k < K; ++k) k_of_draw[k] = k;
+        w.nd = (!compact_run && mapped) ? n_draw : K;
+        w.mapped = mapped; w.Kf = Kf;
         CKS(cudaMemcpyAsync(w.k_of_draw, k_of_draw.data(), (size_t)K * 4, cudaMemcpyHostToDevice, st));
+        CKS(cudaMemcpyAsync(w.src_of_k, src_of_k.data(), (size_t)Kt * 4, cudaMemcpyHostToDevice, st));
+        CKS(cudaMemcpyAsync(w.w_of_k, w_of_k.data(), (size_t)Kt * 4, cudaMemcpyHostToDevice, st));
+        CKS(cudaMemcpyAsync(w.fix_k, fix_k.data(), (size_t)Kt * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (compact_run) {   // ---- the locked clusters' log-likelihood columns, once for the whole run
+        Ctl hc0{};
+        hc0.copy_slot = -1; hc0.best_solve = -1; hc0.best_loss = -INFINITY; hc0.live_cols = (uint32_t)Kf;
+        CKS(cudaMemcpyAsync(w.ctl, &hc0, sizeof(Ctl), cudaMemcpyHostToDevice, st));
+        std::vector<int> ones(w.ep.n_groups, 1);
+        CKS(cudaMemcpyAsync(w.e_group_active, ones.data(), (size_t)w.ep.n_groups * 4, cudaMemcpyHostToDevice, st));
+        const size_t ne = (size_t)ctx->L * Kf;
+        if (ne) fixed_tables_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(d_base, w.fix_k, w.LA, w.LB, w.ctl, (uint32_t)ctx->L, w.Cpad, Kf);
+        launch_e(ctx, log_prior);
+        const size_t nc = (size_t)ctx->N * Kf;
+        if (nc) copy_fixed_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(w.ELL, w.ELLfix, (uint32_t)ctx->N, w.Cpad, Kf);
+        CKS(cudaStreamSynchronize(st));   // `ones` goes out of scope
+        CKS(cudaGetLastError());
     }
     CKS(cudaMemcpyAsync(w.k_locked, k_locked.data(), (size_t)K, cudaMemcpyHostToDevice, st));
     h2d += keys.size() * 4 + (size_t)n_local * 4 + (size_t)K * 5;
@@ -921,11 +972,12 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     hc.queue_head = std::min(slots, n_local); hc.queue_len = n_local; hc.copy_slot = -1; hc.best_solve = -1; hc.best_loss = -INFINITY;
     CKS(cudaMemcpyAsync(w.st, hst.data(), sizeof(SlotState) * slots, cudaMemcpyHostToDevice, st));
     CKS(cudaMemcpyAsync(w.ctl, &hc, sizeof(Ctl), cudaMemcpyHostToDevice, st));
-    CKS(cudaMemsetAsync(w.counts, 0, (size_t)slots * K * 4, st));
+    CKS(cudaMemsetAsync(w.counts, 0, (size_t)slots * Kt * 4, st));
 
     IterLaunch it;
     it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0 && !cell_mode;
     it.allreduce = p->cell_allreduce; it.comm_user = p->comm_user;
+    it.base_theta_dev = d_base;
     it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, d_init, w.draw_of_k, w.TH, w.LA, w.LB,
                            (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream,
                            d_assign, d_words, d_words ? d_words + n_local : nullptr, ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->pk_csc, (uint32_t)ctx->N};
@@ -1016,8 +1068,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     r->best_loss = fc.best_loss;
     r->nnz_updates = ctx->nnz * total_iters;
     if (fc.has_best) {
-        if (r->best_log_probs) { CKS(cudaMemcpy(r->best_log_probs, w.best_lp, (size_t)ctx->N * K * 4, cudaMemcpyDeviceToHost)); d2h += (size_t)ctx->N * K * 4; }
-        if (r->best_theta) { CKS(cudaMemcpy(r->best_theta, w.best_theta, (size_t)ctx->L * K * 4, cudaMemcpyDeviceToHost)); d2h += (size_t)ctx->L * K * 4; }
+        if (r->best_log_probs) { CKS(cudaMemcpy(r->best_log_probs, w.best_lp, (size_t)ctx->N * Kt * 4, cudaMemcpyDeviceToHost)); d2h += (size_t)ctx->N * Kt * 4; }
+        if (r->best_theta) { CKS(cudaMemcpy(r->best_theta, w.best_theta, (size_t)ctx->L * Kt * 4, cudaMemcpyDeviceToHost)); d2h += (size_t)ctx->L * Kt * 4; }
     }
     // per-iteration trace (S:264 / S:354)
     if (p->keep_trace) {
@@ -1090,6 +1142,7 @@ static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
     Workspace& w = ctx->ws;
     w.stats = nullptr;          // the hooks always run the single-GPU M pass
     w.nd = k;                   // ... with a weight column for every cluster
+    w.mapped = false; w.Kf = 0;
     w.stats_floats = 0;
     std::vector<int> ga(std::max(std::max(w.ep.n_groups, w.mp.n_groups), w.lp.n_groups), 1);
     cudaMemcpyAsync(w.l_group_active, ga.data(), (size_t)w.lp.n_groups * 4, cudaMemcpyHostToDevice, ctx->stream);

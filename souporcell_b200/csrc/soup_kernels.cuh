@@ -472,41 +472,34 @@ struct PostArgs {
     const Ctl* ctl;
     int* counts;          // [slots][K] cells per cluster (LAST max, S:254), or nullptr
     uint32_t N, Cpad;
-    int K, slots, method;
-    // Locked clusters (souporcell3 re-runs, S:92-97) take no part in the M pass: the weights of the nd re-drawn clusters of a slot are
-    // stored compactly, W[cell][slot*nd + draw_of_k[k]], and the M kernels map their columns back (MArgs::k_of_draw).  nd == K: plain layout.
-    const int* draw_of_k; // [K]: compact index of cluster k, -1 = locked
-    int nd;
+    int K, slots, method; // K = every cluster of the model (the loops below run over all of them, in index order)
+    // Locked clusters of the souporcell3 re-runs (S:92-97).  Their centers never change during the run, so
+    //  * their log-likelihood columns are computed ONCE per run (ELLfix [N][Kf]) and the engine's tables / E / M passes hold only the
+    //    Kx re-drawn clusters per slot: cluster k reads ELL[cell][slot*Kx + src_of_k[k]] if src_of_k[k] >= 0, else ELLfix[cell][-src_of_k[k]-1];
+    //  * they take no part in the M pass: the weight of cluster k goes to W[cell][slot*nd + w_of_k[k]], or nowhere if w_of_k[k] < 0.
+    // nullptr = identity (every cluster has its own engine column / weight column).
+    int Kx, nd;
+    const int* src_of_k;
+    const int* w_of_k;
+    const float* ELLfix;
+    int Kf;
 };
-
-__device__ __forceinline__ float rust_lse(const float* x, int K) {   // log_sum_exp S:428-432
-    float m = -INFINITY;
-    for (int k = 0; k < K; ++k) m = fmaxf(m, x[k]);
-    float s = 0.0f;
-    for (int k = 0; k < K; ++k) s = s + soupmath::glibc_expf(x[k] - m);
-    return m + soupmath::glibc_logf(s);
-}
 
 // thread = (cell, slot), slot fastest: a warp covers `sw` neighbouring slots of 32 / sw cells, so its ELL / W accesses —
 // nearly all of this kernel's traffic — are contiguous runs of sw*K*4 bytes (the LSE store, 4 bytes per thread, is the
 // strided one).  sw = 32 while many solves are live, the next power of two above the live slots in the tail of a job.
 constexpr int POST_WARPS = 4;
-__global__ void __launch_bounds__(32 * POST_WARPS) post_kernel(PostArgs a) {
-    const uint32_t live_slots = min((a.ctl->live_cols + (uint32_t)a.K - 1) / (uint32_t)a.K, (uint32_t)a.slots);
-    uint32_t sw = 32;
-    while (sw > 1 && (sw >> 1) >= live_slots) sw >>= 1;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cw = 32 / sw;
-    const uint32_t cell = (blockIdx.x * POST_WARPS + warp) * cw + lane / sw;
-    const int slot = (int)(blockIdx.y * 32 + (lane & (sw - 1)));
-    if (cell >= a.N || slot >= a.slots || (uint32_t)slot >= live_slots) return;
-    const SlotState s = a.st[slot];
-    if (!s.active) return;
+
+template <typename Fetch, typename Store>
+__device__ __forceinline__ void post_body(const PostArgs& a, uint32_t cell, int slot, const SlotState& s, Fetch X, Store put) {
     const int K = a.K;
-    const float* x = a.ELL + (size_t)cell * a.Cpad + (size_t)slot * K;
-    float* w = a.W + (size_t)cell * a.Cpad + (size_t)slot * a.nd;
-    const bool compact = a.nd != K;   // write p_k at its compact position, skip locked clusters
-#define SOUP_STORE_W(k, val) do { const float v_ = (val); if (!compact) w[k] = v_; else { const int d_ = a.draw_of_k[k]; if (d_ >= 0) w[d_] = v_; } } while (0)
-    a.LSE[(size_t)slot * a.N + cell] = rust_lse(x, K);
+    {   // log_sum_exp S:428-432
+        float m = -INFINITY;
+        for (int k = 0; k < K; ++k) m = fmaxf(m, X(k));
+        float sum = 0.0f;
+        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf(X(k) - m);
+        a.LSE[(size_t)slot * a.N + cell] = m + soupmath::glibc_logf(sum);
+    }
     const float total = a.total_alleles[cell];
     float temp;
     if (a.method == SOUP_METHOD_EM) temp = fmaxf(total / ldexpf(20.0f, s.temp_step), 1.0f);   // S:233
@@ -515,24 +508,24 @@ __global__ void __launch_bounds__(32 * POST_WARPS) post_kernel(PostArgs a) {
     if (a.method == SOUP_METHOD_EM) {
         // normalize_in_log_with_temp S:443-454 on the log-likelihoods themselves
         float m = -INFINITY;
-        for (int k = 0; k < K; ++k) m = fmaxf(m, x[k] / temp);
+        for (int k = 0; k < K; ++k) m = fmaxf(m, X(k) / temp);
         float sum = 0.0f;
-        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf(x[k] / temp - m);
+        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf(X(k) / temp - m);
         const float lse = m + soupmath::glibc_logf(sum);
-        for (int k = 0; k < K; ++k) SOUP_STORE_W(k, soupmath::glibc_expf(x[k] / temp - lse));
+        for (int k = 0; k < K; ++k) put(k, soupmath::glibc_expf(X(k) / temp - lse));
     } else {
         // calculate_q_for_current_cell S:360-384 in the reference's literal operation order
         int win = 0;
         float best = -3.40282347e+38f;   // f32::MIN S:411
-        for (int k = 0; k < K; ++k) if (x[k] > best) { best = x[k]; win = k; }
-        const float wl = -x[win];
+        for (int k = 0; k < K; ++k) { const float xk = X(k); if (xk > best) { best = xk; win = k; } }
+        const float wl = -X(win);
         float m = -INFINITY;
-        for (int k = 0; k < K; ++k) m = fmaxf(m, k != win ? 25.0f * (wl + x[k]) : 0.0f);
+        for (int k = 0; k < K; ++k) m = fmaxf(m, k != win ? 25.0f * (wl + X(k)) : 0.0f);
         float sum = 0.0f;
-        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf((k != win ? 25.0f * (wl + x[k]) : 0.0f) - m);
+        for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf((k != win ? 25.0f * (wl + X(k)) : 0.0f) - m);
         const float q_denom = m + soupmath::glibc_logf(sum);
         const float c0 = 50.0f * wl, c2 = 2.0f * q_denom;
-#define SOUP_Q(k) ((c0 - (27.0f * -x[k])) - c2)
+#define SOUP_Q(k) ((c0 - (27.0f * -X(k))) - c2)
         m = -INFINITY;
         for (int k = 0; k < K; ++k) m = fmaxf(m, SOUP_Q(k));
         sum = 0.0f;
@@ -544,18 +537,39 @@ __global__ void __launch_bounds__(32 * POST_WARPS) post_kernel(PostArgs a) {
         sum = 0.0f;
         for (int k = 0; k < K; ++k) sum = sum + soupmath::glibc_expf((SOUP_Q(k) - q_sum) / temp - m);
         const float lse = m + soupmath::glibc_logf(sum);
-        for (int k = 0; k < K; ++k) SOUP_STORE_W(k, soupmath::glibc_expf((SOUP_Q(k) - q_sum) / temp - lse));
+        for (int k = 0; k < K; ++k) put(k, soupmath::glibc_expf((SOUP_Q(k) - q_sum) / temp - lse));
 #undef SOUP_Q
     }
-#undef SOUP_STORE_W
     if (a.counts) {   // max_by(total_cmp) keeps the LAST maximum (S:254)
         int bi = 0;
-        int32_t bk = total_key(x[0]);
+        int32_t bk = total_key(X(0));
         for (int k = 1; k < K; ++k) {
-            int32_t kk = total_key(x[k]);
+            int32_t kk = total_key(X(k));
             if (kk >= bk) { bk = kk; bi = k; }
         }
         atomicAdd(a.counts + (size_t)slot * K + bi, 1);
+    }
+}
+
+__global__ void __launch_bounds__(32 * POST_WARPS) post_kernel(PostArgs a) {
+    const uint32_t live_slots = min((a.ctl->live_cols + (uint32_t)a.Kx - 1) / (uint32_t)a.Kx, (uint32_t)a.slots);
+    uint32_t sw = 32;
+    while (sw > 1 && (sw >> 1) >= live_slots) sw >>= 1;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cw = 32 / sw;
+    const uint32_t cell = (blockIdx.x * POST_WARPS + warp) * cw + lane / sw;
+    const int slot = (int)(blockIdx.y * 32 + (lane & (sw - 1)));
+    if (cell >= a.N || slot >= a.slots || (uint32_t)slot >= live_slots) return;
+    const SlotState s = a.st[slot];
+    if (!s.active) return;
+    const float* x = a.ELL + (size_t)cell * a.Cpad + (size_t)slot * a.Kx;
+    float* w = a.W + (size_t)cell * a.Cpad + (size_t)slot * a.nd;
+    if (!a.src_of_k && !a.w_of_k) {
+        post_body(a, cell, slot, s, [&](int k) { return x[k]; }, [&](int k, float v) { w[k] = v; });
+    } else {
+        const float* fx = a.ELLfix + (size_t)cell * a.Kf;
+        post_body(a, cell, slot, s,
+                  [&](int k) { const int i = a.src_of_k ? a.src_of_k[k] : k; return i >= 0 ? x[i] : fx[-i - 1]; },
+                  [&](int k, float v) { const int d = a.w_of_k ? a.w_of_k[k] : k; if (d >= 0) w[d] = v; });
     }
 }
 
@@ -993,21 +1007,46 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ SP
 }
 
 // ------------------------------------------------------------------ harvest: keep the best solve (S:110-114)
+// `src_of_k` (or nullptr = identity): where cluster k of the model lives — engine column slot*Kx + src_of_k[k], or, for a cluster locked
+// during a souporcell3 re-run (src < 0), the per-run ELLfix column / its unchanged row of base_theta (PostArgs)
 __global__ void harvest_kernel(const Ctl* __restrict__ ctl, const float* __restrict__ ELL, const float* __restrict__ TH,
                                float* __restrict__ best_lp, float* __restrict__ best_theta, uint32_t N, uint32_t L,
-                               uint32_t Cpad, int K) {
+                               uint32_t Cpad, int K, int Kx, const int* __restrict__ src_of_k, const float* __restrict__ ELLfix, int Kf,
+                               const float* __restrict__ base_theta) {
     const int slot = ctl->copy_slot;
     if (slot < 0) return;
     const size_t nlp = (size_t)N * K, nth = (size_t)L * K;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nlp + nth; i += (size_t)gridDim.x * blockDim.x) {
         if (i < nlp) {
             const size_t cell = i / K, k = i - cell * K;
-            best_lp[i] = ELL[cell * Cpad + (size_t)slot * K + k];
+            const int src = src_of_k ? src_of_k[k] : (int)k;
+            best_lp[i] = src >= 0 ? ELL[cell * Cpad + (size_t)slot * Kx + src] : ELLfix[cell * Kf + (-src - 1)];
         } else {
             const size_t e = i - nlp, l = e / K, k = e - l * K;
-            best_theta[k * L + l] = TH[l * Cpad + (size_t)slot * K + k];
+            const int src = src_of_k ? src_of_k[k] : (int)k;
+            best_theta[k * L + l] = src >= 0 ? TH[l * Cpad + (size_t)slot * Kx + src] : base_theta[k * L + l];
         }
     }
+}
+
+// ELLfix[cell][j] = ELL[cell][j] for j < Kf (the one-off E pass over the locked clusters of a re-run)
+__global__ void copy_fixed_kernel(const float* __restrict__ ELL, float* __restrict__ ELLfix, uint32_t N, uint32_t Cpad, int Kf) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * Kf) return;
+    const size_t cell = i / Kf, j = i - cell * Kf;
+    ELLfix[i] = ELL[cell * Cpad + j];
+}
+// ln tables of the locked clusters in columns [0, Kf): theta = base_theta[fix_k[j]][l]
+__global__ void fixed_tables_kernel(const float* __restrict__ base_theta, const int* __restrict__ fix_k, float* LA, float* LB, Ctl* ctl,
+                                    uint32_t L, uint32_t Cpad, int Kf) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // e = l*Kf + j
+    if (e >= (size_t)L * Kf) return;
+    const size_t l = e / Kf, j = e - l * Kf;
+    const float th = base_theta[(size_t)fix_k[j] * L + l];
+    const float la = soupmath::glibc_logf(th), lb = soupmath::glibc_logf(1.0f - th);
+    LA[l * Cpad + j] = la;
+    LB[l * Cpad + j] = lb;
+    if (!isfinite(la) || !isfinite(lb)) ctl->nonfinite = 1;
 }
 
 // ------------------------------------------------------------------ refill: theta0 of the next solve (S:485-498, 554-563)
