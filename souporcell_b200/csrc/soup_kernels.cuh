@@ -800,9 +800,11 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         if ((v >> 2) >= 1 && !((lc.hm >> (v >> 2)) & 1u)) continue;   // dead sub-block
-        const uint32_t cc = col_of<V>(col0, lane, v);
-        if (cc >= live_cols) continue;                  // beyond the live weight columns (compact layouts leave the rest of W stale)
-        const uint32_t c = m_table_col(a, cc);
+        uint32_t c = col_of<V>(col0, lane, v);
+        if (a.nd != a.K) {                              // compact weight columns: skip what lies beyond the live ones, map the rest back
+            if (c >= live_cols) continue;
+            c = m_table_col(a, c);
+        }
         const size_t o = (size_t)locus * a.Cpad + c;
         if (partial) {   // cell-sharded: hand the partial statistics to the all-reduce; theta_kernel finishes the M pass
             a.SP[o] = s.v[v];
