@@ -770,10 +770,13 @@ struct MArgs {
 };
 // the prefix of W's columns that holds live weights, and the table column a weight column belongs to
 __device__ __forceinline__ uint32_t m_live_cols(const MArgs& a) { return a.nd == a.K ? a.ctl->live_cols : a.ctl->live_cols / a.K * a.nd; }
+// (kept out of line: it runs once per output column and only when clusters are locked, and inlining it costs the hot loops registers)
+__device__ __noinline__ uint32_t m_table_col_mapped(const int* __restrict__ k_of_draw, uint32_t K, uint32_t nd, uint32_t cc) {
+    const uint32_t slot = cc / nd;
+    return slot * K + (uint32_t)k_of_draw[cc - slot * nd];
+}
 __device__ __forceinline__ uint32_t m_table_col(const MArgs& a, uint32_t cc) {
-    if (a.nd == a.K) return cc;
-    const uint32_t slot = cc / a.nd;
-    return slot * a.K + (uint32_t)a.k_of_draw[cc - slot * a.nd];
+    return a.nd == a.K ? cc : m_table_col_mapped(a.k_of_draw, a.K, a.nd, cc);
 }
 __device__ __forceinline__ bool m_coop(const MArgs& a, uint32_t live) { return a.coop_mode == 2 || (a.coop_mode == 1 && live <= a.tail_cols); }
 __device__ __forceinline__ uint32_t m_coop_loci(const MArgs& a, uint32_t live) { return live <= a.tail_cols ? a.n_long_tail : a.n_long; }
