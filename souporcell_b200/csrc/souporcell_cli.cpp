@@ -4,16 +4,18 @@
 // any failure with nothing written to stdout.  All numerics run on the GPU through libsoupgpu.
 //
 // Extra, optional flags (absent from the reference; the pipeline's argv works unchanged):
-//   --gpus N           use the first N visible GPUs (restart-sharded); default: all visible
+//   --gpus N           use the first N visible GPUs (restart-sharded); default: as many as the job can keep busy
 //   --max_slots N      resident solves per GPU (0 = auto)
 //   --quiet_iterations do not print the per-iteration "binomial" lines
 //   --csr_cache FILE   binary cache of the parsed + filtered matrix (.soupcsr): read when it exists and was built
 //                      with the same filter, written after the text parse otherwise
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <chrono>
@@ -44,7 +46,7 @@ const Opt kOpts[] = {
     {"min_ref_umis", 0, false, false, "min ref umis to use locus for clustering"},
     {"souporcell3", 's', false, false, "activate bad cluster detection and multiple runs"},
     {"clustering_method", 'm', false, false, "choose between expectation maximization (em) and k harmonic means (khm)"},
-    {"gpus", 0, false, false, "[soupgpu] number of GPUs to shard restarts over (default: all visible)"},
+    {"gpus", 0, false, false, "[soupgpu] number of GPUs to shard restarts over (default: as many of the visible ones as the job can keep busy)"},
     {"max_slots", 0, false, false, "[soupgpu] resident solves per GPU (default: auto)"},
     {"quiet_iterations", 0, false, true, "[soupgpu] do not log per-iteration lines"},
     {"csr_cache", 0, false, false, "[soupgpu] .soupcsr cache of the parsed matrix (read if present, else written)"},
@@ -148,10 +150,11 @@ int main(int argc, char** argv) {
 
     // The CUDA driver context takes a few hundred ms to come up: start it now, in the background, while the text
     // matrices are parsed on the CPU.
+    // Only device 0 here: most jobs need one GPU (below), and every further context costs its own start-up.
     std::future<int> cuda_up = std::async(std::launch::async, [] {
         int n = 0;
         if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
-        for (int g = 0; g < n; ++g) { cudaSetDevice(g); cudaFree(nullptr); }
+        if (n > 0) { cudaSetDevice(0); cudaFree(nullptr); }
         return n;
     });
 
@@ -185,15 +188,31 @@ int main(int argc, char** argv) {
     int visible = cuda_up.get();
     sw.lap("wait for CUDA context");
     if (visible == 0) die("souporcell (soupgpu): no CUDA device available; this build has no CPU fallback", 101);
-    int n_gpu = vals.count("gpus") ? (int)parse_num(get("gpus", "1"), "gpus", 1024) : visible;
-    if (n_gpu < 1 || n_gpu > visible) die("souporcell (soupgpu): --gpus out of range", 1);
     const uint64_t spt = (restarts + threads - 1) / threads;
+    int n_gpu;
+    if (vals.count("gpus")) {
+        n_gpu = (int)parse_num(get("gpus", "1"), "gpus", 1024);
+        if (n_gpu < 1 || n_gpu > visible) die("souporcell (soupgpu): --gpus out of range", 1);
+    } else {
+        // default: as many of the visible GPUs as the job can keep busy.  A context takes 1-2 s to come up and a replica of the
+        // matrix; one GPU sustains ~1.3e12 (entry x cluster) updates per second, a solve runs ~17 iterations, souporcell3 up to 3 runs
+        const double est_s = (double)m->nnz * (double)(threads * spt) * (double)k * 17.0 * (s3 ? 3.0 : 1.0) / 1.3e12;
+        n_gpu = (int)std::min<double>((double)visible, std::max(1.0, std::ceil(est_s / 0.5)));
+    }
     if ((uint64_t)n_gpu > threads * spt) n_gpu = (int)std::max<uint64_t>(1, threads * spt);
     std::vector<soup_ctx*> ctxs(n_gpu, nullptr);
-    for (int g = 0; g < n_gpu; ++g) {
-        if (soup_ctx_create(g, nullptr, &ctxs[g]) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
-        if (soup_load_csr(ctxs[g], m->n_cells, m->n_loci, m->nnz, m->row_ptr, m->locus, m->alt, m->ref) != SOUP_OK)
-            die(std::string("souporcell (soupgpu): ") + soup_last_error(ctxs[g]), 101);
+    {   // one thread per GPU: context creation, upload and the GPU transpose of the replicas run side by side
+        std::vector<std::string> errs(n_gpu);
+        auto bring_up = [&](int g) {
+            if (soup_ctx_create(g, nullptr, &ctxs[g]) != SOUP_OK) { errs[g] = soup_last_error(nullptr); return; }
+            if (soup_load_csr(ctxs[g], m->n_cells, m->n_loci, m->nnz, m->row_ptr, m->locus, m->alt, m->ref) != SOUP_OK) errs[g] = soup_last_error(ctxs[g]);
+        };
+        std::vector<std::thread> pool;
+        for (int g = 1; g < n_gpu; ++g) pool.emplace_back(bring_up, g);
+        bring_up(0);
+        for (auto& t : pool) t.join();
+        for (int g = 0; g < n_gpu; ++g)
+            if (!errs[g].empty()) die("souporcell (soupgpu): " + errs[g], 101);
     }
 
     sw.lap("upload + GPU transpose");
