@@ -157,3 +157,74 @@ def test_gpu_troublet_cli_matches_oracle_cli(dataset):
     assert same_calls >= len(a) - 2                     # a call may differ only for a posterior sitting on a threshold
     pick = lambda s: sorted(l for l in s.splitlines() if l.startswith("removing") or "cells removed" in l)
     assert pick(ours.stderr) == pick(theirs.stderr)
+
+
+def _rust_f64(v):
+    """Rust `{}` for f64: shortest round-trip digits (Python's repr gives the same digits), never in scientific notation."""
+    v = float(v)
+    if math.isnan(v):
+        return "NaN"
+    if math.isinf(v):
+        return "-inf" if v < 0 else "inf"
+    if v == 0:
+        return "-0" if math.copysign(1, v) < 0 else "0"
+    from decimal import Decimal
+    s = format(Decimal(repr(v)), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    return s
+
+
+def test_tsv_writer_and_f64_formatting(tmp_path):
+    """soup_troublet_write (T:36-41, T:233-243) and the oracle's printer on crafted values: Rust's f64 Display, the status names,
+    `a/b` assignments for doublets."""
+    from souporcell_b200 import api
+    vals = [1.0, 0.1, -41.24912227493646, 1e-7, 1.1015978990922601e-07, 1e21, 123456789012345680.0, 0.0, -0.0, float("inf"), float("-inf"),
+            float("nan"), 5e-324, 1.7976931348623157e308, 0.999999996610466, -0.5]
+    L = trb()
+    L.trb_format_f64.argtypes = [C.c_double, C.c_char_p, C.c_int32]
+    buf = C.create_string_buffer(512)
+    for v in vals:
+        assert L.trb_format_f64(v, buf, 512) > 0 and buf.value.decode() == _rust_f64(v), v
+    n, k = 4, 3
+    out = dict(status=np.array([0, 1, 2, 3], np.int32), best_singlet=np.array([2, 0, 1, 1], np.int32), doublet1=np.array([0, 0, 1, 2], np.int32),
+               doublet2=np.array([1, 2, 2, 0], np.int32), singlet_posterior=np.array(vals[:4]), doublet_posterior=np.array(vals[4:8]),
+               log_prob_singleton=np.array(vals[8:12]), log_prob_doublet=np.array(vals[12:16]),
+               cluster_logprobs=np.arange(n * k, dtype=np.float64).reshape(n, k) * -1.25)
+    r = api._TroubletResult(*[out[f].ctypes.data_as(C.c_void_p) for f, _ in api._TroubletResult._fields_[:9]])
+    names = ["AAAC-1", "AAAG-1", "AAAT-1", "AACA-1"]
+    blob = b"".join(x.encode() + b"\0" for x in names) + b"\0"
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    path = str(tmp_path / "t.tsv")
+    f = libc.fopen(path.encode(), b"w")
+    assert sp.lib().soup_troublet_write(f, blob, n, k, C.byref(r)) == 0
+    libc.fclose(f)
+    rows = open(path).read().split("\n")
+    assert rows[0] == "barcode\tstatus\tassignment\tsinglet_posterior\tdoublet_posterior\tlog_prob_singleton\tlog_prob_doublet\tcluster0\tcluster1\tcluster2"
+    want_assign = ["2", "0", "1/2", "2/0"]
+    want_status = ["singlet", "unassigned", "doublet", "unassigned"]
+    for i in range(n):
+        tok = rows[1 + i].split("\t")
+        assert tok[:3] == [names[i], want_status[i], want_assign[i]]
+        assert tok[3:7] == [_rust_f64(out[f][i]) for f in ("singlet_posterior", "doublet_posterior", "log_prob_singleton", "log_prob_doublet")]
+        assert tok[7:] == [_rust_f64(x) for x in out["cluster_logprobs"][i]]
+    assert rows[1 + n] == ""
+
+
+def test_clusters_loader_edge_cases(tmp_path):
+    p = tmp_path / "c.tsv"
+    p.write_text("A-1\t0\t-1.5\t-2.5\r\nB-1\t1\t-3\t-0.25\n  C-1\t1\t-7e0\t-1e-3  \n")     # CRLF, surrounding blanks (line.trim())
+    names, losses, n_clusters = sp.load_clusters(str(p))
+    assert names == ["A-1", "B-1", "C-1"] and n_clusters == 2
+    assert np.array_equal(losses, np.array([[-1.5, -2.5], [-3.0, -0.25], [-7.0, -0.001]]))
+    p.write_text("A-1\t0\t-1.5\t-2.5\nB-1\t1\t-3\n")                                       # ragged rows
+    with pytest.raises(sp.SoupError):
+        sp.load_clusters(str(p))
+    p.write_text("A-1\tx\t-1.5\n")                                                          # parse::<usize>() fails
+    with pytest.raises(sp.SoupError):
+        sp.load_clusters(str(p))
+    with pytest.raises(sp.SoupError):
+        sp.load_clusters(str(tmp_path / "missing.tsv"))
