@@ -6,6 +6,9 @@
                        load_cell_data (/root/reference/souporcell/src/main.rs:601-681) — typed in, not computed.
   format_f32.json      Rust `{}` / `{:8}` renderings of f32 values (known Rust behaviour) — typed in.
   bad_clusters.json    bad_cluster_detection cut-offs (main.rs:150-187) for K = 16 / 64 worked out by hand.
+  troublet_micro.json  troublet's call_doublets (/root/reference/troublet/src/main.rs:32-244) on a 36-cell x 30-locus matrix with two planted
+                       doublets, from an INDEPENDENT pure-Python restatement (this script; ln_gamma = math.lgamma, not the Lanczos
+                       series the oracle restates from statrs): log-probabilities compared at 1e-9 relative, calls exactly.
   em_micro.json        one E+M pass and a full em()/khm() on the micro matrix from an INDEPENDENT numpy restatement
                        of main.rs:189-483 (this script; float32 arithmetic, float64 log/exp rounded to f32, so it can
                        differ from glibc logf/expf by an ulp: compared at 2e-6 relative, iteration counts exactly).
@@ -192,7 +195,101 @@ def solve(cells, theta, method, L):
     return theta, lps, float(last), iters, trace
 
 
+# ---------------------------------------------------------------- troublet: independent pure-Python restatement (T:32-244, T:261-412)
+def troublet_micro():
+    import math
+    rng = np.random.default_rng(2024)
+    n_cells, n_loci, K = 36, 30, 3
+    geno = rng.integers(0, 3, size=(K, n_loci)) / 2.0
+    donor = np.arange(n_cells) % K
+    donor2 = donor.copy()
+    donor2[[4, 17]] = (donor[[4, 17]] + 1) % K                      # two planted doublets
+    entries = []                                                     # (locus, cell, ref, alt), file order = (locus, cell)
+    for l in range(n_loci):
+        for c in range(n_cells):
+            if rng.random() < 0.8:
+                depth = int(rng.integers(1, 5)) + (3 if c in (4, 17) else 0)
+                g = 0.5 * (geno[donor[c], l] + geno[donor2[c], l])
+                alt = int(rng.binomial(depth, 0.98 * g + 0.01))
+                entries.append([l, c, depth - alt, alt])
+    # clusters file: a confident assignment to the (first) donor
+    losses = [[-5.0 if k == donor[c] else -60.0 - 3.0 * k for k in range(K)] for c in range(n_cells)]
+    prior, thr_d, thr_s = 0.5, 0.9, 0.9
+    lnb = lambda a, b: math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b)
+    lnbin = lambda n, k: math.lgamma(n + 1) - math.lgamma(k + 1) - math.lgamma(n - k + 1)
+    term = lambda r, a, f, cnt: lnbin(r + a, r) + lnb(r + f * cnt + 1.0, a + (1.0 - f) * cnt + 1.0) - lnb(f * cnt + 1.0, (1.0 - f) * cnt + 1.0)
+    clamp = lambda f: min(max(f, 0.01), 0.99)
+    lse = lambda xs: max(xs) + math.log(sum(math.exp(x - max(xs)) for x in xs))
+    best_col = [max(range(K), key=lambda k: (losses[c][k], -k)) for c in range(n_cells)]
+    S0 = np.zeros((K, n_loci, 2))
+    lines = np.zeros(n_loci, dtype=int)
+    cells = [[] for _ in range(n_cells)]
+    for l, c, r, a in entries:
+        S0[best_col[c], l] += (r, a)
+        lines[l] += 1
+        cells[c].append((l, r, a))
+    A = S0.copy()
+    soup = [S0[:, l, 0].sum() / S0[:, l].sum() if S0[:, l].sum() > 0 else 0.0 for l in range(n_loci)]   # p_soup = 0: unused
+    removed, rounds, out = set(), 0, None
+    while True:
+        first = rounds == 0
+        rounds += 1
+        out, new = [], []
+        for c in range(n_cells):
+            sing = []
+            for k in range(K):
+                lp = math.log(1.0 - prior)
+                for l, r, a in cells[c]:
+                    if lines[l] < 20:
+                        continue
+                    t = A[k, l].sum()
+                    f = 0.5 if t <= 0 else clamp(A[k, l, 0] / t)
+                    lp += term(r, a, f, t)
+                sing.append(lp)
+            order = sorted(range(K), key=lambda k: (-sing[k], k))    # stable descending
+            best_s = max(range(K), key=lambda k: (sing[k], -k))
+            best_d, pair = -math.inf, (0, 0)
+            top = order[:min(K, 4)]
+            for i in range(len(top)):
+                for j in range(i + 1, len(top)):
+                    c1, c2 = top[i], top[j]
+                    lp = math.log(prior)
+                    for l, r, a in cells[c]:
+                        if lines[l] < 20:
+                            continue
+                        t1, t2 = A[c1, l].sum(), A[c2, l].sum()
+                        if first:
+                            f = 0.5 if t1 <= 0 else (clamp(0.5 * A[c1, l, 0] / t1 + 0.5 * A[c2, l, 0] / t2) if t2 > 0 else clamp(A[c1, l, 0] / t1))
+                        else:
+                            rr, aa = A[c1, l, 0] + S0[c2, l, 0], A[c1, l, 1] + S0[c2, l, 1]
+                            f = 0.5 if rr + aa <= 0 else clamp(rr / (rr + aa))
+                        lp += term(r, a, f, (t1 + t2) / 2.0)
+                    if lp > best_d:
+                        best_d, pair = lp, (c1, c2)
+            sp_ = math.exp(max(losses[c]) - lse(losses[c]))
+            dp_ = math.exp(best_d - lse([sing[best_s], best_d]))
+            if sing[best_s] > best_d:
+                status = 0 if sp_ > thr_s else 1
+            elif dp_ >= thr_d:
+                status = 2
+                if c not in removed:
+                    removed.add(c)
+                    new.append(c)
+            else:
+                status = 3
+            out.append(dict(status=status, best_singlet=best_s, doublet=list(pair), singlet_posterior=sp_, doublet_posterior=dp_,
+                            log_prob_singleton=sing[best_s], log_prob_doublet=best_d, cluster_logprobs=sing))
+        for c in new:
+            for l, r, a in cells[c]:
+                A[best_col[c], l] -= (r, a)
+        if not new:
+            break
+    return {"n_cells": n_cells, "n_loci": n_loci, "k": K, "entries": entries, "losses": losses, "doublet_prior": prior,
+            "planted_doublets": [4, 17], "rounds": rounds, "removed": sorted(removed), "tolerance": 1e-9, "cells": out}
+
+
 def main():
+    dump("troublet_micro.json", troublet_micro())
     dump("chacha_kat.json", CHACHA)
     dump("loader_micro.json", LOADER)
     dump("format_f32.json", FORMAT)

@@ -228,3 +228,31 @@ def test_clusters_loader_edge_cases(tmp_path):
         sp.load_clusters(str(p))
     with pytest.raises(sp.SoupError):
         sp.load_clusters(str(tmp_path / "missing.tsv"))
+
+
+def test_oracle_against_independent_python_golden(tmp_path):
+    """tests/golden/troublet_micro.json: call_doublets restated independently in pure Python (math.lgamma instead of the Lanczos series)
+    on a 36 x 30 matrix with two planted doublets.  The C++ oracle must make the same calls and agree on every log-probability."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "troublet_micro.json")))
+    n, L, k = g["n_cells"], g["n_loci"], g["k"]
+    for name, col in (("alt.mtx", 3), ("ref.mtx", 2)):
+        with open(tmp_path / name, "w") as fh:
+            fh.write("%%MatrixMarket matrix coordinate real general\n% golden\n")
+            fh.write(f"{L} {n} {len(g['entries'])}\n")
+            for e in g["entries"]:
+                fh.write(f"{e[0] + 1} {e[1] + 1} {e[col]}\n")
+    with open(tmp_path / "clusters.tsv", "w") as fh:
+        for c in range(n):
+            best = int(np.argmax(g["losses"][c]))
+            fh.write(f"CELL{c:03d}-1\t{best}\t" + "\t".join(repr(float(x)) for x in g["losses"][c]) + "\n")
+    got = oracle_run(str(tmp_path / "alt.mtx"), str(tmp_path / "ref.mtx"), str(tmp_path / "clusters.tsv"), n, k, doublet_prior=g["doublet_prior"])
+    assert got["rounds"] == g["rounds"] and got["removed"] == len(g["removed"])
+    assert sorted(np.nonzero(got["status"] == 2)[0].tolist()) == g["removed"] == g["planted_doublets"]
+    tol = g["tolerance"]
+    for c, want in enumerate(g["cells"]):
+        assert got["status"][c] == want["status"] and got["best_singlet"][c] == want["best_singlet"], c
+        assert [got["doublet1"][c], got["doublet2"][c]] == want["doublet"], c
+        np.testing.assert_allclose(got["cluster_logprobs"][c], want["cluster_logprobs"], rtol=tol)
+        np.testing.assert_allclose([got["log_prob_singleton"][c], got["log_prob_doublet"][c]], [want["log_prob_singleton"], want["log_prob_doublet"]], rtol=tol)
+        np.testing.assert_allclose([got["singlet_posterior"][c], got["doublet_posterior"][c]], [want["singlet_posterior"], want["doublet_posterior"]], rtol=1e-7, atol=1e-300)
