@@ -73,6 +73,19 @@ void ChaChaRng::seek_word(uint64_t word) {
 // ------------------------------------------------------------------ statrs 0.11.0 ln_binomial
 // function::factorial: FCACHE[i] = FCACHE[i-1] * i (f64, i <= 170); ln_factorial(x) =
 // FCACHE[x].ln() for x <= 170 else ln_gamma(x+1); ln_binomial(n,k) = lf(n) - lf(k) - lf(n-k).
+// function::gamma::ln_gamma (Lanczos approximation, r = 10.900511, 11 coefficients), the x >= 0.5 branch: the only caller
+// passes n + 1 with n > 170.  Restated from the published statrs source (not under /root/reference): unpinned.
+static double statrs_ln_gamma(double x) {
+    static const double r = 10.900511;
+    static const double dk[11] = {2.48574089138753565546e-5, 1.05142378581721974210,  -3.45687097222016235469,
+                                  4.51227709466894823700,    -2.98285225323576655721, 1.05639711577126713077,
+                                  -1.95428773191645869583e-1, 1.70970543404441224307e-2, -5.71926117404305781283e-4,
+                                  4.63399473359905636708e-6, -2.71994908488607703910e-9};
+    static const double ln_2_sqrt_e_over_pi = 0.6207822376352452223455184457816472122518527279025978;
+    double s = dk[0];
+    for (int i = 1; i < 11; ++i) s += dk[i] / (x + (double)i - 1.0);
+    return std::log(s) + ln_2_sqrt_e_over_pi + (x - 0.5) * std::log((x - 0.5 + r) / M_E);
+}
 static double ln_factorial(uint64_t x) {
     static double fcache[171];
     static std::once_flag once;
@@ -81,7 +94,7 @@ static double ln_factorial(uint64_t x) {
         for (int i = 1; i <= 170; ++i) fcache[i] = fcache[i - 1] * (double)i;
     });
     if (x <= 170) return std::log(fcache[x]);
-    return std::lgamma((double)x + 1.0);   // statrs uses its own Lanczos ln_gamma: unpinned for n > 170
+    return statrs_ln_gamma((double)x + 1.0);
 }
 double ln_binomial(uint64_t n, uint64_t k) {
     if (k > n) return -std::numeric_limits<double>::infinity();

@@ -32,8 +32,18 @@ const char* thread_error() { return g_thread_error.c_str(); }
 
 // statrs 0.11.0 function::factorial — FCACHE[i] = FCACHE[i-1] * i for i <= 170, ln_factorial =
 // ln(FCACHE[x]) (x <= 170) else ln_gamma(x + 1); ln_binomial(n, k) = lf(n) - lf(k) - lf(n - k).
-// For n > 170 statrs uses its own Lanczos ln_gamma; libm lgamma stands in (differences are
-// below f32 resolution except at rounding ties — documented in DESIGN.md).
+// For n > 170 statrs evaluates its own Lanczos ln_gamma (function::gamma, r = 10.900511, 11 terms; arguments here are
+// >= 172, so only the x >= 0.5 branch exists); libm's lgamma differs from it in the last bits, which can flip the f32 rounding.
+static double lanczos_ln_gamma(double x) {
+    constexpr double kR = 10.900511;
+    constexpr double kLn2SqrtEOverPi = 0.6207822376352452223455184457816472122518527279025978;
+    constexpr double kD[11] = {2.48574089138753565546e-5,  1.05142378581721974210,   -3.45687097222016235469,  4.51227709466894823700,
+                               -2.98285225323576655721,    1.05639711577126713077,   -1.95428773191645869583e-1, 1.70970543404441224307e-2,
+                               -5.71926117404305781283e-4, 4.63399473359905636708e-6, -2.71994908488607703910e-9};
+    double series = kD[0];
+    for (int i = 1; i < 11; ++i) series += kD[i] / (x + (double)i - 1.0);
+    return std::log(series) + kLn2SqrtEOverPi + (x - 0.5) * std::log((x - 0.5 + kR) / M_E);
+}
 static double ln_factorial(uint64_t x) {
     static double cache[171];
     static std::once_flag once;
@@ -41,7 +51,7 @@ static double ln_factorial(uint64_t x) {
         cache[0] = 1.0;
         for (int i = 1; i <= 170; ++i) cache[i] = cache[i - 1] * (double)i;
     });
-    return x <= 170 ? std::log(cache[x]) : std::lgamma((double)x + 1.0);
+    return x <= 170 ? std::log(cache[x]) : lanczos_ln_gamma((double)x + 1.0);
 }
 float ln_binomial_f32(uint32_t n, uint32_t k) {
     if (k > n) return -INFINITY;

@@ -57,6 +57,17 @@ def test_format_and_ln_binomial():
         assert np.float32(float(sp.format_f32(float(v)))) == v            # round-trips
     for n, k in [(0, 0), (1, 0), (1, 1), (2, 1), (3, 2), (10, 3), (170, 85), (171, 3), (400, 200), (5, 6)]:
         assert np.float32(sp.ln_binomial_f32(n, k)) == np.float32(orc.ln_binomial(n, k)) or (k > n)
+    # n > 170: statrs leaves its factorial table for the Lanczos ln_gamma (host_util.cpp / oracle.cpp restate it separately).
+    # Library and oracle must agree bit for bit; math.lgamma is the independent check of the series (f64: 1e-12, hence a few f32 ulps).
+    import math
+    rng = np.random.default_rng(5)
+    ns = np.concatenate([np.arange(171, 400), rng.integers(400, 70000, 300)])
+    for n in ns.tolist():
+        for k in {0, 1, n // 3, n // 2, n - 1, n}:
+            got = np.float32(sp.ln_binomial_f32(n, k))
+            assert got.view(np.uint32) == np.float32(orc.ln_binomial(n, k)).view(np.uint32), (n, k)
+            want = math.lgamma(n + 1) - math.lgamma(k + 1) - math.lgamma(n - k + 1)
+            assert orc.ln_binomial(n, k) == pytest.approx(want, rel=1e-12, abs=1e-8), (n, k)
 
 
 def test_loader_golden_and_vs_oracle(tmp_path):
