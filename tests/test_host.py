@@ -264,3 +264,34 @@ def test_gz_input_and_binary_cache_roundtrip(tmp_path):
         fh.write(blob[:-8])                                        # truncated
     with pytest.raises(sp.SoupError):
         sp.load_mtx(alt, ref, cache=cache)
+
+
+def test_header_is_plain_c_and_ctypes_mirrors_match_its_layout(tmp_path):
+    """include/soupgpu.h is the drop-in boundary: it must compile as plain C (what bindgen / cgo / a Rust -sys crate consume), and every
+    ctypes mirror in api.py must have the header's field names, order, offsets and sizes."""
+    mirrors = {"soup_mtx": api._Mtx, "soup_solve_params": api._SolveParams, "soup_solve_result": api._SolveResult,
+               "soup_iter_record": api._IterRecord, "soup_stats": api._Stats, "soup_main_params": api._MainParams,
+               "soup_main_result": api._MainResult, "soup_troublet_params": api._TroubletParams, "soup_troublet_result": api._TroubletResult}
+    hdr = open(os.path.join(ROOT, "include", "soupgpu.h")).read()
+    declared = set(re.findall(r"^\}\s*(soup_[a-z0-9_]+)\s*;", hdr, flags=re.M))
+    assert declared == set(mirrors), declared ^ set(mirrors)
+    lines = ["#include <stddef.h>", "#include <stdio.h>", '#include "soupgpu.h"', "int main(void) {"]
+    for name, cls in mirrors.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu %zu\\n", offsetof({name}, {field}), sizeof((({name}*)0)->{field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict((ln.split()[0], tuple(int(x) for x in ln.split()[1:])) for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in mirrors.items():
+        assert got[name] == (ctypes.sizeof(cls),), (name, got[name], ctypes.sizeof(cls))
+        body = re.search(r"typedef struct " + name + r"\s*\{(.*?)\}\s*" + name + r"\s*;", hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        n_members = sum(d.count(",") + 1 for d in body.split(";") if d.strip())
+        assert n_members == len(cls._fields_), (name, n_members, len(cls._fields_))       # no header field without a mirror
+        for field, _ in cls._fields_:
+            d = getattr(cls, field)
+            assert got[f"{name}.{field}"] == (d.offset, d.size), (name, field, got[f"{name}.{field}"], (d.offset, d.size))
