@@ -295,3 +295,17 @@ def test_header_is_plain_c_and_ctypes_mirrors_match_its_layout(tmp_path):
         for field, _ in cls._fields_:
             d = getattr(cls, field)
             assert got[f"{name}.{field}"] == (d.offset, d.size), (name, field, got[f"{name}.{field}"], (d.offset, d.size))
+
+
+def test_integration_md_rust_mirror_is_current():
+    """INTEGRATION.md shows the -sys crate a maintainer would add: its #[repr(C)] structs must list the header's fields in order and
+    its extern block may only name exported functions."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    mirrors = {"soup_mtx": api._Mtx, "soup_main_params": api._MainParams, "soup_main_result": api._MainResult}
+    for name, cls in mirrors.items():
+        body = re.search(r"#\[repr\(C\)\] pub struct " + name + r" \{(.*?)\n\}", doc, flags=re.S).group(1)
+        body = re.sub(r"//[^\n]*", "", body)
+        fields = [f.replace("r#", "") for f in re.findall(r"pub ((?:r#)?[a-z_0-9]+)\s*:", body)]
+        assert fields == [f for f, _ in cls._fields_], (name, fields)
+    fns = set(re.findall(r"\b(soup_[a-z0-9_]+)\(", doc))
+    assert fns and fns <= set(api.EXPORTS), fns - set(api.EXPORTS)
