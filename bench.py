@@ -338,10 +338,7 @@ def ours_cells(args):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg, csr = workload(args.config)
     n, L, row_ptr, locus, alt, ref = csr
-    rp = row_ptr.astype(np.int64)
-    cuts = [0] + [int(np.searchsorted(rp, rp[-1] * i // world)) for i in range(1, world)] + [n]
-    a, b = cuts[rank], cuts[rank + 1]
-    shard = (b - a, L, (rp[a:b + 1] - rp[a]).astype(np.uint64), locus[rp[a]:rp[b]], alt[rp[a]:rp[b]], ref[rp[a]:rp[b]])
+    shard = api.split_cells(csr, world)[1][rank]
     K, restarts = cfg["k"], cfg["restarts"]
     method = sp.METHOD_KHM if cfg["method"] == "khm" else sp.METHOD_EM
     stream = torch.cuda.Stream()

@@ -558,6 +558,23 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
                       int(r.slot_iterations), int(r.timed_iterations), float(r.estep_ms), float(r.mstep_ms))
 
 
+def split_cells(csr, parts: int):
+    """Cell sharding: cut the cells into `parts` contiguous ranges balanced by nnz; every shard keeps all loci.
+    csr = (n_cells, n_loci, row_ptr, locus, alt, ref).  Returns (cuts [parts + 1], [csr tuple per shard]) — shard r holds cells
+    cuts[r]:cuts[r + 1], its row_ptr rebased to 0; a shard may be empty when parts exceeds what the matrix can feed."""
+    n, L, row_ptr, locus, alt, ref = csr
+    if parts < 1:
+        raise ValueError("split_cells: parts must be >= 1")
+    rp = np.asarray(row_ptr).astype(np.int64)
+    cuts = [0] + [int(np.searchsorted(rp, rp[-1] * i // parts)) for i in range(1, parts)] + [int(n)]
+    cuts = [min(max(c, 0), int(n)) for c in cuts]
+    out = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s, e = int(rp[a]), int(rp[b])
+        out.append((b - a, L, (rp[a:b + 1] - s).astype(np.uint64), locus[s:e], alt[s:e], ref[s:e]))
+    return cuts, out
+
+
 def exchange_best(rank, world, allgather, bcast, loss, solve, has_best, log_probs=None, theta=None):
     """soup_exchange_best: returns (loss, solve, has_best, winner_rank); log_probs / theta (float32 arrays) are overwritten in place."""
     l, s_, h, w = C.c_float(loss), C.c_int32(solve), C.c_int32(int(has_best)), C.c_int32(-1)

@@ -65,3 +65,30 @@ def test_restart_shards_partition_the_solves():
         flat = sorted(s for o in owned for s in o)
         assert flat == list(range(n_solves))
         assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+
+
+def test_split_cells_partitions_the_matrix_by_nnz():
+    # cell sharding: contiguous ranges, every cell and entry exactly once, nnz balanced to within one row
+    sys.path.insert(0, ROOT)
+    from souporcell_b200 import api, synth
+    v = synth.generate(n_cells=400, n_loci=3000, k=3, mean_loci=150, seed=9)
+    row_ptr, locus, alt, ref, i2l = synth.filter_to_csr(v)
+    csr = (v.n_cells, int(i2l.shape[0]), row_ptr, locus, alt, ref)
+    nnz, longest = int(row_ptr[-1]), int(np.diff(row_ptr.astype(np.int64)).max())
+    for parts in (1, 2, 3, 8):
+        cuts, shards = api.split_cells(csr, parts)
+        assert cuts[0] == 0 and cuts[-1] == v.n_cells and all(a <= b for a, b in zip(cuts[:-1], cuts[1:])) and len(shards) == parts
+        assert sum(s[0] for s in shards) == v.n_cells
+        for name, col in (("locus", 3), ("alt", 4), ("ref", 5)):
+            assert np.array_equal(np.concatenate([s[col] for s in shards]), csr[col]), name
+        for (a, b), s in zip(zip(cuts[:-1], cuts[1:]), shards):
+            assert s[1] == csr[1] and s[2][0] == 0 and s[2].dtype == np.uint64
+            assert np.array_equal(s[2].astype(np.int64), row_ptr[a:b + 1].astype(np.int64) - int(row_ptr[a]))
+            assert abs(int(s[2][-1]) - nnz / parts) <= 2 * longest
+    # more parts than cells with data: empty shards are legal, nothing is lost
+    tiny = (3, 5, np.array([0, 2, 2, 3], dtype=np.uint64), np.array([0, 4, 1], dtype=np.uint32), np.ones(3, np.uint32), np.zeros(3, np.uint32))
+    cuts, shards = api.split_cells(tiny, 5)
+    assert sum(s[0] for s in shards) == 3 and sum(int(s[2][-1]) for s in shards) == 3
+    import pytest
+    with pytest.raises(ValueError):
+        api.split_cells(tiny, 0)

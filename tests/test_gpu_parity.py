@@ -6,6 +6,7 @@ import pytest
 from helpers import random_theta, synth_csr
 from oracle import oracle_py as orc
 import souporcell_b200 as sp
+from souporcell_b200 import api
 
 pytestmark = pytest.mark.gpu
 
@@ -332,14 +333,7 @@ def test_full_size_properties_config2():
 # ---------------------------------------------------------------------------------------------- cell-sharded mode
 def _split_cells(csr, parts):
     """contiguous cell ranges balanced by nnz; each shard keeps all loci."""
-    n, L, row_ptr, locus, alt, ref = csr
-    rp = row_ptr.astype(np.int64)
-    cuts = [0] + [int(np.searchsorted(rp, rp[-1] * i // parts)) for i in range(1, parts)] + [n]
-    out = []
-    for a, b in zip(cuts[:-1], cuts[1:]):
-        s, e = rp[a], rp[b]
-        out.append((b - a, L, (rp[a:b + 1] - s).astype(np.uint64), locus[s:e], alt[s:e], ref[s:e]))
-    return cuts, out
+    return api.split_cells(csr, parts)
 
 
 @pytest.mark.parametrize("mode", ["default", "long_coop"])
