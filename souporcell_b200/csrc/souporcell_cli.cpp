@@ -15,6 +15,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <algorithm>
 #include <thread>
 #include <vector>
 
@@ -52,13 +53,35 @@ const Opt kOpts[] = {
     {"csr_cache", 0, false, false, "[soupgpu] .soupcsr cache of the parsed matrix (read if present, else written)"},
 };
 
+// clap 2's help layout (what `souporcell -h` prints, README.md:252-297 of the reference): options sorted by long name, the help text
+// in one column 4 blanks after the longest `--name <name>` — unless that leaves it less room than it needs on a 120-column line, in
+// which case it moves to the next line (12 blanks) followed by an empty line.  The soupgpu extras follow in a section of their own.
 void usage(FILE* f) {
     fprintf(f, "souporcell 3.0\nHaynes Heaton <whheaton@gmail.com>\nclustering scRNAseq cells by genotype\n\nUSAGE:\n"
                "    souporcell [OPTIONS] --alt_matrix <alt_matrix> --barcodes <barcodes> --num_clusters <num_clusters> --ref_matrix <ref_matrix>\n\n"
                "FLAGS:\n    -h, --help       Prints help information\n    -V, --version    Prints version information\n\nOPTIONS:\n");
-    for (const Opt& o : kOpts) {
-        if (o.shrt) fprintf(f, "    -%c, --%s%s    %s\n", o.shrt, o.name, o.flag ? "" : " <value>", o.help);
-        else fprintf(f, "        --%s%s    %s\n", o.name, o.flag ? "" : (o.multiple ? " <value>..." : " <value>"), o.help);
+    auto left = [](const Opt& o) {
+        std::string s = std::string("--") + o.name;
+        if (!o.flag) s += std::string(" <") + o.name + ">" + (o.multiple ? "..." : "");
+        return s;
+    };
+    auto extra = [](const Opt& o) { return strncmp(o.help, "[soupgpu]", 9) == 0; };
+    for (int section = 0; section < 2; ++section) {
+        std::vector<const Opt*> opts;
+        size_t longest = 0;
+        for (const Opt& o : kOpts)
+            if (extra(o) == (section == 1)) { opts.push_back(&o); longest = std::max(longest, left(o).size()); }
+        std::sort(opts.begin(), opts.end(), [](const Opt* a, const Opt* b) { return strcmp(a->name, b->name) < 0; });
+        if (section == 1) fprintf(f, "\nSOUPGPU OPTIONS:\n");
+        const size_t term = 120, taken = longest + 12;
+        for (const Opt* o : opts) {
+            const std::string l = left(*o);
+            if (o->shrt) fprintf(f, "    -%c, %s", o->shrt, l.c_str());
+            else fprintf(f, "        %s", l.c_str());
+            const bool next_line = term >= taken && (float)taken / (float)term > 0.40f && strlen(o->help) > term - taken;
+            if (next_line) fprintf(f, "\n            %s\n\n", o->help);
+            else fprintf(f, "%*s%s\n", (int)(longest - l.size() + 4), "", o->help);
+        }
     }
 }
 
@@ -116,8 +139,12 @@ int main(int argc, char** argv) {
         vals[o->name].push_back(argv[++i]);
         if (o->multiple) while (i + 1 < argc && argv[i + 1][0] != '-') vals[o->name].push_back(argv[++i]);
     }
-    for (const char* req : {"alt_matrix", "barcodes", "num_clusters", "ref_matrix"})
-        if (!vals.count(req)) { fprintf(stderr, "error: The following required arguments were not provided:\n    --%s <%s>\n\n", req, req); usage(stderr); return 1; }
+    {   // clap lists every missing required argument, then the usage
+        std::string missing;
+        for (const char* req : {"alt_matrix", "barcodes", "num_clusters", "ref_matrix"})
+            if (!vals.count(req)) missing += std::string("    --") + req + " <" + req + ">\n";
+        if (!missing.empty()) { fprintf(stderr, "error: The following required arguments were not provided:\n%s\n", missing.c_str()); usage(stderr); return 1; }
+    }
     auto get = [&](const char* n, const char* d) { return vals.count(n) ? vals[n].back() : std::string(d); };
 
     // ---- load_params S:756-853

@@ -1,5 +1,6 @@
 // `troublet` drop-in: the reference's argv grammar (/root/reference/troublet/src/params.yml:1-49, load_params
 // T:473-505), the TSV on stdout (T:36-41, T:233-243) and its log lines on stderr, on top of libsoupgpu's soup_troublet.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -15,15 +16,29 @@ static void die(const std::string& msg, int code) {
 }
 
 int main(int argc, char** argv) {
-    struct Opt { const char* name; char sh; bool multiple; };
-    static const Opt OPTS[] = {{"alts", 'a', false}, {"refs", 'r', false}, {"clusters", 'c', false}, {"doublet_prior", 'd', false},
-                               {"debug", 'b', true}, {"doublet_threshold", 0, false}, {"singlet_threshold", 0, false}};
+    struct Opt { const char* name; char sh; bool multiple; const char* help; };
+    // params.yml:5-49, in the order clap prints them (by long name)
+    static const Opt OPTS[] = {{"alts", 'a', false, "alt allele counts per cell in sparse matrix format out of vartrix"},
+                               {"clusters", 'c', false, "cluster file output from schism"},
+                               {"debug", 'b', true, "print debug info for index of cells listed"},
+                               {"doublet_prior", 'd', false, "prior on doublets. Defaults to 0.5"},
+                               {"doublet_threshold", 0, false, "doublet posterior threshold, defaults to 0.90"},
+                               {"refs", 'r', false, "ref allele counts per cell in sparse matrix format out of vartrix"},
+                               {"singlet_threshold", 0, false, "singlet posterior threshold, defaults to 0.90"}};
+    static const char* USAGE = "USAGE:\n    troublet [OPTIONS] --alts <alts> --clusters <clusters>";
     std::map<std::string, std::vector<std::string>> vals;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "-h" || a == "--help") {
             printf("troublet 2.4\nHaynes Heaton <whheaton@gmail.com>\nIntergenotypic doublet detection given cluster assignments and cell allele counts\n\n"
-                   "USAGE:\n    troublet [OPTIONS] --alts <alts> --clusters <clusters>\n");
+                   "%s\n\nFLAGS:\n    -h, --help       Prints help information\n    -V, --version    Prints version information\n\nOPTIONS:\n", USAGE);
+            size_t width = 0;
+            for (const Opt& q : OPTS) width = std::max(width, 2 * strlen(q.name) + (q.multiple ? 8 : 5));
+            for (const Opt& q : OPTS) {   // "    -a, --alts <alts>    help", help column aligned as clap does
+                std::string left = std::string("--") + q.name + " <" + q.name + ">" + (q.multiple ? "..." : "");
+                if (q.sh) printf("    -%c, %-*s    %s\n", q.sh, (int)width, left.c_str(), q.help);
+                else printf("        %-*s    %s\n", (int)width, left.c_str(), q.help);
+            }
             return 0;
         }
         if (a == "-V" || a == "--version") { printf("troublet 2.4\n"); return 0; }
@@ -39,7 +54,7 @@ int main(int argc, char** argv) {
             for (const Opt& q : OPTS) if (q.sh && a[1] == q.sh) o = &q;
             if (a.size() > 2) { v = a.substr(a[2] == '=' ? 3 : 2); has = true; }
         }
-        if (!o) die("error: Found argument '" + a + "' which wasn't expected, or isn't valid in this context\n\nUSAGE:\n    troublet [OPTIONS] --alts <alts> --clusters <clusters>", 1);
+        if (!o) die("error: Found argument '" + a + "' which wasn't expected, or isn't valid in this context\n\n" + USAGE + "\n\nFor more information try --help", 1);
         if (!has) {
             if (i + 1 >= argc) die(std::string("error: The argument '--") + o->name + " <" + o->name + ">' requires a value but none was supplied", 1);
             v = argv[++i];
@@ -47,7 +62,12 @@ int main(int argc, char** argv) {
         vals[o->name].push_back(v);
         while (o->multiple && i + 1 < argc && argv[i + 1][0] != '-') vals[o->name].push_back(argv[++i]);
     }
-    if (!vals.count("alts") || !vals.count("clusters")) die("error: The following required arguments were not provided:\n    --alts <alts>\n    --clusters <clusters>", 1);
+    {   // clap lists the missing required arguments only
+        std::string missing;
+        for (const char* req : {"alts", "clusters"})
+            if (!vals.count(req)) missing += std::string("\n    --") + req + " <" + req + ">";
+        if (!missing.empty()) die("error: The following required arguments were not provided:" + missing + "\n\n" + USAGE + "\n\nFor more information try --help", 1);
+    }
     if (!vals.count("refs")) die("thread 'main' panicked at 'called `Option::unwrap()` on a `None` value'", 101);   // T:476
     auto num = [&](const char* name, const char* dflt) {
         const std::string s = vals.count(name) ? vals[name].back() : dflt;

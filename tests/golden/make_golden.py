@@ -13,6 +13,11 @@
                        of main.rs:189-483 (this script; float32 arithmetic, float64 log/exp rounded to f32, so it can
                        differ from glibc logf/expf by an ulp: compared at 2e-6 relative, iteration counts exactly).
 
+  cli_flags.json       the clap flag tables of both binaries, READ from souporcell/src/params.yml and troublet/src/params.yml.
+  readme_souporcell_help.json  the `souporcell -h` text the reference's README.md:253-297 shows.
+  readme_troublet_help.json    the `troublet -h` text the reference's README.md:322-340 shows.
+  readme_troublet_sample.json  the ten sample rows of clusters.tsv in the reference's README.md:147-157 (its own troublet's output).
+
 The reference itself has no tests or fixtures and cannot be built here (no Rust toolchain), so none of
 these come from running it: PARITY UNPINNED.
 """
@@ -288,7 +293,43 @@ def troublet_micro():
             "planted_doublets": [4, 17], "rounds": rounds, "removed": sorted(removed), "tolerance": 1e-9, "cells": out}
 
 
+REFERENCE = "/root/reference"
+
+
+def reference_derived():
+    """Fixtures READ from the reference tree (not computed): the clap flag tables of both binaries and the sample clusters.tsv the
+    README prints.  Only regenerated where /root/reference exists; the committed JSON files travel."""
+    import yaml
+    flags = {}
+    for tool in ("souporcell", "troublet"):
+        doc = yaml.safe_load(open(os.path.join(REFERENCE, tool, "src", "params.yml")))
+        args = []
+        for a in doc["args"]:
+            (name, spec), = a.items()
+            args.append({"name": name, "long": spec["long"], "short": spec.get("short"), "takes_value": bool(spec.get("takes_value", False)),
+                         "required": bool(spec.get("required", False)), "multiple": bool(spec.get("multiple", False))})
+        flags[tool] = {"source": f"{tool}/src/params.yml", "name": doc["name"], "version": str(doc["version"]), "args": args}
+    dump("cli_flags.json", flags)
+    lines = open(os.path.join(REFERENCE, "README.md")).read().split("\n")[146:157]
+    rows = [ln.split() for ln in lines]
+    assert rows[0][0] == "barcode" and len(rows) == 11 and all(len(r) == 7 for r in rows)
+    dump("readme_troublet_sample.json", {
+        "source": "README.md:147-157 of the reference: the sample clusters.tsv printed by its own troublet binary (an earlier column set: no "
+                  "posterior columns). The only reference-produced numbers in the tree; whitespace-split because the README shows the tabs expanded.",
+        "header": rows[0], "rows": rows[1:]})
+    readme = open(os.path.join(REFERENCE, "README.md")).read().split("\n")
+    assert readme[320] == "troublet -h" and readme[339].lstrip().startswith("--singlet_threshold")
+    assert readme[251] == "souporcell -h" and readme[296].lstrip().startswith("-t, --threads")
+    dump("readme_souporcell_help.json", {"source": "README.md:253-297 of the reference: what `souporcell -h` printed (clap 2.x on a 120-column "
+                                                   "terminal; two help strings still said NOT YET IMPLEMENTED, params.yml:50,56 no longer do)",
+                                         "lines": readme[252:297]})
+    dump("readme_troublet_help.json", {"source": "README.md:322-340 of the reference: what `troublet -h` printed (clap 2.x; the README's build "
+                                                 "called itself 3.0, troublet/src/params.yml says 2.4)", "lines": readme[321:340]})
+
+
 def main():
+    if os.path.isdir(REFERENCE):
+        reference_derived()
     dump("troublet_micro.json", troublet_micro())
     dump("chacha_kat.json", CHACHA)
     dump("loader_micro.json", LOADER)

@@ -309,3 +309,55 @@ def test_integration_md_rust_mirror_is_current():
         assert fields == [f for f, _ in cls._fields_], (name, fields)
     fns = set(re.findall(r"\b(soup_[a-z0-9_]+)\(", doc))
     assert fns and fns <= set(api.EXPORTS), fns - set(api.EXPORTS)
+
+
+@pytest.mark.parametrize("tool", ["souporcell", "troublet"])
+def test_cli_accepts_every_flag_of_the_reference_params_yml(tool):
+    """tests/golden/cli_flags.json is read from the reference's params.yml files (clap 2).  Every long / short flag must be known to
+    the drop-in (in `--flag value`, `--flag=value` and `-f value` forms), -h must list them all, -V must print the reference's version,
+    and leaving out any required flag must be the usage error.  argv errors come before any GPU work, so this runs without one."""
+    spec = load("cli_flags.json")[tool]
+    exe = build.CLI if tool == "souporcell" else build.TROUBLET_CLI
+    run = lambda args: subprocess.run([exe] + args, capture_output=True, text=True)
+    assert run(["-V"]).stdout == f"{spec['name']} {spec['version']}\n"
+    help_text = run(["-h"]).stdout
+    for a in spec["args"]:
+        assert "--" + a["long"] in help_text, a["long"]
+        if a["short"]:
+            assert re.search(r"-" + a["short"] + r"\b", help_text), a["short"]
+    required = [a for a in spec["args"] if a["required"]]
+    assert required
+    for a in spec["args"]:
+        assert a["takes_value"]                                   # every flag of both tools takes a value
+        forms = [["--" + a["long"], "x"], ["--" + a["long"] + "=x"]] + ([["-" + a["short"], "x"]] if a["short"] else [])
+        for form in forms:
+            r = run(form)                                         # the other required flags are missing: usage error, not "unknown flag"
+            assert r.returncode != 0 and r.stdout == "", form
+            if not (a["required"] and len(required) == 1):
+                assert "required arguments" in r.stderr and "wasn't expected" not in r.stderr, (form, r.stderr)
+    for skip in required:                                         # all required but one
+        args = sum((["--" + a["long"], "/nonexistent"] for a in required if a is not skip), [])
+        r = run(args)
+        assert r.returncode != 0 and r.stdout == "" and "required arguments" in r.stderr and "--" + skip["long"] in r.stderr, (skip["long"], r.stderr)
+    r = run(["--definitely_not_a_flag", "1"])
+    assert r.returncode != 0 and "wasn't expected" in r.stderr
+
+
+def test_troublet_help_is_the_text_the_reference_readme_shows():
+    """tests/golden/readme_troublet_help.json = README.md:322-340 of the reference (clap 2 layout: flags sorted by long name, help column
+    aligned).  Only the version line differs (the README's build printed 3.0, troublet/src/params.yml says 2.4)."""
+    want = load("readme_troublet_help.json")["lines"]
+    got = subprocess.run([build.TROUBLET_CLI, "-h"], capture_output=True, text=True).stdout.split("\n")
+    assert got[-1] == "" and got[0] == "troublet 2.4" and want[0] == "troublet 3.0"
+    assert [ln.rstrip() for ln in got[1:-1]] == [ln.rstrip() for ln in want[1:]]
+
+
+def test_souporcell_help_is_the_text_the_reference_readme_shows():
+    """tests/golden/readme_souporcell_help.json = README.md:253-297 of the reference: clap 2's layout on 120 columns (options sorted by
+    long name; a help text that does not fit beside the longest option moves to the next line).  Two help strings lost their
+    'NOT YET IMPLEMENTED ' prefix in params.yml since; the soupgpu extras follow in a section of their own."""
+    want = [ln.replace("NOT YET IMPLEMENTED ", "").rstrip() for ln in load("readme_souporcell_help.json")["lines"]]
+    got = [ln.rstrip() for ln in subprocess.run([build.CLI, "-h"], capture_output=True, text=True).stdout.split("\n")]
+    cut = got.index("SOUPGPU OPTIONS:")
+    assert got[:cut - 1] == want and got[cut - 1] == ""
+    assert all("[soupgpu]" in ln for ln in got[cut + 1:] if ln)
