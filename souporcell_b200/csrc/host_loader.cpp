@@ -17,8 +17,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 #include "soup_common.hpp"
@@ -107,103 +109,167 @@ size_t skip_lines(const Mapped& m, size_t from, size_t k) {
     }
     return pos;
 }
-uint64_t count_lines(const char* b, const char* e) {   // number of lines BufRead::lines() yields for [b, e)
-    uint64_t n = 0;
-    const char* p = b;
-    while (p < e) {
-        const void* q = memchr(p, '\n', (size_t)(e - p));
-        if (!q) { ++n; break; }
-        ++n;
-        p = (const char*)q + 1;
+// Runs fn(i) for i in [0, n) on up to `nthreads` threads (dynamic distribution, one item at a time).
+template <typename F>
+void parallel_for(unsigned nthreads, size_t n, F fn) {
+    if (n == 0) return;
+    const unsigned t_n = (unsigned)std::min<size_t>(std::max(1u, nthreads), n);
+    if (t_n == 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < t_n; ++t)
+        pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
+    for (auto& th : pool) th.join();
+}
+
+// Newline counts of a file body [b, e) per byte block, built in parallel: how many lines BufRead::lines() yields, and where
+// line k starts, without a serial pass over the text.
+struct NewlineIndex {
+    size_t b = 0, e = 0, blk = 1;
+    std::vector<uint64_t> before;   // before[i] = '\n' bytes in blocks [0, i); size nblk + 1
+    uint64_t lines = 0;
+};
+NewlineIndex index_newlines(const char* base, size_t b, size_t e, unsigned nthreads) {
+    NewlineIndex ix;
+    ix.b = b; ix.e = e;
+    const size_t len = e - b;
+    ix.blk = 256 << 10;
+    const size_t nblk = (len + ix.blk - 1) / ix.blk;
+    ix.before.assign(nblk + 1, 0);
+    parallel_for(nthreads, nblk, [&](size_t i) {
+        const char* p = base + b + i * ix.blk;
+        const char* f = base + std::min(e, b + (i + 1) * ix.blk);
+        uint64_t n = 0;
+        for (; p < f; ++p) n += (*p == '\n');   // vectorises
+        ix.before[i + 1] = n;
+    });
+    for (size_t i = 0; i < nblk; ++i) ix.before[i + 1] += ix.before[i];
+    ix.lines = ix.before[nblk] + ((len > 0 && base[e - 1] != '\n') ? 1 : 0);   // an unterminated last line counts
+    return ix;
+}
+// Byte offset of the start of line `target` (0-based, relative to the body start): just past newline number `target`.
+size_t line_offset(const char* base, const NewlineIndex& ix, uint64_t target) {
+    if (target == 0) return ix.b;
+    if (target > ix.before.back()) return ix.e;
+    const size_t i = (size_t)(std::lower_bound(ix.before.begin(), ix.before.end(), target) - ix.before.begin()) - 1;   // before[i] < target <= before[i + 1]
+    uint64_t need = target - ix.before[i];
+    const char* p = base + ix.b + i * ix.blk;
+    const char* f = base + std::min(ix.e, ix.b + (i + 1) * ix.blk);
+    while (need > 0) {
+        p = (const char*)memchr(p, '\n', (size_t)(f - p)) + 1;   // exists: the block holds at least `need` newlines
+        --need;
     }
-    return n;
+    return (size_t)(p - base);
 }
 
 struct Chunk { size_t a_begin, r_begin; uint64_t first_line, n_lines; };
 
 struct ParseError { std::atomic<int> code{0}; char msg[256]; void set(int c, const char* m) { int z = 0; if (code.compare_exchange_strong(z, c)) { strncpy(msg, m, sizeof(msg) - 1); msg[sizeof(msg) - 1] = 0; } } };
 
+// per-thread partial tallies of S:629-632 (wrapping u32 sums commute, so partials add up to the serial result)
+struct Tally {
+    std::vector<uint32_t> cells_ref, cells_alt, umis_ref, umis_alt;
+    std::vector<uint8_t> seen;
+    void init(uint64_t n) { cells_ref.assign(n, 0); cells_alt.assign(n, 0); umis_ref.assign(n, 0); umis_alt.assign(n, 0); seen.assign(n, 0); }
+};
+
+// ---- one line of each file.  The fast forms cover what vartrix writes ("l c v\n": 1-9 digit fields, single blanks or tabs,
+// optional CR); anything else — signs, padding, extra tokens, long numbers — goes through the general tokenizer, which decides alone
+// what is an error.  Both advance `p` past the line.
+inline bool fast_uint(const char*& p, const char* end, uint64_t* out) {
+    const char* s = p;
+    uint32_t v = 0;
+    while (p < end) {
+        const unsigned d = (unsigned)(unsigned char)*p - '0';
+        if (d > 9) break;
+        v = v * 10 + d;
+        ++p;
+    }
+    const size_t n = (size_t)(p - s);
+    if (n == 0 || n > 9) return false;
+    *out = v;
+    return true;
+}
+inline bool fast_blanks(const char*& p, const char* end) {
+    const char* s = p;
+    while (p < end && (*p == ' ' || *p == '\t')) ++p;
+    return p > s;
+}
+inline bool fast_token(const char*& p, const char* end) {   // a token whose content is not looked at
+    const char* s = p;
+    while (p < end && !is_ws(*p) && *p != '\n') ++p;
+    return p > s;
+}
+inline bool fast_eol(const char*& p, const char* end) {
+    if (p < end && *p == '\r') ++p;
+    if (p == end) return true;
+    if (*p != '\n') return false;
+    ++p;
+    return true;
+}
+inline bool alt_line(const char*& p, const char* end, uint64_t* l, uint64_t* c, uint64_t* v) {
+    const char* q = p;
+    if (fast_uint(q, end, l) && fast_blanks(q, end) && fast_uint(q, end, c) && fast_blanks(q, end) && fast_uint(q, end, v) && fast_eol(q, end)) {
+        p = q;
+        return true;
+    }
+    const char* e = (const char*)memchr(p, '\n', (size_t)(end - p));
+    if (!e) e = end;
+    const char *tb, *te;
+    q = p;
+    p = e < end ? e + 1 : end;
+    return next_token(q, e, tb, te) && parse_u64(tb, te, l) && next_token(q, e, tb, te) && parse_u64(tb, te, c) &&
+           next_token(q, e, tb, te) && parse_u64(tb, te, v) && *v <= UINT32_MAX;
+}
+inline bool ref_line(const char*& p, const char* end, uint64_t* v) {   // only the third token is ever parsed (S:625)
+    const char* q = p;
+    if (fast_token(q, end) && fast_blanks(q, end) && fast_token(q, end) && fast_blanks(q, end) && fast_uint(q, end, v) && fast_eol(q, end)) {
+        p = q;
+        return true;
+    }
+    const char* e = (const char*)memchr(p, '\n', (size_t)(end - p));
+    if (!e) e = end;
+    const char *tb, *te;
+    q = p;
+    p = e < end ? e + 1 : end;
+    return next_token(q, e, tb, te) && next_token(q, e, tb, te) && next_token(q, e, tb, te) && parse_u64(tb, te, v) && *v <= UINT32_MAX;
+}
+
 void parse_chunk(const Mapped& A, const Mapped& R, const Chunk& ch, uint64_t total_loci, uint64_t total_cells,
-                 uint32_t* locus, uint32_t* cell, uint32_t* alt, uint32_t* ref, ParseError* err) {
+                 uint32_t* locus, uint32_t* cell, uint32_t* alt, uint32_t* ref, Tally& t, ParseError* err) {
     const char* ap = A.p + ch.a_begin;
     const char* rp = R.p + ch.r_begin;
     const char* aend = A.p + A.n;
     const char* rend = R.p + R.n;
     for (uint64_t i = 0; i < ch.n_lines; ++i) {
-        const char* ae = (const char*)memchr(ap, '\n', (size_t)(aend - ap));
-        if (!ae) ae = aend;
-        const char* re = (const char*)memchr(rp, '\n', (size_t)(rend - rp));
-        if (!re) re = rend;
-        const char *tb, *te;
         uint64_t l, c, av, rv;
-        const char* p = ap;
-        if (!next_token(p, ae, tb, te) || !parse_u64(tb, te, &l) || !next_token(p, ae, tb, te) || !parse_u64(tb, te, &c) ||
-            !next_token(p, ae, tb, te) || !parse_u64(tb, te, &av) || av > UINT32_MAX) {
-            err->set(SOUP_ERR_INVALID, "alt mtx: malformed entry line (reference panics on unwrap)");
-            return;
-        }
-        p = rp;
-        if (!next_token(p, re, tb, te) || !next_token(p, re, tb, te) || !next_token(p, re, tb, te) || !parse_u64(tb, te, &rv) ||
-            rv > UINT32_MAX) {
-            err->set(SOUP_ERR_INVALID, "ref mtx: malformed entry line (reference panics on unwrap)");
-            return;
-        }
+        if (!alt_line(ap, aend, &l, &c, &av)) { err->set(SOUP_ERR_INVALID, "alt mtx: malformed entry line (reference panics on unwrap)"); return; }
+        if (!ref_line(rp, rend, &rv)) { err->set(SOUP_ERR_INVALID, "ref mtx: malformed entry line (reference panics on unwrap)"); return; }
         if (l == 0 || l - 1 >= total_loci) { err->set(SOUP_ERR_INVALID, "assertion failed: locus < total_loci"); return; }
         if (c == 0 || c - 1 >= total_cells) { err->set(SOUP_ERR_INVALID, "assertion failed: cell < total_cells"); return; }
-        uint64_t o = ch.first_line + i;
-        locus[o] = (uint32_t)(l - 1);
+        const uint64_t o = ch.first_line + i;
+        const uint32_t li = (uint32_t)(l - 1);
+        locus[o] = li;
         cell[o] = (uint32_t)(c - 1);
         alt[o] = (uint32_t)av;
         ref[o] = (uint32_t)rv;
-        ap = ae < aend ? ae + 1 : aend;
-        rp = re < rend ? re + 1 : rend;
+        t.seen[li] = 1;
+        if (rv > 0) { t.cells_ref[li] += 1; t.umis_ref[li] += (uint32_t)rv; }
+        if (av > 0) { t.cells_alt[li] += 1; t.umis_alt[li] += (uint32_t)av; }
     }
 }
 
-// Byte offsets of `want.size()` ascending line indices (relative to body start) inside body [b, e).
-std::vector<size_t> locate_lines(const char* base, size_t b, size_t e, const std::vector<uint64_t>& want, unsigned nthreads) {
-    // pass 1: newline counts per byte block, in parallel
-    size_t len = e - b;
-    size_t nblk = std::max<size_t>(1, std::min<size_t>(nthreads * 4, len / (1 << 20) + 1));
-    size_t blk = (len + nblk - 1) / nblk;
-    std::vector<uint64_t> cnt(nblk, 0);
-    std::vector<std::thread> pool;
-    std::atomic<size_t> next{0};
-    for (unsigned t = 0; t < nthreads; ++t)
-        pool.emplace_back([&] {
-            for (size_t i; (i = next.fetch_add(1)) < nblk;) {
-                size_t s = b + i * blk, f = std::min(e, s + blk);
-                uint64_t n = 0;
-                for (const char* p = base + s; p < base + f;) {
-                    const void* q = memchr(p, '\n', (size_t)(base + f - p));
-                    if (!q) break;
-                    ++n;
-                    p = (const char*)q + 1;
-                }
-                cnt[i] = n;
-            }
-        });
-    for (auto& th : pool) th.join();
-    std::vector<size_t> out(want.size());
-    uint64_t lines_before = 0;
-    size_t bi = 0;
-    for (size_t w = 0; w < want.size(); ++w) {
-        uint64_t target = want[w];   // offset of the start of line `target` = just past newline #target
-        if (target == 0) { out[w] = b; continue; }
-        while (bi < nblk && lines_before + cnt[bi] < target) { lines_before += cnt[bi]; ++bi; }
-        if (bi >= nblk) { out[w] = e; continue; }
-        size_t s = b + bi * blk, f = std::min(e, s + blk);
-        uint64_t need = target - lines_before;
-        const char* p = base + s;
-        while (need > 0) {
-            const void* q = memchr(p, '\n', (size_t)(base + f - p));
-            p = (const char*)q + 1;   // guaranteed to exist: cnt[bi] >= need
-            --need;
-        }
-        out[w] = (size_t)(p - base);
+// SOUP_DEBUG_LOAD=1: wall time of each loader phase on stderr
+struct LoadTimer {
+    const bool on = getenv("SOUP_DEBUG_LOAD") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "soup_debug load %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
     }
-    return out;
-}
+};
 
 void* alloc_out(size_t bytes, bool pinned) {
     if (bytes == 0) bytes = 8;
@@ -228,6 +294,8 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
     if (!A.open(alt_path)) { set_thread_error("cannot open alt mtx file"); return SOUP_ERR_IO; }   // S:602
     if (!R.open(ref_path)) { set_thread_error("cannot open ref mtx file"); return SOUP_ERR_IO; }   // S:605
     unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* e = getenv("SOUP_LOADER_THREADS")) nthreads = (unsigned)std::min(256, std::max(1, atoi(e)));   // tests / tuning
+    LoadTimer lt;
 
     // header: the zip only reaches line 2 if both files have it
     size_t a2 = skip_lines(A, 0, 2), r2 = skip_lines(R, 0, 2);
@@ -247,97 +315,124 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
     }
     if (total_loci > UINT32_MAX || total_cells > UINT32_MAX) { set_thread_error("matrix dimensions above 2^32 are not supported"); return SOUP_ERR_UNSUPPORTED; }
     uint64_t n_lines = 0;
-    if (have_header) n_lines = std::min(count_lines(A.p + a3, A.p + A.n), count_lines(R.p + r3, R.p + R.n));
+    NewlineIndex ia, ir;
+    if (have_header) {
+        ia = index_newlines(A.p, a3, A.n, nthreads);
+        ir = index_newlines(R.p, r3, R.n, nthreads);
+        n_lines = std::min(ia.lines, ir.lines);   // izip! stops at the shorter file (S:616)
+    }
+    lt.lap("open + index lines");
 
-    // ---- parallel lockstep parse into COO (file order)
-    std::vector<uint32_t> c_locus(n_lines), c_cell(n_lines), c_alt(n_lines), c_ref(n_lines);
+    // ---- parallel lockstep parse into COO (file order) + per-thread locus tallies (S:629-632: every line counts, wrapping u32)
+    std::unique_ptr<uint32_t[]> c_locus(new uint32_t[n_lines + 1]), c_cell(new uint32_t[n_lines + 1]), c_alt(new uint32_t[n_lines + 1]),
+        c_ref(new uint32_t[n_lines + 1]);
+    const size_t nchunks = std::max<size_t>(1, std::min<size_t>(nthreads * 4, n_lines / 65536 + 1));
+    const unsigned nworkers = (unsigned)std::min<size_t>(nthreads, nchunks);
+    std::vector<Tally> tally(nworkers);
     if (n_lines) {
-        size_t nchunks = std::max<size_t>(1, std::min<size_t>(nthreads * 4, n_lines / 65536 + 1));
-        std::vector<uint64_t> first(nchunks + 1);
-        for (size_t i = 0; i <= nchunks; ++i) first[i] = n_lines * i / nchunks;
-        std::vector<uint64_t> want(first.begin(), first.end() - 1);
-        std::vector<size_t> aoff = locate_lines(A.p, a3, A.n, want, nthreads);
-        std::vector<size_t> roff = locate_lines(R.p, r3, R.n, want, nthreads);
         std::vector<Chunk> chunks(nchunks);
-        for (size_t i = 0; i < nchunks; ++i) chunks[i] = {aoff[i], roff[i], first[i], first[i + 1] - first[i]};
+        parallel_for(nthreads, nchunks, [&](size_t i) {
+            const uint64_t first = n_lines * i / nchunks, last = n_lines * (i + 1) / nchunks;
+            chunks[i] = {line_offset(A.p, ia, first), line_offset(R.p, ir, first), first, last - first};
+        });
         ParseError err;
         std::atomic<size_t> next{0};
         std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nthreads; ++t)
-            pool.emplace_back([&] {
+        for (unsigned t = 0; t < nworkers; ++t)
+            pool.emplace_back([&, t] {
+                tally[t].init(total_loci);
                 for (size_t i; (i = next.fetch_add(1)) < nchunks && !err.code.load();)
-                    parse_chunk(A, R, chunks[i], total_loci, total_cells, c_locus.data(), c_cell.data(), c_alt.data(), c_ref.data(), &err);
+                    parse_chunk(A, R, chunks[i], total_loci, total_cells, c_locus.get(), c_cell.get(), c_alt.get(), c_ref.get(), tally[t], &err);
             });
         for (auto& th : pool) th.join();
         if (err.code.load()) { set_thread_error("%s", err.msg); return err.code.load(); }
     }
+    lt.lap("parse");
 
-    // ---- per-locus tallies (wrapping u32, every line counted) and the filter  S:629-632, S:659
-    std::vector<uint32_t> cells_ref(total_loci, 0), cells_alt(total_loci, 0), umis_ref(total_loci, 0), umis_alt(total_loci, 0);
-    std::vector<uint8_t> seen(total_loci, 0);
-    for (uint64_t i = 0; i < n_lines; ++i) {
-        uint32_t l = c_locus[i];
-        seen[l] = 1;
-        if (c_ref[i] > 0) { cells_ref[l] += 1; umis_ref[l] += c_ref[i]; }
-        if (c_alt[i] > 0) { cells_alt[l] += 1; umis_alt[l] += c_alt[i]; }
+    // ---- the filter  S:659 over the merged tallies; kept loci numbered densely in ascending original id (S:648-675)
+    std::vector<uint8_t> keep(total_loci, 0);
+    const bool raw = (flags & SOUP_MTX_RAW) != 0;
+    {
+        const size_t span = 1 << 14, nspan = (size_t)((total_loci + span - 1) / span);
+        parallel_for(nthreads, nspan, [&](size_t b) {
+            for (uint64_t l = b * span; l < std::min<uint64_t>(total_loci, (b + 1) * span); ++l) {
+                uint32_t cr = 0, ca = 0, ur = 0, ua = 0;
+                uint8_t seen = 0;
+                if (n_lines)
+                    for (const Tally& t : tally) { cr += t.cells_ref[l]; ca += t.cells_alt[l]; ur += t.umis_ref[l]; ua += t.umis_alt[l]; seen |= t.seen[l]; }
+                keep[l] = raw || (seen && cr >= min_ref && ca >= min_alt && ur >= min_ref_umis && ua >= min_alt_umis);
+            }
+        });
     }
+    std::vector<Tally>().swap(tally);
     std::vector<uint32_t> remap(total_loci, UINT32_MAX);
     std::vector<uint64_t> index_to_locus;
-    const bool raw = (flags & SOUP_MTX_RAW) != 0;
     for (uint64_t l = 0; l < total_loci; ++l)
-        if (raw || (seen[l] && cells_ref[l] >= min_ref && cells_alt[l] >= min_alt && umis_ref[l] >= min_ref_umis && umis_alt[l] >= min_alt_umis)) {
+        if (keep[l]) {
             remap[l] = (uint32_t)index_to_locus.size();
             index_to_locus.push_back(l);
         }
+    lt.lap("tallies + filter");
 
-    // ---- stable counting sort of the kept lines by cell (file order preserved inside a cell)
+    // ---- stable counting sort of the kept lines by cell (file order preserved inside a cell), in parallel: every part owns a
+    // contiguous range of lines and its own histogram over the cells; part p's slots of cell c follow those of parts < p.
+    const size_t parts = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(nthreads, n_lines / 65536 + 1));
+    std::vector<std::vector<uint64_t>> hist(parts);
+    parallel_for(nthreads, parts, [&](size_t p) {
+        std::vector<uint64_t>& h = hist[p];
+        h.assign(total_cells, 0);
+        for (uint64_t i = n_lines * p / parts; i < n_lines * (p + 1) / parts; ++i)
+            if (remap[c_locus[i]] != UINT32_MAX) h[c_cell[i]] += 1;
+    });
     std::vector<uint64_t> start(total_cells + 1, 0);
-    for (uint64_t i = 0; i < n_lines; ++i)
-        if (remap[c_locus[i]] != UINT32_MAX) start[c_cell[i] + 1] += 1;
-    for (uint64_t c = 0; c < total_cells; ++c) start[c + 1] += start[c];
-    uint64_t kept = start[total_cells];
-    struct Ent { uint32_t locus, alt, ref; };
-    std::vector<Ent> ents(kept);
     {
-        std::vector<uint64_t> cur(start.begin(), start.end() - 1);
-        for (uint64_t i = 0; i < n_lines; ++i) {
-            uint32_t nl = remap[c_locus[i]];
+        uint64_t run = 0;
+        for (uint64_t c = 0; c < total_cells; ++c) {
+            start[c] = run;
+            for (size_t p = 0; p < parts; ++p) { const uint64_t n = hist[p][c]; hist[p][c] = run; run += n; }
+        }
+        start[total_cells] = run;
+    }
+    const uint64_t kept = start[total_cells];
+    struct Ent { uint32_t locus, alt, ref; };
+    std::unique_ptr<Ent[]> ents(new Ent[kept + 1]);
+    parallel_for(nthreads, parts, [&](size_t p) {
+        uint64_t* cur = hist[p].data();
+        for (uint64_t i = n_lines * p / parts; i < n_lines * (p + 1) / parts; ++i) {
+            const uint32_t nl = remap[c_locus[i]];
             if (nl != UINT32_MAX) ents[cur[c_cell[i]]++] = {nl, c_alt[i], c_ref[i]};
         }
-    }
-    std::vector<uint32_t>().swap(c_locus); std::vector<uint32_t>().swap(c_cell);
-    std::vector<uint32_t>().swap(c_alt); std::vector<uint32_t>().swap(c_ref);
+    });
+    std::vector<std::vector<uint64_t>>().swap(hist);
+    c_locus.reset(); c_cell.reset(); c_alt.reset(); c_ref.reset();
+    lt.lap("sort by cell");
 
     // ---- per cell: ascending locus, duplicates last-wins (S:634), drop ref+alt == 0 (S:664)
     std::vector<uint64_t> row_len(total_cells, 0);
     {
-        std::atomic<uint64_t> next{0};
-        std::vector<std::thread> pool;
         const uint64_t step = 256;
-        for (unsigned t = 0; t < nthreads; ++t)
-            pool.emplace_back([&] {
-                for (uint64_t c0; (c0 = next.fetch_add(step)) < total_cells;)
-                    for (uint64_t c = c0; c < std::min(total_cells, c0 + step); ++c) {
-                        Ent* b = ents.data() + start[c];
-                        Ent* e = ents.data() + start[c + 1];
-                        if (raw) { row_len[c] = (uint64_t)(e - b); continue; }   // T:334: every line, in file order
-                        bool sorted = true;
-                        for (Ent* q = b; q + 1 < e; ++q)
-                            if (q[0].locus >= q[1].locus) { sorted = false; break; }
-                        if (!sorted) std::stable_sort(b, e, [](const Ent& x, const Ent& y) { return x.locus < y.locus; });
-                        Ent* w = b;
-                        for (Ent* q = b; q < e; ++q) {
-                            if (q + 1 < e && q[1].locus == q[0].locus) continue;   // a later duplicate overrides
-                            if (q->alt + q->ref == 0) continue;                    // wrapping u32 add, as S:664
-                            *w++ = *q;
-                        }
-                        row_len[c] = (uint64_t)(w - b);
-                    }
-            });
-        for (auto& th : pool) th.join();
+        parallel_for(nthreads, (size_t)((total_cells + step - 1) / step), [&](size_t blk) {
+            for (uint64_t c = blk * step; c < std::min<uint64_t>(total_cells, (blk + 1) * step); ++c) {
+                Ent* b = ents.get() + start[c];
+                Ent* e = ents.get() + start[c + 1];
+                if (raw) { row_len[c] = (uint64_t)(e - b); continue; }   // T:334: every line, in file order
+                bool sorted = true;
+                for (Ent* q = b; q + 1 < e; ++q)
+                    if (q[0].locus >= q[1].locus) { sorted = false; break; }
+                if (!sorted) std::stable_sort(b, e, [](const Ent& x, const Ent& y) { return x.locus < y.locus; });
+                Ent* w = b;
+                for (Ent* q = b; q < e; ++q) {
+                    if (q + 1 < e && q[1].locus == q[0].locus) continue;   // a later duplicate overrides
+                    if (q->alt + q->ref == 0) continue;                    // wrapping u32 add, as S:664
+                    *w++ = *q;
+                }
+                row_len[c] = (uint64_t)(w - b);
+            }
+        });
     }
     uint64_t nnz = 0;
     for (uint64_t c = 0; c < total_cells; ++c) nnz += row_len[c];
+    lt.lap("per-cell order");
 
     bool pinned = (flags & SOUP_MTX_PINNED) != 0;
     soup_mtx* m = (soup_mtx*)calloc(1, sizeof(soup_mtx));
@@ -357,18 +452,25 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
         set_thread_error(pinned ? "pinned host allocation failed (no CUDA driver?)" : "out of memory");
         return pinned ? SOUP_ERR_CUDA : SOUP_ERR_NOMEM;
     }
-    uint64_t pos = 0;
-    for (uint64_t c = 0; c < total_cells; ++c) {
-        m->row_ptr[c] = pos;
-        const Ent* b = ents.data() + start[c];
-        for (uint64_t j = 0; j < row_len[c]; ++j, ++pos) {
-            m->locus[pos] = b[j].locus;
-            m->alt[pos] = b[j].alt;
-            m->ref[pos] = b[j].ref;
-        }
+    {
+        uint64_t pos = 0;
+        for (uint64_t c = 0; c < total_cells; ++c) { m->row_ptr[c] = pos; pos += row_len[c]; }
+        m->row_ptr[total_cells] = pos;
+        const uint64_t step = 256;
+        parallel_for(nthreads, (size_t)((total_cells + step - 1) / step), [&](size_t blk) {
+            for (uint64_t c = blk * step; c < std::min<uint64_t>(total_cells, (blk + 1) * step); ++c) {
+                const Ent* b = ents.get() + start[c];
+                uint64_t o = m->row_ptr[c];
+                for (uint64_t j = 0; j < row_len[c]; ++j, ++o) {
+                    m->locus[o] = b[j].locus;
+                    m->alt[o] = b[j].alt;
+                    m->ref[o] = b[j].ref;
+                }
+            }
+        });
     }
-    m->row_ptr[total_cells] = pos;
     if (!index_to_locus.empty()) memcpy(m->index_to_locus, index_to_locus.data(), index_to_locus.size() * sizeof(uint64_t));
+    lt.lap("write csr");
     *out = m;
     return SOUP_OK;
 }

@@ -361,3 +361,61 @@ def test_souporcell_help_is_the_text_the_reference_readme_shows():
     cut = got.index("SOUPGPU OPTIONS:")
     assert got[:cut - 1] == want and got[cut - 1] == ""
     assert all("[soupgpu]" in ln for ln in got[cut + 1:] if ln)
+
+
+def test_loader_multichunk_irregular_lines_any_thread_count(tmp_path):
+    """A body long enough to split into several parse chunks and counting-sort parts (> 65536 lines each side of a cut), shuffled, with
+    duplicates, and with lines the fast path must hand to the general tokenizer (tabs, padding, '+', CRLF, extra tokens, long zero-padded
+    numbers, junk in the unparsed ref tokens): identical to the oracle's loader and identical for every thread count."""
+    v = synth.generate(n_cells=1400, n_loci=5000, k=3, mean_loci=300, seed=33)
+    rng = np.random.default_rng(4)
+    p = rng.permutation(v.nnz)
+    lo, ce, al, rf = (x[p] for x in (v.locus, v.cell, v.alt, v.ref))
+    dup = rng.integers(0, v.nnz, 500)                              # duplicates of existing coordinates with other counts: last one wins
+    lo, ce = np.concatenate([lo, lo[dup]]), np.concatenate([ce, ce[dup]])
+    al, rf = np.concatenate([al, rng.integers(0, 4, 500).astype(al.dtype)]), np.concatenate([rf, rng.integers(0, 4, 500).astype(rf.dtype)])
+    n = lo.shape[0]
+    assert n > 4 * 65536, n
+    forms = ["{l} {c} {x}\n", "{l}\t{c}\t{x}\n", "  {l}   {c}  {x}  \n", "+{l} +{c} +{x}\n", "{l} {c} {x}\r\n", "{l} {c} {x} trailing tokens 9\n",
+             "0000000000{l} {c} 000000000000{x}\n", "{l} {c} {x}\t\r\n"]
+    kind = np.where(rng.random(n) < 0.02, rng.integers(1, len(forms), n), 0)
+    with open(tmp_path / "alt.mtx", "w", newline="") as fa, open(tmp_path / "ref.mtx", "w", newline="") as fr:
+        for fh in (fa, fr):
+            fh.write("%%MatrixMarket matrix coordinate real general\n% irregular\n")
+            fh.write(f"{v.n_loci} {v.n_cells} {n}\n")
+        for i in range(n):
+            fa.write(forms[kind[i]].format(l=lo[i] + 1, c=ce[i] + 1, x=al[i]))
+            if kind[i] == 5:
+                fr.write(f"junk -7.5e3 {rf[i]}\n")                 # only the third ref token is ever parsed (S:625)
+            else:
+                fr.write(forms[kind[i]].format(l=lo[i] + 1, c=ce[i] + 1, x=rf[i]))
+        fa.write(f"{lo[0] + 1} {ce[0] + 1} {al[0]}")               # no newline at the end of either file: still a line
+        fr.write(f"{lo[0] + 1} {ce[0] + 1} {rf[0]}")
+    alt, ref = str(tmp_path / "alt.mtx"), str(tmp_path / "ref.mtx")
+    ex = orc.OracleData.from_mtx(alt, ref, 3, 3).export()
+    old = os.environ.get("SOUP_LOADER_THREADS")
+    try:
+        for threads in ("1", "3", "8", None):
+            if threads is None:
+                os.environ.pop("SOUP_LOADER_THREADS", None)
+            else:
+                os.environ["SOUP_LOADER_THREADS"] = threads
+            m = sp.load_mtx(alt, ref, 3, 3)
+            for k in ("row_ptr", "locus", "alt", "ref", "index_to_locus"):
+                assert np.array_equal(getattr(m, k), ex[k]), (threads, k)
+            raw = sp.load_mtx(alt, ref, raw=True)                  # troublet's view: every line, file order inside a cell
+            assert raw.nnz == n + 1 and raw.n_loci == v.n_loci
+            order = np.argsort(np.concatenate([ce, ce[:1]]), kind="stable")
+            assert np.array_equal(raw.locus, np.concatenate([lo, lo[:1]])[order].astype(raw.locus.dtype)), threads
+            assert np.array_equal(raw.alt, np.concatenate([al, al[:1]])[order].astype(raw.alt.dtype)), threads
+    finally:
+        if old is None:
+            os.environ.pop("SOUP_LOADER_THREADS", None)
+        else:
+            os.environ["SOUP_LOADER_THREADS"] = old
+    # a malformed line in a late chunk is still the reference's panic
+    bad = open(alt).read().split("\n")
+    bad[len(bad) - 10] = "12 x 3"
+    open(alt, "w").write("\n".join(bad))
+    with pytest.raises(sp.SoupError):
+        sp.load_mtx(alt, ref, 3, 3)
