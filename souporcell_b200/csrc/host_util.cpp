@@ -2,12 +2,15 @@
 // formatting, the ln_binomial table, barcodes, the TSV writer, souporcell3 outlier logic.
 // Reference: /root/reference/souporcell/src/main.rs ("S:").
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <charconv>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iterator>
+#include <memory>
 #include <mutex>
 #include <zlib.h>
 
@@ -59,30 +62,97 @@ float ln_binomial_f32(uint32_t n, uint32_t k) {
 }
 
 // Rust's Display for f32: shortest digits that round-trip, positional notation, no exponent.
-std::string format_f32(float v) {
-    if (std::isnan(v)) return "NaN";
-    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
-    if (v == 0.0f) return std::signbit(v) ? "-0" : "0";
+// Rust's `{}` for floats: the shortest digits that round-trip, positional notation, never an exponent.  Writes at dst and returns the
+// end; at most 64 bytes for f32 ("-0." + 44 zeros + 9 digits), 352 for f64 ("-0." + 323 zeros + 17 digits).
+template <typename T>
+char* format_float_into(char* dst, T v) {
+    auto put = [&dst](const char* lit) { while (*lit) *dst++ = *lit++; return dst; };
+    if (std::isnan(v)) return put("NaN");
+    if (std::isinf(v)) return put(v < 0 ? "-inf" : "inf");
+    if (v == 0) return put(std::signbit(v) ? "-0" : "0");
     char buf[48];
-    auto res = std::to_chars(buf, buf + sizeof(buf) - 1, v, std::chars_format::scientific);
-    *res.ptr = '\0';   // to_chars does not terminate; the exponent is parsed with atoi below
+    const auto res = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);   // d[.ddd]e[+-]xx
     const char* p = buf;
-    std::string out;
-    if (*p == '-') { out.push_back('-'); ++p; }
-    std::string digits;
-    const char* e = p;
-    while (e < res.ptr && *e != 'e') { if (*e != '.') digits.push_back(*e); ++e; }
-    int exp10 = atoi(e + 1);
-    int nd = (int)digits.size();
-    if (exp10 >= 0) {
-        if (nd <= exp10 + 1) { out += digits; out.append((size_t)(exp10 + 1 - nd), '0'); }
-        else { out.append(digits, 0, (size_t)exp10 + 1); out.push_back('.'); out.append(digits, (size_t)exp10 + 1, std::string::npos); }
+    if (*p == '-') { *dst++ = '-'; ++p; }
+    char digits[24];
+    int nd = 0;
+    for (; p < res.ptr && *p != 'e'; ++p)
+        if (*p != '.') digits[nd++] = *p;
+    ++p;                                   // 'e'
+    const bool neg = *p == '-';
+    ++p;                                   // sign (always present)
+    int exp10 = 0;
+    for (; p < res.ptr; ++p) exp10 = exp10 * 10 + (*p - '0');
+    if (!neg) {
+        if (nd <= exp10 + 1) {
+            memcpy(dst, digits, (size_t)nd); dst += nd;
+            memset(dst, '0', (size_t)(exp10 + 1 - nd)); dst += exp10 + 1 - nd;
+        } else {
+            memcpy(dst, digits, (size_t)exp10 + 1); dst += exp10 + 1;
+            *dst++ = '.';
+            memcpy(dst, digits + exp10 + 1, (size_t)(nd - exp10 - 1)); dst += nd - exp10 - 1;
+        }
     } else {
-        out += "0.";
-        out.append((size_t)(-exp10 - 1), '0');
-        out += digits;
+        *dst++ = '0'; *dst++ = '.';
+        memset(dst, '0', (size_t)(exp10 - 1)); dst += exp10 - 1;
+        memcpy(dst, digits, (size_t)nd); dst += nd;
     }
-    return out;
+    return dst;
+}
+char* format_f32_into(char* dst, float v) { return format_float_into(dst, v); }
+constexpr size_t kMaxF32 = 64, kMaxF64 = 352;
+
+// Formats rows [0, n) in parallel (blocks of 512 rows, a wave of blocks at a time) and writes them to `out` in order.
+// row_max(i) bounds the bytes of row i; emit(i, w) writes the row at w and returns its end.  Each block goes through a local pointer
+// into its own cache-line-aligned buffer (neighbouring std::string headers would false-share on every append).
+template <typename Max, typename Emit>
+int32_t write_rows(FILE* out, uint64_t n, size_t typical_row, Max row_max, Emit emit) {
+    struct alignas(128) Buf {
+        std::unique_ptr<char[]> p;
+        size_t cap = 0, len = 0;
+    };
+    const uint64_t block = 512;
+    const unsigned nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const uint64_t n_blocks = (n + block - 1) / block, wave = (uint64_t)nthreads * 4;
+    std::vector<Buf> text(std::min(wave, std::max<uint64_t>(n_blocks, 1)));
+    for (uint64_t b0 = 0; b0 < n_blocks; b0 += wave) {
+        const uint64_t nb = std::min(wave, n_blocks - b0);
+        std::atomic<uint64_t> next{0};
+        auto work = [&] {
+            for (uint64_t j; (j = next.fetch_add(1)) < nb;) {
+                Buf& buf = text[j];
+                char* base = buf.p.get();
+                size_t cap = buf.cap, len = 0;
+                for (uint64_t i = (b0 + j) * block; i < std::min(n, (b0 + j + 1) * block); ++i) {
+                    const size_t need = row_max(i);
+                    if (len + need > cap) {
+                        const size_t ncap = std::max(cap * 2, len + need + typical_row * (size_t)block);
+                        std::unique_ptr<char[]> np(new char[ncap]);
+                        if (len) memcpy(np.get(), base, len);
+                        buf.p.swap(np);
+                        base = buf.p.get();
+                        cap = ncap;
+                    }
+                    len = (size_t)(emit(i, base + len) - base);
+                }
+                buf.cap = cap;
+                buf.len = len;
+            }
+        };
+        if (nb == 1 || nthreads == 1) work();
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < std::min<uint64_t>(nthreads, nb); ++t) pool.emplace_back(work);
+            for (auto& th : pool) th.join();
+        }
+        for (uint64_t j = 0; j < nb; ++j)
+            if (fwrite(text[j].p.get(), 1, text[j].len, out) != text[j].len) { set_thread_error("write failed"); return SOUP_ERR_IO; }
+    }
+    return SOUP_OK;
+}
+std::string format_f32(float v) {
+    char b[64];
+    return std::string(b, format_f32_into(b, v));
 }
 std::string format_f32_w8(float v) {
     std::string s = format_f32(v);
@@ -158,29 +228,9 @@ int32_t soup_thread_seeds(uint8_t seed, uint32_t threads, uint32_t run, uint8_t*
 }
 
 // ---- troublet host side: load_clusters T:414-449 and the TSV writer T:36-41, T:233-243
-static std::string format_f64(double v) {   // Rust `{}` for f64: shortest round-trip digits, never scientific
-    if (std::isnan(v)) return "NaN";
-    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
-    if (v == 0.0) return std::signbit(v) ? "-0" : "0";
-    char buf[64];
-    auto res = std::to_chars(buf, buf + sizeof(buf) - 1, v, std::chars_format::scientific);
-    *res.ptr = '\0';
-    const char* p = buf;
-    std::string out;
-    if (*p == '-') { out.push_back('-'); ++p; }
-    std::string digits;
-    const char* e = p;
-    while (e < res.ptr && *e != 'e') { if (*e != '.') digits.push_back(*e); ++e; }
-    const int exp10 = atoi(e + 1), nd = (int)digits.size();
-    if (exp10 >= 0) {
-        if (nd <= exp10 + 1) { out += digits; out.append((size_t)(exp10 + 1 - nd), '0'); }
-        else { out.append(digits, 0, (size_t)exp10 + 1); out.push_back('.'); out.append(digits, (size_t)exp10 + 1, std::string::npos); }
-    } else {
-        out += "0.";
-        out.append((size_t)(-exp10 - 1), '0');
-        out += digits;
-    }
-    return out;
+static std::string format_f64(double v) {   // Rust `{}` for f64
+    char b[kMaxF64];
+    return std::string(b, format_float_into(b, v));
 }
 
 int32_t soup_clusters_load(const char* path, char** barcode_blob, double** losses, uint64_t* n_cells, int32_t* k, int32_t* n_clusters) {
@@ -242,23 +292,40 @@ int32_t soup_troublet_write(void* out_file, const char* barcode_blob, uint64_t n
     FILE* f = (FILE*)out_file;
     if (!f || !barcode_blob || !r || k <= 0) { set_thread_error("soup_troublet_write: bad argument"); return SOUP_ERR_INVALID; }
     static const char* NAME[4] = {"singlet", "unassigned", "doublet", "unassigned"};
-    std::string out = "barcode\tstatus\tassignment\tsinglet_posterior\tdoublet_posterior\tlog_prob_singleton\tlog_prob_doublet\t";
-    for (int32_t c = 0; c < k; ++c) { out += "cluster" + std::to_string(c); out += c + 1 == k ? "\n" : "\t"; }
-    const char* q = barcode_blob;
-    for (uint64_t cell = 0; cell < n_cells; ++cell) {
-        out += q;
-        q += strlen(q) + 1;
-        const int st = r->status[cell];
-        out += "\t"; out += NAME[st & 3]; out += "\t";
-        if (st == SOUP_TROUBLET_SINGLET || st == SOUP_TROUBLET_UNASSIGNED) out += std::to_string(r->best_singlet[cell]);
-        else out += std::to_string(r->doublet1[cell]) + "/" + std::to_string(r->doublet2[cell]);
-        out += "\t" + format_f64(r->singlet_posterior[cell]) + "\t" + format_f64(r->doublet_posterior[cell]) + "\t" +
-               format_f64(r->log_prob_singleton[cell]) + "\t" + format_f64(r->log_prob_doublet[cell]) + "\t";
-        for (int32_t c = 0; c < k; ++c) { out += format_f64(r->cluster_logprobs[cell * (uint64_t)k + c]); if (c + 1 < k) out += "\t"; }
-        out += "\n";
-        if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), f); out.clear(); }
+    std::string head = "barcode\tstatus\tassignment\tsinglet_posterior\tdoublet_posterior\tlog_prob_singleton\tlog_prob_doublet\t";
+    for (int32_t c = 0; c < k; ++c) { head += "cluster" + std::to_string(c); head += c + 1 == k ? "\n" : "\t"; }
+    if (fwrite(head.data(), 1, head.size(), f) != head.size()) { set_thread_error("write failed"); return SOUP_ERR_IO; }
+    std::vector<const char*> bc(n_cells);
+    size_t longest = 0;
+    {
+        const char* q = barcode_blob;
+        for (uint64_t i = 0; i < n_cells; ++i) { bc[i] = q; const size_t l = strlen(q); longest = std::max(longest, l); q += l + 1; }
     }
-    fwrite(out.data(), 1, out.size(), f);
+    auto field = [](char* w, double v) { w = format_float_into(w, v); *w++ = '\t'; return w; };
+    const int32_t rc = write_rows(
+        f, n_cells, longest + 48 + ((size_t)k + 4) * 20,
+        [&](uint64_t cell) { return strlen(bc[cell]) + 64 + ((size_t)k + 4) * (kMaxF64 + 1); },
+        [&](uint64_t cell, char* w) {
+            const size_t bl = strlen(bc[cell]);
+            memcpy(w, bc[cell], bl); w += bl;
+            *w++ = '\t';
+            const int st = r->status[cell];
+            for (const char* nm = NAME[st & 3]; *nm;) *w++ = *nm++;
+            *w++ = '\t';
+            if (st == SOUP_TROUBLET_SINGLET || st == SOUP_TROUBLET_UNASSIGNED) w = std::to_chars(w, w + 12, r->best_singlet[cell]).ptr;
+            else { w = std::to_chars(w, w + 12, r->doublet1[cell]).ptr; *w++ = '/'; w = std::to_chars(w, w + 12, r->doublet2[cell]).ptr; }
+            *w++ = '\t';
+            w = field(w, r->singlet_posterior[cell]);
+            w = field(w, r->doublet_posterior[cell]);
+            w = field(w, r->log_prob_singleton[cell]);
+            w = field(w, r->log_prob_doublet[cell]);
+            for (int32_t c = 0; c < k; ++c) {
+                w = format_float_into(w, r->cluster_logprobs[cell * (uint64_t)k + c]);
+                *w++ = c + 1 < k ? '\t' : '\n';
+            }
+            return w;
+        });
+    if (rc != SOUP_OK) return rc;
     return ferror(f) ? SOUP_ERR_IO : SOUP_OK;
 }
 
@@ -410,28 +477,34 @@ int32_t soup_write_clusters(void* out_file, const char* barcode_blob, uint64_t n
                             uint64_t n_cells, int32_t k) {
     FILE* out = (FILE*)out_file;
     if (!out || (!barcode_blob && n_barcodes) || (!lp && n_cells) || k <= 0) { set_thread_error("soup_write_clusters: bad argument"); return SOUP_ERR_INVALID; }
-    uint64_t n = std::min(n_barcodes, n_cells);
-    const char* bc = barcode_blob;
-    std::string line;
-    for (uint64_t i = 0; i < n; ++i) {
-        const float* row = lp + i * (uint64_t)k;
-        int best = 0;
-        float best_lp = -INFINITY;
-        for (int c = 0; c < k; ++c)
-            if (row[c] > best_lp) { best = c; best_lp = row[c]; }
-        line.assign(bc);
-        bc += strlen(bc) + 1;
-        line.push_back('\t');
-        line += std::to_string(best);
-        line.push_back('\t');
-        for (int c = 0; c < k; ++c) {
-            line += format_f32(row[c]);
-            if (c < k - 1) line.push_back('\t');
-        }
-        line.push_back('\n');
-        if (fwrite(line.data(), 1, line.size(), out) != line.size()) { set_thread_error("write failed"); return SOUP_ERR_IO; }
+    const uint64_t n = std::min(n_barcodes, n_cells);   // zip() stops at the shorter (S:133)
+    std::vector<const char*> bc(n);
+    {
+        const char* q = barcode_blob;
+        for (uint64_t i = 0; i < n; ++i) { bc[i] = q; q += strlen(q) + 1; }
     }
-    return SOUP_OK;
+    size_t longest = 0;
+    for (uint64_t i = 0; i < n; ++i) longest = std::max(longest, strlen(bc[i]));
+    return write_rows(
+        out, n, longest + 16 + (size_t)k * 14,
+        [&](uint64_t i) { return strlen(bc[i]) + 16 + (size_t)k * (kMaxF32 + 1); },
+        [&](uint64_t i, char* w) {
+            const float* row = lp + i * (uint64_t)k;
+            int best = 0;
+            float best_lp = -INFINITY;                              // first maximum (S:134-141)
+            for (int c = 0; c < k; ++c)
+                if (row[c] > best_lp) { best = c; best_lp = row[c]; }
+            const size_t bl = strlen(bc[i]);
+            memcpy(w, bc[i], bl); w += bl;
+            *w++ = '\t';
+            w = std::to_chars(w, w + 12, best).ptr;
+            *w++ = '\t';
+            for (int c = 0; c < k; ++c) {
+                w = format_f32_into(w, row[c]);
+                *w++ = c < k - 1 ? '\t' : '\n';
+            }
+            return w;
+        });
 }
 
 // S:150-187

@@ -419,3 +419,36 @@ def test_loader_multichunk_irregular_lines_any_thread_count(tmp_path):
     open(alt, "w").write("\n".join(bad))
     with pytest.raises(sp.SoupError):
         sp.load_mtx(alt, ref, 3, 3)
+
+
+def test_write_clusters_many_blocks_matches_oracle_formatting(tmp_path):
+    """The TSV writer formats blocks of cells in parallel and writes them in order: enough rows for several waves of blocks, ragged
+    barcode lengths, special values; every token must be the oracle's rendering, the cluster column the FIRST maximum (S:134-141)."""
+    n, k = 40000, 3
+    rng = np.random.default_rng(12)
+    lp = (-rng.random((n, k)) * 10.0 ** rng.integers(-6, 5, (n, k))).astype(np.float32)
+    special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-45, -1.17549435e-38, 3.4028235e38, -16777216.0, 0.1, -1e-7, 123456.79], dtype=np.float32)
+    idx = rng.integers(0, n * k, 3000)
+    lp.reshape(-1)[idx] = special[rng.integers(0, special.shape[0], 3000)]
+    lp[17] = [-5.0, -5.0, -5.0]                                      # ties: strict '>' keeps the first
+    lp[18] = [np.nan, np.nan, np.nan]                                # nothing beats -inf: cluster 0
+    names = ["BC" + "ACGT" * int(rng.integers(0, 6)) + f"{i}-1" for i in range(n)]
+    out = tmp_path / "big.tsv"
+    sp.write_clusters(str(out), names, lp)
+    rows = out.read_text().split("\n")
+    assert rows[-1] == "" and len(rows) == n + 1
+    fmt = {}
+    for i in range(n):
+        tok = rows[i].split("\t")
+        assert tok[0] == names[i] and len(tok) == k + 2, i
+        best, best_v = 0, -np.inf
+        for c in range(k):
+            if lp[i, c] > best_v:
+                best, best_v = c, lp[i, c]
+        assert tok[1] == str(best), i
+        for c in range(k):
+            v = float(lp[i, c])
+            key = lp[i, c].tobytes()
+            if key not in fmt:
+                fmt[key] = orc.format_f32(v)
+            assert tok[2 + c] == fmt[key], (i, c, v)

@@ -298,3 +298,37 @@ def test_f64_display_against_the_reference_readme_sample(tmp_path):
     got = [ln.split("\t") for ln in open(path).read().splitlines()[1:]]
     for r, t in zip(rows, got):
         assert t[:3] == r[:3] and t[5:] == r[3:], (r, t)          # columns 3-4 are the posteriors the sample's version did not print
+
+
+def test_troublet_writer_many_blocks(tmp_path):
+    """soup_troublet_write formats blocks of rows in parallel: several blocks, all four statuses, special values; every token against
+    the independent Python rendering of Rust's f64 Display."""
+    from souporcell_b200 import api
+    n, k = 3000, 5
+    rng = np.random.default_rng(3)
+    special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 5e-324, 1.7976931348623157e308, 1e21, 1e-7, 0.1, -41.24912227493646, 0.999999996610466])
+    draw = lambda shape: np.where(rng.random(shape) < 0.05, special[rng.integers(0, special.shape[0], shape)], -rng.random(shape) * 10.0 ** rng.integers(-9, 6, shape))
+    out = dict(status=rng.integers(0, 4, n).astype(np.int32), best_singlet=rng.integers(0, k, n).astype(np.int32), doublet1=rng.integers(0, k, n).astype(np.int32),
+               doublet2=rng.integers(0, k, n).astype(np.int32), singlet_posterior=draw(n), doublet_posterior=draw(n), log_prob_singleton=draw(n),
+               log_prob_doublet=draw(n), cluster_logprobs=np.ascontiguousarray(draw((n, k))))
+    res = api._TroubletResult(*[out[f].ctypes.data_as(C.c_void_p) for f, _ in api._TroubletResult._fields_[:9]])
+    names = [f"CELL{'AC' * int(rng.integers(0, 9))}{i}-1" for i in range(n)]
+    blob = b"".join(x.encode() + b"\0" for x in names) + b"\0"
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    path = str(tmp_path / "big.tsv")
+    f = libc.fopen(path.encode(), b"w")
+    assert sp.lib().soup_troublet_write(f, blob, n, k, C.byref(res)) == 0
+    libc.fclose(f)
+    rows = open(path).read().split("\n")
+    assert len(rows) == n + 2 and rows[-1] == "" and rows[0].endswith("\tcluster4")
+    status = ["singlet", "unassigned", "doublet", "unassigned"]
+    for i in range(n):
+        tok = rows[1 + i].split("\t")
+        st = int(out["status"][i])
+        want_assign = str(out["best_singlet"][i]) if st in (0, 1) else f"{out['doublet1'][i]}/{out['doublet2'][i]}"
+        assert tok[:3] == [names[i], status[st], want_assign], i
+        want = [out[f][i] for f in ("singlet_posterior", "doublet_posterior", "log_prob_singleton", "log_prob_doublet")] + list(out["cluster_logprobs"][i])
+        assert tok[3:] == [_rust_f64(x) for x in want], i
