@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-pthread",
 ]
 LIB_SOURCES = ["soup_device.cu", "host_loader.cpp", "host_util.cpp", "soup_driver.cpp"]
-LIB_HEADERS = ["soup_kernels.cuh", "troublet_kernels.cuh", "soup_common.hpp", "glibc_flt32.h", os.path.join("..", "..", "include", "soupgpu.h")]
+LIB_HEADERS = ["soup_kernels.cuh", "troublet_kernels.cuh", "soup_common.hpp", "host_parallel.hpp", "glibc_flt32.h", os.path.join("..", "..", "include", "soupgpu.h")]
 
 
 def _newer(target: str, deps) -> bool:

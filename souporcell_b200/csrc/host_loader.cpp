@@ -23,6 +23,7 @@
 #include <memory>
 #include <thread>
 
+#include "host_parallel.hpp"
 #include "soup_common.hpp"
 
 namespace soup {
@@ -109,19 +110,6 @@ size_t skip_lines(const Mapped& m, size_t from, size_t k) {
     }
     return pos;
 }
-// Runs fn(i) for i in [0, n) on up to `nthreads` threads (dynamic distribution, one item at a time).
-template <typename F>
-void parallel_for(unsigned nthreads, size_t n, F fn) {
-    if (n == 0) return;
-    const unsigned t_n = (unsigned)std::min<size_t>(std::max(1u, nthreads), n);
-    if (t_n == 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
-    std::atomic<size_t> next{0};
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < t_n; ++t)
-        pool.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); });
-    for (auto& th : pool) th.join();
-}
-
 // Newline counts of a file body [b, e) per byte block, built in parallel: how many lines BufRead::lines() yields, and where
 // line k starts, without a serial pass over the text.
 struct NewlineIndex {

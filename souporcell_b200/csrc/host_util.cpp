@@ -1,6 +1,10 @@
 // Host-side pieces of libsoupgpu that need no GPU: RNG streams, Rust-compatible number
 // formatting, the ln_binomial table, barcodes, the TSV writer, souporcell3 outlier logic.
 // Reference: /root/reference/souporcell/src/main.rs ("S:").
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -14,6 +18,7 @@
 #include <mutex>
 #include <zlib.h>
 
+#include "host_parallel.hpp"
 #include "soup_common.hpp"
 
 namespace soup {
@@ -235,55 +240,133 @@ static std::string format_f64(double v) {   // Rust `{}` for f64
 
 int32_t soup_clusters_load(const char* path, char** barcode_blob, double** losses, uint64_t* n_cells, int32_t* k, int32_t* n_clusters) {
     if (!path || !barcode_blob || !losses || !n_cells || !k || !n_clusters) { set_thread_error("soup_clusters_load: bad argument"); return SOUP_ERR_INVALID; }
-    FILE* f = fopen(path, "rb");
-    if (!f) { set_thread_error("Unable to open file %s", path); return SOUP_ERR_IO; }
-    std::string content;
-    char buf[1 << 16];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) content.append(buf, n);
-    fclose(f);
-    std::string blob;
-    std::vector<double> vals;
-    uint64_t cells = 0;
-    int32_t cols = -1;
-    uint64_t max_cluster = 0;
-    size_t pos = 0;
-    while (pos < content.size()) {
-        size_t e = content.find('\n', pos);
-        if (e == std::string::npos) e = content.size();
-        std::string line = content.substr(pos, e - pos);
-        pos = e + 1;
-        size_t b0 = line.find_first_not_of(" \t\r\n"), e0 = line.find_last_not_of(" \t\r\n");   // line.trim()
-        line = b0 == std::string::npos ? std::string() : line.substr(b0, e0 - b0 + 1);
-        std::vector<std::string> tok;
-        for (size_t q = 0;;) {
-            size_t t = line.find('\t', q);
-            tok.push_back(line.substr(q, t == std::string::npos ? std::string::npos : t - q));
-            if (t == std::string::npos) break;
-            q = t + 1;
+    // the file is mapped (or, for something that is not a regular file, read) — a 100k x 64 clusters file is 70 MB
+    struct Text {
+        const char* p = nullptr;
+        size_t n = 0;
+        bool mapped = false;
+        std::string owned;
+        ~Text() { if (mapped) munmap((void*)p, n); }
+        const char* data() const { return p; }
+        size_t size() const { return n; }
+    } content;
+    {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) { set_thread_error("Unable to open file %s", path); return SOUP_ERR_IO; }
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) { content.p = (const char*)m; content.n = (size_t)st.st_size; content.mapped = true; }
         }
-        if (tok.size() < 2) { set_thread_error("clusters file line %llu: index out of bounds: the len is %zu but the index is 1", (unsigned long long)cells + 1, tok.size()); return SOUP_ERR_INVALID; }
-        char* endp = nullptr;
-        const unsigned long long c1 = strtoull(tok[1].c_str(), &endp, 10);
-        if (tok[1].empty() || *endp) { set_thread_error("clusters file line %llu: cannot parse the cluster column", (unsigned long long)cells + 1); return SOUP_ERR_INVALID; }
-        max_cluster = std::max<uint64_t>(max_cluster, c1);
-        const int32_t here = (int32_t)tok.size() - 2;
-        if (cols < 0) cols = here;
-        if (here != cols) { set_thread_error("clusters file line %llu: %d log-probability columns, expected %d", (unsigned long long)cells + 1, here, cols); return SOUP_ERR_INVALID; }
-        for (size_t i = 2; i < tok.size(); ++i) {
-            const double v = strtod(tok[i].c_str(), &endp);
-            if (tok[i].empty() || *endp) { set_thread_error("clusters file line %llu: cannot parse '%s' as f64", (unsigned long long)cells + 1, tok[i].c_str()); return SOUP_ERR_INVALID; }
-            vals.push_back(v);
+        if (!content.mapped) {
+            char buf[1 << 16];
+            ssize_t got;
+            while ((got = ::read(fd, buf, sizeof(buf))) > 0) content.owned.append(buf, (size_t)got);
+            content.p = content.owned.data();
+            content.n = content.owned.size();
         }
-        blob.append(tok[0]);
-        blob.push_back('\0');
-        ++cells;
+        ::close(fd);
     }
+    // lines as BufRead::lines() yields them, each trimmed like str::trim (T:422)
+    struct Line { const char* b; const char* e; };
+    std::vector<Line> lines;
+    for (size_t pos = 0; pos < content.size();) {
+        const char* b = content.data() + pos;
+        const char* e = (const char*)memchr(b, '\n', content.size() - pos);
+        if (!e) e = content.data() + content.size();
+        pos = (size_t)(e - content.data()) + 1;
+        auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; };
+        while (b < e && blank(*b)) ++b;
+        while (e > b && blank(e[-1])) --e;
+        lines.push_back({b, e});
+    }
+    const uint64_t cells = lines.size();
+    int32_t cols = 0;
+    if (cells) cols = (int32_t)std::count(lines[0].b, lines[0].e, '\t') - 1;    // tokens = tabs + 1, minus barcode and cluster
+    const size_t n_vals = cols > 0 ? (size_t)cells * (size_t)cols : 0;
+    struct Free { void operator()(void* q) const { free(q); } };
+    std::unique_ptr<double[], Free> vals((double*)malloc(std::max<size_t>(n_vals, 1) * sizeof(double)));   // handed to the caller at the end
+    if (!vals) { set_thread_error("out of memory"); return SOUP_ERR_NOMEM; }
+    std::vector<Line> names(cells);
+    // rows are parsed in parallel; the error reported is the one of the earliest bad line, as a sequential reader would hit it
+    std::mutex err_mu;
+    uint64_t err_line = UINT64_MAX;
+    std::string err_msg;
+    auto fail = [&](uint64_t line, const char* fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        std::string m = vformat(fmt, ap);
+        va_end(ap);
+        std::lock_guard<std::mutex> g(err_mu);
+        if (line < err_line) { err_line = line; err_msg.swap(m); }
+    };
+    const uint64_t step = 256, n_blocks = (cells + step - 1) / step;
+    std::vector<uint64_t> block_max(n_blocks, 0);
+    parallel_for(host_threads(), (size_t)n_blocks, [&](size_t blk) {
+        std::string tmp;
+        for (uint64_t i = blk * step; i < std::min(cells, (blk + 1) * step); ++i) {
+            const char* p = lines[i].b;
+            const char* const end = lines[i].e;
+            auto token = [&](const char*& tb, const char*& te) {   // str::split("\t"): empty tokens count, the last one ends the line
+                if (p > end) return false;
+                tb = p;
+                te = (const char*)memchr(p, '\t', (size_t)(end - p));
+                if (!te) te = end;
+                p = te + 1;
+                return true;
+            };
+            const char *tb, *te;
+            token(tb, te);
+            names[i] = {tb, te};
+            if (!token(tb, te)) { fail(i, "clusters file line %llu: index out of bounds: the len is 1 but the index is 1", (unsigned long long)i + 1); return; }
+            {   // parse::<usize>(): optional '+', then digits only
+                const char* q = tb;
+                if (q < te && *q == '+') ++q;
+                uint64_t c1 = 0;
+                bool ok = q < te;
+                for (; ok && q < te; ++q) {
+                    const unsigned d = (unsigned)(unsigned char)*q - '0';
+                    if (d > 9 || c1 > (UINT64_MAX - d) / 10) ok = false; else c1 = c1 * 10 + d;
+                }
+                if (!ok) { fail(i, "clusters file line %llu: cannot parse the cluster column", (unsigned long long)i + 1); return; }
+                block_max[blk] = std::max(block_max[blk], c1);
+            }
+            int32_t here = 0;
+            while (token(tb, te)) {
+                if (here >= cols) { ++here; continue; }
+                double v = 0;
+                // digits, '.', exponent and '-' only: from_chars (correctly rounded, like strtod); anything else — '+', inf, nan, blanks —
+                // takes the strtod route that has always defined what this reader accepts
+                bool plain = tb < te;
+                for (const char* q = tb; plain && q < te; ++q) plain = (*q >= '0' && *q <= '9') || *q == '.' || *q == 'e' || *q == 'E' || *q == '-';
+                bool ok;
+                if (plain) {
+                    const auto r = std::from_chars(tb, te, v, std::chars_format::general);
+                    ok = r.ec == std::errc() && r.ptr == te;
+                    if (r.ec == std::errc::result_out_of_range) plain = false;   // strtod decides (inf / 0 / subnormal)
+                }
+                if (!plain) {
+                    tmp.assign(tb, te);
+                    char* endp = nullptr;
+                    v = strtod(tmp.c_str(), &endp);
+                    ok = !tmp.empty() && *endp == 0;
+                }
+                if (!ok) { fail(i, "clusters file line %llu: cannot parse '%s' as f64", (unsigned long long)i + 1, std::string(tb, te).c_str()); return; }
+                vals[(size_t)i * (size_t)cols + (size_t)here] = v;
+                ++here;
+            }
+            if (here != cols) { fail(i, "clusters file line %llu: %d log-probability columns, expected %d", (unsigned long long)i + 1, here, cols < 0 ? 0 : cols); return; }
+        }
+    });
+    if (err_line != UINT64_MAX) { set_thread_error("%s", err_msg.c_str()); return SOUP_ERR_INVALID; }
+    uint64_t max_cluster = 0;
+    for (uint64_t m : block_max) max_cluster = std::max(max_cluster, m);
+    std::string blob;
+    for (const Line& nm : names) { blob.append(nm.b, (size_t)(nm.e - nm.b)); blob.push_back('\0'); }
     *barcode_blob = (char*)malloc(std::max<size_t>(blob.size(), 1));
-    *losses = (double*)malloc(std::max<size_t>(vals.size(), 1) * sizeof(double));
-    if (!*barcode_blob || !*losses) { free(*barcode_blob); free(*losses); set_thread_error("out of memory"); return SOUP_ERR_NOMEM; }
+    if (!*barcode_blob) { set_thread_error("out of memory"); return SOUP_ERR_NOMEM; }
     memcpy(*barcode_blob, blob.data(), blob.size());
-    memcpy(*losses, vals.data(), vals.size() * sizeof(double));
+    *losses = vals.release();
     *n_cells = cells; *k = cols < 0 ? 0 : cols; *n_clusters = (int32_t)max_cluster + 1;
     return SOUP_OK;
 }
