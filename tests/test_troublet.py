@@ -332,3 +332,38 @@ def test_troublet_writer_many_blocks(tmp_path):
         assert tok[:3] == [names[i], status[st], want_assign], i
         want = [out[f][i] for f in ("singlet_posterior", "doublet_posterior", "log_prob_singleton", "log_prob_doublet")] + list(out["cluster_logprobs"][i])
         assert tok[3:] == [_rust_f64(x) for x in want], i
+
+
+def test_clusters_loader_many_rows_and_earliest_error(tmp_path):
+    """soup_clusters_load parses rows in parallel blocks: values must equal Python's float() of every token (both correctly rounded),
+    whatever the spelling, and with several bad lines the EARLIEST one is reported, as a sequential reader would hit it."""
+    n, k = 3000, 6
+    rng = np.random.default_rng(8)
+    vals = -rng.random((n, k)) * 10.0 ** rng.integers(-12, 9, (n, k))
+    spell = [lambda v: repr(float(v)), lambda v: f"{v:.17e}", lambda v: f"{v:.6f}", lambda v: "+" + repr(float(abs(v))), lambda v: f"{v:.3E}"]
+    rows, want = [], np.empty((n, k))
+    for i in range(n):
+        toks = []
+        for c in range(k):
+            t = spell[int(rng.integers(0, len(spell)))](vals[i, c])
+            toks.append(t)
+            want[i, c] = float(t)
+        rows.append(f"BC{i}-1\t{i % 5}\t" + "\t".join(toks))
+    rows[7] = "BC7-1\t+4\tinf\t-inf\tnan\t-0\t1e-400\t1e400"          # parse::<usize>() takes '+'; overflow / underflow go to inf / 0
+    want[7] = [np.inf, -np.inf, np.nan, -0.0, 0.0, np.inf]
+    p = tmp_path / "c.tsv"
+    p.write_text("\n".join(rows) + "\n")
+    names, losses, n_clusters = sp.load_clusters(str(p))
+    assert names == [f"BC{i}-1" for i in range(n)] and n_clusters == 5 and losses.shape == (n, k)
+    assert np.array_equal(losses, want, equal_nan=True) and np.signbit(losses[7, 3])
+    bad = list(rows)
+    bad[2500] = bad[2500].replace("\t", "\tx", 2)                    # cluster column "x..."
+    bad[900] = bad[900] + "\t-1.0"                                   # one column too many
+    bad[1700] = "lonely-barcode"
+    p.write_text("\n".join(bad) + "\n")
+    with pytest.raises(sp.SoupError) as e:
+        sp.load_clusters(str(p))
+    assert "line 901" in str(e.value), str(e.value)
+    p.write_text("")                                                 # empty file: no cells, no columns
+    names, losses, n_clusters = sp.load_clusters(str(p))
+    assert names == [] and losses.shape[0] == 0
