@@ -102,7 +102,7 @@ uint64_t parse_num(const std::string& s, const char* what, uint64_t maxv) {
 }
 
 struct Stopwatch {
-    bool on = getenv("SOUP_DEBUG_ITERS") != nullptr;
+    bool on = getenv("SOUP_DEBUG_ITERS") != nullptr || getenv("SOUP_DEBUG_CLI") != nullptr;   // SOUP_DEBUG_CLI: stage times only, no device syncs
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     void lap(const char* what) {
         auto t1 = std::chrono::steady_clock::now();
