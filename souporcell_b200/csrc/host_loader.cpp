@@ -279,8 +279,14 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
     if (!alt_path || !ref_path || !out) { set_thread_error("soup_mtx_load: bad argument"); return SOUP_ERR_INVALID; }
     *out = nullptr;
     Mapped A, R;
-    if (!A.open(alt_path)) { set_thread_error("cannot open alt mtx file"); return SOUP_ERR_IO; }   // S:602
-    if (!R.open(ref_path)) { set_thread_error("cannot open ref mtx file"); return SOUP_ERR_IO; }   // S:605
+    {   // both at once: a ".gz" input is inflated while it is opened
+        bool ok_a = false;
+        std::thread ta([&] { ok_a = A.open(alt_path); });
+        const bool ok_r = R.open(ref_path);
+        ta.join();
+        if (!ok_a) { set_thread_error("cannot open alt mtx file"); return SOUP_ERR_IO; }   // S:602
+        if (!ok_r) { set_thread_error("cannot open ref mtx file"); return SOUP_ERR_IO; }   // S:605
+    }
     unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
     if (const char* e = getenv("SOUP_LOADER_THREADS")) nthreads = (unsigned)std::min(256, std::max(1, atoi(e)));   // tests / tuning
     LoadTimer lt;
