@@ -185,6 +185,12 @@ def test_cli_contract_without_gpu(tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run(base, capture_output=True, text=True)
         assert r.returncode != 0 and r.stdout == "" and "total loci used 3" in r.stderr and "no CPU fallback" in r.stderr
+        # the argv souporcell_pipeline.py:526-532 builds, in its order (values are strings there, `-s true`, `-m khm` lower-cased)
+        pipeline = [exe, "-k", "2", "-a", alt, "-r", ref, "--restarts", "100", "-b", str(bc), "--min_ref", "2", "--min_alt", "2",
+                    "--threads", "8", "-s", "true", "-m", "khm"]
+        r = subprocess.run(pipeline, capture_output=True, text=True)
+        assert r.returncode != 0 and r.stdout == "" and "total loci used 3" in r.stderr and "no CPU fallback" in r.stderr
+        assert "wasn't expected" not in r.stderr and "required arguments" not in r.stderr
 
 
 def write_vcf(path, n_records, samples, rng, gz=False):
