@@ -154,11 +154,25 @@ struct Chunk { size_t a_begin, r_begin; uint64_t first_line, n_lines; };
 
 struct ParseError { std::atomic<int> code{0}; char msg[256]; void set(int c, const char* m) { int z = 0; if (code.compare_exchange_strong(z, c)) { strncpy(msg, m, sizeof(msg) - 1); msg[sizeof(msg) - 1] = 0; } } };
 
-// per-thread partial tallies of S:629-632 (wrapping u32 sums commute, so partials add up to the serial result)
+// locus tallies of S:629-632, shared by the parse workers: relaxed atomic adds (wrapping u32 sums commute, so the totals equal
+// the sequential ones).  One set for the whole matrix — the common-variants VCFs the pipeline feeds vartrix have tens of millions of
+// loci, so a copy per thread is not an option.
 struct Tally {
-    std::vector<uint32_t> cells_ref, cells_alt, umis_ref, umis_alt;
-    std::vector<uint8_t> seen;
-    void init(uint64_t n) { cells_ref.assign(n, 0); cells_alt.assign(n, 0); umis_ref.assign(n, 0); umis_alt.assign(n, 0); seen.assign(n, 0); }
+    std::unique_ptr<std::atomic<uint32_t>[]> cells_ref, cells_alt, umis_ref, umis_alt;
+    std::unique_ptr<std::atomic<uint8_t>[]> seen;
+    void init(uint64_t n, unsigned nthreads) {
+        cells_ref.reset(new std::atomic<uint32_t>[n + 1]); cells_alt.reset(new std::atomic<uint32_t>[n + 1]);
+        umis_ref.reset(new std::atomic<uint32_t>[n + 1]); umis_alt.reset(new std::atomic<uint32_t>[n + 1]);
+        seen.reset(new std::atomic<uint8_t>[n + 1]);
+        const uint64_t span = 1 << 16;
+        parallel_for(nthreads, (size_t)((n + span - 1) / span), [&](size_t b) {
+            for (uint64_t l = b * span; l < std::min<uint64_t>(n, (b + 1) * span); ++l) {
+                cells_ref[l].store(0, std::memory_order_relaxed); cells_alt[l].store(0, std::memory_order_relaxed);
+                umis_ref[l].store(0, std::memory_order_relaxed); umis_alt[l].store(0, std::memory_order_relaxed);
+                seen[l].store(0, std::memory_order_relaxed);
+            }
+        });
+    }
 };
 
 // ---- one line of each file.  The fast forms cover what vartrix writes ("l c v\n": 1-9 digit fields, single blanks or tabs,
@@ -241,9 +255,9 @@ void parse_chunk(const Mapped& A, const Mapped& R, const Chunk& ch, uint64_t tot
         cell[o] = (uint32_t)(c - 1);
         alt[o] = (uint32_t)av;
         ref[o] = (uint32_t)rv;
-        t.seen[li] = 1;
-        if (rv > 0) { t.cells_ref[li] += 1; t.umis_ref[li] += (uint32_t)rv; }
-        if (av > 0) { t.cells_alt[li] += 1; t.umis_alt[li] += (uint32_t)av; }
+        if (!t.seen[li].load(std::memory_order_relaxed)) t.seen[li].store(1, std::memory_order_relaxed);
+        if (rv > 0) { t.cells_ref[li].fetch_add(1, std::memory_order_relaxed); t.umis_ref[li].fetch_add((uint32_t)rv, std::memory_order_relaxed); }
+        if (av > 0) { t.cells_alt[li].fetch_add(1, std::memory_order_relaxed); t.umis_alt[li].fetch_add((uint32_t)av, std::memory_order_relaxed); }
     }
 }
 
@@ -275,7 +289,7 @@ extern "C" void soup_mtx_free(soup_mtx* m) {
 }
 
 extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uint32_t min_alt, uint32_t min_ref,
-                                 uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags, soup_mtx** out) {
+                                 uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags, soup_mtx** out) try {
     if (!alt_path || !ref_path || !out) { set_thread_error("soup_mtx_load: bad argument"); return SOUP_ERR_INVALID; }
     *out = nullptr;
     Mapped A, R;
@@ -322,7 +336,8 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
         c_ref(new uint32_t[n_lines + 1]);
     const size_t nchunks = std::max<size_t>(1, std::min<size_t>(nthreads * 4, n_lines / 65536 + 1));
     const unsigned nworkers = (unsigned)std::min<size_t>(nthreads, nchunks);
-    std::vector<Tally> tally(nworkers);
+    Tally tally;
+    tally.init(total_loci, nthreads);
     if (n_lines) {
         std::vector<Chunk> chunks(nchunks);
         parallel_for(nthreads, nchunks, [&](size_t i) {
@@ -331,14 +346,10 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
         });
         ParseError err;
         std::atomic<size_t> next{0};
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nworkers; ++t)
-            pool.emplace_back([&, t] {
-                tally[t].init(total_loci);
-                for (size_t i; (i = next.fetch_add(1)) < nchunks && !err.code.load();)
-                    parse_chunk(A, R, chunks[i], total_loci, total_cells, c_locus.get(), c_cell.get(), c_alt.get(), c_ref.get(), tally[t], &err);
-            });
-        for (auto& th : pool) th.join();
+        parallel_for(nworkers, nworkers, [&](size_t) {   // the workers share the chunk queue
+            for (size_t i; (i = next.fetch_add(1)) < nchunks && !err.code.load();)
+                parse_chunk(A, R, chunks[i], total_loci, total_cells, c_locus.get(), c_cell.get(), c_alt.get(), c_ref.get(), tally, &err);
+        });
         if (err.code.load()) { set_thread_error("%s", err.msg); return err.code.load(); }
     }
     lt.lap("parse");
@@ -350,15 +361,14 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
         const size_t span = 1 << 14, nspan = (size_t)((total_loci + span - 1) / span);
         parallel_for(nthreads, nspan, [&](size_t b) {
             for (uint64_t l = b * span; l < std::min<uint64_t>(total_loci, (b + 1) * span); ++l) {
-                uint32_t cr = 0, ca = 0, ur = 0, ua = 0;
-                uint8_t seen = 0;
-                if (n_lines)
-                    for (const Tally& t : tally) { cr += t.cells_ref[l]; ca += t.cells_alt[l]; ur += t.umis_ref[l]; ua += t.umis_alt[l]; seen |= t.seen[l]; }
+                const uint32_t cr = tally.cells_ref[l].load(std::memory_order_relaxed), ca = tally.cells_alt[l].load(std::memory_order_relaxed);
+                const uint32_t ur = tally.umis_ref[l].load(std::memory_order_relaxed), ua = tally.umis_alt[l].load(std::memory_order_relaxed);
+                const bool seen = tally.seen[l].load(std::memory_order_relaxed) != 0;
                 keep[l] = raw || (seen && cr >= min_ref && ca >= min_alt && ur >= min_ref_umis && ua >= min_alt_umis);
             }
         });
     }
-    std::vector<Tally>().swap(tally);
+    tally = Tally();
     std::vector<uint32_t> remap(total_loci, UINT32_MAX);
     std::vector<uint64_t> index_to_locus;
     for (uint64_t l = 0; l < total_loci; ++l)
@@ -468,6 +478,7 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
     *out = m;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_mtx_load")
 
 
 // ------------------------------------------------------------------ binary CSR cache
@@ -485,7 +496,7 @@ static_assert(sizeof(CacheHeader) == 64, "cache header layout");
 }  // namespace
 
 extern "C" int32_t soup_mtx_save(const soup_mtx* m, const char* path, uint32_t min_alt, uint32_t min_ref, uint32_t min_alt_umis,
-                                 uint32_t min_ref_umis, uint32_t flags) {
+                                 uint32_t min_ref_umis, uint32_t flags) try {
     if (!m || !path) { set_thread_error("soup_mtx_save: bad argument"); return SOUP_ERR_INVALID; }
     const std::string tmp = std::string(path) + ".tmp";
     FILE* f = fopen(tmp.c_str(), "wb");
@@ -502,9 +513,10 @@ extern "C" int32_t soup_mtx_save(const soup_mtx* m, const char* path, uint32_t m
     if (!ok) { remove(tmp.c_str()); set_thread_error("soup_mtx_save: write to %s failed", path); return SOUP_ERR_IO; }
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_mtx_save")
 
 extern "C" int32_t soup_mtx_load_cache(const char* path, uint32_t min_alt, uint32_t min_ref, uint32_t min_alt_umis, uint32_t min_ref_umis,
-                                       uint32_t flags, soup_mtx** out) {
+                                       uint32_t flags, soup_mtx** out) try {
     if (!path || !out) { set_thread_error("soup_mtx_load_cache: bad argument"); return SOUP_ERR_INVALID; }
     *out = nullptr;
     Mapped F;
@@ -543,3 +555,4 @@ extern "C" int32_t soup_mtx_load_cache(const char* path, uint32_t min_alt, uint3
     *out = m;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_mtx_load_cache")

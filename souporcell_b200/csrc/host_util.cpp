@@ -144,12 +144,8 @@ int32_t write_rows(FILE* out, uint64_t n, size_t typical_row, Max row_max, Emit 
                 buf.len = len;
             }
         };
-        if (nb == 1 || nthreads == 1) work();
-        else {
-            std::vector<std::thread> pool;
-            for (unsigned t = 0; t < std::min<uint64_t>(nthreads, nb); ++t) pool.emplace_back(work);
-            for (auto& th : pool) th.join();
-        }
+        const size_t workers = (size_t)std::min<uint64_t>(nthreads, nb);
+        parallel_for((unsigned)workers, workers, [&](size_t) { work(); });
         for (uint64_t j = 0; j < nb; ++j)
             if (fwrite(text[j].p.get(), 1, text[j].len, out) != text[j].len) { set_thread_error("write failed"); return SOUP_ERR_IO; }
     }
@@ -238,7 +234,7 @@ static std::string format_f64(double v) {   // Rust `{}` for f64
     return std::string(b, format_float_into(b, v));
 }
 
-int32_t soup_clusters_load(const char* path, char** barcode_blob, double** losses, uint64_t* n_cells, int32_t* k, int32_t* n_clusters) {
+int32_t soup_clusters_load(const char* path, char** barcode_blob, double** losses, uint64_t* n_cells, int32_t* k, int32_t* n_clusters) try {
     if (!path || !barcode_blob || !losses || !n_cells || !k || !n_clusters) { set_thread_error("soup_clusters_load: bad argument"); return SOUP_ERR_INVALID; }
     // the file is mapped (or, for something that is not a regular file, read) — a 100k x 64 clusters file is 70 MB
     struct Text {
@@ -370,8 +366,9 @@ int32_t soup_clusters_load(const char* path, char** barcode_blob, double** losse
     *n_cells = cells; *k = cols < 0 ? 0 : cols; *n_clusters = (int32_t)max_cluster + 1;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_clusters_load")
 
-int32_t soup_troublet_write(void* out_file, const char* barcode_blob, uint64_t n_cells, int32_t k, const soup_troublet_result* r) {
+int32_t soup_troublet_write(void* out_file, const char* barcode_blob, uint64_t n_cells, int32_t k, const soup_troublet_result* r) try {
     FILE* f = (FILE*)out_file;
     if (!f || !barcode_blob || !r || k <= 0) { set_thread_error("soup_troublet_write: bad argument"); return SOUP_ERR_INVALID; }
     static const char* NAME[4] = {"singlet", "unassigned", "doublet", "unassigned"};
@@ -411,18 +408,20 @@ int32_t soup_troublet_write(void* out_file, const char* barcode_blob, uint64_t n
     if (rc != SOUP_OK) return rc;
     return ferror(f) ? SOUP_ERR_IO : SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_troublet_write")
 
-int32_t soup_format_f32(float v, int32_t width8, char* buf, int32_t buflen) {
+int32_t soup_format_f32(float v, int32_t width8, char* buf, int32_t buflen) try {
     std::string s = width8 ? format_f32_w8(v) : format_f32(v);
     if (!buf || (int32_t)s.size() + 1 > buflen) { set_thread_error("soup_format_f32: buffer too small"); return SOUP_ERR_INVALID; }
     memcpy(buf, s.c_str(), s.size() + 1);
     return (int32_t)s.size();
 }
+SOUP_CATCH_RETURN("soup_format_f32")
 
 float soup_ln_binomial_f32(uint32_t n, uint32_t k) { return ln_binomial_f32(n, k); }
 
 // load_barcodes S:707-718 / reader S:500-511
-int32_t soup_barcodes_load(const char* path, char** blob, uint64_t* n_barcodes) {
+int32_t soup_barcodes_load(const char* path, char** blob, uint64_t* n_barcodes) try {
     if (!path || !blob || !n_barcodes) { set_thread_error("soup_barcodes_load: bad argument"); return SOUP_ERR_INVALID; }
     std::string content;
     size_t plen = strlen(path);
@@ -459,11 +458,12 @@ int32_t soup_barcodes_load(const char* path, char** blob, uint64_t* n_barcodes) 
     *n_barcodes = n;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_barcodes_load")
 
 // init_cluster_centers_known_genotypes S:514-542: theta[k][l] = 0.5, then for every VCF record whose index is a used
 // locus and every named sample: (min(hap0,1) + min(hap1,1)) / 2 clamped to [0.01, 0.99]; a GT starting with '.' keeps 0.5.
 int32_t soup_known_genotypes_load(const char* vcf_path, const char* sample_names, int32_t n_samples, int32_t k,
-                                  const uint64_t* index_to_locus, uint64_t n_loci, float* theta) {
+                                  const uint64_t* index_to_locus, uint64_t n_loci, float* theta) try {
     if (!vcf_path || !theta || k <= 0 || n_samples < 0 || (n_samples && !sample_names) || (n_loci && !index_to_locus)) {
         set_thread_error("soup_known_genotypes_load: bad argument");
         return SOUP_ERR_INVALID;
@@ -554,10 +554,11 @@ int32_t soup_known_genotypes_load(const char* vcf_path, const char* sample_names
     }
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_known_genotypes_load")
 
 // S:133-147: zip(barcodes, best_log_probabilities), FIRST max (strict >), Rust {} floats.
 int32_t soup_write_clusters(void* out_file, const char* barcode_blob, uint64_t n_barcodes, const float* lp,
-                            uint64_t n_cells, int32_t k) {
+                            uint64_t n_cells, int32_t k) try {
     FILE* out = (FILE*)out_file;
     if (!out || (!barcode_blob && n_barcodes) || (!lp && n_cells) || k <= 0) { set_thread_error("soup_write_clusters: bad argument"); return SOUP_ERR_INVALID; }
     const uint64_t n = std::min(n_barcodes, n_cells);   // zip() stops at the shorter (S:133)
@@ -589,15 +590,17 @@ int32_t soup_write_clusters(void* out_file, const char* barcode_blob, uint64_t n
             return w;
         });
 }
+SOUP_CATCH_RETURN("soup_write_clusters")
 
 // S:150-187
 int32_t soup_bad_cluster_detection(int32_t run, int32_t k, const float* best_lp, uint64_t n_cells, int32_t* out_idx,
-                                   void* log_file) {
+                                   void* log_file) try {
     if (k <= 0 || run < 0 || !out_idx) { set_thread_error("soup_bad_cluster_detection: bad argument"); return SOUP_ERR_INVALID; }
     if (k < 16 || run == 0) return 0;
     std::vector<uint64_t> counts((size_t)k, 0);
     soup::count_cluster_cells(best_lp, n_cells, k, counts.data());
     return soup::bad_clusters_from_counts(run, k, counts.data(), out_idx, log_file);
 }
+SOUP_CATCH_RETURN("soup_bad_cluster_detection")
 
 }  // extern "C"

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <thread>
 
+#include "host_parallel.hpp"
 #include "soup_common.hpp"
 
 using namespace soup;
@@ -50,7 +51,7 @@ void log_solves(FILE* log, const soup_main_params* p, int spt, const std::vector
 // winner (higher loss; ties -> lowest solve index, S:110/S:120), fetch its buffers from the owning rank.
 extern "C" int32_t soup_exchange_best(int32_t rank, int32_t world, soup_allgather_fn allgather, soup_bcast_fn bcast, void* user,
                                       float* loss, int32_t* solve, int32_t* has_best, float* log_probs, uint64_t n_log_probs,
-                                      float* theta, uint64_t n_theta, int32_t* winner_rank) {
+                                      float* theta, uint64_t n_theta, int32_t* winner_rank) try {
     if (world <= 1) { if (winner_rank) *winner_rank = 0; return SOUP_OK; }
     if (!allgather || !bcast || !loss || !solve || !has_best || rank < 0 || rank >= world) { set_thread_error("soup_exchange_best: bad argument"); return SOUP_ERR_INVALID; }
     Candidate mine{*loss, *solve, *has_best, 0, 0};
@@ -69,8 +70,9 @@ extern "C" int32_t soup_exchange_best(int32_t rank, int32_t world, soup_allgathe
     if (e != SOUP_OK) { set_thread_error("soup_exchange_best: bcast callback failed (%d)", e); return e; }
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_exchange_best")
 
-extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_main_params* p, soup_main_result* r, void* log_file) {
+extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_main_params* p, soup_main_result* r, void* log_file) try {
     if (!ctxs || n_ctx <= 0 || !ctxs[0]) { set_thread_error("soup_main: need at least one context"); return SOUP_ERR_INVALID; }
     soup_ctx* ctx0 = ctxs[0];
     if (!p || !r || !r->best_log_probs) { set_thread_error("soup_main: null argument"); return SOUP_ERR_INVALID; }
@@ -240,3 +242,4 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
     if (r->best_theta && have_best) memcpy(r->best_theta, best_theta.data(), best_theta.size() * sizeof(float));
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_main")
