@@ -50,3 +50,8 @@ inline unsigned host_threads() { return std::max(1u, std::min(64u, std::thread::
     catch (const std::bad_alloc&) { soup::set_thread_error("%s: out of memory", fn_name_); return SOUP_ERR_NOMEM; }                   \
     catch (const std::exception& e_) { soup::set_thread_error("%s: %s", fn_name_, e_.what()); return SOUP_ERR_INVALID; }              \
     catch (...) { soup::set_thread_error("%s: unknown C++ exception", fn_name_); return SOUP_ERR_INVALID; }
+// The same for entry points that take a `soup_ctx* ctx`: the message goes where soup_last_error(ctx) reads it.
+#define SOUP_CATCH_RETURN_CTX(fn_name_)                                                                                                \
+    catch (const std::bad_alloc&) { return ctx ? ctx->fail(SOUP_ERR_NOMEM, "%s: out of memory", fn_name_) : SOUP_ERR_NOMEM; }          \
+    catch (const std::exception& e_) { return ctx ? ctx->fail(SOUP_ERR_INVALID, "%s: %s", fn_name_, e_.what()) : SOUP_ERR_INVALID; }   \
+    catch (...) { return ctx ? ctx->fail(SOUP_ERR_INVALID, "%s: unknown C++ exception", fn_name_) : SOUP_ERR_INVALID; }

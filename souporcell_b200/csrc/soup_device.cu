@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 
 #include "soup_kernels.cuh"
+#include "host_parallel.hpp"
 
 using namespace soup;
 
@@ -159,7 +160,7 @@ static void free_matrix(soup_ctx* ctx) {
 
 extern "C" const char* soup_last_error(const soup_ctx* ctx) { return ctx ? ctx->err.c_str() : thread_error(); }
 
-extern "C" int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx** out) {
+extern "C" int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx** out) try {
     if (!out) { set_thread_error("soup_ctx_create: bad argument"); return SOUP_ERR_INVALID; }
     *out = nullptr;
     int n = 0;
@@ -236,6 +237,7 @@ extern "C" int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx**
     *out = ctx;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN("soup_ctx_create")
 
 extern "C" void soup_ctx_destroy(soup_ctx* ctx) {
     if (!ctx) return;
@@ -281,7 +283,7 @@ struct PhaseTimer {
 };
 
 extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loci, uint64_t nnz_in, const uint64_t* row_ptr,
-                                 const uint32_t* locus, const uint32_t* alt, const uint32_t* ref) {
+                                 const uint32_t* locus, const uint32_t* alt, const uint32_t* ref) try {
     if (!ctx) return SOUP_ERR_INVALID;
     PhaseTimer pt;
     if (!row_ptr || (nnz_in && (!locus || !alt || !ref))) return ctx->fail(SOUP_ERR_INVALID, "soup_load_csr: null pointer");
@@ -451,6 +453,7 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     ctx->loaded = true;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN_CTX("soup_load_csr")
 
 extern "C" int32_t soup_get_dims(soup_ctx* ctx, uint64_t* n_cells, uint64_t* n_loci, uint64_t* nnz) {
     if (!ctx) return SOUP_ERR_INVALID;
@@ -460,7 +463,7 @@ extern "C" int32_t soup_get_dims(soup_ctx* ctx, uint64_t* n_cells, uint64_t* n_l
     if (nnz) *nnz = ctx->nnz;
     return SOUP_OK;
 }
-extern "C" int32_t soup_get_csc(soup_ctx* ctx, uint64_t* col_ptr, uint32_t* cell, uint32_t* alt, uint32_t* ref) {
+extern "C" int32_t soup_get_csc(soup_ctx* ctx, uint64_t* col_ptr, uint32_t* cell, uint32_t* alt, uint32_t* ref) try {
     if (!ctx || !ctx->loaded) return ctx ? ctx->fail(SOUP_ERR_INVALID, "no matrix loaded") : SOUP_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (col_ptr) CK(cudaMemcpy(col_ptr, ctx->d_col_ptr, (ctx->L + 1) * 8, cudaMemcpyDeviceToHost));
@@ -479,13 +482,15 @@ extern "C" int32_t soup_get_csc(soup_ctx* ctx, uint64_t* col_ptr, uint32_t* cell
     }
     return SOUP_OK;
 }
-extern "C" int32_t soup_get_cell_totals(soup_ctx* ctx, float* total_alleles) {
+SOUP_CATCH_RETURN_CTX("soup_get_csc")
+extern "C" int32_t soup_get_cell_totals(soup_ctx* ctx, float* total_alleles) try {
     if (!ctx || !ctx->loaded || !total_alleles) return ctx ? ctx->fail(SOUP_ERR_INVALID, "no matrix loaded") : SOUP_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (ctx->N) CK(cudaMemcpy(total_alleles, ctx->d_total_alleles, ctx->N * 4, cudaMemcpyDeviceToHost));
     return SOUP_OK;
 }
-extern "C" int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc) {
+SOUP_CATCH_RETURN_CTX("soup_get_cell_totals")
+extern "C" int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc) try {
     if (!ctx || !ctx->loaded || !lbc) return ctx ? ctx->fail(SOUP_ERR_INVALID, "no matrix loaded") : SOUP_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     std::vector<float4> h(ctx->nnz);
@@ -493,8 +498,9 @@ extern "C" int32_t soup_get_csr_lbc(soup_ctx* ctx, float* lbc) {
     for (uint64_t i = 0; i < ctx->nnz; ++i) lbc[i] = h[i].z;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN_CTX("soup_get_csr_lbc")
 
-extern "C" int32_t soup_cluster_allele_counts(soup_ctx* ctx, const int32_t* cell_cluster, int32_t k, uint64_t* counts) {
+extern "C" int32_t soup_cluster_allele_counts(soup_ctx* ctx, const int32_t* cell_cluster, int32_t k, uint64_t* counts) try {
     if (!ctx) return SOUP_ERR_INVALID;
     if (!ctx->loaded) return ctx->fail(SOUP_ERR_INVALID, "no matrix loaded (call soup_load_csr first)");
     if (!cell_cluster || !counts || k <= 0) return ctx->fail(SOUP_ERR_INVALID, "soup_cluster_allele_counts: bad argument");
@@ -517,6 +523,7 @@ extern "C" int32_t soup_cluster_allele_counts(soup_ctx* ctx, const int32_t* cell
     if (e != cudaSuccess) { cudaGetLastError(); return ctx->fail(e == cudaErrorMemoryAllocation ? SOUP_ERR_NOMEM : SOUP_ERR_CUDA, "soup_cluster_allele_counts: %s", cudaGetErrorString(e)); }
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN_CTX("soup_cluster_allele_counts")
 
 // ------------------------------------------------------------------ workspace
 // Column groups of one kernel: `n_main` groups of 32*VM columns and, if the column count is not a
@@ -727,7 +734,7 @@ static void enqueue_iteration(IterLaunch& it) {
 }
 
 // ------------------------------------------------------------------ soup_solve
-extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_solve_result* r) {
+extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_solve_result* r) try {
     if (!ctx) return SOUP_ERR_INVALID;
     if (!p || !r) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: null argument");
     if (!ctx->loaded) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: no matrix loaded (call soup_load_csr first)");
@@ -1108,8 +1115,9 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     ctx->stats.h2d_bytes = h2d; ctx->stats.d2h_bytes = d2h;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN_CTX("soup_solve")
 
-extern "C" int32_t soup_get_trace(soup_ctx* ctx, int32_t solve, soup_iter_record* out, int32_t cap, int32_t* n) {
+extern "C" int32_t soup_get_trace(soup_ctx* ctx, int32_t solve, soup_iter_record* out, int32_t cap, int32_t* n) try {
     if (!ctx || !n) return SOUP_ERR_INVALID;
     for (size_t i = 0; i < ctx->h_trace_solve.size(); ++i)
         if (ctx->h_trace_solve[i] == solve) {
@@ -1123,6 +1131,7 @@ extern "C" int32_t soup_get_trace(soup_ctx* ctx, int32_t solve, soup_iter_record
         }
     return ctx->fail(SOUP_ERR_INVALID, "soup_get_trace: solve %d was not run by the last soup_solve (or keep_trace was 0)", solve);
 }
+SOUP_CATCH_RETURN_CTX("soup_get_trace")
 
 extern "C" int32_t soup_get_stats(soup_ctx* ctx, soup_stats* out) {
     if (!ctx || !out) return SOUP_ERR_INVALID;
@@ -1157,7 +1166,7 @@ static int32_t hook_setup(soup_ctx* ctx, int k, int n_slots, int lanes) {
 
 extern "C" int32_t soup_estep(soup_ctx* ctx, int32_t k, int32_t method, int32_t n_slots, int32_t lanes, const float* theta,
                               const int32_t* temp_step, float* log_probs, float* weights, float* lse, float* loss,
-                              int32_t* cells_per_cluster) {
+                              int32_t* cells_per_cluster) try {
     if (!ctx) return SOUP_ERR_INVALID;
     if (!theta || !temp_step) return ctx->fail(SOUP_ERR_INVALID, "soup_estep: null argument");
     CK(cudaSetDevice(ctx->device));
@@ -1221,9 +1230,10 @@ extern "C" int32_t soup_estep(soup_ctx* ctx, int32_t k, int32_t method, int32_t 
     ctx->stats.slots = n_slots; ctx->stats.lanes = w.ep.VM; ctx->stats.groups = w.ep.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN_CTX("soup_estep")
 
 extern "C" int32_t soup_mstep(soup_ctx* ctx, int32_t k, int32_t n_slots, int32_t lanes, const float* weights, const float* theta_in,
-                              const int32_t* locked, int32_t n_locked, float* theta_out) {
+                              const int32_t* locked, int32_t n_locked, float* theta_out) try {
     if (!ctx) return SOUP_ERR_INVALID;
     if (!weights || !theta_in || !theta_out || n_locked < 0 || (n_locked && !locked)) return ctx->fail(SOUP_ERR_INVALID, "soup_mstep: null argument");
     CK(cudaSetDevice(ctx->device));
@@ -1268,8 +1278,9 @@ extern "C" int32_t soup_mstep(soup_ctx* ctx, int32_t k, int32_t n_slots, int32_t
     ctx->stats.slots = n_slots; ctx->stats.lanes = w.ep.VM; ctx->stats.groups = w.ep.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN_CTX("soup_mstep")
 
-extern "C" int32_t soup_device_math(soup_ctx* ctx, int32_t op, const float* in, float* out, uint64_t n) {
+extern "C" int32_t soup_device_math(soup_ctx* ctx, int32_t op, const float* in, float* out, uint64_t n) try {
     if (!ctx) return SOUP_ERR_INVALID;
     if (!in || !out || (op != 0 && op != 1)) return ctx->fail(SOUP_ERR_INVALID, "soup_device_math: bad argument");
     CK(cudaSetDevice(ctx->device));
@@ -1285,13 +1296,14 @@ extern "C" int32_t soup_device_math(soup_ctx* ctx, int32_t op, const float* in, 
     if (e != cudaSuccess) return ctx->fail(SOUP_ERR_CUDA, "soup_device_math: %s", cudaGetErrorString(e));
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN_CTX("soup_device_math")
 
 // ------------------------------------------------------------------ troublet: call_doublets T:32-244 on the GPU
 #include "troublet_kernels.cuh"
 
 extern "C" int32_t soup_troublet(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loci, uint64_t nnz, const uint64_t* row_ptr, const uint32_t* locus,
                                  const uint32_t* alt, const uint32_t* ref, const double* losses, int32_t k, int32_t n_clusters,
-                                 const soup_troublet_params* p, soup_troublet_result* r, const char* barcode_blob, void* log_file) {
+                                 const soup_troublet_params* p, soup_troublet_result* r, const char* barcode_blob, void* log_file) try {
     using namespace troublet_dev;
     if (!ctx) return SOUP_ERR_INVALID;
     if (!row_ptr || !losses || !p || !r || k <= 0 || (nnz && (!locus || !alt || !ref))) return ctx->fail(SOUP_ERR_INVALID, "soup_troublet: bad argument");
@@ -1457,3 +1469,4 @@ extern "C" int32_t soup_troublet(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
 #undef CKT
     return SOUP_OK;
 }
+SOUP_CATCH_RETURN_CTX("soup_troublet")
