@@ -458,3 +458,41 @@ def test_write_clusters_many_blocks_matches_oracle_formatting(tmp_path):
             if key not in fmt:
                 fmt[key] = orc.format_f32(v)
             assert tok[2 + c] == fmt[key], (i, c, v)
+
+
+def test_sass_exactness_guards():
+    """Static check of the built sm_100a code (cuobjdump runs without a GPU).  Bit-exactness against the reference's f32 arithmetic rests on
+    the compiler never fusing a multiply into an add (Rust never contracts; ptxas was seen to turn a packed multiply feeding a packed add
+    into FFMA2 even under -fmad=false): the E kernels — every (cell, cluster) sum is `acc + (lbc + a*x) + r*y` — must hold no FFMA at all,
+    no kernel may hold an FFMA2, and the packed adds (FADD2) the design relies on must be there.  (FFMA inside the M / post kernels is the
+    IEEE division and double -> float code, which is exact by construction.)  The cubin must be sm_100a."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    sass = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True, check=True).stdout
+    assert "arch = sm_100a" in sass
+    per = {}
+    cur = None
+    for ln in sass.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            per[cur] = {"FFMA": 0, "FFMA2": 0, "FADD2": 0, "FMUL": 0}
+        elif cur:
+            for op in ("FFMA2", "FADD2"):
+                if re.search(r"\b" + op + r"\b", ln):
+                    per[cur][op] += 1
+            if re.search(r"\bFFMA\b", ln):
+                per[cur]["FFMA"] += 1
+            if re.search(r"\bFMUL\b", ln):
+                per[cur]["FMUL"] += 1
+    estep = {k: v for k, v in per.items() if "estep_kernel" in k}
+    mstep = {k: v for k, v in per.items() if "mstep_kernel" in k}
+    assert len(estep) == 5 and len(mstep) == 5, (sorted(estep), sorted(mstep))      # V = 1, 2, 4, 8, 16 columns per lane
+    for k, v in estep.items():
+        assert v["FFMA"] == 0 and v["FMUL"] > 0, (k, v)
+        assert v["FADD2"] > 0 or "ILi1E" in k, (k, v)                                # one column per lane has nothing to pair
+    for k, v in per.items():
+        assert v["FFMA2"] == 0, (k, v)
+    assert all(v["FADD2"] > 0 for v in mstep.values())
