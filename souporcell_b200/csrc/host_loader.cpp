@@ -301,7 +301,7 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
         if (!ok_a) { set_thread_error("cannot open alt mtx file"); return SOUP_ERR_IO; }   // S:602
         if (!ok_r) { set_thread_error("cannot open ref mtx file"); return SOUP_ERR_IO; }   // S:605
     }
-    unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
+    unsigned nthreads = host_threads();   // at most 64
     if (const char* e = getenv("SOUP_LOADER_THREADS")) nthreads = (unsigned)std::min(256, std::max(1, atoi(e)));   // tests / tuning
     LoadTimer lt;
 
