@@ -24,6 +24,9 @@ namespace soup {
 
 // entries (row gathers) in flight per warp in the E walk, by columns per lane: a narrow body runs when few solves are
 // still live, and then the walk is a latency chain per warp, so narrow bodies go deeper
+#ifndef SOUP_E_FASTBATCH
+#define SOUP_E_FASTBATCH 0   // experiment: all-simple batches of the E walk take a branch-free body (see e_batch)
+#endif
 #ifndef SOUP_E_U1
 #define SOUP_E_U1 16
 #endif
@@ -331,6 +334,28 @@ __device__ __forceinline__ void e_batch(FVec<V>& acc, const uint32_t (&cur)[U], 
     // the same registers.  The second row of a two-allele entry goes to the shared tile `tb` — early for the first such
     // entry of the batch, late (an exposed load) for the rare further ones.
     FVec<V> t[U], tb;
+#if SOUP_E_FASTBATCH
+    // Experiment (off): 85 % of the entries are simple words, so most batches hold nothing else.  One warp-uniform
+    // test per batch then buys a body without per-entry class branches (the BSSY / BSYNC / BRA triples are 21 % of the pass's
+    // instructions): U row gathers, then `acc += t` or `acc += t + t` — the same operations in the same order as below.
+    if (U > 1) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) any |= cur[u];
+        if (word_simple(any)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) ld_row<V>(t[u], row_at(la, cur[u] & CSR_ROW_MASK, row_bytes), hm);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool twice = (cur[u] & CSR_DOUBLE) != 0;
+#pragma unroll
+                for (int v = 0; v < V; ++v) t[u].v[v] = twice ? __fadd_rn(t[u].v[v], t[u].v[v]) : t[u].v[v];
+                vadd<V>(acc, t[u]);
+            }
+            return;
+        }
+    }
+#endif
     int owner = -1;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
