@@ -346,22 +346,23 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     ctx->N = n_cells; ctx->L = n_loci; ctx->nnz = nnz;
     // entry words (soup_kernels.cuh "entry words"): bit 31 = general; index bits as needed, the rest split between
     // the two count fields (<= 6 bits each)
-    auto make_packing = [](uint64_t n_index) {
+    auto make_packing = [](uint64_t n_index, uint32_t top) {   // count fields below bit `top`
         uint32_t ib = 1;
         while ((1ull << ib) < std::max<uint64_t>(n_index, 2)) ++ib;
         Packing pk;
-        pk.cbits = std::min<uint32_t>(6, (31 - ib) / 2);
+        pk.cbits = std::min<uint32_t>(6, (top - ib) / 2);
         pk.cmask = (1u << pk.cbits) - 1;
-        pk.sh_a = 31 - pk.cbits;
-        pk.sh_r = 31 - 2 * pk.cbits;
+        pk.sh_a = top - pk.cbits;
+        pk.sh_r = top - 2 * pk.cbits;
         pk.imask = (1u << pk.sh_r) - 1;
         pk.plane_rows = 0;
         pk.alt_bit = 1u << pk.sh_a;
         return pk;
     };
-    ctx->pk_csr = make_packing(n_loci);
+    // CSR words index the joint ln table (2 planes of max(L, 1) rows) and keep bit 30 for the "row counts twice" flag of simple words
+    ctx->pk_csr = make_packing(2 * std::max<uint64_t>(n_loci, 1), 30);
     ctx->pk_csr.plane_rows = (uint32_t)std::max<uint64_t>(n_loci, 1);   // = the row count ensure_workspace gives each ln-table plane
-    ctx->pk_csc = make_packing(n_cells);
+    ctx->pk_csc = make_packing(n_cells, 31);
     const size_t nz = std::max<uint64_t>(nnz, 1);
     const size_t nmax = std::max<uint64_t>(std::max(n_cells, n_loci), 1);
     CKL(B.col_ptr.ensure((n_loci + 1) * 8)); CKL(B.csr_idx.ensure(nz * 4)); CKL(B.csc_idx.ensure(nz * 4));
@@ -619,14 +620,14 @@ struct IterLaunch {
     bool queue_drained = false;   // the host has SEEN queue_head >= queue_len: no slot can get a pending solve any more, so refill launches stop
 };
 
-#define SOUP_DISPATCH(KERNEL, PLAN, ARGS)                                                       \
+#define SOUP_DISPATCH(KERNEL, THREADS, PLAN, ARGS)                                              \
     do {                                                                                        \
         switch ((PLAN).VM) {                                                                    \
-            case 16: KERNEL<16><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;             \
-            case 8: KERNEL<8><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;               \
-            case 4: KERNEL<4><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;               \
-            case 2: KERNEL<2><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;               \
-            default: KERNEL<1><<<grid, EM_THREADS, 0, ctx->stream>>>(ARGS); break;              \
+            case 16: KERNEL<16><<<grid, THREADS, 0, ctx->stream>>>(ARGS); break;                \
+            case 8: KERNEL<8><<<grid, THREADS, 0, ctx->stream>>>(ARGS); break;                  \
+            case 4: KERNEL<4><<<grid, THREADS, 0, ctx->stream>>>(ARGS); break;                  \
+            case 2: KERNEL<2><<<grid, THREADS, 0, ctx->stream>>>(ARGS); break;                  \
+            default: KERNEL<1><<<grid, THREADS, 0, ctx->stream>>>(ARGS); break;                 \
         }                                                                                       \
     } while (0)
 
@@ -637,7 +638,7 @@ static void launch_e(soup_ctx* ctx, float log_prior) {
     const EArgs a{ctx->d_csr_idx, ctx->d_csr_aux, ctx->d_row_ptr, ctx->d_cell_order, w.LA, w.LB, w.ELL, w.e_group_active, w.ctl,
                   ctx->pk_csr, (uint32_t)ctx->N, w.Cpad, bpg, (uint32_t)(w.forced_lanes != 0), log_prior};
     const dim3 grid(bpg * w.ep.n_groups);
-    SOUP_DISPATCH(estep_kernel, w.ep, a);
+    SOUP_DISPATCH(estep_kernel, EM_THREADS, w.ep, a);
 }
 static void launch_m(soup_ctx* ctx) {
     Workspace& w = ctx->ws;
@@ -662,7 +663,7 @@ static void launch_m(soup_ctx* ctx) {
         cudaEventRecord(ctx->ev_mjoin, ctx->side_long);
     }
     const dim3 grid(long_blocks + wide_chunks * w.mp.n_groups);
-    if (grid.x != 0) SOUP_DISPATCH(mstep_kernel, w.mp, a);
+    if (grid.x != 0) SOUP_DISPATCH(mstep_kernel, EM_THREADS, w.mp, a);
     if (coop) cudaStreamWaitEvent(ctx->stream, ctx->ev_mjoin, 0);
 }
 static void launch_post(soup_ctx* ctx, int method, bool counts) {

@@ -24,20 +24,17 @@ namespace soup {
 
 // entries (row gathers) in flight per warp in the E walk, by columns per lane: a narrow body runs when few solves are
 // still live, and then the walk is a latency chain per warp, so narrow bodies go deeper
-#ifndef SOUP_E_FASTBATCH
-#define SOUP_E_FASTBATCH 0   // experiment: all-simple batches of the E walk take a branch-free body (see e_batch)
-#endif
 #ifndef SOUP_E_U1
-#define SOUP_E_U1 16
+#define SOUP_E_U1 8
 #endif
 #ifndef SOUP_E_U2
 #define SOUP_E_U2 8
 #endif
 #ifndef SOUP_E_U4
-#define SOUP_E_U4 6
+#define SOUP_E_U4 8
 #endif
 #ifndef SOUP_E_U8
-#define SOUP_E_U8 3
+#define SOUP_E_U8 4
 #endif
 #ifndef SOUP_E_U16
 #define SOUP_E_U16 2
@@ -169,6 +166,11 @@ template <int V> __device__ __forceinline__ LaneCols<V> lane_setup(uint32_t col0
     return lc;
 }
 
+// threadIdx.x >> 5 in a form ptxas KNOWS to be warp-uniform (REDUX writes a uniform register).  Everything derived from it — the
+// row a warp owns, its entry count, the words it loads from uniform addresses — then stays uniform in ptxas' divergence analysis, and
+// the walks' loops and class branches compile without BSSY / BSYNC reconvergence pairs and without the BRA.DIV guard in front of every SHFL.
+__device__ __forceinline__ uint32_t warp_id_uniform() { return __reduce_max_sync(0xffffffffu, threadIdx.x >> 5); }
+
 // base + row * row_bytes in ONE instruction (IMAD.WIDE.U32); the compiler otherwise widens the
 // index arithmetic to 64 bits and spends four instructions per gathered row.
 __device__ __forceinline__ const float* row_at(const float* base, uint32_t row, uint32_t row_bytes) {
@@ -192,6 +194,20 @@ __device__ __forceinline__ void add2(float& x0, float& x1, float a0, float a1) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
 #else
     x0 = __fadd_rn(x0, a0); x1 = __fadd_rn(x1, a1);
+#endif
+}
+// acc = fma(p, c, acc) on two columns (FFMA2).  Only used with c == 0 or a power of two, where p*c is exact and the fused
+// operation therefore rounds exactly like the reference's separate multiply and add.
+__device__ __forceinline__ void fma2(float& x0, float& x1, float p0, float p1, float c) {
+#if SOUP_PACKED_FP
+    uint64_t x, p, cc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(p0), "f"(p1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c), "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(x) : "l"(p), "l"(cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+#else
+    x0 = __fmaf_rn(p0, c, x0); x1 = __fmaf_rn(p1, c, x1);
 #endif
 }
 // acc += t
@@ -269,13 +285,14 @@ struct EDec { uint32_t locus, ai, ri; };
 __device__ __forceinline__ EDec e_decode(uint32_t w, const Packing& pk) {
     EDec d;
     if (word_simple(w)) {
-        const uint32_t row = w & CSR_ROW_MASK, n = (w & CSR_DOUBLE) ? 2u : 1u;
+        const uint32_t row = w & pk.imask, n = (w & CSR_DOUBLE) ? 2u : 1u;
         const bool isref = row >= pk.plane_rows;
         d.locus = isref ? row - pk.plane_rows : row;
         d.ai = isref ? 0u : n;
         d.ri = isref ? n : 0u;
     } else {
-        d.locus = w & pk.imask;
+        const uint32_t row = w & pk.imask;
+        d.locus = row >= pk.plane_rows ? row - pk.plane_rows : row;
         d.ai = (w >> pk.sh_a) & pk.cmask;
         d.ri = (w >> pk.sh_r) & pk.cmask;
     }
@@ -285,21 +302,15 @@ __device__ __forceinline__ EDec e_decode(uint32_t w, const Packing& pk) {
 template <int V>
 struct ETile { FVec<V> a, b; };
 
-template <int V, bool EXACT_SKIP>
-__device__ __forceinline__ void e_issue(ETile<V>& t, uint32_t w, const Packing& pk, const float* __restrict__ la,
-                                        const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
-    if (EXACT_SKIP && word_simple(w)) {
-        ld_row<V>(t.a, row_at(la, w & CSR_ROW_MASK, row_bytes), hm);   // the two planes are one allocation: a row of the joint table
-        return;
-    }
+// ---- literal walk (Ctl::nonfinite: a ln table holds +-inf, so no zero-count product may be dropped): both rows of every
+// entry, the reference's expression as written.  Rare; kept simple.
+template <int V>
+__device__ __forceinline__ void e_literal_entry(FVec<V>& acc, uint32_t w, const Packing& pk, const float4* __restrict__ aux,
+                                                const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
     const EDec d = e_decode(w, pk);
-    if (!EXACT_SKIP || d.ai != 0) ld_row<V>(t.a, row_at(la, d.locus, row_bytes), hm);
-    if (!EXACT_SKIP || d.ri != 0) ld_row<V>(t.b, row_at(lb, d.locus, row_bytes), hm);
-}
-template <int V, bool EXACT_SKIP>
-__device__ __forceinline__ void e_consume(FVec<V>& acc, const ETile<V>& t, uint32_t w, const Packing& pk, const float4* __restrict__ aux) {
-    if (EXACT_SKIP && word_simple(w)) { vadd<V>(acc, (w & CSR_DOUBLE) ? vdouble<V>(t.a) : t.a); return; }
-    const EDec d = e_decode(w, pk);
+    ETile<V> t;
+    ld_row<V>(t.a, row_at(la, d.locus, row_bytes), hm);
+    ld_row<V>(t.b, row_at(lb, d.locus, row_bytes), hm);
     float alt, ref, lbc;
     if (d.ai == pk.cmask && d.ri == pk.cmask && !word_simple(w)) {          // counts outside the packed fields (rare)
         const float4 x = __ldg(aux);
@@ -307,129 +318,118 @@ __device__ __forceinline__ void e_consume(FVec<V>& acc, const ETile<V>& t, uint3
     } else {
         alt = (float)d.ai; ref = (float)d.ri; lbc = c_lbc[(d.ai << 6) | d.ri];
     }
-    if (EXACT_SKIP && d.ri == 0) {
-        vadd<V>(acc, vshift<V>(vscale<V>(t.a, alt), lbc));
-    } else if (EXACT_SKIP && d.ai == 0) {
-        vadd<V>(acc, vshift<V>(vscale<V>(t.b, ref), lbc));
+    FVec<V> x = vshift<V>(vscale<V>(t.a, alt), lbc);
+    vadd<V>(x, vscale<V>(t.b, ref));
+    vadd<V>(acc, x);
+}
+template <int V>
+__device__ __forceinline__ void e_walk_literal(FVec<V>& acc, const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t n,
+                                               const Packing& pk, const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
+#pragma unroll 1
+    for (uint32_t j = 0; j < n; ++j) e_literal_entry<V>(acc, __ldg(p + j), pk, aux + j, la, lb, row_bytes, hm);
+}
+
+// ---- the walk (every table value finite).  A warp owns (cell, column group).  It takes the cell's entry words 32 at a time with
+// ONE coalesced load (lane j holds word j), classifies them once per chunk with warp votes — whose results ptxas knows to be
+// warp-uniform, so the per-entry class tests below are uniform branches without the BSSY / BSYNC reconvergence pairs that
+// tests on a loaded word cost — and then serves the entries strictly in order: the owner lane's pre-masked row index and
+// multiplier are broadcast with SHFL, every lane gathers its V columns of that ONE row, and
+//   * count 1 / 2 / 4 ... of one allele (85 % of the entries are 1 or 2):   acc = fma(t, c, acc), c a power of two.  t*c is then
+//     exact, so the fused operation rounds exactly like the reference's  acc + c*t  (and lbc == ln C(n,n) == +0, 0 + x == x);
+//   * any other count of one allele:  acc += rn(c*t);
+//   * both alleles (or counts beyond the packed fields):  the second row is fetched late and the literal expression runs.
+// The general classes read {alt, ref, lbc} from the side record of the entry (owner lane, once per chunk).
+template <int V> __device__ __forceinline__ void vfma(FVec<V>& acc, const FVec<V>& t, float c) {
+    if constexpr (V == 1) acc.v[0] = __fmaf_rn(t.v[0], c, acc.v[0]);
+    else {
+#pragma unroll
+        for (int v = 0; v + 1 < V; v += 2) fma2(acc.v[v], acc.v[v + 1], t.v[v], t.v[v + 1], c);
+    }
+}
+__device__ __forceinline__ bool pow2_or_zero(float c) { return (__float_as_uint(c) & 0x007fffffu) == 0u; }   // (finite by construction)
+
+template <int V>
+__device__ __forceinline__ void e_general(FVec<V>& acc, const FVec<V>& t, bool both, uint32_t src, uint32_t row, const float4& x, float cf,
+                                          const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
+    if (both) {
+        FVec<V> tb;
+        ld_row<V>(tb, row_at(la, row + pk.plane_rows, row_bytes), hm);
+        const float alt = __shfl_sync(0xffffffffu, x.x, src), ref = __shfl_sync(0xffffffffu, x.y, src), lbc = __shfl_sync(0xffffffffu, x.z, src);
+        FVec<V> y = vshift<V>(vscale<V>(t, alt), lbc);
+        vadd<V>(y, vscale<V>(tb, ref));
+        vadd<V>(acc, y);
     } else {
-        FVec<V> x = vshift<V>(vscale<V>(t.a, alt), lbc);
-        vadd<V>(x, vscale<V>(t.b, ref));
-        vadd<V>(acc, x);
+        vadd<V>(acc, vscale<V>(t, __shfl_sync(0xffffffffu, cf, src)));
     }
 }
 
-template <int V, int U, bool EXACT_SKIP>
-__device__ __forceinline__ void e_batch(FVec<V>& acc, const uint32_t (&cur)[U], const Packing& pk, const float4* __restrict__ aux,
-                                        const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
-    if (!EXACT_SKIP) {   // literal expression for every entry (non-finite tables): both rows of every entry
-        ETile<V> t[U];
+// One entry of the chunk: `e` (warp-uniform) is its position, t the gathered row.
+template <int V>
+__device__ __forceinline__ void e_consume(FVec<V>& acc, const FVec<V>& t, uint32_t e, uint32_t r, float cf, const float4& x, uint32_t gm, uint32_t bm,
+                                          const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
+    if (!((gm >> e) & 1u)) vfma<V>(acc, t, __shfl_sync(0xffffffffu, cf, e));
+    else e_general<V>(acc, t, (bm >> e) & 1u, e, r, x, cf, pk, la, row_bytes, hm);
+}
+
+// The rows of a chunk are gathered through a ring of U row registers: entry e lives in slot e % U, and as soon as it has been
+// consumed the slot takes the row of entry e + U.  So U - 1 .. U row gathers (U KB at 256 columns) stay in flight per warp the whole
+// time — the pass is bound by the latency of these gathers, not by any unit's throughput (ncu: long-scoreboard stalls dominate, L1 data
+// pipe 63 %, L2 52 %, issue 45 %) — instead of a batch that is issued, awaited and consumed before the next one starts.
+// The next chunk's words are fetched while this one is served.
+template <int V, int U>
+__device__ __forceinline__ void e_walk(FVec<V>& acc, const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t n,
+                                       const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t w_next = lane < n ? __ldg(p + lane) : 0u;
+#pragma unroll 1
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t cnt = min(32u, n - base);
+        const uint32_t w = w_next;
+        w_next = base + 32 + lane < n ? __ldg(p + base + 32 + lane) : 0u;
+        const uint32_t row = w & pk.imask;
+        float cf = (w & CSR_DOUBLE) ? 2.0f : 1.0f;
+        float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        bool gen = false, both = false;
+        if (!word_simple(w)) {
+            x = __ldg(aux + base + lane);
+            const bool marker = ((w >> pk.sh_a) & pk.cmask) == pk.cmask && ((w >> pk.sh_r) & pk.cmask) == pk.cmask;
+            both = marker || (x.x != 0.0f && x.y != 0.0f);
+            cf = x.x != 0.0f ? x.x : x.y;
+            gen = both || !pow2_or_zero(cf);
+        }
+        const uint32_t gm = __ballot_sync(0xffffffffu, gen), bm = __ballot_sync(0xffffffffu, both);
+        FVec<V> t[U];
+        uint32_t r[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) e_issue<V, false>(t[u], cur[u], pk, la, lb, row_bytes, hm);
-#pragma unroll
-        for (int u = 0; u < U; ++u) e_consume<V, false>(acc, t[u], cur[u], pk, aux + u);
-        return;
-    }
-    // Exact-shortcut path.  The pass is bound by the row gathers a warp keeps in flight, and ~93 % of the entries need
-    // ONE row (single-UMI, or several UMIs of one allele), so a tile slot is one row: twice the entries in flight for
-    // the same registers.  The second row of a two-allele entry goes to the shared tile `tb` — early for the first such
-    // entry of the batch, late (an exposed load) for the rare further ones.
-    FVec<V> t[U], tb;
-#if SOUP_E_FASTBATCH
-    // Experiment (off): 85 % of the entries are simple words, so most batches hold nothing else.  One warp-uniform
-    // test per batch then buys a body without per-entry class branches (the BSSY / BSYNC / BRA triples are 21 % of the pass's
-    // instructions): U row gathers, then `acc += t` or `acc += t + t` — the same operations in the same order as below.
-    if (U > 1) {
-        uint32_t any = 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) any |= cur[u];
-        if (word_simple(any)) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) ld_row<V>(t[u], row_at(la, cur[u] & CSR_ROW_MASK, row_bytes), hm);
+        for (int u = 0; u < U; ++u) {
+            r[u] = __shfl_sync(0xffffffffu, row, u);                      // (lanes >= cnt hold row 0: a valid, unused gather)
+            ld_row<V>(t[u], row_at(la, r[u], row_bytes), hm);
+        }
+        uint32_t e = 0;
+#pragma unroll 1
+        for (; e + 2 * U <= cnt; e += U) {                                // steady state: consume entry e + u, refill its slot with e + U + u
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool twice = (cur[u] & CSR_DOUBLE) != 0;
-#pragma unroll
-                for (int v = 0; v < V; ++v) t[u].v[v] = twice ? __fadd_rn(t[u].v[v], t[u].v[v]) : t[u].v[v];
-                vadd<V>(acc, t[u]);
+                e_consume<V>(acc, t[u], e + u, r[u], cf, x, gm, bm, pk, la, row_bytes, hm);
+                r[u] = __shfl_sync(0xffffffffu, row, e + U + u);
+                ld_row<V>(t[u], row_at(la, r[u], row_bytes), hm);
             }
-            return;
         }
-    }
-#endif
-    int owner = -1;
+        // fewer than 2U entries left in the chunk: the ring holds entries [e, e + U); refills only where an entry exists
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint32_t w = cur[u];
-        if (word_simple(w)) { ld_row<V>(t[u], row_at(la, w & CSR_ROW_MASK, row_bytes), hm); continue; }
-        const uint32_t locus = w & pk.imask, ai = (w >> pk.sh_a) & pk.cmask, ri = (w >> pk.sh_r) & pk.cmask;
-        if (ai != 0) {
-            ld_row<V>(t[u], row_at(la, locus, row_bytes), hm);
-            if (ri != 0 && owner < 0) { ld_row<V>(tb, row_at(lb, locus, row_bytes), hm); owner = u; }
-        } else {
-            ld_row<V>(t[u], row_at(lb, locus, row_bytes), hm);
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint32_t w = cur[u];
-        if (word_simple(w)) {
-            if (w & CSR_DOUBLE) vadd<V>(acc, vdouble<V>(t[u]));
-            else vadd<V>(acc, t[u]);
-            continue;
-        }
-        const uint32_t ai = (w >> pk.sh_a) & pk.cmask, ri = (w >> pk.sh_r) & pk.cmask;
-        float alt, ref, lbc;
-        if (ai == pk.cmask && ri == pk.cmask) {          // counts outside the packed fields (rare)
-            const float4 x = __ldg(aux + u);
-            alt = x.x; ref = x.y; lbc = x.z;
-        } else {
-            alt = (float)ai; ref = (float)ri; lbc = c_lbc[(ai << 6) | ri];
-        }
-        const bool marker = ai == pk.cmask && ri == pk.cmask;
-        if (ri == 0) {
-            // one allele only: lbc = ln C(n, n) = +0 and 0 + x == x (x = alt * ln th is never -0), so acc += alt * ln th
-            vadd<V>(acc, vcount<V>(t[u], ai, alt));
-        } else if (ai == 0) {
-            vadd<V>(acc, vcount<V>(t[u], ri, ref));
-        } else {
-            if (owner != u) ld_row<V>(tb, row_at(lb, w & pk.imask, row_bytes), hm);
-            FVec<V> x = vshift<V>(marker ? vscale<V>(t[u], alt) : vcount<V>(t[u], ai, alt), lbc);
-            vadd<V>(x, marker ? vscale<V>(tb, ref) : vcount<V>(tb, ri, ref));
-            vadd<V>(acc, x);
-        }
-    }
-}
-
-// Software-pipelined walk: the next U entry words are fetched while the current U row gathers are in
-// flight; many resident warps (small register footprint, compact code) hide the rest.  The loop body is
-// kept to ONE copy of the batch code — an earlier ping-pong version tripled the kernel's SASS and lost
-// more to instruction-cache misses than it saved in register moves.
-template <int V, int U, bool EXACT_SKIP>
-__device__ __forceinline__ void e_walk(FVec<V>& acc, const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t n,
-                                       const Packing& pk, const float* __restrict__ la, const float* __restrict__ lb, uint32_t row_bytes, uint32_t hm) {
-    uint32_t x[U], y[U];
-    uint32_t done = 0;
-    if (n >= U) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) x[u] = __ldg(p + u);
-#pragma unroll 1
-        for (;;) {
-            const bool more = done + 2 * U <= n;
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) y[u] = __ldg(p + done + U + u);
+        for (int u = 0; u < U; ++u) {
+            if (e + u < cnt) {
+                e_consume<V>(acc, t[u], e + u, r[u], cf, x, gm, bm, pk, la, row_bytes, hm);
+                if (e + U + u < cnt) {
+                    r[u] = __shfl_sync(0xffffffffu, row, e + U + u);
+                    ld_row<V>(t[u], row_at(la, r[u], row_bytes), hm);
+                }
             }
-            e_batch<V, U, EXACT_SKIP>(acc, x, pk, aux + done, la, lb, row_bytes, hm);
-            done += U;
-            if (!more) break;
-#pragma unroll
-            for (int u = 0; u < U; ++u) x[u] = y[u];
         }
-    }
-#pragma unroll 1
-    for (; done < n; ++done) {
-        const uint32_t w[1] = {__ldg(p + done)};
-        e_batch<V, 1, EXACT_SKIP>(acc, w, pk, aux + done, la, lb, row_bytes, hm);
+        e += U;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (e + u < cnt) e_consume<V>(acc, t[u], e + u, r[u], cf, x, gm, bm, pk, la, row_bytes, hm);
     }
 }
 
@@ -451,8 +451,8 @@ __device__ __forceinline__ void estep_body(const EArgs& a, uint32_t cell, uint32
 #pragma unroll
     for (int v = 0; v < V; ++v) acc.v[v] = a.log_prior;
     constexpr int U = V == 1 ? SOUP_E_U1 : (V == 2 ? SOUP_E_U2 : (V == 4 ? SOUP_E_U4 : (V == 8 ? SOUP_E_U8 : SOUP_E_U16)));
-    if (!a.ctl->nonfinite) e_walk<V, U, true>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.LB + lc.col, a.Cpad * 4u, lc.hm);
-    else e_walk<V, 2, false>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.LB + lc.col, a.Cpad * 4u, lc.hm);
+    if (!a.ctl->nonfinite) e_walk<V, U>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.Cpad * 4u, lc.hm);
+    else e_walk_literal<V>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.LB + lc.col, a.Cpad * 4u, lc.hm);
     if (lc.live) st_row<V>(a.ELL + (size_t)cell * a.Cpad + lc.col, acc, lc.hm);
 }
 
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_E_MINB : 2) * (256
     const uint32_t live = a.ctl->live_cols, col0 = group * (32 * VM);
     if (col0 >= live || !a.group_active[group]) return;
     const uint32_t chunk = blockIdx.x - group * a.blocks_per_group;
-    const uint32_t ci = chunk * EM_WARPS + (EM_WARPS > 1 ? threadIdx.x >> 5 : 0);
+    const uint32_t ci = chunk * EM_WARPS + (EM_WARPS > 1 ? warp_id_uniform() : 0);
     if (ci >= a.N) return;
     const uint32_t cell = a.cell_order[ci];
     const int v = fit_lanes<VM>(live - col0, a.no_narrow);
@@ -706,72 +706,120 @@ __global__ void __launch_bounds__(1024) control_kernel(ControlArgs a) {
 __device__ __forceinline__ float small_u2f(uint32_t i) {   // exact (float)i for i < 2^23 without the conversion pipe
     return __fadd_rn(__uint_as_float(0x4B000000u | i), -8388608.0f);
 }
-// SHORTCUT = false: the literal expression for every entry, no data-dependent branch (long-locus role: a locus covered
-// by every cell is a 10^4..10^5-long strictly sequential chain owned by one warp, and on that critical path a branch per
-// entry costs more than the multiplies it saves; also the path for non-finite weights).
-// SHORTCUT = true : single-UMI entries skip the multiplies (p*1 == p) and, for alt == 0, the s update (s + p*0 == s
-// while the weights are finite — Ctl::nonfinite == 0); used by the wide role, which is instruction-issue bound.
-template <int V, bool SHORTCUT>
-__device__ __forceinline__ void m_consume(FVec<V>& s, FVec<V>& d, const FVec<V>& p, uint32_t w, const Packing& pk, const float2* __restrict__ aux) {
-    if (SHORTCUT && word_simple(w)) {
-        vadd<V>(d, p);
-        if (w & pk.alt_bit) vadd<V>(s, p);
-        return;
-    }
-    // every CSC word carries both count fields (a simple word: alt 0/1, alt+ref 1), so the decode is uniform
-    const uint32_t ai = (w >> pk.sh_a) & pk.cmask, ti = (w >> pk.sh_r) & pk.cmask;
-    if (SHORTCUT && ti == 2) {                               // two UMIs: p*2 == p+p exactly, p*1 == p, and s + p*0 == s
-        const FVec<V> p2 = vdouble<V>(p);
-        vadd<V>(d, p2);
-        if (ai == 1) vadd<V>(s, p);
-        else if (ai == 2) vadd<V>(s, p2);
-        return;
-    }
-    float alt = small_u2f(ai), tot = small_u2f(ti);
-    if (ai == pk.cmask && ti == pk.cmask) {                  // counts outside the packed fields (rare)
-        const float2 x = __ldg(aux);
-        alt = x.x; tot = x.y;
-    }
-    if (!SHORTCUT || ai != 0) vadd<V>(s, vscale<V>(p, alt));
-    vadd<V>(d, vscale<V>(p, tot));
+// The walk mirrors the E pass: a warp owns (locus, column group), takes the locus's entry words 32 at a time with one coalesced
+// load, the owner lane decodes cell / alt / alt+ref ONCE, and the entries are then served strictly in order — cell row index and
+// the two multipliers broadcast with SHFL, every lane gathers its V weights of that cell's row:
+//   * both counts 0 or a power of two (91 % of the entries have alt+ref <= 2):  s = fma(p, alt, s), d = fma(p, alt+ref, d).  p*c is
+//     exact for such c, so the fused operation rounds exactly like the reference's  s + p*alt  — for every p, finite or not
+//     (fma(NaN, 0, s) and s + NaN*0 are both NaN), which is why this pass needs no Ctl::nonfinite variant;
+//   * anything else:  s += rn(p*alt); d += rn(p*(alt+ref))  as written (warp-uniform branch on a vote mask).
+template <int V>
+__device__ __forceinline__ void m_general(FVec<V>& s, FVec<V>& d, const FVec<V>& p, float af, float tf) {
+    vadd<V>(s, vscale<V>(p, af));
+    vadd<V>(d, vscale<V>(p, tf));
 }
-
-template <int V, int U, bool EXACT_SKIP>
-__device__ __forceinline__ void m_batch(FVec<V>& s, FVec<V>& d, const uint32_t (&cur)[U], const Packing& pk, const float2* __restrict__ aux,
-                                        const float* __restrict__ w, uint32_t row_bytes, uint32_t hm) {
-    FVec<V> p[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) ld_row<V>(p[u], row_at(w, cur[u] & pk.imask, row_bytes), hm);
-#pragma unroll
-    for (int u = 0; u < U; ++u) m_consume<V, EXACT_SKIP>(s, d, p[u], cur[u], pk, aux + u);
+template <int V>
+__device__ __forceinline__ void m_consume(FVec<V>& s, FVec<V>& d, const FVec<V>& p, uint32_t e, float af, float tf, uint32_t gm) {
+    const float a = __shfl_sync(0xffffffffu, af, e), t = __shfl_sync(0xffffffffu, tf, e);
+    if (!((gm >> e) & 1u)) { vfma<V>(s, p, a); vfma<V>(d, p, t); }
+    else m_general<V>(s, d, p, a, t);
 }
-
-template <int V, int U, bool EXACT_SKIP>
+// (the same ring of U row registers as the E walk: entry e lives in slot e % U and the slot is refilled as soon as it is consumed)
+template <int V, int U>
 __device__ __forceinline__ void m_walk(FVec<V>& s, FVec<V>& d, const uint32_t* __restrict__ q, const float2* __restrict__ aux, uint32_t n,
                                        const Packing& pk, const float* __restrict__ w, uint32_t row_bytes, uint32_t hm) {
-    uint32_t x[U], y[U];
-    uint32_t done = 0;
-    if (n >= U) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) x[u] = __ldg(q + u);
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t w_next = lane < n ? __ldg(q + lane) : 0u;
 #pragma unroll 1
-        for (;;) {
-            const bool more = done + 2 * U <= n;
-            if (more) {
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t cnt = min(32u, n - base);
+        const uint32_t wd = w_next;
+        w_next = base + 32 + lane < n ? __ldg(q + base + 32 + lane) : 0u;
+        // every CSC word carries both count fields (a simple word: alt 0/1, alt+ref 1), so the decode is uniform
+        const uint32_t ai = (wd >> pk.sh_a) & pk.cmask, ti = (wd >> pk.sh_r) & pk.cmask;
+        float af = small_u2f(ai), tf = small_u2f(ti);
+        if (ai == pk.cmask && ti == pk.cmask && lane < cnt) {    // counts outside the packed fields (rare)
+            const float2 x = __ldg(aux + base + lane);
+            af = x.x; tf = x.y;
+        }
+        const uint32_t cell = wd & pk.imask;
+        const uint32_t gm = __ballot_sync(0xffffffffu, !(pow2_or_zero(af) && pow2_or_zero(tf)));
+        FVec<V> p[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) y[u] = __ldg(q + done + U + u);
+        for (int u = 0; u < U; ++u) ld_row<V>(p[u], row_at(w, __shfl_sync(0xffffffffu, cell, u), row_bytes), hm);   // (lanes >= cnt hold cell 0: a valid, unused gather)
+        uint32_t e = 0;
+#pragma unroll 1
+        for (; e + 2 * U <= cnt; e += U) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                m_consume<V>(s, d, p[u], e + u, af, tf, gm);
+                ld_row<V>(p[u], row_at(w, __shfl_sync(0xffffffffu, cell, e + U + u), row_bytes), hm);
             }
-            m_batch<V, U, EXACT_SKIP>(s, d, x, pk, aux + done, w, row_bytes, hm);
-            done += U;
-            if (!more) break;
+        }
 #pragma unroll
-            for (int u = 0; u < U; ++u) x[u] = y[u];
+        for (int u = 0; u < U; ++u) {
+            if (e + u < cnt) {
+                m_consume<V>(s, d, p[u], e + u, af, tf, gm);
+                if (e + U + u < cnt) ld_row<V>(p[u], row_at(w, __shfl_sync(0xffffffffu, cell, e + U + u), row_bytes), hm);
+            }
+        }
+        e += U;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (e + u < cnt) m_consume<V>(s, d, p[u], e + u, af, tf, gm);
+    }
+}
+
+// Long loci.  A locus covered by most cells is a 10^4..10^5-long strictly sequential chain per column, and the M pass cannot end
+// before its longest chain does: with U gathers in flight a chain advances one entry per (gather latency / U) cycles (measured: at 25
+// resident solves the pass took 85 % of the time it takes at 50 — the chains, not the throughput, set its duration).  So the long loci
+// get narrow column groups (many warps per locus, few instructions per entry and warp) and a ring of U = 16 rows that is refilled
+// ACROSS chunk boundaries — the next chunk is decoded while the current one is served, so the chain never drains — and the literal
+// expression for every entry (at 1-2 columns per lane the multiplies cost less than a class test).
+template <int V, int U, bool GUARD>
+__device__ __forceinline__ void m_deep_chunk(FVec<V>& s, FVec<V>& d, FVec<V> (&p)[U], uint32_t cnt, uint32_t left_after,
+                                             uint32_t cell, float af, float tf, uint32_t cell2,
+                                             const float* __restrict__ w, uint32_t row_bytes, uint32_t hm) {
+    static_assert(32 % U == 0, "the ring must divide a chunk");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        FVec<V>& slot = p[i % U];
+        if (!GUARD || (uint32_t)i < cnt) m_general<V>(s, d, slot, __shfl_sync(0xffffffffu, af, i), __shfl_sync(0xffffffffu, tf, i));
+        const int j = i + U;                    // the stream entry that takes the slot
+        if (j < 32) {
+            if (!GUARD || (uint32_t)j < cnt) ld_row<V>(slot, row_at(w, __shfl_sync(0xffffffffu, cell, j), row_bytes), hm);
+        } else {
+            if (!GUARD || (uint32_t)(j - 32) < left_after) ld_row<V>(slot, row_at(w, __shfl_sync(0xffffffffu, cell2, j - 32), row_bytes), hm);
         }
     }
+}
+template <int V, int U>
+__device__ __forceinline__ void m_walk_deep(FVec<V>& s, FVec<V>& d, const uint32_t* __restrict__ q, const float2* __restrict__ aux, uint32_t n,
+                                            const Packing& pk, const float* __restrict__ w, uint32_t row_bytes, uint32_t hm) {
+    const uint32_t lane = threadIdx.x & 31;
+    auto decode = [&](uint32_t base, uint32_t& cell, float& af, float& tf) {       // chunk at `base` (may lie beyond the end: zeros)
+        const uint32_t wd = base + lane < n ? __ldg(q + base + lane) : 0u;
+        const uint32_t ai = (wd >> pk.sh_a) & pk.cmask, ti = (wd >> pk.sh_r) & pk.cmask;
+        af = small_u2f(ai); tf = small_u2f(ti);
+        if (ai == pk.cmask && ti == pk.cmask && base + lane < n) {                 // counts outside the packed fields (rare)
+            const float2 x = __ldg(aux + base + lane);
+            af = x.x; tf = x.y;
+        }
+        cell = wd & pk.imask;
+    };
+    uint32_t cell, cell2;
+    float af, tf, af2, tf2;
+    decode(0, cell, af, tf);
+    FVec<V> p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ld_row<V>(p[u], row_at(w, __shfl_sync(0xffffffffu, cell, u), row_bytes), hm);   // (beyond the end: cell 0, a valid unused gather)
 #pragma unroll 1
-    for (; done < n; ++done) {
-        const uint32_t wd[1] = {__ldg(q + done)};
-        m_batch<V, 1, EXACT_SKIP>(s, d, wd, pk, aux + done, w, row_bytes, hm);
+    for (uint32_t base = 0; base < n; base += 32) {
+        decode(base + 32, cell2, af2, tf2);
+        const uint32_t left = n - base;
+        if (left >= 64) m_deep_chunk<V, U, false>(s, d, p, 32u, 32u, cell, af, tf, cell2, w, row_bytes, hm);
+        else m_deep_chunk<V, U, true>(s, d, p, min(left, 32u), left > 32u ? left - 32u : 0u, cell, af, tf, cell2, w, row_bytes, hm);
+        cell = cell2; af = af2; tf = tf2;
     }
 }
 
@@ -816,14 +864,9 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
     FVec<V> s, d;
 #pragma unroll
     for (int v = 0; v < V; ++v) { s.v[v] = partial ? 0.0f : 1.0f; d.v[v] = partial ? 0.0f : 2.0f; }   // pseudocounts S:197-198, S:456-464
-    if (DEEP) {
-        if (SOUP_M_LONG_SHORTCUT && !a.ctl->nonfinite) m_walk<V, SOUP_M_ULONG, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
-        else m_walk<V, SOUP_M_ULONG, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
-    } else {
-        constexpr int U = V <= 2 ? SOUP_M_U2 : (V == 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16));
-        if (!a.ctl->nonfinite) m_walk<V, U, true>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
-        else m_walk<V, 2, false>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
-    }
+    constexpr int U = V <= 2 ? SOUP_M_U2 : (V == 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16));
+    if constexpr (DEEP) m_walk_deep<V, SOUP_M_ULONG>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
+    else m_walk<V, U>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
     if (!lc.live) return;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -853,7 +896,7 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
 // where the per-entry cost is amortised over more columns (narrowed to the live columns like the E pass).
 template <int VM>
 __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256 / EM_THREADS)) mstep_kernel(const MArgs a) {
-    const uint32_t warp = EM_WARPS > 1 ? threadIdx.x >> 5 : 0;
+    const uint32_t warp = EM_WARPS > 1 ? warp_id_uniform() : 0;
     const uint32_t live = m_live_cols(a);
     const bool coop = m_coop(a, live);
     if (blockIdx.x < a.long_blocks) {
@@ -1309,10 +1352,13 @@ __device__ __forceinline__ uint32_t pack_general(uint32_t idx, uint32_t c0, uint
     if (c0 >= pk.cmask || c1 >= pk.cmask) c0 = c1 = pk.cmask;   // out-of-field: marker, the side record holds the counts
     return 0x80000000u | (c0 << pk.sh_a) | (c1 << pk.sh_r) | idx;
 }
+// CSR words: bits [0, sh_r) of EVERY word are the first row of the joint ln table the entry reads — locus (alt != 0, or counts beyond
+// the fields) or plane_rows + locus (ref only); an entry with both alleles reads row + plane_rows as well.
 __device__ __forceinline__ uint32_t pack_csr_word(uint32_t locus, uint32_t alt, uint32_t ref, const Packing& pk) {
     if (ref == 0 && (alt == 1 || alt == 2)) return locus | (alt == 2 ? CSR_DOUBLE : 0u);
     if (alt == 0 && (ref == 1 || ref == 2)) return (pk.plane_rows + locus) | (ref == 2 ? CSR_DOUBLE : 0u);
-    return pack_general(locus, alt, ref, pk);
+    const bool overflow = alt >= pk.cmask || ref >= pk.cmask;
+    return pack_general(alt != 0 || overflow ? locus : pk.plane_rows + locus, alt, ref, pk);
 }
 __device__ __forceinline__ uint32_t pack_csc_word(uint32_t cell, uint32_t alt, uint32_t ref, const Packing& pk) {
     if (alt == 1 && ref == 0) return cell | (1u << pk.sh_r) | (1u << pk.sh_a);

@@ -462,10 +462,13 @@ def test_write_clusters_many_blocks_matches_oracle_formatting(tmp_path):
 
 def test_sass_exactness_guards():
     """Static check of the built sm_100a code (cuobjdump runs without a GPU).  Bit-exactness against the reference's f32 arithmetic rests on
-    the compiler never fusing a multiply into an add (Rust never contracts; ptxas was seen to turn a packed multiply feeding a packed add
-    into FFMA2 even under -fmad=false): the E kernels — every (cell, cluster) sum is `acc + (lbc + a*x) + r*y` — must hold no FFMA at all,
-    no kernel may hold an FFMA2, and the packed adds (FADD2) the design relies on must be there.  (FFMA inside the M / post kernels is the
-    IEEE division and double -> float code, which is exact by construction.)  The cubin must be sm_100a."""
+    the compiler never fusing a multiply into an add on its own (Rust never contracts; ptxas was seen to turn a packed multiply feeding a
+    packed add into FFMA2 even under -fmad=false).  The E / M walks do issue fused operations themselves, but only through `vfma` with a
+    multiplier that is 0 or a power of two (the product is then exact, so fused and unfused round alike); every other multiply must stay a
+    scalar FMUL followed by a packed add.  So: FFMA2 may appear in the E / M kernels only, those kernels must still hold the unfused
+    FMUL + FADD2 pairs of the general classes, and no other kernel may hold an FFMA2.  (Scalar FFMA inside the M / post kernels is the
+    IEEE division and double -> float code, exact by construction; in the one-column E body it is `vfma` itself.)  The bit-exact GPU
+    suite (counts 1..200 of either allele, test_gpu_parity.py) is the dynamic half of this guard.  The cubin must be sm_100a."""
     import shutil
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump):
@@ -491,8 +494,12 @@ def test_sass_exactness_guards():
     mstep = {k: v for k, v in per.items() if "mstep_kernel" in k}
     assert len(estep) == 5 and len(mstep) == 5, (sorted(estep), sorted(mstep))      # V = 1, 2, 4, 8, 16 columns per lane
     for k, v in estep.items():
-        assert v["FFMA"] == 0 and v["FMUL"] > 0, (k, v)
+        assert v["FMUL"] > 0, (k, v)
         assert v["FADD2"] > 0 or "ILi1E" in k, (k, v)                                # one column per lane has nothing to pair
+        assert v["FFMA2"] > 0 or "ILi1E" in k, (k, v)
+        if "ILi1E" not in k:
+            assert v["FADD2"] > v["FFMA2"], (k, v)                                   # the general classes were not contracted away
     for k, v in per.items():
-        assert v["FFMA2"] == 0, (k, v)
+        if "estep_kernel" not in k and "mstep_kernel" not in k:
+            assert v["FFMA2"] == 0, (k, v)
     assert all(v["FADD2"] > 0 for v in mstep.values())
