@@ -54,6 +54,9 @@ namespace soup {
 #ifndef SOUP_M_LONG_SHORTCUT
 #define SOUP_M_LONG_SHORTCUT 0   // 1: the long role also takes the single-UMI shortcuts (sign test + predicated adds)
 #endif
+#ifndef SOUP_DEEP_VMAX
+#define SOUP_DEEP_VMAX 4  // bodies of at most this many columns per lane run the cross-chunk ring of 32 / V rows (few live solves: latency chains)
+#endif
 #ifndef SOUP_E_VMAX
 #define SOUP_E_VMAX 8    // widest E-pass column group, in columns per lane
 #endif
@@ -348,12 +351,14 @@ template <int V> __device__ __forceinline__ void vfma(FVec<V>& acc, const FVec<V
 }
 __device__ __forceinline__ bool pow2_or_zero(float c) { return (__float_as_uint(c) & 0x007fffffu) == 0u; }   // (finite by construction)
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
 template <int V>
 __device__ __forceinline__ void e_general(FVec<V>& acc, const FVec<V>& t, bool both, uint32_t src, uint32_t row, const float4& x, float cf,
                                           const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
     if (both) {
         FVec<V> tb;
-        ld_row<V>(tb, row_at(la, row + pk.plane_rows, row_bytes), hm);
+        ld_row<V>(tb, row_at(la, __shfl_sync(0xffffffffu, row, src) + pk.plane_rows, row_bytes), hm);
         const float alt = __shfl_sync(0xffffffffu, x.x, src), ref = __shfl_sync(0xffffffffu, x.y, src), lbc = __shfl_sync(0xffffffffu, x.z, src);
         FVec<V> y = vshift<V>(vscale<V>(t, alt), lbc);
         vadd<V>(y, vscale<V>(tb, ref));
@@ -363,73 +368,112 @@ __device__ __forceinline__ void e_general(FVec<V>& acc, const FVec<V>& t, bool b
     }
 }
 
-// One entry of the chunk: `e` (warp-uniform) is its position, t the gathered row.
+// One chunk of 32 entry words, classified (lane j holds entry j; gm / bm are warp votes)
+struct EChunk { uint32_t row; float cf; float4 x; uint32_t gm, bm; };
+__device__ __forceinline__ EChunk e_chunk(const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t base, uint32_t n, const Packing& pk) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = base + lane < n ? __ldg(p + base + lane) : 0u;      // (beyond the end: row 0, a valid unused gather)
+    EChunk c;
+    c.row = w & pk.imask;
+    c.cf = (w & CSR_DOUBLE) ? 2.0f : 1.0f;
+    c.x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    bool gen = false, both = false;
+    if (!word_simple(w)) {
+        c.x = __ldg(aux + base + lane);
+        const bool marker = ((w >> pk.sh_a) & pk.cmask) == pk.cmask && ((w >> pk.sh_r) & pk.cmask) == pk.cmask;
+        both = marker || (c.x.x != 0.0f && c.x.y != 0.0f);
+        c.cf = c.x.x != 0.0f ? c.x.x : c.x.y;
+        gen = both || !pow2_or_zero(c.cf);
+    }
+    c.gm = __ballot_sync(0xffffffffu, gen);
+    c.bm = __ballot_sync(0xffffffffu, both);
+    return c;
+}
+// entry `e` (warp-uniform) of chunk c; t is its gathered row
 template <int V>
-__device__ __forceinline__ void e_consume(FVec<V>& acc, const FVec<V>& t, uint32_t e, uint32_t r, float cf, const float4& x, uint32_t gm, uint32_t bm,
+__device__ __forceinline__ void e_consume(FVec<V>& acc, const FVec<V>& t, uint32_t e, const EChunk& c,
                                           const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
-    if (!((gm >> e) & 1u)) vfma<V>(acc, t, __shfl_sync(0xffffffffu, cf, e));
-    else e_general<V>(acc, t, (bm >> e) & 1u, e, r, x, cf, pk, la, row_bytes, hm);
+    if (!((c.gm >> e) & 1u)) vfma<V>(acc, t, __shfl_sync(0xffffffffu, c.cf, e));
+    else e_general<V>(acc, t, (c.bm >> e) & 1u, e, c.row, c.x, c.cf, pk, la, row_bytes, hm);
+}
+template <int V>
+__device__ __forceinline__ void e_fetch(FVec<V>& t, uint32_t e, const EChunk& c, const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm, bool pf) {
+    const uint32_t r = __shfl_sync(0xffffffffu, c.row, e);
+    ld_row<V>(t, row_at(la, r, row_bytes), hm);
+    if (pf && ((c.bm >> e) & 1u)) prefetch_l1(row_at(la, r + pk.plane_rows, row_bytes));   // the second row of a two-allele entry: into L1 ahead of its late load
 }
 
-// The rows of a chunk are gathered through a ring of U row registers: entry e lives in slot e % U, and as soon as it has been
-// consumed the slot takes the row of entry e + U.  So U - 1 .. U row gathers (U KB at 256 columns) stay in flight per warp the whole
-// time — the pass is bound by the latency of these gathers, not by any unit's throughput (ncu: long-scoreboard stalls dominate, L1 data
-// pipe 63 %, L2 52 %, issue 45 %) — instead of a batch that is issued, awaited and consumed before the next one starts.
-// The next chunk's words are fetched while this one is served.
+// The rows are gathered through a ring of U row registers: entry e lives in slot e % U, and as soon as it has been consumed the slot
+// takes the row of entry e + U.  So U - 1 .. U row gathers (U KB at 256 columns) stay in flight per warp the whole time, instead of a
+// batch that is issued, awaited and consumed before the next one starts (the pass is bound by the latency of these gathers: ncu shows
+// long-scoreboard stalls dominating with the L1 data pipe at 63 %, L2 at 52 % and issue at 45 %).
+// Wide bodies (V = 8, 16; the full-occupancy passes, bound by throughput) refill the ring inside a chunk and prefetch the next
+// chunk's words.  Narrow bodies (V <= 4: few live solves, the tail of a job, where a pass lasts as long as its longest cell) take
+// U = 32 / V slots and refill ACROSS the chunk boundary from the already classified next chunk, so the chain never drains.
 template <int V, int U>
 __device__ __forceinline__ void e_walk(FVec<V>& acc, const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t n,
                                        const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t w_next = lane < n ? __ldg(p + lane) : 0u;
 #pragma unroll 1
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t cnt = min(32u, n - base);
-        const uint32_t w = w_next;
-        w_next = base + 32 + lane < n ? __ldg(p + base + 32 + lane) : 0u;
-        const uint32_t row = w & pk.imask;
-        float cf = (w & CSR_DOUBLE) ? 2.0f : 1.0f;
-        float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        bool gen = false, both = false;
-        if (!word_simple(w)) {
-            x = __ldg(aux + base + lane);
-            const bool marker = ((w >> pk.sh_a) & pk.cmask) == pk.cmask && ((w >> pk.sh_r) & pk.cmask) == pk.cmask;
-            both = marker || (x.x != 0.0f && x.y != 0.0f);
-            cf = x.x != 0.0f ? x.x : x.y;
-            gen = both || !pow2_or_zero(cf);
-        }
-        const uint32_t gm = __ballot_sync(0xffffffffu, gen), bm = __ballot_sync(0xffffffffu, both);
+        const EChunk c = e_chunk(p, aux, base, n, pk);
         FVec<V> t[U];
-        uint32_t r[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            r[u] = __shfl_sync(0xffffffffu, row, u);                      // (lanes >= cnt hold row 0: a valid, unused gather)
-            ld_row<V>(t[u], row_at(la, r[u], row_bytes), hm);
-        }
+        for (int u = 0; u < U; ++u) e_fetch<V>(t[u], u, c, pk, la, row_bytes, hm, false);
         uint32_t e = 0;
 #pragma unroll 1
         for (; e + 2 * U <= cnt; e += U) {                                // steady state: consume entry e + u, refill its slot with e + U + u
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                e_consume<V>(acc, t[u], e + u, r[u], cf, x, gm, bm, pk, la, row_bytes, hm);
-                r[u] = __shfl_sync(0xffffffffu, row, e + U + u);
-                ld_row<V>(t[u], row_at(la, r[u], row_bytes), hm);
+                e_consume<V>(acc, t[u], e + u, c, pk, la, row_bytes, hm);
+                e_fetch<V>(t[u], e + U + u, c, pk, la, row_bytes, hm, false);
             }
         }
         // fewer than 2U entries left in the chunk: the ring holds entries [e, e + U); refills only where an entry exists
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (e + u < cnt) {
-                e_consume<V>(acc, t[u], e + u, r[u], cf, x, gm, bm, pk, la, row_bytes, hm);
-                if (e + U + u < cnt) {
-                    r[u] = __shfl_sync(0xffffffffu, row, e + U + u);
-                    ld_row<V>(t[u], row_at(la, r[u], row_bytes), hm);
-                }
+                e_consume<V>(acc, t[u], e + u, c, pk, la, row_bytes, hm);
+                if (e + U + u < cnt) e_fetch<V>(t[u], e + U + u, c, pk, la, row_bytes, hm, false);
             }
         }
         e += U;
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (e + u < cnt) e_consume<V>(acc, t[u], e + u, r[u], cf, x, gm, bm, pk, la, row_bytes, hm);
+            if (e + u < cnt) e_consume<V>(acc, t[u], e + u, c, pk, la, row_bytes, hm);
+    }
+}
+
+template <int V, int U, bool GUARD>
+__device__ __forceinline__ void e_deep_chunk(FVec<V>& acc, FVec<V> (&t)[U], uint32_t cnt, uint32_t left_after, const EChunk& c, const EChunk& c2,
+                                             const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
+    static_assert(32 % U == 0, "the ring must divide a chunk");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        FVec<V>& slot = t[i % U];
+        if (!GUARD || (uint32_t)i < cnt) e_consume<V>(acc, slot, i, c, pk, la, row_bytes, hm);
+        const int j = i + U;                    // the stream entry that takes the slot
+        if (j < 32) {
+            if (!GUARD || (uint32_t)j < cnt) e_fetch<V>(slot, j, c, pk, la, row_bytes, hm, true);
+        } else {
+            if (!GUARD || (uint32_t)(j - 32) < left_after) e_fetch<V>(slot, j - 32, c2, pk, la, row_bytes, hm, true);
+        }
+    }
+}
+template <int V, int U>
+__device__ __forceinline__ void e_walk_deep(FVec<V>& acc, const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t n,
+                                            const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
+    EChunk c = e_chunk(p, aux, 0, n, pk);
+    FVec<V> t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) e_fetch<V>(t[u], u, c, pk, la, row_bytes, hm, true);
+#pragma unroll 1
+    for (uint32_t base = 0; base < n; base += 32) {
+        const EChunk c2 = e_chunk(p, aux, base + 32, n, pk);
+        const uint32_t left = n - base;
+        if (left >= 64) e_deep_chunk<V, U, false>(acc, t, 32u, 32u, c, c2, pk, la, row_bytes, hm);
+        else e_deep_chunk<V, U, true>(acc, t, min(left, 32u), left > 32u ? left - 32u : 0u, c, c2, pk, la, row_bytes, hm);
+        c = c2;
     }
 }
 
@@ -451,7 +495,10 @@ __device__ __forceinline__ void estep_body(const EArgs& a, uint32_t cell, uint32
 #pragma unroll
     for (int v = 0; v < V; ++v) acc.v[v] = a.log_prior;
     constexpr int U = V == 1 ? SOUP_E_U1 : (V == 2 ? SOUP_E_U2 : (V == 4 ? SOUP_E_U4 : (V == 8 ? SOUP_E_U8 : SOUP_E_U16)));
-    if (!a.ctl->nonfinite) e_walk<V, U>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.Cpad * 4u, lc.hm);
+    if (!a.ctl->nonfinite) {
+        if constexpr (V <= SOUP_DEEP_VMAX) e_walk_deep<V, 32 / V>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.Cpad * 4u, lc.hm);
+        else e_walk<V, U>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.Cpad * 4u, lc.hm);
+    }
     else e_walk_literal<V>(acc, a.csr_idx + j0, a.csr_aux + j0, n, a.pk, a.LA + lc.col, a.LB + lc.col, a.Cpad * 4u, lc.hm);
     if (lc.live) st_row<V>(a.ELL + (size_t)cell * a.Cpad + lc.col, acc, lc.hm);
 }
@@ -866,6 +913,7 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
     for (int v = 0; v < V; ++v) { s.v[v] = partial ? 0.0f : 1.0f; d.v[v] = partial ? 0.0f : 2.0f; }   // pseudocounts S:197-198, S:456-464
     constexpr int U = V <= 2 ? SOUP_M_U2 : (V == 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16));
     if constexpr (DEEP) m_walk_deep<V, SOUP_M_ULONG>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
+    else if constexpr (V <= 2 && V <= SOUP_DEEP_VMAX) m_walk_deep<V, 32 / V>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
     else m_walk<V, U>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
     if (!lc.live) return;
 #pragma unroll
