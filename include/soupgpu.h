@@ -64,13 +64,14 @@ int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uint32_t min_a
                       uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags, soup_mtx** out);
 void soup_mtx_free(soup_mtx* m);
 /* Binary cache of a loaded matrix (`.soupcsr`): soup_mtx_save writes what soup_mtx_load returned together with the
- * filter it was built with; soup_mtx_load_cache reads it back (and fails with SOUP_ERR_INVALID if the filter / RAW flag differ or
- * the file is not consistent), so re-runs, troublet and consensus skip the text parse.  The wire format of record stays the
+ * filter it was built with and a fingerprint (size, mtime, hash of both ends) of the two text matrices it was parsed from;
+ * soup_mtx_load_cache reads it back (and fails with SOUP_ERR_INVALID if the filter / RAW flag differ, the cache was built from
+ * other alt / ref files, or the file is not consistent), so re-runs, troublet and consensus skip the text parse.  The wire format of record stays the
  * vartrix text mtx; ".mtx.gz" inputs are accepted by soup_mtx_load as an extension (the reference opens them uncompressed, S:602-607). */
-int32_t soup_mtx_save(const soup_mtx* m, const char* path, uint32_t min_alt, uint32_t min_ref, uint32_t min_alt_umis,
-                      uint32_t min_ref_umis, uint32_t flags);
-int32_t soup_mtx_load_cache(const char* path, uint32_t min_alt, uint32_t min_ref, uint32_t min_alt_umis, uint32_t min_ref_umis,
-                            uint32_t flags, soup_mtx** out);
+int32_t soup_mtx_save(const soup_mtx* m, const char* path, const char* alt_path, const char* ref_path, uint32_t min_alt, uint32_t min_ref,
+                      uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags);
+int32_t soup_mtx_load_cache(const char* path, const char* alt_path, const char* ref_path, uint32_t min_alt, uint32_t min_ref,
+                            uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags, soup_mtx** out);
 
 /* load_barcodes S:707-718 (+ reader S:500-511: ".gz" via zlib).  Returns one malloc'ed
  * buffer of NUL-separated barcodes; free with soup_free(). */

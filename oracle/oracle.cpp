@@ -13,6 +13,7 @@
 #include <limits>
 #include <mutex>
 #include <stdexcept>
+#include <atomic>
 #include <thread>
 #include <unordered_map>
 #include <unordered_set>
@@ -396,6 +397,53 @@ StepOut em_khm_step(size_t loci, std::vector<std::vector<float>>& centers, const
     return out;
 }
 
+// Oracle-only (Params::inner_threads > 1): the SAME per-cell and per-(cluster, locus) arithmetic chains as the loop of S:225-243,
+// evaluated concurrently so the full-size parity tests finish in seconds.  Bit-identical to the serial loop by construction (and by
+// test): a cell's pass (S:229-236) reads only the centers; the loss is then summed over cells in index order by one thread
+// (S:230); and the accumulation S:476-483 is split by CLUSTER — every (cluster, locus) sum still takes the cells in ascending order.
+static void iteration_in_parallel(ClusterMethod method, const std::vector<CellData>& cells, const std::vector<std::vector<float>>& centers,
+                                  float log_prior, int temp_step, int n_threads, std::vector<std::vector<float>>* final_lp,
+                                  std::vector<std::vector<float>>* sums, std::vector<std::vector<float>>* denoms, float* loss_out) {
+    const size_t n = cells.size(), k = centers.size();
+    std::vector<std::vector<float>> probs(n);
+    std::vector<float> lse(n);
+    std::vector<std::thread> pool;
+    std::atomic<size_t> next{0};
+    for (int t = 0; t < n_threads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                const size_t i0 = next.fetch_add(64);
+                if (i0 >= n) break;
+                for (size_t i = i0; i < std::min(n, i0 + 64); ++i)
+                    lse[i] = cell_pass(method, cells[i], centers, log_prior, temp_step, &(*final_lp)[i], &probs[i]);
+            }
+        });
+    for (auto& th : pool) th.join();
+    pool.clear();
+    float loss = 0.0f;
+    for (size_t i = 0; i < n; ++i) loss += lse[i];
+    *loss_out = loss;
+    std::atomic<size_t> next_k{0};
+    for (int t = 0; t < n_threads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                const size_t c = next_k.fetch_add(1);
+                if (c >= k) break;
+                std::vector<float>& s = (*sums)[c];
+                std::vector<float>& d = (*denoms)[c];
+                for (size_t i = 0; i < n; ++i) {
+                    const CellData& cell = cells[i];
+                    const float p = probs[i][c];
+                    for (size_t j = 0; j < cell.loci.size(); ++j) {
+                        s[cell.loci[j]] += p * (float)cell.alt_counts[j];
+                        d[cell.loci[j]] += p * (float)(cell.alt_counts[j] + cell.ref_counts[j]);
+                    }
+                }
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
 static std::mutex g_trace_mutex;
 
 static float em_khm(ClusterMethod method, size_t loci, std::vector<std::vector<float>>& centers,
@@ -417,9 +465,13 @@ static float em_khm(ClusterMethod method, size_t loci, std::vector<std::vector<f
         while (log_loss_change > log_loss_change_limit && iterations < params.iteration_cap) {   // S:222 (cap=1000)
             float log_binom_loss = 0.0f;
             reset_sums_denoms(loci, sums, denoms, k);
-            for (size_t i = 0; i < cells.size(); ++i) {
-                log_binom_loss += cell_pass(method, cells[i], centers, log_prior, temp_step, &(*final_lp)[i], &prob);
-                update_centers_average(sums, denoms, cells[i], prob);
+            if (params.inner_threads <= 1) {
+                for (size_t i = 0; i < cells.size(); ++i) {
+                    log_binom_loss += cell_pass(method, cells[i], centers, log_prior, temp_step, &(*final_lp)[i], &prob);
+                    update_centers_average(sums, denoms, cells[i], prob);
+                }
+            } else {
+                iteration_in_parallel(method, cells, centers, log_prior, temp_step, params.inner_threads, final_lp, &sums, &denoms, &log_binom_loss);
             }
             total_log_loss = log_binom_loss;
             log_loss_change = log_binom_loss - last_log_loss;

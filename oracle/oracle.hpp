@@ -72,6 +72,9 @@ struct Params {
     // oracle-only knob (not in the reference): cap on iterations per solve so a
     // bounded CPU-baseline sample can be timed.  1000 = reference behaviour.
     int iteration_cap = 1000;
+    // oracle-only knob: > 1 evaluates one iteration's independent chains on that many threads (bit-identical to the serial loop; see
+    // iteration_in_parallel in oracle.cpp).  1 = the reference's loop as written.
+    int inner_threads = 1;
 };
 
 struct LoadedData {

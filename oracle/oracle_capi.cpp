@@ -82,7 +82,7 @@ int orc_step(void* dv, int K, int method, int temp_step, float* theta, const int
 
 // one full em()/khm() solve from theta [K][L] (updated in place).  trace_* arrays hold
 // `trace_cap` entries (per-iteration loss / change / temp_step / clusters_above_threshold).
-int orc_solve(void* dv, int K, int method, float* theta, const int* locked, int n_locked, int iteration_cap,
+static int orc_solve_impl(void* dv, int K, int method, float* theta, const int* locked, int n_locked, int iteration_cap, int inner_threads,
               float* log_probs, float* loss, int* iterations, int trace_cap, float* trace_loss, float* trace_change,
               int* trace_temp_step, int* trace_above) {
     LoadedData* d = (LoadedData*)dv;
@@ -91,6 +91,7 @@ int orc_solve(void* dv, int K, int method, float* theta, const int* locked, int 
     Params p;
     p.num_clusters = K;
     p.iteration_cap = iteration_cap;
+    p.inner_threads = inner_threads;
     Trace tr;
     std::vector<std::vector<float>> lp;
     int iters = 0;
@@ -107,6 +108,20 @@ int orc_solve(void* dv, int K, int method, float* theta, const int* locked, int 
         if (trace_above) trace_above[i] = tr.iters[i].clusters_above_threshold;
     }
     return 0;
+}
+
+int orc_solve(void* dv, int K, int method, float* theta, const int* locked, int n_locked, int iteration_cap,
+              float* log_probs, float* loss, int* iterations, int trace_cap, float* trace_loss, float* trace_change,
+              int* trace_temp_step, int* trace_above) {
+    return orc_solve_impl(dv, K, method, theta, locked, n_locked, iteration_cap, 1, log_probs, loss, iterations, trace_cap, trace_loss,
+                          trace_change, trace_temp_step, trace_above);
+}
+// the same with the iteration's independent chains spread over `inner_threads` threads (bit-identical; Params::inner_threads)
+int orc_solve_mt(void* dv, int K, int method, float* theta, const int* locked, int n_locked, int iteration_cap, int inner_threads,
+                 float* log_probs, float* loss, int* iterations, int trace_cap, float* trace_loss, float* trace_change,
+                 int* trace_temp_step, int* trace_above) {
+    return orc_solve_impl(dv, K, method, theta, locked, n_locked, iteration_cap, inner_threads, log_probs, loss, iterations, trace_cap,
+                          trace_loss, trace_change, trace_temp_step, trace_above);
 }
 
 // souporcell_main without the TSV print.  Returns 0 ok, 1 if nothing beat -inf (no best), <0 error.

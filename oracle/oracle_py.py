@@ -134,8 +134,9 @@ class OracleData:
         lib().orc_step(self._h, K, method, temp_step, _p(th), _p(lk), lk.size, _p(lp), _p(w), _p(lse), C.byref(loss))
         return dict(theta_out=th, log_probs=lp, weights=w, lse=lse, loss=np.float32(loss.value))
 
-    def solve(self, theta, method=0, locked=(), iteration_cap=1000):
-        """One em()/khm() call (S:189 / S:280) from theta [K][L]."""
+    def solve(self, theta, method=0, locked=(), iteration_cap=1000, inner_threads=1):
+        """One em()/khm() call (S:189 / S:280) from theta [K][L].  inner_threads > 1: the iteration's independent chains run
+        concurrently (bit-identical to the serial loop; for the full-size parity tests)."""
         th = np.array(theta, dtype=np.float32, order="C", copy=True)
         K = th.shape[0]
         lp = np.empty((self.n_cells, K), dtype=np.float32)
@@ -147,8 +148,8 @@ class OracleData:
         tt = np.empty(cap, dtype=np.int32)
         ta = np.empty(cap, dtype=np.int32)
         lk = np.ascontiguousarray(list(locked), dtype=np.int32)
-        lib().orc_solve(self._h, K, method, _p(th), _p(lk), lk.size, iteration_cap, _p(lp), C.byref(loss), C.byref(iters), cap,
-                        _p(tl), _p(tc), _p(tt), _p(ta))
+        lib().orc_solve_mt(self._h, K, method, _p(th), _p(lk), lk.size, iteration_cap, max(1, int(inner_threads)), _p(lp), C.byref(loss),
+                           C.byref(iters), cap, _p(tl), _p(tc), _p(tt), _p(ta))
         n = iters.value
         return dict(theta=th, log_probs=lp, loss=np.float32(loss.value), iterations=n,
                     trace=[(int(tt[i]), np.float32(tl[i]), np.float32(tc[i]), int(ta[i])) for i in range(n)])

@@ -180,20 +180,8 @@ class CellCSR:
 MTX_RAW = 2
 
 
-def load_mtx(alt_path, ref_path, min_alt=4, min_ref=4, min_alt_umis=0, min_ref_umis=0, raw=False, cache=None) -> CellCSR:
-    """load_cell_data S:601-681 (defaults S:764-767, 811-816); raw=True: troublet's view of the files (SOUP_MTX_RAW).
-    `cache`: path of a .soupcsr file — read if present (and built with the same filter), else written after the text parse."""
+def _mtx_to_csr(m) -> "CellCSR":
     L = lib()
-    m = C.POINTER(_Mtx)()
-    flags = MTX_RAW if raw else 0
-    L.soup_mtx_load_cache.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.POINTER(_Mtx))]
-    L.soup_mtx_save.argtypes = [C.POINTER(_Mtx), C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
-    if cache is not None and os.path.exists(cache):
-        _check(L.soup_mtx_load_cache(os.fsencode(cache), min_alt, min_ref, min_alt_umis, min_ref_umis, flags, C.byref(m)))
-    else:
-        _check(L.soup_mtx_load(os.fsencode(alt_path), os.fsencode(ref_path), min_alt, min_ref, min_alt_umis, min_ref_umis, flags, C.byref(m)))
-        if cache is not None:
-            _check(L.soup_mtx_save(m, os.fsencode(cache), min_alt, min_ref, min_alt_umis, min_ref_umis, flags))
     try:
         s = m.contents
         n, nnz, nl = int(s.n_cells), int(s.nnz), int(s.n_loci)
@@ -202,6 +190,46 @@ def load_mtx(alt_path, ref_path, min_alt=4, min_ref=4, min_alt_umis=0, min_ref_u
                        cp(s.alt, nnz, np.uint32), cp(s.ref, nnz, np.uint32), cp(s.index_to_locus, nl, np.uint64))
     finally:
         L.soup_mtx_free(m)
+
+
+def _cache_argtypes(L):
+    L.soup_mtx_load_cache.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.POINTER(_Mtx))]
+    L.soup_mtx_save.argtypes = [C.POINTER(_Mtx), C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+
+
+def load_mtx_cache(cache, alt_path, ref_path, min_alt=4, min_ref=4, min_alt_umis=0, min_ref_umis=0, raw=False) -> "CellCSR":
+    """soup_mtx_load_cache: the matrix stored in the .soupcsr file `cache`, which must have been built with this filter from these
+    very alt / ref files (size, mtime and content fingerprint) — SoupError otherwise."""
+    L = lib()
+    _cache_argtypes(L)
+    m = C.POINTER(_Mtx)()
+    _check(L.soup_mtx_load_cache(os.fsencode(cache), os.fsencode(alt_path), os.fsencode(ref_path), min_alt, min_ref, min_alt_umis, min_ref_umis,
+                                 MTX_RAW if raw else 0, C.byref(m)))
+    return _mtx_to_csr(m)
+
+
+def load_mtx(alt_path, ref_path, min_alt=4, min_ref=4, min_alt_umis=0, min_ref_umis=0, raw=False, cache=None) -> CellCSR:
+    """load_cell_data S:601-681 (defaults S:764-767, 811-816); raw=True: troublet's view of the files (SOUP_MTX_RAW).
+    `cache`: path of a .soupcsr file — read if present and built with the same filter from these very files (size / mtime / content
+    fingerprint), else (re)written after the text parse, exactly as `souporcell --csr_cache` does."""
+    L = lib()
+    _cache_argtypes(L)
+    m = C.POINTER(_Mtx)()
+    flags = MTX_RAW if raw else 0
+    a, r = os.fsencode(alt_path), os.fsencode(ref_path)
+    hit = False
+    if cache is not None and os.path.exists(cache):
+        rc = L.soup_mtx_load_cache(os.fsencode(cache), a, r, min_alt, min_ref, min_alt_umis, min_ref_umis, flags, C.byref(m))
+        if rc == ERR_INVALID:      # another filter, other source matrices or an older layout: rebuild it
+            m = C.POINTER(_Mtx)()
+        else:
+            _check(rc)
+            hit = True
+    if not hit:
+        _check(L.soup_mtx_load(a, r, min_alt, min_ref, min_alt_umis, min_ref_umis, flags, C.byref(m)))
+        if cache is not None:
+            _check(L.soup_mtx_save(m, os.fsencode(cache), a, r, min_alt, min_ref, min_alt_umis, min_ref_umis, flags))
+    return _mtx_to_csr(m)
 
 
 def load_barcodes(path):

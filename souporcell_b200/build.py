@@ -30,6 +30,7 @@ NVCC_FLAGS = [
 ]
 # Compile-time experiments (e.g. SOUP_NVCC_DEFINES="-DSOUP_E_FASTBATCH=1" python -m souporcell_b200.build --force); empty = the measured build.
 NVCC_FLAGS += os.environ.get("SOUP_NVCC_DEFINES", "").split()
+LINK_LIBS = ["-lz"]
 LIB_SOURCES = ["soup_device.cu", "host_loader.cpp", "host_util.cpp", "soup_driver.cpp"]
 LIB_HEADERS = ["soup_kernels.cuh", "troublet_kernels.cuh", "soup_common.hpp", "host_parallel.hpp", "glibc_flt32.h", os.path.join("..", "..", "include", "soupgpu.h")]
 
@@ -49,12 +50,27 @@ def _run(cmd, cwd=None):
     return proc.stdout
 
 
+FLAGS_STAMP = LIB + ".flags"
+
+
+def _flags_changed() -> bool:
+    """The effective nvcc command line is part of the staleness check: a library built with SOUP_NVCC_DEFINES (an experiment) must not
+    survive into a plain build, test or bench run, and changing the defines must take effect without --force."""
+    try:
+        with open(FLAGS_STAMP) as fh:
+            return fh.read() != " ".join(NVCC_FLAGS)
+    except OSError:
+        return True
+
+
 def build_lib(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in LIB_SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in LIB_HEADERS]
-    if force or _newer(LIB, deps):
+    if force or _newer(LIB, deps) or _flags_changed():
         os.makedirs(LIB_DIR, exist_ok=True)
-        _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + ["-lz"])
+        _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs + LINK_LIBS)
+        with open(FLAGS_STAMP, "w") as fh:
+            fh.write(" ".join(NVCC_FLAGS))
     return LIB
 
 

@@ -237,8 +237,10 @@ inline bool ref_line(const char*& p, const char* end, uint64_t* v) {   // only t
     return next_token(q, e, tb, te) && next_token(q, e, tb, te) && next_token(q, e, tb, te) && parse_u64(tb, te, v) && *v <= UINT32_MAX;
 }
 
+// `raw` (troublet's view, T:312-320): locus and cell are read from the REF line too and must equal the alt line's — the reference
+// asserts "allele matrices do not match"; souporcell itself never looks at them (S:622-626).
 void parse_chunk(const Mapped& A, const Mapped& R, const Chunk& ch, uint64_t total_loci, uint64_t total_cells,
-                 uint32_t* locus, uint32_t* cell, uint32_t* alt, uint32_t* ref, Tally& t, ParseError* err) {
+                 uint32_t* locus, uint32_t* cell, uint32_t* alt, uint32_t* ref, Tally& t, ParseError* err, bool raw) {
     const char* ap = A.p + ch.a_begin;
     const char* rp = R.p + ch.r_begin;
     const char* aend = A.p + A.n;
@@ -246,7 +248,13 @@ void parse_chunk(const Mapped& A, const Mapped& R, const Chunk& ch, uint64_t tot
     for (uint64_t i = 0; i < ch.n_lines; ++i) {
         uint64_t l, c, av, rv;
         if (!alt_line(ap, aend, &l, &c, &av)) { err->set(SOUP_ERR_INVALID, "alt mtx: malformed entry line (reference panics on unwrap)"); return; }
-        if (!ref_line(rp, rend, &rv)) { err->set(SOUP_ERR_INVALID, "ref mtx: malformed entry line (reference panics on unwrap)"); return; }
+        if (!raw) {
+            if (!ref_line(rp, rend, &rv)) { err->set(SOUP_ERR_INVALID, "ref mtx: malformed entry line (reference panics on unwrap)"); return; }
+        } else {
+            uint64_t rl, rc;
+            if (!alt_line(rp, rend, &rl, &rc, &rv)) { err->set(SOUP_ERR_INVALID, "ref mtx: malformed entry line (reference panics on unwrap)"); return; }
+            if (rl != l || rc != c) { err->set(SOUP_ERR_INVALID, "allele matrices do not match"); return; }
+        }
         if (l == 0 || l - 1 >= total_loci) { err->set(SOUP_ERR_INVALID, "assertion failed: locus < total_loci"); return; }
         if (c == 0 || c - 1 >= total_cells) { err->set(SOUP_ERR_INVALID, "assertion failed: cell < total_cells"); return; }
         const uint64_t o = ch.first_line + i;
@@ -348,7 +356,7 @@ extern "C" int32_t soup_mtx_load(const char* alt_path, const char* ref_path, uin
         std::atomic<size_t> next{0};
         parallel_for(nworkers, nworkers, [&](size_t) {   // the workers share the chunk queue
             for (size_t i; (i = next.fetch_add(1)) < nchunks && !err.code.load();)
-                parse_chunk(A, R, chunks[i], total_loci, total_cells, c_locus.get(), c_cell.get(), c_alt.get(), c_ref.get(), tally, &err);
+                parse_chunk(A, R, chunks[i], total_loci, total_cells, c_locus.get(), c_cell.get(), c_alt.get(), c_ref.get(), tally, &err, (flags & SOUP_MTX_RAW) != 0);
         });
         if (err.code.load()) { set_thread_error("%s", err.msg); return err.code.load(); }
     }
@@ -486,23 +494,53 @@ SOUP_CATCH_RETURN("soup_mtx_load")
 // text matrices again) skip the text parse.  Little-endian, 64-byte header, then the five arrays back to back.
 namespace {
 struct CacheHeader {
-    char magic[8];            // "SOUPCSR1"
+    char magic[8];            // "SOUPCSR2"
     uint64_t n_cells, n_loci_total, n_loci, nnz;
     uint32_t min_alt, min_ref, min_alt_umis, min_ref_umis;   // the filter the matrix was built with (S:659)
     uint32_t flags;           // SOUP_MTX_RAW or 0
     uint32_t reserved;
+    // the two text matrices the cache was parsed from (alt, ref): size, modification time, and a hash of their ends — a cache file
+    // reused for OTHER matrices would otherwise print a clusters TSV for the wrong data without a word
+    uint64_t src_size[2], src_mtime_ns[2], src_hash[2];
+    uint64_t pad[2];
 };
-static_assert(sizeof(CacheHeader) == 64, "cache header layout");
+static_assert(sizeof(CacheHeader) == 128, "cache header layout");
+
+// size / mtime / FNV-1a of the first and last 64 KB (+ the size): cheap, and enough to tell two vartrix outputs apart
+bool fingerprint(const char* path, uint64_t* size, uint64_t* mtime_ns, uint64_t* hash) {
+    struct stat st;
+    if (stat(path, &st) != 0) return false;
+    *size = (uint64_t)st.st_size;
+    *mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const unsigned char* b, size_t n) { for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+    std::vector<unsigned char> buf(64 * 1024);
+    size_t got = fread(buf.data(), 1, buf.size(), f);
+    mix(buf.data(), got);
+    if (*size > buf.size()) {
+        const uint64_t off = *size > 2 * buf.size() ? *size - buf.size() : buf.size();
+        if (fseeko(f, (off_t)off, SEEK_SET) == 0) { got = fread(buf.data(), 1, buf.size(), f); mix(buf.data(), got); }
+    }
+    fclose(f);
+    mix((const unsigned char*)size, sizeof(*size));
+    *hash = h;
+    return true;
+}
 }  // namespace
 
-extern "C" int32_t soup_mtx_save(const soup_mtx* m, const char* path, uint32_t min_alt, uint32_t min_ref, uint32_t min_alt_umis,
-                                 uint32_t min_ref_umis, uint32_t flags) try {
-    if (!m || !path) { set_thread_error("soup_mtx_save: bad argument"); return SOUP_ERR_INVALID; }
+extern "C" int32_t soup_mtx_save(const soup_mtx* m, const char* path, const char* alt_path, const char* ref_path, uint32_t min_alt, uint32_t min_ref,
+                                 uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags) try {
+    if (!m || !path || !alt_path || !ref_path) { set_thread_error("soup_mtx_save: bad argument"); return SOUP_ERR_INVALID; }
     const std::string tmp = std::string(path) + ".tmp";
     FILE* f = fopen(tmp.c_str(), "wb");
     if (!f) { set_thread_error("soup_mtx_save: cannot create %s", tmp.c_str()); return SOUP_ERR_IO; }
     CacheHeader h{};
-    memcpy(h.magic, "SOUPCSR1", 8);
+    memcpy(h.magic, "SOUPCSR2", 8);
+    const char* src[2] = {alt_path, ref_path};
+    for (int i = 0; i < 2; ++i)
+        if (!fingerprint(src[i], &h.src_size[i], &h.src_mtime_ns[i], &h.src_hash[i])) { fclose(f); remove(tmp.c_str()); set_thread_error("soup_mtx_save: cannot read %s", src[i]); return SOUP_ERR_IO; }
     h.n_cells = m->n_cells; h.n_loci_total = m->n_loci_total; h.n_loci = m->n_loci; h.nnz = m->nnz;
     h.min_alt = min_alt; h.min_ref = min_ref; h.min_alt_umis = min_alt_umis; h.min_ref_umis = min_ref_umis; h.flags = flags & SOUP_MTX_RAW;
     bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
@@ -515,16 +553,27 @@ extern "C" int32_t soup_mtx_save(const soup_mtx* m, const char* path, uint32_t m
 }
 SOUP_CATCH_RETURN("soup_mtx_save")
 
-extern "C" int32_t soup_mtx_load_cache(const char* path, uint32_t min_alt, uint32_t min_ref, uint32_t min_alt_umis, uint32_t min_ref_umis,
-                                       uint32_t flags, soup_mtx** out) try {
-    if (!path || !out) { set_thread_error("soup_mtx_load_cache: bad argument"); return SOUP_ERR_INVALID; }
+extern "C" int32_t soup_mtx_load_cache(const char* path, const char* alt_path, const char* ref_path, uint32_t min_alt, uint32_t min_ref,
+                                       uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags, soup_mtx** out) try {
+    if (!path || !out || !alt_path || !ref_path) { set_thread_error("soup_mtx_load_cache: bad argument"); return SOUP_ERR_INVALID; }
     *out = nullptr;
     Mapped F;
     if (!F.open(path)) { set_thread_error("cannot open %s", path); return SOUP_ERR_IO; }
     if (F.n < sizeof(CacheHeader)) { set_thread_error("%s: not a .soupcsr file", path); return SOUP_ERR_INVALID; }
     CacheHeader h;
     memcpy(&h, F.p, sizeof(h));
-    if (memcmp(h.magic, "SOUPCSR1", 8) != 0) { set_thread_error("%s: not a .soupcsr file", path); return SOUP_ERR_INVALID; }
+    if (memcmp(h.magic, "SOUPCSR2", 8) != 0) { set_thread_error("%s: not a .soupcsr file (or an older layout)", path); return SOUP_ERR_INVALID; }
+    {   // the cache must have been parsed from THESE two matrices
+        const char* src[2] = {alt_path, ref_path};
+        for (int i = 0; i < 2; ++i) {
+            uint64_t sz = 0, mt = 0, hs = 0;
+            if (!fingerprint(src[i], &sz, &mt, &hs)) { set_thread_error("cannot open %s", src[i]); return SOUP_ERR_IO; }
+            if (sz != h.src_size[i] || mt != h.src_mtime_ns[i] || hs != h.src_hash[i]) {
+                set_thread_error("%s was built from another %s matrix than %s (size / mtime / content differ)", path, i == 0 ? "alt" : "ref", src[i]);
+                return SOUP_ERR_INVALID;
+            }
+        }
+    }
     if (h.min_alt != min_alt || h.min_ref != min_ref || h.min_alt_umis != min_alt_umis || h.min_ref_umis != min_ref_umis || h.flags != (flags & SOUP_MTX_RAW)) {
         set_thread_error("%s was built with another filter (min_alt %u min_ref %u min_alt_umis %u min_ref_umis %u raw %u)", path, h.min_alt, h.min_ref,
                          h.min_alt_umis, h.min_ref_umis, h.flags);

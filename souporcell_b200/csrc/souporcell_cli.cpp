@@ -198,14 +198,14 @@ int main(int argc, char** argv) {
         FILE* probe = fopen(cache.c_str(), "rb");
         if (probe) {
             fclose(probe);
-            if (soup_mtx_load_cache(cache.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, &m) == SOUP_OK) from_cache = true;
+            if (soup_mtx_load_cache(cache.c_str(), alt_mtx.c_str(), ref_mtx.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, &m) == SOUP_OK) from_cache = true;
             else fprintf(stderr, "csr_cache ignored: %s\n", soup_last_error(nullptr));
         }
     }
     if (!from_cache) {
         if (soup_mtx_load(alt_mtx.c_str(), ref_mtx.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0, &m) != SOUP_OK)
             die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
-        if (!cache.empty() && soup_mtx_save(m, cache.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0) != SOUP_OK)
+        if (!cache.empty() && soup_mtx_save(m, cache.c_str(), alt_mtx.c_str(), ref_mtx.c_str(), min_alt, min_ref, min_alt_umis, min_ref_umis, 0) != SOUP_OK)
             fprintf(stderr, "csr_cache not written: %s\n", soup_last_error(nullptr));
     }
     fprintf(stderr, "total loci used %llu\n", (unsigned long long)m->n_loci);   // S:678

@@ -237,8 +237,9 @@ def test_known_genotypes_init_matches_oracle(tmp_path, gz):
 
 
 def test_gz_input_and_binary_cache_roundtrip(tmp_path):
-    """`.mtx.gz` inputs parse like the plain files, and a `.soupcsr` cache gives back exactly the parsed matrix
-    (and refuses to be used for another filter, or when damaged)."""
+    """`.mtx.gz` inputs parse like the plain files, and a `.soupcsr` cache gives back exactly the parsed matrix — and
+    refuses to be used for another filter, for OTHER alt / ref matrices than it was built from, or when damaged (`load_mtx(cache=)`
+    and `souporcell --csr_cache` then rebuild it instead of printing results for the wrong data)."""
     import gzip
     import shutil
     v = synth.generate(n_cells=120, n_loci=900, k=3, mean_loci=60, seed=5)
@@ -255,21 +256,42 @@ def test_gz_input_and_binary_cache_roundtrip(tmp_path):
     cache = str(tmp_path / "m.soupcsr")
     first = sp.load_mtx(alt, ref, cache=cache)                     # parses the text, writes the cache
     assert os.path.exists(cache) and same(plain, first)
-    os.remove(alt); os.remove(ref)
-    again = sp.load_mtx(alt, ref, cache=cache)                     # the text files are gone: this is the cache
-    assert same(plain, again)
-    with pytest.raises(sp.SoupError):
-        sp.load_mtx(alt, ref, min_alt=6, cache=cache)              # built with another filter
+    assert same(plain, sp.load_mtx_cache(cache, alt, ref))         # the cache itself
+    assert same(plain, sp.load_mtx(alt, ref, cache=cache))
+    with pytest.raises(sp.SoupError, match="another filter"):
+        sp.load_mtx_cache(cache, alt, ref, min_alt=6)
     raw_cache = str(tmp_path / "raw.soupcsr")
     raw = sp.load_mtx(alt + ".gz", ref + ".gz", raw=True, cache=raw_cache)
-    assert raw.nnz == v.nnz and same(raw, sp.load_mtx(alt, ref, raw=True, cache=raw_cache))
+    assert raw.nnz == v.nnz and same(raw, sp.load_mtx_cache(raw_cache, alt + ".gz", ref + ".gz", raw=True))
     with pytest.raises(sp.SoupError):
-        sp.load_mtx(alt, ref, cache=raw_cache)                     # RAW view asked for as the filtered one
+        sp.load_mtx_cache(raw_cache, alt + ".gz", ref + ".gz")     # RAW view asked for as the filtered one
+    # a cache reused for other matrices (the advisor's reproduction): rejected, and load_mtx(cache=) returns the NEW data
+    other = tmp_path / "other"
+    v2 = synth.generate(n_cells=120, n_loci=900, k=3, mean_loci=60, seed=6)
+    alt2, ref2, _ = synth.write_files(v2, str(other))
+    plain2 = sp.load_mtx(alt2, ref2)
+    assert not same(plain, plain2)
+    with pytest.raises(sp.SoupError, match="built from another"):
+        sp.load_mtx_cache(cache, alt2, ref2)
+    with pytest.raises(sp.SoupError, match="built from another"):
+        sp.load_mtx_cache(cache, alt, ref2)                        # only the ref matrix differs
+    assert same(plain2, sp.load_mtx(alt2, ref2, cache=cache))      # rebuilt, not reused
+    assert same(plain2, sp.load_mtx_cache(cache, alt2, ref2))
+    with pytest.raises(sp.SoupError):
+        sp.load_mtx_cache(cache, alt, ref)                         # ... and now it belongs to the second pair
+    # a rewritten source file of the same size: the modification time / content hash differ
+    data = open(alt2, "rb").read()
+    os.utime(alt2, ns=(os.stat(alt2).st_atime_ns, os.stat(alt2).st_mtime_ns + 5_000_000_000))
+    with pytest.raises(sp.SoupError, match="built from another"):
+        sp.load_mtx_cache(cache, alt2, ref2)
+    assert open(alt2, "rb").read() == data
+    assert same(plain2, sp.load_mtx(alt2, ref2, cache=cache))
     blob = bytearray(open(cache, "rb").read())
     with open(cache, "wb") as fh:
         fh.write(blob[:-8])                                        # truncated
     with pytest.raises(sp.SoupError):
-        sp.load_mtx(alt, ref, cache=cache)
+        sp.load_mtx_cache(cache, alt2, ref2)
+    assert same(plain2, sp.load_mtx(alt2, ref2, cache=cache))
 
 
 def test_header_is_plain_c_and_ctypes_mirrors_match_its_layout(tmp_path):

@@ -137,3 +137,24 @@ def test_solve_structure_invariants():
         assert so["theta"].min() >= np.float32(0.01) and so["theta"].max() <= np.float32(0.99)
         capped = d.solve(th0, method=m, iteration_cap=5)
         assert capped["iterations"] == 5
+
+
+def test_inner_threads_are_bit_identical_to_the_serial_loop():
+    """The oracle's multi-threaded iteration (Params::inner_threads, used by the full-size parity tests) evaluates the reference's own
+    per-cell and per-(cluster, locus) chains concurrently: every bit of the trace, the log-probabilities and the centers must equal
+    the serial loop of S:225-243, for EM and KHM, with locked clusters, for any thread count."""
+    from souporcell_b200 import synth
+    v = synth.generate(n_cells=400, n_loci=2500, k=5, mean_loci=150, seed=31)
+    row_ptr, locus, alt, ref, i2l = synth.filter_to_csr(v)
+    od = orc.OracleData.from_csr(v.n_cells, int(i2l.shape[0]), row_ptr, locus, alt, ref)
+    rng = np.random.default_rng(5)
+    th0 = np.clip(rng.random((5, int(i2l.shape[0])), dtype=np.float32), 1e-4, 0.9999).astype(np.float32)
+    for method in (0, 1):
+        for locked in ((), (1, 3)):
+            want = od.solve(th0, method=method, locked=locked, iteration_cap=25)
+            for nt in (2, 3, 8):
+                got = od.solve(th0, method=method, locked=locked, iteration_cap=25, inner_threads=nt)
+                assert got["iterations"] == want["iterations"]
+                assert [(t[0], np.float32(t[1]).tobytes(), np.float32(t[2]).tobytes(), t[3]) for t in got["trace"]] == \
+                       [(t[0], np.float32(t[1]).tobytes(), np.float32(t[2]).tobytes(), t[3]) for t in want["trace"]]
+                assert got["theta"].tobytes() == want["theta"].tobytes() and got["log_probs"].tobytes() == want["log_probs"].tobytes()

@@ -92,6 +92,20 @@ def test_clusters_loader_and_raw_matrix(dataset):
     assert np.array_equal(raw.locus, v.locus[order].astype(np.uint32)) and np.array_equal(raw.alt, v.alt[order]) and np.array_equal(raw.ref, v.ref[order])
 
 
+def test_raw_view_asserts_that_the_two_matrices_match(dataset, tmp_path):
+    """T:315-320: troublet takes locus and cell from the REF line and asserts they equal the alt line's ("allele matrices do not
+    match"); souporcell itself reads them from the alt line only (S:622-626), so the filtered view must keep accepting such files."""
+    lines = open(dataset["ref"]).read().splitlines()
+    tok = lines[5].split()
+    for which, repl in (("locus", f"{int(tok[0]) + 1} {tok[1]} {tok[2]}"), ("cell", f"{tok[0]} {int(tok[1]) % dataset['v'].n_cells + 1} {tok[2]}")):
+        bad = str(tmp_path / f"ref_bad_{which}.mtx")
+        with open(bad, "w") as fh:
+            fh.write("\n".join(lines[:5] + [repl] + lines[6:]) + "\n")
+        with pytest.raises(sp.SoupError, match="allele matrices do not match"):
+            sp.load_mtx(dataset["alt"], bad, raw=True)
+        assert sp.load_mtx(dataset["alt"], bad).nnz == sp.load_mtx(dataset["alt"], dataset["ref"]).nnz
+
+
 def test_oracle_calls_doublets_and_iterates(dataset):
     v = dataset["v"]
     got = oracle_run(dataset["alt"], dataset["ref"], dataset["clusters"], v.n_cells, 4)
