@@ -104,27 +104,28 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
 
     for (int run = 0; run < 3; ++run) {          // S:70
         int n_bad = 0;
-        if (have_best || run == 0) {
-            if (cell_mode && K >= 16 && run > 0) {
-                // the cluster sizes S:156-162 over ALL cells: add the cell group's counts up (host all-gather, K u64 per process)
-                std::vector<uint64_t> mine((size_t)K, 0);
-                count_cluster_cells(r->best_log_probs, have_best ? n_cells : 0, K, mine.data());
-                int32_t group = p->cell_group_size > 0 ? p->cell_group_size : 1;
-                std::vector<uint64_t> all((size_t)K * group, 0);
-                int32_t e = p->cell_allgather(p->cell_comm_user, mine.data(), all.data(), (uint64_t)K * sizeof(uint64_t));
-                if (e != SOUP_OK) { set_thread_error("soup_main: the cell_allgather callback failed (%d)", e); return e; }
-                for (int32_t g = 1; g < group; ++g)
-                    for (int c = 0; c < K; ++c) all[c] += all[(size_t)g * K + c];
-                n_bad = bad_clusters_from_counts(run, K, all.data(), bad.data(), log);
-            } else {
-                n_bad = soup_bad_cluster_detection(run, K, r->best_log_probs, have_best ? n_cells : 0, bad.data(), log);
-            }
+        if (cell_mode && K >= 16 && run > 0) {
+            // the cluster sizes S:156-162 over ALL cells: add the cell group's counts up (host all-gather, K u64 per process)
+            std::vector<uint64_t> mine((size_t)K, 0);
+            count_cluster_cells(r->best_log_probs, have_best ? n_cells : 0, K, mine.data());
+            int32_t group = p->cell_group_size > 0 ? p->cell_group_size : 1;
+            std::vector<uint64_t> all((size_t)K * group, 0);
+            int32_t e = p->cell_allgather(p->cell_comm_user, mine.data(), all.data(), (uint64_t)K * sizeof(uint64_t));
+            if (e != SOUP_OK) { set_thread_error("soup_main: the cell_allgather callback failed (%d)", e); return e; }
+            for (int32_t g = 1; g < group; ++g)
+                for (int c = 0; c < K; ++c) all[c] += all[(size_t)g * K + c];
+            n_bad = bad_clusters_from_counts(run, K, all.data(), bad.data(), log);
         } else {
-            // S:93 would index an empty best_cluster_centers and panic
+            // (K < 16 or run 0: an empty list, S:151-153 — also when no solve was finite, where the reference just ends the runs)
+            n_bad = soup_bad_cluster_detection(run, K, r->best_log_probs, have_best ? n_cells : 0, bad.data(), log);
+        }
+        if (n_bad < 0) return n_bad;
+        if (run > 0 && n_bad > 0 && !have_best && n_solves > 0) {
+            // S:93-95 copies the EMPTY best_cluster_centers and indexes it with the flagged clusters (K >= 16 flags some even with no
+            // cell assigned): the reference panics as soon as a solve of this run starts
             set_thread_error("souporcell3 run %d: no finite solve in the previous run (the reference panics here)", run + 1);
             return SOUP_ERR_INVALID;
         }
-        if (n_bad < 0) return n_bad;
         if (run != 0 && n_bad == 0) {            // S:73-76
             if (log) fprintf(log, "No outliers detected on run %d!, Exiting.\n", run + 1);
             break;
@@ -166,7 +167,10 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             if (c.rc == SOUP_OK) soup_get_stats(ctxs[i], &c.stats);
         };
         const auto tw0 = std::chrono::steady_clock::now();
-        if (n_ctx == 1) work(0);
+        if (n_solves == 0) {
+            // --restarts 0: S:81 runs no solve, every thread reports -inf, the TSV is empty (S:142 zips over no rows) and the exit is clean
+            for (auto& c : pc) { c.res.has_best = 0; c.res.best_solve = -1; c.res.best_loss = -INFINITY; }
+        } else if (n_ctx == 1) work(0);
         else {
             std::vector<std::thread> pool;
             for (int i = 0; i < n_ctx; ++i) pool.emplace_back(work, i);

@@ -1,5 +1,7 @@
 """GPU parity: libsoupgpu (through the C ABI) vs the CPU oracle on identical seeded inputs.
 Bit-exact (np.array_equal on the raw f32 bits) unless stated otherwise."""
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -296,6 +298,24 @@ def test_cli_end_to_end_matches_oracle_cli(tmp_path):
         assert ours.stdout == theirs.stdout and ours.stdout.count("\n") == v.n_cells
         pick = lambda s: sorted(l for l in s.splitlines() if l.startswith(("binomial", "total loci", "best total", "thread ")))
         assert pick(ours.stderr) == pick(theirs.stderr)
+
+
+def test_cli_no_restarts_and_no_outlier_edge_cases(tmp_path):
+    """--restarts 0 (S:63 -> 0 solves per thread): no solve runs, `best total log probability = -inf`, an empty TSV and a clean exit,
+    with and without souporcell3 (k < 16: "No outliers detected on run 2!"; k >= 16: clusters are flagged on every run, but S:93 is
+    never reached because no solve starts) — byte for byte what the oracle CLI prints."""
+    from souporcell_b200 import build, synth
+    v = synth.generate(n_cells=60, n_loci=500, k=3, mean_loci=40, seed=2)
+    alt, ref, bc = synth.write_files(v, str(tmp_path))
+    for extra in (["-k", "3", "--restarts", "0"], ["-k", "3", "--restarts", "0", "-s", "true"], ["-k", "16", "--restarts", "0", "-s", "true", "-m", "khm"]):
+        args = ["-a", alt, "-r", ref, "-b", bc] + extra
+        ours = subprocess.run([build.CLI] + args, capture_output=True, text=True)
+        theirs = subprocess.run([orc.CLI_PATH] + args, capture_output=True, text=True)
+        assert ours.returncode == 0 and theirs.returncode == 0, ours.stderr[-500:]
+        assert ours.stdout == theirs.stdout == ""
+        keep = lambda s: [l for l in s.splitlines() if not l.startswith(("oracle_timing", "soup_"))]
+        assert keep(ours.stderr) == keep(theirs.stderr)
+        assert "best total log probability = -inf" in ours.stderr
 
 
 def test_full_size_properties_config2():
