@@ -407,19 +407,22 @@ def test_loader_multichunk_irregular_lines_any_thread_count(tmp_path):
     forms = ["{l} {c} {x}\n", "{l}\t{c}\t{x}\n", "  {l}   {c}  {x}  \n", "+{l} +{c} +{x}\n", "{l} {c} {x}\r\n", "{l} {c} {x} trailing tokens 9\n",
              "0000000000{l} {c} 000000000000{x}\n", "{l} {c} {x}\t\r\n"]
     kind = np.where(rng.random(n) < 0.02, rng.integers(1, len(forms), n), 0)
-    with open(tmp_path / "alt.mtx", "w", newline="") as fa, open(tmp_path / "ref.mtx", "w", newline="") as fr:
-        for fh in (fa, fr):
+    # ref_t.mtx: the same matrix without the junk tokens — troublet parses the ref line's locus and cell too (T:315-320)
+    with open(tmp_path / "alt.mtx", "w", newline="") as fa, open(tmp_path / "ref.mtx", "w", newline="") as fr, open(tmp_path / "ref_t.mtx", "w", newline="") as ft:
+        for fh in (fa, fr, ft):
             fh.write("%%MatrixMarket matrix coordinate real general\n% irregular\n")
             fh.write(f"{v.n_loci} {v.n_cells} {n}\n")
         for i in range(n):
             fa.write(forms[kind[i]].format(l=lo[i] + 1, c=ce[i] + 1, x=al[i]))
+            ft.write(forms[kind[i]].format(l=lo[i] + 1, c=ce[i] + 1, x=rf[i]))
             if kind[i] == 5:
                 fr.write(f"junk -7.5e3 {rf[i]}\n")                 # only the third ref token is ever parsed (S:625)
             else:
                 fr.write(forms[kind[i]].format(l=lo[i] + 1, c=ce[i] + 1, x=rf[i]))
         fa.write(f"{lo[0] + 1} {ce[0] + 1} {al[0]}")               # no newline at the end of either file: still a line
         fr.write(f"{lo[0] + 1} {ce[0] + 1} {rf[0]}")
-    alt, ref = str(tmp_path / "alt.mtx"), str(tmp_path / "ref.mtx")
+        ft.write(f"{lo[0] + 1} {ce[0] + 1} {rf[0]}")
+    alt, ref, ref_t = str(tmp_path / "alt.mtx"), str(tmp_path / "ref.mtx"), str(tmp_path / "ref_t.mtx")
     ex = orc.OracleData.from_mtx(alt, ref, 3, 3).export()
     old = os.environ.get("SOUP_LOADER_THREADS")
     try:
@@ -431,7 +434,7 @@ def test_loader_multichunk_irregular_lines_any_thread_count(tmp_path):
             m = sp.load_mtx(alt, ref, 3, 3)
             for k in ("row_ptr", "locus", "alt", "ref", "index_to_locus"):
                 assert np.array_equal(getattr(m, k), ex[k]), (threads, k)
-            raw = sp.load_mtx(alt, ref, raw=True)                  # troublet's view: every line, file order inside a cell
+            raw = sp.load_mtx(alt, ref_t, raw=True)                # troublet's view: every line, file order inside a cell
             assert raw.nnz == n + 1 and raw.n_loci == v.n_loci
             order = np.argsort(np.concatenate([ce, ce[:1]]), kind="stable")
             assert np.array_equal(raw.locus, np.concatenate([lo, lo[:1]])[order].astype(raw.locus.dtype)), threads
@@ -441,6 +444,8 @@ def test_loader_multichunk_irregular_lines_any_thread_count(tmp_path):
             os.environ.pop("SOUP_LOADER_THREADS", None)
         else:
             os.environ["SOUP_LOADER_THREADS"] = old
+    with pytest.raises(sp.SoupError):                              # troublet's view unwraps the ref line's first two tokens as well
+        sp.load_mtx(alt, ref, raw=True)
     # a malformed line in a late chunk is still the reference's panic
     bad = open(alt).read().split("\n")
     bad[len(bad) - 10] = "12 x 3"
