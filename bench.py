@@ -40,11 +40,30 @@ METRIC = "E+M nnz-updates/s (clustering hot path)"
 UNIT = "nnz-updates/s"
 
 
+CACHE_DIR = os.environ.get("SOUP_BENCH_CACHE", "/tmp/soupgpu_bench_cache")
+
+
 def workload(config: int):
+    """The filtered CSR of BASELINE config `config` (seeded synthetic vartrix data).  Generating the larger configs takes numpy 20-80 s, so
+    the arrays are kept in a scratch cache: under torchrun local rank 0 writes it and the other ranks wait for the file."""
     c = dict(synth.CONFIGS[config])
-    v = synth.generate_config(config)
-    row_ptr, locus, alt, ref, i2l = synth.filter_to_csr(v)
-    return c, (v.n_cells, int(i2l.shape[0]), row_ptr, locus, alt, ref)
+    path = os.path.join(CACHE_DIR, f"config{config}_seed{synth.BASE_SEED + config}_v2.npz")
+    if not os.path.exists(path):
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            v = synth.generate_config(config)
+            row_ptr, locus, alt, ref, i2l = synth.filter_to_csr(v)
+            os.makedirs(CACHE_DIR, exist_ok=True)
+            tmp = path + f".tmp{os.getpid()}.npz"
+            np.savez(tmp, n_cells=np.int64(v.n_cells), n_loci=np.int64(i2l.shape[0]), row_ptr=row_ptr, locus=locus, alt=alt, ref=ref)
+            os.replace(tmp, path)
+        else:
+            t0 = time.time()
+            while not os.path.exists(path):
+                if time.time() - t0 > 1800:
+                    raise SystemExit("bench.py: timed out waiting for local rank 0 to generate the synthetic matrix")
+                time.sleep(0.5)
+    z = np.load(path)
+    return c, (int(z["n_cells"]), int(z["n_loci"]), z["row_ptr"], z["locus"], z["alt"], z["ref"])
 
 
 def algorithmic_bytes(nnz, K, L, N):
@@ -62,6 +81,21 @@ def profiled_traffic(kernel):
             return json.load(fh)[kernel]["dram_bytes_per_launch"]
     except Exception:
         return None
+
+
+def profiled_limits(kernel, avg_launch_ms):
+    """What the committed ncu --set full capture says binds `kernel` (profiles/ncu_traffic.json): real DRAM GB/s and the share of the L2 -> SM
+    crossbar cap, from a full-occupancy launch; dram_gbs_real_live = the same DRAM bytes over this run's own average launch time."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)[kernel]
+    except Exception:
+        return {}
+    out = {k: d[k] for k in ("dram_gbs_real", "l2_xbar_tbs", "l2_xbar_frac", "issue_active_pct", "capture_launch_us") if k in d}
+    if avg_launch_ms > 0 and "dram_bytes_per_launch" in d:
+        out["dram_gbs_real_live_upper"] = d["dram_bytes_per_launch"] / (avg_launch_ms * 1e-3) / 1e9
+    return out
 
 
 def measured_peak():
@@ -212,7 +246,9 @@ def ours(args):
     torch.cuda.set_stream(stream)                           # so torch.cuda.Event brackets the library's kernels
     ctx = sp.Context(local, stream=stream.cuda_stream)
     ctx.load_csr(*csr)
-    cb = api.torch_exchange_callbacks(dist) if world > 1 else (None, None)
+    # one NCCL communicator inside libsoupgpu per rank: the once-per-run winner exchange of restart sharding and the per-iteration
+    # all-reduce of cell sharding run over it (torch.distributed only carries its 128-byte id and the bench's own barriers)
+    comm = sp.Comm.from_torch(ctx, dist) if world > 1 else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -223,7 +259,7 @@ def ours(args):
 
     def job(time_kernels=False):
         return sp.main(ctx, K, method=method, restarts=restarts, threads=restarts, seed=4, time_kernels=time_kernels,
-                       proc_rank=rank, proc_world=world, allgather=cb[0], bcast=cb[1])
+                       proc_rank=rank, proc_world=world, proc_comm=comm)
 
     def timed(fn):
         flush.zero_()
@@ -291,6 +327,66 @@ def ours(args):
     h2d = (n + 1) * 8 + nnz * 12 + restarts // world * 32
     d2h = n * K * 4 + K * L * 4
 
+    # ---- sub-records: strong scaling of restart sharding (config 3, 100 restarts fixed) and the cell-sharded mode (config-4 shape)
+    subs = {}
+    if not args.no_sub:
+        ctx.close()
+        ctx = None
+        del flush
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+        def sub_leg(config, restarts_total, mode, k=None, steps=2, warm=1):
+            """One fixed job on the whole box.  mode 'restarts': solve s on rank s mod world, no data-path collective.
+            mode 'cells': rank r holds the r-th contiguous cell range, every rank runs every restart, ncclAllReduce of the M-step sums."""
+            scfg, scsr = workload(config)
+            sn, sL, srp, slo, sal, srf = scsr
+            sk = k or scfg["k"]
+            smethod = sp.METHOD_KHM if scfg["method"] == "khm" else sp.METHOD_EM
+            c2 = sp.Context(local, stream=stream.cuda_stream)
+            cm = None
+            try:
+                if mode == "cells" and world > 1:
+                    part = api.split_cells(scsr, world)[1][rank]
+                    c2.load_csr(*part)
+                    cm = sp.Comm.from_torch(c2, dist)
+                    run = lambda: sp.main(c2, sk, method=smethod, restarts=restarts_total, threads=restarts_total, seed=4, cell_comms=[cm], n_cells_global=sn)
+                else:
+                    c2.load_csr(*scsr)
+                    cm = sp.Comm.from_torch(c2, dist) if world > 1 else None
+                    run = lambda: sp.main(c2, sk, method=smethod, restarts=restarts_total, threads=restarts_total, seed=4,
+                                          proc_rank=rank, proc_world=world, proc_comm=cm)
+                for _ in range(warm):
+                    timed(run)
+                ms = upd = 0.0
+                r = None
+                for _ in range(steps):
+                    r, ms_d, _ = timed(run)
+                    ms += ms_d
+                    # cells: every rank counts its own entries (the sum over ranks is the whole matrix); restarts: its own solves
+                    upd += total(r.nnz_updates)
+                st = c2.stats()
+                be_, bm_ = algorithmic_bytes(int(slo.shape[0]), sk, sL, sn)
+                rec = {"value": upd / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warm, "scaling": "strong",
+                       "n_gpus": world, "sharding": mode if world > 1 else "none (one GPU: the base of the strong-scaling curve)",
+                       "workload": f"BASELINE.json configs[{config - 1}] matrix: {scfg['method'].upper()} k={sk}, {sn} cells x {sL} loci used, nnz={int(slo.shape[0])}, "
+                                   f"{restarts_total} restarts in all (fixed as GPUs are added), every restart to convergence",
+                       "best_loss": float(r.best_loss), "solve_iterations": int(total(r.slot_iterations) if mode != "cells" else r.slot_iterations),
+                       "hbm_equiv_frac_per_gpu": upd / (ms * 1e-3) / world * (be_ + bm_) / int(slo.shape[0]) / 1e9 / measured_peak()[0]}
+                if mode == "cells" and world > 1:
+                    iters = max(int(st["estep_launches"]), 1)
+                    rec["allreduce"] = {"bytes_per_rank_per_job": int(st["allreduce_bytes"]), "calls_per_job": int(st["allreduce_calls"]),
+                                        "mean_bytes_per_iteration": int(st["allreduce_bytes"]) / iters,
+                                        "full_width_bytes_per_iteration": (2 * sL * int(st["padded_cols"]) + int(st["slots"])) * 4,
+                                        "note": "one ncclAllReduce per locus range per iteration, overlapped with the M pass; only the live restarts' columns travel"}
+                return rec
+            finally:
+                if cm is not None:
+                    cm.close()
+                c2.close()
+
+        subs["strong"] = sub_leg(3, 100, "restarts")
+        subs["cells"] = sub_leg(4, 8, "cells", k=64)
+
     if rank == 0:
         be, bm = algorithmic_bytes(nnz, K, L, n)
         peak, peak_src = measured_peak()
@@ -307,18 +403,27 @@ def ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(kern), "peak_source": peak_src, "bytes_per_launch": per_launch_bytes,
+                         "measured_limiter": "l2_gather+issue",
+                         "limiter_note": "achieved/peak is an HBM-EQUIVALENT figure (algorithmic un-batched bytes / time).  Batched restarts share one pass over the "
+                                         "matrix, so the real DRAM traffic (dram_gbs_real) is a few percent of HBM; what binds is the L2->SM row-gather path "
+                                         "(l2_xbar_frac of the 6300 B/clk slice cap) and instruction issue (profiles/, DESIGN.md section 4)",
+                         **profiled_limits(kern, k_ms / max(em[2], 1)),
                          "avg_launch_ms": k_ms / max(em[2], 1), "estep_ms": em[0], "mstep_ms": em[1], "launches_timed": em[2],
                          "timing": f"per-launch CUDA events on the launching stream over {args.steps} extra steps of the same job ({ev_ms / args.steps:.2f} ms/step with events)",
                          "whole_step": {"bytes_per_nnz_update": (be + bm) / nnz, "achieved_per_gpu": value / world * (be + bm) / nnz / 1e9,
                                         "frac": value / world * (be + bm) / nnz / 1e9 / peak,
                                         "note": "whole job (all kernels, partial-occupancy tail included) per GPU vs the same peak"}},
         }
+        line.update(subs)
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             rate, desc, _ = run_oracle_sample(csr, cfg, cores, 15.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -345,11 +450,11 @@ def ours_cells(args):
     torch.cuda.set_stream(stream)
     ctx = sp.Context(local, stream=stream.cuda_stream)
     ctx.load_csr(*shard)
-    cb = api.torch_allreduce_callback(dist)
+    comm = sp.Comm.from_torch(ctx, dist)       # NCCL inside libsoupgpu; torch.distributed only carries its id
     seeds = sp.thread_seeds(4, restarts, 0)
 
     def job():
-        return ctx.solve(K, method=method, n_streams=restarts, solves_per_stream=1, stream_seeds=seeds, cell_allreduce=cb, n_cells_global=n)
+        return ctx.solve(K, method=method, n_streams=restarts, solves_per_stream=1, stream_seeds=seeds, cell_comm=comm, n_cells_global=n)
 
     ms = upd = launches = 0.0
     for i in range(args.warmup + args.steps):
@@ -374,8 +479,10 @@ def ours_cells(args):
                 "roofline": {"bound": "hbm", "achieved": value / world * (be + bm) / int(locus.shape[0]) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": value / world * (be + bm) / int(locus.shape[0]) / 1e9 / peak, "traffic": None, "peak_source": src,
                              "note": "whole job per GPU"},
-                "allreduce_floats_per_iteration": int(r.stats["padded_cols"]) * L * 2 + int(r.stats["slots"])}
+                "allreduce_bytes_per_job_per_rank": int(r.stats["allreduce_bytes"]), "allreduce_calls_per_job": int(r.stats["allreduce_calls"]),
+                "allreduce_full_width_floats_per_iteration": int(r.stats["padded_cols"]) * L * 2 + int(r.stats["slots"])}
         print(json.dumps(line), flush=True)
+    comm.close()
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -389,6 +496,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config number (1-based)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the strong-scaling (config 3) and cell-sharded (config-4 shape) sub-records")
     ap.add_argument("--shard", default="restarts", choices=["restarts", "cells"], help="multi-GPU partition (default: restarts, weak scaling)")
     args = ap.parse_args()
     from souporcell_b200 import build

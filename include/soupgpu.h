@@ -132,6 +132,23 @@ int32_t soup_cluster_allele_counts(soup_ctx* ctx, const int32_t* cell_cluster /*
  * their partial losses. */
 typedef int32_t (*soup_allreduce_fn)(void* user, void* device_buf, uint64_t n_floats, void* cuda_stream);
 
+/* The same all-reduce done by the library itself over NCCL (linked into libsoupgpu): a soup_comm is one rank's NCCL communicator bound to
+ * a context's device.  The ranks of a communicator are either the contexts of ONE process (soup_comm_create_all = ncclCommInitAll; the
+ * CLI's `--shard cells`) or one context per process (soup_comm_unique_id on one rank, the 128 bytes handed to every rank by the
+ * launcher's own channel, then soup_comm_create = ncclCommInitRank).  With a communicator the statistics are reduced in locus
+ * ranges while the M pass is still producing the next range, and only the columns of the live restarts travel.
+ * The two host helpers move small host buffers over the communicator (staged through device memory): the once-per-run winner exchange
+ * of restart sharding (S:110-125 across processes) and the per-cluster cell counts of souporcell3 (S:156-162). */
+typedef struct soup_comm soup_comm;
+#define SOUP_COMM_ID_BYTES 128
+int32_t soup_comm_unique_id(uint8_t id[SOUP_COMM_ID_BYTES]);
+int32_t soup_comm_create(soup_ctx* ctx, const uint8_t id[SOUP_COMM_ID_BYTES], int32_t rank, int32_t world, soup_comm** out);
+int32_t soup_comm_create_all(soup_ctx* const* ctxs, int32_t n_ctx, soup_comm** out /*[n_ctx]*/);
+void soup_comm_destroy(soup_comm* comm);
+int32_t soup_comm_rank(const soup_comm* comm, int32_t* rank, int32_t* world);
+int32_t soup_comm_allgather(soup_comm* comm, const void* send, void* recv, uint64_t bytes_per_rank);   /* host buffers */
+int32_t soup_comm_bcast(soup_comm* comm, void* buf, uint64_t bytes, int32_t root);                      /* host buffer */
+
 /* cluster-center initialisation (ClusterInit S:749-754).  kmeans++ / middle_variance / known cell assignments are
  * `assert!(false)` in the reference (S:545,550,597) and are rejected by the CLI with the same message. */
 #define SOUP_INIT_RANDOM_UNIFORM 0      /* init_cluster_centers_uniform S:554-563 (the default) */
@@ -167,6 +184,7 @@ typedef struct soup_solve_params {
     uint64_t n_cells_global;          /* total cells over all ranks (the convergence limit S:214 uses it) */
     int32_t init_strategy;            /* SOUP_INIT_* : how a solve's centers are drawn from its seed stream when neither theta0
                                        * nor init_theta is given (--initialization_strategy, S:491-496) */
+    soup_comm* cell_comm;             /* cell sharding over NCCL inside the library (instead of the cell_allreduce callback); NULL = off */
 } soup_solve_params;
 
 typedef struct soup_solve_result {
@@ -202,6 +220,8 @@ typedef struct soup_stats {
     uint64_t slot_iterations;   /* sum over launches of active solves (= sum of iterations) */
     int32_t slots, lanes, groups, padded_cols;
     uint64_t h2d_bytes, d2h_bytes; /* copies made by the last load / solve call */
+    uint64_t allreduce_bytes;      /* cell sharding: bytes this rank handed to the all-reduce over the whole call */
+    uint64_t allreduce_calls;      /* ... in this many calls (locus ranges x iterations) */
 } soup_stats;
 int32_t soup_get_stats(soup_ctx* ctx, soup_stats* out);
 
@@ -298,6 +318,13 @@ typedef struct soup_main_params {
     uint64_t n_cells_global;
     soup_allgather_fn cell_allgather;
     int32_t cell_group_size;          /* processes in the cell group (what cell_allgather gathers over) */
+    /* The same two modes over NCCL inside the library (no callbacks):
+     *  - cell_comms: one communicator per context.  n_ctx > 1: the contexts of this process are the cell group (context i holds the
+     *    i-th contiguous cell range; best_log_probs covers all of them, in order).  n_ctx == 1: one process per cell shard, as above
+     *    (the per-cluster cell counts travel through soup_comm_allgather).
+     *  - proc_comm: restart sharding over processes (proc_rank / proc_world): the winner exchange runs over it instead of allgather / bcast. */
+    soup_comm* const* cell_comms;     /* [n_ctx] or NULL */
+    soup_comm* proc_comm;             /* or NULL */
 } soup_main_params;
 typedef struct soup_main_result {
     int32_t has_best, runs;

@@ -33,6 +33,7 @@ EXPORTS = [
     "soup_ctx_create", "soup_ctx_destroy", "soup_load_csr", "soup_get_dims", "soup_get_csc", "soup_get_cell_totals",
     "soup_get_csr_lbc", "soup_cluster_allele_counts", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
     "soup_main", "soup_exchange_best", "soup_write_clusters", "soup_clusters_load", "soup_troublet", "soup_troublet_write", "soup_mtx_save", "soup_mtx_load_cache",
+    "soup_comm_unique_id", "soup_comm_create", "soup_comm_create_all", "soup_comm_destroy", "soup_comm_rank", "soup_comm_allgather", "soup_comm_bcast",
 ]
 
 
@@ -54,7 +55,8 @@ class _SolveParams(C.Structure):
                 ("reinit_clusters", C.c_void_p), ("n_reinit", C.c_int32), ("iteration_cap", C.c_int32),
                 ("max_slots", C.c_int32), ("lanes", C.c_int32), ("record_counts", C.c_int32), ("keep_trace", C.c_int32),
                 ("poll_chunk", C.c_int32), ("time_kernels", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
-                ("cell_allreduce", C.c_void_p), ("comm_user", C.c_void_p), ("n_cells_global", C.c_uint64), ("init_strategy", C.c_int32)]
+                ("cell_allreduce", C.c_void_p), ("comm_user", C.c_void_p), ("n_cells_global", C.c_uint64), ("init_strategy", C.c_int32),
+                ("cell_comm", C.c_void_p)]
 
 
 class _SolveResult(C.Structure):
@@ -71,7 +73,8 @@ class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("estep_launches", C.c_uint64), ("mstep_launches", C.c_uint64),
                 ("solve_ms", C.c_double), ("estep_ms", C.c_double), ("mstep_ms", C.c_double), ("timed_iterations", C.c_uint64),
                 ("slot_iterations", C.c_uint64), ("slots", C.c_int32), ("lanes", C.c_int32),
-                ("groups", C.c_int32), ("padded_cols", C.c_int32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("groups", C.c_int32), ("padded_cols", C.c_int32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("allreduce_bytes", C.c_uint64), ("allreduce_calls", C.c_uint64)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
@@ -85,7 +88,8 @@ class _MainParams(C.Structure):
                 ("lanes", C.c_int32), ("record_counts", C.c_int32), ("verbose_trace", C.c_int32), ("time_kernels", C.c_int32),
                 ("known_theta", C.c_void_p), ("proc_rank", C.c_int32), ("proc_world", C.c_int32), ("allgather", ALLGATHER_FN), ("bcast", BCAST_FN),
                 ("comm_user", C.c_void_p), ("init_strategy", C.c_int32), ("cell_allreduce", C.c_void_p), ("cell_comm_user", C.c_void_p),
-                ("n_cells_global", C.c_uint64), ("cell_allgather", ALLGATHER_FN), ("cell_group_size", C.c_int32)]
+                ("n_cells_global", C.c_uint64), ("cell_allgather", ALLGATHER_FN), ("cell_group_size", C.c_int32),
+                ("cell_comms", C.POINTER(C.c_void_p)), ("proc_comm", C.c_void_p)]
 
 
 class _MainResult(C.Structure):
@@ -98,12 +102,29 @@ class _MainResult(C.Structure):
 _lib = None
 
 
+def _preload_nccl():
+    """libsoupgpu links libnccl.so.2.  torch ships its own copy under the same soname; whichever is loaded first serves both, and torch
+    needs ITS version.  So in a Python process the bundled one is mapped first (a no-op when torch is already imported); the
+    `souporcell` executable, which has no torch, takes the system library."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def lib():
     """Load libsoupgpu.so (built in-tree by souporcell_b200.build / __graft_entry__.build)."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise SoupError(ERR_CUDA, f"{LIB_PATH} is missing — run `python -m souporcell_b200.build`; there is no fallback path")
+        _preload_nccl()
         L = C.CDLL(LIB_PATH)
         L.soup_last_error.restype = C.c_char_p
         L.soup_last_error.argtypes = [C.c_void_p]
@@ -144,6 +165,14 @@ def lib():
         L.soup_troublet.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
         L.soup_troublet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int32, C.c_void_p]
+        L.soup_comm_unique_id.argtypes = [C.c_void_p]
+        L.soup_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.soup_comm_create_all.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
+        L.soup_comm_destroy.argtypes = [C.c_void_p]
+        L.soup_comm_destroy.restype = None
+        L.soup_comm_rank.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.soup_comm_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.soup_comm_bcast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32]
         _lib = L
     return _lib
 
@@ -454,7 +483,7 @@ class Context:
     def solve(self, k, method=METHOD_EM, n_streams=1, solves_per_stream=1, stream_seeds=None, theta0=None,
               base_theta=None, reinit_clusters=None, iteration_cap=0, max_slots=0, lanes=0, record_counts=False,
               keep_trace=False, poll_chunk=0, time_kernels=False, shard_rank=0, shard_world=1, cell_allreduce=None,
-              n_cells_global=0, init_strategy=INIT_RANDOM_UNIFORM) -> SolveResult:
+              n_cells_global=0, init_strategy=INIT_RANDOM_UNIFORM, cell_comm=None) -> SolveResult:
         n_solves = n_streams * solves_per_stream
         p = _SolveParams()
         p.k, p.method, p.n_streams, p.solves_per_stream = k, method, n_streams, solves_per_stream
@@ -484,6 +513,9 @@ class Context:
             p.cell_allreduce = C.cast(cell_allreduce, C.c_void_p)
             p.n_cells_global = n_cells_global
             keep.append(cell_allreduce)
+        if cell_comm is not None:
+            p.cell_comm = cell_comm._h
+            p.n_cells_global = n_cells_global
         r = _SolveResult()
         lp = np.zeros((self.n_cells, k), dtype=np.float32)
         th = np.zeros((k, self.n_loci), dtype=np.float32)
@@ -554,10 +586,13 @@ class MainResult:
 def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3=False, iteration_cap=0, max_slots=0,
          lanes=0, record_counts=False, verbose_trace=False, time_kernels=False, proc_rank=0, proc_world=1, allgather=None,
          bcast=None, known_theta=None, init_strategy=INIT_RANDOM_UNIFORM, cell_allreduce=None, cell_allgather=None, cell_group_size=0,
-         n_cells_global=0) -> MainResult:
-    """souporcell_main S:60-131 over one context per GPU (restart-sharded)."""
+         n_cells_global=0, cell_comms=None, proc_comm=None) -> MainResult:
+    """souporcell_main S:60-131 over one context per GPU: restart-sharded, or — with `cell_comms`, one Comm per context — cell-sharded
+    (context i holds the i-th contiguous range of the cells; the result covers all of them in order)."""
     if isinstance(ctxs, Context):
         ctxs = [ctxs]
+    if isinstance(cell_comms, Comm):
+        cell_comms = [cell_comms]
     arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
     p = _MainParams()
     p.k, p.method, p.restarts, p.threads, p.seed = k, method, restarts, threads, seed
@@ -576,7 +611,13 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
         p.allgather = allgather
     if bcast is not None:
         p.bcast = bcast
-    n, L = ctxs[0].n_cells, ctxs[0].n_loci
+    if cell_comms is not None:
+        comm_arr = (C.c_void_p * len(ctxs))(*[c._h for c in cell_comms])
+        p.cell_comms = comm_arr
+        p.n_cells_global = n_cells_global
+    if proc_comm is not None:
+        p.proc_comm = proc_comm._h
+    n, L = (sum(c.n_cells for c in ctxs) if cell_comms is not None else ctxs[0].n_cells), ctxs[0].n_loci
     lp = np.zeros((n, k), dtype=np.float32)
     th = np.zeros((k, L), dtype=np.float32)
     r = _MainResult()
@@ -584,6 +625,59 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
     _check(lib().soup_main(arr, len(ctxs), C.byref(p), C.byref(r), None))
     return MainResult(bool(r.has_best), r.runs, float(r.best_loss), lp, th, int(r.nnz_updates), int(r.kernel_launches), float(r.solve_ms),
                       int(r.slot_iterations), int(r.timed_iterations), float(r.estep_ms), float(r.mstep_ms))
+
+
+class Comm:
+    """soup_comm: one rank of an NCCL communicator inside libsoupgpu, bound to a context's device."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(lib().soup_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def create(cls, ctx, unique_id: bytes, rank: int, world: int) -> "Comm":
+        """One rank per process (ncclCommInitRank): `unique_id` comes from Comm.unique_id() on one rank, sent to the others by the launcher."""
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().soup_comm_create(ctx._h, buf, rank, world, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def create_all(cls, ctxs):
+        """The contexts of this process (one GPU each) as the ranks of one communicator (ncclCommInitAll)."""
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        out = (C.c_void_p * len(ctxs))()
+        _check(lib().soup_comm_create_all(arr, len(ctxs), out))
+        return [cls(C.c_void_p(out[i])) for i in range(len(ctxs))]
+
+    @classmethod
+    def from_torch(cls, ctx, dist) -> "Comm":
+        """One rank per process under torchrun: rank 0's unique id travels over the torch.distributed process group (any backend)."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls.create(ctx, box[0], rank, world)
+
+    def rank(self):
+        r, w = C.c_int32(), C.c_int32()
+        _check(lib().soup_comm_rank(self._h, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def allgather(self, data: bytes) -> bytes:
+        _, w = self.rank()
+        out = (C.c_uint8 * (len(data) * w))()
+        _check(lib().soup_comm_allgather(self._h, data, out, len(data)))
+        return bytes(out)
+
+    def close(self):
+        if self._h:
+            lib().soup_comm_destroy(self._h)
+            self._h = None
 
 
 def split_cells(csr, parts: int):

@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 ]
 # Compile-time experiments (e.g. SOUP_NVCC_DEFINES="-DSOUP_E_FASTBATCH=1" python -m souporcell_b200.build --force); empty = the measured build.
 NVCC_FLAGS += os.environ.get("SOUP_NVCC_DEFINES", "").split()
-LINK_LIBS = ["-lz"]
+LINK_LIBS = ["-lz", "-lnccl"]
 LIB_SOURCES = ["soup_device.cu", "host_loader.cpp", "host_util.cpp", "soup_driver.cpp"]
 LIB_HEADERS = ["soup_kernels.cuh", "troublet_kernels.cuh", "soup_common.hpp", "host_parallel.hpp", "glibc_flt32.h", os.path.join("..", "..", "include", "soupgpu.h")]
 

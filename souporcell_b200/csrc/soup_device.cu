@@ -2,6 +2,7 @@
 // engine (soup_solve) and the fine-grained parity hooks.  sm_100a only; there is no CPU fallback.
 // Reference: /root/reference/souporcell/src/main.rs ("S:").
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -74,9 +75,10 @@ struct DevBuf {   // grow-only device allocation
 };
 struct LoadBufs {
     DevBuf row_ptr, col_ptr, csr_idx, csc_idx, csr_aux, csc_aux, cell_order, locus_order, total_alleles;   // the matrix
+    DevBuf cell_order_m;   // cell-sharded mode: the M pass's range-major visiting order of the loci
     DevBuf locus, alt, ref, vals, vals2, keys, keys2, len, len2, idx, idx2, tmp, flags;                        // load-time scratch
     void release_all() {
-        for (DevBuf* b : {&row_ptr, &col_ptr, &csr_idx, &csc_idx, &csr_aux, &csc_aux, &cell_order, &locus_order, &total_alleles,
+        for (DevBuf* b : {&row_ptr, &col_ptr, &csr_idx, &csc_idx, &csr_aux, &csc_aux, &cell_order, &locus_order, &total_alleles, &cell_order_m,
                           &locus, &alt, &ref, &vals, &vals2, &keys, &keys2, &len, &len2, &idx, &idx2, &tmp, &flags}) b->release();
     }
 };
@@ -87,6 +89,13 @@ struct soup_ctx {
     cudaStream_t stream = nullptr, side = nullptr;   // side: loss + control, concurrent with the M pass
     cudaStream_t side_long = nullptr;                // the M pass's long-locus kernel, concurrent with its wide role
     cudaEvent_t ev_mfork = nullptr, ev_mjoin = nullptr;
+    // cell-sharded mode: the all-reduce of each locus range and the theta pass behind it run here while the M pass produces the next range
+    cudaStream_t comm_stream = nullptr;
+    static constexpr int MAX_CELL_CHUNKS = 16;
+    cudaEvent_t ev_chunk[MAX_CELL_CHUNKS] = {}, ev_comm = nullptr, ev_loss = nullptr;
+    int cell_ranges = 0;                                  // locus ranges of the cell-sharded M pass (0 = order not built for this matrix)
+    uint32_t cell_range_row[MAX_CELL_CHUNKS + 1] = {};    // range c = locus ids [row[c], row[c + 1])
+    uint32_t cell_range_pos[MAX_CELL_CHUNKS + 1] = {};    // ... visited at the positions [pos[c], pos[c + 1]) of lb.cell_order_m (pos[0] = n_long)
     int long_coop = 1;          // 0 never, 1 while few columns are live (the tail of a job), 2 always (SOUP_LONG_COOP)
     uint32_t tail_cols = 128;   // "few": at most this many live columns (SOUP_TAIL_COLS, <= 256)
     bool own_stream = false;
@@ -197,6 +206,10 @@ extern "C" int32_t soup_ctx_create(int32_t device, void* cuda_stream, soup_ctx**
         cudaStreamCreateWithPriority(&ctx->side_long, cudaStreamNonBlocking, hi);
         cudaEventCreateWithFlags(&ctx->ev_mfork, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_mjoin, cudaEventDisableTiming);
+        cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi);
+        for (cudaEvent_t& e : ctx->ev_chunk) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_loss, cudaEventDisableTiming);
         if (const char* e = getenv("SOUP_LONG_COOP")) ctx->long_coop = std::min(2, std::max(0, atoi(e)));
         if (const char* e = getenv("SOUP_TAIL_COLS")) ctx->tail_cols = (uint32_t)std::min(256, std::max(1, atoi(e)));
         if (cudaFuncSetAttribute(mstep_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ML_SMEM_FLOATS * sizeof(float))) != cudaSuccess) {
@@ -256,9 +269,119 @@ extern "C" void soup_ctx_destroy(soup_ctx* ctx) {
     if (ctx->side_long) cudaStreamDestroy(ctx->side_long);
     if (ctx->ev_mfork) cudaEventDestroy(ctx->ev_mfork);
     if (ctx->ev_mjoin) cudaEventDestroy(ctx->ev_mjoin);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+    if (ctx->ev_loss) cudaEventDestroy(ctx->ev_loss);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+
+// ------------------------------------------------------------------ soup_comm: one rank of an NCCL communicator, bound to a context's device
+struct soup_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+    cudaStream_t stream = nullptr;       // the helpers' own stream (host-buffer all-gather / broadcast)
+    DevBuf stage;                        // device staging of the host helpers
+};
+static int32_t nccl_fail(const char* what, ncclResult_t r) {
+    set_thread_error("%s failed: %s", what, ncclGetErrorString(r));
+    return SOUP_ERR_CUDA;
+}
+extern "C" int32_t soup_comm_unique_id(uint8_t id[SOUP_COMM_ID_BYTES]) try {
+    static_assert(sizeof(ncclUniqueId) == SOUP_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    if (!id) { set_thread_error("soup_comm_unique_id: null argument"); return SOUP_ERR_INVALID; }
+    ncclUniqueId u;
+    ncclResult_t r = ncclGetUniqueId(&u);
+    if (r != ncclSuccess) return nccl_fail("ncclGetUniqueId", r);
+    memcpy(id, &u, sizeof(u));
+    return SOUP_OK;
+}
+SOUP_CATCH_RETURN("soup_comm_unique_id")
+static soup_comm* comm_wrap(ncclComm_t c, int rank, int world, int device) {
+    soup_comm* m = new soup_comm();
+    m->comm = c; m->rank = rank; m->world = world; m->device = device;
+    cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    return m;
+}
+extern "C" int32_t soup_comm_create(soup_ctx* ctx, const uint8_t id[SOUP_COMM_ID_BYTES], int32_t rank, int32_t world, soup_comm** out) try {
+    if (!ctx || !id || !out || world < 1 || rank < 0 || rank >= world) { set_thread_error("soup_comm_create: bad argument"); return SOUP_ERR_INVALID; }
+    *out = nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { set_thread_error("soup_comm_create: cudaSetDevice failed"); return SOUP_ERR_CUDA; }
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclComm_t c = nullptr;
+    ncclResult_t r = ncclCommInitRank(&c, world, u, rank);
+    if (r != ncclSuccess) return nccl_fail("ncclCommInitRank", r);
+    *out = comm_wrap(c, rank, world, ctx->device);
+    return SOUP_OK;
+}
+SOUP_CATCH_RETURN("soup_comm_create")
+extern "C" int32_t soup_comm_create_all(soup_ctx* const* ctxs, int32_t n_ctx, soup_comm** out) try {
+    if (!ctxs || !out || n_ctx < 1) { set_thread_error("soup_comm_create_all: bad argument"); return SOUP_ERR_INVALID; }
+    std::vector<int> devs(n_ctx);
+    for (int i = 0; i < n_ctx; ++i) {
+        if (!ctxs[i]) { set_thread_error("soup_comm_create_all: null context"); return SOUP_ERR_INVALID; }
+        devs[i] = ctxs[i]->device;
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) { set_thread_error("soup_comm_create_all: contexts %d and %d share device %d (NCCL needs one GPU per rank)", j, i, devs[i]); return SOUP_ERR_INVALID; }
+        out[i] = nullptr;
+    }
+    std::vector<ncclComm_t> cs(n_ctx, nullptr);
+    ncclResult_t r = ncclCommInitAll(cs.data(), n_ctx, devs.data());
+    if (r != ncclSuccess) return nccl_fail("ncclCommInitAll", r);
+    for (int i = 0; i < n_ctx; ++i) { cudaSetDevice(devs[i]); out[i] = comm_wrap(cs[i], i, n_ctx, devs[i]); }
+    return SOUP_OK;
+}
+SOUP_CATCH_RETURN("soup_comm_create_all")
+extern "C" void soup_comm_destroy(soup_comm* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    m->stage.release();
+    if (m->comm) ncclCommDestroy(m->comm);
+    delete m;
+}
+extern "C" int32_t soup_comm_rank(const soup_comm* m, int32_t* rank, int32_t* world) {
+    if (!m) { set_thread_error("soup_comm_rank: null communicator"); return SOUP_ERR_INVALID; }
+    if (rank) *rank = m->rank;
+    if (world) *world = m->world;
+    return SOUP_OK;
+}
+// host buffers over the communicator, staged through device memory (a few bytes to a few MB, once per run)
+extern "C" int32_t soup_comm_allgather(soup_comm* m, const void* send, void* recv, uint64_t bytes) try {
+    if (!m || !send || !recv) { set_thread_error("soup_comm_allgather: bad argument"); return SOUP_ERR_INVALID; }
+    if (bytes == 0) return SOUP_OK;
+    if (cudaSetDevice(m->device) != cudaSuccess || m->stage.ensure((size_t)bytes * (m->world + 1)) != cudaSuccess) { cudaGetLastError(); set_thread_error("soup_comm_allgather: staging allocation failed"); return SOUP_ERR_NOMEM; }
+    char* d_send = (char*)m->stage.p;
+    char* d_recv = d_send + bytes;
+    cudaError_t e = cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess) {
+        ncclResult_t r = ncclAllGather(d_send, d_recv, bytes, ncclChar, m->comm, m->stream);
+        if (r != ncclSuccess) return nccl_fail("ncclAllGather", r);
+        e = cudaMemcpyAsync(recv, d_recv, bytes * m->world, cudaMemcpyDeviceToHost, m->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) { set_thread_error("soup_comm_allgather: %s", cudaGetErrorString(e)); return SOUP_ERR_CUDA; }
+    return SOUP_OK;
+}
+SOUP_CATCH_RETURN("soup_comm_allgather")
+extern "C" int32_t soup_comm_bcast(soup_comm* m, void* buf, uint64_t bytes, int32_t root) try {
+    if (!m || !buf || root < 0 || root >= m->world) { set_thread_error("soup_comm_bcast: bad argument"); return SOUP_ERR_INVALID; }
+    if (bytes == 0) return SOUP_OK;
+    if (cudaSetDevice(m->device) != cudaSuccess || m->stage.ensure((size_t)bytes) != cudaSuccess) { cudaGetLastError(); set_thread_error("soup_comm_bcast: staging allocation failed"); return SOUP_ERR_NOMEM; }
+    cudaError_t e = cudaSuccess;
+    if (m->rank == root) e = cudaMemcpyAsync(m->stage.p, buf, bytes, cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess) {
+        ncclResult_t r = ncclBroadcast(m->stage.p, m->stage.p, bytes, ncclChar, root, m->comm, m->stream);
+        if (r != ncclSuccess) return nccl_fail("ncclBroadcast", r);
+        if (m->rank != root) e = cudaMemcpyAsync(buf, m->stage.p, bytes, cudaMemcpyDeviceToHost, m->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) { set_thread_error("soup_comm_bcast: %s", cudaGetErrorString(e)); return SOUP_ERR_CUDA; }
+    return SOUP_OK;
+}
+SOUP_CATCH_RETURN("soup_comm_bcast")
 
 // ------------------------------------------------------------------ soup_load_csr
 #include <chrono>
@@ -295,6 +418,7 @@ extern "C" int32_t soup_load_csr(soup_ctx* ctx, uint64_t n_cells, uint64_t n_loc
     CK(cudaSetDevice(ctx->device));
     ctx->stats = soup_stats{};
     ctx->loaded = false;
+    ctx->cell_ranges = 0;
     cudaStream_t st = ctx->stream;
     // Device buffers are grow-only and cached in the context: reloading a matrix of the same size allocates nothing.
     LoadBufs& B = ctx->lb;
@@ -611,9 +735,16 @@ struct IterLaunch {
     float log_prior, limit;
     bool record_counts;
     int timed_iter = -1;   // >= 0: bracket this iteration's E and M launches with events ev_k[4*i .. 4*i+3]
-    soup_allreduce_fn allreduce = nullptr;   // cell-sharded mode
+    soup_allreduce_fn allreduce = nullptr;   // cell-sharded mode: the caller's all-reduce ...
     void* comm_user = nullptr;
+    soup_comm* comm = nullptr;               // ... or NCCL inside the library
     int32_t comm_error = 0;
+    bool cell_mode = false;
+    // Columns the statistics rows carry: a multiple of 4 that covers every live column.  Every rank takes the value from the same
+    // completed poll (two chunks of iterations back), and Ctl::live_cols never grows, so the ranks always agree on the reduced sizes.
+    uint32_t scols = 0;
+    int n_ranges = 1;                        // locus ranges the M pass / all-reduce / theta pass are pipelined over
+    uint64_t allreduce_bytes = 0, allreduce_calls = 0;
     RefillArgs refill;
     FinalizeArgs fin;
     const float* base_theta_dev = nullptr;   // [K_out][L] centers of the previous run (compact re-run: the locked clusters' rows)
@@ -640,20 +771,33 @@ static void launch_e(soup_ctx* ctx, float log_prior) {
     const dim3 grid(bpg * w.ep.n_groups);
     SOUP_DISPATCH(estep_kernel, EM_THREADS, w.ep, a);
 }
-static void launch_m(soup_ctx* ctx) {
+// One launch of the M pass over the loci [li_begin, li_end) of the LPT order (nullptr = the whole pass).  `with_long`: this launch
+// also carries the long role's blocks and the cooperative long-locus kernel (both only ever touch the first loci of the order).
+struct MRange {
+    uint32_t li_begin, li_end;
+    bool with_long;
+    float* SP;                 // cell-sharded mode: the statistics buffer (MArgs::SP)
+    uint32_t scols;
+    const uint32_t* order;     // visiting order of the loci (cell-sharded mode: range-major), nullptr = the LPT order
+};
+static void launch_m(soup_ctx* ctx, const MRange* range = nullptr) {
     Workspace& w = ctx->ws;
-    const uint32_t chunks = (uint32_t)((ctx->L + EM_WARPS - 1) / EM_WARPS);
-    if (chunks == 0) return;
-    const uint32_t n_long = ctx->n_long, long_items = n_long * (uint32_t)w.lp.n_groups;
+    if (ctx->L == 0) return;
+    const uint32_t n_long = ctx->n_long;
     const uint32_t n_tail = ctx->n_long_tail;
-    const bool coop = ctx->long_coop != 0 && n_tail > 0;   // long loci by mstep_long_kernel on its own high-priority stream (MArgs::coop_mode)
+    MRange all{n_long, (uint32_t)ctx->L, true, nullptr, 0, nullptr};
+    const MRange& r = range ? *range : all;
+    const uint32_t li_begin = std::max(r.li_begin, n_long);     // (loci in front of n_long are never the wide role's)
+    const uint32_t long_items = r.with_long ? n_long * (uint32_t)w.lp.n_groups : 0u;
+    const bool coop = r.with_long && ctx->long_coop != 0 && n_tail > 0;   // long loci by mstep_long_kernel on its own high-priority stream (MArgs::coop_mode)
     const uint32_t long_blocks = (long_items + EM_WARPS - 1) / EM_WARPS;
-    const uint32_t wide_chunks = (uint32_t)((ctx->L - n_long + EM_WARPS - 1) / EM_WARPS);
-    const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
-                  w.m_group_active, w.l_group_active, w.ctl, w.stats, w.stats ? w.stats + (size_t)ctx->L * w.Cpad : nullptr, ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups,
+    const uint32_t wide_chunks = r.li_end > li_begin ? (r.li_end - li_begin + EM_WARPS - 1) / EM_WARPS : 0u;
+    const MArgs a{ctx->d_csc_idx, ctx->d_csc_aux, ctx->d_col_ptr, r.order ? r.order : ctx->d_locus_order, w.W, w.TH, w.LA, w.LB, w.col_write,
+                  w.m_group_active, w.l_group_active, w.ctl, r.SP, r.scols, li_begin, r.li_end,
+                  ctx->pk_csc, (uint32_t)ctx->L, w.Cpad, (uint32_t)w.mp.n_groups,
                   n_long, (uint32_t)w.lp.n_groups, long_blocks, wide_chunks,
                   (uint32_t)((uint64_t)ctx->N * w.Cpad * 4 > (48ull << 20)), (uint32_t)(w.forced_lanes != 0),
-                  coop ? (uint32_t)ctx->long_coop : 0u, ctx->tail_cols, n_tail, w.k_of_draw, (uint32_t)w.K, (uint32_t)(w.nd > 0 ? w.nd : w.K)};
+                  ctx->long_coop != 0 && n_tail > 0 ? (uint32_t)ctx->long_coop : 0u, ctx->tail_cols, n_tail, w.k_of_draw, (uint32_t)w.K, (uint32_t)(w.nd > 0 ? w.nd : w.K)};
     if (coop) {
         const uint32_t groups256 = (w.Cpad + ML_THREADS - 1) / ML_THREADS;
         const uint32_t blocks = ctx->long_coop == 2 ? std::max(n_tail, n_long * groups256) : n_tail;
@@ -682,7 +826,7 @@ static void launch_refill(soup_ctx* ctx, const RefillArgs& a) {
 // kernels one iteration enqueues: E, post, loss, control, M (+ the long-locus kernel), harvest, finalize, migrate
 // (+ refill while the queue is not known to be drained, + theta in cell-sharded mode)
 static uint64_t launches_per_iteration(const soup_ctx* ctx, bool refill, bool cell_mode) {
-    return 8 + (ctx->long_coop != 0 && ctx->n_long_tail > 0 ? 1 : 0) + (refill ? 1 : 0) + (cell_mode ? 1 : 0);
+    return 8 + (ctx->long_coop != 0 && ctx->n_long_tail > 0 ? 1 : 0) + (refill ? 1 : 0) + (cell_mode ? 2 * (uint64_t)std::max(ctx->cell_ranges, 1) - 1 : 0);
 }
 
 static void launch_loss_control(soup_ctx* ctx, cudaStream_t st, bool counts, float limit) {
@@ -706,15 +850,41 @@ static void enqueue_iteration(IterLaunch& it) {
     launch_e(ctx, it.log_prior);
     if (ev) cudaEventRecord(ev[1], ctx->stream);
     launch_post(ctx, it.method, it.record_counts);
-    if (it.allreduce) {
-        float* loss = w.stats + 2 * (size_t)ctx->L * w.Cpad;
-        loss_kernel<<<w.slots, 256, 0, ctx->stream>>>(w.LSE, w.st, loss, (uint32_t)ctx->N);
+    if (it.cell_mode) {
+        // statistics buffer [L][2][scols] (MArgs::SP), the slots' partial losses behind it.  The M pass runs as n_ranges launches over
+        // ranges of locus ids (cell_order: the long loci first, then range by range, longest first inside a range); as soon as a
+        // range is complete its all-reduce and theta pass start on comm_stream while the next range is being produced.
+        const uint32_t L = (uint32_t)ctx->L, scols = it.scols;
+        const int n_ranges = ctx->cell_ranges;
+        float* loss = w.stats + 2 * (size_t)L * scols;
+        cudaEventRecord(ctx->ev_fork, ctx->stream);                 // the partial loss sums hide behind the M pass
+        cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
+        loss_kernel<<<w.slots, 256, 0, ctx->side>>>(w.LSE, w.st, loss, (uint32_t)ctx->N);
+        cudaEventRecord(ctx->ev_loss, ctx->side);
         if (ev) cudaEventRecord(ev[2], ctx->stream);
-        launch_m(ctx);
+        for (int c = 0; c < n_ranges; ++c) {
+            const uint32_t row0 = ctx->cell_range_row[c], rows = ctx->cell_range_row[c + 1] - row0;
+            const MRange range{ctx->cell_range_pos[c], ctx->cell_range_pos[c + 1], c == 0, w.stats, scols, (const uint32_t*)ctx->lb.cell_order_m.p};
+            launch_m(ctx, &range);
+            cudaEventRecord(ctx->ev_chunk[c], ctx->stream);
+            cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_chunk[c], 0);
+            const bool last = c == n_ranges - 1;
+            if (last) cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_loss, 0);
+            float* sp = w.stats + 2 * (size_t)row0 * scols;
+            const uint64_t n_floats = 2 * (uint64_t)rows * scols + (last ? (uint64_t)w.slots : 0u);
+            int32_t e = SOUP_OK;
+            if (it.comm) {
+                if (ncclAllReduce(sp, sp, n_floats, ncclFloat, ncclSum, it.comm->comm, ctx->comm_stream) != ncclSuccess) e = SOUP_ERR_CUDA;
+            } else {
+                e = it.allreduce(it.comm_user, sp, n_floats, (void*)ctx->comm_stream);
+            }
+            if (e != SOUP_OK && it.comm_error == 0) it.comm_error = e;
+            it.allreduce_bytes += n_floats * 4; it.allreduce_calls += 1;
+            if (rows) theta_kernel<<<ctx->sm_count * 4, 256, 0, ctx->comm_stream>>>(w.stats, scols, row0, rows, w.col_write, w.TH, w.LA, w.LB, w.Cpad);
+        }
         if (ev) cudaEventRecord(ev[3], ctx->stream);
-        const int32_t e = it.allreduce(it.comm_user, w.stats, w.stats_floats, (void*)ctx->stream);
-        if (e != SOUP_OK && it.comm_error == 0) it.comm_error = e;
-        theta_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(w.stats, w.stats + (size_t)ctx->L * w.Cpad, w.col_write, w.TH, w.LA, w.LB, (uint32_t)ctx->L, w.Cpad);
+        cudaEventRecord(ctx->ev_comm, ctx->comm_stream);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0);
         ControlArgs c{loss, w.st, w.ctl, nullptr, w.trace, w.solve_loss, w.solve_iters, (uint32_t)ctx->N, w.K, w.slots, w.iter_cap, it.limit};
         control_kernel<<<1, std::min(1024, (w.slots + 31) / 32 * 32), 0, ctx->stream>>>(c);
     } else {
@@ -732,6 +902,36 @@ static void enqueue_iteration(IterLaunch& it) {
     if (!it.queue_drained) launch_refill(ctx, it.refill);
     finalize_kernel<<<1, 1024, 0, ctx->stream>>>(it.fin);
     migrate_kernel<<<dim3(96, (unsigned)w.slots), 256, 0, ctx->stream>>>(w.ctl, w.moves, w.TH, w.LA, w.LB, (uint32_t)ctx->L, w.Cpad, w.K);
+}
+
+// Cell-sharded mode: the M pass's visiting order of the loci.  The statistics travel in ranges of locus ids (the same on every rank),
+// so the order is: the long loci (the first n_long_tail of this rank's LPT order, wherever their ids lie: the first launch finishes
+// them), then range by range, longest first inside a range.
+static int32_t build_cell_order(soup_ctx* ctx) {
+    if (ctx->cell_ranges > 0) return SOUP_OK;
+    const uint32_t L = (uint32_t)ctx->L;
+    int P = L < 4096 ? 1 : 4;                                     // (a function of L alone: every rank must cut the same ranges)
+    if (const char* e = getenv("SOUP_CELL_RANGES")) P = atoi(e);  // tuning / tests; the same on every rank
+    P = std::max(1, std::min(P, (int)soup_ctx::MAX_CELL_CHUNKS));
+    if ((uint32_t)P > std::max(L, 1u)) P = (int)std::max(L, 1u);
+    std::vector<uint32_t> lpt(std::max<uint32_t>(L, 1)), order(std::max<uint32_t>(L, 1));
+    CK(cudaSetDevice(ctx->device));
+    if (L) CK(cudaMemcpy(lpt.data(), ctx->d_locus_order, (size_t)L * 4, cudaMemcpyDeviceToHost));
+    const uint32_t rows = (L + (uint32_t)P - 1) / (uint32_t)P, prefix = std::min(L, std::max(ctx->n_long, ctx->n_long_tail));
+    std::vector<uint32_t> count(P + 1, 0);
+    for (uint32_t i = prefix; i < L; ++i) count[lpt[i] / std::max(rows, 1u) + 1] += 1;
+    for (int c = 0; c <= P; ++c) ctx->cell_range_row[c] = std::min(L, (uint32_t)c * rows);
+    std::vector<uint32_t> at(P + 1, 0);
+    at[0] = prefix;
+    for (int c = 0; c < P; ++c) at[c + 1] = at[c] + count[c + 1];
+    ctx->cell_range_pos[0] = std::min(ctx->n_long, prefix);
+    for (int c = 1; c <= P; ++c) ctx->cell_range_pos[c] = at[c];
+    for (uint32_t i = 0; i < prefix; ++i) order[i] = lpt[i];
+    for (uint32_t i = prefix; i < L; ++i) order[at[lpt[i] / std::max(rows, 1u)]++] = lpt[i];
+    if (ctx->lb.cell_order_m.ensure(std::max<size_t>(L, 1) * 4) != cudaSuccess) { cudaGetLastError(); return ctx->fail(SOUP_ERR_NOMEM, "soup_solve: cannot allocate the cell-sharded visiting order"); }
+    if (L) CK(cudaMemcpy(ctx->lb.cell_order_m.p, order.data(), (size_t)L * 4, cudaMemcpyHostToDevice));
+    ctx->cell_ranges = P;
+    return SOUP_OK;
 }
 
 // ------------------------------------------------------------------ soup_solve
@@ -769,7 +969,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     if (r->solve_iters) for (int i = 0; i < n_solves; ++i) r->solve_iters[i] = 0;
     ctx->h_trace.clear(); ctx->h_trace_solve.clear(); ctx->h_trace_iters.clear(); ctx->h_trace_cap = iter_cap;
 
-    const bool cell_mode = p->cell_allreduce != nullptr;
+    const bool cell_mode = p->cell_allreduce != nullptr || p->cell_comm != nullptr;
+    if (p->cell_comm && p->cell_comm->device != ctx->device) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: cell_comm belongs to another device");
     // cell_mode with world > 1 is the hybrid mode: every process of a cell group passes the same shard_rank (its
     // group), runs the same subset of the solves, and the all-reduce callback spans that group only
     if (cell_mode && p->n_cells_global < ctx->N) return ctx->fail(SOUP_ERR_INVALID, "soup_solve: n_cells_global must be the total cell count over all ranks");
@@ -814,6 +1015,8 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     Workspace& w = ctx->ws;
     cudaStream_t st = ctx->stream;
     if (cell_mode) {
+        rc = build_cell_order(ctx);
+        if (rc != SOUP_OK) return rc;
         const size_t need = 2 * (size_t)ctx->L * w.Cpad + (size_t)slots;
         if (w.stats_floats != need) {
             float* sp = nullptr;
@@ -984,7 +1187,9 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
 
     IterLaunch it;
     it.ctx = ctx; it.method = p->method; it.log_prior = log_prior; it.limit = limit; it.record_counts = p->record_counts != 0 && !cell_mode;
-    it.allreduce = p->cell_allreduce; it.comm_user = p->comm_user;
+    it.allreduce = p->cell_allreduce; it.comm_user = p->comm_user; it.comm = p->cell_comm; it.cell_mode = cell_mode;
+    auto cover4 = [&](uint32_t live) { return std::min(w.Cpad, (std::max(live, 1u) + 3u) & ~3u); };
+    it.scols = cover4((uint32_t)(std::min(slots, n_local) * K));
     it.base_theta_dev = d_base;
     it.refill = RefillArgs{w.st, w.ctl, w.queue, w.stream_keys, d_theta0, d_base, d_init, w.draw_of_k, w.TH, w.LA, w.LB,
                            (uint32_t)ctx->L, w.Cpad, K, n_draw, p->solves_per_stream,
@@ -1023,7 +1228,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
             enqueue_iteration(it);
         }
         iters_enqueued += chunk;
-        launches += (uint64_t)chunk * launches_per_iteration(ctx, !it.queue_drained, it.allreduce != nullptr);
+        launches += (uint64_t)chunk * launches_per_iteration(ctx, !it.queue_drained, it.cell_mode);
         cudaError_t e = cudaMemcpyAsync(ctx->h_ctl + which, w.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_poll[which], st);
         return e;
@@ -1044,6 +1249,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
         if (it.comm_error) { cleanup(); return ctx->fail(it.comm_error, "soup_solve: the all-reduce callback failed (%d)", it.comm_error); }
         if (ctx->h_ctl[cur].done_count >= n_local) break;
         if (ctx->h_ctl[cur].queue_head >= ctx->h_ctl[cur].queue_len) it.queue_drained = true;
+        if (cell_mode) it.scols = std::min(it.scols, cover4(ctx->h_ctl[cur].live_cols));   // (the same poll on every rank; live_cols never grows)
         if (iters_enqueued > (uint64_t)n_local * (uint64_t)(iter_cap + TEMP_STEPS) + 64) { cleanup(); return ctx->fail(SOUP_ERR_CUDA, "soup_solve: device control loop did not converge"); }
     }
     const double t_loop1 = now_ms();
@@ -1114,6 +1320,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     ctx->stats.slot_iterations = fc.slot_iterations;
     ctx->stats.slots = slots; ctx->stats.lanes = w.ep.VM; ctx->stats.groups = w.ep.n_groups; ctx->stats.padded_cols = (int32_t)w.Cpad;
     ctx->stats.h2d_bytes = h2d; ctx->stats.d2h_bytes = d2h;
+    ctx->stats.allreduce_bytes = it.allreduce_bytes; ctx->stats.allreduce_calls = it.allreduce_calls;
     return SOUP_OK;
 }
 SOUP_CATCH_RETURN_CTX("soup_solve")

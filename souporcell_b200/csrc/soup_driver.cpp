@@ -78,18 +78,40 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
     if (!p || !r || !r->best_log_probs) { set_thread_error("soup_main: null argument"); return SOUP_ERR_INVALID; }
     if (p->threads == 0 || p->k <= 0) { set_thread_error("soup_main: threads and k must be >= 1"); return SOUP_ERR_INVALID; }
     const int pworld = p->proc_world > 1 ? p->proc_world : 1, prank = pworld > 1 ? p->proc_rank : 0;
-    const bool cell_mode = p->cell_allreduce != nullptr;
-    if (cell_mode && n_ctx != 1) { set_thread_error("soup_main: cell sharding takes ONE context per process"); return SOUP_ERR_INVALID; }
-    if (cell_mode && (!p->cell_allgather || p->cell_group_size <= 0)) { set_thread_error("soup_main: cell sharding needs cell_allgather and cell_group_size"); return SOUP_ERR_INVALID; }
-    if (pworld > 1 && (!p->allgather || !p->bcast)) { set_thread_error("soup_main: proc_world > 1 needs the allgather and bcast callbacks"); return SOUP_ERR_INVALID; }
+    const bool cell_mode = p->cell_allreduce != nullptr || p->cell_comms != nullptr;
+    // cell sharding over NCCL inside the library: the contexts of this process form the cell group (n_ctx > 1), or one process per shard
+    const bool cell_local = p->cell_comms != nullptr && n_ctx > 1;
+    int32_t cg_rank = 0, cg_world = 1;
+    if (p->cell_comms) {
+        for (int i = 0; i < n_ctx; ++i)
+            if (!p->cell_comms[i] || !ctxs[i]) { set_thread_error("soup_main: cell_comms needs one communicator per context"); return SOUP_ERR_INVALID; }
+        soup_comm_rank(p->cell_comms[0], &cg_rank, &cg_world);
+        if (cell_local && cg_world != n_ctx) { set_thread_error("soup_main: the communicator spans %d ranks but %d contexts were given", cg_world, n_ctx); return SOUP_ERR_INVALID; }
+    }
+    if (cell_mode && !p->cell_comms && n_ctx != 1) { set_thread_error("soup_main: cell sharding through callbacks takes ONE context per process"); return SOUP_ERR_INVALID; }
+    if (cell_mode && !p->cell_comms && (!p->cell_allgather || p->cell_group_size <= 0)) { set_thread_error("soup_main: cell sharding needs cell_allgather and cell_group_size"); return SOUP_ERR_INVALID; }
+    if (pworld > 1 && !p->proc_comm && (!p->allgather || !p->bcast)) { set_thread_error("soup_main: proc_world > 1 needs proc_comm or the allgather and bcast callbacks"); return SOUP_ERR_INVALID; }
     FILE* log = (FILE*)log_file;
     const int K = p->k;
     uint64_t n_cells = 0, n_loci = 0, nnz = 0;
     int32_t rc = soup_get_dims(ctx0, &n_cells, &n_loci, &nnz);
     if (rc != SOUP_OK) { set_thread_error("%s", soup_last_error(ctx0)); return rc; }
+    // cell group inside this process: context i holds the i-th contiguous range of the cells; results cover all of them in order
+    std::vector<uint64_t> cell_off(n_ctx + 1, 0);
+    if (cell_local) {
+        for (int i = 0; i < n_ctx; ++i) {
+            uint64_t nc = 0, nl = 0;
+            rc = soup_get_dims(ctxs[i], &nc, &nl, nullptr);
+            if (rc != SOUP_OK) { set_thread_error("%s", soup_last_error(ctxs[i])); return rc; }
+            if (nl != n_loci) { set_thread_error("soup_main: the cell shards must hold the same loci"); return SOUP_ERR_INVALID; }
+            cell_off[i + 1] = cell_off[i] + nc;
+        }
+        n_cells = cell_off[n_ctx];
+    }
+    const uint64_t n_cells_global = cell_local ? n_cells : p->n_cells_global;
     const int spt = (int)std::ceil((float)p->restarts / (float)p->threads);   // S:63 (f32 arithmetic)
     const int n_solves = (int)p->threads * spt;
-    const int world = pworld * n_ctx;
+    const int world = cell_local ? pworld : pworld * n_ctx;   // restart shards (a cell group runs the same solves on every member)
 
     uint8_t seed[32];
     memset(seed, p->seed, 32);                   // S:61
@@ -104,14 +126,15 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
 
     for (int run = 0; run < 3; ++run) {          // S:70
         int n_bad = 0;
-        if (cell_mode && K >= 16 && run > 0) {
+        if (cell_mode && !cell_local && K >= 16 && run > 0) {
             // the cluster sizes S:156-162 over ALL cells: add the cell group's counts up (host all-gather, K u64 per process)
             std::vector<uint64_t> mine((size_t)K, 0);
             count_cluster_cells(r->best_log_probs, have_best ? n_cells : 0, K, mine.data());
-            int32_t group = p->cell_group_size > 0 ? p->cell_group_size : 1;
+            int32_t group = p->cell_comms ? cg_world : (p->cell_group_size > 0 ? p->cell_group_size : 1);
             std::vector<uint64_t> all((size_t)K * group, 0);
-            int32_t e = p->cell_allgather(p->cell_comm_user, mine.data(), all.data(), (uint64_t)K * sizeof(uint64_t));
-            if (e != SOUP_OK) { set_thread_error("soup_main: the cell_allgather callback failed (%d)", e); return e; }
+            int32_t e = p->cell_comms ? soup_comm_allgather(p->cell_comms[0], mine.data(), all.data(), (uint64_t)K * sizeof(uint64_t))
+                                      : p->cell_allgather(p->cell_comm_user, mine.data(), all.data(), (uint64_t)K * sizeof(uint64_t));
+            if (e != SOUP_OK) { if (!p->cell_comms) set_thread_error("soup_main: the cell_allgather callback failed (%d)", e); return e; }
             for (int32_t g = 1; g < group; ++g)
                 for (int c = 0; c < K; ++c) all[c] += all[(size_t)g * K + c];
             n_bad = bad_clusters_from_counts(run, K, all.data(), bad.data(), log);
@@ -145,7 +168,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
         std::vector<PerCtx> pc(n_ctx);
         auto work = [&](int i) {
             PerCtx& c = pc[i];
-            c.lp.resize((size_t)n_cells * K);
+            c.lp.resize((size_t)(cell_local ? cell_off[i + 1] - cell_off[i] : n_cells) * K);
             c.th.resize((size_t)K * n_loci);
             c.loss.assign(n_solves, NAN);
             c.iters.assign(n_solves, 0);
@@ -154,13 +177,14 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             sp.stream_seeds = seeds.data();
             sp.init_theta = p->known_theta;
             sp.init_strategy = p->init_strategy;
-            sp.cell_allreduce = p->cell_allreduce; sp.comm_user = p->cell_comm_user; sp.n_cells_global = p->n_cells_global;
+            sp.cell_allreduce = p->cell_allreduce; sp.comm_user = p->cell_comm_user; sp.n_cells_global = n_cells_global;
+            sp.cell_comm = p->cell_comms ? p->cell_comms[i] : nullptr;
             sp.base_theta = run > 0 ? best_theta.data() : nullptr;
             sp.reinit_clusters = run > 0 ? bad.data() : nullptr;
             sp.n_reinit = run > 0 ? n_bad : 0;
             sp.iteration_cap = p->iteration_cap; sp.max_slots = p->max_slots; sp.lanes = p->lanes;
             sp.record_counts = p->record_counts; sp.keep_trace = p->verbose_trace; sp.time_kernels = p->time_kernels;
-            sp.shard_rank = prank * n_ctx + i; sp.shard_world = world;
+            sp.shard_rank = cell_local ? prank : prank * n_ctx + i; sp.shard_world = world;
             c.res.best_log_probs = c.lp.data(); c.res.best_theta = c.th.data();
             c.res.solve_loss = c.loss.data(); c.res.solve_iters = c.iters.data();
             c.rc = soup_solve(ctxs[i], &sp, &c.res);
@@ -190,8 +214,12 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             run_ms = std::max(run_ms, pc[i].stats.solve_ms);
             r->nnz_updates += pc[i].res.nnz_updates;
             r->kernel_launches += pc[i].stats.kernel_launches;
-            r->slot_iterations += pc[i].stats.slot_iterations;
+            if (!cell_local || i == 0) r->slot_iterations += pc[i].stats.slot_iterations;
             if (i == 0) { r->estep_ms += pc[i].stats.estep_ms; r->mstep_ms += pc[i].stats.mstep_ms; r->timed_iterations += pc[i].stats.timed_iterations; }
+            if (cell_local) {                      // every member of the cell group ran the same solves with the same reduced numbers
+                if (i == 0) { for (int s = prank; s < n_solves; s += world) { loss[s] = pc[0].loss[s]; iters[s] = pc[0].iters[s]; mine[s] = 1; } win_ctx = pc[0].res.has_best ? 0 : -1; }
+                continue;
+            }
             for (int s = prank * n_ctx + i; s < n_solves; s += world) { loss[s] = pc[i].loss[s]; iters[s] = pc[i].iters[s]; mine[s] = 1; }
             if (better(pc[i].res.best_loss, pc[i].res.best_solve, pc[i].res.has_best != 0,
                        win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY, win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, win_ctx >= 0))
@@ -202,7 +230,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             if (p->verbose_trace) {   // per-iteration lines S:264 / S:354, grouped per solve
                 std::vector<soup_iter_record> rec(p->iteration_cap > 0 ? p->iteration_cap : 1000);
                 for (int s = 0; s < n_solves; ++s) {
-                    int owner = s % world - prank * n_ctx;
+                    int owner = cell_local ? (s % world == prank ? 0 : -1) : s % world - prank * n_ctx;
                     if (owner < 0 || owner >= n_ctx) continue;
                     int32_t n = 0;
                     if (soup_get_trace(ctxs[owner], s, rec.data(), (int32_t)rec.size(), &n) != SOUP_OK) continue;
@@ -221,10 +249,24 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
         float w_loss = win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY;
         int32_t w_solve = win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, w_has = win_ctx >= 0 ? 1 : 0;
         std::vector<float> run_lp, run_th;
-        if (win_ctx >= 0) { run_lp.swap(pc[win_ctx].lp); run_th.swap(pc[win_ctx].th); }
+        if (win_ctx >= 0 && cell_local) {          // the members' rows, in cell order
+            run_lp.resize((size_t)n_cells * K);
+            for (int i = 0; i < n_ctx; ++i) memcpy(run_lp.data() + (size_t)cell_off[i] * K, pc[i].lp.data(), pc[i].lp.size() * sizeof(float));
+            run_th.swap(pc[0].th);
+        }
+        else if (win_ctx >= 0) { run_lp.swap(pc[win_ctx].lp); run_th.swap(pc[win_ctx].th); }
         else { run_lp.assign((size_t)n_cells * K, 0.0f); run_th.assign((size_t)K * n_loci, 0.0f); }
         if (pworld > 1) {
-            int32_t e = soup_exchange_best(prank, pworld, p->allgather, p->bcast, p->comm_user, &w_loss, &w_solve, &w_has,
+            // over NCCL inside the library (proc_comm) or through the caller's host callbacks
+            soup_allgather_fn ag = p->allgather;
+            soup_bcast_fn bc = p->bcast;
+            void* user = p->comm_user;
+            if (p->proc_comm) {
+                ag = [](void* u, const void* send, void* recv, uint64_t n) { return soup_comm_allgather((soup_comm*)u, send, recv, n); };
+                bc = [](void* u, void* buf, uint64_t n, int32_t root) { return soup_comm_bcast((soup_comm*)u, buf, n, root); };
+                user = p->proc_comm;
+            }
+            int32_t e = soup_exchange_best(prank, pworld, ag, bc, user, &w_loss, &w_solve, &w_has,
                                            run_lp.data(), run_lp.size(), run_th.data(), run_th.size(), nullptr);
             if (e != SOUP_OK) return e;
         }

@@ -876,7 +876,12 @@ struct MArgs {
     const int* group_active;        // wide role: column groups of 32*VM
     const int* long_group_active;   // long role: column groups of 32*SOUP_M_VLONG
     const Ctl* ctl;
-    float* SP; float* DP;           // cell-sharded mode: partial sums of this rank's cells, [L][Cpad] each (else nullptr)
+    // cell-sharded mode: partial sums of this rank's cells, [L][2][scols]: row 2*locus holds sum p*alt, row 2*locus + 1 holds
+    // sum p*(alt+ref), column = table column (else nullptr).  scols (a multiple of 4) covers every live column.  Rows are locus ids,
+    // the same on every rank, so a range of loci is one contiguous block for the all-reduce.
+    float* SP;
+    uint32_t scols;
+    uint32_t li_begin, li_end;      // wide role: this launch covers the positions [li_begin, li_end) of locus_order
     Packing pk;
     uint32_t L, Cpad, n_groups;
     uint32_t n_long, long_groups, long_blocks, wide_chunks, group_major;   // loci [0, n_long) of the LPT order take the long role
@@ -902,7 +907,8 @@ __device__ __forceinline__ bool m_coop(const MArgs& a, uint32_t live) { return a
 __device__ __forceinline__ uint32_t m_coop_loci(const MArgs& a, uint32_t live) { return live <= a.tail_cols ? a.n_long_tail : a.n_long; }
 
 template <int V, bool DEEP>
-__device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint32_t col0, uint32_t live_cols) {
+__device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t li, uint32_t col0, uint32_t live_cols) {
+    const uint32_t locus = a.locus_order[li];
     const uint32_t lane = threadIdx.x & 31;
     const LaneCols<V> lc = lane_setup<V>(col0, live_cols);
     const uint64_t j0 = a.col_ptr[locus];
@@ -924,12 +930,14 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t locus, uint3
             if (c >= live_cols) continue;
             c = m_table_col(a, c);
         }
-        const size_t o = (size_t)locus * a.Cpad + c;
         if (partial) {   // cell-sharded: hand the partial statistics to the all-reduce; theta_kernel finishes the M pass
-            a.SP[o] = s.v[v];
-            a.DP[o] = d.v[v];
+            if (c >= a.scols) continue;
+            const size_t so = (size_t)(2u * locus) * a.scols + c;
+            a.SP[so] = s.v[v];
+            a.SP[so + a.scols] = d.v[v];
             continue;
         }
+        const size_t o = (size_t)locus * a.Cpad + c;
         if (!a.col_write[c]) continue;                // locked cluster (S:389) or idle column
         const float th = fmaxf(fminf(__fdiv_rn(s.v[v], d.v[v]), 0.99f), 0.01f);   // S:392-393
         a.TH[o] = th;
@@ -954,7 +962,7 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256
         const uint32_t li = item / a.long_groups, group = item - li * a.long_groups;
         const uint32_t col0 = group * (32 * SOUP_M_VLONG);
         if (col0 >= live || (a.nd == a.K && !a.long_group_active[group])) return;   // (the activity masks are in table columns)
-        mstep_body<SOUP_M_VLONG, true>(a, a.locus_order[li], col0, live);
+        mstep_body<SOUP_M_VLONG, true>(a, li, col0, live);
         return;
     }
     // wide role: locus-major (group fastest) while the whole weight plane fits L2 — every group's longer loci then start
@@ -965,15 +973,17 @@ __global__ void __launch_bounds__(EM_THREADS, (VM <= 8 ? SOUP_M_MINB : 2) * (256
     else { chunk = bi / a.n_groups; group = bi - chunk * a.n_groups; }
     const uint32_t col0 = group * (32 * VM);
     if (col0 >= live || (a.nd == a.K && !a.group_active[group])) return;
-    const uint32_t li = (coop ? m_coop_loci(a, live) : a.n_long) + chunk * EM_WARPS + warp;
-    if (li >= a.L) return;
-    const uint32_t locus = a.locus_order[li];
+    // (the loci below `first` belong to the long role / the cooperative kernel; which of the two is decided on the device, so the grid
+    // always starts at li_begin and the warps in front of `first` leave)
+    const uint32_t first = coop ? m_coop_loci(a, live) : a.n_long;
+    const uint32_t li = a.li_begin + chunk * EM_WARPS + warp;
+    if (li < first || li >= a.li_end) return;
     const int v = fit_lanes<VM>(live - col0, a.no_narrow);
-    if (VM >= 16 && v == 16) mstep_body<(VM >= 16 ? 16 : VM), false>(a, locus, col0, live);
-    else if (VM >= 8 && v == 8) mstep_body<(VM >= 8 ? 8 : VM), false>(a, locus, col0, live);
-    else if (VM >= 4 && v == 4) mstep_body<(VM >= 4 ? 4 : VM), false>(a, locus, col0, live);
-    else if (VM >= 2 && v == 2) mstep_body<(VM >= 2 ? 2 : VM), false>(a, locus, col0, live);
-    else mstep_body<1, false>(a, locus, col0, live);
+    if (VM >= 16 && v == 16) mstep_body<(VM >= 16 ? 16 : VM), false>(a, li, col0, live);
+    else if (VM >= 8 && v == 8) mstep_body<(VM >= 8 ? 8 : VM), false>(a, li, col0, live);
+    else if (VM >= 4 && v == 4) mstep_body<(VM >= 4 ? 4 : VM), false>(a, li, col0, live);
+    else if (VM >= 2 && v == 2) mstep_body<(VM >= 2 ? 2 : VM), false>(a, li, col0, live);
+    else mstep_body<1, false>(a, li, col0, live);
 }
 
 // ------------------------------------------------------------------ M pass, long loci: one CTA per (locus, 256 columns)
@@ -1102,8 +1112,11 @@ __global__ void __launch_bounds__(ML_THREADS) mstep_long_kernel(const MArgs a) {
     }
     if (t >= rem) return;
     const uint32_t col = m_table_col(a, col0 + t);
+    if (partial) {
+        if (col < a.scols) { const size_t so = (size_t)(2u * locus) * a.scols + col; a.SP[so] = s; a.SP[so + a.scols] = d; }
+        return;
+    }
     const size_t o = (size_t)locus * a.Cpad + col;
-    if (partial) { a.SP[o] = s; a.DP[o] = d; return; }
     if (!a.col_write[col]) return;                                     // locked cluster (S:389) or idle column
     const float th = fmaxf(fminf(__fdiv_rn(s, d), 0.99f), 0.01f);      // S:392-393
     a.TH[o] = th;
@@ -1114,16 +1127,20 @@ __global__ void __launch_bounds__(ML_THREADS) mstep_long_kernel(const MArgs a) {
 // cell-sharded mode, after the all-reduce of (SP, DP): theta = clamp((1 + S) / (2 + D)) and the ln tables.
 // The pseudocount joins the globally reduced sum here, so the rounding differs from the sequential reference
 // (and from the single-GPU path) in the last bits: this mode agrees to tolerance, not bit for bit.
-__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ SP, const float* __restrict__ DP, const uint8_t* __restrict__ col_write,
-                                                    float* __restrict__ TH, float* __restrict__ LA, float* __restrict__ LB, uint32_t L, uint32_t Cpad) {
-    const size_t n = (size_t)L * Cpad;
+__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ stats, uint32_t scols, uint32_t row0, uint32_t rows,
+                                                    const uint8_t* __restrict__ col_write,
+                                                    float* __restrict__ TH, float* __restrict__ LA, float* __restrict__ LB, uint32_t Cpad) {
+    // the loci [row0, row0 + rows) of the reduced statistics (MArgs::SP layout), table columns [0, scols)
+    const size_t n = (size_t)rows * scols;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t c = (uint32_t)(i % Cpad);
+        const uint32_t r = (uint32_t)(i / scols), c = (uint32_t)(i - (size_t)r * scols);
         if (!col_write[c]) continue;
-        const float th = fmaxf(fminf(__fdiv_rn(__fadd_rn(1.0f, SP[i]), __fadd_rn(2.0f, DP[i])), 0.99f), 0.01f);
-        TH[i] = th;
-        LA[i] = soupmath::glibc_logf(th);
-        LB[i] = soupmath::glibc_logf(1.0f - th);
+        const size_t so = (size_t)(2u * (row0 + r)) * scols + c;
+        const float th = fmaxf(fminf(__fdiv_rn(__fadd_rn(1.0f, stats[so]), __fadd_rn(2.0f, stats[so + scols])), 0.99f), 0.01f);
+        const size_t o = (size_t)(row0 + r) * Cpad + c;
+        TH[o] = th;
+        LA[o] = soupmath::glibc_logf(th);
+        LB[o] = soupmath::glibc_logf(1.0f - th);
     }
 }
 

@@ -47,7 +47,8 @@ const Opt kOpts[] = {
     {"min_ref_umis", 0, false, false, "min ref umis to use locus for clustering"},
     {"souporcell3", 's', false, false, "activate bad cluster detection and multiple runs"},
     {"clustering_method", 'm', false, false, "choose between expectation maximization (em) and k harmonic means (khm)"},
-    {"gpus", 0, false, false, "[soupgpu] number of GPUs to shard restarts over (default: as many of the visible ones as the job can keep busy)"},
+    {"gpus", 0, false, false, "[soupgpu] number of GPUs to shard the job over (default: as many of the visible ones as the job can keep busy)"},
+    {"shard", 0, false, false, "[soupgpu] what the GPUs share out: restarts, cells (NCCL all-reduce of the M-step sums), or auto (default)"},
     {"max_slots", 0, false, false, "[soupgpu] resident solves per GPU (default: auto)"},
     {"quiet_iterations", 0, false, true, "[soupgpu] do not log per-iteration lines"},
     {"csr_cache", 0, false, false, "[soupgpu] .soupcsr cache of the parsed matrix (read if present, else written)"},
@@ -226,13 +227,43 @@ int main(int argc, char** argv) {
         const double est_s = (double)m->nnz * (double)(threads * spt) * (double)k * 17.0 * (s3 ? 3.0 : 1.0) / 1.3e12;
         n_gpu = (int)std::min<double>((double)visible, std::max(1.0, std::ceil(est_s / 0.5)));
     }
-    if ((uint64_t)n_gpu > threads * spt) n_gpu = (int)std::max<uint64_t>(1, threads * spt);
+    // restarts: solve s runs on GPU s mod n (every GPU holds the whole matrix, no collective).  cells: GPU g holds the g-th contiguous
+    // range of the cells (balanced by entries), every GPU runs every restart and NCCL all-reduces the M-step sums each iteration.
+    // auto: restarts while there are at least as many solves as GPUs, cells otherwise (and for random_cell_assignment never: it needs
+    // every cell on one GPU).
+    const std::string shard_s = get("shard", "auto");
+    if (shard_s != "auto" && shard_s != "restarts" && shard_s != "cells") die("souporcell (soupgpu): --shard must be one of auto, restarts, cells", 1);
+    bool shard_cells = shard_s == "cells" || (shard_s == "auto" && n_gpu > 1 && (uint64_t)n_gpu > threads * spt && init != "random_cell_assignment");
+    if (shard_cells && init == "random_cell_assignment") die("souporcell (soupgpu): --shard cells is not available with random_cell_assignment", 1);
+    if (!shard_cells && (uint64_t)n_gpu > threads * spt) n_gpu = (int)std::max<uint64_t>(1, threads * spt);
+    if (shard_cells && (uint64_t)n_gpu > std::max<uint64_t>(m->n_cells, 1)) n_gpu = (int)std::max<uint64_t>(m->n_cells, 1);
+    if (n_gpu == 1) shard_cells = false;
     std::vector<soup_ctx*> ctxs(n_gpu, nullptr);
-    {   // one thread per GPU: context creation, upload and the GPU transpose of the replicas run side by side
+    std::vector<soup_comm*> comms;
+    {   // one thread per GPU: context creation, upload and the GPU transpose of the replicas / shards run side by side
         std::vector<std::string> errs(n_gpu);
+        std::vector<uint64_t> cut(n_gpu + 1, 0);
+        std::vector<std::vector<uint64_t>> shard_ptr(n_gpu);
+        if (shard_cells) {
+            for (int g = 1; g < n_gpu; ++g)
+                cut[g] = std::max<uint64_t>(cut[g - 1], (uint64_t)(std::lower_bound(m->row_ptr, m->row_ptr + m->n_cells + 1, m->nnz * (uint64_t)g / (uint64_t)n_gpu) - m->row_ptr));
+            cut[n_gpu] = m->n_cells;
+            for (int g = 0; g < n_gpu; ++g) {
+                cut[g] = std::min(cut[g], m->n_cells);
+                shard_ptr[g].resize(cut[g + 1] - cut[g] + 1);
+                for (uint64_t c = cut[g]; c <= cut[g + 1]; ++c) shard_ptr[g][c - cut[g]] = m->row_ptr[c] - m->row_ptr[cut[g]];
+            }
+        }
         auto bring_up = [&](int g) {
             if (soup_ctx_create(g, nullptr, &ctxs[g]) != SOUP_OK) { errs[g] = soup_last_error(nullptr); return; }
-            if (soup_load_csr(ctxs[g], m->n_cells, m->n_loci, m->nnz, m->row_ptr, m->locus, m->alt, m->ref) != SOUP_OK) errs[g] = soup_last_error(ctxs[g]);
+            int32_t rc;
+            if (shard_cells) {
+                const uint64_t e0 = m->row_ptr[cut[g]];
+                rc = soup_load_csr(ctxs[g], cut[g + 1] - cut[g], m->n_loci, m->row_ptr[cut[g + 1]] - e0, shard_ptr[g].data(), m->locus + e0, m->alt + e0, m->ref + e0);
+            } else {
+                rc = soup_load_csr(ctxs[g], m->n_cells, m->n_loci, m->nnz, m->row_ptr, m->locus, m->alt, m->ref);
+            }
+            if (rc != SOUP_OK) errs[g] = soup_last_error(ctxs[g]);
         };
         std::vector<std::thread> pool;
         for (int g = 1; g < n_gpu; ++g) pool.emplace_back(bring_up, g);
@@ -240,6 +271,10 @@ int main(int argc, char** argv) {
         for (auto& t : pool) t.join();
         for (int g = 0; g < n_gpu; ++g)
             if (!errs[g].empty()) die("souporcell (soupgpu): " + errs[g], 101);
+        if (shard_cells) {
+            comms.assign(n_gpu, nullptr);
+            if (soup_comm_create_all(ctxs.data(), n_gpu, comms.data()) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
+        }
     }
 
     sw.lap("upload + GPU transpose");
@@ -262,6 +297,7 @@ int main(int argc, char** argv) {
     mp.k = (int32_t)k; mp.method = method_s == "khm" ? SOUP_METHOD_KHM : SOUP_METHOD_EM;
     mp.restarts = restarts; mp.threads = (uint32_t)threads; mp.seed = seed; mp.souporcell3 = s3 ? 1 : 0;
     mp.max_slots = (int32_t)parse_num(get("max_slots", "0"), "max_slots", 1024);
+    mp.cell_comms = shard_cells ? comms.data() : nullptr;
     const bool quiet = vals.count("quiet_iterations") > 0;
     mp.record_counts = quiet ? 0 : 1; mp.verbose_trace = quiet ? 0 : 1;
     std::vector<float> best_lp((size_t)m->n_cells * k);
@@ -269,12 +305,13 @@ int main(int argc, char** argv) {
     res.best_log_probs = best_lp.data();
     if (soup_main(ctxs.data(), n_gpu, &mp, &res, stderr) != SOUP_OK) die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
     sw.lap("soup_main");
-    fprintf(stderr, "soupgpu\tgpus\t%d\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, res.solve_ms, (unsigned long long)res.nnz_updates);
+    fprintf(stderr, "soupgpu\tgpus\t%d\tshard\t%s\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, shard_cells ? "cells" : "restarts", res.solve_ms, (unsigned long long)res.nnz_updates);
     // zip(barcodes, best_log_probabilities): an empty best (nothing beat -inf) prints nothing (S:133)
     if (res.has_best && soup_write_clusters(stdout, bc_blob, n_bc, best_lp.data(), m->n_cells, (int32_t)k) != SOUP_OK)
         die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
     if (fflush(stdout) != 0) die("thread 'main' panicked: failed printing to stdout", 101);
     sw.lap("write TSV");
+    for (soup_comm* c : comms) soup_comm_destroy(c);
     for (soup_ctx* c : ctxs) soup_ctx_destroy(c);
     soup_mtx_free(m);
     soup_free(bc_blob);

@@ -66,7 +66,10 @@ def generate(n_cells: int, n_loci: int, k: int, mean_loci: float, max_loci: int 
     cell_of_draw = np.repeat(np.arange(n_cells, dtype=np.int64), draws)
     locus_of_draw = np.searchsorted(cdf, rng.random(cell_of_draw.shape[0]), side="right").astype(np.int64)
     np.minimum(locus_of_draw, n_loci - 1, out=locus_of_draw)
-    key = np.unique(cell_of_draw * n_loci + locus_of_draw)                # dedupe, sorted by (cell, locus)
+    key = cell_of_draw * n_loci + locus_of_draw                           # dedupe, sorted by (cell, locus): the values np.unique returns,
+    key.sort()                                                            # without its hash pass (5x slower than the sort at 4e7 keys)
+    if key.shape[0]:
+        key = key[np.concatenate([[True], key[1:] != key[:-1]])]
     cell = key // n_loci
     locus = key % n_loci
     # cap at max_loci covered loci per cell (keep a random subset)

@@ -58,6 +58,62 @@ def test_exchange_best_two_ranks_gloo():
                 assert lp0 == float(rank + 1) and th0 == float(10 * (rank + 1))
 
 
+def _cell_worker(rank, world, port, out):
+    """One rank of the cell-sharded iteration, on the CPU: this rank's cells' share of the M-step sums S:476-483 (float32, cells ascending,
+    starting from 0 like mstep_kernel's partial mode) and of the loss S:225-230, ONE all-reduce of [S | D | loss] over gloo, then
+    theta = clamp((1 + S) / (2 + D)) as theta_kernel does (S:386-396)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle_py as orc
+    from souporcell_b200 import api
+    from helpers import synth_csr, random_theta
+    v, csr = synth_csr(n_cells=260, n_loci=1800, k=3, mean_loci=100, seed=41)
+    n, L, row_ptr, locus, alt, ref = csr
+    K = 4
+    theta = random_theta(np.random.default_rng(5), (K, L))
+    res = {}
+    for method in (0, 1):
+        whole = orc.OracleData.from_csr(*csr).step(theta, method=method, temp_step=2)
+        cuts, shards = api.split_cells(csr, world)
+        a, b = cuts[rank], cuts[rank + 1]
+        _, _, rp, lo, al, rf = shards[rank]
+        S = np.zeros((K, L), dtype=np.float32)
+        D = np.zeros((K, L), dtype=np.float32)
+        for c in range(b - a):                                  # cells ascending, entries in locus order: the reference's order inside the shard
+            p = whole["weights"][a + c]
+            for j in range(int(rp[c]), int(rp[c + 1])):
+                for k in range(K):
+                    S[k, lo[j]] = np.float32(S[k, lo[j]] + np.float32(p[k] * np.float32(al[j])))
+                    D[k, lo[j]] = np.float32(D[k, lo[j]] + np.float32(p[k] * np.float32(al[j] + rf[j])))
+        loss = np.float32(0)
+        for c in range(a, b):
+            loss = np.float32(loss + whole["lse"][c])
+        buf = torch.from_numpy(np.concatenate([S.ravel(), D.ravel(), [loss]]).astype(np.float32))
+        dist.all_reduce(buf)                                    # the one collective of the iteration
+        red = buf.numpy()
+        Sr, Dr = red[:K * L].reshape(K, L), red[K * L:2 * K * L].reshape(K, L)
+        th = np.clip((np.float32(1) + Sr) / (np.float32(2) + Dr), np.float32(0.01), np.float32(0.99))
+        res[method] = (float(np.max(np.abs(th - whole["theta_out"]) / whole["theta_out"])), float(red[-1]), float(whole["loss"]), th.tobytes())
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cell_sharded_iteration_allreduce_two_ranks_gloo():
+    """The data-path collective of the cell-sharded mode over a real process group: per-rank partial M sums and
+    losses, one all-reduce, every rank ends with the same theta, equal to the unsharded oracle iteration to north_star's 1e-5."""
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_cell_worker, args=(world, port, out), nprocs=world, join=True)
+    for method in (0, 1):
+        err0, loss0, want_loss, th0 = out[0][method]
+        err1, loss1, _, th1 = out[1][method]
+        assert th0 == th1 and loss0 == loss1                    # identical reduced numbers -> identical control decisions on every rank
+        assert err0 < 1e-5, err0
+        assert abs(loss0 - want_loss) <= 1e-5 * abs(want_loss)
+
+
 def test_restart_shards_partition_the_solves():
     # solve s -> shard s mod world: disjoint, complete, and every stream's solves keep their own seed stream / word offset
     for n_solves, world in [(50, 1), (50, 2), (100, 8), (7, 8), (1000, 4)]:
