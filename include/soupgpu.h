@@ -73,6 +73,11 @@ int32_t soup_mtx_save(const soup_mtx* m, const char* path, const char* alt_path,
 int32_t soup_mtx_load_cache(const char* path, const char* alt_path, const char* ref_path, uint32_t min_alt, uint32_t min_ref,
                             uint32_t min_alt_umis, uint32_t min_ref_umis, uint32_t flags, soup_mtx** out);
 
+/* The inverse of soup_mtx_load for generators and benchmarks: one vartrix-style Matrix Market text file (header, `% comment`, `rows cols
+ * nnz`, then `locus cell count` per entry, 1-based) from 0-based coordinates, formatted on all host cores. */
+int32_t soup_mtx_write_text(const char* path, uint64_t n_loci, uint64_t n_cells, uint64_t nnz, const int64_t* locus, const int64_t* cell,
+                            const uint32_t* count, const char* comment);
+
 /* load_barcodes S:707-718 (+ reader S:500-511: ".gz" via zlib).  Returns one malloc'ed
  * buffer of NUL-separated barcodes; free with soup_free(). */
 int32_t soup_barcodes_load(const char* path, char** blob, uint64_t* n_barcodes);

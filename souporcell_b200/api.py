@@ -33,7 +33,7 @@ EXPORTS = [
     "soup_ctx_create", "soup_ctx_destroy", "soup_load_csr", "soup_get_dims", "soup_get_csc", "soup_get_cell_totals",
     "soup_get_csr_lbc", "soup_cluster_allele_counts", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
     "soup_main", "soup_exchange_best", "soup_write_clusters", "soup_clusters_load", "soup_troublet", "soup_troublet_write", "soup_mtx_save", "soup_mtx_load_cache",
-    "soup_comm_unique_id", "soup_comm_create", "soup_comm_create_all", "soup_comm_destroy", "soup_comm_rank", "soup_comm_allgather", "soup_comm_bcast",
+    "soup_mtx_write_text", "soup_comm_unique_id", "soup_comm_create", "soup_comm_create_all", "soup_comm_destroy", "soup_comm_rank", "soup_comm_allgather", "soup_comm_bcast",
 ]
 
 
@@ -165,6 +165,7 @@ def lib():
         L.soup_troublet.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
         L.soup_troublet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int32, C.c_void_p]
+        L.soup_mtx_write_text.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
         L.soup_comm_unique_id.argtypes = [C.c_void_p]
         L.soup_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.soup_comm_create_all.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
@@ -625,6 +626,13 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
     _check(lib().soup_main(arr, len(ctxs), C.byref(p), C.byref(r), None))
     return MainResult(bool(r.has_best), r.runs, float(r.best_loss), lp, th, int(r.nnz_updates), int(r.kernel_launches), float(r.solve_ms),
                       int(r.slot_iterations), int(r.timed_iterations), float(r.estep_ms), float(r.mstep_ms))
+
+
+def write_mtx_text(path, n_loci, n_cells, locus, cell, count, comment="written by souporcell_b200.synth"):
+    """soup_mtx_write_text: one vartrix-style .mtx from 0-based int64 coordinates and uint32 counts."""
+    lo, ce = np.ascontiguousarray(locus, dtype=np.int64), np.ascontiguousarray(cell, dtype=np.int64)
+    cn = np.ascontiguousarray(count, dtype=np.uint32)
+    _check(lib().soup_mtx_write_text(os.fsencode(path), n_loci, n_cells, lo.shape[0], _ptr(lo), _ptr(ce), _ptr(cn), comment.encode()))
 
 
 class Comm:

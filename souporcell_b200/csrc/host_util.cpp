@@ -228,6 +228,46 @@ int32_t soup_thread_seeds(uint8_t seed, uint32_t threads, uint32_t run, uint8_t*
     return SOUP_OK;
 }
 
+// ---- vartrix text writer: the inverse of soup_mtx_load, for generators and benchmarks (coordinates 1-based, `locus cell count` per line)
+int32_t soup_mtx_write_text(const char* path, uint64_t n_loci, uint64_t n_cells, uint64_t nnz, const int64_t* locus, const int64_t* cell,
+                            const uint32_t* count, const char* comment) try {
+    if (!path || (nnz && (!locus || !cell || !count))) { set_thread_error("soup_mtx_write_text: bad argument"); return SOUP_ERR_INVALID; }
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_thread_error("cannot create %s", path); return SOUP_ERR_IO; }
+    fprintf(f, "%%%%MatrixMarket matrix coordinate real general\n%% %s\n%llu %llu %llu\n", comment ? comment : "written by libsoupgpu",
+            (unsigned long long)n_loci, (unsigned long long)n_cells, (unsigned long long)nnz);
+    const uint64_t block = 1u << 18, n_blocks = (nnz + block - 1) / block;
+    const unsigned T = host_threads();
+    std::vector<std::string> bufs(T);
+    auto put = [](char*& o, uint64_t v) {
+        char tmp[24];
+        int n = 0;
+        do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (n) *o++ = tmp[--n];
+    };
+    bool ok = true;
+    for (uint64_t b0 = 0; b0 < n_blocks && ok; b0 += T) {           // waves of T blocks: formatted in parallel, written in order
+        const size_t wave = (size_t)std::min<uint64_t>(T, n_blocks - b0);
+        parallel_for(T, wave, [&](size_t i) {
+            const uint64_t s0 = (b0 + i) * block, s1 = std::min(nnz, s0 + block);
+            std::string& buf = bufs[i];
+            buf.resize((size_t)(s1 - s0) * 64);
+            char* o = &buf[0];
+            for (uint64_t j = s0; j < s1; ++j) {
+                put(o, (uint64_t)locus[j] + 1); *o++ = ' ';
+                put(o, (uint64_t)cell[j] + 1); *o++ = ' ';
+                put(o, count[j]); *o++ = '\n';
+            }
+            buf.resize((size_t)(o - &buf[0]));
+        });
+        for (size_t i = 0; i < wave && ok; ++i) ok = fwrite(bufs[i].data(), 1, bufs[i].size(), f) == bufs[i].size();
+    }
+    if (fclose(f) != 0) ok = false;
+    if (!ok) { set_thread_error("write to %s failed", path); return SOUP_ERR_IO; }
+    return SOUP_OK;
+}
+SOUP_CATCH_RETURN("soup_mtx_write_text")
+
 // ---- troublet host side: load_clusters T:414-449 and the TSV writer T:36-41, T:233-243
 static std::string format_f64(double v) {   // Rust `{}` for f64
     char b[kMaxF64];

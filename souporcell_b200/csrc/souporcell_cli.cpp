@@ -115,6 +115,8 @@ struct Stopwatch {
 }  // namespace
 
 int main(int argc, char** argv) {
+    // stdout carries the TSV (S:133-147): whatever NCCL logs (NCCL_DEBUG=VERSION|WARN|INFO print to stdout by default) goes to stderr
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     Stopwatch sw;
     std::map<std::string, std::vector<std::string>> vals;
     for (int i = 1; i < argc; ++i) {

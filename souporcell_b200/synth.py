@@ -107,7 +107,11 @@ def write_files(v: Vartrix, outdir: str):
     os.makedirs(outdir, exist_ok=True)
     hdr = "%%MatrixMarket matrix coordinate real general\n% written by souporcell_b200.synth\n"
     dims = f"{v.n_loci} {v.n_cells} {v.nnz}\n"
-    for name, vals in (("alt.mtx", v.alt), ("ref.mtx", v.ref)):
+    if v.nnz > (1 << 20):          # large matrices: the library's parallel writer (same bytes; minutes of str() otherwise)
+        from . import api
+        for name, vals in (("alt.mtx", v.alt), ("ref.mtx", v.ref)):
+            api.write_mtx_text(os.path.join(outdir, name), v.n_loci, v.n_cells, v.locus, v.cell, vals)
+    for name, vals in (("alt.mtx", v.alt), ("ref.mtx", v.ref)) if v.nnz <= (1 << 20) else ():
         path = os.path.join(outdir, name)
         with open(path, "w") as fh:
             fh.write(hdr)

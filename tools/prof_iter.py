@@ -1,4 +1,4 @@
-"""Developer probe (not a test): per-iteration E / M times of one config-2 job.  usage: SOUP_DEBUG_ITERS=1 python tests/prof_iter.py [config] [max_slots] [lanes]"""
+"""Developer probe (not a test): per-iteration E / M times of one config-2 job.  usage: SOUP_DEBUG_ITERS=1 python tools/prof_iter.py [config] [max_slots] [lanes]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench

@@ -2,7 +2,7 @@
 iterations does a solve spend in each temperature step?  Decides whether an exact "skip the +0 weights" M pass is worth
 building.  p = exp(y - lse(y)) underflows to exactly +0 once y_max - y > ~104, and s + 0*alt == s.
 
-    python tests/prof_weight_sparsity.py            # a few minutes on 8 cores
+    python tools/prof_weight_sparsity.py            # a few minutes on 8 cores
 """
 import collections
 import os
