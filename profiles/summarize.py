@@ -10,6 +10,7 @@
 import argparse, collections, csv, io, json, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+L2_XBAR_PEAK_TBS = 21.07   # profiles/probes/l2_cap_probe.out
 KEEP = re.compile(r"^(gpu__time_duration\.sum|dram__bytes_(read|write)\.sum|lts__t_sector_hit_rate\.pct|l1tex__t_sector_hit_rate\.pct|"
                   r"lts__throughput\.avg\.pct_of_peak_sustained_elapsed|l1tex__throughput\.avg\.pct_of_peak_sustained_elapsed|"
                   r"sm__throughput\.avg\.pct_of_peak_sustained_elapsed|sm__warps_active\.avg\.pct_of_peak_sustained_active|"
@@ -62,7 +63,16 @@ def full_summary(rep, out, note):
                 def to_bytes(key):
                     v, u = float(d[key].replace(",", "")), units[h.index(key)]
                     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-                traffic[kern] = {"dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
+                def num(key, scale=None):
+                    v, u = float(d[key].replace(",", "")), units[h.index(key)]
+                    return v * (scale or {}).get(u, 1.0)
+                dram = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+                us = num("gpu__time_duration.sum", {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3})
+                xbar = num("derived__lts__lts2xbar_bytes.sum.per_second", {"Tbyte": 1.0, "Gbyte": 1e-3, "Tbyte/second": 1.0, "Gbyte/second": 1e-3})
+                traffic[kern] = {"dram_bytes_per_launch": dram, "capture_launch_us": us, "dram_gbs_real": dram / (us * 1e-6) / 1e9,
+                                 "l2_xbar_tbs": xbar, "l2_xbar_frac": xbar / L2_XBAR_PEAK_TBS, "l2_xbar_peak_tbs": L2_XBAR_PEAK_TBS,
+                                 "l2_xbar_peak_source": "profiles/probes/l2_cap_probe.out: best L2 -> SM row-gather rate measured on this B200 (16 MB table, 64 warps/SM)",
+                                 "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                                  "source": f"{os.path.relpath(out, ROOT)} (ncu --set full, one full-occupancy launch, 50 resident restarts)"}
     return traffic
 
@@ -76,9 +86,9 @@ if __name__ == "__main__":
     ap.add_argument("--rep-note", default="the E and M kernels of one full-occupancy iteration (50 resident restarts, k = 8, config 2: 10,000 cells x 39,930 loci, nnz 6,441,922)")
     a = ap.parse_args()
     if a.launches:
-        print(launch_list(a.launches, os.path.join(ROOT, "profiles", f"{a.tag}_launch_list.csv"), f"round 1 snapshot {a.tag} ({a.launch_note})"))
+        print(launch_list(a.launches, os.path.join(ROOT, "profiles", f"{a.tag}_launch_list.csv"), f"snapshot {a.tag} ({a.launch_note})"))
     if a.rep:
-        t = full_summary(a.rep, os.path.join(ROOT, "profiles", f"{a.tag}_ncu_full_summary.txt"), f"round 1 snapshot {a.tag}: {a.rep_note}")
+        t = full_summary(a.rep, os.path.join(ROOT, "profiles", f"{a.tag}_ncu_full_summary.txt"), f"snapshot {a.tag}: {a.rep_note}")
         if t:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as fh:
                 json.dump(t, fh, indent=1)

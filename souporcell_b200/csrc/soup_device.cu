@@ -3,6 +3,7 @@
 // Reference: /root/reference/souporcell/src/main.rs ("S:").
 #include <cuda_runtime.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
 #include <cmath>
@@ -842,15 +843,23 @@ static void launch_loss_control(soup_ctx* ctx, cudaStream_t st, bool counts, flo
 // Cell-sharded mode (each rank holds a range of cells): E -> post -> partial loss -> partial M -> ONE all-reduce of
 // [S | D | loss] over the ranks (callback, enqueued on this stream) -> theta -> control -> ...; every rank then takes
 // the same control decisions from the same reduced numbers.
+// NVTX ranges around the phases of an iteration as the host enqueues them (nsys projects them onto the kernels they launched)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 static void enqueue_iteration(IterLaunch& it) {
     soup_ctx* ctx = it.ctx;
     Workspace& w = ctx->ws;
+    NvtxRange r_iter("soup iteration");
     cudaEvent_t* ev = it.timed_iter >= 0 ? ctx->ev_k.data() + (size_t)it.timed_iter * 4 : nullptr;
     if (ev) cudaEventRecord(ev[0], ctx->stream);
-    launch_e(ctx, it.log_prior);
+    { NvtxRange r("E pass (binomial_loss)"); launch_e(ctx, it.log_prior); }
     if (ev) cudaEventRecord(ev[1], ctx->stream);
-    launch_post(ctx, it.method, it.record_counts);
+    { NvtxRange r("post (log_sum_exp, weights)"); launch_post(ctx, it.method, it.record_counts); }
     if (it.cell_mode) {
+        NvtxRange r("M pass + all-reduce + theta (cell-sharded)");
         // statistics buffer [L][2][scols] (MArgs::SP), the slots' partial losses behind it.  The M pass runs as n_ranges launches over
         // ranges of locus ids (cell_order: the long loci first, then range by range, longest first inside a range); as soon as a
         // range is complete its all-reduce and theta pass start on comm_stream while the next range is being produced.
@@ -890,13 +899,14 @@ static void enqueue_iteration(IterLaunch& it) {
     } else {
         cudaEventRecord(ctx->ev_fork, ctx->stream);
         cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
-        launch_loss_control(ctx, ctx->side, it.record_counts, it.limit);
+        { NvtxRange r("loss + control (side stream)"); launch_loss_control(ctx, ctx->side, it.record_counts, it.limit); }
         cudaEventRecord(ctx->ev_join, ctx->side);
         if (ev) cudaEventRecord(ev[2], ctx->stream);
-        launch_m(ctx);
+        { NvtxRange r("M pass (update_centers)"); launch_m(ctx); }
         if (ev) cudaEventRecord(ev[3], ctx->stream);
         cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     }
+    NvtxRange r_tail("harvest + refill + finalize");
     harvest_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(w.ctl, w.ELL, w.TH, w.best_lp, w.best_theta, (uint32_t)ctx->N, (uint32_t)ctx->L, w.Cpad, w.K_out, w.K,
                                                                w.mapped ? w.src_of_k : nullptr, w.ELLfix, w.Kf, it.base_theta_dev);
     if (!it.queue_drained) launch_refill(ctx, it.refill);

@@ -22,6 +22,8 @@
 #include <chrono>
 #include <future>
 
+#include <unistd.h>
+
 #include <cuda_runtime_api.h>
 
 #include "soup_common.hpp"
@@ -115,8 +117,6 @@ struct Stopwatch {
 }  // namespace
 
 int main(int argc, char** argv) {
-    // stdout carries the TSV (S:133-147): whatever NCCL logs (NCCL_DEBUG=VERSION|WARN|INFO print to stdout by default) goes to stderr
-    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     Stopwatch sw;
     std::map<std::string, std::vector<std::string>> vals;
     for (int i = 1; i < argc; ++i) {
@@ -149,6 +149,16 @@ int main(int argc, char** argv) {
         if (!missing.empty()) { fprintf(stderr, "error: The following required arguments were not provided:\n%s\n", missing.c_str()); usage(stderr); return 1; }
     }
     auto get = [&](const char* n, const char* d) { return vals.count(n) ? vals[n].back() : std::string(d); };
+    // stdout carries the TSV (S:133-147) and nothing else: the table is written through a private duplicate of it, and descriptor 1 is
+    // pointed at stderr for the rest of the process, so whatever a library prints there (NCCL's version / warning lines) cannot reach it
+    fflush(stdout);
+    FILE* tsv_out = nullptr;
+    {
+        const int fd = dup(STDOUT_FILENO);
+        if (fd >= 0) tsv_out = fdopen(fd, "w");
+        if (!tsv_out) die("thread 'main' panicked: failed printing to stdout", 101);
+        dup2(STDERR_FILENO, STDOUT_FILENO);
+    }
 
     // ---- load_params S:756-853
     const std::string ref_mtx = get("ref_matrix", ""), alt_mtx = get("alt_matrix", ""), barcodes_path = get("barcodes", "");
@@ -309,9 +319,9 @@ int main(int argc, char** argv) {
     sw.lap("soup_main");
     fprintf(stderr, "soupgpu\tgpus\t%d\tshard\t%s\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, shard_cells ? "cells" : "restarts", res.solve_ms, (unsigned long long)res.nnz_updates);
     // zip(barcodes, best_log_probabilities): an empty best (nothing beat -inf) prints nothing (S:133)
-    if (res.has_best && soup_write_clusters(stdout, bc_blob, n_bc, best_lp.data(), m->n_cells, (int32_t)k) != SOUP_OK)
+    if (res.has_best && soup_write_clusters(tsv_out, bc_blob, n_bc, best_lp.data(), m->n_cells, (int32_t)k) != SOUP_OK)
         die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
-    if (fflush(stdout) != 0) die("thread 'main' panicked: failed printing to stdout", 101);
+    if (fflush(tsv_out) != 0) die("thread 'main' panicked: failed printing to stdout", 101);
     sw.lap("write TSV");
     for (soup_comm* c : comms) soup_comm_destroy(c);
     for (soup_ctx* c : ctxs) soup_ctx_destroy(c);

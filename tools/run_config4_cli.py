@@ -57,7 +57,7 @@ for mode in args.modes.split(","):
         wall = time.time() - t0
         stages = {l.split("cli", 1)[1].rsplit(None, 2)[0].strip(): float(l.split()[-2]) for l in p.stderr.splitlines() if l.startswith("soup_debug cli")}
         info = [l for l in p.stderr.splitlines() if l.startswith(("soupgpu", "total loci", "best total", "No outliers"))]
-        rows = p.stdout.splitlines()
+        rows = [l for l in p.stdout.splitlines() if "\t" in l]
         tsv[mode] = rows
         rec["runs"][f"{mode}_{rep}"] = {"argv": plans[mode], "wall_s": wall, "rc": p.returncode, "stages_ms": stages, "log": info, "rows": len(rows),
                                         "tsv_md5": hashlib.md5(p.stdout.encode()).hexdigest()}
