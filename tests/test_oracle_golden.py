@@ -158,3 +158,34 @@ def test_inner_threads_are_bit_identical_to_the_serial_loop():
                 assert [(t[0], np.float32(t[1]).tobytes(), np.float32(t[2]).tobytes(), t[3]) for t in got["trace"]] == \
                        [(t[0], np.float32(t[1]).tobytes(), np.float32(t[2]).tobytes(), t[3]) for t in want["trace"]]
                 assert got["theta"].tobytes() == want["theta"].tobytes() and got["log_probs"].tobytes() == want["log_probs"].tobytes()
+
+
+def test_complete_config0_solves_against_independent_restatement():
+    """Whole em() / khm() solves at synth config 0 (300 cells, k = 3, the four restarts of --seed 4 --threads 4) from the independent
+    pure-Python restatement of main.rs:189-483 (tests/golden/make_config0_golden.py): the oracle must take the same number of iterations
+    through the same temperature steps, reach the same losses (float64-vs-libm log/exp: 1e-4 relative over a whole solve), pick the same best restart
+    and give every cell the same hard assignment."""
+    from souporcell_b200 import synth
+    g = load("config0_solves.json")
+    v = synth.generate_config(0)
+    row_ptr, locus, alt, ref, i2l = synth.filter_to_csr(v)
+    assert (v.n_cells, int(i2l.shape[0]), int(locus.shape[0])) == (g["n_cells"], g["loci_used"], g["nnz"])
+    d = orc.OracleData.from_csr(v.n_cells, int(i2l.shape[0]), row_ptr, locus, alt, ref)
+    seeds = orc.thread_seeds(g["seed"], g["threads"], 0)
+    for name, m in (("em", 0), ("khm", 1)):
+        want = g["methods"][name]
+        losses = []
+        for rec in want["solves"]:
+            theta0 = orc.init_uniform(bytes(seeds[rec["thread"]]), 0, g["k"], g["loci_used"])
+            so = d.solve(theta0, method=m)
+            assert so["iterations"] == rec["iterations"], (name, rec["thread"])
+            assert [t[0] for t in so["trace"]] == rec["temp_steps"]
+            np.testing.assert_allclose([t[1] for t in so["trace"]], rec["losses"], rtol=1e-4)
+            assert np.array_equal(np.argmax(so["log_probs"], axis=1), np.array(rec["assignments"]))
+            losses.append(so["loss"])
+        # the driver on the same seeds: same winner (S:110-125), same assignments
+        r = d.main(g["k"], method=m, restarts=g["restarts"], threads=g["threads"], seed=g["seed"])
+        best = want["best_thread"]
+        assert r["has_best"] and np.float32(r["best_loss"]) == np.float32(max(losses))
+        assert np.array_equal(np.argmax(r["best_log_probs"], axis=1), np.array(want["solves"][int(np.argmax(losses))]["assignments"]))
+        assert abs(want["solves"][best]["loss"] - r["best_loss"]) <= 1e-4 * abs(r["best_loss"])
