@@ -34,13 +34,13 @@ namespace soup {
 #define SOUP_E_U4 8
 #endif
 #ifndef SOUP_E_U8
-#define SOUP_E_U8 4
-#endif
+#define SOUP_E_U8 3      // (with SOUP_E_MINB 4: 64 registers, 32 warps per SM.  Measured, profiles/r2g_variants.txt / r2h_variants.txt: a ring of 3 rows at
+#endif                   //  4 CTAs per SM beats 4 rows at 3 CTAs by 7 %; 2 rows at 5 CTAs, 8 rows at 2 CTAs and the fully unrolled chunk are all slower)
 #ifndef SOUP_E_U16
 #define SOUP_E_U16 2
 #endif
 #ifndef SOUP_M_U8
-#define SOUP_M_U8 4
+#define SOUP_M_U8 3      // (with SOUP_M_MINB 4, like the E walk: -6 % against 4 rows at 3 CTAs per SM)
 #endif
 #ifndef SOUP_M_U16
 #define SOUP_M_U16 2
@@ -67,7 +67,7 @@ namespace soup {
 #define SOUP_M_VWIDE 8   // columns per lane for all other loci
 #endif
 #ifndef SOUP_E_MINB
-#define SOUP_E_MINB 3    // min resident CTAs per SM the E kernel is compiled for
+#define SOUP_E_MINB 4    // min resident CTAs per SM the E kernel is compiled for
 #endif
 #ifndef SOUP_M_U
 #define SOUP_M_U 8
@@ -76,7 +76,7 @@ namespace soup {
 #define SOUP_M_U2 8   // 1 / 2 columns per lane (few live solves: a latency chain per warp)
 #endif
 #ifndef SOUP_M_MINB
-#define SOUP_M_MINB 3
+#define SOUP_M_MINB 4
 #endif
 #ifndef SOUP_EM_THREADS
 #define SOUP_EM_THREADS 256
