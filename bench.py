@@ -429,6 +429,65 @@ def ours(args):
         dist.destroy_process_group()
 
 
+def ours_sweep(args):
+    """BASELINE.json configs[4]: restart sweep 10-1000 restarts at k = 32 (restart-parallel, any number of ranks).  One JSON line whose
+    `sweep` list holds, per restart count, the whole-job rate and time; `value` is the rate at the largest count."""
+    import torch
+    import souporcell_b200 as sp
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg, csr = workload(args.config)
+    n, L, row_ptr, locus, alt, ref = csr
+    K = cfg["k"]
+    method = sp.METHOD_KHM if cfg["method"] == "khm" else sp.METHOD_EM
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = sp.Context(local, stream=stream.cuda_stream)
+    ctx.load_csr(*csr)
+    comm = sp.Comm.from_torch(ctx, dist) if world > 1 else None
+    out = []
+    for restarts in (10, 30, 100, 300, 1000):
+        def job():
+            return sp.main(ctx, K, method=method, restarts=restarts, threads=restarts, seed=4, proc_rank=rank, proc_world=world, proc_comm=comm)
+        ms = upd = 0.0
+        reps = 1 if restarts >= 300 else 2
+        for i in range(1 + reps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            r = job()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1), float(r.nnz_updates)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                tm = t.clone()
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dist.all_reduce(t)
+                t[0] = tm[0]
+            if i > 0:
+                ms += float(t[0]); upd += float(t[1])
+        out.append({"restarts": restarts, "value": upd / (ms * 1e-3), "ms_per_job": ms / reps, "best_loss": float(r.best_loss)})
+    if rank == 0:
+        line = {"metric": METRIC, "value": out[-1]["value"], "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": out[-1]["ms_per_job"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config_dict(args, cfg, csr, "10..1000 in all"), sharding="restarts (solve mod world), no data-path collective"),
+                "sweep": out}
+        print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def ours_cells(args):
     """Cell-sharded leg (optional: `--shard cells`, N > 1): every rank holds a contiguous range of the cells,
     runs all restarts, and all-reduces the M-pass statistics [2][L][columns] + losses over NCCL every iteration.
@@ -496,6 +555,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config number (1-based)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="restart sweep 10..1000 (BASELINE configs[4]; use with --config 5)")
     ap.add_argument("--no-sub", action="store_true", help="skip the strong-scaling (config 3) and cell-sharded (config-4 shape) sub-records")
     ap.add_argument("--shard", default="restarts", choices=["restarts", "cells"], help="multi-GPU partition (default: restarts, weak scaling)")
     args = ap.parse_args()
@@ -504,6 +564,8 @@ def main():
         build.build_all()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.sweep:
+        ours_sweep(args)
     elif args.shard == "cells" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         ours_cells(args)
     else:

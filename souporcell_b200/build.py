@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-pthread",
 ]
-# Compile-time experiments (e.g. SOUP_NVCC_DEFINES="-DSOUP_E_FASTBATCH=1" python -m souporcell_b200.build --force); empty = the measured build.
+# Compile-time experiments (e.g. SOUP_NVCC_DEFINES="-DSOUP_E_U8=4 -DSOUP_E_MINB=3" python -m souporcell_b200.build --force); empty = the measured build.
 NVCC_FLAGS += os.environ.get("SOUP_NVCC_DEFINES", "").split()
 LINK_LIBS = ["-lz", "-lnccl"]
 LIB_SOURCES = ["soup_device.cu", "host_loader.cpp", "host_util.cpp", "soup_driver.cpp"]
