@@ -22,7 +22,13 @@
 #include <chrono>
 #include <future>
 
+#include <signal.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
 #include <unistd.h>
+
+#include <atomic>
+#include <new>
 
 #include <cuda_runtime_api.h>
 
@@ -102,6 +108,83 @@ uint64_t parse_num(const std::string& s, const char* what, uint64_t maxv) {
         v = v * 10 + (uint64_t)(s[i] - '0');
     }
     return v;
+}
+
+// ---- GPUs visible to this process, found WITHOUT touching the CUDA driver: the tokens CUDA_VISIBLE_DEVICES would take.
+// (cuInit brings up every visible GPU — 5.7 s on an 8 x B200 box against 0.6 s for one device — so a process that needs one GPU, or one
+// rank per GPU, narrows CUDA_VISIBLE_DEVICES before its first CUDA call.)
+std::vector<std::string> visible_gpu_tokens() {
+    std::vector<std::string> out;
+    if (const char* e = getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string cur;
+        for (const char* p = e;; ++p) {
+            if (*p == ',' || *p == 0) {
+                if (cur.empty() || cur == "-1") break;          // CUDA stops at the first invalid entry
+                out.push_back(cur);
+                cur.clear();
+                if (*p == 0) break;
+            } else if (*p != ' ') cur.push_back(*p);
+        }
+        return out;
+    }
+    int n = 0;
+    for (int i = 0; i < 1024; ++i) {
+        char path[64];
+        snprintf(path, sizeof path, "/dev/nvidia%d", i);
+        if (access(path, F_OK) == 0) ++n;
+    }
+    for (int i = 0; i < n; ++i) out.push_back(std::to_string(i));
+    return out;
+}
+
+// ---- one rank per GPU as PROCESSES (restart sharding): the ranks meet once per run through this block of shared memory
+struct ShmCtl {
+    std::atomic<uint32_t> count, gen, abort;
+    uint32_t world;
+    alignas(64) unsigned char slots[64][64];   // soup_allgather_fn: <= 64 bytes per rank
+    double solve_ms[64];
+    unsigned long long nnz_updates[64];
+};
+struct ProcGroup {
+    ShmCtl* ctl = nullptr;
+    unsigned char* xfer = nullptr;             // soup_bcast_fn: the winner's log-probabilities / centers
+    size_t xfer_bytes = 0;
+    int rank = 0, world = 1;
+    std::vector<pid_t> children;               // rank 0 only
+    bool wait() {                              // barrier; false = a peer failed
+        ShmCtl& c = *ctl;
+        const uint32_t g = c.gen.load();
+        if (c.count.fetch_add(1) + 1 == (uint32_t)world) { c.count.store(0); c.gen.fetch_add(1); return !c.abort.load(); }
+        for (uint64_t spins = 0; c.gen.load() == g; ++spins) {
+            if (c.abort.load()) return false;
+            if ((spins & 1023) == 1023) {      // every ~50 ms: is everybody still alive?
+                if (rank != 0 && getppid() == 1) { c.abort.store(1); return false; }
+                if (rank == 0)
+                    for (pid_t pid : children) {
+                        int st = 0;
+                        if (waitpid(pid, &st, WNOHANG) == pid && !(WIFEXITED(st) && WEXITSTATUS(st) == 0)) { c.abort.store(1); return false; }
+                    }
+            }
+            usleep(50);
+        }
+        return !c.abort.load();
+    }
+};
+int32_t shm_allgather(void* user, const void* send, void* recv, uint64_t bytes) {
+    ProcGroup& g = *(ProcGroup*)user;
+    if (bytes > 64) return SOUP_ERR_INVALID;
+    memcpy(g.ctl->slots[g.rank], send, bytes);
+    if (!g.wait()) return SOUP_ERR_INVALID;
+    for (int q = 0; q < g.world; ++q) memcpy((char*)recv + (size_t)q * bytes, g.ctl->slots[q], bytes);
+    return g.wait() ? SOUP_OK : SOUP_ERR_INVALID;
+}
+int32_t shm_bcast(void* user, void* buf, uint64_t bytes, int32_t root) {
+    ProcGroup& g = *(ProcGroup*)user;
+    if (bytes > g.xfer_bytes) return SOUP_ERR_INVALID;
+    if (g.rank == root) memcpy(g.xfer, buf, bytes);
+    if (!g.wait()) return SOUP_ERR_INVALID;
+    if (g.rank != root) memcpy(buf, g.xfer, bytes);
+    return g.wait() ? SOUP_OK : SOUP_ERR_INVALID;
 }
 
 struct Stopwatch {
@@ -188,15 +271,26 @@ int main(int argc, char** argv) {
     if (init == "kmeans++") die("thread 'main' panicked: kmeans++ not yet implemented", 101);           // S:550
     if (init == "middle_variance") die("thread 'main' panicked: middle variance not yet implemented", 101);   // S:597
 
-    // The CUDA driver context takes a few hundred ms to come up: start it now, in the background, while the text
-    // matrices are parsed on the CPU.
-    // Only device 0 here: most jobs need one GPU (below), and every further context costs its own start-up.
-    std::future<int> cuda_up = std::async(std::launch::async, [] {
-        int n = 0;
-        if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
-        if (n > 0) { cudaSetDevice(0); cudaFree(nullptr); }
-        return n;
-    });
+    // The CUDA driver takes 0.6 s to bring up one GPU and 5.7 s to bring up eight (cuInit initialises every visible device), so
+    //  * a process that will use ONE GPU narrows CUDA_VISIBLE_DEVICES to it first, and starts the driver now, in the background, while
+    //    the text matrices are parsed on the CPU;
+    //  * when several GPUs are visible and the job may want them, the driver stays untouched until the matrix is parsed and the number of
+    //    GPUs is decided: restart sharding then runs one PROCESS per GPU (each sees one device), cell sharding one thread per GPU.
+    const std::vector<std::string> gpu_tokens = visible_gpu_tokens();
+    const bool gpus_given = vals.count("gpus") > 0;
+    const int gpus_arg = gpus_given ? (int)parse_num(get("gpus", "1"), "gpus", 1024) : 0;
+    const bool one_gpu_for_sure = gpu_tokens.size() <= 1 || gpus_arg == 1;
+    if (one_gpu_for_sure && gpu_tokens.size() > 1) setenv("CUDA_VISIBLE_DEVICES", gpu_tokens[0].c_str(), 1);
+    std::future<int> cuda_up;
+    auto start_cuda = [&] {
+        cuda_up = std::async(std::launch::async, [] {
+            int n = 0;
+            if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+            if (n > 0) { cudaSetDevice(0); cudaFree(nullptr); }
+            return n;
+        });
+    };
+    if (one_gpu_for_sure) start_cuda();
 
     // ---- load_barcodes S:707-718, load_cell_data S:601-681
     char* bc_blob = nullptr;
@@ -225,16 +319,16 @@ int main(int argc, char** argv) {
     sw.lap("parse mtx + barcodes");
 
     // ---- GPUs
-    int visible = cuda_up.get();
-    sw.lap("wait for CUDA context");
+    int visible = one_gpu_for_sure ? cuda_up.get() : (int)gpu_tokens.size();
+    if (one_gpu_for_sure) sw.lap("wait for CUDA context");
     if (visible == 0) die("souporcell (soupgpu): no CUDA device available; this build has no CPU fallback", 101);
     const uint64_t spt = (restarts + threads - 1) / threads;
     int n_gpu;
-    if (vals.count("gpus")) {
-        n_gpu = (int)parse_num(get("gpus", "1"), "gpus", 1024);
+    if (gpus_given) {
+        n_gpu = gpus_arg;
         if (n_gpu < 1 || n_gpu > visible) die("souporcell (soupgpu): --gpus out of range", 1);
     } else {
-        // default: as many of the visible GPUs as the job can keep busy.  A context takes 1-2 s to come up and a replica of the
+        // default: as many of the visible GPUs as the job can keep busy.  A context takes about a second to come up and a replica of the
         // matrix; one GPU sustains ~1.3e12 (entry x cluster) updates per second, a solve runs ~17 iterations, souporcell3 up to 3 runs
         const double est_s = (double)m->nnz * (double)(threads * spt) * (double)k * 17.0 * (s3 ? 3.0 : 1.0) / 1.3e12;
         n_gpu = (int)std::min<double>((double)visible, std::max(1.0, std::ceil(est_s / 0.5)));
@@ -250,10 +344,53 @@ int main(int argc, char** argv) {
     if (!shard_cells && (uint64_t)n_gpu > threads * spt) n_gpu = (int)std::max<uint64_t>(1, threads * spt);
     if (shard_cells && (uint64_t)n_gpu > std::max<uint64_t>(m->n_cells, 1)) n_gpu = (int)std::max<uint64_t>(m->n_cells, 1);
     if (n_gpu == 1) shard_cells = false;
-    std::vector<soup_ctx*> ctxs(n_gpu, nullptr);
+
+    // ---- init_cluster_centers_known_genotypes S:514-542 (host only; before the ranks split)
+    std::vector<float> known_theta;
+    if (known_gt) {
+        std::string blob;
+        int n_names = 0;
+        if (vals.count("known_genotypes_sample_names"))
+            for (const std::string& nm : vals["known_genotypes_sample_names"]) { blob += nm; blob.push_back('\0'); ++n_names; }
+        known_theta.resize((size_t)k * m->n_loci);
+        if (soup_known_genotypes_load(get("known_genotypes", "").c_str(), blob.c_str(), n_names, (int32_t)k, m->index_to_locus, m->n_loci, known_theta.data()) != SOUP_OK)
+            die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    }
+
+    // ---- restart sharding over several GPUs: one process per GPU.  The parsed matrix is inherited by fork() (copy-on-write, never
+    // written), each rank sees ONE device — its driver comes up in the time one GPU takes, all ranks in parallel — and the ranks meet
+    // once per run in shared memory (soup_main's allgather / bcast callbacks).  Rank 0 is this process and prints the TSV.
+    ProcGroup pg;
+    const bool multi_proc = !one_gpu_for_sure && !shard_cells && n_gpu > 1 && !getenv("SOUP_CLI_ONE_PROCESS");
+    if (multi_proc) {
+        pg.world = n_gpu;
+        pg.xfer_bytes = std::max<size_t>((size_t)m->n_cells * k, (size_t)k * m->n_loci) * sizeof(float);
+        void* map = mmap(nullptr, sizeof(ShmCtl) + pg.xfer_bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+        if (map == MAP_FAILED) die("souporcell (soupgpu): cannot map the ranks' shared memory", 101);
+        pg.ctl = new (map) ShmCtl();
+        pg.ctl->count.store(0); pg.ctl->gen.store(0); pg.ctl->abort.store(0);
+        pg.ctl->world = (uint32_t)n_gpu;
+        pg.xfer = (unsigned char*)map + sizeof(ShmCtl);
+        fflush(stderr);
+        for (int g = 1; g < n_gpu; ++g) {
+            const pid_t pid = fork();
+            if (pid < 0) { pg.ctl->abort.store(1); die("souporcell (soupgpu): fork failed", 101); }
+            if (pid == 0) { pg.rank = g; pg.children.clear(); sw.on = false; break; }
+            pg.children.push_back(pid);
+        }
+        setenv("CUDA_VISIBLE_DEVICES", gpu_tokens[pg.rank].c_str(), 1);
+    } else if (!one_gpu_for_sure && n_gpu == 1 && gpu_tokens.size() > 1) {
+        setenv("CUDA_VISIBLE_DEVICES", gpu_tokens[0].c_str(), 1);
+    }
+    auto fail = [&](const std::string& msg) {     // a rank that fails takes the others down with it
+        if (pg.ctl) pg.ctl->abort.store(1);
+        die(msg, 101);
+    };
+    const int n_ctx = multi_proc ? 1 : n_gpu;      // contexts of THIS process
+    std::vector<soup_ctx*> ctxs(n_ctx, nullptr);
     std::vector<soup_comm*> comms;
     {   // one thread per GPU: context creation, upload and the GPU transpose of the replicas / shards run side by side
-        std::vector<std::string> errs(n_gpu);
+        std::vector<std::string> errs(n_ctx);
         std::vector<uint64_t> cut(n_gpu + 1, 0);
         std::vector<std::vector<uint64_t>> shard_ptr(n_gpu);
         if (shard_cells) {
@@ -278,11 +415,11 @@ int main(int argc, char** argv) {
             if (rc != SOUP_OK) errs[g] = soup_last_error(ctxs[g]);
         };
         std::vector<std::thread> pool;
-        for (int g = 1; g < n_gpu; ++g) pool.emplace_back(bring_up, g);
+        for (int g = 1; g < n_ctx; ++g) pool.emplace_back(bring_up, g);
         bring_up(0);
         for (auto& t : pool) t.join();
-        for (int g = 0; g < n_gpu; ++g)
-            if (!errs[g].empty()) die("souporcell (soupgpu): " + errs[g], 101);
+        for (int g = 0; g < n_ctx; ++g)
+            if (!errs[g].empty()) fail("souporcell (soupgpu): " + errs[g]);
         if (shard_cells) {
             comms.assign(n_gpu, nullptr);
             if (soup_comm_create_all(ctxs.data(), n_gpu, comms.data()) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
@@ -290,18 +427,6 @@ int main(int argc, char** argv) {
     }
 
     sw.lap("upload + GPU transpose");
-    // ---- init_cluster_centers_known_genotypes S:514-542
-    std::vector<float> known_theta;
-    if (known_gt) {
-        std::string blob;
-        int n_names = 0;
-        if (vals.count("known_genotypes_sample_names"))
-            for (const std::string& nm : vals["known_genotypes_sample_names"]) { blob += nm; blob.push_back('\0'); ++n_names; }
-        known_theta.resize((size_t)k * m->n_loci);
-        if (soup_known_genotypes_load(get("known_genotypes", "").c_str(), blob.c_str(), n_names, (int32_t)k, m->index_to_locus, m->n_loci, known_theta.data()) != SOUP_OK)
-            die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
-    }
-
     // ---- souporcell_main S:60-148
     soup_main_params mp{};
     mp.known_theta = known_gt ? known_theta.data() : nullptr;
@@ -315,17 +440,53 @@ int main(int argc, char** argv) {
     std::vector<float> best_lp((size_t)m->n_cells * k);
     soup_main_result res{};
     res.best_log_probs = best_lp.data();
-    if (soup_main(ctxs.data(), n_gpu, &mp, &res, stderr) != SOUP_OK) die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
+    // every rank logs its own solves; the run-level lines (cluster analysis, best total) come from rank 0 alone
+    char* log_buf = nullptr;
+    size_t log_len = 0;
+    FILE* log = pg.rank == 0 ? stderr : open_memstream(&log_buf, &log_len);
+    if (multi_proc) { mp.proc_rank = pg.rank; mp.proc_world = pg.world; mp.allgather = shm_allgather; mp.bcast = shm_bcast; mp.comm_user = &pg; }
+    if (soup_main(ctxs.data(), n_ctx, &mp, &res, log) != SOUP_OK) fail(std::string("thread 'main' panicked: ") + soup_last_error(nullptr));
     sw.lap("soup_main");
-    fprintf(stderr, "soupgpu\tgpus\t%d\tshard\t%s\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, shard_cells ? "cells" : "restarts", res.solve_ms, (unsigned long long)res.nnz_updates);
+    double solve_ms = res.solve_ms;
+    unsigned long long nnz_updates = res.nnz_updates;
+    if (multi_proc) {
+        pg.ctl->solve_ms[pg.rank] = res.solve_ms;
+        pg.ctl->nnz_updates[pg.rank] = res.nnz_updates;
+        if (pg.rank != 0) {
+            fclose(log);
+            std::string own;
+            for (const char* p = log_buf; p && *p;) {
+                const char* e = strchr(p, '\n');
+                const size_t len = e ? (size_t)(e - p) + 1 : strlen(p);
+                if (!strncmp(p, "thread ", 7) || !strncmp(p, "binomial", 8)) own.append(p, len);
+                p += len;
+            }
+            fwrite(own.data(), 1, own.size(), stderr);
+            fflush(stderr);
+        }
+        if (!pg.wait()) fail("souporcell (soupgpu): another rank failed");
+        if (pg.rank != 0) _exit(0);               // (no teardown: the process ends here)
+        solve_ms = 0; nnz_updates = 0;
+        for (int q = 0; q < pg.world; ++q) { solve_ms = std::max(solve_ms, pg.ctl->solve_ms[q]); nnz_updates += pg.ctl->nnz_updates[q]; }
+    }
+    fprintf(stderr, "soupgpu\tgpus\t%d\tshard\t%s\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, shard_cells ? "cells" : "restarts", solve_ms, nnz_updates);
     // zip(barcodes, best_log_probabilities): an empty best (nothing beat -inf) prints nothing (S:133)
     if (res.has_best && soup_write_clusters(tsv_out, bc_blob, n_bc, best_lp.data(), m->n_cells, (int32_t)k) != SOUP_OK)
-        die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
-    if (fflush(tsv_out) != 0) die("thread 'main' panicked: failed printing to stdout", 101);
+        fail(std::string("thread 'main' panicked: ") + soup_last_error(nullptr));
+    if (fflush(tsv_out) != 0) fail("thread 'main' panicked: failed printing to stdout");
     sw.lap("write TSV");
-    for (soup_comm* c : comms) soup_comm_destroy(c);
-    for (soup_ctx* c : ctxs) soup_ctx_destroy(c);
-    soup_mtx_free(m);
-    soup_free(bc_blob);
-    return 0;
+    int rc = 0;
+    for (pid_t pid : pg.children) {
+        int st = 0;
+        if (waitpid(pid, &st, 0) == pid && !(WIFEXITED(st) && WEXITSTATUS(st) == 0)) rc = 101;
+    }
+    if (getenv("SOUP_CLI_TEARDOWN")) {            // orderly release of every device object (leak checkers); the default is to end the
+        for (soup_comm* c : comms) soup_comm_destroy(c);   // process right here: nothing is pending, and tearing down eight contexts with
+        for (soup_ctx* c : ctxs) soup_ctx_destroy(c);      // gigabytes of buffers costs a second or two of wall time that buys nothing
+        soup_mtx_free(m);
+        soup_free(bc_blob);
+        return rc;
+    }
+    fflush(stderr);
+    _exit(rc);
 }

@@ -707,6 +707,14 @@ def test_cell_sharded_two_gpus_real_nccl(k, s3, method, tmp_path):
     two = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "cells"], capture_output=True, text=True)
     assert one.returncode == 0 and two.returncode == 0, two.stderr[-600:]
     assert "shard\tcells" in two.stderr
+    # restart sharding over 2 GPUs = one PROCESS per GPU meeting in shared memory: byte-identical TSV, every solve logged exactly once
+    procs = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "restarts"], capture_output=True, text=True)
+    assert procs.returncode == 0, procs.stderr[-600:]
+    assert procs.stdout == one.stdout and "gpus\t2\tshard\trestarts" in procs.stderr
+    solves = lambda err: sorted(l for l in err.splitlines() if l.startswith(("thread ", "binomial")))
+    assert [l.split(" best so far")[0] for l in solves(procs.stderr) if l.startswith("thread ")] == [l.split(" best so far")[0] for l in solves(one.stderr) if l.startswith("thread ")]
+    assert [l for l in solves(procs.stderr) if l.startswith("binomial")] == [l for l in solves(one.stderr) if l.startswith("binomial")]
+    assert procs.stderr.count("best total log probability") == 1
     col = lambda out: [ln.split("\t")[:2] for ln in out.splitlines()]
     assert col(one.stdout) == col(two.stdout) and len(col(one.stdout)) == v.n_cells
     f1 = np.array([ln.split("\t")[2:] for ln in one.stdout.splitlines()], dtype=np.float64)

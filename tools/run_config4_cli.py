@@ -73,7 +73,19 @@ if "single" in tsv:
         same = tsv[mode] == ref_rows
         assign = [r.split("\t")[1] for r in tsv[mode]]
         agree = sum(a == b for a, b in zip(assign, ref_assign)) / max(len(ref_assign), 1)
-        rec["runs"][f"{mode}_vs_single"] = {"tsv_identical": same, "assignments_agree": agree}
+        # cluster labels are arbitrary (another restart may win): agreement after the best one-to-one matching of the labels, and
+        # the adjusted Rand index of the two partitions
+        a, b = np.array(assign, dtype=np.int64), np.array(ref_assign, dtype=np.int64)
+        kk = int(max(a.max(), b.max())) + 1
+        cont = np.zeros((kk, kk), dtype=np.int64)
+        np.add.at(cont, (a, b), 1)
+        from scipy.optimize import linear_sum_assignment
+        ri, ci = linear_sum_assignment(-cont)
+        matched = int(cont[ri, ci].sum()) / max(len(a), 1)
+        comb = lambda x: x * (x - 1) / 2.0
+        sum_ij, sa, sb, tot = comb(cont).sum(), comb(cont.sum(1)).sum(), comb(cont.sum(0)).sum(), comb(len(a))
+        ari = float((sum_ij - sa * sb / tot) / (0.5 * (sa + sb) - sa * sb / tot))
+        rec["runs"][f"{mode}_vs_single"] = {"tsv_identical": same, "assignments_agree_raw_labels": agree, "assignments_agree_matched_labels": matched, "adjusted_rand_index": ari}
         print(mode, "vs single:", rec["runs"][f"{mode}_vs_single"], flush=True)
 with open(os.path.join(args.out, f"config{args.config}_gpus{n_gpu}.json"), "w") as fh:
     json.dump(rec, fh, indent=1)
