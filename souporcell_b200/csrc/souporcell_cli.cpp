@@ -144,6 +144,7 @@ struct ShmCtl {
     alignas(64) unsigned char slots[64][64];   // soup_allgather_fn: <= 64 bytes per rank
     double solve_ms[64];
     unsigned long long nnz_updates[64];
+    unsigned char nccl_id[SOUP_COMM_ID_BYTES];   // cell sharding: rank 0's ncclUniqueId
 };
 struct ProcGroup {
     ShmCtl* ctl = nullptr;
@@ -357,11 +358,13 @@ int main(int argc, char** argv) {
             die(std::string("thread 'main' panicked: ") + soup_last_error(nullptr), 101);
     }
 
-    // ---- restart sharding over several GPUs: one process per GPU.  The parsed matrix is inherited by fork() (copy-on-write, never
-    // written), each rank sees ONE device — its driver comes up in the time one GPU takes, all ranks in parallel — and the ranks meet
-    // once per run in shared memory (soup_main's allgather / bcast callbacks).  Rank 0 is this process and prints the TSV.
+    // ---- several GPUs: one process per GPU.  The parsed matrix is inherited by fork() (copy-on-write, never written), each rank sees
+    // ONE device — its driver comes up in the time one GPU takes, all ranks in parallel.  Restart sharding: the ranks meet once per run
+    // in shared memory (soup_main's allgather / bcast callbacks).  Cell sharding: rank 0's NCCL id travels through the same block, the
+    // ranks form one communicator (soup_comm_create) and every rank's rows of the result are collected there at the end.
+    // Rank 0 is this process and prints the TSV.  (SOUP_CLI_ONE_PROCESS keeps everything in one process: one thread per GPU.)
     ProcGroup pg;
-    const bool multi_proc = !one_gpu_for_sure && !shard_cells && n_gpu > 1 && !getenv("SOUP_CLI_ONE_PROCESS");
+    const bool multi_proc = !one_gpu_for_sure && n_gpu > 1 && n_gpu <= 64 && !getenv("SOUP_CLI_ONE_PROCESS");
     if (multi_proc) {
         pg.world = n_gpu;
         pg.xfer_bytes = std::max<size_t>((size_t)m->n_cells * k, (size_t)k * m->n_loci) * sizeof(float);
@@ -387,6 +390,7 @@ int main(int argc, char** argv) {
         die(msg, 101);
     };
     const int n_ctx = multi_proc ? 1 : n_gpu;      // contexts of THIS process
+    uint64_t cell_lo = 0, cell_hi = m->n_cells;    // cells whose rows this process's soup_main returns
     std::vector<soup_ctx*> ctxs(n_ctx, nullptr);
     std::vector<soup_comm*> comms;
     {   // one thread per GPU: context creation, upload and the GPU transpose of the replicas / shards run side by side
@@ -403,12 +407,13 @@ int main(int argc, char** argv) {
                 for (uint64_t c = cut[g]; c <= cut[g + 1]; ++c) shard_ptr[g][c - cut[g]] = m->row_ptr[c] - m->row_ptr[cut[g]];
             }
         }
-        auto bring_up = [&](int g) {
+        auto bring_up = [&](int g) {               // context g of this process: device g, and (cell sharding) the shard of its rank
+            const int sh = multi_proc ? pg.rank : g;
             if (soup_ctx_create(g, nullptr, &ctxs[g]) != SOUP_OK) { errs[g] = soup_last_error(nullptr); return; }
             int32_t rc;
             if (shard_cells) {
-                const uint64_t e0 = m->row_ptr[cut[g]];
-                rc = soup_load_csr(ctxs[g], cut[g + 1] - cut[g], m->n_loci, m->row_ptr[cut[g + 1]] - e0, shard_ptr[g].data(), m->locus + e0, m->alt + e0, m->ref + e0);
+                const uint64_t e0 = m->row_ptr[cut[sh]];
+                rc = soup_load_csr(ctxs[g], cut[sh + 1] - cut[sh], m->n_loci, m->row_ptr[cut[sh + 1]] - e0, shard_ptr[sh].data(), m->locus + e0, m->alt + e0, m->ref + e0);
             } else {
                 rc = soup_load_csr(ctxs[g], m->n_cells, m->n_loci, m->nnz, m->row_ptr, m->locus, m->alt, m->ref);
             }
@@ -420,9 +425,17 @@ int main(int argc, char** argv) {
         for (auto& t : pool) t.join();
         for (int g = 0; g < n_ctx; ++g)
             if (!errs[g].empty()) fail("souporcell (soupgpu): " + errs[g]);
-        if (shard_cells) {
+        if (shard_cells && multi_proc) {           // one rank per process: ncclCommInitRank over the id rank 0 publishes
+            if (pg.rank == 0 && soup_comm_unique_id(pg.ctl->nccl_id) != SOUP_OK) fail(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr));
+            if (!pg.wait()) fail("souporcell (soupgpu): another rank failed");
+            comms.assign(1, nullptr);
+            if (soup_comm_create(ctxs[0], pg.ctl->nccl_id, pg.rank, pg.world, &comms[0]) != SOUP_OK) fail(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr));
+        } else if (shard_cells) {
             comms.assign(n_gpu, nullptr);
             if (soup_comm_create_all(ctxs.data(), n_gpu, comms.data()) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
+        }
+        if (shard_cells && multi_proc) {           // where this rank's rows of the result go
+            cell_lo = cut[pg.rank]; cell_hi = cut[pg.rank + 1];
         }
     }
 
@@ -444,7 +457,8 @@ int main(int argc, char** argv) {
     char* log_buf = nullptr;
     size_t log_len = 0;
     FILE* log = pg.rank == 0 ? stderr : open_memstream(&log_buf, &log_len);
-    if (multi_proc) { mp.proc_rank = pg.rank; mp.proc_world = pg.world; mp.allgather = shm_allgather; mp.bcast = shm_bcast; mp.comm_user = &pg; }
+    if (multi_proc && !shard_cells) { mp.proc_rank = pg.rank; mp.proc_world = pg.world; mp.allgather = shm_allgather; mp.bcast = shm_bcast; mp.comm_user = &pg; }
+    if (multi_proc && shard_cells) mp.n_cells_global = m->n_cells;
     if (soup_main(ctxs.data(), n_ctx, &mp, &res, log) != SOUP_OK) fail(std::string("thread 'main' panicked: ") + soup_last_error(nullptr));
     sw.lap("soup_main");
     double solve_ms = res.solve_ms;
@@ -452,7 +466,11 @@ int main(int argc, char** argv) {
     if (multi_proc) {
         pg.ctl->solve_ms[pg.rank] = res.solve_ms;
         pg.ctl->nnz_updates[pg.rank] = res.nnz_updates;
-        if (pg.rank != 0) {
+        if (shard_cells) {                         // every rank ran every solve on its cells: collect the rows, in cell order
+            if (res.has_best) memcpy(pg.xfer + (size_t)cell_lo * k * sizeof(float), best_lp.data(), (size_t)(cell_hi - cell_lo) * k * sizeof(float));
+            pg.ctl->nnz_updates[pg.rank] = res.nnz_updates;
+        }
+        if (pg.rank != 0 && !shard_cells) {
             fclose(log);
             std::string own;
             for (const char* p = log_buf; p && *p;) {
@@ -468,6 +486,7 @@ int main(int argc, char** argv) {
         if (pg.rank != 0) _exit(0);               // (no teardown: the process ends here)
         solve_ms = 0; nnz_updates = 0;
         for (int q = 0; q < pg.world; ++q) { solve_ms = std::max(solve_ms, pg.ctl->solve_ms[q]); nnz_updates += pg.ctl->nnz_updates[q]; }
+        if (shard_cells && res.has_best) memcpy(best_lp.data(), pg.xfer, (size_t)m->n_cells * k * sizeof(float));
     }
     fprintf(stderr, "soupgpu\tgpus\t%d\tshard\t%s\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, shard_cells ? "cells" : "restarts", solve_ms, nnz_updates);
     // zip(barcodes, best_log_probabilities): an empty best (nothing beat -inf) prints nothing (S:133)

@@ -704,8 +704,10 @@ def test_cell_sharded_two_gpus_real_nccl(k, s3, method, tmp_path):
     a, r, b = synth.write_files(v, str(tmp_path))
     args = ["-a", a, "-r", r, "-b", b, "-k", str(k), "--restarts", "6", "-t", "3", "--seed", "5", "-m", "khm" if method == sp.METHOD_KHM else "em", "-s", "true" if s3 else "false"]
     one = subprocess.run([build.CLI] + args + ["--gpus", "1"], capture_output=True, text=True)
-    two = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "cells"], capture_output=True, text=True)
+    two = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "cells"], capture_output=True, text=True)       # one process per GPU
     assert one.returncode == 0 and two.returncode == 0, two.stderr[-600:]
+    two_t = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "cells"], capture_output=True, text=True, env=dict(os.environ, SOUP_CLI_ONE_PROCESS="1"))
+    assert two_t.returncode == 0 and two_t.stdout == two.stdout, two_t.stderr[-600:]                                  # one thread per GPU: the same bytes
     assert "shard\tcells" in two.stderr
     # restart sharding over 2 GPUs = one PROCESS per GPU meeting in shared memory: byte-identical TSV, every solve logged exactly once
     procs = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "restarts"], capture_output=True, text=True)

@@ -64,11 +64,12 @@ for mode in args.modes.split(","):
         print(mode, rep, json.dumps(rec["runs"][f"{mode}_{rep}"]), flush=True)
         if p.returncode != 0:
             print(p.stderr[-2000:], flush=True)
-if "single" in tsv:
-    ref_rows = tsv["single"]
+ref_mode = "single" if "single" in tsv else ("restarts" if "restarts" in tsv else None)   # (restart sharding prints the single-GPU run's bytes)
+if ref_mode:
+    ref_rows = tsv[ref_mode]
     ref_assign = [r.split("\t")[1] for r in ref_rows]
     for mode in tsv:
-        if mode == "single":
+        if mode == ref_mode:
             continue
         same = tsv[mode] == ref_rows
         assign = [r.split("\t")[1] for r in tsv[mode]]
@@ -85,7 +86,7 @@ if "single" in tsv:
         comb = lambda x: x * (x - 1) / 2.0
         sum_ij, sa, sb, tot = comb(cont).sum(), comb(cont.sum(1)).sum(), comb(cont.sum(0)).sum(), comb(len(a))
         ari = float((sum_ij - sa * sb / tot) / (0.5 * (sa + sb) - sa * sb / tot))
-        rec["runs"][f"{mode}_vs_single"] = {"tsv_identical": same, "assignments_agree_raw_labels": agree, "assignments_agree_matched_labels": matched, "adjusted_rand_index": ari}
-        print(mode, "vs single:", rec["runs"][f"{mode}_vs_single"], flush=True)
+        rec["runs"][f"{mode}_vs_{ref_mode}"] = {"tsv_identical": same, "assignments_agree_raw_labels": agree, "assignments_agree_matched_labels": matched, "adjusted_rand_index": ari}
+        print(mode, "vs", ref_mode, rec["runs"][f"{mode}_vs_{ref_mode}"], flush=True)
 with open(os.path.join(args.out, f"config{args.config}_gpus{n_gpu}.json"), "w") as fh:
     json.dump(rec, fh, indent=1)
