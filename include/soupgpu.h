@@ -330,6 +330,10 @@ typedef struct soup_main_params {
      *  - proc_comm: restart sharding over processes (proc_rank / proc_world): the winner exchange runs over it instead of allgather / bcast. */
     soup_comm* const* cell_comms;     /* [n_ctx] or NULL */
     soup_comm* proc_comm;             /* or NULL */
+    /* Several cell groups on the same GPUs (0 / 1 = one): the n_ctx contexts are cell_groups groups of n_ctx / cell_groups contexts,
+     * group-major; every group holds the same cell ranges, has its own communicator and runs its share of the restarts (solve mod
+     * groups), so one group's all-reduce overlaps the other groups' E / M passes. */
+    int32_t cell_groups;
 } soup_main_params;
 typedef struct soup_main_result {
     int32_t has_best, runs;

@@ -89,7 +89,7 @@ class _MainParams(C.Structure):
                 ("known_theta", C.c_void_p), ("proc_rank", C.c_int32), ("proc_world", C.c_int32), ("allgather", ALLGATHER_FN), ("bcast", BCAST_FN),
                 ("comm_user", C.c_void_p), ("init_strategy", C.c_int32), ("cell_allreduce", C.c_void_p), ("cell_comm_user", C.c_void_p),
                 ("n_cells_global", C.c_uint64), ("cell_allgather", ALLGATHER_FN), ("cell_group_size", C.c_int32),
-                ("cell_comms", C.POINTER(C.c_void_p)), ("proc_comm", C.c_void_p)]
+                ("cell_comms", C.POINTER(C.c_void_p)), ("proc_comm", C.c_void_p), ("cell_groups", C.c_int32)]
 
 
 class _MainResult(C.Structure):
@@ -587,7 +587,7 @@ class MainResult:
 def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3=False, iteration_cap=0, max_slots=0,
          lanes=0, record_counts=False, verbose_trace=False, time_kernels=False, proc_rank=0, proc_world=1, allgather=None,
          bcast=None, known_theta=None, init_strategy=INIT_RANDOM_UNIFORM, cell_allreduce=None, cell_allgather=None, cell_group_size=0,
-         n_cells_global=0, cell_comms=None, proc_comm=None) -> MainResult:
+         n_cells_global=0, cell_comms=None, proc_comm=None, cell_groups=1) -> MainResult:
     """souporcell_main S:60-131 over one context per GPU: restart-sharded, or — with `cell_comms`, one Comm per context — cell-sharded
     (context i holds the i-th contiguous range of the cells; the result covers all of them in order)."""
     if isinstance(ctxs, Context):
@@ -616,9 +616,10 @@ def main(ctxs, k, method=METHOD_EM, restarts=100, threads=1, seed=4, souporcell3
         comm_arr = (C.c_void_p * len(ctxs))(*[c._h for c in cell_comms])
         p.cell_comms = comm_arr
         p.n_cells_global = n_cells_global
+        p.cell_groups = cell_groups
     if proc_comm is not None:
         p.proc_comm = proc_comm._h
-    n, L = (sum(c.n_cells for c in ctxs) if cell_comms is not None else ctxs[0].n_cells), ctxs[0].n_loci
+    n, L = (sum(c.n_cells for c in ctxs[:len(ctxs) // max(cell_groups, 1)]) if cell_comms is not None else ctxs[0].n_cells), ctxs[0].n_loci
     lp = np.zeros((n, k), dtype=np.float32)
     th = np.zeros((k, L), dtype=np.float32)
     r = _MainResult()

@@ -79,15 +79,22 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
     if (p->threads == 0 || p->k <= 0) { set_thread_error("soup_main: threads and k must be >= 1"); return SOUP_ERR_INVALID; }
     const int pworld = p->proc_world > 1 ? p->proc_world : 1, prank = pworld > 1 ? p->proc_rank : 0;
     const bool cell_mode = p->cell_allreduce != nullptr || p->cell_comms != nullptr;
-    // cell sharding over NCCL inside the library: the contexts of this process form the cell group (n_ctx > 1), or one process per shard
-    const bool cell_local = p->cell_comms != nullptr && n_ctx > 1;
+    // Cell sharding over NCCL inside the library.  The contexts are G cell groups (soup_main_params.cell_groups, default 1) of SL
+    // contexts each, group-major: context g*SL + s holds the s-th of this process's cell ranges for group g.  Every group spans the
+    // same S ranges (the size of its communicator) and runs its own share of the restarts (solve mod groups) — two groups on the SAME
+    // GPUs overlap one group's all-reduce with the other's E / M passes.  SL == S: every range is here (one process, the result covers
+    // all cells); SL < S: one process per range.
+    const int G = p->cell_comms && p->cell_groups > 1 ? p->cell_groups : 1;
+    const int SL = n_ctx / G;
     int32_t cg_rank = 0, cg_world = 1;
     if (p->cell_comms) {
+        if (n_ctx % G != 0) { set_thread_error("soup_main: %d contexts do not split into %d cell groups", n_ctx, G); return SOUP_ERR_INVALID; }
         for (int i = 0; i < n_ctx; ++i)
             if (!p->cell_comms[i] || !ctxs[i]) { set_thread_error("soup_main: cell_comms needs one communicator per context"); return SOUP_ERR_INVALID; }
         soup_comm_rank(p->cell_comms[0], &cg_rank, &cg_world);
-        if (cell_local && cg_world != n_ctx) { set_thread_error("soup_main: the communicator spans %d ranks but %d contexts were given", cg_world, n_ctx); return SOUP_ERR_INVALID; }
+        if (SL != 1 && SL != cg_world) { set_thread_error("soup_main: a cell group spans %d ranks but %d of its contexts were given (1 or all of them)", cg_world, SL); return SOUP_ERR_INVALID; }
     }
+    const bool cell_local = p->cell_comms != nullptr && SL == cg_world;   // every cell range of a group is in this process
     if (cell_mode && !p->cell_comms && n_ctx != 1) { set_thread_error("soup_main: cell sharding through callbacks takes ONE context per process"); return SOUP_ERR_INVALID; }
     if (cell_mode && !p->cell_comms && (!p->cell_allgather || p->cell_group_size <= 0)) { set_thread_error("soup_main: cell sharding needs cell_allgather and cell_group_size"); return SOUP_ERR_INVALID; }
     if (pworld > 1 && !p->proc_comm && (!p->allgather || !p->bcast)) { set_thread_error("soup_main: proc_world > 1 needs proc_comm or the allgather and bcast callbacks"); return SOUP_ERR_INVALID; }
@@ -97,21 +104,23 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
     int32_t rc = soup_get_dims(ctx0, &n_cells, &n_loci, &nnz);
     if (rc != SOUP_OK) { set_thread_error("%s", soup_last_error(ctx0)); return rc; }
     // cell group inside this process: context i holds the i-th contiguous range of the cells; results cover all of them in order
-    std::vector<uint64_t> cell_off(n_ctx + 1, 0);
-    if (cell_local) {
-        for (int i = 0; i < n_ctx; ++i) {
-            uint64_t nc = 0, nl = 0;
-            rc = soup_get_dims(ctxs[i], &nc, &nl, nullptr);
-            if (rc != SOUP_OK) { set_thread_error("%s", soup_last_error(ctxs[i])); return rc; }
-            if (nl != n_loci) { set_thread_error("soup_main: the cell shards must hold the same loci"); return SOUP_ERR_INVALID; }
-            cell_off[i + 1] = cell_off[i] + nc;
-        }
-        n_cells = cell_off[n_ctx];
+    std::vector<uint64_t> cell_off(SL + 1, 0);
+    if (p->cell_comms) {
+        for (int g = 0; g < G; ++g)
+            for (int sI = 0; sI < SL; ++sI) {
+                uint64_t nc = 0, nl = 0;
+                rc = soup_get_dims(ctxs[g * SL + sI], &nc, &nl, nullptr);
+                if (rc != SOUP_OK) { set_thread_error("%s", soup_last_error(ctxs[g * SL + sI])); return rc; }
+                if (nl != n_loci) { set_thread_error("soup_main: the cell shards must hold the same loci"); return SOUP_ERR_INVALID; }
+                if (g == 0) cell_off[sI + 1] = cell_off[sI] + nc;
+                else if (cell_off[sI + 1] - cell_off[sI] != nc) { set_thread_error("soup_main: every cell group must hold the same cell ranges"); return SOUP_ERR_INVALID; }
+            }
+        n_cells = cell_off[SL];
     }
     const uint64_t n_cells_global = cell_local ? n_cells : p->n_cells_global;
     const int spt = (int)std::ceil((float)p->restarts / (float)p->threads);   // S:63 (f32 arithmetic)
     const int n_solves = (int)p->threads * spt;
-    const int world = cell_local ? pworld : pworld * n_ctx;   // restart shards (a cell group runs the same solves on every member)
+    const int world = p->cell_comms ? pworld * G : pworld * n_ctx;   // restart shards (a cell group runs the same solves on every member)
 
     uint8_t seed[32];
     memset(seed, p->seed, 32);                   // S:61
@@ -168,7 +177,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
         std::vector<PerCtx> pc(n_ctx);
         auto work = [&](int i) {
             PerCtx& c = pc[i];
-            c.lp.resize((size_t)(cell_local ? cell_off[i + 1] - cell_off[i] : n_cells) * K);
+            c.lp.resize((size_t)(p->cell_comms ? cell_off[i % SL + 1] - cell_off[i % SL] : n_cells) * K);
             c.th.resize((size_t)K * n_loci);
             c.loss.assign(n_solves, NAN);
             c.iters.assign(n_solves, 0);
@@ -184,7 +193,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             sp.n_reinit = run > 0 ? n_bad : 0;
             sp.iteration_cap = p->iteration_cap; sp.max_slots = p->max_slots; sp.lanes = p->lanes;
             sp.record_counts = p->record_counts; sp.keep_trace = p->verbose_trace; sp.time_kernels = p->time_kernels;
-            sp.shard_rank = cell_local ? prank : prank * n_ctx + i; sp.shard_world = world;
+            sp.shard_rank = p->cell_comms ? prank * G + i / SL : prank * n_ctx + i; sp.shard_world = world;
             c.res.best_log_probs = c.lp.data(); c.res.best_theta = c.th.data();
             c.res.solve_loss = c.loss.data(); c.res.solve_iters = c.iters.data();
             c.rc = soup_solve(ctxs[i], &sp, &c.res);
@@ -214,10 +223,14 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             run_ms = std::max(run_ms, pc[i].stats.solve_ms);
             r->nnz_updates += pc[i].res.nnz_updates;
             r->kernel_launches += pc[i].stats.kernel_launches;
-            if (!cell_local || i == 0) r->slot_iterations += pc[i].stats.slot_iterations;
+            if (!p->cell_comms || i % SL == 0) r->slot_iterations += pc[i].stats.slot_iterations;
             if (i == 0) { r->estep_ms += pc[i].stats.estep_ms; r->mstep_ms += pc[i].stats.mstep_ms; r->timed_iterations += pc[i].stats.timed_iterations; }
-            if (cell_local) {                      // every member of the cell group ran the same solves with the same reduced numbers
-                if (i == 0) { for (int s = prank; s < n_solves; s += world) { loss[s] = pc[0].loss[s]; iters[s] = pc[0].iters[s]; mine[s] = 1; } win_ctx = pc[0].res.has_best ? 0 : -1; }
+            if (p->cell_comms) {                   // every member of a cell group ran the same solves with the same reduced numbers:
+                if (i % SL != 0) continue;         // the group's first context speaks for it
+                for (int s = prank * G + i / SL; s < n_solves; s += world) { loss[s] = pc[i].loss[s]; iters[s] = pc[i].iters[s]; mine[s] = 1; }
+                if (better(pc[i].res.best_loss, pc[i].res.best_solve, pc[i].res.has_best != 0,
+                           win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY, win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, win_ctx >= 0))
+                    win_ctx = i;
                 continue;
             }
             for (int s = prank * n_ctx + i; s < n_solves; s += world) { loss[s] = pc[i].loss[s]; iters[s] = pc[i].iters[s]; mine[s] = 1; }
@@ -230,8 +243,9 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             if (p->verbose_trace) {   // per-iteration lines S:264 / S:354, grouped per solve
                 std::vector<soup_iter_record> rec(p->iteration_cap > 0 ? p->iteration_cap : 1000);
                 for (int s = 0; s < n_solves; ++s) {
-                    int owner = cell_local ? (s % world == prank ? 0 : -1) : s % world - prank * n_ctx;
-                    if (owner < 0 || owner >= n_ctx) continue;
+                    int owner = s % world - prank * (p->cell_comms ? G : n_ctx);
+                    if (owner < 0 || owner >= (p->cell_comms ? G : n_ctx)) continue;
+                    if (p->cell_comms) owner *= SL;
                     int32_t n = 0;
                     if (soup_get_trace(ctxs[owner], s, rec.data(), (int32_t)rec.size(), &n) != SOUP_OK) continue;
                     for (int j = 0; j < n; ++j) {
@@ -249,10 +263,10 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
         float w_loss = win_ctx >= 0 ? pc[win_ctx].res.best_loss : -INFINITY;
         int32_t w_solve = win_ctx >= 0 ? pc[win_ctx].res.best_solve : -1, w_has = win_ctx >= 0 ? 1 : 0;
         std::vector<float> run_lp, run_th;
-        if (win_ctx >= 0 && cell_local) {          // the members' rows, in cell order
+        if (win_ctx >= 0 && p->cell_comms) {       // the winning group's rows, in cell order
             run_lp.resize((size_t)n_cells * K);
-            for (int i = 0; i < n_ctx; ++i) memcpy(run_lp.data() + (size_t)cell_off[i] * K, pc[i].lp.data(), pc[i].lp.size() * sizeof(float));
-            run_th.swap(pc[0].th);
+            for (int sI = 0; sI < SL; ++sI) memcpy(run_lp.data() + (size_t)cell_off[sI] * K, pc[win_ctx + sI].lp.data(), pc[win_ctx + sI].lp.size() * sizeof(float));
+            run_th.swap(pc[win_ctx].th);
         }
         else if (win_ctx >= 0) { run_lp.swap(pc[win_ctx].lp); run_th.swap(pc[win_ctx].th); }
         else { run_lp.assign((size_t)n_cells * K, 0.0f); run_th.assign((size_t)K * n_loci, 0.0f); }

@@ -144,7 +144,7 @@ struct ShmCtl {
     alignas(64) unsigned char slots[64][64];   // soup_allgather_fn: <= 64 bytes per rank
     double solve_ms[64];
     unsigned long long nnz_updates[64];
-    unsigned char nccl_id[SOUP_COMM_ID_BYTES];   // cell sharding: rank 0's ncclUniqueId
+    unsigned char nccl_id[4][SOUP_COMM_ID_BYTES];   // cell sharding: rank 0's ncclUniqueId of every cell group
 };
 struct ProcGroup {
     ShmCtl* ctl = nullptr;
@@ -389,7 +389,16 @@ int main(int argc, char** argv) {
         if (pg.ctl) pg.ctl->abort.store(1);
         die(msg, 101);
     };
-    const int n_ctx = multi_proc ? 1 : n_gpu;      // contexts of THIS process
+    // Cell sharding runs the restarts as `cell_groups` groups on the SAME GPUs (each group every GPU, its own communicator, its share of
+    // the restarts): while one group's M-step sums are on the NVLinks, the other's E / M passes have the SMs.  SOUP_CELL_GROUPS overrides.
+    int cell_groups = 1;
+    if (shard_cells) {
+        cell_groups = threads * spt >= 2 ? 2 : 1;
+        if (const char* e = getenv("SOUP_CELL_GROUPS")) cell_groups = std::max(1, std::min(4, atoi(e)));
+        cell_groups = (int)std::min<uint64_t>((uint64_t)cell_groups, std::max<uint64_t>(1, threads * spt));
+    }
+    const int gpus_here = multi_proc ? 1 : n_gpu;  // GPUs of THIS process
+    const int n_ctx = gpus_here * cell_groups;     // its contexts: group-major, context g * gpus_here + d on device d
     uint64_t cell_lo = 0, cell_hi = m->n_cells;    // cells whose rows this process's soup_main returns
     std::vector<soup_ctx*> ctxs(n_ctx, nullptr);
     std::vector<soup_comm*> comms;
@@ -407,9 +416,9 @@ int main(int argc, char** argv) {
                 for (uint64_t c = cut[g]; c <= cut[g + 1]; ++c) shard_ptr[g][c - cut[g]] = m->row_ptr[c] - m->row_ptr[cut[g]];
             }
         }
-        auto bring_up = [&](int g) {               // context g of this process: device g, and (cell sharding) the shard of its rank
-            const int sh = multi_proc ? pg.rank : g;
-            if (soup_ctx_create(g, nullptr, &ctxs[g]) != SOUP_OK) { errs[g] = soup_last_error(nullptr); return; }
+        auto bring_up = [&](int g) {               // context g of this process: device g % gpus_here, and (cell sharding) the shard of that GPU
+            const int dev = g % gpus_here, sh = multi_proc ? pg.rank : dev;
+            if (soup_ctx_create(dev, nullptr, &ctxs[g]) != SOUP_OK) { errs[g] = soup_last_error(nullptr); return; }
             int32_t rc;
             if (shard_cells) {
                 const uint64_t e0 = m->row_ptr[cut[sh]];
@@ -425,14 +434,18 @@ int main(int argc, char** argv) {
         for (auto& t : pool) t.join();
         for (int g = 0; g < n_ctx; ++g)
             if (!errs[g].empty()) fail("souporcell (soupgpu): " + errs[g]);
-        if (shard_cells && multi_proc) {           // one rank per process: ncclCommInitRank over the id rank 0 publishes
-            if (pg.rank == 0 && soup_comm_unique_id(pg.ctl->nccl_id) != SOUP_OK) fail(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr));
+        if (shard_cells && multi_proc) {           // one rank per process: ncclCommInitRank over the ids rank 0 publishes, one per cell group
+            if (pg.rank == 0)
+                for (int g = 0; g < cell_groups; ++g)
+                    if (soup_comm_unique_id(pg.ctl->nccl_id[g]) != SOUP_OK) fail(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr));
             if (!pg.wait()) fail("souporcell (soupgpu): another rank failed");
-            comms.assign(1, nullptr);
-            if (soup_comm_create(ctxs[0], pg.ctl->nccl_id, pg.rank, pg.world, &comms[0]) != SOUP_OK) fail(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr));
+            comms.assign(cell_groups, nullptr);
+            for (int g = 0; g < cell_groups; ++g)
+                if (soup_comm_create(ctxs[g], pg.ctl->nccl_id[g], pg.rank, pg.world, &comms[g]) != SOUP_OK) fail(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr));
         } else if (shard_cells) {
-            comms.assign(n_gpu, nullptr);
-            if (soup_comm_create_all(ctxs.data(), n_gpu, comms.data()) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
+            comms.assign(n_ctx, nullptr);
+            for (int g = 0; g < cell_groups; ++g)
+                if (soup_comm_create_all(ctxs.data() + (size_t)g * n_gpu, n_gpu, comms.data() + (size_t)g * n_gpu) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
         }
         if (shard_cells && multi_proc) {           // where this rank's rows of the result go
             cell_lo = cut[pg.rank]; cell_hi = cut[pg.rank + 1];
@@ -448,6 +461,7 @@ int main(int argc, char** argv) {
     mp.restarts = restarts; mp.threads = (uint32_t)threads; mp.seed = seed; mp.souporcell3 = s3 ? 1 : 0;
     mp.max_slots = (int32_t)parse_num(get("max_slots", "0"), "max_slots", 1024);
     mp.cell_comms = shard_cells ? comms.data() : nullptr;
+    mp.cell_groups = cell_groups;
     const bool quiet = vals.count("quiet_iterations") > 0;
     mp.record_counts = quiet ? 0 : 1; mp.verbose_trace = quiet ? 0 : 1;
     std::vector<float> best_lp((size_t)m->n_cells * k);
@@ -488,7 +502,8 @@ int main(int argc, char** argv) {
         for (int q = 0; q < pg.world; ++q) { solve_ms = std::max(solve_ms, pg.ctl->solve_ms[q]); nnz_updates += pg.ctl->nnz_updates[q]; }
         if (shard_cells && res.has_best) memcpy(best_lp.data(), pg.xfer, (size_t)m->n_cells * k * sizeof(float));
     }
-    fprintf(stderr, "soupgpu\tgpus\t%d\tshard\t%s\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu, shard_cells ? "cells" : "restarts", solve_ms, nnz_updates);
+    fprintf(stderr, "soupgpu\tgpus\t%d\tshard\t%s\tsolve_ms\t%.3f\tnnz_updates\t%llu\n", n_gpu,
+            shard_cells ? (cell_groups > 1 ? "cells (2+ groups)" : "cells") : "restarts", solve_ms, nnz_updates);
     // zip(barcodes, best_log_probabilities): an empty best (nothing beat -inf) prints nothing (S:133)
     if (res.has_best && soup_write_clusters(tsv_out, bc_blob, n_bc, best_lp.data(), m->n_cells, (int32_t)k) != SOUP_OK)
         fail(std::string("thread 'main' panicked: ") + soup_last_error(nullptr));

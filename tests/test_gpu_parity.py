@@ -764,3 +764,31 @@ def test_restart_sharded_two_processes_winner_exchange_over_nccl():
         assert bits([loss])[0] == bits([want.best_loss])[0]
         assert lp == want.best_log_probs.tobytes() and th == want.best_theta.tobytes()
     assert out[0][3] + out[1][3] == want.nnz_updates
+
+
+def test_two_cell_groups_on_one_gpu_agree_with_one_context():
+    """soup_main with two cell GROUPS on the same GPU (each its own one-rank NCCL communicator and context, restarts split solve mod 2,
+    both solver loops running side by side — what overlaps one group's all-reduce with the other's passes on a multi-GPU box): same winner
+    and, at north_star's tolerance, the same result as the plain single-context driver; k = 16 with souporcell3 exercises the re-runs."""
+    v, csr = synth_csr(n_cells=420, n_loci=2600, k=5, mean_loci=130, seed=23)
+    for K, method, s3 in ((4, sp.METHOD_EM, False), (16, sp.METHOD_KHM, True)):
+        with sp.Context(0) as whole:
+            whole.load_csr(*csr)
+            want = sp.main(whole, K, method=method, restarts=5, threads=5, seed=9, souporcell3=s3)
+        ctxs = [sp.Context(0), sp.Context(0)]
+        comms = []
+        try:
+            for c in ctxs:
+                c.load_csr(*csr)
+                comms.append(sp.Comm.create_all([c])[0])
+            got = sp.main(ctxs, K, method=method, restarts=5, threads=5, seed=9, souporcell3=s3, cell_comms=comms, cell_groups=2)
+        finally:
+            for c in comms:
+                c.close()
+            for c in ctxs:
+                c.close()
+        assert got.runs == want.runs and got.best_log_probs.shape == want.best_log_probs.shape
+        np.testing.assert_allclose(got.best_loss, want.best_loss, rtol=1e-5)
+        np.testing.assert_allclose(got.best_theta, want.best_theta, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(got.best_log_probs, want.best_log_probs, rtol=1e-5)
+        assert np.array_equal(got.assignments, want.assignments) and got.nnz_updates == want.nnz_updates

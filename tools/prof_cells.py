@@ -25,26 +25,34 @@ part = api.split_cells(csr, world)[1][rank]
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 out = {"world": world, "config": cfgno, "restarts": restarts, "k": K, "cells": n, "loci": L, "jobs": [], "nccl_allreduce": []}
-for ranges in os.environ.get("PROF_RANGES", "4,1,2,8").split(","):
+for combo in os.environ.get("PROF_COMBOS", "4:1,4:2,1:2,1:1,2:2").split(","):       # locus ranges : cell groups
+    ranges, groups = combo.split(":")
     os.environ["SOUP_CELL_RANGES"] = ranges
-    ctx = sp.Context(local, stream=stream.cuda_stream)
-    ctx.load_csr(*part)
-    comm = sp.Comm.from_torch(ctx, dist)
+    ctxs, comms = [], []
+    for g in range(int(groups)):
+        c = sp.Context(local, stream=stream.cuda_stream) if g == 0 else sp.Context(local)
+        c.load_csr(*part)
+        ctxs.append(c); comms.append(sp.Comm.from_torch(c, dist))
     ms = []
     for rep in range(3):
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        r = sp.main(ctx, K, method=method, restarts=restarts, threads=restarts, seed=4, cell_comms=[comm], n_cells_global=n, time_kernels=(rep == 2))
+        r = sp.main(ctxs, K, method=method, restarts=restarts, threads=restarts, seed=4, cell_comms=comms, cell_groups=int(groups), n_cells_global=n)
         e1.record(stream)
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms.append(float(t[0]))
-    st = ctx.stats()
-    out["jobs"].append({"ranges": int(ranges), "ms": ms, "iterations_enqueued": int(st["estep_launches"]), "allreduce_bytes": int(st["allreduce_bytes"]),
-                        "E_ms_timed": r.estep_ms, "M_plus_comm_enqueue_ms_timed": r.mstep_ms, "best_loss": r.best_loss, "slot_iterations": r.slot_iterations})
-    comm.close(); ctx.close()
+    st = ctxs[0].stats()
+    out["jobs"].append({"ranges": int(ranges), "cell_groups": int(groups), "ms": ms, "iterations_enqueued_group0": int(st["estep_launches"]),
+                        "allreduce_bytes_group0": int(st["allreduce_bytes"]), "best_loss": r.best_loss, "slot_iterations": r.slot_iterations})
+    if rank == 0:
+        print("#", json.dumps(out["jobs"][-1]), file=sys.stderr, flush=True)
+    for c in comms:
+        c.close()
+    for c in ctxs:
+        c.close()
 for mb in (45, 90, 180, 360, 720):
     x = torch.ones(mb * (1 << 20) // 4, dtype=torch.float32, device="cuda")
     for _ in range(2):

@@ -35,6 +35,7 @@ if not os.path.exists(bc):
     t0 = time.time()
     synth.write_files(v, args.dir)
     rec["write_text_s"] = time.time() - t0
+    np.save(os.path.join(args.dir, "donor.npy"), v.donor)          # ground truth of the synthetic cells
     cache = os.path.join(bench.CACHE_DIR, f"config{args.config}_seed{synth.BASE_SEED + args.config}_v2.npz")
     if not os.path.exists(cache):       # what bench.workload() would compute
         row_ptr, locus, a, r, i2l = synth.filter_to_csr(v)
@@ -64,29 +65,29 @@ for mode in args.modes.split(","):
         print(mode, rep, json.dumps(rec["runs"][f"{mode}_{rep}"]), flush=True)
         if p.returncode != 0:
             print(p.stderr[-2000:], flush=True)
-ref_mode = "single" if "single" in tsv else ("restarts" if "restarts" in tsv else None)   # (restart sharding prints the single-GPU run's bytes)
-if ref_mode:
-    ref_rows = tsv[ref_mode]
-    ref_assign = [r.split("\t")[1] for r in ref_rows]
-    for mode in tsv:
-        if mode == ref_mode:
-            continue
-        same = tsv[mode] == ref_rows
-        assign = [r.split("\t")[1] for r in tsv[mode]]
-        agree = sum(a == b for a, b in zip(assign, ref_assign)) / max(len(ref_assign), 1)
-        # cluster labels are arbitrary (another restart may win): agreement after the best one-to-one matching of the labels, and
-        # the adjusted Rand index of the two partitions
-        a, b = np.array(assign, dtype=np.int64), np.array(ref_assign, dtype=np.int64)
-        kk = int(max(a.max(), b.max())) + 1
-        cont = np.zeros((kk, kk), dtype=np.int64)
-        np.add.at(cont, (a, b), 1)
-        from scipy.optimize import linear_sum_assignment
-        ri, ci = linear_sum_assignment(-cont)
-        matched = int(cont[ri, ci].sum()) / max(len(a), 1)
-        comb = lambda x: x * (x - 1) / 2.0
-        sum_ij, sa, sb, tot = comb(cont).sum(), comb(cont.sum(1)).sum(), comb(cont.sum(0)).sum(), comb(len(a))
-        ari = float((sum_ij - sa * sb / tot) / (0.5 * (sa + sb) - sa * sb / tot))
-        rec["runs"][f"{mode}_vs_{ref_mode}"] = {"tsv_identical": same, "assignments_agree_raw_labels": agree, "assignments_agree_matched_labels": matched, "adjusted_rand_index": ari}
+def compare(a, b):
+    """Two labelings of the same cells: agreement after the best one-to-one matching of the (arbitrary) labels, adjusted Rand index."""
+    from scipy.optimize import linear_sum_assignment
+    a, b = np.asarray(a, dtype=np.int64), np.asarray(b, dtype=np.int64)
+    kk = int(max(a.max(), b.max())) + 1
+    cont = np.zeros((kk, kk), dtype=np.int64)
+    np.add.at(cont, (a, b), 1)
+    ri, ci = linear_sum_assignment(-cont)
+    comb = lambda x: x * (x - 1) / 2.0
+    sum_ij, sa, sb, tot = comb(cont).sum(), comb(cont.sum(1)).sum(), comb(cont.sum(0)).sum(), comb(len(a))
+    return {"agree_matched_labels": int(cont[ri, ci].sum()) / max(len(a), 1), "adjusted_rand_index": float((sum_ij - sa * sb / tot) / (0.5 * (sa + sb) - sa * sb / tot))}
+
+
+truth = np.load(os.path.join(args.dir, "donor.npy")) if os.path.exists(os.path.join(args.dir, "donor.npy")) else None
+labels = {mode: [int(r.split("\t")[1]) for r in rows] for mode, rows in tsv.items() if rows}
+for mode, lab in labels.items():
+    if truth is not None and len(lab) == len(truth):
+        rec["runs"][f"{mode}_vs_ground_truth"] = compare(lab, truth)
+        print(mode, "vs the synthetic donors:", rec["runs"][f"{mode}_vs_ground_truth"], flush=True)
+ref_mode = "single" if "single" in labels else ("restarts" if "restarts" in labels else None)   # (restart sharding prints the single-GPU run's bytes)
+for mode, lab in labels.items():
+    if ref_mode and mode != ref_mode:
+        rec["runs"][f"{mode}_vs_{ref_mode}"] = dict(compare(lab, labels[ref_mode]), tsv_identical=tsv[mode] == tsv[ref_mode])
         print(mode, "vs", ref_mode, rec["runs"][f"{mode}_vs_{ref_mode}"], flush=True)
 with open(os.path.join(args.out, f"config{args.config}_gpus{n_gpu}.json"), "w") as fh:
     json.dump(rec, fh, indent=1)
