@@ -190,6 +190,8 @@ typedef struct soup_solve_params {
     int32_t init_strategy;            /* SOUP_INIT_* : how a solve's centers are drawn from its seed stream when neither theta0
                                        * nor init_theta is given (--initialization_strategy, S:491-496) */
     soup_comm* cell_comm;             /* cell sharding over NCCL inside the library (instead of the cell_allreduce callback); NULL = off */
+    int32_t cell_ranges;              /* cell sharding: locus ranges the M pass / all-reduce / theta pass are pipelined over; 0 = auto (4; the
+                                       * SOUP_CELL_RANGES environment variable overrides both).  Must be the same on every rank. */
 } soup_solve_params;
 
 typedef struct soup_solve_result {

@@ -56,7 +56,7 @@ class _SolveParams(C.Structure):
                 ("max_slots", C.c_int32), ("lanes", C.c_int32), ("record_counts", C.c_int32), ("keep_trace", C.c_int32),
                 ("poll_chunk", C.c_int32), ("time_kernels", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
                 ("cell_allreduce", C.c_void_p), ("comm_user", C.c_void_p), ("n_cells_global", C.c_uint64), ("init_strategy", C.c_int32),
-                ("cell_comm", C.c_void_p)]
+                ("cell_comm", C.c_void_p), ("cell_ranges", C.c_int32)]
 
 
 class _SolveResult(C.Structure):

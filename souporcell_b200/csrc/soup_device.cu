@@ -917,13 +917,13 @@ static void enqueue_iteration(IterLaunch& it) {
 // Cell-sharded mode: the M pass's visiting order of the loci.  The statistics travel in ranges of locus ids (the same on every rank),
 // so the order is: the long loci (the first n_long_tail of this rank's LPT order, wherever their ids lie: the first launch finishes
 // them), then range by range, longest first inside a range.
-static int32_t build_cell_order(soup_ctx* ctx) {
-    if (ctx->cell_ranges > 0) return SOUP_OK;
+static int32_t build_cell_order(soup_ctx* ctx, int requested) {
     const uint32_t L = (uint32_t)ctx->L;
-    int P = L < 4096 ? 1 : 4;                                     // (a function of L alone: every rank must cut the same ranges)
+    int P = requested > 0 ? requested : (L < 4096 ? 1 : 4);       // (a function of the caller's choice and L alone: every rank must cut the same ranges)
     if (const char* e = getenv("SOUP_CELL_RANGES")) P = atoi(e);  // tuning / tests; the same on every rank
     P = std::max(1, std::min(P, (int)soup_ctx::MAX_CELL_CHUNKS));
     if ((uint32_t)P > std::max(L, 1u)) P = (int)std::max(L, 1u);
+    if (ctx->cell_ranges == P) return SOUP_OK;                    // (reset by soup_load_csr)
     std::vector<uint32_t> lpt(std::max<uint32_t>(L, 1)), order(std::max<uint32_t>(L, 1));
     CK(cudaSetDevice(ctx->device));
     if (L) CK(cudaMemcpy(lpt.data(), ctx->d_locus_order, (size_t)L * 4, cudaMemcpyDeviceToHost));
@@ -1025,7 +1025,7 @@ extern "C" int32_t soup_solve(soup_ctx* ctx, const soup_solve_params* p, soup_so
     Workspace& w = ctx->ws;
     cudaStream_t st = ctx->stream;
     if (cell_mode) {
-        rc = build_cell_order(ctx);
+        rc = build_cell_order(ctx, p->cell_ranges);
         if (rc != SOUP_OK) return rc;
         const size_t need = 2 * (size_t)ctx->L * w.Cpad + (size_t)slots;
         if (w.stats_floats != need) {

@@ -188,6 +188,7 @@ extern "C" int32_t soup_main(soup_ctx* const* ctxs, int32_t n_ctx, const soup_ma
             sp.init_strategy = p->init_strategy;
             sp.cell_allreduce = p->cell_allreduce; sp.comm_user = p->cell_comm_user; sp.n_cells_global = n_cells_global;
             sp.cell_comm = p->cell_comms ? p->cell_comms[i] : nullptr;
+            sp.cell_ranges = G > 1 ? 1 : 0;      // several groups overlap each other: splitting the M pass into ranges only costs launches then
             sp.base_theta = run > 0 ? best_theta.data() : nullptr;
             sp.reinit_clusters = run > 0 ? bad.data() : nullptr;
             sp.n_reinit = run > 0 ? n_bad : 0;
