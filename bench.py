@@ -418,8 +418,9 @@ def ours(args):
                          "traffic": profiled_traffic(kern), "peak_source": peak_src, "bytes_per_launch": per_launch_bytes,
                          "measured_limiter": "l2_gather+issue",
                          "limiter_note": "achieved/peak is an HBM-EQUIVALENT figure (algorithmic un-batched bytes / time).  Batched restarts share one pass over the "
-                                         "matrix, so the real DRAM traffic (dram_gbs_real) is a few percent of HBM; what binds is the L2->SM row-gather path "
-                                         "(l2_xbar_frac of the 6300 B/clk slice cap) and instruction issue (profiles/, DESIGN.md section 4)",
+                                         "matrix, so the real DRAM traffic (dram_gbs_real, ncu) is a few percent of HBM; what binds is the L2->SM row-gather path "
+                                         "(l2_xbar_tbs; l2_xbar_frac = its share of the 21 TB/s a pure gather reaches on this GPU) and the walks' own "
+                                         "dependent chains (issue_active_pct); figures from the committed ncu --set full capture, profiles/ncu_traffic.json",
                          **profiled_limits(kern, k_ms / max(em[2], 1)),
                          "avg_launch_ms": k_ms / max(em[2], 1), "estep_ms": em[0], "mstep_ms": em[1], "launches_timed": em[2],
                          "timing": f"per-launch CUDA events on the launching stream over {args.steps} extra steps of the same job ({ev_ms / args.steps:.2f} ms/step with events)",
