@@ -149,6 +149,8 @@ typedef struct soup_comm soup_comm;
 int32_t soup_comm_unique_id(uint8_t id[SOUP_COMM_ID_BYTES]);
 int32_t soup_comm_create(soup_ctx* ctx, const uint8_t id[SOUP_COMM_ID_BYTES], int32_t rank, int32_t world, soup_comm** out);
 int32_t soup_comm_create_all(soup_ctx* const* ctxs, int32_t n_ctx, soup_comm** out /*[n_ctx]*/);
+/* a second communicator over the same ranks of this process (ncclCommSplit: no new bootstrap) — one per further cell group */
+int32_t soup_comm_dup_all(soup_comm* const* comms, int32_t n, soup_comm** out /*[n]*/);
 void soup_comm_destroy(soup_comm* comm);
 int32_t soup_comm_rank(const soup_comm* comm, int32_t* rank, int32_t* world);
 int32_t soup_comm_allgather(soup_comm* comm, const void* send, void* recv, uint64_t bytes_per_rank);   /* host buffers */

@@ -33,7 +33,7 @@ EXPORTS = [
     "soup_ctx_create", "soup_ctx_destroy", "soup_load_csr", "soup_get_dims", "soup_get_csc", "soup_get_cell_totals",
     "soup_get_csr_lbc", "soup_cluster_allele_counts", "soup_solve", "soup_get_trace", "soup_get_stats", "soup_estep", "soup_mstep", "soup_device_math",
     "soup_main", "soup_exchange_best", "soup_write_clusters", "soup_clusters_load", "soup_troublet", "soup_troublet_write", "soup_mtx_save", "soup_mtx_load_cache",
-    "soup_mtx_write_text", "soup_comm_unique_id", "soup_comm_create", "soup_comm_create_all", "soup_comm_destroy", "soup_comm_rank", "soup_comm_allgather", "soup_comm_bcast",
+    "soup_mtx_write_text", "soup_comm_unique_id", "soup_comm_create", "soup_comm_create_all", "soup_comm_dup_all", "soup_comm_destroy", "soup_comm_rank", "soup_comm_allgather", "soup_comm_bcast",
 ]
 
 
@@ -169,6 +169,7 @@ def lib():
         L.soup_comm_unique_id.argtypes = [C.c_void_p]
         L.soup_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.soup_comm_create_all.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
+        L.soup_comm_dup_all.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
         L.soup_comm_destroy.argtypes = [C.c_void_p]
         L.soup_comm_destroy.restype = None
         L.soup_comm_rank.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -663,6 +664,14 @@ class Comm:
         out = (C.c_void_p * len(ctxs))()
         _check(lib().soup_comm_create_all(arr, len(ctxs), out))
         return [cls(C.c_void_p(out[i])) for i in range(len(ctxs))]
+
+    @classmethod
+    def dup_all(cls, comms):
+        """A second communicator over the same ranks of this process (ncclCommSplit), e.g. for another cell group on the same GPUs."""
+        arr = (C.c_void_p * len(comms))(*[c._h for c in comms])
+        out = (C.c_void_p * len(comms))()
+        _check(lib().soup_comm_dup_all(arr, len(comms), out))
+        return [cls(C.c_void_p(out[i])) for i in range(len(comms))]
 
     @classmethod
     def from_torch(cls, ctx, dist) -> "Comm":

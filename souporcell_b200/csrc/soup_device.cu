@@ -335,6 +335,23 @@ extern "C" int32_t soup_comm_create_all(soup_ctx* const* ctxs, int32_t n_ctx, so
     return SOUP_OK;
 }
 SOUP_CATCH_RETURN("soup_comm_create_all")
+// A second communicator over the same ranks (ncclCommSplit with one colour: no new bootstrap), for another cell group on the same GPUs
+extern "C" int32_t soup_comm_dup_all(soup_comm* const* in, int32_t n, soup_comm** out) try {
+    if (!in || !out || n < 1) { set_thread_error("soup_comm_dup_all: bad argument"); return SOUP_ERR_INVALID; }
+    std::vector<ncclComm_t> cs(n, nullptr);
+    ncclResult_t r = ncclGroupStart();
+    for (int i = 0; i < n && r == ncclSuccess; ++i) {
+        if (!in[i]) { ncclGroupEnd(); set_thread_error("soup_comm_dup_all: null communicator"); return SOUP_ERR_INVALID; }
+        cudaSetDevice(in[i]->device);
+        r = ncclCommSplit(in[i]->comm, 0, in[i]->rank, &cs[i], nullptr);
+    }
+    ncclResult_t e = ncclGroupEnd();
+    if (r == ncclSuccess) r = e;
+    if (r != ncclSuccess) return nccl_fail("ncclCommSplit", r);
+    for (int i = 0; i < n; ++i) { cudaSetDevice(in[i]->device); out[i] = comm_wrap(cs[i], in[i]->rank, in[i]->world, in[i]->device); }
+    return SOUP_OK;
+}
+SOUP_CATCH_RETURN("soup_comm_dup_all")
 extern "C" void soup_comm_destroy(soup_comm* m) {
     if (!m) return;
     cudaSetDevice(m->device);

@@ -280,8 +280,14 @@ int main(int argc, char** argv) {
     const std::vector<std::string> gpu_tokens = visible_gpu_tokens();
     const bool gpus_given = vals.count("gpus") > 0;
     const int gpus_arg = gpus_given ? (int)parse_num(get("gpus", "1"), "gpus", 1024) : 0;
-    const bool one_gpu_for_sure = gpu_tokens.size() <= 1 || gpus_arg == 1;
-    if (one_gpu_for_sure && gpu_tokens.size() > 1) setenv("CUDA_VISIBLE_DEVICES", gpu_tokens[0].c_str(), 1);
+    // ("for sure" = the GPUs this process will use are known before the parse: one visible device, or --gpus given — then exactly those
+    //  are made visible and the driver starts right away)
+    const bool one_gpu_for_sure = gpu_tokens.size() <= 1 || (gpus_given && !getenv("SOUP_CLI_PROCESSES"));
+    if (one_gpu_for_sure && gpus_given && gpus_arg >= 1 && (size_t)gpus_arg < gpu_tokens.size()) {
+        std::string use;
+        for (int g = 0; g < gpus_arg; ++g) use += (g ? "," : "") + gpu_tokens[g];
+        setenv("CUDA_VISIBLE_DEVICES", use.c_str(), 1);
+    }
     std::future<int> cuda_up;
     auto start_cuda = [&] {
         cuda_up = std::async(std::launch::async, [] {
@@ -329,10 +335,12 @@ int main(int argc, char** argv) {
         n_gpu = gpus_arg;
         if (n_gpu < 1 || n_gpu > visible) die("souporcell (soupgpu): --gpus out of range", 1);
     } else {
-        // default: as many of the visible GPUs as the job can keep busy.  A context takes about a second to come up and a replica of the
-        // matrix; one GPU sustains ~1.3e12 (entry x cluster) updates per second, a solve runs ~17 iterations, souporcell3 up to 3 runs
+        // default: the number of GPUs that minimises the wall time of the PROCESS.  One GPU sustains ~1.3e12 (entry x cluster) updates per
+        // second, a solve runs ~17 iterations, souporcell3 up to 3 runs; every GPU the process touches costs about a second of CUDA driver
+        // bring-up, upload and teardown (measured on 2- and 8-GPU B200 boxes: cuInit 0.7 s, upload + transpose 0.15 s, exit 0.35 s per GPU).
+        // wall(n) = est / n + n * 1 s  is smallest at n = sqrt(est): config 4 (14 s of solves) -> 4 GPUs, config 2 (0.03 s) -> 1.
         const double est_s = (double)m->nnz * (double)(threads * spt) * (double)k * 17.0 * (s3 ? 3.0 : 1.0) / 1.3e12;
-        n_gpu = (int)std::min<double>((double)visible, std::max(1.0, std::ceil(est_s / 0.5)));
+        n_gpu = (int)std::min<double>((double)visible, std::max(1.0, std::floor(std::sqrt(est_s) + 0.5)));
     }
     // restarts: solve s runs on GPU s mod n (every GPU holds the whole matrix, no collective).  cells: GPU g holds the g-th contiguous
     // range of the cells (balanced by entries), every GPU runs every restart and NCCL all-reduces the M-step sums each iteration.
@@ -364,7 +372,10 @@ int main(int argc, char** argv) {
     // ranks form one communicator (soup_comm_create) and every rank's rows of the result are collected there at the end.
     // Rank 0 is this process and prints the TSV.  (SOUP_CLI_ONE_PROCESS keeps everything in one process: one thread per GPU.)
     ProcGroup pg;
-    const bool multi_proc = !one_gpu_for_sure && n_gpu > 1 && n_gpu <= 64 && !getenv("SOUP_CLI_ONE_PROCESS");
+    // Measured (8 x B200, config 4): one process with a thread per GPU comes up in 5.7 s (cuInit over the 8 devices) + 1.3 s (upload);
+    // eight processes that each see one GPU take 9 s for the same step — the driver serialises their bring-up — so the process-per-GPU
+    // model is opt-in (SOUP_CLI_PROCESSES=1) and the default is one process that sees exactly the GPUs it uses.
+    const bool multi_proc = !one_gpu_for_sure && n_gpu > 1 && n_gpu <= 64 && getenv("SOUP_CLI_PROCESSES") != nullptr;
     if (multi_proc) {
         pg.world = n_gpu;
         pg.xfer_bytes = std::max<size_t>((size_t)m->n_cells * k, (size_t)k * m->n_loci) * sizeof(float);
@@ -382,8 +393,10 @@ int main(int argc, char** argv) {
             pg.children.push_back(pid);
         }
         setenv("CUDA_VISIBLE_DEVICES", gpu_tokens[pg.rank].c_str(), 1);
-    } else if (!one_gpu_for_sure && n_gpu == 1 && gpu_tokens.size() > 1) {
-        setenv("CUDA_VISIBLE_DEVICES", gpu_tokens[0].c_str(), 1);
+    } else if (!one_gpu_for_sure && (size_t)n_gpu < gpu_tokens.size()) {
+        std::string use;                           // the driver brings up every VISIBLE device: show it the ones this job uses
+        for (int g = 0; g < n_gpu; ++g) use += (g ? "," : "") + gpu_tokens[g];
+        setenv("CUDA_VISIBLE_DEVICES", use.c_str(), 1);
     }
     auto fail = [&](const std::string& msg) {     // a rank that fails takes the others down with it
         if (pg.ctl) pg.ctl->abort.store(1);
@@ -443,9 +456,12 @@ int main(int argc, char** argv) {
             for (int g = 0; g < cell_groups; ++g)
                 if (soup_comm_create(ctxs[g], pg.ctl->nccl_id[g], pg.rank, pg.world, &comms[g]) != SOUP_OK) fail(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr));
         } else if (shard_cells) {
-            comms.assign(n_ctx, nullptr);
-            for (int g = 0; g < cell_groups; ++g)
-                if (soup_comm_create_all(ctxs.data() + (size_t)g * n_gpu, n_gpu, comms.data() + (size_t)g * n_gpu) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
+            comms.assign(n_ctx, nullptr);           // group 0: ncclCommInitAll; every further group: a split of it (no second bootstrap)
+            if (soup_comm_create_all(ctxs.data(), n_gpu, comms.data()) != SOUP_OK) die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
+            for (int g = 1; g < cell_groups; ++g)
+                if (soup_comm_dup_all(comms.data(), n_gpu, comms.data() + (size_t)g * n_gpu) != SOUP_OK &&
+                    soup_comm_create_all(ctxs.data() + (size_t)g * n_gpu, n_gpu, comms.data() + (size_t)g * n_gpu) != SOUP_OK)
+                    die(std::string("souporcell (soupgpu): ") + soup_last_error(nullptr), 101);
         }
         if (shard_cells && multi_proc) {           // where this rank's rows of the result go
             cell_lo = cut[pg.rank]; cell_hi = cut[pg.rank + 1];

@@ -704,13 +704,15 @@ def test_cell_sharded_two_gpus_real_nccl(k, s3, method, tmp_path):
     a, r, b = synth.write_files(v, str(tmp_path))
     args = ["-a", a, "-r", r, "-b", b, "-k", str(k), "--restarts", "6", "-t", "3", "--seed", "5", "-m", "khm" if method == sp.METHOD_KHM else "em", "-s", "true" if s3 else "false"]
     one = subprocess.run([build.CLI] + args + ["--gpus", "1"], capture_output=True, text=True)
-    two = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "cells"], capture_output=True, text=True)       # one process per GPU
+    two = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "cells"], capture_output=True, text=True)       # one thread per GPU
     assert one.returncode == 0 and two.returncode == 0, two.stderr[-600:]
-    two_t = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "cells"], capture_output=True, text=True, env=dict(os.environ, SOUP_CLI_ONE_PROCESS="1"))
-    assert two_t.returncode == 0 and two_t.stdout == two.stdout, two_t.stderr[-600:]                                  # one thread per GPU: the same bytes
+    two_p = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "cells"], capture_output=True, text=True, env=dict(os.environ, SOUP_CLI_PROCESSES="1"))
+    assert two_p.returncode == 0 and two_p.stdout == two.stdout, two_p.stderr[-600:]                                  # one process per GPU: the same bytes
     assert "shard\tcells" in two.stderr
     # restart sharding over 2 GPUs = one PROCESS per GPU meeting in shared memory: byte-identical TSV, every solve logged exactly once
-    procs = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "restarts"], capture_output=True, text=True)
+    threads2 = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "restarts"], capture_output=True, text=True)
+    assert threads2.returncode == 0 and threads2.stdout == one.stdout, threads2.stderr[-600:]
+    procs = subprocess.run([build.CLI] + args + ["--gpus", "2", "--shard", "restarts"], capture_output=True, text=True, env=dict(os.environ, SOUP_CLI_PROCESSES="1"))
     assert procs.returncode == 0, procs.stderr[-600:]
     assert procs.stdout == one.stdout and "gpus\t2\tshard\trestarts" in procs.stderr
     solves = lambda err: sorted(l for l in err.splitlines() if l.startswith(("thread ", "binomial")))

@@ -18,6 +18,7 @@ ap.add_argument("--gpus", type=int, default=0)
 ap.add_argument("--modes", default="restarts,cells,single")
 ap.add_argument("--restarts", type=int, default=100)
 ap.add_argument("--config", type=int, default=4)
+ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--dir", default="/tmp/soup_config4")
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config4_cli"))
 args = ap.parse_args()
@@ -47,12 +48,14 @@ rec["text_bytes"] = [os.path.getsize(alt), os.path.getsize(ref)]
 print(json.dumps({k: rec[k] for k in rec if k != "runs"}), flush=True)
 base = ["-a", alt, "-r", ref, "-b", bc, "-k", str(cfg["k"]), "--restarts", str(args.restarts), "-t", str(args.restarts), "-m", cfg["method"],
         "-s", "true" if args.config == 4 else "false", "--quiet_iterations"]
-plans = {"restarts": ["--gpus", str(n_gpu), "--shard", "restarts"], "cells": ["--gpus", str(n_gpu), "--shard", "cells"], "single": ["--gpus", "1"]}
+plans = {"restarts": ["--gpus", str(n_gpu), "--shard", "restarts"], "cells": ["--gpus", str(n_gpu), "--shard", "cells"], "single": ["--gpus", "1"],
+         "auto": [],                                      # the CLI picks the number of GPUs (sqrt rule) and the sharding itself
+         "restarts4": ["--gpus", "4", "--shard", "restarts"], "restarts2": ["--gpus", "2", "--shard", "restarts"], "cells4": ["--gpus", "4", "--shard", "cells"]}
 tsv = {}
 for mode in args.modes.split(","):
     if mode not in plans or (mode != "single" and n_gpu < 2):
         continue
-    for rep in range(2 if mode != "single" else 1):       # the second run reads the text from the page cache, like a pipeline stage that follows vartrix
+    for rep in range(args.reps if mode != "single" else 1):       # the second run reads the text from the page cache, like a pipeline stage that follows vartrix
         t0 = time.time()
         p = subprocess.run([build.CLI] + base + plans[mode], capture_output=True, text=True, env=dict(os.environ, SOUP_DEBUG_CLI="1"))
         wall = time.time() - t0
