@@ -282,10 +282,29 @@ int main(int argc, char** argv) {
     const int gpus_arg = gpus_given ? (int)parse_num(get("gpus", "1"), "gpus", 1024) : 0;
     // ("for sure" = the GPUs this process will use are known before the parse: one visible device, or --gpus given — then exactly those
     //  are made visible and the driver starts right away)
-    const bool one_gpu_for_sure = gpu_tokens.size() <= 1 || (gpus_given && !getenv("SOUP_CLI_PROCESSES"));
-    if (one_gpu_for_sure && gpus_given && gpus_arg >= 1 && (size_t)gpus_arg < gpu_tokens.size()) {
+    // Without --gpus the number of GPUs follows from the size of the job (below), and the size of the job from the size of the alt matrix:
+    // a vartrix line is ~12-13 bytes, so the file length gives the entry count well enough for a sqrt rule.
+    const uint64_t spt0 = (restarts + threads - 1) / threads;
+    auto gpus_for = [&](double nnz_est) {
+        // The number of GPUs that minimises the wall time of the PROCESS.  One GPU sustains ~1.3e12 (entry x cluster) updates per second, a
+        // solve runs ~17 iterations, the souporcell3 re-runs add about as much again (they hold only the re-drawn clusters); every GPU the
+        // process touches costs about a second of CUDA driver bring-up, upload and teardown (measured on 2- and 8-GPU B200 boxes).
+        // wall(n) = est / n + n * 1 s  is smallest at n = sqrt(est): config 4 (14 s of solves) -> 4 GPUs, config 2 (0.03 s) -> 1.
+        const double est_s = nnz_est * (double)(threads * spt0) * (double)k * 17.0 * (s3 ? 2.0 : 1.0) / 1.3e12;
+        return (int)std::max(1.0, std::floor(std::sqrt(est_s) + 0.5));
+    };
+    int gpus_guess = 0;
+    if (!gpus_given && gpu_tokens.size() > 1 && !getenv("SOUP_CLI_PROCESSES")) {
+        double bytes = 0;
+        if (FILE* f = fopen(alt_mtx.c_str(), "rb")) { if (fseek(f, 0, SEEK_END) == 0) bytes = (double)ftell(f); fclose(f); }
+        const bool gz = alt_mtx.size() > 3 && alt_mtx.compare(alt_mtx.size() - 3, 3, ".gz") == 0;
+        gpus_guess = std::min<int>((int)gpu_tokens.size(), gpus_for(bytes / 13.0 * (gz ? 5.0 : 1.0)));
+    }
+    const int gpus_early = gpus_given ? gpus_arg : gpus_guess;     // 0 = not known yet
+    const bool one_gpu_for_sure = gpu_tokens.size() <= 1 || (gpus_early >= 1 && !getenv("SOUP_CLI_PROCESSES"));
+    if (one_gpu_for_sure && gpus_early >= 1 && (size_t)gpus_early < gpu_tokens.size()) {
         std::string use;
-        for (int g = 0; g < gpus_arg; ++g) use += (g ? "," : "") + gpu_tokens[g];
+        for (int g = 0; g < gpus_early; ++g) use += (g ? "," : "") + gpu_tokens[g];
         setenv("CUDA_VISIBLE_DEVICES", use.c_str(), 1);
     }
     std::future<int> cuda_up;
@@ -335,12 +354,7 @@ int main(int argc, char** argv) {
         n_gpu = gpus_arg;
         if (n_gpu < 1 || n_gpu > visible) die("souporcell (soupgpu): --gpus out of range", 1);
     } else {
-        // default: the number of GPUs that minimises the wall time of the PROCESS.  One GPU sustains ~1.3e12 (entry x cluster) updates per
-        // second, a solve runs ~17 iterations, souporcell3 up to 3 runs; every GPU the process touches costs about a second of CUDA driver
-        // bring-up, upload and teardown (measured on 2- and 8-GPU B200 boxes: cuInit 0.7 s, upload + transpose 0.15 s, exit 0.35 s per GPU).
-        // wall(n) = est / n + n * 1 s  is smallest at n = sqrt(est): config 4 (14 s of solves) -> 4 GPUs, config 2 (0.03 s) -> 1.
-        const double est_s = (double)m->nnz * (double)(threads * spt) * (double)k * 17.0 * (s3 ? 3.0 : 1.0) / 1.3e12;
-        n_gpu = (int)std::min<double>((double)visible, std::max(1.0, std::floor(std::sqrt(est_s) + 0.5)));
+        n_gpu = std::min(visible, gpus_for((double)m->nnz));   // (`visible` is what the pre-estimate above left visible)
     }
     // restarts: solve s runs on GPU s mod n (every GPU holds the whole matrix, no collective).  cells: GPU g holds the g-th contiguous
     // range of the cells (balanced by entries), every GPU runs every restart and NCCL all-reduces the M-step sums each iteration.
