@@ -356,64 +356,38 @@ __device__ __forceinline__ bool pow2_or_zero(float c) { return (__float_as_uint(
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
-// SOUP_E_AUX_DIRECT: the general classes read their side record {alt, ref, lbc} straight from global memory (one broadcast LDG.128 at a
-// warp-uniform address) instead of from a float4 every lane holds for the whole chunk — four registers (eight in the cross-chunk walk) less.
-#ifndef SOUP_E_AUX_DIRECT
-#define SOUP_E_AUX_DIRECT 0
-#endif
 template <int V>
-__device__ __forceinline__ void e_general(FVec<V>& acc, const FVec<V>& t, bool both, uint32_t src, uint32_t row, const float4& xr, const float4* __restrict__ aux_chunk, float cf,
+__device__ __forceinline__ void e_general(FVec<V>& acc, const FVec<V>& t, bool both, uint32_t src, uint32_t row, const float4& x, float cf,
                                           const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
-#if SOUP_E_AUX_DIRECT
-    const float4 xs = __ldg(aux_chunk + src);
-    (void)xr;
-#endif
     if (both) {
         FVec<V> tb;
         ld_row<V>(tb, row_at(la, __shfl_sync(0xffffffffu, row, src) + pk.plane_rows, row_bytes), hm);
-#if SOUP_E_AUX_DIRECT
-        const float alt = xs.x, ref = xs.y, lbc = xs.z;
-#else
-        const float alt = __shfl_sync(0xffffffffu, xr.x, src), ref = __shfl_sync(0xffffffffu, xr.y, src), lbc = __shfl_sync(0xffffffffu, xr.z, src);
-#endif
+        const float alt = __shfl_sync(0xffffffffu, x.x, src), ref = __shfl_sync(0xffffffffu, x.y, src), lbc = __shfl_sync(0xffffffffu, x.z, src);
         FVec<V> y = vshift<V>(vscale<V>(t, alt), lbc);
         vadd<V>(y, vscale<V>(tb, ref));
         vadd<V>(acc, y);
     } else {
-#if SOUP_E_AUX_DIRECT
-        vadd<V>(acc, vscale<V>(t, xs.x != 0.0f ? xs.x : xs.y));
-        (void)cf;
-#else
         vadd<V>(acc, vscale<V>(t, __shfl_sync(0xffffffffu, cf, src)));
-#endif
     }
 }
 
 // One chunk of 32 entry words, classified (lane j holds entry j; gm / bm are warp votes)
-#if SOUP_E_AUX_DIRECT
-struct EChunk { uint32_t row; float cf; const float4* aux; uint32_t gm, bm; };
-#else
-struct EChunk { uint32_t row; float cf; float4 x; const float4* aux; uint32_t gm, bm; };
-#endif
+struct EChunk { uint32_t row; float cf; float4 x; uint32_t gm, bm; };
 __device__ __forceinline__ EChunk e_chunk(const uint32_t* __restrict__ p, const float4* __restrict__ aux, uint32_t base, uint32_t n, const Packing& pk) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t w = base + lane < n ? __ldg(p + base + lane) : 0u;      // (beyond the end: row 0, a valid unused gather)
     EChunk c;
     c.row = w & pk.imask;
     c.cf = (w & CSR_DOUBLE) ? 2.0f : 1.0f;
-    c.aux = aux + base;
-    float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    c.x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     bool gen = false, both = false;
     if (!word_simple(w)) {
-        x = __ldg(aux + base + lane);
+        c.x = __ldg(aux + base + lane);
         const bool marker = ((w >> pk.sh_a) & pk.cmask) == pk.cmask && ((w >> pk.sh_r) & pk.cmask) == pk.cmask;
-        both = marker || (x.x != 0.0f && x.y != 0.0f);
-        c.cf = x.x != 0.0f ? x.x : x.y;
+        both = marker || (c.x.x != 0.0f && c.x.y != 0.0f);
+        c.cf = c.x.x != 0.0f ? c.x.x : c.x.y;
         gen = both || !pow2_or_zero(c.cf);
     }
-#if !SOUP_E_AUX_DIRECT
-    c.x = x;
-#endif
     c.gm = __ballot_sync(0xffffffffu, gen);
     c.bm = __ballot_sync(0xffffffffu, both);
     return c;
@@ -423,11 +397,7 @@ template <int V>
 __device__ __forceinline__ void e_consume(FVec<V>& acc, const FVec<V>& t, uint32_t e, const EChunk& c,
                                           const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm) {
     if (!((c.gm >> e) & 1u)) vfma<V>(acc, t, __shfl_sync(0xffffffffu, c.cf, e));
-#if SOUP_E_AUX_DIRECT
-    else e_general<V>(acc, t, (c.bm >> e) & 1u, e, c.row, make_float4(0.0f, 0.0f, 0.0f, 0.0f), c.aux, c.cf, pk, la, row_bytes, hm);
-#else
-    else e_general<V>(acc, t, (c.bm >> e) & 1u, e, c.row, c.x, c.aux, c.cf, pk, la, row_bytes, hm);
-#endif
+    else e_general<V>(acc, t, (c.bm >> e) & 1u, e, c.row, c.x, c.cf, pk, la, row_bytes, hm);
 }
 template <int V>
 __device__ __forceinline__ void e_fetch(FVec<V>& t, uint32_t e, const EChunk& c, const Packing& pk, const float* __restrict__ la, uint32_t row_bytes, uint32_t hm, bool pf) {
@@ -903,60 +873,6 @@ __device__ __forceinline__ void m_walk_deep(FVec<V>& s, FVec<V>& d, const uint32
     }
 }
 
-// The wide role with the chunk fully unrolled (SOUP_M_DEEP_WIDE): every lane index and vote-mask bit of the 32 entries of a chunk is a
-// compile-time constant, so the per-entry index arithmetic, the loop counters and their branches of m_walk disappear; the ring is
-// refilled across the chunk boundary from the next, already decoded chunk.  Same classes, same operations in the same order as m_walk.
-#ifndef SOUP_M_DEEP_WIDE
-#define SOUP_M_DEEP_WIDE 0
-#endif
-template <int V, int U, bool GUARD>
-__device__ __forceinline__ void m_deepc_chunk(FVec<V>& s, FVec<V>& d, FVec<V> (&p)[U], uint32_t cnt, uint32_t left_after,
-                                              uint32_t cell, float af, float tf, uint32_t gm, uint32_t cell2,
-                                              const float* __restrict__ w, uint32_t row_bytes, uint32_t hm) {
-    static_assert(32 % U == 0, "the ring must divide a chunk");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        FVec<V>& slot = p[i % U];
-        if (!GUARD || (uint32_t)i < cnt) m_consume<V>(s, d, slot, i, af, tf, gm);
-        const int j = i + U;                    // the stream entry that takes the slot
-        if (j < 32) {
-            if (!GUARD || (uint32_t)j < cnt) ld_row<V>(slot, row_at(w, __shfl_sync(0xffffffffu, cell, j), row_bytes), hm);
-        } else {
-            if (!GUARD || (uint32_t)(j - 32) < left_after) ld_row<V>(slot, row_at(w, __shfl_sync(0xffffffffu, cell2, j - 32), row_bytes), hm);
-        }
-    }
-}
-template <int V, int U>
-__device__ __forceinline__ void m_walk_deepc(FVec<V>& s, FVec<V>& d, const uint32_t* __restrict__ q, const float2* __restrict__ aux, uint32_t n,
-                                             const Packing& pk, const float* __restrict__ w, uint32_t row_bytes, uint32_t hm) {
-    const uint32_t lane = threadIdx.x & 31;
-    auto decode = [&](uint32_t base, uint32_t& cell, float& af, float& tf, uint32_t& gm) {   // chunk at `base` (may lie beyond the end: zeros)
-        const uint32_t wd = base + lane < n ? __ldg(q + base + lane) : 0u;
-        const uint32_t ai = (wd >> pk.sh_a) & pk.cmask, ti = (wd >> pk.sh_r) & pk.cmask;
-        af = small_u2f(ai); tf = small_u2f(ti);
-        if (ai == pk.cmask && ti == pk.cmask && base + lane < n) {                 // counts outside the packed fields (rare)
-            const float2 x = __ldg(aux + base + lane);
-            af = x.x; tf = x.y;
-        }
-        cell = wd & pk.imask;
-        gm = __ballot_sync(0xffffffffu, !(pow2_or_zero(af) && pow2_or_zero(tf)));
-    };
-    uint32_t cell, cell2, gm, gm2;
-    float af, tf, af2, tf2;
-    decode(0, cell, af, tf, gm);
-    FVec<V> p[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) ld_row<V>(p[u], row_at(w, __shfl_sync(0xffffffffu, cell, u), row_bytes), hm);   // (beyond the end: cell 0, a valid unused gather)
-#pragma unroll 1
-    for (uint32_t base = 0; base < n; base += 32) {
-        decode(base + 32, cell2, af2, tf2, gm2);
-        const uint32_t left = n - base;
-        if (left >= 64) m_deepc_chunk<V, U, false>(s, d, p, 32u, 32u, cell, af, tf, gm, cell2, w, row_bytes, hm);
-        else m_deepc_chunk<V, U, true>(s, d, p, min(left, 32u), left > 32u ? left - 32u : 0u, cell, af, tf, gm, cell2, w, row_bytes, hm);
-        cell = cell2; af = af2; tf = tf2; gm = gm2;
-    }
-}
-
 struct MArgs {
     const uint32_t* csc_idx; const float2* csc_aux; const uint64_t* col_ptr; const uint32_t* locus_order;
     const float* W; float* TH; float* LA; float* LB; const uint8_t* col_write;
@@ -1007,7 +923,6 @@ __device__ __forceinline__ void mstep_body(const MArgs& a, uint32_t li, uint32_t
     constexpr int U = V <= 2 ? SOUP_M_U2 : (V == 4 ? SOUP_M_U : (V == 8 ? SOUP_M_U8 : SOUP_M_U16));
     if constexpr (DEEP) m_walk_deep<V, SOUP_M_ULONG>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
     else if constexpr (V <= 2 && V <= SOUP_DEEP_VMAX) m_walk_deep<V, 32 / V>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
-    else if constexpr (SOUP_M_DEEP_WIDE != 0 && V >= 4 && 32 % U == 0) m_walk_deepc<V, U>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
     else m_walk<V, U>(s, d, a.csc_idx + j0, a.csc_aux + j0, n, a.pk, a.W + lc.col, a.Cpad * 4u, lc.hm);
     if (!lc.live) return;
 #pragma unroll
