@@ -530,3 +530,23 @@ def test_sass_exactness_guards():
         if "estep_kernel" not in k and "mstep_kernel" not in k:
             assert v["FFMA2"] == 0, (k, v)
     assert all(v["FADD2"] > 0 for v in mstep.values())
+
+
+def test_mtx_text_writer_matches_the_python_writer(tmp_path):
+    """soup_mtx_write_text (parallel blocks, written in order) produces the bytes synth.write_files' plain-Python path writes — header,
+    comment, dimensions, one `locus cell count` line per entry — over several waves of blocks, and the loader reads them back."""
+    from souporcell_b200 import api
+    rng = np.random.default_rng(8)
+    n_loci, n_cells, nnz = 70000, 900, 700000                    # > 2 blocks of 2^18 entries
+    locus = np.sort(rng.integers(0, n_loci, nnz)).astype(np.int64)
+    cell = rng.integers(0, n_cells, nnz).astype(np.int64)
+    cnt = rng.integers(0, 5000, nnz).astype(np.uint32)
+    cnt[:10] = [0, 1, 9, 10, 99, 100, 4294967295, 12345678, 7, 70]
+    path = str(tmp_path / "w.mtx")
+    api.write_mtx_text(path, n_loci, n_cells, locus, cell, cnt, comment="written by souporcell_b200.synth")
+    want = "%%MatrixMarket matrix coordinate real general\n% written by souporcell_b200.synth\n" + f"{n_loci} {n_cells} {nnz}\n" + \
+           "".join(f"{l + 1} {c + 1} {x}\n" for l, c, x in zip(locus.tolist(), cell.tolist(), cnt.tolist()))
+    assert open(path).read() == want
+    empty = str(tmp_path / "e.mtx")
+    api.write_mtx_text(empty, 3, 2, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint32))
+    assert open(empty).read().splitlines()[-1] == "3 2 0"
