@@ -414,9 +414,10 @@ def ours(args):
             "e2e": {"value": e_upd / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            # bound: the roofline the contract's figures are taken against (algorithmic bytes over the measured HBM bandwidth).
+            # limited_by: what MEASURABLY limits the kernel (ncu: L2 -> SM row gathers + the walks' dependent chains; DRAM is at a few percent).
+            "roofline": {"bound": "hbm", "limited_by": "l2_gather+issue", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(kern), "peak_source": peak_src, "bytes_per_launch": per_launch_bytes,
-                         "measured_limiter": "l2_gather+issue",
                          "limiter_note": "achieved/peak is an HBM-EQUIVALENT figure (algorithmic un-batched bytes / time).  Batched restarts share one pass over the "
                                          "matrix, so the real DRAM traffic (dram_gbs_real, ncu) is a few percent of HBM; what binds is the L2->SM row-gather path "
                                          "(l2_xbar_tbs; l2_xbar_frac = its share of the 21 TB/s a pure gather reaches on this GPU) and the walks' own "
