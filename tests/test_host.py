@@ -550,3 +550,22 @@ def test_mtx_text_writer_matches_the_python_writer(tmp_path):
     empty = str(tmp_path / "e.mtx")
     api.write_mtx_text(empty, 3, 2, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint32))
     assert open(empty).read().splitlines()[-1] == "3 2 0"
+
+
+def test_bench_workload_cache_round_trips(tmp_path, monkeypatch):
+    """bench.py keeps the generated matrices in a scratch cache (config 4 takes numpy half a minute): the cached arrays are the
+    generator's, a second call reads the file, and a half-written file can never be picked up (written under another name, then renamed)."""
+    import importlib
+    import bench
+    monkeypatch.setattr(bench, "CACHE_DIR", str(tmp_path / "cache"))
+    cfg, csr = bench.workload(0)
+    v = synth.generate_config(0)
+    row_ptr, locus, alt, ref, i2l = synth.filter_to_csr(v)
+    assert cfg == synth.CONFIGS[0] and csr[0] == v.n_cells and csr[1] == int(i2l.shape[0])
+    for got, want in zip(csr[2:], (row_ptr, locus, alt, ref)):
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+    files = os.listdir(tmp_path / "cache")
+    assert len(files) == 1 and files[0].endswith(".npz") and ".tmp" not in files[0]
+    monkeypatch.setattr(synth, "generate_config", lambda *a, **k: (_ for _ in ()).throw(AssertionError("regenerated")))
+    cfg2, csr2 = bench.workload(0)                                 # served from the file
+    assert np.array_equal(csr2[3], csr[3])
