@@ -569,3 +569,20 @@ def test_bench_workload_cache_round_trips(tmp_path, monkeypatch):
     monkeypatch.setattr(synth, "generate_config", lambda *a, **k: (_ for _ in ()).throw(AssertionError("regenerated")))
     cfg2, csr2 = bench.workload(0)                                 # served from the file
     assert np.array_equal(csr2[3], csr[3])
+
+
+def test_cli_without_a_usable_gpu_fails_loudly_in_every_process_model(tmp_path):
+    """No CPU fallback: with no usable CUDA device the drop-in exits 101 with a message and an empty stdout — as one process, with
+    `--gpus 2` (two devices named but not there), and as one process per GPU, where a rank that fails must take the others down with it
+    instead of leaving them waiting in the shared-memory barrier."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    v = synth.generate(n_cells=60, n_loci=400, k=2, mean_loci=40, seed=3)
+    a, r, b = synth.write_files(v, str(tmp_path))
+    args = [build.CLI, "-a", a, "-r", r, "-b", b, "-k", "2", "--restarts", "4", "-t", "2"]
+    for extra, env in (([], {}), (["--gpus", "2"], {"CUDA_VISIBLE_DEVICES": "0,1"}), (["--gpus", "2"], {"CUDA_VISIBLE_DEVICES": "0,1", "SOUP_CLI_PROCESSES": "1"}),
+                       (["--gpus", "2", "--shard", "cells"], {"CUDA_VISIBLE_DEVICES": "0,1", "SOUP_CLI_PROCESSES": "1"})):
+        p = subprocess.run(args + extra, capture_output=True, text=True, env=dict(os.environ, **env), timeout=60)
+        assert p.returncode == 101 and p.stdout == "", (extra, env, p.returncode)
+        assert "no CUDA device" in p.stderr and "no CPU fallback" in p.stderr
